@@ -1,0 +1,459 @@
+"""CPU oracle for the ManiPose lifting hot path (TEST INFRASTRUCTURE — NOT PRODUCT CODE).
+
+A plain-PyTorch fp32 *functional* restatement of the reference's algorithm for the hot path
+SURVEY.md §8(a) lists (MixSTE backbone -> K hypothesis heads -> manifold decoder -> WTA loss /
+hypothesis metrics).  Every function cites the reference ``file:line`` it follows (paths are
+relative to ``/root/reference/``).  It works from a ``state_dict`` with the reference's
+parameter names, so it can check the product on identical weights.
+
+Who may import this: ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs — only as the checker / the timed CPU baseline,
+never as a product code path.  ``manipose_b200`` must never import it.
+
+Parity pin: the reference ships NO tests, golden vectors or known-answer fixtures for this
+path, so this oracle is pinned against *outputs of the reference itself run in
+the build container* (``oracle/ref_loader.py`` imports the unmodified reference with the three
+shims of SURVEY.md §8c): ``tests/test_oracle_vs_reference.py`` compares every function here with
+the reference on seeded inputs whenever ``/root/reference`` exists, and
+``scripts/make_goldens.py`` froze reference outputs into ``tests/golden/*.pt`` which
+``tests/test_oracle_golden.py`` checks everywhere (including the GPU box).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------
+# Skeleton constants (hpe/mh_so3_hpe/data/h36m_lifting.py:40-57,649-660 after the 17-joint
+# reduction == hpe/mh_so3_hpe/data/dataset_3dhp.py:132-138); SURVEY.md §A.1.
+# --------------------------------------------------------------------------------------
+H36M17_PARENTS = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15]
+H36M17_T_POSE_OPERATORS = [
+    (0, 0, 0),
+    (1, 0, 0), (0, -1, 0), (0, -1, 0),
+    (-1, 0, 0), (0, -1, 0), (0, -1, 0),
+    (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 1, 0),
+    (-1, 0, 0), (-1, 0, 0), (-1, 0, 0),
+    (1, 0, 0), (1, 0, 0), (1, 0, 0),
+]
+H36M17_JOINTS_LEFT = [4, 5, 6, 11, 12, 13]
+H36M17_JOINTS_RIGHT = [1, 2, 3, 14, 15, 16]
+# hpe/mh_so3_hpe/metrics/losses.py:6-8
+STANDARD_H36M_WEIGHTS = torch.tensor(
+    [1, 1, 2.5, 2.5, 1, 2.5, 2.5, 1, 1, 1, 1.5, 1.5, 4, 4, 1.5, 4, 4], dtype=torch.float32
+)
+
+
+def has_children(parents: List[int]) -> List[bool]:
+    """hpe/mh_so3_hpe/data/skeleton.py:85-89."""
+    out = [False] * len(parents)
+    for p in parents:
+        if p != -1:
+            out[p] = True
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# D1-D3: 6-D -> SO(3)   (hpe/mh_so3_hpe/architectures/utils/rotation_tools.py)
+# --------------------------------------------------------------------------------------
+def normalize_vector(v: torch.Tensor) -> torch.Tensor:
+    """rotation_tools.py:6-17 — v / max(sqrt(sum v^2), 1e-8) (epsilon on v.device)."""
+    mag = torch.sqrt(v.pow(2).sum(1))
+    mag = torch.max(mag, torch.tensor([1e-8], dtype=v.dtype, device=v.device))
+    return v / mag[:, None]
+
+
+def cross_product(u: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """rotation_tools.py:21-32."""
+    i = u[:, 1] * v[:, 2] - u[:, 2] * v[:, 1]
+    j = u[:, 2] * v[:, 0] - u[:, 0] * v[:, 2]
+    k = u[:, 0] * v[:, 1] - u[:, 1] * v[:, 0]
+    return torch.stack((i, j, k), dim=1)
+
+
+def rotation_matrix_from_ortho6d(r6: torch.Tensor) -> torch.Tensor:
+    """rotation_tools.py:35-57 — x = n(a), z = n(x × b), y = z × x; COLUMNS are [x y z]."""
+    x = normalize_vector(r6[:, 0:3])
+    z = normalize_vector(cross_product(x, r6[:, 3:6]))
+    y = cross_product(z, x)
+    return torch.stack((x, y, z), dim=2)
+
+
+def rotation_matrix_from_ortho4d(r4: torch.Tensor) -> torch.Tensor:
+    """rotation_tools.py:60-116 — R_theta · R_phi from two normalised 2-vectors."""
+    n = r4.shape[0]
+    cs_t = normalize_vector(r4[:, 0:2])
+    cs_p = normalize_vector(r4[:, 2:4])
+    zeros = torch.zeros((n, 1), dtype=r4.dtype)
+    theta_y = torch.cat([cs_t, zeros], dim=1)
+    theta_z = torch.tensor([0.0, 0.0, 1.0], dtype=r4.dtype).expand(n, -1)
+    theta_x = cross_product(theta_y, theta_z)
+    phi_y = torch.cat([zeros, cs_p], dim=1)
+    phi_x = torch.tensor([1.0, 0.0, 0.0], dtype=r4.dtype).expand(n, -1)
+    phi_z = cross_product(phi_x, phi_y)
+    r_theta = torch.stack((theta_x, theta_y, theta_z), dim=2)
+    r_phi = torch.stack((phi_x, phi_y, phi_z), dim=2)
+    return r_theta.bmm(r_phi)
+
+
+# --------------------------------------------------------------------------------------
+# D4-D7: decoder   (hpe/mh_so3_hpe/architectures/pose_decoder.py, utils/forward_kinematics.py)
+# --------------------------------------------------------------------------------------
+def build_t_pose(bones_length: torch.Tensor, parents=H36M17_PARENTS,
+                 operators=H36M17_T_POSE_OPERATORS) -> torch.Tensor:
+    """pose_decoder.py:98-120 — t[b+1] = t[parent[b+1]] + op[b+1] * len[b]; [N,16,1] -> [N,17,3]."""
+    n, n_parts, _ = bones_length.shape
+    assert n_parts == len(parents) - 1
+    t_pose = torch.zeros((n, len(parents), 3), dtype=torch.float32)
+    for b in range(n_parts):
+        op = torch.tensor(operators[b + 1], dtype=torch.float32)
+        t_pose[:, b + 1, :] = t_pose[:, parents[b + 1], :] + op * bones_length[:, b]
+    return t_pose
+
+
+def forward_kinematics(t_pose: torch.Tensor, rotations: torch.Tensor, root_positions: torch.Tensor,
+                       parents=H36M17_PARENTS) -> torch.Tensor:
+    """forward_kinematics.py:6-48 — Rw[j] = Rw[par] R[j]; p[j] = Rw[j](t[j]-t[par]) + p[par]."""
+    kids = has_children(parents)
+    pos: List[torch.Tensor] = []
+    rot: List[Optional[torch.Tensor]] = []
+    for j in range(rotations.shape[1]):
+        if parents[j] == -1:
+            pos.append(root_positions)
+            rot.append(rotations[:, 0])
+        else:
+            p = parents[j]
+            offset = (t_pose[:, j, :] - t_pose[:, p, :]).view(-1, 3, 1)
+            rw = rot[p].matmul(rotations[:, j])
+            pos.append(rw.matmul(offset).view(-1, 3) + pos[p])
+            rot.append(rw if kids[j] else None)
+    return torch.stack(pos, dim=2).permute(0, 2, 1)
+
+
+def pose_decoder(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor,
+                 root_positions: torch.Tensor, rot_rep_dim: int = 6,
+                 parents=H36M17_PARENTS, operators=H36M17_T_POSE_OPERATORS) -> torch.Tensor:
+    """pose_decoder.py:32-96 — rotations_repr [N,J,D], bones [B,16,1] (row n uses clip n // (N/B))."""
+    assert rot_rep_dim in (4, 6), f"Unsupported rotations representation dimension: {rot_rep_dim}"
+    assert rotations_repr.shape[-1] == rot_rep_dim
+    n, j, _ = rotations_repr.shape
+    b = bones_lengths_repr.shape[0]
+    assert n % b == 0
+    reps = n // b
+    bones = torch.stack([bones_lengths_repr] * reps, dim=1).reshape(n, -1, 1)  # :85-96
+    flat = rotations_repr.reshape(-1, rot_rep_dim)
+    mats = rotation_matrix_from_ortho6d(flat) if rot_rep_dim == 6 else rotation_matrix_from_ortho4d(flat)
+    mats = mats.reshape(n, j, 3, 3)
+    t_pose = build_t_pose(bones, parents, operators)
+    return forward_kinematics(t_pose, mats, root_positions, parents)
+
+
+# --------------------------------------------------------------------------------------
+# B1-B5: MixSTE backbone   (hpe/mh_so3_hpe/architectures/mix_ste.py)
+# --------------------------------------------------------------------------------------
+def _ln(x, sd, prefix, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+
+
+def attention(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, num_heads: int) -> torch.Tensor:
+    """mix_ste.py:255-282 (comb=False) — qkv rows ordered [q|k|v] x heads; scale = head_dim**-0.5."""
+    bsz, n, c = x.shape
+    hd = c // num_heads
+    qkv = F.linear(x, sd[prefix + ".qkv.weight"], sd.get(prefix + ".qkv.bias"))
+    qkv = qkv.reshape(bsz, n, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * (hd ** -0.5)
+    attn = attn.softmax(dim=-1)
+    out = (attn @ v).transpose(1, 2).reshape(bsz, n, c)
+    return F.linear(out, sd[prefix + ".proj.weight"], sd[prefix + ".proj.bias"])
+
+
+def block(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, num_heads: int) -> torch.Tensor:
+    """mix_ste.py:352-358 in eval mode (DropPath = identity, residual_scale = 1), LN eps 1e-6 (:49)."""
+    x = x + attention(_ln(x, sd, prefix + ".norm1", 1e-6), sd, prefix + ".attn", num_heads)
+    h = _ln(x, sd, prefix + ".norm2", 1e-6)
+    h = F.linear(h, sd[prefix + ".mlp.fc1.weight"], sd[prefix + ".mlp.fc1.bias"])
+    h = F.gelu(h)  # exact erf GELU (nn.GELU default, mix_ste.py:200)
+    h = F.linear(h, sd[prefix + ".mlp.fc2.weight"], sd[prefix + ".mlp.fc2.bias"])
+    return x + h
+
+
+def mixste_trunk(x_emb: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, depth: int,
+                 num_heads: int) -> torch.Tensor:
+    """mix_ste.py:128-173 after the patch embedding: x_emb is [B, L, J, C] (embedding done)."""
+    b, l, j, c = x_emb.shape
+    x = x_emb.reshape(b * l, j, c) + sd[prefix + "Spatial_pos_embed"]                # :137
+    x = block(x, sd, prefix + "STEblocks.0", num_heads)                               # :140-141
+    x = _ln(x, sd, prefix + "Spatial_norm", 1e-6)                                     # :143
+    x = x.reshape(b, l, j, c).permute(0, 2, 1, 3).reshape(b * j, l, c)                # :144
+    x = x + sd[prefix + "Temporal_pos_embed"]                                         # :149
+    x = block(x, sd, prefix + "TTEblocks.0", num_heads)                               # :151-152
+    x = _ln(x, sd, prefix + "Temporal_norm", 1e-6)                                    # :154
+    x = x.reshape(b, j, l, c).permute(0, 2, 1, 3)                                     # rmcl:249 / :181
+    for i in range(1, depth):                                                         # :160-171
+        x = x.reshape(b * l, j, c)
+        x = block(x, sd, prefix + f"STEblocks.{i}", num_heads)
+        x = _ln(x, sd, prefix + "Spatial_norm", 1e-6)
+        x = x.reshape(b, l, j, c).permute(0, 2, 1, 3).reshape(b * j, l, c)
+        x = block(x, sd, prefix + f"TTEblocks.{i}", num_heads)
+        x = _ln(x, sd, prefix + "Temporal_norm", 1e-6)
+        x = x.reshape(b, j, l, c).permute(0, 2, 1, 3)
+    return x.contiguous()                                                             # [B, L, J, C]
+
+
+def _depth_of(sd: Dict[str, torch.Tensor], prefix: str) -> int:
+    d = 0
+    while f"{prefix}STEblocks.{d}.norm1.weight" in sd:
+        d += 1
+    return d
+
+
+def rotations_module(x: torch.Tensor, sd: Dict[str, torch.Tensor], num_heads: int = 8,
+                     prefix: str = "rotations_module.") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """RMCLRotMixSTE.forward, rmcl_manifold_mix_ste.py:239-264 (+ MCLHead :291-298).
+
+    Returns (rot6d [B,K,L,J,D], scores [B,K,L,1], logits [B,K,L,1])."""
+    depth = _depth_of(sd, prefix)
+    emb = F.linear(x, sd[prefix + "Spatial_patch_to_embedding.weight"],
+                   sd[prefix + "Spatial_patch_to_embedding.bias"])                   # mix_ste.py:134
+    feat = mixste_trunk(emb, sd, prefix, depth, num_heads)
+    preds, logits = [], []
+    k = 0
+    while f"{prefix}head.{k}.norm.weight" in sd:
+        hp = f"{prefix}head.{k}"
+        h = _ln(feat, sd, hp + ".norm", 1e-5)                                         # rmcl:277,292
+        pe = F.linear(h, sd[hp + ".prediction_head.weight"], sd[hp + ".prediction_head.bias"])
+        preds.append(pe[..., :-1])                                                    # rmcl:294
+        logits.append(F.linear(pe[..., -1], sd[hp + ".score_head.weight"], sd[hp + ".score_head.bias"]))
+        k += 1
+    hyp = torch.stack(preds, dim=1)
+    lg = torch.stack(logits, dim=1)
+    return hyp, lg.softmax(dim=1), lg
+
+
+def single_rotations_module(x: torch.Tensor, sd: Dict[str, torch.Tensor], num_heads: int = 8,
+                            prefix: str = "rotations_module.") -> torch.Tensor:
+    """MixSTE.forward, mix_ste.py:175-191 with the plain head (LN eps 1e-5 + Linear) -> [B,L,J,D]."""
+    depth = _depth_of(sd, prefix)
+    emb = F.linear(x, sd[prefix + "Spatial_patch_to_embedding.weight"],
+                   sd[prefix + "Spatial_patch_to_embedding.bias"])
+    feat = mixste_trunk(emb, sd, prefix, depth, num_heads)
+    h = _ln(feat, sd, prefix + "head.0", 1e-5)
+    return F.linear(h, sd[prefix + "head.1.weight"], sd[prefix + "head.1.bias"])
+
+
+def segments_module(x: torch.Tensor, sd: Dict[str, torch.Tensor], num_heads: int = 8,
+                    prefix: str = "segments_module.") -> torch.Tensor:
+    """BonesMixSTE.forward, manifold_mix_ste.py:139-154 -> bone lengths [B, S, 1] (signed)."""
+    b, l = x.shape[:2]
+    depth = _depth_of(sd, prefix)
+    w = sd[prefix + "joints_to_segments_proj.weight"]
+    c = sd[prefix + "Spatial_pos_embed"].shape[-1]
+    s = w.shape[0] // c
+    emb = F.linear(x.reshape(b * l, -1), w, sd[prefix + "joints_to_segments_proj.bias"]).reshape(b, l, s, c)
+    feat = mixste_trunk(emb, sd, prefix, depth, num_heads)
+    h = _ln(feat, sd, prefix + "head.0", 1e-5)                                        # mix_ste.py:123-126
+    out = F.linear(h, sd[prefix + "head.1.weight"], sd[prefix + "head.1.bias"])       # [B, L, S, 1]
+    return out.mean(dim=1)                                                            # :153
+
+
+def rmcl_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], num_heads_rot: int = 8,
+                 num_heads_seg: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """RMCLManifoldMixSTE.forward, rmcl_manifold_mix_ste.py:83-106 -> (poses [B,K,L,J,3], scores [B,K,L,1])."""
+    b, l = x.shape[:2]
+    rot, scores, _ = rotations_module(x, sd, num_heads_rot)
+    k, j, d = rot.shape[1], rot.shape[3], rot.shape[4]
+    bones = segments_module(x, sd, num_heads_seg)
+    root = torch.zeros(b * l * k, 3)
+    poses = pose_decoder(rot.reshape(b * k * l, j, d), bones, root, rot_rep_dim=d)
+    return poses.reshape(b, k, l, j, 3), scores
+
+
+def manifold_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], num_heads_rot: int = 8,
+                     num_heads_seg: int = 8) -> torch.Tensor:
+    """ManifoldMixSTE.forward (single hypothesis), manifold_mix_ste.py:74-88 -> [B,L,J,3]."""
+    b, l = x.shape[:2]
+    rot = single_rotations_module(x, sd, num_heads_rot)
+    j, d = rot.shape[2], rot.shape[3]
+    bones = segments_module(x, sd, num_heads_seg)
+    poses = pose_decoder(rot.reshape(b * l, j, d), bones, torch.zeros(b * l, 3), rot_rep_dim=d)
+    return poses.reshape(b, l, j, 3)
+
+
+# --------------------------------------------------------------------------------------
+# L1-L6: losses   (hpe/mh_so3_hpe/metrics/losses.py, regularizations.py)
+# --------------------------------------------------------------------------------------
+def l2_loss_per_hyp(hyp: torch.Tensor, y: torch.Tensor, weights: Optional[torch.Tensor] = None,
+                    squared: bool = False) -> torch.Tensor:
+    """losses.py:104-123 (+ :14-72) — [B,K,L,J,3],[B,L,J,3] -> [B,K,L]."""
+    tgt = y[:, None].expand_as(hyp)
+    if squared:
+        if weights is None:  # F.mse_loss over everything: a scalar (reference quirk, :57-58)
+            return F.mse_loss(hyp, tgt)
+        return (weights[None, None, :, None] * (hyp - tgt) ** 2).mean(dim=4).mean(dim=3)
+    if weights is None:
+        weights = torch.ones(y.shape[-2])
+    return (weights[None, None, :] * torch.norm(hyp - tgt, p=2, dim=4)).mean(dim=3)
+
+
+def wta_l2_loss_and_activate_head(hyp, y, weights=None, squared=False):
+    """losses.py:126-138 — torch.min over the hypothesis dim -> (values [B,L], int64 indices [B,L])."""
+    return torch.min(l2_loss_per_hyp(hyp, y, weights, squared), dim=1)
+
+
+def wta_with_scoring_loss(hyp, scores, y, beta, weights=None, squared=False):
+    """losses.py:141-170 — WTA mean + beta * BCE(scores, one_hot(winner)); bare scalar if beta == 0."""
+    wta, idx = wta_l2_loss_and_activate_head(hyp, y, weights, squared)
+    if beta == 0:
+        return wta.mean()
+    b, k, l = hyp.shape[:3]
+    gt = F.one_hot(idx, k).permute(0, 2, 1).to(torch.float32)                         # :158-163
+    bce = F.binary_cross_entropy(scores.view(b, k, l), gt)
+    return wta.mean() + beta * bce, beta * bce
+
+
+def mean_velocity_error(pred: torch.Tensor, target: torch.Tensor, axis: int = 1, squared: bool = False):
+    """losses.py:75-101."""
+    if pred.dim() > target.dim():
+        target = target.unsqueeze(1).expand_as(pred)
+    dv = torch.diff(pred, dim=axis) - torch.diff(target, dim=axis)
+    if squared:
+        return torch.mean(dv ** 2)
+    return torch.mean(torch.norm(dv, dim=target.dim() - 1))
+
+
+def smoothness_regularization(pred: torch.Tensor, weights: Optional[torch.Tensor] = None, axis: int = 1):
+    """regularizations.py:160-174."""
+    v = torch.diff(pred, dim=axis)
+    if weights is None:
+        # reference quirk kept: ones_like(v[0, 0, :, 0]) has J entries only for 4-D input (:165-166)
+        weights = torch.ones_like(v[0, 0, :, 0])
+    assert weights.shape[0] == v.shape[-2]
+    return torch.mean(weights[None, None, :, None] * v ** 2)
+
+
+def training_loss(poses, scores, y, beta=0.1, vel_w=2.0, smooth_w=0.5, weights=STANDARD_H36M_WEIGHTS,
+                  squared=False):
+    """make_loss + compute_and_acc_loss for the RMCL model, hpe/main_h36m_lifting.py:101-209 with the
+    hpe/conf/config.yaml:33-37 defaults.  Returns (total, dict of terms)."""
+    wl = wta_l2_loss_and_activate_head(poses, y, weights, squared)[0].mean()
+    terms = {"wloss": wl}
+    total = wl
+    if beta != 0:
+        terms["score_reg"] = wta_with_scoring_loss(poses, scores, y, beta, weights, squared)[1]
+        total = total + terms["score_reg"]
+    if vel_w > 0:
+        terms["vloss"] = vel_w * mean_velocity_error(poses, y, axis=2, squared=squared)
+        total = total + terms["vloss"]
+    if smooth_w > 0:
+        terms["sreg"] = smooth_w * smoothness_regularization(poses, weights, axis=2)
+        total = total + terms["sreg"]
+    return total, terms
+
+
+# --------------------------------------------------------------------------------------
+# M1-M3: hypothesis aggregation / metrics
+# --------------------------------------------------------------------------------------
+def poses_from_hyp_idx(hyp: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """rmcl_manifold_mix_ste.py:121-139 — gather hypothesis idx[b,l] -> [B,L,J,3]."""
+    b, k, l, j, _ = hyp.shape
+    gather = idx[:, None, :, None, None].expand(b, 1, l, j, 3)
+    return hyp.gather(1, gather)[:, 0]
+
+
+def aggregate(hyp, scores=None, mode="weighted_ave", ground_truth=None):
+    """rmcl_manifold_mix_ste.py:141-185."""
+    if mode == "best_score":
+        assert scores is not None
+        return poses_from_hyp_idx(hyp, torch.argmax(scores, dim=1)[..., 0])
+    if mode == "weighted_ave":
+        assert scores is not None
+        return torch.sum(hyp * scores.unsqueeze(-1), dim=1)
+    if mode == "oracle":
+        assert ground_truth is not None
+        val, idx = wta_l2_loss_and_activate_head(hyp, ground_truth, None, False)
+        return val, poses_from_hyp_idx(hyp, idx)
+    raise ValueError(f"Only best_score and weighted_ave modes are implemented.Got {mode}.")
+
+
+def concat_hyp_and_scores(hyp: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
+    """rmcl_manifold_mix_ste.py:108-119 -> [B,K,L,J,4]."""
+    return torch.cat((hyp, scores.unsqueeze(3).expand(-1, -1, -1, hyp.shape[3], -1)), dim=-1)
+
+
+def mpjpe_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
+    """mean_joint_errors.py:8-36."""
+    d = torch.norm(gt.reshape(-1, 3) - pred.reshape(-1, 3), 2, 1)
+    if mode == "average":
+        return d.mean()
+    if mode == "sum":
+        return d.sum()
+    if mode == "no_agg":
+        return d
+    raise ValueError(f"Unexpected value for 'mode' encoutered: {mode}.")
+
+
+def pose_flip(x: torch.Tensor, left=H36M17_JOINTS_LEFT, right=H36M17_JOINTS_RIGHT) -> torch.Tensor:
+    """hpe/mh_so3_hpe/augmentations/functional.py:7-28 — negate x coordinate, swap L/R joints (copy)."""
+    out = x.clone()
+    out[..., 0] *= -1
+    out[..., left + right, :] = out[..., right + left, :]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic weights (no reference needed): same names/shapes as SURVEY.md §A.3
+# --------------------------------------------------------------------------------------
+def make_state_dict(num_frame=243, n_hyp=5, num_joints=17, num_bones=16, in_chans=2, rot_rep_dim=6,
+                    embed_dim_rot=512, depth_rot=8, embed_dim_seg=128, depth_seg=2, mlp_ratio=2.0,
+                    seed=0, std=0.02, single_head=False) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic state_dict with the reference's key names and shapes.  Linear weights ~
+    N(0, 1/fan_in) (close to nn.Linear's default scale), LN affine and pos-embeds perturbed by ``std``
+    so zero-init pos-embeds and unit LN affine are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f):
+        sd[name + ".weight"] = torch.randn(out_f, in_f, generator=g) / math.sqrt(in_f)
+        sd[name + ".bias"] = torch.randn(out_f, generator=g) * std
+
+    def ln(name, c):
+        sd[name + ".weight"] = 1.0 + torch.randn(c, generator=g) * std
+        sd[name + ".bias"] = torch.randn(c, generator=g) * std
+
+    def trunk(prefix, c, depth, n_tok):
+        sd[prefix + "Spatial_pos_embed"] = torch.randn(1, n_tok, c, generator=g) * std
+        sd[prefix + "Temporal_pos_embed"] = torch.randn(1, num_frame, c, generator=g) * std
+        hidden = int(c * mlp_ratio)
+        for kind in ("STEblocks", "TTEblocks"):
+            for i in range(depth):
+                p = f"{prefix}{kind}.{i}"
+                ln(p + ".norm1", c)
+                lin(p + ".attn.qkv", 3 * c, c)
+                lin(p + ".attn.proj", c, c)
+                ln(p + ".norm2", c)
+                lin(p + ".mlp.fc1", hidden, c)
+                lin(p + ".mlp.fc2", c, hidden)
+        ln(prefix + "Spatial_norm", c)
+        ln(prefix + "Temporal_norm", c)
+
+    rp = "rotations_module."
+    lin(rp + "Spatial_patch_to_embedding", embed_dim_rot, in_chans)
+    trunk(rp, embed_dim_rot, depth_rot, num_joints)
+    if single_head:
+        ln(rp + "head.0", embed_dim_rot)
+        lin(rp + "head.1", rot_rep_dim, embed_dim_rot)
+    else:
+        for k in range(n_hyp):
+            ln(f"{rp}head.{k}.norm", embed_dim_rot)
+            lin(f"{rp}head.{k}.prediction_head", rot_rep_dim + 1, embed_dim_rot)
+            lin(f"{rp}head.{k}.score_head", 1, num_joints)
+    sp = "segments_module."
+    lin(sp + "joints_to_segments_proj", num_bones * embed_dim_seg, num_joints * in_chans)
+    trunk(sp, embed_dim_seg, depth_seg, num_bones)
+    ln(sp + "head.0", embed_dim_seg)
+    lin(sp + "head.1", 1, embed_dim_seg)
+    return sd

@@ -1,0 +1,140 @@
+"""Freezes outputs of the UNMODIFIED reference (imported read-only from /root/reference through
+oracle/ref_loader.py) into small fixtures under tests/golden/.  Run in the build container only:
+
+    python scripts/make_goldens.py
+
+The reference has no golden vectors of its own; these are the pins the GPU box uses,
+because /root/reference does not exist there.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def weights_checksum(sd):
+    return float(sum(t.double().sum() for t in sd.values())), float(sum(t.double().abs().sum() for t in sd.values()))
+
+
+def decoder_golden(ref):
+    g = torch.Generator().manual_seed(1234)
+    n_clips, k, t = 4, 5, 13
+    n = n_clips * k * t
+    r6 = torch.randn(n, 17, 6, generator=g)
+    stress = torch.zeros(n, dtype=torch.bool)
+    r6[::17, 3] *= 1e-9
+    stress[::17] = True
+    r6[5::23, 7, 3:6] = 2.5 * r6[5::23, 7, 0:3]
+    stress[5::23] = True
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, 1, generator=g)
+    bones_signed = bones * torch.where(torch.rand(n_clips, 16, 1, generator=g) < 0.3, -1.0, 1.0)
+    root = torch.randn(n, 3, generator=g)
+    dec = ref.PoseDecoder(ref.make_skeleton(), rot_rep_dim=6)
+    out = {
+        "rot6d": r6, "stress_rows": stress, "bones": bones, "bones_signed": bones_signed, "root": root,
+        "poses_zero_root": dec(r6, bones, torch.zeros(n, 3)),
+        "poses_signed_root": dec(r6, bones_signed, root),
+        "rotmats": ref.rotation_tools.compute_rotation_matrix_from_ortho6d(r6.reshape(-1, 6)).reshape(n, 17, 3, 3),
+        "K": k, "T": t,
+    }
+    # KAT from hpe/useful_aux_scripts/test_forward_kinematics.py:104-106 (bone lengths) with identity 6-D
+    kat_len = torch.tensor([0.2, 0.5, 0.5, 0.2, 0.5, 0.5, 0.2, 0.2, 0.2, 0.2, 0.2, 0.4, 0.4, 0.2, 0.4, 0.4]).view(1, 16, 1)
+    ident = torch.tensor([1.0, 0, 0, 0, 1.0, 0]).expand(1, 17, 6).contiguous()
+    out["kat_bones"] = kat_len
+    out["kat_pose_identity"] = dec(ident, kat_len, torch.zeros(1, 3))
+    out["kat_t_pose"] = dec.build_t_pose_from_bone_lengths(kat_len)
+    r4 = torch.randn(20, 17, 4, generator=g)
+    dec4 = ref.PoseDecoder(ref.make_skeleton(), rot_rep_dim=4)
+    out["rot4d"] = r4
+    out["poses_4d"] = dec4(r4, bones, torch.zeros(20, 3))
+    torch.save(out, os.path.join(OUT, "decoder.pt"))
+
+
+def loss_golden(ref):
+    M = ref.metrics
+    g = torch.Generator().manual_seed(99)
+    b, k, t = 3, 5, 11
+    y = 0.3 * torch.randn(b, t, 17, 3, generator=g)
+    y[:, :, 0] = 0
+    hyp = (y[:, None] + 0.1 * torch.randn(b, k, t, 17, 3, generator=g)).requires_grad_(True)
+    logits = torch.randn(b, k, t, 1, generator=g, requires_grad=True)
+    scores = logits.softmax(dim=1)
+    w = M.STANDARD_H36M_WEIGHTS
+    out = {"hyp": hyp.detach().clone(), "logits": logits.detach().clone(), "scores": scores.detach().clone(), "y": y}
+    for name, weights, squared in (("w", w, False), ("u", None, False), ("wsq", w, True)):
+        v, i = M.wta_l2_loss_and_activate_head(hyp, y, weights, squared)
+        out[f"wta_val_{name}"], out[f"wta_idx_{name}"] = v.detach().clone(), i.clone()
+        tot, bce = M.wta_with_scoring_loss(hyp, scores, y, 0.1, weights, squared)
+        out[f"score_total_{name}"], out[f"score_bce_{name}"] = tot.detach().clone(), bce.detach().clone()
+    out["vel"] = M.mean_velocity_error(hyp, y, axis=2).detach().clone()
+    out["vel_sq"] = M.mean_velocity_error(hyp, y, axis=2, squared=True).detach().clone()
+    out["smooth_w"] = M.smoothness_regularization(hyp, w, axis=2).detach().clone()
+    # the training loss of hpe/main_h36m_lifting.py:101-209 with config.yaml defaults, and its gradients
+    wl = M.wta_l2_loss_and_activate_head(hypothesis=hyp, y=y, weights=w, squared=False)[0].mean()
+    sr = M.wta_with_scoring_loss(hypothesis=hyp, scores=scores, y=y, beta=0.1, weights=w, squared=False)[1]
+    vl = 2.0 * M.mean_velocity_error(predicted=hyp, target=y, squared=False, axis=2)
+    sg = 0.5 * M.smoothness_regularization(prediction=hyp, weights=w, axis=2)
+    loss = torch.zeros(1)
+    for term in (wl, sr, vl, sg):
+        loss = loss + term
+    loss.backward()
+    out.update(train_total=loss.detach().clone(), train_wloss=wl.detach().clone(), train_score_reg=sr.detach().clone(),
+               train_vloss=vl.detach().clone(), train_sreg=sg.detach().clone(),
+               grad_hyp=hyp.grad.clone(), grad_logits=logits.grad.clone())
+    torch.manual_seed(0)
+    m = ref.architectures.RMCLManifoldMixSTE(ref.make_skeleton(), num_frame=9, n_hyp=k)
+    hd, sc = hyp.detach(), scores.detach()
+    out["agg_weighted"] = m.aggregate(hd, sc, "weighted_ave")
+    out["agg_best"] = m.aggregate(hd, sc, "best_score")
+    out["agg_oracle_val"], out["agg_oracle_pose"] = m.aggregate(hd, mode="oracle", ground_truth=y)
+    out["mpjpe_sum"] = M.mpjpe_error(out["agg_weighted"], y, "sum")
+    out["mpjpe_avg"] = M.mpjpe_error(out["agg_weighted"], y, "average")
+    torch.save(out, os.path.join(OUT, "loss.pt"))
+
+
+def forward_golden(ref):
+    out = {}
+    for tag, T, k, perturb in (("t27k5_init", 27, 5, False), ("t27k5_pert", 27, 5, True), ("t9k1_pert", 9, 1, True)):
+        torch.manual_seed(42)
+        m = ref.architectures.RMCLManifoldMixSTE(ref.make_skeleton(), num_frame=T, n_hyp=k, drop_path_rate=0.1).eval()
+        if perturb:
+            g = torch.Generator().manual_seed(7)
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.add_(torch.randn(p.shape, generator=g) * 0.02)
+        x = 0.3 * torch.randn(1, T, 17, 2, generator=torch.Generator().manual_seed(1234))
+        with torch.no_grad():
+            poses, scores = m(x)
+            rot, _ = m.rotations_module(x)
+            bones = m.segments_module(x)
+        out[tag] = {"T": T, "K": k, "perturb": perturb, "x": x, "poses": poses, "scores": scores,
+                    "rot6d": rot, "bones": bones, "checksum": weights_checksum(m.state_dict()),
+                    "keys": [(n, tuple(t.shape)) for n, t in m.state_dict().items()]}
+    # seeded synthetic weights (oracle.make_state_dict) loaded INTO the reference model
+    sys.path.insert(0, ROOT)
+    from oracle.manipose_oracle import make_state_dict
+    sd = make_state_dict(num_frame=27, n_hyp=5, seed=3)
+    m = ref.architectures.RMCLManifoldMixSTE(ref.make_skeleton(), num_frame=27, n_hyp=5).eval()
+    m.load_state_dict(sd)
+    x = 0.3 * torch.randn(2, 27, 17, 2, generator=torch.Generator().manual_seed(77))
+    with torch.no_grad():
+        poses, scores = m(x)
+    out["t27k5_synth"] = {"T": 27, "K": 5, "seed": 3, "x": x, "poses": poses, "scores": scores,
+                          "checksum": weights_checksum(sd)}
+    torch.save(out, os.path.join(OUT, "forward.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    decoder_golden(ref)
+    loss_golden(ref)
+    forward_golden(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
