@@ -1,0 +1,188 @@
+/* libmanipose_sm100.so — C ABI of the B200-native (sm_100a) ManiPose lifting hot path.
+ *
+ * The reference (cedricrommel/manipose) is pure PyTorch with no FFI; the entry points below are what
+ * a ctypes binding for its hot path binds.  Each one cites the reference
+ * function (path:line under the reference checkout) whose work it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless said otherwise;
+ *   - all tensors are contiguous, row-major, with the reference's dimension order;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, never synchronises,
+ *     and is capturable in a CUDA graph;
+ *   - returns MP_OK (0) or a negative MP_E* code; mp_last_error() gives the message (thread-local);
+ *   - no CPU fallback and no other-architecture fallback: a non-sm_100 device is MP_EDEVICE.
+ */
+#ifndef MANIPOSE_SM100_H_
+#define MANIPOSE_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_ABI_VERSION 1
+
+enum {
+  MP_OK = 0,
+  MP_EINVAL = -1,       /* bad shape / null pointer / bad flag (reference: assert / ValueError)     */
+  MP_EUNSUPPORTED = -2, /* valid in the reference but not built here (e.g. another skeleton tree)  */
+  MP_EDEVICE = -3,      /* current device is not sm_100                                            */
+  MP_ELAUNCH = -4,      /* cudaGetLastError() after a launch                                       */
+  MP_EALIGN = -5,       /* pointer not 16-byte aligned where the kernel needs it                   */
+  MP_EWORKSPACE = -6    /* workspace too small                                                     */
+};
+
+typedef void* mp_stream_t; /* cudaStream_t */
+
+int mp_abi_version(void);
+const char* mp_last_error(void);
+/* 0 if the current CUDA device is sm_100 (B200), MP_EDEVICE otherwise. */
+int mp_device_check(void);
+
+/* Skeleton tables (hpe/mh_so3_hpe/data/skeleton.py:7-172, t_pose_operators from
+ * hpe/mh_so3_hpe/data/h36m_lifting.py:40-57).  The kernels are specialised at compile time for the
+ * 17-joint H36M / MPI-INF-3DHP tree (both datasets use it: h36m_lifting.py:649-660 ==
+ * dataset_3dhp.py:132-138); this call VALIDATES the caller's tables against it and returns
+ * MP_EUNSUPPORTED for any other tree.  parents[num_joints], operators[num_joints*3] (row 0 ignored). */
+int mp_set_skeleton(int num_joints, const int32_t* host_parents, const float* host_t_pose_operators);
+
+/* ---- manifold decoder -----------------------------------------------------
+ * PoseDecoder.forward (hpe/mh_so3_hpe/architectures/pose_decoder.py:32-55) =
+ * compute_rotation_matrix_from_ortho6d (utils/rotation_tools.py:35-57) + build_t_pose_from_bone_lengths
+ * (pose_decoder.py:98-120) + forward_kinematics (utils/forward_kinematics.py:6-48), fused with the
+ * softmax over hypotheses of RMCLRotMixSTE.forward (rmcl_manifold_mix_ste.py:262).
+ *   rot6d   [n_clips*n_hyp*n_frames, 17, 6] fp32   (the reference's "(B H L) J D" flattening)
+ *   bone_len[n_clips, 16] fp32 (signed)             pose n uses clip n / (n_hyp*n_frames)
+ *   root    [n_poses, 3] or NULL (= zeros, what the reference passes)
+ *   logits  [n_clips, n_hyp, n_frames] or NULL; scores (same shape) = softmax over n_hyp
+ *   poses   [n_poses, 17, 3] fp32 */
+#define MP_DEC_EXACT 0 /* same IEEE fp32 operations in the same order as the reference's torch-CPU path:
+                          poses bit-identical to the oracle (default)                                */
+#define MP_DEC_FAST 1  /* rsqrt + FMA contraction: <= 1e-6 relative difference, fewer instructions   */
+int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root, const float* logits,
+                   float* poses, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames,
+                   int rot_rep_dim, int flags, mp_stream_t stream);
+/* Backward of the above w.r.t. rot6d, bone_len (summed over a clip's poses; the caller zeroes
+ * grad_bone_len first) and root (grad_root may be NULL). Recomputes rotations from rot6d. */
+int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_poses,
+                   float* grad_rot6d, float* grad_bone_len, float* grad_root, int64_t n_clips,
+                   int64_t n_hyp, int64_t n_frames, int rot_rep_dim, mp_stream_t stream);
+/* softmax over n_hyp backward: grad_logits = s * (g - sum_k s g); all [n_clips, n_hyp, n_frames]. */
+int mp_softmax_hyp_bwd(const float* scores, const float* grad_scores, float* grad_logits,
+                       int64_t n_clips, int64_t n_hyp, int64_t n_frames, mp_stream_t stream);
+
+/* ---- losses and hypothesis metrics ---------------------------------
+ * terms layout (fp32[MP_LOSS_NTERMS]) written by mp_loss_fwd: */
+enum {
+  MP_TERM_WTA = 0,    /* wta_l2_loss_and_activate_head(...)[0].mean()  (losses.py:126-138)          */
+  MP_TERM_BCE = 1,    /* F.binary_cross_entropy(scores, one_hot(winner)) (losses.py:165-168)        */
+  MP_TERM_VEL = 2,    /* mean_velocity_error(axis=2) (losses.py:75-101)                             */
+  MP_TERM_SMOOTH = 3, /* smoothness_regularization(axis=2) (regularizations.py:160-174)             */
+  MP_TERM_TOTAL = 4,  /* wta + beta*bce + vel_w*vel + smooth_w*smooth (main_h36m_lifting.py:101-209) */
+  MP_LOSS_NTERMS = 8
+};
+/* _l2_loss_per_hyp + torch.min(dim=1) (losses.py:104-138): hyp [B,K,T,17,3], y [B,T,17,3],
+ * joint_weights[17] or NULL (= ones) -> wta_val [B,T] fp32, wta_idx [B,T] int64 (lowest k on ties),
+ * per_hyp [B,K,T] or NULL.  Bit-exact with torch CPU (AVX2 sum order) on identical inputs. */
+int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int squared,
+               float* wta_val, int64_t* wta_idx, float* per_hyp, int64_t B, int64_t K, int64_t T,
+               mp_stream_t stream);
+/* All four training-loss terms in one pass (make_loss closures, hpe/main_h36m_lifting.py:129-169).
+ * scores [B,K,T] (or [B,K,T,1]); workspace >= mp_loss_workspace_bytes(B,K,T). */
+size_t mp_loss_workspace_bytes(int64_t B, int64_t K, int64_t T);
+int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const float* joint_weights,
+                int squared, float beta, float vel_w, float smooth_w, float* terms, float* wta_val,
+                int64_t* wta_idx, int64_t B, int64_t K, int64_t T, void* workspace,
+                size_t workspace_bytes, mp_stream_t stream);
+/* Gradient of grad_total * MP_TERM_TOTAL w.r.t. hyp and scores (wta_idx from mp_loss_fwd). */
+int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const float* joint_weights,
+                const int64_t* wta_idx, int squared, float beta, float vel_w, float smooth_w,
+                const float* grad_total, float* grad_hyp, float* grad_scores, int64_t B, int64_t K,
+                int64_t T, mp_stream_t stream);
+
+/* RMCLManifoldMixSTE.aggregate (rmcl_manifold_mix_ste.py:141-185) + poses_from_hyp_idx (:121-139). */
+enum { MP_AGG_WEIGHTED_AVE = 0, MP_AGG_BEST_SCORE = 1, MP_AGG_ORACLE = 2 };
+/* hyp [B,K,T,17,3]; scores [B,K,T] (modes 0,1); y [B,T,17,3] (mode 2).  out_pose [B,T,17,3];
+ * out_val [B,T] (mode 2: unweighted per-frame MPJPE of the winner) or NULL; out_idx [B,T] int64 or NULL. */
+int mp_aggregate(const float* hyp, const float* scores, const float* y, int mode, float* out_pose,
+                 float* out_val, int64_t* out_idx, int64_t B, int64_t K, int64_t T, mp_stream_t stream);
+/* mpjpe_error (mean_joint_errors.py:31-36): sum over n_points of ||gt - pred||_2 -> out[0] (fp32 sum),
+ * out[1] (mean).  workspace >= mp_mpjpe_workspace_bytes(n_points). */
+size_t mp_mpjpe_workspace_bytes(int64_t n_points);
+int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, void* workspace,
+             size_t workspace_bytes, mp_stream_t stream);
+
+/* ---- MixSTE backbone building blocks, bf16 activations ---------------------
+ * Token order is always [clip, frame, joint] (one layout, no transposes: the reference's
+ * rearranges, mix_ste.py:131,144,167,171,184, become strided reads inside the attention kernel). */
+
+/* Y[M,N] (bf16) = epilogue(A[M,K] (bf16) @ W[N,K]^T (bf16) + bias[N] (fp32)); nn.Linear call sites
+ * mix_ste.py:209-222 (fc1/fc2), :257,:280 (qkv/proj).  tcgen05.mma + TMEM accumulators + TMA.
+ *   MP_EPI_BIAS: bias only; MP_EPI_GELU: exact-erf GELU (nn.GELU, mix_ste.py:200);
+ *   MP_EPI_RESIDUAL: Y = resid[M,N] (bf16) + A W^T + bias  (Block.forward, mix_ste.py:352-358).
+ * K % 64 == 0, N % 64 == 0; lda/ldw/ldy = row strides in elements (16-byte aligned rows). */
+enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2 };
+int mp_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* Y,
+                 int64_t M, int64_t N, int64_t K, int epilogue, mp_stream_t stream);
+
+/* LayerNorm family (fp32 statistics over C in {128, 512}; one warp per token).
+ *   x_in  [n_tokens, C] bf16
+ *   if post_gamma != NULL: x = LN(x_in; post_gamma, post_beta, post_eps)       (shared Spatial_norm /
+ *        Temporal_norm, mix_ste.py:143,154,166,170) (+ pos_embed[(token / pos_div) % pos_mod, C] fp32 if
+ *        pos_embed != NULL: the Temporal_pos_embed add of mix_ste.py:149); written to x_out (bf16)
+ *   if ln_gamma != NULL: h_out = LN(x; ln_gamma, ln_beta, ln_eps) (next block's norm1, :353), bf16 */
+int mp_layernorm(const void* x_in, void* x_out, void* h_out, const float* post_gamma,
+                 const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
+                 int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                 int64_t n_tokens, int C, mp_stream_t stream);
+
+/* Joint embedding + spatial pos-embed + first norm1 (MixSTE.STE_forward, mix_ste.py:128-138):
+ *   x[tok, c] = W[c,0:2] . in[tok,0:2] + b[c] + spos[tok % 17, c]  (fp32 math) -> x_out bf16,
+ *   h_out = LN(x; ln_gamma, ln_beta, 1e-6) bf16.  in [n_tokens, 2] fp32, C = 512. */
+int mp_embed_joints(const float* in2d, const float* W, const float* b, const float* spos,
+                    const float* ln_gamma, const float* ln_beta, float ln_eps, void* x_out,
+                    void* h_out, int64_t n_tokens, int n_joints, int C, mp_stream_t stream);
+/* joints_to_segments_proj + pos-embed + norm1 (BonesMixSTE.forward, manifold_mix_ste.py:139-148):
+ *   in [n_frames, 34] fp32, W [16*128, 34], b [2048], spos [16,128] -> x_out/h_out [n_frames*16,128]. */
+int mp_embed_segments(const float* in2d, const float* W, const float* b, const float* spos,
+                      const float* ln_gamma, const float* ln_beta, float ln_eps, void* x_out,
+                      void* h_out, int64_t n_frames, int in_features, int n_segments, int C,
+                      mp_stream_t stream);
+
+/* Multi-head softmax attention (Attention.forward, mix_ste.py:255-282), mma.sync tensor cores.
+ *   qkv [n_clips*n_frames*n_tok, 3*C] bf16, columns [q|k|v] x heads x head_dim (mix_ste.py:257-261)
+ *   out [n_clips*n_frames*n_tok, C] bf16;  head_dim in {64, 16}; scale = head_dim^-0.5
+ *   MP_ATTN_SPATIAL: sequences = the n_tok tokens of one frame;
+ *   MP_ATTN_TEMPORAL: sequences = the n_frames frames of one (clip, token) track (n_frames <= 256). */
+enum { MP_ATTN_SPATIAL = 0, MP_ATTN_TEMPORAL = 1 };
+int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C,
+                 int n_heads, int mode, mp_stream_t stream);
+
+/* K hypothesis heads (RMCLRotMixSTE.forward tail + MCLHead, rmcl_manifold_mix_ste.py:251-298):
+ *   x [n_frames_total*17, 512] bf16 = output of the last temporal block BEFORE Temporal_norm;
+ *   applies Temporal_norm (post_*), then per head k: LN(eps 1e-5; hg/hb [K,512]) -> Linear(512 -> out_dim
+ *   (+1 if with_score); hw [K, out_dim+1, 512], hbias [K, out_dim+1]) -> rot [B,K,T,17,out_dim] fp32 and,
+ *   if with_score, logits[B,K,T] = score_w[K,17] . score_emb + score_b[K].
+ *   with_score = 0 is MixSTE.head of the single-hypothesis model (mix_ste.py:123-126, K = 1). */
+int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta, float post_eps,
+                 const float* hg, const float* hb, const float* hw, const float* hbias,
+                 const float* score_w, const float* score_b, float* rot, float* logits,
+                 int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score,
+                 mp_stream_t stream);
+/* Bone-length head (MixSTE.head + mean over time, mix_ste.py:123-126,187; manifold_mix_ste.py:150-154):
+ *   x [n_clips*n_frames*16, 128] bf16 before Temporal_norm -> bone_len [n_clips,16] fp32.
+ *   workspace >= n_clips*n_frames*16*4 bytes. */
+int mp_bones_head(const void* x, const float* post_gamma, const float* post_beta, float post_eps,
+                  const float* hg, const float* hb, const float* hw, const float* hbias,
+                  float* bone_len, int64_t n_clips, int64_t n_frames, int n_segments, int C,
+                  void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
+/* fp32 -> bf16 (weight shadows refreshed by the host wrapper after optimizer.step()). */
+int mp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANIPOSE_SM100_H_ */

@@ -1,0 +1,477 @@
+// Memory-bound pieces of the MixSTE backbone: joint / segment embeddings, the LayerNorm family, the K hypothesis
+// heads and the bone-length head.  bf16 activations, fp32 statistics and parameters, one warp per token.
+//
+// Replaces (reference, paths under hpe/mh_so3_hpe/architectures/):
+//   mix_ste.py:128-138      STE_forward: Spatial_patch_to_embedding + Spatial_pos_embed
+//   manifold_mix_ste.py:139-148 BonesMixSTE: joints_to_segments_proj (+ pos embed)
+//   mix_ste.py:49,143,149,154,166,170,353,356  norm1 / norm2 / Spatial_norm / Temporal_norm / Temporal_pos_embed
+//   rmcl_manifold_mix_ste.py:251-298  K x MCLHead (LN eps 1e-5, Linear 512->7, score Linear 17->1)
+//   mix_ste.py:123-126,187 + manifold_mix_ste.py:150-154  segment head + mean over time
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mp {
+namespace {
+
+// ---- a token row held by a warp: C/32 consecutive-in-groups-of-8 channels per lane -----------------------------
+// C = 512: lane owns channels [8*lane, 8*lane+8) and [256 + 8*lane, 256 + 8*lane + 8)   (two 16-byte accesses)
+// C = 128: lane owns channels [4*lane, 4*lane+4)                                          (one 8-byte access)
+template <int C>
+struct Row {
+  static constexpr int kPer = C / 32;
+  static_assert(C == 512 || C == 128, "C must be 128 or 512");
+  __device__ static __forceinline__ int chan(int lane, int i) {
+    if (C == 512) return (i < 8 ? 0 : 256) + lane * 8 + (i & 7);
+    return lane * 4 + i;
+  }
+  __device__ static __forceinline__ void load_bf16(const __nv_bfloat16* __restrict__ row, int lane, float (&v)[kPer]) {
+    if (C == 512) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + h * 256 + lane * 8);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[h * 8 + 0] = a.x; v[h * 8 + 1] = a.y; v[h * 8 + 2] = b.x; v[h * 8 + 3] = b.y;
+        v[h * 8 + 4] = c.x; v[h * 8 + 5] = c.y; v[h * 8 + 6] = d.x; v[h * 8 + 7] = d.y;
+      }
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(row + lane * 4);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+  }
+  __device__ static __forceinline__ void store_bf16(__nv_bfloat16* __restrict__ row, int lane, const float (&v)[kPer]) {
+    if (C == 512) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 u;
+        u.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]);
+        u.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+        u.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]);
+        u.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+        *reinterpret_cast<uint4*>(row + h * 256 + lane * 8) = u;
+      }
+    } else {
+      uint2 u;
+      u.x = pack_bf16x2(v[0], v[1]);
+      u.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(row + lane * 4) = u;
+    }
+  }
+  // fp32 parameter vector (gamma, beta, pos-embed row ...) in the same per-lane channel order
+  __device__ static __forceinline__ void load_f32(const float* __restrict__ p, int lane, float (&v)[kPer]) {
+    if (C == 512) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p + h * 256 + lane * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p + h * 256 + lane * 8 + 4));
+        v[h * 8 + 0] = a.x; v[h * 8 + 1] = a.y; v[h * 8 + 2] = a.z; v[h * 8 + 3] = a.w;
+        v[h * 8 + 4] = b.x; v[h * 8 + 5] = b.y; v[h * 8 + 6] = b.z; v[h * 8 + 7] = b.w;
+      }
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p + lane * 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+  }
+  // round to bf16 and back (what the next kernel will read)
+  __device__ static __forceinline__ void round_bf16(float (&v)[kPer]) {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  }
+  // mean and 1/sqrt(var + eps) over the row (two-pass, biased variance: nn.LayerNorm)
+  __device__ static __forceinline__ void stats(const float (&v)[kPer], float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) s += v[i];
+    mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const float d = v[i] - mean;
+      q = fmaf(d, d, q);
+    }
+    rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+  }
+  __device__ static __forceinline__ void normalize(float (&v)[kPer], float mean, float rstd, const float (&g)[kPer], const float (&b)[kPer]) {
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], b[i]);
+  }
+};
+
+constexpr int kTokWarps = 8;  // warps per CTA in the token kernels
+
+// -------------------------------------------------------------------------------------------------- LayerNorm family
+template <int C>
+__global__ void __launch_bounds__(kTokWarps * 32)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x_in, __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out,
+                 const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps, const float* __restrict__ pos,
+                 int64_t pos_div, int64_t pos_mod, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
+                 int64_t n_tokens) {
+  using R = Row<C>;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
+  float pg[R::kPer], pb[R::kPer], lg[R::kPer], lb[R::kPer];
+  if (post_g) {
+    R::load_f32(post_g, lane, pg);
+    R::load_f32(post_b, lane, pb);
+  }
+  if (ln_g) {
+    R::load_f32(ln_g, lane, lg);
+    R::load_f32(ln_b, lane, lb);
+  }
+  for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
+    float v[R::kPer];
+    R::load_bf16(x_in + tok * C, lane, v);
+    float mean, rstd;
+    if (post_g) {
+      R::stats(v, post_eps, mean, rstd);
+      R::normalize(v, mean, rstd, pg, pb);
+      if (pos) {
+        float pe[R::kPer];
+        R::load_f32(pos + ((tok / pos_div) % pos_mod) * C, lane, pe);
+#pragma unroll
+        for (int i = 0; i < R::kPer; ++i) v[i] += pe[i];
+      }
+      R::round_bf16(v);
+      R::store_bf16(x_out + tok * C, lane, v);
+    }
+    if (ln_g) {
+      R::stats(v, ln_eps, mean, rstd);
+      R::normalize(v, mean, rstd, lg, lb);
+      R::store_bf16(h_out + tok * C, lane, v);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- joint embedding
+// x[tok, c] = W[c,0] in0 + W[c,1] in1 + b[c] + spos[tok % J, c]; h = LN(x)          (C = 512)
+__global__ void __launch_bounds__(kTokWarps * 32)
+embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
+                    const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
+                    __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out, int64_t n_tokens, int n_joints) {
+  using R = Row<512>;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
+  float w0[R::kPer], w1[R::kPer], bb[R::kPer], lg[R::kPer], lb[R::kPer];
+#pragma unroll
+  for (int i = 0; i < R::kPer; ++i) {
+    const int c = R::chan(lane, i);
+    w0[i] = __ldg(W + c * 2 + 0);
+    w1[i] = __ldg(W + c * 2 + 1);
+  }
+  R::load_f32(bias, lane, bb);
+  R::load_f32(ln_g, lane, lg);
+  R::load_f32(ln_b, lane, lb);
+  for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
+    const float2 p = __ldg(reinterpret_cast<const float2*>(in2d) + tok);
+    float pe[R::kPer], v[R::kPer];
+    R::load_f32(spos + (tok % n_joints) * 512, lane, pe);
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) v[i] = fmaf(w1[i], p.y, fmaf(w0[i], p.x, bb[i])) + pe[i];
+    R::round_bf16(v);
+    R::store_bf16(x_out + tok * 512, lane, v);
+    float mean, rstd;
+    R::stats(v, ln_eps, mean, rstd);
+    R::normalize(v, mean, rstd, lg, lb);
+    R::store_bf16(h_out + tok * 512, lane, v);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- segment embedding
+// per frame: in[34] -> [16 segments x 128]; a CTA owns ONE segment (its 128 x 34 weight slice lives transposed in
+// shared memory) and streams frames; token = frame * 16 + segment.
+constexpr int kSegC = 128;
+__global__ void __launch_bounds__(kTokWarps * 32)
+embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
+                      const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
+                      __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out, int64_t n_frames, int in_features,
+                      int n_segments) {
+  using R = Row<kSegC>;
+  extern __shared__ __align__(16) float wt[];  // [in_features][128]
+  const int seg = blockIdx.y;
+  for (int i = threadIdx.x; i < in_features * kSegC; i += blockDim.x) {
+    const int c = i % kSegC, f = i / kSegC;
+    wt[f * kSegC + c] = W[(size_t)(seg * kSegC + c) * in_features + f];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float bb[R::kPer], pe[R::kPer], lg[R::kPer], lb[R::kPer];
+  R::load_f32(bias + seg * kSegC, lane, bb);
+  R::load_f32(spos + seg * kSegC, lane, pe);
+  R::load_f32(ln_g, lane, lg);
+  R::load_f32(ln_b, lane, lb);
+  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
+  for (int64_t fr = warp_global; fr < n_frames; fr += stride) {
+    const float* in = in2d + fr * in_features;
+    float v[R::kPer];
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) v[i] = bb[i];
+    for (int f = 0; f < in_features; ++f) {
+      const float xin = __ldg(in + f);
+      const float4 wv = *reinterpret_cast<const float4*>(wt + f * kSegC + lane * 4);
+      v[0] = fmaf(wv.x, xin, v[0]);
+      v[1] = fmaf(wv.y, xin, v[1]);
+      v[2] = fmaf(wv.z, xin, v[2]);
+      v[3] = fmaf(wv.w, xin, v[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) v[i] += pe[i];
+    const int64_t tok = fr * n_segments + seg;
+    R::round_bf16(v);
+    R::store_bf16(x_out + tok * kSegC, lane, v);
+    float mean, rstd;
+    R::stats(v, ln_eps, mean, rstd);
+    R::normalize(v, mean, rstd, lg, lb);
+    R::store_bf16(h_out + tok * kSegC, lane, v);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- hypothesis heads
+// LN_k(x) W_k^T + b_k = rstd * (x . (g_k*W_k) - mean * sum(g_k*W_k)) + (W_k beta_k + b_k): the K LayerNorms share the
+// token statistics, so the K heads are ONE [512 x K*O] projection with folded weights held in shared memory.
+constexpr int kHeadC = 512;
+__global__ void __launch_bounds__(kTokWarps * 32)
+heads_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
+                 const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
+                 const float* __restrict__ score_w, const float* __restrict__ score_b, float* __restrict__ rot, float* __restrict__ logits,
+                 int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
+  using R = Row<kHeadC>;
+  extern __shared__ __align__(16) float sm[];
+  const int O = out_dim + (with_score ? 1 : 0);  // outputs per head
+  const int KO = n_hyp * O;
+  float* wf = sm;                        // [KO][512] folded weights g_k[c] * W_k[o][c]
+  float* csum = wf + (size_t)KO * kHeadC;  // [KO] sum_c wf
+  float* dconst = csum + KO;             // [KO] W_k beta_k + b_k
+  float* stage = dconst + KO;            // [warps][n_hyp][17*out_dim] rot staging
+
+  for (int i = threadIdx.x; i < KO * kHeadC; i += blockDim.x) {
+    const int c = i % kHeadC, ko = i / kHeadC, k = ko / O;
+    wf[i] = hg[k * kHeadC + c] * hw[(size_t)ko * kHeadC + c];
+  }
+  __syncthreads();
+  for (int ko = threadIdx.x >> 5; ko < KO; ko += blockDim.x >> 5) {
+    const int lane = threadIdx.x & 31, k = ko / O;
+    float s = 0.f, dd = 0.f;
+    for (int c = lane; c < kHeadC; c += 32) {
+      s += wf[(size_t)ko * kHeadC + c];
+      dd = fmaf(hw[(size_t)ko * kHeadC + c], hb[k * kHeadC + c], dd);
+    }
+    s = warp_sum(s);
+    dd = warp_sum(dd);
+    if (lane == 0) {
+      csum[ko] = s;
+      dconst[ko] = dd + hbias[ko];
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rot_per_pose = kJ * out_dim;
+  float* my_stage = stage + (size_t)warp * n_hyp * rot_per_pose;
+  float pg[R::kPer], pb[R::kPer];
+  R::load_f32(post_g, lane, pg);
+  R::load_f32(post_b, lane, pb);
+  const int64_t total_frames = n_clips * n_frames;
+  for (int64_t fr = (int64_t)blockIdx.x * kTokWarps + warp; fr < total_frames; fr += (int64_t)gridDim.x * kTokWarps) {
+    const int64_t b = fr / n_frames;
+    const int t = (int)(fr - b * n_frames);
+    float logit_acc = 0.f;  // lane k (< n_hyp) accumulates its head's logit
+    for (int j = 0; j < kJ; ++j) {
+      float v[R::kPer];
+      R::load_bf16(x + (fr * kJ + j) * kHeadC, lane, v);
+      float mean, rstd;
+      R::stats(v, post_eps, mean, rstd);
+      R::normalize(v, mean, rstd, pg, pb);   // Temporal_norm (eps 1e-6), kept in fp32
+      R::stats(v, 1e-5f, mean, rstd);        // shared statistics of the K head LayerNorms (eps 1e-5)
+      for (int ko = 0; ko < KO; ++ko) {
+        const float* wrow = wf + (size_t)ko * kHeadC;
+        float acc = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 a = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8);
+          const float4 c4 = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8 + 4);
+          acc = fmaf(v[h * 8 + 0], a.x, acc);
+          acc = fmaf(v[h * 8 + 1], a.y, acc);
+          acc = fmaf(v[h * 8 + 2], a.z, acc);
+          acc = fmaf(v[h * 8 + 3], a.w, acc);
+          acc = fmaf(v[h * 8 + 4], c4.x, acc);
+          acc = fmaf(v[h * 8 + 5], c4.y, acc);
+          acc = fmaf(v[h * 8 + 6], c4.z, acc);
+          acc = fmaf(v[h * 8 + 7], c4.w, acc);
+        }
+        acc = warp_sum(acc);
+        const float val = fmaf(rstd, acc - mean * csum[ko], dconst[ko]);
+        const int k = ko / O, o = ko - k * O;
+        if (o < out_dim) {
+          if (lane == 0) my_stage[k * rot_per_pose + j * out_dim + o] = val;
+        } else if (lane == k) {
+          logit_acc = fmaf(score_w[k * kJ + j], val, logit_acc);   // score_head: Linear(17 -> 1)
+        }
+      }
+    }
+    __syncwarp();
+    // rot[b, k, t, :, :] is 17*out_dim contiguous floats per (b,k,t)
+    for (int k = 0; k < n_hyp; ++k) {
+      float* dst = rot + (((size_t)b * n_hyp + k) * n_frames + t) * rot_per_pose;
+      for (int i = lane; i < rot_per_pose; i += 32) dst[i] = my_stage[k * rot_per_pose + i];
+    }
+    if (with_score && lane < n_hyp) logits[((size_t)b * n_hyp + lane) * n_frames + t] = logit_acc + score_b[lane];
+    __syncwarp();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- bone-length head
+// value[token] = Linear(128 -> 1)(LN_head(Temporal_norm(x)))  ;  bone_len[b, s] = mean_t value[b, t, s]
+__global__ void __launch_bounds__(kTokWarps * 32)
+bones_value_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
+                   const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
+                   float* __restrict__ values, int64_t n_tokens) {
+  using R = Row<kSegC>;
+  const int lane = threadIdx.x & 31;
+  float pg[R::kPer], pb[R::kPer], g[R::kPer], bt[R::kPer], w[R::kPer];
+  R::load_f32(post_g, lane, pg);
+  R::load_f32(post_b, lane, pb);
+  R::load_f32(hg, lane, g);
+  R::load_f32(hb, lane, bt);
+  R::load_f32(hw, lane, w);
+  const float b0 = hbias[0];
+  for (int64_t tok = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5); tok < n_tokens; tok += (int64_t)gridDim.x * kTokWarps) {
+    float v[R::kPer];
+    R::load_bf16(x + tok * kSegC, lane, v);
+    float mean, rstd;
+    R::stats(v, post_eps, mean, rstd);
+    R::normalize(v, mean, rstd, pg, pb);
+    R::stats(v, 1e-5f, mean, rstd);
+    R::normalize(v, mean, rstd, g, bt);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) acc = fmaf(v[i], w[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) values[tok] = acc + b0;
+  }
+}
+__global__ void bones_mean_kernel(const float* __restrict__ values, float* __restrict__ bone_len, int64_t n_clips, int n_frames, int n_seg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_clips * n_seg) return;
+  const int64_t b = i / n_seg;
+  const int s = (int)(i - b * n_seg);
+  float acc = 0.f;
+  for (int t = 0; t < n_frames; ++t) acc += values[(b * n_frames + t) * n_seg + s];
+  bone_len[i] = acc / (float)n_frames;
+}
+
+int token_grid(int64_t n_tokens) {
+  int64_t ctas = (n_tokens + kTokWarps - 1) / kTokWarps;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+
+}  // namespace
+}  // namespace mp
+
+extern "C" {
+
+int mp_layernorm(const void* x_in, void* x_out, void* h_out, const float* post_gamma, const float* post_beta, float post_eps,
+                 const float* pos_embed, int64_t pos_div, int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                 int64_t n_tokens, int C, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(C == 512 || C == 128, MP_EUNSUPPORTED, "mp_layernorm: C=%d (built for 512 and 128)", C);
+  MP_REQUIRE(x_in && n_tokens >= 0, MP_EINVAL, "mp_layernorm: bad arguments");
+  MP_REQUIRE((post_gamma == nullptr) == (post_beta == nullptr) && (ln_gamma == nullptr) == (ln_beta == nullptr), MP_EINVAL,
+             "mp_layernorm: gamma/beta go together");
+  MP_REQUIRE(post_gamma || ln_gamma, MP_EINVAL, "mp_layernorm: nothing to do");
+  MP_REQUIRE(!post_gamma || x_out, MP_EINVAL, "mp_layernorm: x_out required with the post-norm");
+  MP_REQUIRE(!ln_gamma || h_out, MP_EINVAL, "mp_layernorm: h_out required with the pre-norm");
+  MP_REQUIRE(!pos_embed || (post_gamma && pos_div >= 1 && pos_mod >= 1), MP_EINVAL, "mp_layernorm: pos_embed needs the post-norm and pos_div/pos_mod >= 1");
+  MP_REQUIRE(aligned16(x_in) && aligned16(x_out) && aligned16(h_out), MP_EALIGN, "mp_layernorm: activations must be 16-byte aligned");
+  if (n_tokens == 0) return MP_OK;
+  const int grid = token_grid(n_tokens);
+  if (C == 512)
+    layernorm_kernel<512><<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_in, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, post_gamma, post_beta, post_eps, pos_embed, pos_div,
+        pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
+  else
+    layernorm_kernel<128><<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_in, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, post_gamma, post_beta, post_eps, pos_embed, pos_div,
+        pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
+  return check_launch("layernorm_kernel");
+}
+
+int mp_embed_joints(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma, const float* ln_beta,
+                    float ln_eps, void* x_out, void* h_out, int64_t n_tokens, int n_joints, int C, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(C == 512, MP_EUNSUPPORTED, "mp_embed_joints: C=%d (built for 512)", C);
+  MP_REQUIRE(in2d && W && b && spos && ln_gamma && ln_beta && x_out && h_out && n_tokens >= 0 && n_joints >= 1, MP_EINVAL,
+             "mp_embed_joints: bad arguments");
+  MP_REQUIRE(aligned16(x_out) && aligned16(h_out) && aligned16(in2d), MP_EALIGN, "mp_embed_joints: pointers must be 16-byte aligned");
+  if (n_tokens == 0) return MP_OK;
+  embed_joints_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(
+      in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, n_tokens, n_joints);
+  return check_launch("embed_joints_kernel");
+}
+
+int mp_embed_segments(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma, const float* ln_beta,
+                      float ln_eps, void* x_out, void* h_out, int64_t n_frames, int in_features, int n_segments, int C,
+                      mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(C == kSegC, MP_EUNSUPPORTED, "mp_embed_segments: C=%d (built for 128)", C);
+  MP_REQUIRE(in2d && W && b && spos && ln_gamma && ln_beta && x_out && h_out && n_frames >= 0, MP_EINVAL, "mp_embed_segments: bad arguments");
+  MP_REQUIRE(in_features >= 1 && in_features <= 128 && n_segments >= 1 && n_segments <= 64, MP_EINVAL, "mp_embed_segments: bad sizes");
+  if (n_frames == 0) return MP_OK;
+  const size_t smem = (size_t)in_features * kSegC * sizeof(float);
+  int gx = (int)((n_frames + kTokWarps - 1) / kTokWarps);
+  const int cap = sm_count() * 2 / n_segments + 1;
+  if (gx > cap) gx = cap;
+  embed_segments_kernel<<<dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream>>>(
+      in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, n_frames, in_features, n_segments);
+  return check_launch("embed_segments_kernel");
+}
+
+int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
+                 const float* hw, const float* hbias, const float* score_w, const float* score_b, float* rot, float* logits,
+                 int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(x && post_gamma && post_beta && hg && hb && hw && hbias && rot, MP_EINVAL, "mp_heads_fwd: null pointer");
+  MP_REQUIRE(!with_score || (score_w && score_b && logits), MP_EINVAL, "mp_heads_fwd: score head pointers required");
+  MP_REQUIRE(n_hyp >= 1 && n_hyp <= 16 && (out_dim == 6 || out_dim == 4), MP_EINVAL, "mp_heads_fwd: bad n_hyp/out_dim");
+  MP_REQUIRE(n_clips >= 0 && n_frames >= 1, MP_EINVAL, "mp_heads_fwd: bad sizes");
+  if (n_clips == 0) return MP_OK;
+  const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
+  const size_t smem = ((size_t)KO * kHeadC + 2 * KO + (size_t)kTokWarps * n_hyp * kJ * out_dim) * sizeof(float);
+  MP_REQUIRE(smem <= 227 * 1024, MP_EUNSUPPORTED, "mp_heads_fwd: n_hyp=%d needs %zu bytes of shared memory", n_hyp, smem);
+  cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
+  const int64_t cap = (int64_t)sm_count() * (smem > 110 * 1024 ? 1 : 2);
+  if (ctas > cap) ctas = cap;
+  heads_fwd_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias, score_w, score_b, rot, logits, n_clips, (int)n_frames,
+      n_hyp, out_dim, with_score);
+  return check_launch("heads_fwd_kernel");
+}
+
+int mp_bones_head(const void* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
+                  const float* hw, const float* hbias, float* bone_len, int64_t n_clips, int64_t n_frames, int n_segments, int C,
+                  void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(C == kSegC, MP_EUNSUPPORTED, "mp_bones_head: C=%d (built for 128)", C);
+  MP_REQUIRE(x && post_gamma && post_beta && hg && hb && hw && hbias && bone_len && workspace, MP_EINVAL, "mp_bones_head: null pointer");
+  const int64_t n_tokens = n_clips * n_frames * n_segments;
+  MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * sizeof(float), MP_EWORKSPACE, "mp_bones_head: workspace too small");
+  if (n_tokens == 0) return MP_OK;
+  float* values = reinterpret_cast<float*>(workspace);
+  bones_value_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, post_gamma, post_beta,
+                                                                                         post_eps, hg, hb, hw, hbias, values, n_tokens);
+  MP_CHECK(check_launch("bones_value_kernel"));
+  const int64_t n_out = n_clips * n_segments;
+  bones_mean_kernel<<<(int)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream>>>(values, bone_len, n_clips, (int)n_frames, n_segments);
+  return check_launch("bones_mean_kernel");
+}
+
+}  // extern "C"

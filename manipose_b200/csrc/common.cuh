@@ -1,0 +1,73 @@
+// Shared host/device helpers for libmanipose_sm100.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/manipose_sm100.h"
+
+namespace mp {
+
+// ---- error plumbing (thread-local message, negative codes, never throws/exits) -----------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);          // cudaGetLastError() -> MP_ELAUNCH
+int require_sm100();                         // current device must be compute capability 10.x
+int sm_count();
+
+#define MP_REQUIRE(cond, code, ...)                  \
+  do {                                               \
+    if (!(cond)) return ::mp::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define MP_CHECK(expr)            \
+  do {                            \
+    int _mp_rc = (expr);          \
+    if (_mp_rc != MP_OK) return _mp_rc; \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- skeleton (H36M-17 / MPI-INF-3DHP tree) as compile-time tables --------------
+constexpr int kJ = 17;
+constexpr int kBones = 16;
+__host__ __device__ constexpr int parent_of(int j) {
+  constexpr int p[kJ] = {-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15};
+  return p[j];
+}
+// t_pose_operators: axis (0 = x, 1 = y) and sign of the unit offset from the parent
+__host__ __device__ constexpr int axis_of(int j) {
+  constexpr int a[kJ] = {0, 0, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0};
+  return a[j];
+}
+__host__ __device__ constexpr float sign_of(int j) {
+  constexpr float s[kJ] = {0.f, 1.f, -1.f, -1.f, -1.f, -1.f, -1.f, 1.f, 1.f, 1.f, 1.f, -1.f, -1.f, -1.f, 1.f, 1.f, 1.f};
+  return s[j];
+}
+__host__ __device__ constexpr bool is_leaf(int j) { return j == 3 || j == 6 || j == 10 || j == 13 || j == 16; }
+
+// ---- small device utilities ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+}  // namespace mp

@@ -1,0 +1,303 @@
+// Manifold decoder forward: 6-D -> SO(3) (Gram-Schmidt) + T-pose from bone lengths + forward kinematics down the
+// 17-joint tree + softmax over the K hypotheses, one memory-bound kernel.
+//
+// Replaces (reference, paths under hpe/mh_so3_hpe/architectures/):
+//   utils/rotation_tools.py:6-57    normalize_vector / cross_product / compute_rotation_matrix_from_ortho6d
+//   pose_decoder.py:85-120          _compute_bones_length / build_t_pose_from_bone_lengths
+//   utils/forward_kinematics.py:6-48 forward_kinematics
+//   rmcl_manifold_mix_ste.py:262    scores_logits.softmax(dim=1)
+//
+// Data movement: a warp owns a tile of 32 consecutive poses = 13,056 contiguous bytes of rot6d.  One lane pulls the
+// tile into shared memory with a single bulk async copy (TMA engine, mbarrier completion); each lane then decodes ONE
+// pose reading its 102 floats as 8-byte conflict-free LDS; the 51 results go back into the same (dead) tile buffer and
+// leave with one bulk async store.  Algorithmic HBM traffic: 408 + 204 bytes per pose (+8 for logit/score).
+//
+// Arithmetic: in EXACT mode every operation is the same IEEE fp32 operation, in the same order, as the reference's
+// PyTorch CPU path (unfused mul/add/sub, sqrt, max, three divisions, sequential k-loop of the 3x3 bmm), so poses
+// are bit-identical to the oracle.  FAST mode uses rsqrt and FMA contraction (<= 1e-6 relative difference).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mp {
+namespace {
+
+constexpr int kIn = kJ * 6;    // 102 floats per pose in
+constexpr int kOut = kJ * 3;   // 51 floats per pose out
+constexpr int kTile = 32;      // poses per warp tile
+constexpr int kTileInBytes = kTile * kIn * 4;    // 13056
+constexpr int kTileOutBytes = kTile * kOut * 4;  // 6528
+constexpr int kWarpsPerCta = 4;
+
+template <bool kExact>
+struct Arith {
+  static __device__ __forceinline__ float mul(float a, float b) { return kExact ? __fmul_rn(a, b) : a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return kExact ? __fadd_rn(a, b) : a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return kExact ? __fsub_rn(a, b) : a - b; }
+  // v / max(sqrt(v.v), 1e-8)   (rotation_tools.py:6-17)
+  static __device__ __forceinline__ void normalize(float& x, float& y, float& z) {
+    if (kExact) {
+      float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      float m = fmaxf(__fsqrt_rn(s), 1e-8f);
+      x = __fdiv_rn(x, m);
+      y = __fdiv_rn(y, m);
+      z = __fdiv_rn(z, m);
+    } else {
+      float s = x * x + y * y + z * z;
+      float inv = (s >= 1e-16f) ? rsqrtf(s) : 1e8f;
+      x *= inv;
+      y *= inv;
+      z *= inv;
+    }
+  }
+  // u x v   (rotation_tools.py:21-32)
+  static __device__ __forceinline__ void cross(float u0, float u1, float u2, float v0, float v1, float v2, float& i, float& j,
+                                               float& k) {
+    i = sub(mul(u1, v2), mul(u2, v1));
+    j = sub(mul(u2, v0), mul(u0, v2));
+    k = sub(mul(u0, v1), mul(u1, v0));
+  }
+  // dot of a row with a column, torch CPU bmm order: ((a0 b0) + a1 b1) + a2 b2, each op rounded
+  static __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return add(add(mul(a0, b0), mul(a1, b1)), mul(a2, b2));
+  }
+};
+
+// Per-lane state of one pose; every index is a compile-time constant after template expansion, so all of it is
+// scalarised into registers and the live ranges follow the tree (at most ~3 world rotations alive).
+struct PoseState {
+  float rw[kJ][9];   // world rotations, row-major (leaves never stored: forward_kinematics.py:41-46)
+  float pos[kOut];   // joint positions
+  float t[kJ][2];    // T-pose x / y coordinates (z is identically 0)
+};
+
+template <bool kExact, int j>
+__device__ __forceinline__ void decode_joint(PoseState& st, const float* __restrict__ lane_in, const float* __restrict__ len) {
+  using A = Arith<kExact>;
+  // ---- 6-D -> rotation matrix with columns [x y z]  (rotation_tools.py:35-57)
+  const float2 v01 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 0);
+  const float2 v23 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 2);
+  const float2 v45 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 4);
+  float x0 = v01.x, x1 = v01.y, x2 = v23.x;
+  const float b0 = v23.y, b1 = v45.x, b2 = v45.y;
+  A::normalize(x0, x1, x2);
+  float z0, z1, z2;
+  A::cross(x0, x1, x2, b0, b1, b2, z0, z1, z2);
+  A::normalize(z0, z1, z2);
+  float y0, y1, y2;
+  A::cross(z0, z1, z2, x0, x1, x2, y0, y1, y2);
+  // local rotation, row-major: r[row][col], col 0 = x, 1 = y, 2 = z
+  const float r[9] = {x0, y0, z0, x1, y1, z1, x2, y2, z2};
+
+  if constexpr (j == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) st.rw[0][i] = r[i];
+    st.t[0][0] = 0.f;
+    st.t[0][1] = 0.f;
+    // st.pos[0..2] preset by the caller (root position)
+  } else {
+    constexpr int p = parent_of(j);
+    constexpr int ax = axis_of(j);
+    constexpr float sg = sign_of(j);
+    // T-pose by cumulative adds, offset recovered by subtraction (pose_decoder.py:115-119, forward_kinematics.py:31-33)
+    const float step = sg > 0.f ? len[j - 1] : -len[j - 1];
+    st.t[j][ax] = A::add(st.t[p][ax], step);
+    st.t[j][1 - ax] = st.t[p][1 - ax];
+    const float off = A::sub(st.t[j][ax], st.t[p][ax]);
+    const float* rp = st.rw[p];
+    if constexpr (is_leaf(j)) {
+      // only column `ax` of Rw[j] = Rw[p] R[j] is needed for the position
+#pragma unroll
+      for (int row = 0; row < 3; ++row) {
+        const float c = A::dot3(rp[row * 3 + 0], rp[row * 3 + 1], rp[row * 3 + 2], r[0 * 3 + ax], r[1 * 3 + ax], r[2 * 3 + ax]);
+        st.pos[j * 3 + row] = A::add(A::mul(c, off), st.pos[p * 3 + row]);
+      }
+    } else {
+#pragma unroll
+      for (int row = 0; row < 3; ++row) {
+#pragma unroll
+        for (int col = 0; col < 3; ++col)
+          st.rw[j][row * 3 + col] =
+              A::dot3(rp[row * 3 + 0], rp[row * 3 + 1], rp[row * 3 + 2], r[0 * 3 + col], r[1 * 3 + col], r[2 * 3 + col]);
+        st.pos[j * 3 + row] = A::add(A::mul(st.rw[j][row * 3 + ax], off), st.pos[p * 3 + row]);
+      }
+    }
+  }
+  if constexpr (j + 1 < kJ) decode_joint<kExact, j + 1>(st, lane_in, len);
+}
+
+template <bool kExact>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
+                   const float* __restrict__ logits, float* __restrict__ poses, float* __restrict__ scores, uint32_t n_poses,
+                   uint32_t poses_per_clip, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames, int bulk_ok) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw + warp * kTileInBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kWarpsPerCta * kTileInBytes) + warp;
+
+  if (lane == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+
+  const uint32_t n_tiles = (n_poses + kTile - 1) / kTile;
+  const uint32_t warp_global = blockIdx.x * kWarpsPerCta + warp;
+  const uint32_t warp_stride = gridDim.x * kWarpsPerCta;
+  uint32_t phase = 0;
+
+  for (uint32_t tile_idx = warp_global; tile_idx < n_tiles; tile_idx += warp_stride) {
+    const uint32_t pose0 = tile_idx * kTile;
+    const uint32_t n_here = min((uint32_t)kTile, n_poses - pose0);
+    const bool full = bulk_ok && (n_here == kTile);
+    const float* gin = rot6d + (size_t)pose0 * kIn;
+    float* gout = poses + (size_t)pose0 * kOut;
+
+    // ---- stage the tile of rot6d into shared memory
+    if (full) {
+      if (lane == 0) {
+        ptx::mbar_expect_tx(bar, kTileInBytes);
+        ptx::bulk_g2s(tile, gin, kTileInBytes, bar);
+      }
+      ptx::mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      for (uint32_t i = lane; i < n_here * kIn; i += 32) tile[i] = gin[i];
+      __syncwarp();
+    }
+
+    // ---- one pose per lane
+    PoseState st;
+    const uint32_t pose = pose0 + lane;
+    const bool active = lane < n_here;
+    if (active) {
+      const uint32_t clip = pose / poses_per_clip;
+      float len[kBones];
+      const float4* lp = reinterpret_cast<const float4*>(bone_len + (size_t)clip * kBones);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(lp + i);
+        len[4 * i + 0] = v.x;
+        len[4 * i + 1] = v.y;
+        len[4 * i + 2] = v.z;
+        len[4 * i + 3] = v.w;
+      }
+      if (root != nullptr) {
+        st.pos[0] = root[(size_t)pose * 3 + 0];
+        st.pos[1] = root[(size_t)pose * 3 + 1];
+        st.pos[2] = root[(size_t)pose * 3 + 2];
+      } else {
+        st.pos[0] = st.pos[1] = st.pos[2] = 0.f;
+      }
+      decode_joint<kExact, 0>(st, tile + lane * kIn, len);
+    }
+    __syncwarp();  // every lane is done reading the tile: reuse it for the output
+
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < kOut; ++i) tile[lane * kOut + i] = st.pos[i];
+    }
+    if (full) {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::bulk_s2g(gout, tile, kTileOutBytes);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();  // the buffer is about to be refilled
+      }
+      __syncwarp();
+    } else {
+      __syncwarp();
+      for (uint32_t i = lane; i < n_here * kOut; i += 32) gout[i] = tile[i];
+      __syncwarp();
+    }
+  }
+
+  // ---- hypothesis scores: softmax over K of logits[b, :, t]  (rmcl_manifold_mix_ste.py:262)
+  if (logits != nullptr) {
+    const uint32_t n_items = n_clips * n_frames;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_items; idx += gridDim.x * blockDim.x) {
+      const uint32_t b = idx / n_frames, t = idx - b * n_frames;
+      const float* lg = logits + (size_t)b * n_hyp * n_frames + t;
+      float mx = -INFINITY;
+      for (uint32_t k = 0; k < n_hyp; ++k) mx = fmaxf(mx, lg[(size_t)k * n_frames]);
+      float sum = 0.f;
+      for (uint32_t k = 0; k < n_hyp; ++k) sum += expf(lg[(size_t)k * n_frames] - mx);
+      float* sc = scores + (size_t)b * n_hyp * n_frames + t;
+      for (uint32_t k = 0; k < n_hyp; ++k) sc[(size_t)k * n_frames] = expf(lg[(size_t)k * n_frames] - mx) / sum;
+    }
+  }
+}
+
+__global__ void softmax_hyp_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ grad_scores,
+                                       float* __restrict__ grad_logits, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames) {
+  const uint32_t n_items = n_clips * n_frames;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_items; idx += gridDim.x * blockDim.x) {
+    const uint32_t b = idx / n_frames, t = idx - b * n_frames;
+    const size_t base = (size_t)b * n_hyp * n_frames + t;
+    float dot = 0.f;
+    for (uint32_t k = 0; k < n_hyp; ++k) dot += scores[base + (size_t)k * n_frames] * grad_scores[base + (size_t)k * n_frames];
+    for (uint32_t k = 0; k < n_hyp; ++k) {
+      const size_t i = base + (size_t)k * n_frames;
+      grad_logits[i] = scores[i] * (grad_scores[i] - dot);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mp
+
+extern "C" {
+
+int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root, const float* logits, float* poses,
+                   float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames, int rot_rep_dim, int flags,
+                   mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  // reference: assert rot_rep_dim in [4, 6] (pose_decoder.py:27-30)
+  MP_REQUIRE(rot_rep_dim == 4 || rot_rep_dim == 6, MP_EINVAL, "Unsupported rotations representation dimension: %d", rot_rep_dim);
+  MP_REQUIRE(rot_rep_dim == 6, MP_EUNSUPPORTED,
+             "rot_rep_dim=4 (compute_rotation_matrix_from_ortho4d) is not built: no BASELINE config uses it");
+  MP_REQUIRE(n_clips >= 0 && n_hyp >= 1 && n_frames >= 1, MP_EINVAL, "mp_decoder_fwd: bad sizes");
+  const int64_t n_poses = n_clips * n_hyp * n_frames;
+  if (n_poses == 0) return MP_OK;
+  MP_REQUIRE(n_poses < (int64_t)1 << 31, MP_EINVAL, "mp_decoder_fwd: %lld poses exceed 2^31", (long long)n_poses);
+  MP_REQUIRE(rot6d && bone_len && poses, MP_EINVAL, "mp_decoder_fwd: null pointer");
+  MP_REQUIRE((logits == nullptr) == (scores == nullptr), MP_EINVAL, "mp_decoder_fwd: logits and scores go together");
+  MP_REQUIRE(aligned16(bone_len), MP_EALIGN, "mp_decoder_fwd: bone_len must be 16-byte aligned");
+
+  const int bulk_ok = aligned16(rot6d) && aligned16(poses);
+  const size_t smem = (size_t)kWarpsPerCta * kTileInBytes + kWarpsPerCta * sizeof(uint64_t);
+  const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
+  int64_t ctas = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t max_ctas = (int64_t)sm_count() * 4;
+  if (ctas > max_ctas) ctas = max_ctas;
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(
+        rot6d, bone_len, root, logits, poses, scores, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), (uint32_t)n_clips,
+        (uint32_t)n_hyp, (uint32_t)n_frames, bulk_ok);
+  };
+  if (flags & MP_DEC_FAST)
+    launch(decoder_fwd_kernel<false>);
+  else
+    launch(decoder_fwd_kernel<true>);
+  return check_launch("decoder_fwd_kernel");
+}
+
+int mp_softmax_hyp_bwd(const float* scores, const float* grad_scores, float* grad_logits, int64_t n_clips, int64_t n_hyp,
+                       int64_t n_frames, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(scores && grad_scores && grad_logits, MP_EINVAL, "mp_softmax_hyp_bwd: null pointer");
+  const int64_t n = n_clips * n_frames;
+  if (n <= 0) return MP_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  softmax_hyp_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, grad_scores, grad_logits, (uint32_t)n_clips,
+                                                                            (uint32_t)n_hyp, (uint32_t)n_frames);
+  return check_launch("softmax_hyp_bwd_kernel");
+}
+
+}  // extern "C"

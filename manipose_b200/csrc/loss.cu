@@ -1,0 +1,553 @@
+// Winner-takes-all loss with scoring (rMCL), velocity + smoothness terms, hypothesis aggregation and MPJPE:
+// warp-tile reduction kernels, forward and backward.
+//
+// Replaces (reference, paths under hpe/mh_so3_hpe/):
+//   metrics/losses.py:14-72,104-123   weighted_mpjpe_loss / weighted_mse_loss / _l2_loss_per_hyp
+//   metrics/losses.py:126-170         wta_l2_loss_and_activate_head / wta_with_scoring_loss
+//   metrics/losses.py:75-101          mean_velocity_error
+//   metrics/regularizations.py:160-174 smoothness_regularization
+//   architectures/rmcl_manifold_mix_ste.py:121-185 poses_from_hyp_idx / aggregate
+//   metrics/mean_joint_errors.py:31-36 mpjpe_error
+//
+// Layout: hyp [B,K,T,17,3], y [B,T,17,3].  A warp owns 32 consecutive frames of one clip; for each hypothesis it
+// stages the 32(+halo) contiguous frames (204 B each) of hyp and y into shared memory with 16-byte cp.async, then lane t
+// reduces frame t reading with stride 51 floats (bank-conflict free).  Per-hypothesis errors use exactly the IEEE
+// operation sequence of PyTorch's CPU kernels (FMA chain in the 3-norm, the 8-lane sum order of its reduction, the
+// divide by 17), so winner indices are bit-identical to the oracle's on identical inputs.  Scalar terms are reduced
+// warp -> per-warp double partial -> one fixed-order finalize block (deterministic, no atomics).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mp {
+namespace {
+
+constexpr int kF = kJ * 3;                 // 51 floats per frame
+constexpr int kTileFrames = 32;
+constexpr int kStageFloats = 34 * kF + 8;  // 32 frames + halo each side + alignment shift, multiple of 4
+constexpr int kStageBytes = kStageFloats * 4;
+constexpr int kLossWarps = 8;
+constexpr int kMaxPartialWarps = 148 * 2 * kLossWarps;
+constexpr int kMaxHyp = 32;
+
+__constant__ float c_ones17[kJ] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+
+// Copies floats [g0, g0+n) of `base` (16-byte aligned, `total` floats long) into sbuf so that element g0+i lands at
+// sbuf[shift + i]; returns shift in [0,3].  Whole 16-byte chunks go through cp.async, the array tail through LDG.
+__device__ __forceinline__ int stage_floats(float* sbuf, const float* __restrict__ base, size_t g0, uint32_t n, size_t total,
+                                            int lane) {
+  const size_t a0 = g0 & ~(size_t)3;
+  const int shift = (int)(g0 - a0);
+  const uint32_t nchunks = (shift + n + 3) >> 2;
+  for (uint32_t c = lane; c < nchunks; c += 32) {
+    const size_t gi = a0 + 4 * (size_t)c;
+    if (gi + 4 <= total) {
+      ptx::cp_async16(sbuf + 4 * c, base + gi);
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (gi + q < total) sbuf[4 * c + q] = base[gi + q];
+    }
+  }
+  return shift;
+}
+__device__ __forceinline__ void stage_wait() {
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
+  __syncwarp();
+}
+
+// sum of 17 values in the order of PyTorch's CPU reduction over a contiguous inner dim of size 17:
+// 8-lane vector partials p_k = v_k + v_{k+8}, then v_16 + p_0 + p_1 + ... + p_7, left to right.
+__device__ __forceinline__ float sum17_torch_order(const float (&v)[kJ]) {
+  float acc = v[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc = __fadd_rn(acc, __fadd_rn(v[k], v[k + 8]));
+  return acc;
+}
+
+// e = mean_j w_j * ||h_j - y_j||  (unsquared) or mean_j mean_c w_j (h - y)^2 (squared), bit-exact vs torch CPU.
+template <bool kSquared>
+__device__ __forceinline__ float frame_error(const float* __restrict__ h, const float* __restrict__ yy, const float* __restrict__ w) {
+  float v[kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    const float d0 = __fsub_rn(h[j * 3 + 0], yy[j * 3 + 0]);
+    const float d1 = __fsub_rn(h[j * 3 + 1], yy[j * 3 + 1]);
+    const float d2 = __fsub_rn(h[j * 3 + 2], yy[j * 3 + 2]);
+    if (kSquared) {
+      const float q0 = __fmul_rn(w[j], __fmul_rn(d0, d0));
+      const float q1 = __fmul_rn(w[j], __fmul_rn(d1, d1));
+      const float q2 = __fmul_rn(w[j], __fmul_rn(d2, d2));
+      v[j] = __fdiv_rn(__fadd_rn(__fadd_rn(q0, q1), q2), 3.0f);
+    } else {
+      const float s = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+      v[j] = __fmul_rn(w[j], __fsqrt_rn(s));
+    }
+  }
+  return __fdiv_rn(sum17_torch_order(v), 17.0f);
+}
+
+struct LossDims {
+  uint32_t B, K, T;
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+template <bool kSquared, bool kAllTerms>
+__global__ void __launch_bounds__(kLossWarps * 32, 2)
+loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
+                const float* __restrict__ weights, LossDims d, float* __restrict__ wta_val, int64_t* __restrict__ wta_idx,
+                float* __restrict__ per_hyp, double* __restrict__ partials) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ybuf = reinterpret_cast<float*>(smem_raw + (size_t)warp * 2 * kStageBytes);
+  float* hbuf = ybuf + kStageFloats;
+
+  float w[kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) w[j] = weights ? weights[j] : c_ones17[j];
+
+  const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
+  const uint32_t n_items = d.B * tiles_per_clip;
+  const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
+  double acc_wta = 0, acc_bce = 0, acc_vel = 0, acc_sm = 0;
+
+  for (uint32_t item = blockIdx.x * kLossWarps + warp; item < n_items; item += gridDim.x * kLossWarps) {
+    const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kTileFrames;
+    const uint32_t nf = min((uint32_t)kTileFrames, d.T - t0);
+    const uint32_t nload = kAllTerms ? min((uint32_t)kTileFrames + 1, d.T - t0) : nf;
+    const bool valid = lane < nf;
+    const bool has_next = kAllTerms && (t0 + lane + 1 < d.T);
+
+    __syncwarp();
+    const int sy = stage_floats(ybuf, y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
+    float best = INFINITY, vel = 0.f, sm = 0.f;
+    int best_k = 0;
+    for (uint32_t k = 0; k < d.K; ++k) {
+      __syncwarp();
+      const int sh = stage_floats(hbuf, hyp, (((size_t)b * d.K + k) * d.T + t0) * kF, nload * kF, h_total, lane);
+      stage_wait();
+      if (valid) {
+        const float* hp = hbuf + sh + lane * kF;
+        const float* yp = ybuf + sy + lane * kF;
+        const float e = frame_error<kSquared>(hp, yp, w);
+        if (per_hyp) per_hyp[((size_t)b * d.K + k) * d.T + t0 + lane] = e;
+        if (k == 0 || e < best) {  // torch.min(dim=1): lowest index on ties
+          best = e;
+          best_k = (int)k;
+        }
+        if (has_next) {
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float dvh = hp[kF + j * 3 + c] - hp[j * 3 + c];
+              const float dv = dvh - (yp[kF + j * 3 + c] - yp[j * 3 + c]);
+              q = fmaf(dv, dv, q);
+              sm = fmaf(w[j] * dvh, dvh, sm);
+            }
+            vel += kSquared ? q : sqrtf(q);
+          }
+        }
+      }
+    }
+    float bce = 0.f;
+    if (valid) {
+      wta_val[(size_t)b * d.T + t0 + lane] = best;
+      wta_idx[(size_t)b * d.T + t0 + lane] = best_k;
+      if (kAllTerms && scores) {
+        for (uint32_t k = 0; k < d.K; ++k) {
+          const float s = scores[((size_t)b * d.K + k) * d.T + t0 + lane];
+          // F.binary_cross_entropy: log terms clamped at -100
+          bce -= ((int)k == best_k) ? fmaxf(logf(s), -100.f) : fmaxf(logf(1.f - s), -100.f);
+        }
+      }
+    } else {
+      best = 0.f;
+    }
+    if (kAllTerms) {
+      const float r0 = warp_sum(best), r1 = warp_sum(bce), r2 = warp_sum(vel), r3 = warp_sum(sm);
+      acc_wta += r0;
+      acc_bce += r1;
+      acc_vel += r2;
+      acc_sm += r3;
+    }
+  }
+  if (kAllTerms && lane == 0) {
+    double* p = partials + (size_t)(blockIdx.x * kLossWarps + warp) * 4;
+    p[0] = acc_wta;
+    p[1] = acc_bce;
+    p[2] = acc_vel;
+    p[3] = acc_sm;
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ partials, int n_partials, LossDims d, int squared, float beta,
+                                     float vel_w, float smooth_w, float* __restrict__ terms) {
+  __shared__ double red[4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double a[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n_partials; i += blockDim.x)
+    for (int q = 0; q < 4; ++q) a[q] += partials[(size_t)i * 4 + q];
+  for (int q = 0; q < 4; ++q) {
+    for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    if (lane == 0) red[q][warp] = a[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 4; ++q)
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s[q] += red[q][i];
+    const double bt = (double)d.B * d.T, bkt = bt * d.K, pairs = (double)d.B * d.K * (d.T - 1.0) * kJ;
+    const float wta = (float)(s[0] / bt);
+    const float bce = (float)(s[1] / bkt);
+    const float vel = (float)(s[2] / (squared ? pairs * 3.0 : pairs));
+    const float smo = (float)(s[3] / (pairs * 3.0));
+    terms[MP_TERM_WTA] = wta;
+    terms[MP_TERM_BCE] = bce;
+    terms[MP_TERM_VEL] = vel;
+    terms[MP_TERM_SMOOTH] = smo;
+    // make_loss / compute_and_acc_loss (hpe/main_h36m_lifting.py:101-209): terms with weight <= 0 are not added
+    float total = wta;
+    if (beta != 0.f) total += beta * bce;
+    if (vel_w > 0.f) total += vel_w * vel;
+    if (smooth_w > 0.f) total += smooth_w * smo;
+    terms[MP_TERM_TOTAL] = total;
+    terms[5] = terms[6] = terms[7] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <bool kSquared>
+__global__ void __launch_bounds__(kLossWarps * 32, 2)
+loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
+                const float* __restrict__ weights, const int64_t* __restrict__ wta_idx, LossDims d, float beta, float vel_w,
+                float smooth_w, const float* __restrict__ grad_total, float* __restrict__ grad_hyp,
+                float* __restrict__ grad_scores) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ybuf = reinterpret_cast<float*>(smem_raw + (size_t)warp * 2 * kStageBytes);
+  float* hbuf = ybuf + kStageFloats;
+
+  float w[kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) w[j] = weights ? weights[j] : c_ones17[j];
+
+  const float gt = grad_total ? grad_total[0] : 1.f;
+  const double bt = (double)d.B * d.T, pairs = (double)d.B * d.K * (d.T - 1.0) * kJ;
+  const float c_wta = kSquared ? (float)(gt * 2.0 / (bt * kJ * 3.0)) : (float)(gt / (bt * kJ));
+  const float c_vel = vel_w > 0.f ? (kSquared ? (float)(gt * vel_w * 2.0 / (pairs * 3.0)) : (float)(gt * vel_w / pairs)) : 0.f;
+  const float c_sm = smooth_w > 0.f ? (float)(gt * smooth_w * 2.0 / (pairs * 3.0)) : 0.f;
+  const float c_bce = beta != 0.f ? (float)(gt * beta / (bt * d.K)) : 0.f;
+
+  const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
+  const uint32_t n_items = d.B * tiles_per_clip;
+  const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
+
+  for (uint32_t item = blockIdx.x * kLossWarps + warp; item < n_items; item += gridDim.x * kLossWarps) {
+    const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kTileFrames;
+    const uint32_t nf = min((uint32_t)kTileFrames, d.T - t0);
+    const uint32_t lo = t0 > 0 ? t0 - 1 : 0, hi = min(d.T, t0 + kTileFrames + 1);
+    const uint32_t t = t0 + lane;
+    const bool valid = lane < nf;
+    const bool has_prev = valid && t >= 1, has_next = valid && (t + 1 < d.T);
+    const int64_t kstar = valid ? wta_idx[(size_t)b * d.T + t] : -1;
+
+    __syncwarp();
+    const int sy = stage_floats(ybuf, y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
+    for (uint32_t k = 0; k < d.K; ++k) {
+      __syncwarp();
+      const int sh = stage_floats(hbuf, hyp, (((size_t)b * d.K + k) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+      stage_wait();
+      float g[kF];
+      if (valid) {
+        const float* hc = hbuf + sh + (t - lo) * kF;
+        const float* yc = ybuf + sy + (t - lo) * kF;
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) {
+          float gj[3] = {0.f, 0.f, 0.f};
+          if ((int64_t)k == kstar) {
+            const float d0 = hc[j * 3 + 0] - yc[j * 3 + 0], d1 = hc[j * 3 + 1] - yc[j * 3 + 1], d2 = hc[j * 3 + 2] - yc[j * 3 + 2];
+            if (kSquared) {
+              gj[0] = c_wta * w[j] * d0;
+              gj[1] = c_wta * w[j] * d1;
+              gj[2] = c_wta * w[j] * d2;
+            } else {
+              const float n = sqrtf(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
+              const float r = n > 0.f ? c_wta * w[j] / n : 0.f;
+              gj[0] = r * d0;
+              gj[1] = r * d1;
+              gj[2] = r * d2;
+            }
+          }
+          if (has_next) {  // pair (t, t+1): this frame enters with a minus sign
+            float dvh[3], dv[3], q = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              dvh[c] = hc[kF + j * 3 + c] - hc[j * 3 + c];
+              dv[c] = dvh[c] - (yc[kF + j * 3 + c] - yc[j * 3 + c]);
+              q = fmaf(dv[c], dv[c], q);
+            }
+            const float n = sqrtf(q);
+            const float r = kSquared ? c_vel : (n > 0.f ? c_vel / n : 0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gj[c] -= r * dv[c] + c_sm * w[j] * dvh[c];
+          }
+          if (has_prev) {  // pair (t-1, t): plus sign
+            float dvh[3], dv[3], q = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              dvh[c] = hc[j * 3 + c] - hc[j * 3 + c - kF];
+              dv[c] = dvh[c] - (yc[j * 3 + c] - yc[j * 3 + c - kF]);
+              q = fmaf(dv[c], dv[c], q);
+            }
+            const float n = sqrtf(q);
+            const float r = kSquared ? c_vel : (n > 0.f ? c_vel / n : 0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gj[c] += r * dv[c] + c_sm * w[j] * dvh[c];
+          }
+          g[j * 3 + 0] = gj[0];
+          g[j * 3 + 1] = gj[1];
+          g[j * 3 + 2] = gj[2];
+        }
+        if (grad_scores) {
+          const size_t si = ((size_t)b * d.K + k) * d.T + t;
+          const float s = scores[si];
+          const float tgt = ((int64_t)k == kstar) ? 1.f : 0.f;
+          // binary_cross_entropy_backward: (input - target) / max((1 - input) * input, 1e-12)
+          grad_scores[si] = c_bce * (s - tgt) / fmaxf((1.f - s) * s, 1e-12f);
+        }
+      }
+      __syncwarp();  // all lanes done reading hbuf: reuse it to transpose the gradient tile
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < kF; ++i) hbuf[lane * kF + i] = g[i];
+      }
+      __syncwarp();
+      float* gout = grad_hyp + (((size_t)b * d.K + k) * d.T + t0) * kF;
+      for (uint32_t i = lane; i < nf * kF; i += 32) gout[i] = hbuf[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ aggregation
+__global__ void aggregate_weighted_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out,
+                                          uint32_t B, uint32_t K, uint32_t T) {
+  // torch.sum(hyp * scores.unsqueeze(-1), dim=1): products rounded, accumulated k = 0..K-1 left to right
+  const size_t n = (size_t)B * T * kF;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bt = i / kF;
+    const uint32_t e = (uint32_t)(i - bt * kF);
+    const uint32_t b = (uint32_t)(bt / T), t = (uint32_t)(bt - (size_t)b * T);
+    float acc = 0.f;
+    for (uint32_t k = 0; k < K; ++k) {
+      const size_t f = ((size_t)b * K + k) * T + t;
+      acc = __fadd_rn(acc, __fmul_rn(hyp[f * kF + e], scores[f]));
+    }
+    out[i] = acc;
+  }
+}
+
+__global__ void argmax_score_kernel(const float* __restrict__ scores, int64_t* __restrict__ idx, uint32_t B, uint32_t K, uint32_t T) {
+  const size_t n = (size_t)B * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t b = (uint32_t)(i / T), t = (uint32_t)(i - (size_t)b * T);
+    float best = scores[((size_t)b * K) * T + t];
+    int bk = 0;
+    for (uint32_t k = 1; k < K; ++k) {
+      const float s = scores[((size_t)b * K + k) * T + t];
+      if (s > best) {  // torch.argmax: first maximal index
+        best = s;
+        bk = (int)k;
+      }
+    }
+    idx[i] = bk;
+  }
+}
+
+__global__ void gather_hyp_kernel(const float* __restrict__ hyp, const int64_t* __restrict__ idx, float* __restrict__ out, uint32_t B,
+                                  uint32_t K, uint32_t T) {
+  const size_t n = (size_t)B * T * kF;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bt = i / kF;
+    const uint32_t e = (uint32_t)(i - bt * kF);
+    const uint32_t b = (uint32_t)(bt / T), t = (uint32_t)(bt - (size_t)b * T);
+    const int64_t k = idx[bt];
+    out[i] = hyp[(((size_t)b * K + (size_t)k) * T + t) * kF + e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MPJPE
+constexpr int kMpjpeBlocks = 148 * 4;
+__global__ void mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ gt, size_t n_points,
+                                     double* __restrict__ partials) {
+  __shared__ double red[8];
+  double acc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (size_t)gridDim.x * blockDim.x) {
+    const float d0 = gt[i * 3 + 0] - pred[i * 3 + 0], d1 = gt[i * 3 + 1] - pred[i * 3 + 1], d2 = gt[i * 3 + 2] - pred[i * 3 + 2];
+    acc += (double)__fsqrt_rn(__fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    partials[blockIdx.x] = s;
+  }
+}
+__global__ void mpjpe_finalize_kernel(const double* __restrict__ partials, int n, double n_points, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += partials[i];
+    out[0] = (float)s;
+    out[1] = (float)(s / n_points);
+  }
+}
+
+int check_dims(const char* who, int64_t B, int64_t K, int64_t T) {
+  MP_REQUIRE(B >= 1 && K >= 1 && T >= 1, MP_EINVAL, "%s: bad sizes B=%lld K=%lld T=%lld", who, (long long)B, (long long)K, (long long)T);
+  MP_REQUIRE(K <= kMaxHyp, MP_EINVAL, "%s: n_hyp=%lld exceeds %d", who, (long long)K, kMaxHyp);
+  MP_REQUIRE(B * K * T * kF < ((int64_t)1 << 40) && B * T < ((int64_t)1 << 31), MP_EINVAL, "%s: tensor too large", who);
+  return MP_OK;
+}
+
+int loss_grid(int64_t B, int64_t T) {
+  const int64_t items = B * ((T + kTileFrames - 1) / kTileFrames);
+  int64_t ctas = (items + kLossWarps - 1) / kLossWarps;
+  const int64_t cap = (int64_t)sm_count() * 2;
+  return (int)(ctas < cap ? ctas : cap);
+}
+
+}  // namespace
+}  // namespace mp
+
+extern "C" {
+
+size_t mp_loss_workspace_bytes(int64_t, int64_t, int64_t) { return (size_t)mp::kMaxPartialWarps * 4 * sizeof(double); }
+
+int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int squared, float* wta_val, int64_t* wta_idx,
+               float* per_hyp, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_CHECK(check_dims("mp_wta_fwd", B, K, T));
+  MP_REQUIRE(hyp && y && wta_val && wta_idx, MP_EINVAL, "mp_wta_fwd: null pointer");
+  MP_REQUIRE(aligned16(hyp) && aligned16(y), MP_EALIGN, "mp_wta_fwd: hyp and y must be 16-byte aligned");
+  // reference quirk (losses.py:57-58,126-138): squared + weights=None makes _l2_loss_per_hyp a 0-d tensor and
+  // torch.min(dim=1) raises; keep that an error instead of inventing semantics.
+  MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
+             "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
+  const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
+  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
+  const int grid = loss_grid(B, T);
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
+  };
+  if (squared)
+    launch(loss_fwd_kernel<true, false>);
+  else
+    launch(loss_fwd_kernel<false, false>);
+  return check_launch("loss_fwd_kernel(wta)");
+}
+
+int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const float* joint_weights, int squared, float beta,
+                float vel_w, float smooth_w, float* terms, float* wta_val, int64_t* wta_idx, int64_t B, int64_t K, int64_t T,
+                void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_CHECK(check_dims("mp_loss_fwd", B, K, T));
+  MP_REQUIRE(hyp && y && terms && wta_val && wta_idx && workspace, MP_EINVAL, "mp_loss_fwd: null pointer");
+  MP_REQUIRE(beta == 0.f || scores != nullptr, MP_EINVAL, "mp_loss_fwd: scores required when beta != 0");
+  MP_REQUIRE(aligned16(hyp) && aligned16(y) && aligned16(workspace), MP_EALIGN, "mp_loss_fwd: pointers must be 16-byte aligned");
+  MP_REQUIRE(workspace_bytes >= mp_loss_workspace_bytes(B, K, T), MP_EWORKSPACE, "mp_loss_fwd: workspace too small");
+  MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
+             "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
+  const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
+  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
+  const int grid = loss_grid(B, T);
+  double* partials = reinterpret_cast<double*>(workspace);
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, d, wta_val, wta_idx, nullptr, partials);
+  };
+  if (squared)
+    launch(loss_fwd_kernel<true, true>);
+  else
+    launch(loss_fwd_kernel<false, true>);
+  MP_CHECK(check_launch("loss_fwd_kernel"));
+  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid * kLossWarps, d, squared, beta, vel_w, smooth_w, terms);
+  return check_launch("loss_finalize_kernel");
+}
+
+int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const float* joint_weights, const int64_t* wta_idx,
+                int squared, float beta, float vel_w, float smooth_w, const float* grad_total, float* grad_hyp,
+                float* grad_scores, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_CHECK(check_dims("mp_loss_bwd", B, K, T));
+  MP_REQUIRE(hyp && y && wta_idx && grad_hyp, MP_EINVAL, "mp_loss_bwd: null pointer");
+  MP_REQUIRE(grad_scores == nullptr || scores != nullptr, MP_EINVAL, "mp_loss_bwd: scores required for grad_scores");
+  MP_REQUIRE(aligned16(hyp) && aligned16(y), MP_EALIGN, "mp_loss_bwd: hyp and y must be 16-byte aligned");
+  const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
+  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
+  const int grid = loss_grid(B, T);
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
+                                                                   grad_total, grad_hyp, grad_scores);
+  };
+  if (squared)
+    launch(loss_bwd_kernel<true>);
+  else
+    launch(loss_bwd_kernel<false>);
+  return check_launch("loss_bwd_kernel");
+}
+
+int mp_aggregate(const float* hyp, const float* scores, const float* y, int mode, float* out_pose, float* out_val,
+                 int64_t* out_idx, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_CHECK(check_dims("mp_aggregate", B, K, T));
+  MP_REQUIRE(hyp && out_pose, MP_EINVAL, "mp_aggregate: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)B * T * kF;
+  const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 8 ? (n + 255) / 256 : (size_t)sm_count() * 8);
+  if (mode == MP_AGG_WEIGHTED_AVE) {
+    MP_REQUIRE(scores != nullptr, MP_EINVAL, "Scores required to compute weighted hypothesis average.");
+    aggregate_weighted_kernel<<<blocks, 256, 0, s>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    return check_launch("aggregate_weighted_kernel");
+  }
+  MP_REQUIRE(out_idx != nullptr, MP_EINVAL, "mp_aggregate: out_idx required for best_score / oracle");
+  if (mode == MP_AGG_BEST_SCORE) {
+    MP_REQUIRE(scores != nullptr, MP_EINVAL, "Scores required to compute hypothesis with best confidence.");
+    const int b2 = (int)(((size_t)B * T + 255) / 256);
+    argmax_score_kernel<<<b2 < sm_count() * 8 ? b2 : sm_count() * 8, 256, 0, s>>>(scores, out_idx, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    MP_CHECK(check_launch("argmax_score_kernel"));
+  } else if (mode == MP_AGG_ORACLE) {
+    MP_REQUIRE(y != nullptr && out_val != nullptr, MP_EINVAL, "Ground-truth required to compute best hypothesis.");
+    MP_CHECK(mp_wta_fwd(hyp, y, nullptr, 0, out_val, out_idx, nullptr, B, K, T, stream));
+  } else {
+    return fail(MP_EINVAL, "Only best_score and weighted_ave modes are implemented.Got %d.", mode);
+  }
+  gather_hyp_kernel<<<blocks, 256, 0, s>>>(hyp, out_idx, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+  return check_launch("gather_hyp_kernel");
+}
+
+size_t mp_mpjpe_workspace_bytes(int64_t) { return (size_t)mp::kMpjpeBlocks * sizeof(double); }
+
+int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, void* workspace, size_t workspace_bytes,
+             mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(pred && gt && out && workspace && n_points >= 1, MP_EINVAL, "mp_mpjpe: bad arguments");
+  MP_REQUIRE(workspace_bytes >= mp_mpjpe_workspace_bytes(n_points), MP_EWORKSPACE, "mp_mpjpe: workspace too small");
+  int blocks = (int)((n_points + 255) / 256);
+  if (blocks > kMpjpeBlocks) blocks = kMpjpeBlocks;
+  double* partials = reinterpret_cast<double*>(workspace);
+  mpjpe_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+  MP_CHECK(check_launch("mpjpe_partial_kernel"));
+  mpjpe_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, blocks, (double)n_points, out);
+  return check_launch("mpjpe_finalize_kernel");
+}
+
+}  // extern "C"
