@@ -1,0 +1,296 @@
+"""Headline benchmark: T=243 H36M-shape lifted frames/sec (BASELINE.json) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips B] [--impl reference]
+
+A step is one pass of the lifting hot path (RMCLManifoldMixSTE.forward: MixSTE backbone -> K=5 hypothesis heads ->
+manifold decoder + hypothesis softmax) over one batch of B synthetic clips of T=243 frames, random-init weights
+(hpe/conf/config.yaml defaults, seed 42).  BASELINE config 3 (B=1024, bf16 backbone, fp32 decoder).  Multi-GPU:
+one process per GPU (torchrun), clips sharded, NO collective on the data path; weak scaling (B clips per GPU).
+
+The one JSON line carries: value (device-resident inputs), e2e (pinned-host inputs, H2D + forward + D2H of poses/scores
+inside the timed region), roofline for the dominant kernel (the tcgen05 GEMM, sampled with CUDA events inside the timed
+region) and cpu_baseline (the reference algorithm — oracle/manipose_oracle.py, a PyTorch-CPU restatement pinned to the
+reference — timed on the host cores on a bounded sample).  --impl reference times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T, J, K = 243, 17, 5
+METRIC = "lifted_frames_per_sec_T243_H36M"
+UNIT = "frames/s"
+
+
+def flops_per_frame(t=T, k=K):
+    """Closed form of SURVEY.md §8(d) / BASELINE.md §3 (matmul flops of one forward, per lifted frame)."""
+    return (17 * 8 * 2 * (16 * 512 ** 2) + 17 * 8 * (4 * 17 * 512 + 4 * t * 512)
+            + 16 * 2 * 2 * (16 * 128 ** 2) + 16 * 2 * (4 * 16 * 128 + 4 * t * 128)
+            + (17 * 2 * 2 * 512 + 2 * 34 * 2048) + k * (17 * 2 * 512 * 7 + 2 * 17) + 16 * 2 * 128)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def _oracle_setup(seed=42):
+    import torch
+    from oracle import manipose_oracle as O
+    sd = O.make_state_dict(num_frame=T, n_hyp=K, seed=seed)
+    return O, sd
+
+
+def cpu_forward_rate(clips, reps, warm=True, budget_s=25.0):
+    """Reference algorithm on the host cores: frames/s of rmcl_forward on `clips` synthetic clips (fp32, all threads)."""
+    import torch
+    O, sd = _oracle_setup()
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = 0.3 * torch.randn(clips, T, J, 2, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        if warm:
+            O.rmcl_forward(x[:1], sd)
+        best, t_start, done = None, time.perf_counter(), 0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.rmcl_forward(x, sd)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            done += 1
+            if time.perf_counter() - t_start > budget_s:
+                break
+    return clips * T / best, torch.get_num_threads(), done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    clips = 4
+    import torch
+    O, sd = _oracle_setup()
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = 0.3 * torch.randn(clips, T, J, 2, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.rmcl_forward(x[:1], sd)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.rmcl_forward(x, sd)
+        dt = time.perf_counter() - t0
+    value = clips * T * args.steps / dt
+    sample = f"{clips} clips x {T} frames per step (of the {args.clips}-clip workload), fp32, torch CPU, {torch.get_num_threads()} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1000.0, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ManiPose H36M lifting forward, T={T}, K={K}, J={J}, {args.clips} clips/GPU (BASELINE config 3)",
+                       "reference_arm": "reference algorithm restated in oracle/manipose_oracle.py (pinned to the unmodified reference; "
+                                        "the reference itself is Python and needs timm/mup/.cuda() shims, SURVEY.md §8c)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from manipose_b200 import _build
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "manipose_b200", "libmanipose_sm100.so")):
+        _build.build(verbose=False)
+    if world > 1:
+        dist.barrier()
+    import manipose_b200 as mb
+    from manipose_b200 import ops
+
+    torch.manual_seed(42)
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=T, n_hyp=K, drop_path_rate=0.1)
+    model = model.to(dev).eval()
+    if args.micro_batch_clips:
+        model.rotations_module.micro_batch_tokens = args.micro_batch_clips * T * J
+        model.segments_module.micro_batch_tokens = args.micro_batch_clips * T * J
+    B = args.clips
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = (0.3 * torch.randn(B, T, J, 2, generator=gen)).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = (torch.empty((B, K, T, J, 3), dtype=torch.float32).pin_memory(), torch.empty((B, K, T, 1), dtype=torch.float32).pin_memory())
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident():
+        with torch.no_grad():
+            return model(x_dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            poses, scores = model(xd)
+            out_host[0].copy_(poses, non_blocking=True)
+            out_host[1].copy_(scores, non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # ---- device-resident throughput, with the GEMM of every 16th micro-batch bracketed by CUDA events
+    sampled = []
+    orig_trunk = type(model.rotations_module).trunk
+    counter = {"n": 0}
+
+    def trunk_sampled(self, x2d, n_clips):
+        counter["n"] += 1
+        ops.GEMM_TIMING = sampled if counter["n"] % 16 == 1 else None
+        try:
+            return orig_trunk(self, x2d, n_clips)
+        finally:
+            ops.GEMM_TIMING = None
+
+    model.rotations_module.trunk = trunk_sampled.__get__(model.rotations_module)
+    launches0 = ops.LAUNCHES
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES - launches0
+    del model.rotations_module.trunk
+    frames = B * T * world
+    value = frames * args.steps / (ms / 1000.0)
+
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in sampled)
+    gemm_flops = sum(f for _, _, f in sampled)
+    peaks = measured_peaks()
+    achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    step_tflops = flops_per_frame() * B * T * args.steps / (ms / 1000.0) / 1e12   # per GPU (max-over-ranks time)
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = frames * args.steps / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        cpu_value, cpu_threads, cpu_reps = cpu_forward_rate(clips=4, reps=3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"ManiPose H36M lifting forward (RMCLManifoldMixSTE, config.yaml defaults), T={T}, K={K}, J={J}, "
+                                   f"{B} clips/GPU = BASELINE config 3; bf16 backbone (fp32 accumulate), fp32 decoder",
+                       "clips_per_gpu": B, "frames_per_step": frames, "parallelism": f"clip-sharded x{world}, no collective",
+                       "micro_batch_clips": model.rotations_module.clips_per_micro_batch(),
+                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                       "gflop_per_frame": flops_per_frame() / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": (out_host[0].numel() + out_host[1].numel()) * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all 4 Linear shapes of the blocks)",
+                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_sustained"] if achieved else 0.0, "traffic": None,
+                         "peak_source": f"{peaks['src']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})",
+                         "sampled_launches": len(sampled), "gemm_share_of_step": None,
+                         "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
+                                        "flops": "algorithmic matmul flops of the whole forward / step time"}},
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": f"best of {cpu_reps} passes over 4 clips x {T} frames (972 frames) of the same workload, fp32, torch CPU"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=1024, help="clips per GPU per step (BASELINE config 3: 1024)")
+    ap.add_argument("--micro-batch-clips", type=int, default=0)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,9 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
 int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_poses,
                    float* grad_rot6d, float* grad_bone_len, float* grad_root, int64_t n_clips,
                    int64_t n_hyp, int64_t n_frames, int rot_rep_dim, mp_stream_t stream);
+/* softmax over n_hyp alone (scores_logits.softmax(dim=1), rmcl_manifold_mix_ste.py:262); [n_clips, n_hyp, n_frames]. */
+int mp_softmax_hyp_fwd(const float* logits, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames,
+                       mp_stream_t stream);
 /* softmax over n_hyp backward: grad_logits = s * (g - sum_k s g); all [n_clips, n_hyp, n_frames]. */
 int mp_softmax_hyp_bwd(const float* scores, const float* grad_scores, float* grad_logits,
                        int64_t n_clips, int64_t n_hyp, int64_t n_frames, mp_stream_t stream);
@@ -96,11 +99,14 @@ int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const flo
                 int squared, float beta, float vel_w, float smooth_w, float* terms, float* wta_val,
                 int64_t* wta_idx, int64_t B, int64_t K, int64_t T, void* workspace,
                 size_t workspace_bytes, mp_stream_t stream);
-/* Gradient of grad_total * MP_TERM_TOTAL w.r.t. hyp and scores (wta_idx from mp_loss_fwd). */
+/* Reverse mode of mp_loss_fwd w.r.t. hyp and scores (wta_idx from mp_loss_fwd; beta/vel_w/smooth_w the same).
+ *   grad_terms  [MP_LOSS_NTERMS] device fp32: upstream gradient w.r.t. terms[WTA, BCE, VEL, SMOOTH, TOTAL]
+ *   grad_wta_val[B,T] or NULL: additional upstream gradient w.r.t. the per-frame wta_val output
+ *   grad_scores [B,K,T] or NULL */
 int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const float* joint_weights,
                 const int64_t* wta_idx, int squared, float beta, float vel_w, float smooth_w,
-                const float* grad_total, float* grad_hyp, float* grad_scores, int64_t B, int64_t K,
-                int64_t T, mp_stream_t stream);
+                const float* grad_terms, const float* grad_wta_val, float* grad_hyp, float* grad_scores,
+                int64_t B, int64_t K, int64_t T, mp_stream_t stream);
 
 /* RMCLManifoldMixSTE.aggregate (rmcl_manifold_mix_ste.py:141-185) + poses_from_hyp_idx (:121-139). */
 enum { MP_AGG_WEIGHTED_AVE = 0, MP_AGG_BEST_SCORE = 1, MP_AGG_ORACLE = 2 };
@@ -122,7 +128,7 @@ int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, v
  * mix_ste.py:209-222 (fc1/fc2), :257,:280 (qkv/proj).  tcgen05.mma + TMEM accumulators + TMA.
  *   MP_EPI_BIAS: bias only; MP_EPI_GELU: exact-erf GELU (nn.GELU, mix_ste.py:200);
  *   MP_EPI_RESIDUAL: Y = resid[M,N] (bf16) + A W^T + bias  (Block.forward, mix_ste.py:352-358).
- * K % 64 == 0, N % 64 == 0; lda/ldw/ldy = row strides in elements (16-byte aligned rows). */
+ * K % 64 == 0, N % 128 == 0; A, W, resid and Y are dense row-major (row strides K, K, N, N); Y may alias resid. */
 enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2 };
 int mp_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* Y,
                  int64_t M, int64_t N, int64_t K, int epilogue, mp_stream_t stream);

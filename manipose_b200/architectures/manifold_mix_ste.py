@@ -1,0 +1,81 @@
+"""Single-hypothesis constrained model and the bone-length backbone
+(hpe/mh_so3_hpe/architectures/manifold_mix_ste.py:10-154)."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .mix_ste import MixSTE
+from .pose_decoder import PoseDecoder
+
+
+class BonesMixSTE(MixSTE):
+    """manifold_mix_ste.py:91-154: Linear(J*in -> S*C) per frame, MixSTE over S segment tokens, LN + Linear(C -> 1), mean over time."""
+
+    def __init__(self, num_frame=243, num_joints=17, num_bones=16, in_chans=2, out_dim=1, embed_dim=128, depth=2, num_heads=8,
+                 mlp_ratio=2, qkv_bias=True, qk_scale=None, drop_rate=0, attn_drop_rate=0, drop_path_rate=0.2, norm_layer=None,
+                 mup=False):
+        super().__init__(num_frame=num_frame, num_joints=num_bones, in_chans=in_chans, out_dim=out_dim, embed_dim=embed_dim,
+                         depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                         drop_rate=drop_rate, attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer,
+                         mup=mup)
+        self.num_joints = num_joints
+        self.num_bones = num_bones
+        self.embed_dim = embed_dim
+        self.Spatial_patch_to_embedding = nn.Identity()
+        self.joints_to_segments_proj = nn.Linear(in_features=num_joints * in_chans, out_features=num_bones * embed_dim)
+        self._head_ws = None
+
+    def _embed(self, x2d, n_clips, n_frames, x, h):
+        blk0 = self.STEblocks[0]
+        ops.embed_segments(x2d, self.joints_to_segments_proj.weight, self.joints_to_segments_proj.bias, self.Spatial_pos_embed,
+                           blk0.norm1.weight, blk0.norm1.bias, blk0.norm1.eps, x, h, n_clips * n_frames,
+                           self.joints_to_segments_proj.in_features, self.num_bones, self.embed_dim)
+
+    def bone_lengths_into(self, x2d: torch.Tensor, n_clips: int, out: torch.Tensor) -> None:
+        """One micro-batch: x2d fp32 [n_clips, L, J, in] -> out fp32 [n_clips, S] (signed, no activation)."""
+        feat = self.trunk(x2d, n_clips)
+        n_tokens = feat.shape[0]
+        if self._head_ws is None or self._head_ws.numel() < n_tokens or self._head_ws.device != feat.device:
+            self._head_ws = torch.empty(n_tokens, dtype=torch.float32, device=feat.device)
+        norm, lin = self.head[0], self.head[1]
+        ops.bones_head(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, norm.weight, norm.bias,
+                       lin.weight, lin.bias, out, n_clips, self.num_frame, self.num_bones, self.embed_dim, self._head_ws)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        ops._need_cuda(x)
+        b, l, j, _ = self._check_input(x)
+        x = ops._f32(x)
+        out = torch.empty((b, self.num_bones), dtype=torch.float32, device=x.device)
+        mb = self.clips_per_micro_batch()
+        for s in range(0, b, mb):
+            n = min(mb, b - s)
+            self.bone_lengths_into(x[s:s + n], n, out[s:s + n])
+        return out.unsqueeze(-1)
+
+
+class ManifoldMixSTE(nn.Module):
+    """manifold_mix_ste.py:10-88: rotations backbone + bone-length backbone + manifold decoder (one hypothesis)."""
+
+    def __init__(self, skeleton, num_frame=243, num_joints=17, num_bones=16, in_chans=2, rot_rep_dim=6, embed_dim_rot=512,
+                 depth_rot=8, num_heads_rot=8, embed_dim_seg=128, depth_seg=2, num_heads_seg=8, mlp_ratio=2.0, qkv_bias=True,
+                 qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
+        super().__init__()
+        self.num_joints = num_joints
+        self.rotations_module = MixSTE(num_frame=num_frame, num_joints=num_joints, in_chans=in_chans, out_dim=rot_rep_dim,
+                                       embed_dim=embed_dim_rot, depth=depth_rot, num_heads=num_heads_rot, mlp_ratio=mlp_ratio,
+                                       qkv_bias=qkv_bias, qk_scale=qk_scale, drop_rate=drop_rate, attn_drop_rate=attn_drop_rate,
+                                       drop_path_rate=drop_path_rate, norm_layer=norm_layer, mup=mup)
+        self.segments_module = BonesMixSTE(num_frame=num_frame, num_joints=num_joints, num_bones=num_bones, in_chans=in_chans,
+                                           out_dim=1, embed_dim=embed_dim_seg, depth=depth_seg, num_heads=num_heads_seg,
+                                           mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop_rate=drop_rate,
+                                           attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer,
+                                           mup=mup)
+        self.decoder = PoseDecoder(skeleton=skeleton, rot_rep_dim=rot_rep_dim)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        b, l, _, _ = x.shape
+        rotations = self.rotations_module(x)            # (B, L, J, D)
+        bones_lengths = self.segments_module(x)         # (B, S, 1)
+        poses = self.decoder(rotations_repr=rotations.reshape(b * l, self.num_joints, -1), bones_lengths_repr=bones_lengths,
+                             root_positions=None)
+        return poses.reshape(b, l, self.num_joints, 3)

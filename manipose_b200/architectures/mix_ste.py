@@ -1,0 +1,255 @@
+"""MixSTE backbone behind the reference's nn.Module surface (hpe/mh_so3_hpe/architectures/mix_ste.py:12-368).
+
+The module tree (``STEblocks.{i}.attn.qkv`` ...) exists so that ``state_dict()`` / ``load_state_dict()`` /
+``Adam(model.parameters())`` interoperate with the reference (290 tensors).  The arithmetic does not
+go through ``nn.Linear``: ``MixSTE.trunk`` drives the sm_100a kernels of libmanipose_sm100.so over ONE activation
+layout, [clip, frame, token, C] in bf16:
+
+    embed (+spatial pos-embed, +norm1)                                  mp_embed_joints / mp_embed_segments
+    per block:  qkv GEMM -> attention (spatial | temporal) -> proj GEMM + residual
+                -> norm2 -> fc1 GEMM + GELU -> fc2 GEMM + residual      mp_gemm_bf16 (tcgen05/TMEM/TMA), mp_attention
+                -> shared post-norm (+temporal pos-embed) fused with the next block's norm1      mp_layernorm
+
+The reference's "(B L) J C <-> (B J) L C" rearranges (mix_ste.py:131,144,167,171,184) are strided reads inside the
+temporal attention kernel; nothing is transposed in memory.
+"""
+from functools import partial
+from math import sqrt
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+
+
+class DropPath(nn.Module):
+    """Stochastic depth holder (timm 0.9.16 semantics, used at mix_ste.py:334-336).  Identity in eval mode; the kernels
+    take the per-row keep mask as an explicit input in training (SURVEY.md §7 hard parts)."""
+
+    def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def extra_repr(self):
+        return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+def _no_standalone(name):
+    raise NotImplementedError(
+        f"{name}.forward is not a standalone entry point in manipose_b200: the block runs fused inside MixSTE.trunk "
+        "(sm_100a kernels, one [clip, frame, token, C] layout). Call the enclosing MixSTE / RMCLManifoldMixSTE.")
+
+
+class Mlp(nn.Module):
+    """Parameter holder for mix_ste.py:194-222 (fc1 -> exact GELU -> fc2)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0, changedim=False,
+                 currentdim=0, depth=0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        _no_standalone("Mlp")
+
+
+class Attention(nn.Module):
+    """Parameter holder for mix_ste.py:225-282."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0, comb=False, vis=False,
+                 mup=False):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        default_scale = 1 / head_dim if mup else head_dim ** -0.5
+        self.scale = qk_scale or default_scale
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.comb = comb
+        self.vis = vis
+
+    def forward(self, x, vis=False):
+        _no_standalone("Attention")
+
+
+class Block(nn.Module):
+    """Parameter holder for mix_ste.py:285-368 (pre-LN attention + MLP, residual_scale = 1 without muP)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, attention=Attention, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0,
+                 drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, comb=False, changedim=False, currentdim=0, depth=0,
+                 vis=False, mup=False):
+        super().__init__()
+        if mup:
+            raise NotImplementedError("mup=True (muP residual scaling / readouts) is off in every BASELINE config (config.yaml:52)")
+        if changedim or comb:
+            raise NotImplementedError("changedim / comb blocks are never instantiated by the reference models")
+        self.changedim, self.currentdim, self.depth = changedim, currentdim, depth
+        self.norm1 = norm_layer(dim)
+        self.attn = attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop,
+                              comb=comb, vis=vis, mup=mup)
+        self.residual_scale = 1.0
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.vis = vis
+
+    def forward(self, x, vis=False):
+        _no_standalone("Block")
+
+
+def _version_key(params) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class MixSTE(nn.Module):
+    """mix_ste.py:12-191.  ``forward(x[B,L,J,in_chans]) -> [B,L,J,out_dim]``."""
+
+    # clips per micro-batch of the trunk; activations of one micro-batch are 5*C*2 bytes per token
+    micro_batch_tokens = 32768
+
+    def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
+                 qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
+        super().__init__()
+        if mup:
+            raise NotImplementedError("mup=True is off in every BASELINE config (hpe/conf/config.yaml:52)")
+        if drop_rate != 0.0 or attn_drop_rate != 0.0:
+            raise NotImplementedError("drop_rate / attn_drop_rate are never set by the reference drivers (SURVEY.md §A.2)")
+        if qk_scale is not None:
+            raise NotImplementedError("qk_scale overrides are not built; the kernels use head_dim ** -0.5 (mix_ste.py:240-244)")
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        self.embed_dim = embed_dim
+        self.num_frame = num_frame
+        self.num_tokens = num_joints
+        self.num_heads = num_heads
+        self.in_chans = in_chans
+        self.out_dim = out_dim
+        self.Spatial_patch_to_embedding = nn.Linear(in_chans, embed_dim)
+        self.Spatial_pos_embed = nn.Parameter(torch.zeros(1, num_joints, embed_dim))
+        self.Temporal_pos_embed = nn.Parameter(torch.zeros(1, num_frame, embed_dim))
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.block_depth = depth
+        self.STEblocks = nn.ModuleList([
+            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                  attn_drop=attn_drop_rate, drop_path=dpr[i], norm_layer=norm_layer, depth=0, mup=mup) for i in range(depth)])
+        self.TTEblocks = nn.ModuleList([
+            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                  attn_drop=attn_drop_rate, drop_path=dpr[i], norm_layer=norm_layer, comb=False, changedim=False,
+                  currentdim=i + 1, depth=depth, mup=mup) for i in range(depth)])
+        self.Spatial_norm = norm_layer(embed_dim)
+        self.Temporal_norm = norm_layer(embed_dim)
+        self.head = nn.Sequential(nn.LayerNorm(embed_dim), nn.Linear(embed_dim, out_dim))
+        self._shadow: Dict[str, torch.Tensor] = {}
+        self._shadow_key = None
+        self._ws = None
+
+    # ------------------------------------------------------------------------------------------ weight shadows
+    def _gemm_params(self):
+        out = []
+        for blk in list(self.STEblocks) + list(self.TTEblocks):
+            out += [blk.attn.qkv.weight, blk.attn.proj.weight, blk.mlp.fc1.weight, blk.mlp.fc2.weight]
+        return out
+
+    def _bf16_weights(self) -> List[torch.Tensor]:
+        """bf16 shadows of the GEMM weights, refreshed when a parameter changed (optimizer.step / load_state_dict)."""
+        params = self._gemm_params()
+        key = _version_key(params)
+        if key != self._shadow_key:
+            self._shadow_list = [ops.cast_bf16(p.detach()) for p in params]
+            self._shadow_key = key
+        return self._shadow_list
+
+    def _workspace(self, n_tokens: int, device) -> Dict[str, torch.Tensor]:
+        c = self.embed_dim
+        hidden = self.STEblocks[0].mlp.fc1.out_features
+        wide = max(3 * c, hidden)
+        if self._ws is None or self._ws["x"].shape[0] < n_tokens or self._ws["x"].device != device:
+            self._ws = {
+                "x": torch.empty((n_tokens, c), dtype=torch.bfloat16, device=device),       # residual stream
+                "h": torch.empty((n_tokens, c), dtype=torch.bfloat16, device=device),       # normalised / attention out
+                "wide": torch.empty((n_tokens, wide), dtype=torch.bfloat16, device=device), # qkv, then the MLP hidden
+            }
+        return self._ws
+
+    # ------------------------------------------------------------------------------------------ fused trunk
+    def _embed(self, x2d: torch.Tensor, n_clips: int, n_frames: int, x, h):
+        blk0 = self.STEblocks[0]
+        ops.embed_joints(x2d, self.Spatial_patch_to_embedding.weight, self.Spatial_patch_to_embedding.bias, self.Spatial_pos_embed,
+                         blk0.norm1.weight, blk0.norm1.bias, blk0.norm1.eps, x, h, n_clips * n_frames * self.num_tokens,
+                         self.num_tokens, self.embed_dim)
+
+    def trunk(self, x2d: torch.Tensor, n_clips: int) -> torch.Tensor:
+        """STE_forward + TTE_foward + ST_foward (mix_ste.py:128-173) on one micro-batch.
+
+        x2d: fp32 [n_clips, L, J, in_chans] (contiguous).  Returns the bf16 [n_clips*L*tokens, C] output of the last temporal
+        block BEFORE ``Temporal_norm`` (the head kernels apply it, fused with their own LayerNorm)."""
+        if self.training and any(isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0 for b in self.STEblocks):
+            raise NotImplementedError("training-mode stochastic depth through the fused trunk is not built yet; "
+                                      "call model.eval() (inference) or construct with drop_path_rate=0")
+        n_frames = self.num_frame
+        n_tok, c, heads = self.num_tokens, self.embed_dim, self.num_heads
+        n_tokens = n_clips * n_frames * n_tok
+        ws = self._workspace(n_tokens, x2d.device)
+        x, h = ws["x"][:n_tokens], ws["h"][:n_tokens]
+        hidden_dim = self.STEblocks[0].mlp.fc1.out_features
+        flat = ws["wide"].view(-1)
+        qkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
+        hid = flat[:n_tokens * hidden_dim].view(n_tokens, hidden_dim)   # aliases qkv: never live at the same time
+        w = self._bf16_weights()
+        self._embed(x2d, n_clips, n_frames, x, h)
+        depth = self.block_depth
+        blocks = []
+        for i in range(depth):
+            blocks.append((self.STEblocks[i], 4 * i, L.MP_ATTN_SPATIAL, self.Spatial_norm))
+            blocks.append((self.TTEblocks[i], 4 * (depth + i), L.MP_ATTN_TEMPORAL, self.Temporal_norm))
+        for bi, (blk, wi, mode, post) in enumerate(blocks):
+            ops.gemm(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
+            ops.attention(qkv, h, n_clips, n_frames, n_tok, c, heads, mode)
+            ops.gemm(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+            ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps)
+            ops.gemm(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
+            ops.gemm(hid, w[wi + 3], blk.mlp.fc2.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+            if bi + 1 < len(blocks):
+                nxt = blocks[bi + 1][0]
+                pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
+                ops.layernorm(x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
+                              ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps)
+        return x
+
+    def _check_input(self, x: torch.Tensor):
+        if x.dim() != 4:
+            raise ValueError(f"expected x of shape [B, L, J, C], got {tuple(x.shape)}")
+        b, l, j, cin = x.shape
+        if l != self.num_frame:
+            # the reference fails here too: Temporal_pos_embed is [1, num_frame, C] (mix_ste.py:63-65,149)
+            raise RuntimeError(f"The size of tensor a ({l}) must match the size of tensor b ({self.num_frame}) at non-singleton dimension 1")
+        return b, l, j, cin
+
+    def clips_per_micro_batch(self) -> int:
+        return max(1, self.micro_batch_tokens // (self.num_frame * self.num_tokens))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """mix_ste.py:175-191 with the plain head (LayerNorm eps 1e-5 + Linear): [B,L,J,in] -> [B,L,J,out_dim]."""
+        ops._need_cuda(x)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("backward through the fused MixSTE trunk is not built yet (forward/inference only)")
+        b, l, j, _ = self._check_input(x)
+        x = ops._f32(x)
+        out = torch.empty((b, 1, l, j, self.out_dim), dtype=torch.float32, device=x.device)
+        mb = self.clips_per_micro_batch()
+        norm, lin = self.head[0], self.head[1]
+        for s in range(0, b, mb):
+            n = min(mb, b - s)
+            feat = self.trunk(x[s:s + n], n)
+            ops.heads_fwd(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, norm.weight, norm.bias,
+                          lin.weight, lin.bias, None, None, out[s:s + n], None, n, l, 1, self.out_dim, False)
+        return out[:, 0]

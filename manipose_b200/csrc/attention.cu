@@ -1,0 +1,299 @@
+// Multi-head softmax attention of the MixSTE blocks (Attention.forward, hpe/mh_so3_hpe/architectures/mix_ste.py:255-282)
+// over ONE activation layout, [clip, frame, token, 3C] with columns [q | k | v] x heads x head_dim (mix_ste.py:257-261):
+//   spatial  (STEblocks): sequences are the n_tok (17 joints / 16 segments) tokens of one frame;
+//   temporal (TTEblocks): sequences are the n_frames frames of one (clip, token) track, read with a row stride of
+//                         n_tok*3C elements -- the reference's "(B L) J C -> (B J) L C" rearranges (mix_ste.py:144,167,171)
+//                         never materialise.
+// Both kernels keep Q, K and V of their sequences in shared memory (16-byte cp.async, +16-byte row padding so ldmatrix
+// is bank-conflict free), compute S = QK^T and O = PV on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) with
+// an online softmax in the exp2 domain, and write O through shared memory as 16-byte coalesced rows.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mp {
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// One 16-row query tile against keys [0, n_keys_pad) held in shared memory.
+//   q_rows: smem address of query row 0 of this tile (row stride `ld` bytes); k_rows / v_rows: key / value row 0.
+//   Rows are addressed through row_ptr(base, r) so callers can redirect padding rows to a zero row.
+// Result: o[HD/8][4] (unnormalised) and l[2] (row sums) in the mma C-fragment layout (rows g and g+8).
+template <int HD, typename RowPtr>
+__device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, const uint8_t* k_base, const uint8_t* v_base, int n_keys,
+                                            int n_keys_pad, float scale_log2, RowPtr row_ptr, int lane, float (&o)[HD / 8][4],
+                                            float (&l)[2]) {
+  constexpr int KS = HD / 16;   // k-steps over the head dimension
+  constexpr int NT = HD / 8;    // output n-tiles
+  const int g = lane >> 2, t = lane & 3;
+
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    // A fragment (16 x 16): matrices {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi}
+    const int r = q_row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int kc = ks * 16 + (lane >> 4) * 8;
+    ptx::ldmatrix_x4(qf[ks], row_ptr(q_base, r) + kc * 2);
+  }
+
+  float m[2] = {-INFINITY, -INFINITY};
+  l[0] = l[1] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+
+  for (int key0 = 0; key0 < n_keys_pad; key0 += 32) {
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        // B fragments of two key n-tiles: {keys +0..7, k lo}, {keys +0..7, k hi}, {keys +8..15, k lo}, {keys +8..15, k hi}
+        uint32_t kf[4];
+        const int kr = key0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int kc = ks * 16 + ((lane >> 3) & 1) * 8;
+        ptx::ldmatrix_x4(kf, row_ptr(k_base, kr) + kc * 2);
+        ptx::mma_bf16_16816(s[np * 2 + 0], qf[ks], kf[0], kf[1]);
+        ptx::mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    // scale into the exp2 domain, mask padded keys
+    float cmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = key0 + nt * 8 + 2 * t + (e & 1);
+        const float v = key < n_keys ? s[nt][e] * scale_log2 : -INFINITY;
+        s[nt][e] = v;
+        cmax[e >> 1] = fmaxf(cmax[e >> 1], v);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float mn = fmaxf(m[h], quad_max(cmax[h]));   // finite: every 32-key chunk starts below n_keys
+      corr[h] = exp2f(m[h] - mn);
+      m[h] = mn;
+      l[h] *= corr[h];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      o[i][0] *= corr[0];
+      o[i][1] *= corr[0];
+      o[i][2] *= corr[1];
+      o[i][3] *= corr[1];
+    }
+    uint32_t pf[2][4];   // P as A fragments for the two 16-key k-steps of this chunk
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float p0 = exp2f(s[nt][0] - m[0]), p1 = exp2f(s[nt][1] - m[0]);
+      const float p2 = exp2f(s[nt][2] - m[1]), p3 = exp2f(s[nt][3] - m[1]);
+      l[0] += p0 + p1;
+      l[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < NT / 2; ++dp) {
+        // V^T fragments via ldmatrix.trans: {keys +0..7, dims d}, {keys +8..15, dims d}, {keys +0..7, dims d+8}, {keys +8..15, dims d+8}
+        uint32_t vf[4];
+        const int vr = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int vc = dp * 16 + (lane >> 4) * 8;
+        ptx::ldmatrix_x4_trans(vf, row_ptr(v_base, vr) + vc * 2);
+        ptx::mma_bf16_16816(o[dp * 2 + 0], pf[kk], vf[0], vf[1]);
+        ptx::mma_bf16_16816(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+  }
+  l[0] = quad_sum(l[0]);
+  l[1] = quad_sum(l[1]);
+}
+
+// ------------------------------------------------------------------------------------------------------ temporal
+// One CTA per (clip, token, head); 8 warps share the track's K and V, each warp owns 16-row query tiles.
+constexpr int kTWarps = 8;
+
+template <int HD>
+__global__ void __launch_bounds__(kTWarps * 32, 2)
+attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_frames, int n_tok, int C, int n_heads) {
+  constexpr int LD = HD * 2 + 16;           // padded row bytes
+  constexpr int CH = HD / 8;                // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Tp = (n_frames + 31) & ~31;
+  uint8_t* sq = smem;
+  uint8_t* sk = sq + (size_t)Tp * LD;
+  uint8_t* sv = sk + (size_t)Tp * LD;
+
+  const int head = blockIdx.x % n_heads;
+  const int tok = (blockIdx.x / n_heads) % n_tok;
+  const int clip = blockIdx.x / (n_heads * n_tok);
+  const size_t row_stride = (size_t)n_tok * 3 * C;   // elements between consecutive frames of this track
+  const __nv_bfloat16* base = qkv + ((size_t)clip * n_frames * n_tok + tok) * 3 * C + head * HD;
+
+  // stage Q, K, V rows [0, n_frames); zero rows [n_frames, Tp)
+  const int total = 3 * Tp * CH;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int ch = i % CH;
+    const int r = (i / CH) % Tp;
+    const int sel = i / (CH * Tp);
+    uint8_t* dst = smem + ((size_t)sel * Tp + r) * LD + ch * 16;
+    if (r < n_frames) {
+      ptx::cp_async16(dst, base + (size_t)r * row_stride + sel * C + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale_log2 = rsqrtf((float)HD) * kLog2e;
+  auto row_ptr = [](const uint8_t* b, int r) { return b + (size_t)r * LD; };
+  __nv_bfloat16* obase = out + ((size_t)clip * n_frames * n_tok + tok) * C + head * HD;
+  const size_t orow_stride = (size_t)n_tok * C;
+
+  for (int mt = warp; mt * 16 < n_frames; mt += kTWarps) {
+    float o[HD / 8][4], l[2];
+    attend_tile<HD>(sq, mt * 16, sk, sv, n_frames, Tp, scale_log2, row_ptr, lane, o, l);
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    // this warp's 16 query rows are dead: reuse them to transpose the output tile
+    __syncwarp();
+    uint8_t* orow0 = sq + (size_t)(mt * 16 + g) * LD;
+    uint8_t* orow1 = orow0 + 8 * LD;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      *reinterpret_cast<uint32_t*>(orow0 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(orow1 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+      const int r = mt * 16 + i / CH, ch = i % CH;
+      if (r < n_frames)
+        *reinterpret_cast<uint4*>(obase + (size_t)r * orow_stride + ch * 8) = *reinterpret_cast<const uint4*>(sq + (size_t)r * LD + ch * 16);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------ spatial
+// One CTA per frame, one warp per head.  The frame's [n_tok, 3C] block is contiguous in global memory.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int64_t n_seq, int n_tok, int C, int n_heads) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int LD = 3 * C * 2 + 16;            // padded row bytes; row n_tok is an all-zero row for padded tokens
+  const int CH = 3 * C / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale_log2 = rsqrtf((float)HD) * kLog2e;
+
+  for (int i = threadIdx.x; i < LD / 16; i += blockDim.x) *reinterpret_cast<uint4*>(smem + (size_t)n_tok * LD + i * 16) = make_uint4(0, 0, 0, 0);
+
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    const __nv_bfloat16* src = qkv + (size_t)seq * n_tok * 3 * C;
+    __syncthreads();   // previous iteration's readers are done
+    for (int i = threadIdx.x; i < n_tok * CH; i += blockDim.x) {
+      const int r = i / CH, ch = i - r * CH;
+      ptx::cp_async16(smem + (size_t)r * LD + ch * 16, src + (size_t)r * 3 * C + ch * 8);
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+    __syncthreads();
+
+    if (warp < n_heads) {
+      const int head = warp;
+      const uint8_t* qb = smem + (size_t)head * HD * 2;
+      const uint8_t* kb = qb + (size_t)C * 2;
+      const uint8_t* vb = kb + (size_t)C * 2;
+      const uint8_t* zero_row = smem + (size_t)n_tok * LD;
+      // rows past n_tok read the zero row (the column offset still lands inside it)
+      auto row_ptr = [=](const uint8_t* b, int r) { return r < n_tok ? b + (size_t)r * LD : zero_row + (b - smem) % LD; };
+      for (int mt = 0; mt * 16 < n_tok; ++mt) {
+        float o[HD / 8][4], l[2];
+        attend_tile<HD>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
+        const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+        __syncwarp();
+        // the q columns of this head and these rows are only ever read by this warp: overwrite them with the output
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        uint8_t* w0 = smem + (size_t)r0 * LD + (size_t)head * HD * 2;
+        uint8_t* w1 = smem + (size_t)r1 * LD + (size_t)head * HD * 2;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          if (r0 < n_tok) *reinterpret_cast<uint32_t*>(w0 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+          if (r1 < n_tok) *reinterpret_cast<uint32_t*>(w1 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+        }
+      }
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = out + (size_t)seq * n_tok * C;
+    const int OCH = C / 8;
+    for (int i = threadIdx.x; i < n_tok * OCH; i += blockDim.x) {
+      const int r = i / OCH, ch = i - r * OCH;
+      *reinterpret_cast<uint4*>(dst + (size_t)r * C + ch * 8) = *reinterpret_cast<const uint4*>(smem + (size_t)r * LD + ch * 16);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mp
+
+extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads, int mode,
+                            mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(qkv && out, MP_EINVAL, "mp_attention: null pointer");
+  MP_REQUIRE(n_clips >= 0 && n_frames >= 1 && n_tok >= 1 && n_heads >= 1 && n_heads <= 8 && C % n_heads == 0, MP_EINVAL,
+             "mp_attention: bad sizes");
+  const int hd = C / n_heads;
+  MP_REQUIRE(hd == 64 || hd == 16, MP_EUNSUPPORTED, "mp_attention: head_dim=%d (built for 64 and 16)", hd);
+  MP_REQUIRE(aligned16(qkv) && aligned16(out), MP_EALIGN, "mp_attention: pointers must be 16-byte aligned");
+  if (n_clips == 0) return MP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == MP_ATTN_TEMPORAL) {
+    MP_REQUIRE(n_frames <= 256, MP_EUNSUPPORTED, "mp_attention: temporal sequences longer than 256 frames are not built (got %lld)",
+               (long long)n_frames);
+    const int Tp = ((int)n_frames + 31) & ~31;
+    const size_t smem = (size_t)3 * Tp * (hd * 2 + 16);
+    const int64_t ctas = n_clips * n_tok * n_heads;
+    MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+    auto launch = [&](auto kernel) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kernel<<<(unsigned)ctas, kTWarps * 32, smem, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, (int)n_frames, n_tok, C, n_heads);
+    };
+    if (hd == 64)
+      launch(attn_temporal_kernel<64>);
+    else
+      launch(attn_temporal_kernel<16>);
+    return check_launch("attn_temporal_kernel");
+  }
+  MP_REQUIRE(mode == MP_ATTN_SPATIAL, MP_EINVAL, "mp_attention: unknown mode %d", mode);
+  MP_REQUIRE(n_tok <= 32, MP_EUNSUPPORTED, "mp_attention: spatial sequences longer than 32 tokens are not built (got %d)", n_tok);
+  const size_t smem = (size_t)(n_tok + 1) * (3 * C * 2 + 16);
+  const int64_t n_seq = n_clips * n_frames;
+  const int per_sm = (int)(200 * 1024 / (smem + 1024));
+  int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+  if (grid > n_seq) grid = n_seq;
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<(unsigned)grid, 256, smem, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_seq, n_tok, C, n_heads);
+  };
+  if (hd == 64)
+    launch(attn_spatial_kernel<64>);
+  else
+    launch(attn_spatial_kernel<16>);
+  return check_launch("attn_spatial_kernel");
+}

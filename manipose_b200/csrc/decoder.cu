@@ -125,6 +125,22 @@ __device__ __forceinline__ void decode_joint(PoseState& st, const float* __restr
   if constexpr (j + 1 < kJ) decode_joint<kExact, j + 1>(st, lane_in, len);
 }
 
+// softmax over the hypothesis dim, one (clip, frame) per thread, grid-stride
+__device__ __forceinline__ void softmax_hyp_rows(const float* __restrict__ logits, float* __restrict__ scores, uint32_t n_clips,
+                                                 uint32_t n_hyp, uint32_t n_frames) {
+  const uint32_t n_items = n_clips * n_frames;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_items; idx += gridDim.x * blockDim.x) {
+    const uint32_t b = idx / n_frames, t = idx - b * n_frames;
+    const float* lg = logits + (size_t)b * n_hyp * n_frames + t;
+    float mx = -INFINITY;
+    for (uint32_t k = 0; k < n_hyp; ++k) mx = fmaxf(mx, lg[(size_t)k * n_frames]);
+    float sum = 0.f;
+    for (uint32_t k = 0; k < n_hyp; ++k) sum += expf(lg[(size_t)k * n_frames] - mx);
+    float* sc = scores + (size_t)b * n_hyp * n_frames + t;
+    for (uint32_t k = 0; k < n_hyp; ++k) sc[(size_t)k * n_frames] = expf(lg[(size_t)k * n_frames] - mx) / sum;
+  }
+}
+
 template <bool kExact>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
@@ -215,19 +231,12 @@ decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
   }
 
   // ---- hypothesis scores: softmax over K of logits[b, :, t]  (rmcl_manifold_mix_ste.py:262)
-  if (logits != nullptr) {
-    const uint32_t n_items = n_clips * n_frames;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_items; idx += gridDim.x * blockDim.x) {
-      const uint32_t b = idx / n_frames, t = idx - b * n_frames;
-      const float* lg = logits + (size_t)b * n_hyp * n_frames + t;
-      float mx = -INFINITY;
-      for (uint32_t k = 0; k < n_hyp; ++k) mx = fmaxf(mx, lg[(size_t)k * n_frames]);
-      float sum = 0.f;
-      for (uint32_t k = 0; k < n_hyp; ++k) sum += expf(lg[(size_t)k * n_frames] - mx);
-      float* sc = scores + (size_t)b * n_hyp * n_frames + t;
-      for (uint32_t k = 0; k < n_hyp; ++k) sc[(size_t)k * n_frames] = expf(lg[(size_t)k * n_frames] - mx) / sum;
-    }
-  }
+  if (logits != nullptr) softmax_hyp_rows(logits, scores, n_clips, n_hyp, n_frames);
+}
+
+__global__ void softmax_hyp_fwd_kernel(const float* __restrict__ logits, float* __restrict__ scores, uint32_t n_clips, uint32_t n_hyp,
+                                       uint32_t n_frames) {
+  softmax_hyp_rows(logits, scores, n_clips, n_hyp, n_frames);
 }
 
 __global__ void softmax_hyp_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ grad_scores,
@@ -241,6 +250,231 @@ __global__ void softmax_hyp_bwd_kernel(const float* __restrict__ scores, const f
     for (uint32_t k = 0; k < n_hyp; ++k) {
       const size_t i = base + (size_t)k * n_frames;
       grad_logits[i] = scores[i] * (grad_scores[i] - dot);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ backward
+// Reverse-mode of the fused decoder, one pose per lane, depth-first over the kinematic tree: each joint recomputes its
+// local rotation from the staged 6-D input, recurses into its children (which accumulate into its world-rotation and
+// position gradients), then back-propagates through Rw[j] = Rw[p] R[j], the bone offset and the Gram-Schmidt map, and
+// overwrites its own 6-D slot of the staged tile with the gradient (the tile leaves with one bulk store).
+struct BwdCtx {
+  float* r6;           // lane's 102 staged floats: rot6d in, grad_rot6d out (in place, joint by joint)
+  const float* gp;     // lane's 51 staged floats of grad_poses
+  const float* len;    // 16 bone lengths of the lane's clip
+  float glen[kBones];  // gradient w.r.t. the bone lengths (this pose's contribution)
+};
+
+__device__ __forceinline__ void gs_forward(const float* a6, float (&x)[3], float (&z)[3], float (&y)[3], float& na, float& nw,
+                                           float (&w)[3]) {
+  const float a0 = a6[0], a1 = a6[1], a2 = a6[2], b0 = a6[3], b1 = a6[4], b2 = a6[5];
+  na = fmaxf(sqrtf(a0 * a0 + a1 * a1 + a2 * a2), 1e-8f);
+  x[0] = a0 / na; x[1] = a1 / na; x[2] = a2 / na;
+  w[0] = x[1] * b2 - x[2] * b1;
+  w[1] = x[2] * b0 - x[0] * b2;
+  w[2] = x[0] * b1 - x[1] * b0;
+  nw = fmaxf(sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), 1e-8f);
+  z[0] = w[0] / nw; z[1] = w[1] / nw; z[2] = w[2] / nw;
+  y[0] = z[1] * x[2] - z[2] * x[1];
+  y[1] = z[2] * x[0] - z[0] * x[2];
+  y[2] = z[0] * x[1] - z[1] * x[0];
+}
+
+// gradient of v / max(|v|, 1e-8) given the normalised vector u, the clamped norm n and the upstream gradient gu
+__device__ __forceinline__ void normalize_bwd(const float (&u)[3], float n, bool clamped, const float (&gu)[3], float (&gv)[3]) {
+  const float d = clamped ? 0.f : (u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2]);
+  gv[0] = (gu[0] - u[0] * d) / n;
+  gv[1] = (gu[1] - u[1] * d) / n;
+  gv[2] = (gu[2] - u[2] * d) / n;
+}
+
+template <int j, int c>
+struct Children;
+
+template <int j>
+__device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], float (&g_rwp)[9], float (&g_posp)[3]) {
+  // ---- forward recompute for this joint
+  float x[3], y[3], z[3], w[3], na, nw;
+  gs_forward(ctx.r6 + j * 6, x, z, y, na, nw, w);
+  const float r[9] = {x[0], y[0], z[0], x[1], y[1], z[1], x[2], y[2], z[2]};
+  float rw[9];
+  if constexpr (j == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rw[i] = r[i];
+  } else {
+#pragma unroll
+    for (int row = 0; row < 3; ++row)
+#pragma unroll
+      for (int col = 0; col < 3; ++col)
+        rw[row * 3 + col] = rwp[row * 3 + 0] * r[0 * 3 + col] + rwp[row * 3 + 1] * r[1 * 3 + col] + rwp[row * 3 + 2] * r[2 * 3 + col];
+  }
+  float g_rw[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float g_pos[3] = {ctx.gp[j * 3 + 0], ctx.gp[j * 3 + 1], ctx.gp[j * 3 + 2]};
+  // ---- children accumulate into g_rw / g_pos
+  Children<j, j + 1>::run(ctx, rw, g_rw, g_pos);
+
+  float g_r[9];
+  if constexpr (j == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g_r[i] = g_rw[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g_posp[i] = g_pos[i];   // gradient w.r.t. the root position
+  } else {
+    constexpr int ax = axis_of(j);
+    constexpr float sg = sign_of(j);
+    const float off = sg * ctx.len[j - 1];
+    // pos[j] = pos[p] + off * Rw[j][:, ax]
+    ctx.glen[j - 1] = sg * (g_pos[0] * rw[0 * 3 + ax] + g_pos[1] * rw[1 * 3 + ax] + g_pos[2] * rw[2 * 3 + ax]);
+#pragma unroll
+    for (int row = 0; row < 3; ++row) {
+      g_rw[row * 3 + ax] += off * g_pos[row];
+      g_posp[row] += g_pos[row];
+    }
+    // Rw[j] = Rw[p] R[j]:  G_Rw[p] += G_Rw[j] R[j]^T ;  G_R[j] = Rw[p]^T G_Rw[j]
+#pragma unroll
+    for (int row = 0; row < 3; ++row)
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        g_rwp[row * 3 + col] += g_rw[row * 3 + 0] * r[col * 3 + 0] + g_rw[row * 3 + 1] * r[col * 3 + 1] + g_rw[row * 3 + 2] * r[col * 3 + 2];
+        g_r[row * 3 + col] = rwp[0 * 3 + row] * g_rw[0 * 3 + col] + rwp[1 * 3 + row] * g_rw[1 * 3 + col] + rwp[2 * 3 + row] * g_rw[2 * 3 + col];
+      }
+  }
+  // ---- Gram-Schmidt backward (rotation_tools.py:35-57): columns of G_R are the gradients of x, y, z
+  float gx[3] = {g_r[0], g_r[3], g_r[6]};
+  const float gy[3] = {g_r[1], g_r[4], g_r[7]};
+  float gz[3] = {g_r[2], g_r[5], g_r[8]};
+  // y = z x x
+  gz[0] += x[1] * gy[2] - x[2] * gy[1];
+  gz[1] += x[2] * gy[0] - x[0] * gy[2];
+  gz[2] += x[0] * gy[1] - x[1] * gy[0];
+  gx[0] += gy[1] * z[2] - gy[2] * z[1];
+  gx[1] += gy[2] * z[0] - gy[0] * z[2];
+  gx[2] += gy[0] * z[1] - gy[1] * z[0];
+  // z = w / max(|w|, eps)
+  float gw[3];
+  normalize_bwd(z, nw, nw <= 1e-8f, gz, gw);
+  // w = x x b
+  const float b[3] = {ctx.r6[j * 6 + 3], ctx.r6[j * 6 + 4], ctx.r6[j * 6 + 5]};
+  gx[0] += b[1] * gw[2] - b[2] * gw[1];
+  gx[1] += b[2] * gw[0] - b[0] * gw[2];
+  gx[2] += b[0] * gw[1] - b[1] * gw[0];
+  const float gb[3] = {gw[1] * x[2] - gw[2] * x[1], gw[2] * x[0] - gw[0] * x[2], gw[0] * x[1] - gw[1] * x[0]};
+  float ga[3];
+  normalize_bwd(x, na, na <= 1e-8f, gx, ga);
+  ctx.r6[j * 6 + 0] = ga[0];
+  ctx.r6[j * 6 + 1] = ga[1];
+  ctx.r6[j * 6 + 2] = ga[2];
+  ctx.r6[j * 6 + 3] = gb[0];
+  ctx.r6[j * 6 + 4] = gb[1];
+  ctx.r6[j * 6 + 5] = gb[2];
+}
+
+template <int j, int c>
+struct Children {
+  static __device__ __forceinline__ void run(BwdCtx& ctx, const float (&rw)[9], float (&g_rw)[9], float (&g_pos)[3]) {
+    if constexpr (parent_of(c) == j) bwd_joint<c>(ctx, rw, g_rw, g_pos);
+    Children<j, c + 1>::run(ctx, rw, g_rw, g_pos);
+  }
+};
+template <int j>
+struct Children<j, kJ> {
+  static __device__ __forceinline__ void run(BwdCtx&, const float (&)[9], float (&)[9], float (&)[3]) {}
+};
+
+constexpr int kBwdWarps = 4;
+constexpr int kBwdWarpBytes = kTileInBytes + kTileOutBytes;   // rot6d / grad_rot6d tile + grad_poses tile
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ grad_poses,
+                   float* __restrict__ grad_rot6d, float* __restrict__ grad_bone_len, float* __restrict__ grad_root, uint32_t n_poses,
+                   uint32_t poses_per_clip, int bulk_ok) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = reinterpret_cast<float*>(smem_raw + warp * kBwdWarpBytes);
+  float* gtile = tile + kTile * kIn;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kBwdWarps * kBwdWarpBytes) + warp;
+  if (lane == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+
+  const uint32_t n_tiles = (n_poses + kTile - 1) / kTile;
+  uint32_t phase = 0;
+  for (uint32_t tile_idx = blockIdx.x * kBwdWarps + warp; tile_idx < n_tiles; tile_idx += gridDim.x * kBwdWarps) {
+    const uint32_t pose0 = tile_idx * kTile;
+    const uint32_t n_here = min((uint32_t)kTile, n_poses - pose0);
+    const bool full = bulk_ok && (n_here == kTile);
+    const float* gin = rot6d + (size_t)pose0 * kIn;
+    const float* ggp = grad_poses + (size_t)pose0 * kOut;
+    float* gout = grad_rot6d + (size_t)pose0 * kIn;
+    if (full) {
+      if (lane == 0) {
+        ptx::mbar_expect_tx(bar, kTileInBytes + kTileOutBytes);
+        ptx::bulk_g2s(tile, gin, kTileInBytes, bar);
+        ptx::bulk_g2s(gtile, ggp, kTileOutBytes, bar);
+      }
+      ptx::mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      for (uint32_t i = lane; i < n_here * kIn; i += 32) tile[i] = gin[i];
+      for (uint32_t i = lane; i < n_here * kOut; i += 32) gtile[i] = ggp[i];
+      __syncwarp();
+    }
+
+    const uint32_t pose = pose0 + lane;
+    const bool active = lane < n_here;
+    const uint32_t clip = (active ? pose : pose0) / poses_per_clip;
+    BwdCtx ctx;
+    ctx.r6 = tile + lane * kIn;
+    ctx.gp = gtile + lane * kOut;
+    float len[kBones];
+#pragma unroll
+    for (int i = 0; i < kBones; ++i) {
+      len[i] = __ldg(bone_len + (size_t)clip * kBones + i);
+      ctx.glen[i] = 0.f;
+    }
+    ctx.len = len;
+    float g_root[3] = {0.f, 0.f, 0.f};
+    if (active) {
+      const float ident[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+      float g_dummy[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      bwd_joint<0>(ctx, ident, g_dummy, g_root);
+      if (grad_root != nullptr) {
+        grad_root[(size_t)pose * 3 + 0] = g_root[0];
+        grad_root[(size_t)pose * 3 + 1] = g_root[1];
+        grad_root[(size_t)pose * 3 + 2] = g_root[2];
+      }
+    }
+    // bone-length gradient: sum over the clip's poses.  Lanes of one warp almost always share a clip.
+    const uint32_t clip0 = __shfl_sync(0xffffffffu, clip, 0);
+    const bool uniform = __all_sync(0xffffffffu, clip == clip0);
+    if (uniform) {
+#pragma unroll
+      for (int i = 0; i < kBones; ++i) {
+        const float s = warp_sum(ctx.glen[i]);
+        if (lane == 0) atomicAdd(grad_bone_len + (size_t)clip0 * kBones + i, s);
+      }
+    } else if (active) {
+#pragma unroll
+      for (int i = 0; i < kBones; ++i) atomicAdd(grad_bone_len + (size_t)clip * kBones + i, ctx.glen[i]);
+    }
+
+    if (full) {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::bulk_s2g(gout, tile, kTileInBytes);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();
+      }
+      __syncwarp();
+    } else {
+      __syncwarp();
+      for (uint32_t i = lane; i < n_here * kIn; i += 32) gout[i] = tile[i];
+      __syncwarp();
     }
   }
 }
@@ -284,6 +518,42 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   else
     launch(decoder_fwd_kernel<true>);
   return check_launch("decoder_fwd_kernel");
+}
+
+int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_poses, float* grad_rot6d, float* grad_bone_len,
+                   float* grad_root, int64_t n_clips, int64_t n_hyp, int64_t n_frames, int rot_rep_dim, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(rot_rep_dim == 4 || rot_rep_dim == 6, MP_EINVAL, "Unsupported rotations representation dimension: %d", rot_rep_dim);
+  MP_REQUIRE(rot_rep_dim == 6, MP_EUNSUPPORTED, "rot_rep_dim=4 is not built: no BASELINE config uses it");
+  MP_REQUIRE(n_clips >= 0 && n_hyp >= 1 && n_frames >= 1, MP_EINVAL, "mp_decoder_bwd: bad sizes");
+  const int64_t n_poses = n_clips * n_hyp * n_frames;
+  if (n_poses == 0) return MP_OK;
+  MP_REQUIRE(n_poses < (int64_t)1 << 31, MP_EINVAL, "mp_decoder_bwd: %lld poses exceed 2^31", (long long)n_poses);
+  MP_REQUIRE(rot6d && bone_len && grad_poses && grad_rot6d && grad_bone_len, MP_EINVAL, "mp_decoder_bwd: null pointer");
+  const int bulk_ok = aligned16(rot6d) && aligned16(grad_poses) && aligned16(grad_rot6d);
+  const size_t smem = (size_t)kBwdWarps * kBwdWarpBytes + kBwdWarps * sizeof(uint64_t);
+  const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
+  int64_t ctas = (n_tiles + kBwdWarps - 1) / kBwdWarps;
+  const int64_t max_ctas = (int64_t)sm_count() * 2;
+  if (ctas > max_ctas) ctas = max_ctas;
+  cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  decoder_bwd_kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(
+      rot6d, bone_len, grad_poses, grad_rot6d, grad_bone_len, grad_root, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), bulk_ok);
+  return check_launch("decoder_bwd_kernel");
+}
+
+int mp_softmax_hyp_fwd(const float* logits, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(logits && scores && n_hyp >= 1, MP_EINVAL, "mp_softmax_hyp_fwd: bad arguments");
+  const int64_t n = n_clips * n_frames;
+  if (n <= 0) return MP_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  softmax_hyp_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, scores, (uint32_t)n_clips, (uint32_t)n_hyp,
+                                                                            (uint32_t)n_frames);
+  return check_launch("softmax_hyp_fwd_kernel");
 }
 
 int mp_softmax_hyp_bwd(const float* scores, const float* grad_scores, float* grad_logits, int64_t n_clips, int64_t n_hyp,

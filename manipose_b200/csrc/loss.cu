@@ -221,8 +221,8 @@ template <bool kSquared>
 __global__ void __launch_bounds__(kLossWarps * 32, 2)
 loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, const int64_t* __restrict__ wta_idx, LossDims d, float beta, float vel_w,
-                float smooth_w, const float* __restrict__ grad_total, float* __restrict__ grad_hyp,
-                float* __restrict__ grad_scores) {
+                float smooth_w, const float* __restrict__ grad_terms, const float* __restrict__ grad_wta_val,
+                float* __restrict__ grad_hyp, float* __restrict__ grad_scores) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* ybuf = reinterpret_cast<float*>(smem_raw + (size_t)warp * 2 * kStageBytes);
@@ -232,12 +232,18 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
 #pragma unroll
   for (int j = 0; j < kJ; ++j) w[j] = weights ? weights[j] : c_ones17[j];
 
-  const float gt = grad_total ? grad_total[0] : 1.f;
+  // upstream gradients w.r.t. terms[WTA, BCE, VEL, SMOOTH, TOTAL]; TOTAL expands with the weights of mp_loss_fwd
+  const float gtot = grad_terms[MP_TERM_TOTAL];
+  const float g_wta = grad_terms[MP_TERM_WTA] + gtot;
+  const float g_bce = grad_terms[MP_TERM_BCE] + (beta != 0.f ? beta * gtot : 0.f);
+  const float g_vel = grad_terms[MP_TERM_VEL] + (vel_w > 0.f ? vel_w * gtot : 0.f);
+  const float g_sm = grad_terms[MP_TERM_SMOOTH] + (smooth_w > 0.f ? smooth_w * gtot : 0.f);
   const double bt = (double)d.B * d.T, pairs = (double)d.B * d.K * (d.T - 1.0) * kJ;
-  const float c_wta = kSquared ? (float)(gt * 2.0 / (bt * kJ * 3.0)) : (float)(gt / (bt * kJ));
-  const float c_vel = vel_w > 0.f ? (kSquared ? (float)(gt * vel_w * 2.0 / (pairs * 3.0)) : (float)(gt * vel_w / pairs)) : 0.f;
-  const float c_sm = smooth_w > 0.f ? (float)(gt * smooth_w * 2.0 / (pairs * 3.0)) : 0.f;
-  const float c_bce = beta != 0.f ? (float)(gt * beta / (bt * d.K)) : 0.f;
+  const float wta_mean = (float)(g_wta / bt);                                        // d mean / d wta_val[b,t]
+  const float wta_scale = kSquared ? (float)(2.0 / (kJ * 3.0)) : (float)(1.0 / kJ);  // d wta_val / d (w_j |d_j|) resp. (w_j d^2)
+  const float c_vel = kSquared ? (float)(g_vel * 2.0 / (pairs * 3.0)) : (float)(g_vel / pairs);
+  const float c_sm = (float)(g_sm * 2.0 / (pairs * 3.0));
+  const float c_bce = (float)(g_bce / (bt * d.K));
 
   const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
   const uint32_t n_items = d.B * tiles_per_clip;
@@ -251,6 +257,7 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
     const bool valid = lane < nf;
     const bool has_prev = valid && t >= 1, has_next = valid && (t + 1 < d.T);
     const int64_t kstar = valid ? wta_idx[(size_t)b * d.T + t] : -1;
+    const float c_wta = valid ? (wta_mean + (grad_wta_val ? grad_wta_val[(size_t)b * d.T + t] : 0.f)) * wta_scale : 0.f;
 
     __syncwarp();
     const int sy = stage_floats(ybuf, y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
@@ -480,12 +487,12 @@ int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const flo
 }
 
 int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const float* joint_weights, const int64_t* wta_idx,
-                int squared, float beta, float vel_w, float smooth_w, const float* grad_total, float* grad_hyp,
-                float* grad_scores, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
+                int squared, float beta, float vel_w, float smooth_w, const float* grad_terms, const float* grad_wta_val,
+                float* grad_hyp, float* grad_scores, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_CHECK(check_dims("mp_loss_bwd", B, K, T));
-  MP_REQUIRE(hyp && y && wta_idx && grad_hyp, MP_EINVAL, "mp_loss_bwd: null pointer");
+  MP_REQUIRE(hyp && y && wta_idx && grad_hyp && grad_terms, MP_EINVAL, "mp_loss_bwd: null pointer");
   MP_REQUIRE(grad_scores == nullptr || scores != nullptr, MP_EINVAL, "mp_loss_bwd: scores required for grad_scores");
   MP_REQUIRE(aligned16(hyp) && aligned16(y), MP_EALIGN, "mp_loss_bwd: hyp and y must be 16-byte aligned");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
@@ -494,7 +501,7 @@ int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const flo
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
-                                                                   grad_total, grad_hyp, grad_scores);
+                                                                   grad_terms, grad_wta_val, grad_hyp, grad_scores);
   };
   if (squared)
     launch(loss_bwd_kernel<true>);

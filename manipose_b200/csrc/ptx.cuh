@@ -38,7 +38,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 24)) {
       printf("libmanipose_sm100: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }

@@ -1,0 +1,15 @@
+"""mpjpe_error (hpe/mh_so3_hpe/metrics/mean_joint_errors.py:8-36) on the device reduction kernel."""
+import torch
+
+from .. import ops
+
+
+def mpjpe_error(batch_imp: torch.Tensor, batch_gt: torch.Tensor, mode: str):
+    assert batch_imp.shape[-1] == batch_gt.shape[-1] == 3
+    if mode == "average":
+        return ops.mpjpe(batch_imp, batch_gt)[1]
+    if mode == "sum":
+        return ops.mpjpe(batch_imp, batch_gt)[0]
+    if mode == "no_agg":
+        raise NotImplementedError("mpjpe_error(mode='no_agg') is only used by offline per-action analytics (out of scope, SURVEY.md §2)")
+    raise ValueError(f"Unexpected value for 'mode' encoutered: {mode}.Accepted values are 'average' and 'sum'.")

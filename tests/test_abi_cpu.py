@@ -1,0 +1,109 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/manipose_sm100.h declares; the host modules expose the reference's names / state_dict; the product path fails
+loudly without a GPU (no CPU fallback) and never imports the oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "manipose_sm100.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from manipose_b200 import _build, _lib
+    _build.build(verbose=False)
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from manipose_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/manipose_sm100.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
+
+
+def test_no_compute_without_gpu_fails_loudly(lib):
+    from manipose_b200 import _lib
+    assert lib.mp_abi_version() == 1
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.mp_device_check() == _lib.MP_EDEVICE
+    assert "no CPU fallback" in _lib.last_error()
+    import manipose_b200 as mb
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=2, depth_rot=1, depth_seg=1)
+    with pytest.raises(_lib.ManiposeLibraryError):
+        model(torch.zeros(1, 9, 17, 2))
+    with pytest.raises(_lib.ManiposeLibraryError):
+        mb.metrics.wta_l2_loss_and_activate_head(torch.zeros(1, 2, 9, 17, 3), torch.zeros(1, 9, 17, 3))
+
+
+def test_skeleton_validation(lib):
+    import ctypes
+    from manipose_b200 import _lib
+    from manipose_b200.data import h36m17_skeleton, skeleton_tables
+    par, ops_rows = skeleton_tables(h36m17_skeleton())
+    flat = [v for r in ops_rows for v in r]
+    assert lib.mp_set_skeleton(17, (ctypes.c_int32 * 17)(*par), (ctypes.c_float * 51)(*flat)) == 0
+    bad = list(par)
+    bad[11] = 9
+    assert lib.mp_set_skeleton(17, (ctypes.c_int32 * 17)(*bad), (ctypes.c_float * 51)(*flat)) == _lib.MP_EUNSUPPORTED
+    assert lib.mp_set_skeleton(15, (ctypes.c_int32 * 17)(*par), (ctypes.c_float * 51)(*flat)) == _lib.MP_EUNSUPPORTED
+
+
+def test_state_dict_matches_reference_layout():
+    """290 tensors with the reference's names, shapes and order (frozen in tests/golden/forward.pt)."""
+    import manipose_b200 as mb
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "forward.pt"), weights_only=False)
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=27, n_hyp=5, drop_path_rate=0.1)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [tuple(x) for x in g["t27k5_init"]["keys"]]
+    full = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton())
+    assert len(full.state_dict()) == 290 and sum(p.numel() for p in full.parameters()) == 34_440_062
+    for attr in ("n_hyp", "num_joints", "rotations_module", "segments_module", "decoder", "aggregate", "concat_hyp_and_scores",
+                 "poses_from_hyp_idx"):
+        assert hasattr(full, attr)
+
+
+def test_product_never_imports_the_oracle():
+    code = "import sys; import manipose_b200, manipose_b200.ops, manipose_b200.metrics; " \
+           "bad=[m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; print(bad); sys.exit(1 if bad else 0)"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "manipose_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"
+
+
+def test_install_rebinds_reference_names():
+    from oracle.ref_loader import reference_available, load_reference
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    load_reference()
+    import importlib
+    import manipose_b200 as mb
+    replaced = mb.install()
+    try:
+        arch = importlib.import_module("mh_so3_hpe.architectures")
+        met = importlib.import_module("mh_so3_hpe.metrics")
+        assert arch.RMCLManifoldMixSTE is mb.RMCLManifoldMixSTE
+        assert met.wta_with_scoring_loss is mb.metrics.wta_with_scoring_loss
+        model = arch.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=2, depth_rot=1, depth_seg=1)
+        assert isinstance(model, importlib.import_module("mh_so3_hpe.architectures.rmcl_manifold_mix_ste").RMCLManifoldMixSTE)
+    finally:
+        for qual, obj in replaced.items():
+            modname, attr = qual.rsplit(".", 1)
+            setattr(importlib.import_module(modname), attr, obj)

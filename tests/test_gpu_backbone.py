@@ -1,0 +1,207 @@
+"""Backbone kernels (tcgen05 GEMM, attention, LayerNorm family, embeddings, heads) against fp32 restatements of the same
+op, then the whole forward against the CPU oracle / the reference fixtures.
+
+Tolerances: the backbone computes in bf16 with fp32 accumulation (BASELINE.json: "the bf16 backbone tolerance is stated
+separately"): per-op outputs are compared with an fp32 reference evaluated on the SAME bf16-rounded inputs and must agree
+to bf16 output rounding (rtol 1e-2, atol scaled to the output magnitude).  End to end, aggregated MPJPE must be within
+0.05 mm of the oracle (north_star)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import manipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (4131, 1536, 512), (1000, 512, 512), (4131, 1024, 512), (777, 512, 1024),
+                                   (3888, 384, 128), (3888, 128, 128), (500, 256, 128), (129, 128, 256), (1, 128, 64)])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_vs_fp32(m, n, k, epi):
+    from manipose_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(m + n + k + epi)
+    a = _bf(torch.randn(m, k, generator=gen, device="cuda"))
+    w = _bf(torch.randn(n, k, generator=gen, device="cuda") / math.sqrt(k))
+    bias = torch.randn(n, generator=gen, device="cuda")
+    resid = _bf(torch.randn(m, n, generator=gen, device="cuda"))
+    out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, bias, out, epi, resid=resid if epi == 2 else None)
+    ref = a.float() @ w.float().t() + bias
+    if epi == 1:
+        ref = F.gelu(ref)
+    if epi == 2:
+        ref = ref + resid.float()
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=2e-2)
+    # in-place residual (Y aliases resid), as the trunk uses it
+    if epi == 2:
+        y = resid.clone()
+        ops.gemm(a, w, bias, y, 2, resid=y)
+        torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=2e-2)
+
+
+def test_gemm_is_deterministic_and_persistent_over_many_tiles():
+    from manipose_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    m, n, k = 66096, 1536, 512          # 16 clips x 243 x 17 tokens: 517 x 6 tiles over 148 CTAs
+    a = _bf(torch.randn(m, k, generator=gen, device="cuda"))
+    w = _bf(torch.randn(n, k, generator=gen, device="cuda") / math.sqrt(k))
+    bias = torch.randn(n, generator=gen, device="cuda")
+    o1 = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+    o2 = torch.empty_like(o1)
+    ops.gemm(a, w, bias, o1, 0)
+    ops.gemm(a, w, bias, o2, 0)
+    assert torch.equal(o1, o2)
+    ref = a.float() @ w.float().t() + bias
+    torch.testing.assert_close(o1.float(), ref, rtol=1e-2, atol=2e-2)
+
+
+def _attn_ref(qkv, n_clips, n_frames, n_tok, c, heads, temporal):
+    hd = c // heads
+    x = qkv.float().reshape(n_clips, n_frames, n_tok, 3, heads, hd)
+    q, k, v = x[:, :, :, 0], x[:, :, :, 1], x[:, :, :, 2]           # [B, L, J, H, hd]
+    if temporal:
+        q, k, v = (t.permute(0, 2, 3, 1, 4) for t in (q, k, v))      # [B, J, H, L, hd]
+    else:
+        q, k, v = (t.permute(0, 1, 3, 2, 4) for t in (q, k, v))      # [B, L, H, J, hd]
+    att = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    o = att.softmax(-1) @ v
+    o = o.permute(0, 3, 1, 2, 4) if temporal else o.permute(0, 1, 3, 2, 4)   # -> [B, L, J, H, hd]
+    return o.reshape(n_clips * n_frames * n_tok, c)
+
+
+@pytest.mark.parametrize("n_clips,n_frames,n_tok,c,temporal", [
+    (2, 243, 17, 512, True), (2, 243, 17, 512, False), (3, 27, 17, 512, True), (3, 27, 17, 512, False),
+    (1, 81, 17, 512, True), (2, 243, 16, 128, True), (2, 243, 16, 128, False), (2, 9, 16, 128, True), (1, 1, 17, 512, True)])
+def test_attention_vs_fp32(n_clips, n_frames, n_tok, c, temporal):
+    from manipose_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(n_frames + c)
+    n = n_clips * n_frames * n_tok
+    qkv = _bf(torch.randn(n, 3 * c, generator=gen, device="cuda") * 1.5)
+    out = torch.full((n, c), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.attention(qkv, out, n_clips, n_frames, n_tok, c, 8, 1 if temporal else 0)
+    ref = _attn_ref(qkv, n_clips, n_frames, n_tok, c, 8, temporal)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("c", [512, 128])
+def test_layernorm_family(c):
+    from manipose_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(c)
+    n_tok, n_frames, n_clips = (17, 9, 3) if c == 512 else (16, 9, 3)
+    n = n_clips * n_frames * n_tok
+    x = _bf(torch.randn(n, c, generator=gen, device="cuda") * 2 + 0.5)
+    pg, pb, lg, lb = (torch.randn(c, generator=gen, device="cuda") for _ in range(4))
+    pos = torch.randn(n_frames, c, generator=gen, device="cuda")
+    xo = torch.empty_like(x)
+    ho = torch.empty_like(x)
+    ops.layernorm(x, xo, ho, post=(pg, pb), post_eps=1e-6, pos=pos, pos_div=n_tok, pos_mod=n_frames, ln=(lg, lb), ln_eps=1e-6)
+    xr = F.layer_norm(x.float(), (c,), pg, pb, 1e-6).reshape(n_clips, n_frames, n_tok, c) + pos[None, :, None]
+    xr = xr.reshape(n, c)
+    torch.testing.assert_close(xo.float(), xr, rtol=1e-2, atol=2e-2)
+    hr = F.layer_norm(xo.float(), (c,), lg, lb, 1e-6)
+    torch.testing.assert_close(ho.float(), hr, rtol=1e-2, atol=3e-2)
+    h2 = torch.empty_like(x)
+    ops.layernorm(x, None, h2, ln=(lg, lb), ln_eps=1e-6)
+    torch.testing.assert_close(h2.float(), F.layer_norm(x.float(), (c,), lg, lb, 1e-6), rtol=1e-2, atol=3e-2)
+
+
+def _sd_to(sd, dev):
+    return {k: v.to(dev) for k, v in sd.items()}
+
+
+def _model_from_sd(sd, num_frame, n_hyp, **kw):
+    import manipose_b200 as mb
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=num_frame, n_hyp=n_hyp, **kw)
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def _mpjpe_mm(pred, y):
+    return float((pred - y).norm(dim=-1).mean() * 1000.0)
+
+
+@pytest.mark.parametrize("T,K,B", [(27, 5, 3), (9, 1, 2), (81, 10, 2)])
+def test_forward_vs_oracle_synthetic_weights(T, K, B):
+    """Whole forward on seeded synthetic weights (pos-embeds and LN affines perturbed) vs the fp32 CPU oracle."""
+    sd = O.make_state_dict(num_frame=T, n_hyp=K, seed=3)
+    x = 0.3 * torch.randn(B, T, 17, 2, generator=torch.Generator().manual_seed(77))
+    with torch.no_grad():
+        rot_ref, sc_ref, _ = O.rotations_module(x, sd)
+        bones_ref = O.segments_module(x, sd)
+        poses_ref, scores_ref = O.rmcl_forward(x, sd)
+    m = _model_from_sd(sd, T, K)
+    with torch.no_grad():
+        poses, scores = m(x.cuda())
+        rot, sc = m.rotations_module(x.cuda())
+        bones = m.segments_module(x.cuda())
+    assert poses.shape == (B, K, T, 17, 3) and scores.shape == (B, K, T, 1)
+    # bf16 backbone tolerance (stated separately from the fp32 decoder's 1e-5): relative L2 of the 6-D outputs <= 3e-2,
+    # bone lengths <= 2e-2 relative L2, scores <= 1e-2 absolute
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    assert rel(rot.cpu(), rot_ref) <= 3e-2
+    assert rel(bones.cpu(), bones_ref) <= 2e-2
+    assert float((scores.cpu() - scores_ref).abs().max()) <= 1e-2
+    torch.testing.assert_close(scores.sum(1).cpu(), torch.ones(B, T, 1), rtol=1e-5, atol=1e-6)
+    # the decoder itself is exact given identical inputs: feed the GPU rot / bones to the oracle decoder
+    want = O.pose_decoder(rot.cpu().reshape(B * K * T, 17, 6), bones.cpu(), torch.zeros(B * K * T, 3)).reshape(B, K, T, 17, 3)
+    assert torch.equal(poses.cpu(), want)
+    # end-to-end MPJPE gate (north_star: within 0.05 mm) against a synthetic target
+    y = 0.3 * torch.randn(B, T, 17, 3, generator=torch.Generator().manual_seed(5))
+    agg = m.aggregate(poses, scores, "weighted_ave").cpu()
+    agg_ref = O.aggregate(poses_ref, scores_ref, "weighted_ave")
+    assert abs(_mpjpe_mm(agg, y) - _mpjpe_mm(agg_ref, y)) <= 0.05
+
+
+def test_forward_vs_reference_golden():
+    """Fixtures frozen from the UNMODIFIED reference (scripts/make_goldens.py): seed-42 init and a perturbed variant.  Weights are
+    rebuilt here from the same seeds through our own module tree, which must reproduce the reference's parameter checksum."""
+    import manipose_b200 as mb
+    g = torch.load(os.path.join(GOLD, "forward.pt"), weights_only=False)
+    for tag in ("t27k5_synth",):
+        e = g[tag]
+        sd = O.make_state_dict(num_frame=e["T"], n_hyp=e["K"], seed=e["seed"])
+        chk = (float(sum(t.double().sum() for t in sd.values())), float(sum(t.double().abs().sum() for t in sd.values())))
+        assert chk == tuple(e["checksum"])
+        m = _model_from_sd(sd, e["T"], e["K"])
+        with torch.no_grad():
+            poses, scores = m(e["x"].cuda())
+        y = 0.3 * torch.randn(*e["x"].shape[:3], 3, generator=torch.Generator().manual_seed(5))
+        agg = m.aggregate(poses, scores, "weighted_ave").cpu()
+        agg_ref = (e["poses"] * e["scores"].unsqueeze(-1)).sum(1)
+        assert abs(_mpjpe_mm(agg, y) - _mpjpe_mm(agg_ref, y)) <= 0.05
+        assert float((scores.cpu() - e["scores"]).abs().max()) <= 1e-2
+
+
+def test_default_config_forward_runs_at_t243():
+    """config.yaml defaults (T=243, K=5, 8x512 / 2x128), micro-batched: B larger than one micro-batch, result independent of the
+    micro-batch split (per-clip independence: SURVEY.md §8e)."""
+    import manipose_b200 as mb
+    torch.manual_seed(42)
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), drop_path_rate=0.1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())) * 0.02)
+    m = m.cuda().eval()
+    x = 0.3 * torch.randn(12, 243, 17, 2, generator=torch.Generator().manual_seed(1234)).cuda()
+    with torch.no_grad():
+        poses, scores = m(x)
+        m.rotations_module.micro_batch_tokens = 3 * 243 * 17
+        m.segments_module.micro_batch_tokens = 3 * 243 * 17
+        poses2, scores2 = m(x)
+    assert poses.shape == (12, 5, 243, 17, 3) and torch.isfinite(poses).all()
+    assert torch.equal(poses, poses2) and torch.equal(scores, scores2)
+    assert bool((poses[:, :, :, 0] == 0).all())
+    with pytest.raises(RuntimeError):
+        m(x[:, :100])   # T must equal num_frame, like the reference (Temporal_pos_embed shape)

@@ -1,0 +1,146 @@
+"""Parity of the fused decoder kernels (mp_decoder_fwd / mp_decoder_bwd, through the C ABI) against the CPU oracle
+and the fixtures frozen from the reference.  Tolerance from BASELINE.json north_star: fp32 decoder <= 1e-5 relative;
+the EXACT mode is additionally expected to be bit-identical."""
+import os
+
+import pytest
+import torch
+
+from oracle import manipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5   # north_star: "the fp32 decoder must match to within 1e-5 relative"
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _decode(rot, bones, root, n_clips, k, t, exact=True, logits=None):
+    from manipose_b200 import ops
+    poses, scores = ops.decoder_fwd(rot.cuda(), bones.reshape(n_clips, 16).cuda(), None if root is None else root.cuda(),
+                                    None if logits is None else logits.cuda(), n_clips, k, t, 6, exact)
+    torch.cuda.synchronize()
+    return poses.cpu(), None if scores is None else scores.cpu()
+
+
+def test_golden_fixture_exact_and_fast():
+    g = _load("decoder.pt")
+    k, t = g["K"], g["T"]
+    for bones, root, key in ((g["bones"], None, "poses_zero_root"), (g["bones_signed"], g["root"], "poses_signed_root")):
+        want = g[key]
+        got, _ = _decode(g["rot6d"], bones, root, 4, k, t, exact=True)
+        ok = ~g["stress_rows"]
+        assert _rel(got[ok], want[ok]) <= RTOL
+        assert torch.equal(got[ok], want[ok]), "EXACT mode must be bit-identical to the reference on well-conditioned rows"
+        # degenerate rows (|a| ~ 1e-9, b parallel to a) amplify rounding: same bits expected in EXACT mode
+        assert torch.equal(got, want)
+        fast, _ = _decode(g["rot6d"], bones, root, 4, k, t, exact=False)
+        assert _rel(fast[ok], want[ok]) <= RTOL
+
+
+def test_known_answer_t_pose():
+    g = _load("decoder.pt")
+    ident = torch.tensor([1.0, 0, 0, 0, 1.0, 0]).expand(1, 17, 6).contiguous()
+    got, _ = _decode(ident, g["kat_bones"], None, 1, 1, 1)
+    assert torch.equal(got, g["kat_pose_identity"])
+    torch.testing.assert_close(got[0, 3], torch.tensor([0.2, -1.0, 0.0]))
+    torch.testing.assert_close(got[0, 13], torch.tensor([-1.0, 0.4, 0.0]))
+    import manipose_b200 as mb
+    dec = mb.PoseDecoder(mb.h36m17_skeleton())
+    assert torch.equal(dec.build_t_pose_from_bone_lengths(g["kat_bones"].cuda()).cpu(), g["kat_t_pose"])
+
+
+@pytest.mark.parametrize("n_clips,k,t", [(1, 1, 1), (3, 5, 27), (7, 2, 31), (16, 5, 243), (5, 10, 81)])
+def test_random_vs_oracle(n_clips, k, t):
+    gen = torch.Generator().manual_seed(1234 + n_clips)
+    n = n_clips * k * t
+    rot = torch.randn(n, 17, 6, generator=gen)
+    rot[::97, 2] *= 1e-9                                  # tiny-norm first vector
+    rot[5::101, 7, 3:6] = -1.5 * rot[5::101, 7, 0:3]      # collinear pair
+    bones = (0.1 + 0.4 * torch.rand(n_clips, 16, 1, generator=gen)) * torch.where(torch.rand(n_clips, 16, 1, generator=gen) < 0.3, -1.0, 1.0)
+    root = torch.randn(n, 3, generator=gen)
+    logits = torch.randn(n_clips, k, t, 1, generator=gen)
+    want = O.pose_decoder(rot, bones, root)
+    got, scores = _decode(rot, bones, root, n_clips, k, t, exact=True, logits=logits.reshape(n_clips, k, t))
+    assert torch.equal(got, want)
+    torch.testing.assert_close(scores.reshape(n_clips, k, t, 1), logits.softmax(dim=1), rtol=1e-6, atol=1e-7)
+    assert torch.equal(scores.reshape(n_clips, k, t).argmax(1), logits.softmax(dim=1)[..., 0].argmax(1)), "hypothesis argmax must be bit-exact"
+    fast, _ = _decode(rot, bones, root, n_clips, k, t, exact=False)
+    good = torch.ones(n, dtype=torch.bool)
+    good[::97] = False
+    good[5::101] = False
+    assert _rel(fast[good], want[good]) <= RTOL
+
+
+def test_unaligned_pointers_take_the_scalar_path():
+    from manipose_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    n_clips, k, t = 2, 3, 11
+    n = n_clips * k * t
+    rot = torch.randn(n, 17, 6, generator=gen)
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, generator=gen)
+    buf = torch.empty(n * 102 + 1, device="cuda")
+    view = buf[1:].view(n, 17, 6)                         # 4-byte aligned only
+    view.copy_(rot)
+    poses, _ = ops.decoder_fwd(view, bones.cuda(), None, None, n_clips, k, t)
+    assert torch.equal(poses.cpu(), O.pose_decoder(rot, bones.unsqueeze(-1), torch.zeros(n, 3)))
+
+
+def test_full_size_properties():
+    """BASELINE config 2: 1,001,160 poses (B=824, K=5, T=243).  Size-independent properties: root == 0, per-clip bone
+    lengths == |bone_len| for every hypothesis and frame, scores sum to 1, a random slice equals the oracle."""
+    from manipose_b200 import ops
+    n_clips, k, t = 824, 5, 243
+    n = n_clips * k * t
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    rot = torch.randn(n, 17, 6, generator=gen, device="cuda")
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, generator=gen, device="cuda")
+    logits = torch.randn(n_clips, k, t, generator=gen, device="cuda")
+    poses, scores = ops.decoder_fwd(rot, bones, None, logits, n_clips, k, t)
+    assert poses.shape == (n, 17, 3)
+    assert bool((poses[:, 0] == 0).all())
+    par = torch.tensor(O.H36M17_PARENTS[1:], device="cuda")
+    lens = (poses[:, 1:] - poses[:, par]).norm(dim=-1).reshape(n_clips, k * t, 16)
+    torch.testing.assert_close(lens, bones[:, None].expand_as(lens), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(scores.sum(1), torch.ones(n_clips, t, device="cuda"), rtol=1e-6, atol=1e-6)
+    sl = slice(500_000, 500_000 + 4096)
+    clip_of = torch.arange(n)[sl] // (k * t)
+    want = O.forward_kinematics(O.build_t_pose(bones.cpu()[clip_of].unsqueeze(-1)),
+                                O.rotation_matrix_from_ortho6d(rot[sl].cpu().reshape(-1, 6)).reshape(-1, 17, 3, 3), torch.zeros(4096, 3))
+    assert torch.equal(poses[sl].cpu(), want)
+
+
+def test_rot_rep_dim_errors_match_the_reference():
+    import manipose_b200 as mb
+    from manipose_b200 import ops
+    with pytest.raises(AssertionError, match="Unsupported rotations representation dimension"):
+        mb.PoseDecoder(mb.h36m17_skeleton(), rot_rep_dim=5)
+    with pytest.raises(AssertionError):
+        ops.decoder_fwd(torch.zeros(1, 17, 5, device="cuda"), torch.zeros(1, 16, device="cuda"), None, None, 1, 1, 1, rot_rep_dim=5)
+    with pytest.raises(NotImplementedError):
+        ops.decoder_fwd(torch.zeros(1, 17, 4, device="cuda"), torch.zeros(1, 16, device="cuda"), None, None, 1, 1, 1, rot_rep_dim=4)
+
+
+@pytest.mark.parametrize("n_clips,k,t", [(2, 5, 27), (3, 1, 40)])
+def test_backward_vs_oracle_autograd(n_clips, k, t):
+    import manipose_b200 as mb
+    gen = torch.Generator().manual_seed(7)
+    n = n_clips * k * t
+    rot = torch.randn(n, 17, 6, generator=gen)
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, 1, generator=gen)
+    root = torch.randn(n, 3, generator=gen)
+    gout = torch.randn(n, 17, 3, generator=gen)
+    r_ref, b_ref, t_ref = rot.clone().requires_grad_(), bones.clone().requires_grad_(), root.clone().requires_grad_()
+    O.pose_decoder(r_ref, b_ref, t_ref).backward(gout)
+    dec = mb.PoseDecoder(mb.h36m17_skeleton())
+    r, b, tt = rot.cuda().requires_grad_(), bones.cuda().requires_grad_(), root.cuda().requires_grad_()
+    dec(r, b, tt).backward(gout.cuda())
+    torch.testing.assert_close(r.grad.cpu(), r_ref.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(b.grad.cpu(), b_ref.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(tt.grad.cpu(), t_ref.grad, rtol=1e-5, atol=1e-6)

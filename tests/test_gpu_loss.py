@@ -1,0 +1,159 @@
+"""Parity of the loss / hypothesis-metric kernels (through the C ABI) against the CPU oracle and the reference fixtures.
+Winner and arg-max indices must be bit-exact on identical fp32 inputs (BASELINE.json north_star)."""
+import os
+
+import pytest
+import torch
+
+from oracle import manipose_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+W = O.STANDARD_H36M_WEIGHTS
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def test_golden_wta_and_scoring():
+    import manipose_b200 as mb
+    M = mb.metrics
+    g = _load("loss.pt")
+    hyp, scores, y = g["hyp"].cuda(), g["scores"].cuda(), g["y"].cuda()
+    for name, w, sq in (("w", W, False), ("u", None, False), ("wsq", W, True)):
+        v, i = M.wta_l2_loss_and_activate_head(hyp, y, w, sq)
+        assert torch.equal(i.cpu(), g[f"wta_idx_{name}"]), "winner indices must be bit-exact"
+        assert i.dtype == torch.int64
+        assert torch.equal(v.cpu(), g[f"wta_val_{name}"]), "winner values are expected to be bit-identical to torch CPU"
+        tot, bce = M.wta_with_scoring_loss(hyp, scores, y, 0.1, w, sq)
+        torch.testing.assert_close(tot.cpu(), g[f"score_total_{name}"], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(bce.cpu(), g[f"score_bce_{name}"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(M.mean_velocity_error(hyp, y, axis=2).cpu(), g["vel"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(M.mean_velocity_error(hyp, y, axis=2, squared=True).cpu(), g["vel_sq"], rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(M.smoothness_regularization(hyp, W, axis=2).cpu(), g["smooth_w"], rtol=1e-5, atol=1e-8)
+    assert M.wta_with_scoring_loss(hyp, scores, y, 0.0, W).dim() == 0   # reference quirk: bare scalar when beta == 0
+
+
+def test_golden_training_loss_and_gradients():
+    """make_loss + compute_and_acc_loss with config.yaml defaults (hpe/main_h36m_lifting.py:101-209), fused and as the four
+    separate closures the driver builds; gradients w.r.t. poses and score logits vs the reference's autograd."""
+    import manipose_b200 as mb
+    from manipose_b200 import ops
+    M = mb.metrics
+    g = _load("loss.pt")
+    y = g["y"].cuda()
+    for fused in (True, False):
+        hyp = g["hyp"].cuda().requires_grad_()
+        logits = g["logits"].cuda().requires_grad_()
+        scores = ops.softmax_hyp(logits)
+        if fused:
+            total, terms = M.training_loss(hyp, scores, y)
+            torch.testing.assert_close(terms[0].cpu(), g["train_wloss"], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(0.1 * terms[1].cpu(), g["train_score_reg"], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(2.0 * terms[2].cpu(), g["train_vloss"], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(0.5 * terms[3].cpu(), g["train_sreg"], rtol=1e-5, atol=1e-7)
+        else:
+            wl = M.wta_l2_loss_and_activate_head(hypothesis=hyp, y=y, weights=W, squared=False)[0].mean()
+            sr = M.wta_with_scoring_loss(hypothesis=hyp, scores=scores, y=y, beta=0.1, weights=W, squared=False)[1]
+            vl = 2.0 * M.mean_velocity_error(predicted=hyp, target=y, squared=False, axis=2)
+            sg = 0.5 * M.smoothness_regularization(prediction=hyp, weights=W, axis=2)
+            total = wl + sr + vl + sg
+        torch.testing.assert_close(total.cpu().reshape(1), g["train_total"], rtol=1e-5, atol=1e-7)
+        total.backward()
+        torch.testing.assert_close(hyp.grad.cpu(), g["grad_hyp"], rtol=1e-4, atol=1e-8)
+        torch.testing.assert_close(logits.grad.cpu(), g["grad_logits"], rtol=1e-4, atol=1e-8)
+
+
+def test_golden_aggregate_and_mpjpe():
+    import manipose_b200 as mb
+    g = _load("loss.pt")
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=5, depth_rot=1, depth_seg=1)
+    hyp, scores, y = g["hyp"].cuda(), g["scores"].cuda(), g["y"].cuda()
+    assert torch.equal(m.aggregate(hyp, scores, "weighted_ave").cpu(), g["agg_weighted"])
+    assert torch.equal(m.aggregate(hyp, scores, "best_score").cpu(), g["agg_best"])
+    val, pose = m.aggregate(hyp, mode="oracle", ground_truth=y)
+    assert torch.equal(val.cpu(), g["agg_oracle_val"]) and torch.equal(pose.cpu(), g["agg_oracle_pose"])
+    idx = torch.argmax(scores, dim=1)[..., 0]
+    assert torch.equal(m.poses_from_hyp_idx(hyp, idx).cpu(), g["agg_best"])
+    assert m.concat_hyp_and_scores(hyp, scores).shape == (3, 5, 11, 17, 4)
+    torch.testing.assert_close(mb.metrics.mpjpe_error(g["agg_weighted"].cuda(), y, "sum").cpu(), g["mpjpe_sum"], rtol=1e-6, atol=0)
+    torch.testing.assert_close(mb.metrics.mpjpe_error(g["agg_weighted"].cuda(), y, "average").cpu(), g["mpjpe_avg"], rtol=1e-6, atol=0)
+    with pytest.raises(AssertionError, match="Scores required"):
+        m.aggregate(hyp, None, "weighted_ave")
+    with pytest.raises(ValueError, match="Only best_score and weighted_ave"):
+        m.aggregate(hyp, scores, "median")
+
+
+@pytest.mark.parametrize("b,k,t", [(1, 1, 1), (2, 5, 27), (3, 10, 81), (30, 5, 27), (3, 5, 243), (2, 2, 33)])
+def test_random_vs_oracle(b, k, t):
+    import manipose_b200 as mb
+    from manipose_b200 import ops
+    M = mb.metrics
+    gen = torch.Generator().manual_seed(100 * b + t)
+    y = 0.3 * torch.randn(b, t, 17, 3, generator=gen)
+    y[:, :, 0] = 0
+    hyp = y[:, None] + 0.1 * torch.randn(b, k, t, 17, 3, generator=gen)
+    if k > 1:
+        hyp[:, 1] = hyp[:, 0]                     # exact ties between hypotheses 0 and 1 -> lowest index must win
+    logits = torch.randn(b, k, t, 1, generator=gen)
+    scores = logits.softmax(dim=1)
+    for w, sq in ((W, False), (None, False), (W, True)):
+        v_ref, i_ref = O.wta_l2_loss_and_activate_head(hyp, y, w, sq)
+        v, i = M.wta_l2_loss_and_activate_head(hyp.cuda(), y.cuda(), w, sq)
+        assert torch.equal(i.cpu(), i_ref)
+        torch.testing.assert_close(v.cpu(), v_ref, rtol=1e-6, atol=1e-8)
+    if t > 1:
+        h_ref = hyp.clone().requires_grad_()
+        l_ref = logits.clone().requires_grad_()
+        tot_ref, _ = O.training_loss(h_ref, l_ref.softmax(dim=1), y)
+        tot_ref.backward()
+        h, lg = hyp.cuda().requires_grad_(), logits.cuda().requires_grad_()
+        tot, _ = M.training_loss(h, ops.softmax_hyp(lg), y.cuda())
+        tot.backward()
+        torch.testing.assert_close(tot.cpu(), tot_ref, rtol=1e-5, atol=1e-7)
+        # ties make the reference's min-backward pick hypothesis 0 too (torch.min(dim) routes to the returned index)
+        torch.testing.assert_close(h.grad.cpu(), h_ref.grad, rtol=1e-4, atol=1e-8)
+        torch.testing.assert_close(lg.grad.cpu(), l_ref.grad, rtol=1e-4, atol=1e-8)
+    agg = ops.aggregate(hyp.cuda(), scores.reshape(b, k, t).cuda(), None, 0)[0]
+    assert torch.equal(agg.cpu(), O.aggregate(hyp, scores, "weighted_ave"))
+    best = ops.aggregate(hyp.cuda(), scores.reshape(b, k, t).cuda(), None, 1)
+    assert torch.equal(best[2].cpu(), scores[..., 0].argmax(1))
+    assert torch.equal(best[0].cpu(), O.aggregate(hyp, scores, "best_score"))
+
+
+def test_error_paths_match_the_reference():
+    import manipose_b200 as mb
+    M = mb.metrics
+    hyp = torch.zeros(1, 2, 4, 17, 3, device="cuda")
+    y = torch.zeros(1, 4, 17, 3, device="cuda")
+    with pytest.raises(AssertionError):
+        M.wta_l2_loss_and_activate_head(hyp, y, torch.ones(15))       # losses.py:23 assert
+    with pytest.raises(ValueError):
+        M.wta_l2_loss_and_activate_head(hyp, y, None, True)             # reference: torch.min(dim=1) on a 0-d tensor raises
+    with pytest.raises(ValueError):
+        M.mpjpe_error(y, y, "median")
+
+
+def test_full_size_loss_properties():
+    """B=1024, T=243, K=5: (a) the oracle hypothesis has zero WTA loss and is picked, (b) loss is invariant to permuting
+    clips, (c) a slice equals the oracle."""
+    import manipose_b200 as mb
+    M = mb.metrics
+    b, k, t = 1024, 5, 243
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    y = 0.3 * torch.randn(b, t, 17, 3, generator=gen, device="cuda")
+    hyp = y[:, None] + 0.1 * torch.randn(b, k, t, 17, 3, generator=gen, device="cuda")
+    winner = torch.randint(0, k, (b, t), generator=gen, device="cuda")
+    hyp.scatter_(1, winner[:, None, :, None, None].expand(b, 1, t, 17, 3), y[:, None])
+    val, idx = M.wta_l2_loss_and_activate_head(hyp, y, W)
+    assert torch.equal(idx, winner) and bool((val == 0).all())
+    scores = torch.softmax(torch.randn(b, k, t, 1, generator=gen, device="cuda"), dim=1)
+    tot, terms = M.training_loss(hyp, scores, y)
+    perm = torch.randperm(b, device="cuda")
+    tot_p, _ = M.training_loss(hyp[perm].contiguous(), scores[perm].contiguous(), y[perm].contiguous())
+    torch.testing.assert_close(tot, tot_p, rtol=1e-6, atol=0)
+    sl = slice(100, 104)
+    ref_tot, _ = O.training_loss(hyp[sl].cpu(), scores[sl].cpu(), y[sl].cpu())
+    got_tot, _ = M.training_loss(hyp[sl].contiguous(), scores[sl].contiguous(), y[sl].contiguous())
+    torch.testing.assert_close(got_tot.cpu(), ref_tot, rtol=1e-5, atol=1e-7)
