@@ -58,8 +58,8 @@ int mp_set_skeleton(int num_joints, const int32_t* host_parents, const float* ho
  *   root    [n_poses, 3] or NULL (= zeros, what the reference passes)
  *   logits  [n_clips, n_hyp, n_frames] or NULL; scores (same shape) = softmax over n_hyp
  *   poses   [n_poses, 17, 3] fp32 */
-#define MP_DEC_EXACT 0 /* same IEEE fp32 operations in the same order as the reference's torch-CPU path:
-                          poses bit-identical to the oracle (default)                                */
+#define MP_DEC_EXACT 0 /* one correctly-rounded IEEE fp32 operation per reference operation, same order:
+                          bit-identical to oracle.pose_decoder_ieee, ~1e-7 from torch CPU (default)  */
 #define MP_DEC_FAST 1  /* rsqrt + FMA contraction: <= 1e-6 relative difference, fewer instructions   */
 int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root, const float* logits,
                    float* poses, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames,
@@ -88,7 +88,8 @@ enum {
 };
 /* _l2_loss_per_hyp + torch.min(dim=1) (losses.py:104-138): hyp [B,K,T,17,3], y [B,T,17,3],
  * joint_weights[17] or NULL (= ones) -> wta_val [B,T] fp32, wta_idx [B,T] int64 (lowest k on ties),
- * per_hyp [B,K,T] or NULL.  Bit-exact with torch CPU (AVX2 sum order) on identical inputs. */
+ * per_hyp [B,K,T] or NULL.  Same operation order as torch CPU (FMA 3-norm, 8-lane sum of 17, /17): values agree
+ * to 1 ulp (torch's CPU sqrt is not correctly rounded), winner indices are identical on identical inputs. */
 int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int squared,
                float* wta_val, int64_t* wta_idx, float* per_hyp, int64_t B, int64_t K, int64_t T,
                mp_stream_t stream);

@@ -114,7 +114,7 @@ class MixSTE(nn.Module):
     """mix_ste.py:12-191.  ``forward(x[B,L,J,in_chans]) -> [B,L,J,out_dim]``."""
 
     # clips per micro-batch of the trunk; activations of one micro-batch are 5*C*2 bytes per token
-    micro_batch_tokens = 32768
+    micro_batch_tokens = 36000
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
@@ -235,7 +235,9 @@ class MixSTE(nn.Module):
         return b, l, j, cin
 
     def clips_per_micro_batch(self) -> int:
-        return max(1, self.micro_batch_tokens // (self.num_frame * self.num_tokens))
+        """Clips per micro-batch; a multiple of 4 keeps every per-clip output slice 16-byte aligned (bulk-copy paths)."""
+        n = max(1, self.micro_batch_tokens // (self.num_frame * self.num_tokens))
+        return n - n % 4 if n >= 4 else n
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """mix_ste.py:175-191 with the plain head (LayerNorm eps 1e-5 + Linear): [B,L,J,in] -> [B,L,J,out_dim]."""

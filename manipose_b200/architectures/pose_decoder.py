@@ -17,7 +17,7 @@ class PoseDecoder(nn.Module):
         self.rot_rep_dim = rot_rep_dim
         assert rot_rep_dim in [4, 6], f"Unsupported rotations representation dimension: {self.rot_rep_dim}"
         self._tables = skeleton_tables(skeleton)
-        # exact = same IEEE operation sequence as the reference's torch path (bit-identical poses); False = rsqrt + FMA
+        # exact = one correctly-rounded IEEE op per reference op (bit-identical to oracle.pose_decoder_ieee); False = rsqrt + FMA
         self.exact = True
 
     def forward(self, rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor, root_positions: torch.Tensor) -> torch.Tensor:

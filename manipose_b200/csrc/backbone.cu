@@ -407,7 +407,8 @@ int mp_embed_joints(const float* in2d, const float* W, const float* b, const flo
   MP_REQUIRE(C == 512, MP_EUNSUPPORTED, "mp_embed_joints: C=%d (built for 512)", C);
   MP_REQUIRE(in2d && W && b && spos && ln_gamma && ln_beta && x_out && h_out && n_tokens >= 0 && n_joints >= 1, MP_EINVAL,
              "mp_embed_joints: bad arguments");
-  MP_REQUIRE(aligned16(x_out) && aligned16(h_out) && aligned16(in2d), MP_EALIGN, "mp_embed_joints: pointers must be 16-byte aligned");
+  MP_REQUIRE(aligned16(x_out) && aligned16(h_out) && (reinterpret_cast<uintptr_t>(in2d) & 7u) == 0, MP_EALIGN,
+             "mp_embed_joints: x_out / h_out must be 16-byte aligned, in2d 8-byte aligned");
   if (n_tokens == 0) return MP_OK;
   embed_joints_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(
       in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, n_tokens, n_joints);

@@ -12,9 +12,10 @@
 // pose reading its 102 floats as 8-byte conflict-free LDS; the 51 results go back into the same (dead) tile buffer and
 // leave with one bulk async store.  Algorithmic HBM traffic: 408 + 204 bytes per pose (+8 for logit/score).
 //
-// Arithmetic: in EXACT mode every operation is the same IEEE fp32 operation, in the same order, as the reference's
-// PyTorch CPU path (unfused mul/add/sub, sqrt, max, three divisions, sequential k-loop of the 3x3 bmm), so poses
-// are bit-identical to the oracle.  FAST mode uses rsqrt and FMA contraction (<= 1e-6 relative difference).
+// Arithmetic: in EXACT mode every operation is one correctly-rounded IEEE fp32 operation in the reference's order (unfused
+// mul/add/sub, sqrt, max, three divisions, sequential k-loop of the 3x3 products), so poses are bit-identical to the
+// oracle's correctly-rounded restatement (oracle.pose_decoder_ieee) and within ~1e-7 relative of the torch-CPU reference
+// (whose vectorised sqrt is itself 1 ulp off on ~0.7 % of inputs).  FAST mode uses rsqrt and FMA contraction (<= 1e-6).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -145,7 +146,7 @@ template <bool kExact>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
                    const float* __restrict__ logits, float* __restrict__ poses, float* __restrict__ scores, uint32_t n_poses,
-                   uint32_t poses_per_clip, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames, int bulk_ok) {
+                   uint32_t poses_per_clip, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames, int bulk_in, int bulk_out) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,12 +167,13 @@ decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
   for (uint32_t tile_idx = warp_global; tile_idx < n_tiles; tile_idx += warp_stride) {
     const uint32_t pose0 = tile_idx * kTile;
     const uint32_t n_here = min((uint32_t)kTile, n_poses - pose0);
-    const bool full = bulk_ok && (n_here == kTile);
+    const bool full_in = bulk_in && (n_here == kTile);
+    const bool full = bulk_out && (n_here == kTile);
     const float* gin = rot6d + (size_t)pose0 * kIn;
     float* gout = poses + (size_t)pose0 * kOut;
 
     // ---- stage the tile of rot6d into shared memory
-    if (full) {
+    if (full_in) {
       if (lane == 0) {
         ptx::mbar_expect_tx(bar, kTileInBytes);
         ptx::bulk_g2s(tile, gin, kTileInBytes, bar);
@@ -501,7 +503,7 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   MP_REQUIRE((logits == nullptr) == (scores == nullptr), MP_EINVAL, "mp_decoder_fwd: logits and scores go together");
   MP_REQUIRE(aligned16(bone_len), MP_EALIGN, "mp_decoder_fwd: bone_len must be 16-byte aligned");
 
-  const int bulk_ok = aligned16(rot6d) && aligned16(poses);
+  const int bulk_in = aligned16(rot6d), bulk_out = aligned16(poses);   // unaligned views fall back to coalesced LDG / STG
   const size_t smem = (size_t)kWarpsPerCta * kTileInBytes + kWarpsPerCta * sizeof(uint64_t);
   const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
   int64_t ctas = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -511,7 +513,7 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(
         rot6d, bone_len, root, logits, poses, scores, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), (uint32_t)n_clips,
-        (uint32_t)n_hyp, (uint32_t)n_frames, bulk_ok);
+        (uint32_t)n_hyp, (uint32_t)n_frames, bulk_in, bulk_out);
   };
   if (flags & MP_DEC_FAST)
     launch(decoder_fwd_kernel<false>);

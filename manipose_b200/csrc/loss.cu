@@ -23,7 +23,8 @@ namespace {
 
 constexpr int kF = kJ * 3;                 // 51 floats per frame
 constexpr int kTileFrames = 32;
-constexpr int kStageFloats = 34 * kF + 8;  // 32 frames + halo each side + alignment shift, multiple of 4
+constexpr int kStageFloats = 34 * kF + 10; // 32 frames + halo each side + alignment shift; 1744 = multiple of 4 floats (16 B)
+static_assert(kStageFloats % 4 == 0, "stage buffers must stay 16-byte aligned for cp.async");
 constexpr int kStageBytes = kStageFloats * 4;
 constexpr int kLossWarps = 8;
 constexpr int kMaxPartialWarps = 148 * 2 * kLossWarps;

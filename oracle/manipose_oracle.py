@@ -151,6 +151,64 @@ def pose_decoder(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor,
     return forward_kinematics(t_pose, mats, root_positions, parents)
 
 
+def pose_decoder_ieee(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor, root_positions: torch.Tensor,
+                      parents=H36M17_PARENTS, operators=H36M17_T_POSE_OPERATORS) -> torch.Tensor:
+    """The same algorithm as ``pose_decoder`` (rot_rep_dim = 6) restated in numpy float32, where every +, -, *, / and sqrt is
+    one correctly-rounded IEEE-754 operation and nothing is fused or reassociated: sum of squares as (x^2 + y^2) + z^2
+    (rotation_tools.py:6-17), cross products as two products and a subtraction (:21-32), 3x3 products as
+    ((a0 b0 + a1 b1) + a2 b2) (forward_kinematics.py:31-40), T-pose by cumulative adds with the offset recovered by
+    subtraction (pose_decoder.py:115-119, forward_kinematics.py:31-33).
+
+    Why it exists: torch's CPU ``sqrt`` on this build (MKL/AVX-512 path) is NOT correctly rounded (0.7 % of inputs are 1 ulp
+    off, measured in this container), so ``pose_decoder`` itself is only reproducible to ~1e-7 across platforms.  This
+    restatement is the bit-exact target for the CUDA decoder's EXACT mode; tests pin it to ``pose_decoder`` / the reference
+    fixtures within 1e-6 relative."""
+    import numpy as np
+    r = rotations_repr.detach().cpu().numpy().astype(np.float32)
+    n, nj, _ = r.shape
+    b = bones_lengths_repr.shape[0]
+    assert n % b == 0
+    lens = np.repeat(bones_lengths_repr.detach().cpu().numpy().astype(np.float32).reshape(b, -1), n // b, axis=0)   # [N,16]
+    root = root_positions.detach().cpu().numpy().astype(np.float32)
+    eps = np.float32(1e-8)
+
+    def normalize(x, y, z):
+        m = np.maximum(np.sqrt((x * x + y * y) + z * z), eps)
+        return x / m, y / m, z / m
+
+    def cross(u, v):
+        return (u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0])
+
+    kids = has_children(parents)
+    rw = [None] * nj     # world rotations as [row][col] lists of [N] arrays
+    pos = [None] * nj
+    tp = [None] * nj     # T-pose x / y
+    for j in range(nj):
+        a = [r[:, j, i] for i in range(6)]
+        x = normalize(a[0], a[1], a[2])
+        z = normalize(*cross(x, (a[3], a[4], a[5])))
+        y = cross(z, x)
+        rl = [[x[i], y[i], z[i]] for i in range(3)]          # rows of the local rotation, columns [x y z]
+        if parents[j] == -1:
+            rw[j] = rl
+            pos[j] = [root[:, 0], root[:, 1], root[:, 2]]
+            tp[j] = [np.zeros(n, np.float32), np.zeros(n, np.float32)]
+            continue
+        p = parents[j]
+        op = operators[j]
+        ax = 0 if op[0] != 0 else 1
+        step = lens[:, j - 1] if op[ax] > 0 else -lens[:, j - 1]
+        tp[j] = list(tp[p])
+        tp[j][ax] = tp[p][ax] + step
+        off = tp[j][ax] - tp[p][ax]
+        rp = rw[p]
+        w = [[(rp[row][0] * rl[0][col] + rp[row][1] * rl[1][col]) + rp[row][2] * rl[2][col] for col in range(3)] for row in range(3)]
+        pos[j] = [w[row][ax] * off + pos[p][row] for row in range(3)]
+        rw[j] = w if kids[j] else None
+    out = np.stack([np.stack(pj, axis=-1) for pj in pos], axis=1)
+    return torch.from_numpy(out)
+
+
 # --------------------------------------------------------------------------------------
 # B1-B5: MixSTE backbone   (hpe/mh_so3_hpe/architectures/mix_ste.py)
 # --------------------------------------------------------------------------------------

@@ -155,7 +155,7 @@ def test_forward_vs_oracle_synthetic_weights(T, K, B):
     assert float((scores.cpu() - scores_ref).abs().max()) <= 1e-2
     torch.testing.assert_close(scores.sum(1).cpu(), torch.ones(B, T, 1), rtol=1e-5, atol=1e-6)
     # the decoder itself is exact given identical inputs: feed the GPU rot / bones to the oracle decoder
-    want = O.pose_decoder(rot.cpu().reshape(B * K * T, 17, 6), bones.cpu(), torch.zeros(B * K * T, 3)).reshape(B, K, T, 17, 3)
+    want = O.pose_decoder_ieee(rot.cpu().reshape(B * K * T, 17, 6), bones.cpu(), torch.zeros(B * K * T, 3)).reshape(B, K, T, 17, 3)
     assert torch.equal(poses.cpu(), want)
     # end-to-end MPJPE gate (north_star: within 0.05 mm) against a synthetic target
     y = 0.3 * torch.randn(B, T, 17, 3, generator=torch.Generator().manual_seed(5))

@@ -23,6 +23,20 @@ def test_decoder_golden():
     assert torch.equal(O.pose_decoder(g["rot4d"], g["bones"], torch.zeros(20, 3), rot_rep_dim=4), g["poses_4d"])
 
 
+def test_decoder_ieee_restatement_is_pinned_to_the_reference():
+    """pose_decoder_ieee (numpy, every op correctly rounded) vs the fixtures frozen from the reference: <= 1e-6 relative
+    on well-conditioned rows (the residual is torch-CPU's 1-ulp sqrt), identical on the identity / T-pose known answer."""
+    g = _load("decoder.pt")
+    n = g["rot6d"].shape[0]
+    ok = ~g["stress_rows"]
+    for bones, root, key in ((g["bones"], torch.zeros(n, 3), "poses_zero_root"), (g["bones_signed"], g["root"], "poses_signed_root")):
+        got, want = O.pose_decoder_ieee(g["rot6d"], bones, root), g[key]
+        assert float((got[ok] - want[ok]).abs().max() / want[ok].abs().max()) <= 1e-6
+        assert float((got[~ok] - want[~ok]).abs().max()) <= 1e-5
+    ident = torch.tensor([1.0, 0, 0, 0, 1.0, 0]).expand(1, 17, 6).contiguous()
+    assert torch.equal(O.pose_decoder_ieee(ident, g["kat_bones"], torch.zeros(1, 3)), g["kat_pose_identity"])
+
+
 def test_decoder_known_answers():
     """Identity 6-D reproduces the T-pose bit-exactly; joint values from SURVEY.md §8c (KAT with the
     bone lengths of hpe/useful_aux_scripts/test_forward_kinematics.py:104-106)."""
