@@ -170,7 +170,7 @@ def run_gpu(args):
 
     torch.manual_seed(42)
     model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=T, n_hyp=K, drop_path_rate=0.1)
-    model = model.to(dev).eval()
+    model = model.to(dev).eval().set_compute_dtype(args.dtype)
     if args.micro_batch_clips:
         model.rotations_module.micro_batch_tokens = args.micro_batch_clips * T * J
         model.segments_module.micro_batch_tokens = args.micro_batch_clips * T * J
@@ -249,10 +249,10 @@ def run_gpu(args):
         cpu_value, cpu_threads, cpu_reps = cpu_forward_rate(clips=4, reps=3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": f"ManiPose H36M lifting forward (RMCLManifoldMixSTE, config.yaml defaults), T={T}, K={K}, J={J}, "
-                                   f"{B} clips/GPU = BASELINE config 3; bf16 backbone (fp32 accumulate), fp32 decoder",
+                                   f"{B} clips/GPU = BASELINE config 3; {args.dtype} tensor-core operands (fp32 accumulate, fp32 residual stream), fp32 decoder",
                        "clips_per_gpu": B, "frames_per_step": frames, "parallelism": f"clip-sharded x{world}, no collective",
                        "micro_batch_clips": model.rotations_module.clips_per_micro_batch(),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
@@ -261,7 +261,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": (out_host[0].numel() + out_host[1].numel()) * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all 4 Linear shapes of the blocks)",
+            "roofline": {"bound": "tensor", "kernel": "linear_kernel (tcgen05, all 4 Linear shapes of the rotation blocks)",
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"] if achieved else 0.0, "traffic": None,
                          "peak_source": f"{peaks['src']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})",
@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=1024, help="clips per GPU per step (BASELINE config 3: 1024)")
     ap.add_argument("--micro-batch-clips", type=int, default=0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit operand format of the backbone")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

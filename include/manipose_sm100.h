@@ -121,73 +121,75 @@ size_t mp_mpjpe_workspace_bytes(int64_t n_points);
 int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, void* workspace,
              size_t workspace_bytes, mp_stream_t stream);
 
-/* ---- MixSTE backbone building blocks, bf16 activations ---------------------
- * Token order is always [clip, frame, joint] (one layout, no transposes: the reference's
- * rearranges, mix_ste.py:131,144,167,171,184, become strided reads inside the attention kernel). */
+/* ---- MixSTE backbone building blocks ------------------------------------------------------
+ * Token order is always [clip, frame, token] (one layout, no transposes: the reference's rearranges,
+ * mix_ste.py:131,144,167,171,184, become strided reads inside the attention kernel).
+ * The residual stream x is fp32; everything that feeds a tensor-core contraction (normalised activations, q/k/v,
+ * attention output, MLP hidden, weights) is 16-bit with fp32 accumulation.  `dtype` selects the 16-bit format: */
+enum { MP_DTYPE_BF16 = 0, /* BASELINE config 3: "bf16 backbone" */
+       MP_DTYPE_FP16 = 1  /* same rate and bytes, 3 more mantissa bits (saturating conversions) */ };
 
-/* Y[M,N] (bf16) = epilogue(A[M,K] (bf16) @ W[N,K]^T (bf16) + bias[N] (fp32)); nn.Linear call sites
- * mix_ste.py:209-222 (fc1/fc2), :257,:280 (qkv/proj).  tcgen05.mma + TMEM accumulators + TMA.
- *   MP_EPI_BIAS: bias only; MP_EPI_GELU: exact-erf GELU (nn.GELU, mix_ste.py:200);
- *   MP_EPI_RESIDUAL: Y = resid[M,N] (bf16) + A W^T + bias  (Block.forward, mix_ste.py:352-358).
- * K % 64 == 0, N % 128 == 0; A, W, resid and Y are dense row-major (row strides K, K, N, N); Y may alias resid. */
+/* nn.Linear on tcgen05 (call sites mix_ste.py:209-222 fc1/fc2, :257,:280 qkv/proj):
+ *   MP_EPI_BIAS:     Y[M,N] (16-bit) = A[M,K] W[N,K]^T + bias[N]
+ *   MP_EPI_GELU:     Y[M,N] (16-bit) = GELU_erf(A W^T + bias)                       (nn.GELU, mix_ste.py:200)
+ *   MP_EPI_RESIDUAL: Y[M,N] (fp32)   = resid[M,N] (fp32) + A W^T + bias             (Block.forward, mix_ste.py:352-358)
+ * A, W 16-bit dense row-major (row strides K); bias fp32; K % 64 == 0, N % 128 == 0; Y may alias resid. */
 enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2 };
-int mp_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* Y,
-                 int64_t M, int64_t N, int64_t K, int epilogue, mp_stream_t stream);
+int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N,
+              int64_t K, int epilogue, int dtype, mp_stream_t stream);
 
 /* LayerNorm family (fp32 statistics over C in {128, 512}; one warp per token).
- *   x_in  [n_tokens, C] bf16
+ *   x_in  [n_tokens, C] fp32
  *   if post_gamma != NULL: x = LN(x_in; post_gamma, post_beta, post_eps)       (shared Spatial_norm /
  *        Temporal_norm, mix_ste.py:143,154,166,170) (+ pos_embed[(token / pos_div) % pos_mod, C] fp32 if
- *        pos_embed != NULL: the Temporal_pos_embed add of mix_ste.py:149); written to x_out (bf16)
- *   if ln_gamma != NULL: h_out = LN(x; ln_gamma, ln_beta, ln_eps) (next block's norm1, :353), bf16 */
-int mp_layernorm(const void* x_in, void* x_out, void* h_out, const float* post_gamma,
-                 const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
-                 int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                 int64_t n_tokens, int C, mp_stream_t stream);
+ *        pos_embed != NULL: the Temporal_pos_embed add of mix_ste.py:149); written to x_out (fp32, may alias x_in)
+ *   if ln_gamma != NULL: h_out = LN(x; ln_gamma, ln_beta, ln_eps) (next block's norm1 / this block's norm2), 16-bit */
+int mp_layernorm(const float* x_in, float* x_out, void* h_out, const float* post_gamma, const float* post_beta,
+                 float post_eps, const float* pos_embed, int64_t pos_div, int64_t pos_mod, const float* ln_gamma,
+                 const float* ln_beta, float ln_eps, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
 
 /* Joint embedding + spatial pos-embed + first norm1 (MixSTE.STE_forward, mix_ste.py:128-138):
- *   x[tok, c] = W[c,0:2] . in[tok,0:2] + b[c] + spos[tok % 17, c]  (fp32 math) -> x_out bf16,
- *   h_out = LN(x; ln_gamma, ln_beta, 1e-6) bf16.  in [n_tokens, 2] fp32, C = 512. */
-int mp_embed_joints(const float* in2d, const float* W, const float* b, const float* spos,
-                    const float* ln_gamma, const float* ln_beta, float ln_eps, void* x_out,
-                    void* h_out, int64_t n_tokens, int n_joints, int C, mp_stream_t stream);
+ *   x[tok, c] = W[c,0:2] . in[tok,0:2] + b[c] + spos[tok % 17, c]  -> x_out fp32, h_out = LN(x; ln_*, eps) 16-bit.
+ *   in [n_tokens, 2] fp32, C = 512. */
+int mp_embed_joints(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma,
+                    const float* ln_beta, float ln_eps, float* x_out, void* h_out, int64_t n_tokens, int n_joints,
+                    int C, int dtype, mp_stream_t stream);
 /* joints_to_segments_proj + pos-embed + norm1 (BonesMixSTE.forward, manifold_mix_ste.py:139-148):
- *   in [n_frames, 34] fp32, W [16*128, 34], b [2048], spos [16,128] -> x_out/h_out [n_frames*16,128]. */
-int mp_embed_segments(const float* in2d, const float* W, const float* b, const float* spos,
-                      const float* ln_gamma, const float* ln_beta, float ln_eps, void* x_out,
-                      void* h_out, int64_t n_frames, int in_features, int n_segments, int C,
-                      mp_stream_t stream);
+ *   in [n_frames, 34] fp32, W [16*128, 34], b [2048], spos [16,128] -> x_out fp32 / h_out 16-bit [n_frames*16,128]. */
+int mp_embed_segments(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma,
+                      const float* ln_beta, float ln_eps, float* x_out, void* h_out, int64_t n_frames,
+                      int in_features, int n_segments, int C, int dtype, mp_stream_t stream);
 
-/* Multi-head softmax attention (Attention.forward, mix_ste.py:255-282), mma.sync tensor cores.
- *   qkv [n_clips*n_frames*n_tok, 3*C] bf16, columns [q|k|v] x heads x head_dim (mix_ste.py:257-261)
- *   out [n_clips*n_frames*n_tok, C] bf16;  head_dim in {64, 16}; scale = head_dim^-0.5
+/* Multi-head softmax attention (Attention.forward, mix_ste.py:255-282), tensor cores via mma.sync, fp32 softmax.
+ *   qkv [n_clips*n_frames*n_tok, 3*C] 16-bit, columns [q|k|v] x heads x head_dim (mix_ste.py:257-261)
+ *   out [n_clips*n_frames*n_tok, C] 16-bit;  head_dim in {64, 16}; scale = head_dim^-0.5
  *   MP_ATTN_SPATIAL: sequences = the n_tok tokens of one frame;
  *   MP_ATTN_TEMPORAL: sequences = the n_frames frames of one (clip, token) track (n_frames <= 256). */
 enum { MP_ATTN_SPATIAL = 0, MP_ATTN_TEMPORAL = 1 };
-int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C,
-                 int n_heads, int mode, mp_stream_t stream);
+int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads,
+                 int mode, int dtype, mp_stream_t stream);
 
-/* K hypothesis heads (RMCLRotMixSTE.forward tail + MCLHead, rmcl_manifold_mix_ste.py:251-298):
- *   x [n_frames_total*17, 512] bf16 = output of the last temporal block BEFORE Temporal_norm;
+/* K hypothesis heads (RMCLRotMixSTE.forward tail + MCLHead, rmcl_manifold_mix_ste.py:251-298), all fp32:
+ *   x [n_frames_total*17, 512] fp32 = output of the last temporal block BEFORE Temporal_norm;
  *   applies Temporal_norm (post_*), then per head k: LN(eps 1e-5; hg/hb [K,512]) -> Linear(512 -> out_dim
  *   (+1 if with_score); hw [K, out_dim+1, 512], hbias [K, out_dim+1]) -> rot [B,K,T,17,out_dim] fp32 and,
  *   if with_score, logits[B,K,T] = score_w[K,17] . score_emb + score_b[K].
  *   with_score = 0 is MixSTE.head of the single-hypothesis model (mix_ste.py:123-126, K = 1). */
-int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta, float post_eps,
+int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta, float post_eps,
                  const float* hg, const float* hb, const float* hw, const float* hbias,
                  const float* score_w, const float* score_b, float* rot, float* logits,
                  int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score,
                  mp_stream_t stream);
 /* Bone-length head (MixSTE.head + mean over time, mix_ste.py:123-126,187; manifold_mix_ste.py:150-154):
- *   x [n_clips*n_frames*16, 128] bf16 before Temporal_norm -> bone_len [n_clips,16] fp32.
+ *   x [n_clips*n_frames*16, 128] fp32 before Temporal_norm -> bone_len [n_clips,16] fp32.
  *   workspace >= n_clips*n_frames*16*4 bytes. */
-int mp_bones_head(const void* x, const float* post_gamma, const float* post_beta, float post_eps,
+int mp_bones_head(const float* x, const float* post_gamma, const float* post_beta, float post_eps,
                   const float* hg, const float* hb, const float* hw, const float* hbias,
                   float* bone_len, int64_t n_clips, int64_t n_frames, int n_segments, int C,
                   void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
-/* fp32 -> bf16 (weight shadows refreshed by the host wrapper after optimizer.step()). */
-int mp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mp_stream_t stream);
+/* fp32 -> 16-bit (weight shadows refreshed by the host wrapper after optimizer.step()). */
+int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@ MP_TERM_WTA, MP_TERM_BCE, MP_TERM_VEL, MP_TERM_SMOOTH, MP_TERM_TOTAL, MP_LOSS_NT
 MP_AGG_WEIGHTED_AVE, MP_AGG_BEST_SCORE, MP_AGG_ORACLE = 0, 1, 2
 MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL = 0, 1, 2
 MP_ATTN_SPATIAL, MP_ATTN_TEMPORAL = 0, 1
+MP_DTYPE_BF16, MP_DTYPE_FP16 = 0, 1
 
 P, I64, F, I = c_void_p, c_int64, c_float, c_int
 
@@ -38,14 +39,14 @@ SIGNATURES = {
     "mp_aggregate": (I, [P, P, P, I, P, P, P, I64, I64, I64, P]),
     "mp_mpjpe_workspace_bytes": (c_size_t, [I64]),
     "mp_mpjpe": (I, [P, P, I64, P, P, c_size_t, P]),
-    "mp_gemm_bf16": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
-    "mp_layernorm": (I, [P, P, P, P, P, F, P, I64, I64, P, P, F, I64, I, P]),
-    "mp_embed_joints": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, P]),
-    "mp_embed_segments": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, P]),
-    "mp_attention": (I, [P, P, I64, I64, I, I, I, I, P]),
+    "mp_linear": (I, [P, P, P, P, P, I64, I64, I64, I, I, P]),
+    "mp_layernorm": (I, [P, P, P, P, P, F, P, I64, I64, P, P, F, I64, I, I, P]),
+    "mp_embed_joints": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, P]),
+    "mp_embed_segments": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, I, P]),
+    "mp_attention": (I, [P, P, I64, I64, I, I, I, I, I, P]),
     "mp_heads_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, I64, I64, I, I, I, P]),
     "mp_bones_head": (I, [P, P, P, F, P, P, P, P, P, I64, I64, I, I, P, c_size_t, P]),
-    "mp_cast_f32_to_bf16": (I, [P, P, I64, P]),
+    "mp_cast_f32_to_16": (I, [P, P, I64, I, P]),
 }
 
 _lib = None

@@ -29,7 +29,8 @@ class BonesMixSTE(MixSTE):
         blk0 = self.STEblocks[0]
         ops.embed_segments(x2d, self.joints_to_segments_proj.weight, self.joints_to_segments_proj.bias, self.Spatial_pos_embed,
                            blk0.norm1.weight, blk0.norm1.bias, blk0.norm1.eps, x, h, n_clips * n_frames,
-                           self.joints_to_segments_proj.in_features, self.num_bones, self.embed_dim)
+                           self.joints_to_segments_proj.in_features, self.num_bones, self.embed_dim,
+                           ops.DTYPE_CODE[self.compute_dtype])
 
     def bone_lengths_into(self, x2d: torch.Tensor, n_clips: int, out: torch.Tensor) -> None:
         """One micro-batch: x2d fp32 [n_clips, L, J, in] -> out fp32 [n_clips, S] (signed, no activation)."""
@@ -71,6 +72,14 @@ class ManifoldMixSTE(nn.Module):
                                            attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer,
                                            mup=mup)
         self.decoder = PoseDecoder(skeleton=skeleton, rot_rep_dim=rot_rep_dim)
+
+    def set_compute_dtype(self, name: str) -> "ManifoldMixSTE":
+        """"bf16" (BASELINE config 3) or "fp16" (same speed, 3 more mantissa bits) for both backbones."""
+        if name not in ("bf16", "fp16"):
+            raise ValueError(f"compute dtype must be 'bf16' or 'fp16', got {name!r}")
+        self.rotations_module.compute_dtype = name
+        self.segments_module.compute_dtype = name
+        return self
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b, l, _, _ = x.shape

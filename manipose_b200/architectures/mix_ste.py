@@ -3,11 +3,11 @@
 The module tree (``STEblocks.{i}.attn.qkv`` ...) exists so that ``state_dict()`` / ``load_state_dict()`` /
 ``Adam(model.parameters())`` interoperate with the reference (290 tensors).  The arithmetic does not
 go through ``nn.Linear``: ``MixSTE.trunk`` drives the sm_100a kernels of libmanipose_sm100.so over ONE activation
-layout, [clip, frame, token, C] in bf16:
+layout, [clip, frame, token, C] — fp32 residual stream, 16-bit (``compute_dtype``: "bf16" | "fp16") tensor-core operands:
 
     embed (+spatial pos-embed, +norm1)                                  mp_embed_joints / mp_embed_segments
     per block:  qkv GEMM -> attention (spatial | temporal) -> proj GEMM + residual
-                -> norm2 -> fc1 GEMM + GELU -> fc2 GEMM + residual      mp_gemm_bf16 (tcgen05/TMEM/TMA), mp_attention
+                -> norm2 -> fc1 GEMM + GELU -> fc2 GEMM + residual      mp_linear (tcgen05/TMEM/TMA), mp_attention
                 -> shared post-norm (+temporal pos-embed) fused with the next block's norm1      mp_layernorm
 
 The reference's "(B L) J C <-> (B J) L C" rearranges (mix_ste.py:131,144,167,171,184) are strided reads inside the
@@ -113,8 +113,11 @@ def _version_key(params) -> Tuple:
 class MixSTE(nn.Module):
     """mix_ste.py:12-191.  ``forward(x[B,L,J,in_chans]) -> [B,L,J,out_dim]``."""
 
-    # clips per micro-batch of the trunk; activations of one micro-batch are 5*C*2 bytes per token
+    # tokens per micro-batch of the trunk; activations of one micro-batch are 12*C bytes per token
     micro_batch_tokens = 36000
+    # 16-bit format of everything that feeds a tensor-core contraction ("bf16": BASELINE config 3; "fp16": same speed and
+    # bytes, 3 more mantissa bits — needed for the 0.05 mm end-to-end MPJPE gate, see DESIGN.md §numerics)
+    compute_dtype = "bf16"
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
@@ -159,12 +162,13 @@ class MixSTE(nn.Module):
             out += [blk.attn.qkv.weight, blk.attn.proj.weight, blk.mlp.fc1.weight, blk.mlp.fc2.weight]
         return out
 
-    def _bf16_weights(self) -> List[torch.Tensor]:
-        """bf16 shadows of the GEMM weights, refreshed when a parameter changed (optimizer.step / load_state_dict)."""
+    def _shadow_weights(self) -> List[torch.Tensor]:
+        """16-bit shadows of the GEMM weights, refreshed when a parameter changed (optimizer.step / load_state_dict)."""
         params = self._gemm_params()
-        key = _version_key(params)
+        dt = ops.DTYPE_CODE[self.compute_dtype]
+        key = (dt,) + _version_key(params)
         if key != self._shadow_key:
-            self._shadow_list = [ops.cast_bf16(p.detach()) for p in params]
+            self._shadow_list = [ops.cast16(p.detach(), dt) for p in params]
             self._shadow_key = key
         return self._shadow_list
 
@@ -172,11 +176,12 @@ class MixSTE(nn.Module):
         c = self.embed_dim
         hidden = self.STEblocks[0].mlp.fc1.out_features
         wide = max(3 * c, hidden)
-        if self._ws is None or self._ws["x"].shape[0] < n_tokens or self._ws["x"].device != device:
+        td = ops.TORCH_DTYPE[ops.DTYPE_CODE[self.compute_dtype]]
+        if self._ws is None or self._ws["x"].shape[0] < n_tokens or self._ws["x"].device != device or self._ws["h"].dtype != td:
             self._ws = {
-                "x": torch.empty((n_tokens, c), dtype=torch.bfloat16, device=device),       # residual stream
-                "h": torch.empty((n_tokens, c), dtype=torch.bfloat16, device=device),       # normalised / attention out
-                "wide": torch.empty((n_tokens, wide), dtype=torch.bfloat16, device=device), # qkv, then the MLP hidden
+                "x": torch.empty((n_tokens, c), dtype=torch.float32, device=device),   # residual stream (fp32)
+                "h": torch.empty((n_tokens, c), dtype=td, device=device),              # normalised / attention out
+                "wide": torch.empty((n_tokens, wide), dtype=td, device=device),        # qkv, then the MLP hidden
             }
         return self._ws
 
@@ -185,12 +190,12 @@ class MixSTE(nn.Module):
         blk0 = self.STEblocks[0]
         ops.embed_joints(x2d, self.Spatial_patch_to_embedding.weight, self.Spatial_patch_to_embedding.bias, self.Spatial_pos_embed,
                          blk0.norm1.weight, blk0.norm1.bias, blk0.norm1.eps, x, h, n_clips * n_frames * self.num_tokens,
-                         self.num_tokens, self.embed_dim)
+                         self.num_tokens, self.embed_dim, ops.DTYPE_CODE[self.compute_dtype])
 
     def trunk(self, x2d: torch.Tensor, n_clips: int) -> torch.Tensor:
         """STE_forward + TTE_foward + ST_foward (mix_ste.py:128-173) on one micro-batch.
 
-        x2d: fp32 [n_clips, L, J, in_chans] (contiguous).  Returns the bf16 [n_clips*L*tokens, C] output of the last temporal
+        x2d: fp32 [n_clips, L, J, in_chans] (contiguous).  Returns the fp32 [n_clips*L*tokens, C] output of the last temporal
         block BEFORE ``Temporal_norm`` (the head kernels apply it, fused with their own LayerNorm)."""
         if self.training and any(isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0 for b in self.STEblocks):
             raise NotImplementedError("training-mode stochastic depth through the fused trunk is not built yet; "
@@ -204,7 +209,8 @@ class MixSTE(nn.Module):
         flat = ws["wide"].view(-1)
         qkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
         hid = flat[:n_tokens * hidden_dim].view(n_tokens, hidden_dim)   # aliases qkv: never live at the same time
-        w = self._bf16_weights()
+        w = self._shadow_weights()
+        dt = ops.DTYPE_CODE[self.compute_dtype]
         self._embed(x2d, n_clips, n_frames, x, h)
         depth = self.block_depth
         blocks = []
@@ -212,17 +218,17 @@ class MixSTE(nn.Module):
             blocks.append((self.STEblocks[i], 4 * i, L.MP_ATTN_SPATIAL, self.Spatial_norm))
             blocks.append((self.TTEblocks[i], 4 * (depth + i), L.MP_ATTN_TEMPORAL, self.Temporal_norm))
         for bi, (blk, wi, mode, post) in enumerate(blocks):
-            ops.gemm(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
+            ops.linear(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
             ops.attention(qkv, h, n_clips, n_frames, n_tok, c, heads, mode)
-            ops.gemm(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
-            ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps)
-            ops.gemm(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
-            ops.gemm(hid, w[wi + 3], blk.mlp.fc2.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+            ops.linear(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+            ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
+            ops.linear(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
+            ops.linear(hid, w[wi + 3], blk.mlp.fc2.bias, x, L.MP_EPI_RESIDUAL, resid=x)
             if bi + 1 < len(blocks):
                 nxt = blocks[bi + 1][0]
                 pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
                 ops.layernorm(x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
-                              ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps)
+                              ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
         return x
 
     def _check_input(self, x: torch.Tensor):

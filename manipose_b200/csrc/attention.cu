@@ -28,7 +28,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 //   q_rows: smem address of query row 0 of this tile (row stride `ld` bytes); k_rows / v_rows: key / value row 0.
 //   Rows are addressed through row_ptr(base, r) so callers can redirect padding rows to a zero row.
 // Result: o[HD/8][4] (unnormalised) and l[2] (row sums) in the mma C-fragment layout (rows g and g+8).
-template <int HD, typename RowPtr>
+template <int HD, typename D, typename RowPtr>
 __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, const uint8_t* k_base, const uint8_t* v_base, int n_keys,
                                             int n_keys_pad, float scale_log2, RowPtr row_ptr, int lane, float (&o)[HD / 8][4],
                                             float (&l)[2]) {
@@ -63,8 +63,8 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
         const int kr = key0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
         const int kc = ks * 16 + ((lane >> 3) & 1) * 8;
         ptx::ldmatrix_x4(kf, row_ptr(k_base, kr) + kc * 2);
-        ptx::mma_bf16_16816(s[np * 2 + 0], qf[ks], kf[0], kf[1]);
-        ptx::mma_bf16_16816(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
+        ptx::mma_16816<D>(s[np * 2 + 0], qf[ks], kf[0], kf[1]);
+        ptx::mma_16816<D>(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
       }
     }
     // scale into the exp2 domain, mask padded keys
@@ -101,8 +101,8 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
       const float p2 = exp2f(s[nt][2] - m[1]), p3 = exp2f(s[nt][3] - m[1]);
       l[0] += p0 + p1;
       l[1] += p2 + p3;
-      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      pf[nt >> 1][(nt & 1) * 2 + 0] = D::pack2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = D::pack2(p2, p3);
     }
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
@@ -113,8 +113,8 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
         const int vr = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int vc = dp * 16 + (lane >> 4) * 8;
         ptx::ldmatrix_x4_trans(vf, row_ptr(v_base, vr) + vc * 2);
-        ptx::mma_bf16_16816(o[dp * 2 + 0], pf[kk], vf[0], vf[1]);
-        ptx::mma_bf16_16816(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+        ptx::mma_16816<D>(o[dp * 2 + 0], pf[kk], vf[0], vf[1]);
+        ptx::mma_16816<D>(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
       }
     }
   }
@@ -126,9 +126,9 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
 // One CTA per (clip, token, head); 8 warps share the track's K and V, each warp owns 16-row query tiles.
 constexpr int kTWarps = 8;
 
-template <int HD>
+template <int HD, typename D>
 __global__ void __launch_bounds__(kTWarps * 32, 2)
-attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_frames, int n_tok, int C, int n_heads) {
+attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int n_frames, int n_tok, int C, int n_heads) {
   constexpr int LD = HD * 2 + 16;           // padded row bytes
   constexpr int CH = HD / 8;                // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem[];
@@ -141,7 +141,7 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const int tok = (blockIdx.x / n_heads) % n_tok;
   const int clip = blockIdx.x / (n_heads * n_tok);
   const size_t row_stride = (size_t)n_tok * 3 * C;   // elements between consecutive frames of this track
-  const __nv_bfloat16* base = qkv + ((size_t)clip * n_frames * n_tok + tok) * 3 * C + head * HD;
+  const uint16_t* base = qkv + ((size_t)clip * n_frames * n_tok + tok) * 3 * C + head * HD;
 
   // stage Q, K, V rows [0, n_frames); zero rows [n_frames, Tp)
   const int total = 3 * Tp * CH;
@@ -164,12 +164,12 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const int g = lane >> 2, t = lane & 3;
   const float scale_log2 = rsqrtf((float)HD) * kLog2e;
   auto row_ptr = [](const uint8_t* b, int r) { return b + (size_t)r * LD; };
-  __nv_bfloat16* obase = out + ((size_t)clip * n_frames * n_tok + tok) * C + head * HD;
+  uint16_t* obase = out + ((size_t)clip * n_frames * n_tok + tok) * C + head * HD;
   const size_t orow_stride = (size_t)n_tok * C;
 
   for (int mt = warp; mt * 16 < n_frames; mt += kTWarps) {
     float o[HD / 8][4], l[2];
-    attend_tile<HD>(sq, mt * 16, sk, sv, n_frames, Tp, scale_log2, row_ptr, lane, o, l);
+    attend_tile<HD, D>(sq, mt * 16, sk, sv, n_frames, Tp, scale_log2, row_ptr, lane, o, l);
     const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
     // this warp's 16 query rows are dead: reuse them to transpose the output tile
     __syncwarp();
@@ -177,8 +177,8 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     uint8_t* orow1 = orow0 + 8 * LD;
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) {
-      *reinterpret_cast<uint32_t*>(orow0 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-      *reinterpret_cast<uint32_t*>(orow1 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+      *reinterpret_cast<uint32_t*>(orow0 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][0] * inv0, o[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(orow1 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][2] * inv1, o[i][3] * inv1);
     }
     __syncwarp();
     for (int i = lane; i < 16 * CH; i += 32) {
@@ -191,9 +191,9 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 // ------------------------------------------------------------------------------------------------------ spatial
 // One CTA per frame, one warp per head.  The frame's [n_tok, 3C] block is contiguous in global memory.
-template <int HD>
+template <int HD, typename D>
 __global__ void __launch_bounds__(256)
-attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int64_t n_seq, int n_tok, int C, int n_heads) {
+attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int64_t n_seq, int n_tok, int C, int n_heads) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int LD = 3 * C * 2 + 16;            // padded row bytes; row n_tok is an all-zero row for padded tokens
   const int CH = 3 * C / 8;
@@ -204,7 +204,7 @@ attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   for (int i = threadIdx.x; i < LD / 16; i += blockDim.x) *reinterpret_cast<uint4*>(smem + (size_t)n_tok * LD + i * 16) = make_uint4(0, 0, 0, 0);
 
   for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
-    const __nv_bfloat16* src = qkv + (size_t)seq * n_tok * 3 * C;
+    const uint16_t* src = qkv + (size_t)seq * n_tok * 3 * C;
     __syncthreads();   // previous iteration's readers are done
     for (int i = threadIdx.x; i < n_tok * CH; i += blockDim.x) {
       const int r = i / CH, ch = i - r * CH;
@@ -224,7 +224,7 @@ attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       auto row_ptr = [=](const uint8_t* b, int r) { return r < n_tok ? b + (size_t)r * LD : zero_row + (b - smem) % LD; };
       for (int mt = 0; mt * 16 < n_tok; ++mt) {
         float o[HD / 8][4], l[2];
-        attend_tile<HD>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
+        attend_tile<HD, D>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
         const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
         __syncwarp();
         // the q columns of this head and these rows are only ever read by this warp: overwrite them with the output
@@ -233,13 +233,13 @@ attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         uint8_t* w1 = smem + (size_t)r1 * LD + (size_t)head * HD * 2;
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i) {
-          if (r0 < n_tok) *reinterpret_cast<uint32_t*>(w0 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-          if (r1 < n_tok) *reinterpret_cast<uint32_t*>(w1 + (i * 8 + 2 * t) * 2) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+          if (r0 < n_tok) *reinterpret_cast<uint32_t*>(w0 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][0] * inv0, o[i][1] * inv0);
+          if (r1 < n_tok) *reinterpret_cast<uint32_t*>(w1 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][2] * inv1, o[i][3] * inv1);
         }
       }
     }
     __syncthreads();
-    __nv_bfloat16* dst = out + (size_t)seq * n_tok * C;
+    uint16_t* dst = out + (size_t)seq * n_tok * C;
     const int OCH = C / 8;
     for (int i = threadIdx.x; i < n_tok * OCH; i += blockDim.x) {
       const int r = i / OCH, ch = i - r * OCH;
@@ -252,17 +252,21 @@ attn_spatial_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 }  // namespace mp
 
 extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads, int mode,
-                            mp_stream_t stream) {
+                            int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(qkv && out, MP_EINVAL, "mp_attention: null pointer");
   MP_REQUIRE(n_clips >= 0 && n_frames >= 1 && n_tok >= 1 && n_heads >= 1 && n_heads <= 8 && C % n_heads == 0, MP_EINVAL,
              "mp_attention: bad sizes");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_attention: unknown dtype %d", dtype);
   const int hd = C / n_heads;
   MP_REQUIRE(hd == 64 || hd == 16, MP_EUNSUPPORTED, "mp_attention: head_dim=%d (built for 64 and 16)", hd);
   MP_REQUIRE(aligned16(qkv) && aligned16(out), MP_EALIGN, "mp_attention: pointers must be 16-byte aligned");
   if (n_clips == 0) return MP_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const uint16_t* in = (const uint16_t*)qkv;
+  uint16_t* o = (uint16_t*)out;
+  const bool bf = dtype == MP_DTYPE_BF16;
   if (mode == MP_ATTN_TEMPORAL) {
     MP_REQUIRE(n_frames <= 256, MP_EUNSUPPORTED, "mp_attention: temporal sequences longer than 256 frames are not built (got %lld)",
                (long long)n_frames);
@@ -272,12 +276,13 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
     MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
     auto launch = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kernel<<<(unsigned)ctas, kTWarps * 32, smem, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, (int)n_frames, n_tok, C, n_heads);
+      kernel<<<(unsigned)ctas, kTWarps * 32, smem, s>>>(in, o, (int)n_frames, n_tok, C, n_heads);
     };
-    if (hd == 64)
-      launch(attn_temporal_kernel<64>);
-    else
-      launch(attn_temporal_kernel<16>);
+    if (hd == 64) {
+      if (bf) launch(attn_temporal_kernel<64, Bf16>); else launch(attn_temporal_kernel<64, Fp16>);
+    } else {
+      if (bf) launch(attn_temporal_kernel<16, Bf16>); else launch(attn_temporal_kernel<16, Fp16>);
+    }
     return check_launch("attn_temporal_kernel");
   }
   MP_REQUIRE(mode == MP_ATTN_SPATIAL, MP_EINVAL, "mp_attention: unknown mode %d", mode);
@@ -289,11 +294,12 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   if (grid > n_seq) grid = n_seq;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)grid, 256, smem, s>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n_seq, n_tok, C, n_heads);
+    kernel<<<(unsigned)grid, 256, smem, s>>>(in, o, n_seq, n_tok, C, n_heads);
   };
-  if (hd == 64)
-    launch(attn_spatial_kernel<64>);
-  else
-    launch(attn_spatial_kernel<16>);
+  if (hd == 64) {
+    if (bf) launch(attn_spatial_kernel<64, Bf16>); else launch(attn_spatial_kernel<64, Fp16>);
+  } else {
+    if (bf) launch(attn_spatial_kernel<16, Bf16>); else launch(attn_spatial_kernel<16, Fp16>);
+  }
   return check_launch("attn_spatial_kernel");
 }

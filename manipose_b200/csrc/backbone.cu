@@ -1,5 +1,6 @@
 // Memory-bound pieces of the MixSTE backbone: joint / segment embeddings, the LayerNorm family, the K hypothesis
-// heads and the bone-length head.  bf16 activations, fp32 statistics and parameters, one warp per token.
+// heads and the bone-length head.  fp32 residual stream, 16-bit (bf16 | fp16) normalised activations, fp32 statistics and
+// parameters, one warp per token.
 //
 // Replaces (reference, paths under hpe/mh_so3_hpe/architectures/):
 //   mix_ste.py:128-138      STE_forward: Spatial_patch_to_embedding + Spatial_pos_embed
@@ -24,36 +25,49 @@ struct Row {
     if (C == 512) return (i < 8 ? 0 : 256) + lane * 8 + (i & 7);
     return lane * 4 + i;
   }
-  __device__ static __forceinline__ void load_bf16(const __nv_bfloat16* __restrict__ row, int lane, float (&v)[kPer]) {
+  // fp32 activation row (the residual stream) in the per-lane channel order
+  __device__ static __forceinline__ void load_x(const float* __restrict__ row, int lane, float (&v)[kPer]) {
     if (C == 512) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const uint4 u = *reinterpret_cast<const uint4*>(row + h * 256 + lane * 8);
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        v[h * 8 + 0] = a.x; v[h * 8 + 1] = a.y; v[h * 8 + 2] = b.x; v[h * 8 + 3] = b.y;
-        v[h * 8 + 4] = c.x; v[h * 8 + 5] = c.y; v[h * 8 + 6] = d.x; v[h * 8 + 7] = d.y;
+        const float4 a = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8 + 4);
+        v[h * 8 + 0] = a.x; v[h * 8 + 1] = a.y; v[h * 8 + 2] = a.z; v[h * 8 + 3] = a.w;
+        v[h * 8 + 4] = b.x; v[h * 8 + 5] = b.y; v[h * 8 + 6] = b.z; v[h * 8 + 7] = b.w;
       }
     } else {
-      const uint2 u = *reinterpret_cast<const uint2*>(row + lane * 4);
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+      const float4 a = *reinterpret_cast<const float4*>(row + lane * 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     }
   }
-  __device__ static __forceinline__ void store_bf16(__nv_bfloat16* __restrict__ row, int lane, const float (&v)[kPer]) {
+  __device__ static __forceinline__ void store_x(float* __restrict__ row, int lane, const float (&v)[kPer]) {
+    if (C == 512) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        *reinterpret_cast<float4*>(row + h * 256 + lane * 8) = make_float4(v[h * 8 + 0], v[h * 8 + 1], v[h * 8 + 2], v[h * 8 + 3]);
+        *reinterpret_cast<float4*>(row + h * 256 + lane * 8 + 4) = make_float4(v[h * 8 + 4], v[h * 8 + 5], v[h * 8 + 6], v[h * 8 + 7]);
+      }
+    } else {
+      *reinterpret_cast<float4*>(row + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  // 16-bit normalised activation row (GEMM operand)
+  template <typename D>
+  __device__ static __forceinline__ void store_h(uint16_t* __restrict__ row, int lane, const float (&v)[kPer]) {
     if (C == 512) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint4 u;
-        u.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]);
-        u.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
-        u.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]);
-        u.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+        u.x = D::pack2(v[h * 8 + 0], v[h * 8 + 1]);
+        u.y = D::pack2(v[h * 8 + 2], v[h * 8 + 3]);
+        u.z = D::pack2(v[h * 8 + 4], v[h * 8 + 5]);
+        u.w = D::pack2(v[h * 8 + 6], v[h * 8 + 7]);
         *reinterpret_cast<uint4*>(row + h * 256 + lane * 8) = u;
       }
     } else {
       uint2 u;
-      u.x = pack_bf16x2(v[0], v[1]);
-      u.y = pack_bf16x2(v[2], v[3]);
+      u.x = D::pack2(v[0], v[1]);
+      u.y = D::pack2(v[2], v[3]);
       *reinterpret_cast<uint2*>(row + lane * 4) = u;
     }
   }
@@ -71,11 +85,6 @@ struct Row {
       const float4 a = __ldg(reinterpret_cast<const float4*>(p + lane * 4));
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     }
-  }
-  // round to bf16 and back (what the next kernel will read)
-  __device__ static __forceinline__ void round_bf16(float (&v)[kPer]) {
-#pragma unroll
-    for (int i = 0; i < kPer; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
   }
   // mean and 1/sqrt(var + eps) over the row (two-pass, biased variance: nn.LayerNorm)
   __device__ static __forceinline__ void stats(const float (&v)[kPer], float eps, float& mean, float& rstd) {
@@ -100,9 +109,9 @@ struct Row {
 constexpr int kTokWarps = 8;  // warps per CTA in the token kernels
 
 // -------------------------------------------------------------------------------------------------- LayerNorm family
-template <int C>
+template <int C, typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x_in, __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out,
+layernorm_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, uint16_t* __restrict__ h_out,
                  const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps, const float* __restrict__ pos,
                  int64_t pos_div, int64_t pos_mod, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                  int64_t n_tokens) {
@@ -121,7 +130,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x_in, __nv_bfloat16* __restri
   }
   for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
     float v[R::kPer];
-    R::load_bf16(x_in + tok * C, lane, v);
+    R::load_x(x_in + tok * C, lane, v);
     float mean, rstd;
     if (post_g) {
       R::stats(v, post_eps, mean, rstd);
@@ -132,23 +141,23 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x_in, __nv_bfloat16* __restri
 #pragma unroll
         for (int i = 0; i < R::kPer; ++i) v[i] += pe[i];
       }
-      R::round_bf16(v);
-      R::store_bf16(x_out + tok * C, lane, v);
+      R::store_x(x_out + tok * C, lane, v);
     }
     if (ln_g) {
       R::stats(v, ln_eps, mean, rstd);
       R::normalize(v, mean, rstd, lg, lb);
-      R::store_bf16(h_out + tok * C, lane, v);
+      R::template store_h<D>(h_out + tok * C, lane, v);
     }
   }
 }
 
 // -------------------------------------------------------------------------------------------------- joint embedding
 // x[tok, c] = W[c,0] in0 + W[c,1] in1 + b[c] + spos[tok % J, c]; h = LN(x)          (C = 512)
+template <typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
                     const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
-                    __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out, int64_t n_tokens, int n_joints) {
+                    float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_tokens, int n_joints) {
   using R = Row<512>;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
@@ -169,12 +178,11 @@ embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W,
     R::load_f32(spos + (tok % n_joints) * 512, lane, pe);
 #pragma unroll
     for (int i = 0; i < R::kPer; ++i) v[i] = fmaf(w1[i], p.y, fmaf(w0[i], p.x, bb[i])) + pe[i];
-    R::round_bf16(v);
-    R::store_bf16(x_out + tok * 512, lane, v);
+    R::store_x(x_out + tok * 512, lane, v);
     float mean, rstd;
     R::stats(v, ln_eps, mean, rstd);
     R::normalize(v, mean, rstd, lg, lb);
-    R::store_bf16(h_out + tok * 512, lane, v);
+    R::template store_h<D>(h_out + tok * 512, lane, v);
   }
 }
 
@@ -182,10 +190,11 @@ embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W,
 // per frame: in[34] -> [16 segments x 128]; a CTA owns ONE segment (its 128 x 34 weight slice lives transposed in
 // shared memory) and streams frames; token = frame * 16 + segment.
 constexpr int kSegC = 128;
+template <typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
                       const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
-                      __nv_bfloat16* __restrict__ x_out, __nv_bfloat16* __restrict__ h_out, int64_t n_frames, int in_features,
+                      float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_frames, int in_features,
                       int n_segments) {
   using R = Row<kSegC>;
   extern __shared__ __align__(16) float wt[];  // [in_features][128]
@@ -219,12 +228,11 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < R::kPer; ++i) v[i] += pe[i];
     const int64_t tok = fr * n_segments + seg;
-    R::round_bf16(v);
-    R::store_bf16(x_out + tok * kSegC, lane, v);
+    R::store_x(x_out + tok * kSegC, lane, v);
     float mean, rstd;
     R::stats(v, ln_eps, mean, rstd);
     R::normalize(v, mean, rstd, lg, lb);
-    R::store_bf16(h_out + tok * kSegC, lane, v);
+    R::template store_h<D>(h_out + tok * kSegC, lane, v);
   }
 }
 
@@ -233,7 +241,7 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
 // token statistics, so the K heads are ONE [512 x K*O] projection with folded weights held in shared memory.
 constexpr int kHeadC = 512;
 __global__ void __launch_bounds__(kTokWarps * 32)
-heads_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
+heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
                  const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
                  const float* __restrict__ score_w, const float* __restrict__ score_b, float* __restrict__ rot, float* __restrict__ logits,
                  int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
@@ -280,7 +288,7 @@ heads_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
     float logit_acc = 0.f;  // lane k (< n_hyp) accumulates its head's logit
     for (int j = 0; j < kJ; ++j) {
       float v[R::kPer];
-      R::load_bf16(x + (fr * kJ + j) * kHeadC, lane, v);
+      R::load_x(x + (fr * kJ + j) * kHeadC, lane, v);
       float mean, rstd;
       R::stats(v, post_eps, mean, rstd);
       R::normalize(v, mean, rstd, pg, pb);   // Temporal_norm (eps 1e-6), kept in fp32
@@ -325,7 +333,7 @@ heads_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 // -------------------------------------------------------------------------------------------------- bone-length head
 // value[token] = Linear(128 -> 1)(LN_head(Temporal_norm(x)))  ;  bone_len[b, s] = mean_t value[b, t, s]
 __global__ void __launch_bounds__(kTokWarps * 32)
-bones_value_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
+bones_value_kernel(const float* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
                    const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
                    float* __restrict__ values, int64_t n_tokens) {
   using R = Row<kSegC>;
@@ -339,7 +347,7 @@ bones_value_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   const float b0 = hbias[0];
   for (int64_t tok = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5); tok < n_tokens; tok += (int64_t)gridDim.x * kTokWarps) {
     float v[R::kPer];
-    R::load_bf16(x + tok * kSegC, lane, v);
+    R::load_x(x + tok * kSegC, lane, v);
     float mean, rstd;
     R::stats(v, post_eps, mean, rstd);
     R::normalize(v, mean, rstd, pg, pb);
@@ -373,13 +381,14 @@ int token_grid(int64_t n_tokens) {
 
 extern "C" {
 
-int mp_layernorm(const void* x_in, void* x_out, void* h_out, const float* post_gamma, const float* post_beta, float post_eps,
+int mp_layernorm(const float* x_in, float* x_out, void* h_out, const float* post_gamma, const float* post_beta, float post_eps,
                  const float* pos_embed, int64_t pos_div, int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                 int64_t n_tokens, int C, mp_stream_t stream) {
+                 int64_t n_tokens, int C, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == 512 || C == 128, MP_EUNSUPPORTED, "mp_layernorm: C=%d (built for 512 and 128)", C);
   MP_REQUIRE(x_in && n_tokens >= 0, MP_EINVAL, "mp_layernorm: bad arguments");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_layernorm: unknown dtype %d", dtype);
   MP_REQUIRE((post_gamma == nullptr) == (post_beta == nullptr) && (ln_gamma == nullptr) == (ln_beta == nullptr), MP_EINVAL,
              "mp_layernorm: gamma/beta go together");
   MP_REQUIRE(post_gamma || ln_gamma, MP_EINVAL, "mp_layernorm: nothing to do");
@@ -389,51 +398,62 @@ int mp_layernorm(const void* x_in, void* x_out, void* h_out, const float* post_g
   MP_REQUIRE(aligned16(x_in) && aligned16(x_out) && aligned16(h_out), MP_EALIGN, "mp_layernorm: activations must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
   const int grid = token_grid(n_tokens);
-  if (C == 512)
-    layernorm_kernel<512><<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x_in, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, post_gamma, post_beta, post_eps, pos_embed, pos_div,
-        pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
-  else
-    layernorm_kernel<128><<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x_in, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, post_gamma, post_beta, post_eps, pos_embed, pos_div,
-        pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
+  auto launch = [&](auto kernel) {
+    kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x_in, x_out, (uint16_t*)h_out, post_gamma, post_beta, post_eps, pos_embed,
+                                                              pos_div, pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
+  };
+  const bool bf = dtype == MP_DTYPE_BF16;
+  if (C == 512) {
+    if (bf) launch(layernorm_kernel<512, Bf16>); else launch(layernorm_kernel<512, Fp16>);
+  } else {
+    if (bf) launch(layernorm_kernel<128, Bf16>); else launch(layernorm_kernel<128, Fp16>);
+  }
   return check_launch("layernorm_kernel");
 }
 
 int mp_embed_joints(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma, const float* ln_beta,
-                    float ln_eps, void* x_out, void* h_out, int64_t n_tokens, int n_joints, int C, mp_stream_t stream) {
+                    float ln_eps, float* x_out, void* h_out, int64_t n_tokens, int n_joints, int C, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == 512, MP_EUNSUPPORTED, "mp_embed_joints: C=%d (built for 512)", C);
   MP_REQUIRE(in2d && W && b && spos && ln_gamma && ln_beta && x_out && h_out && n_tokens >= 0 && n_joints >= 1, MP_EINVAL,
              "mp_embed_joints: bad arguments");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_embed_joints: unknown dtype %d", dtype);
   MP_REQUIRE(aligned16(x_out) && aligned16(h_out) && (reinterpret_cast<uintptr_t>(in2d) & 7u) == 0, MP_EALIGN,
              "mp_embed_joints: x_out / h_out must be 16-byte aligned, in2d 8-byte aligned");
   if (n_tokens == 0) return MP_OK;
-  embed_joints_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(
-      in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, n_tokens, n_joints);
+  auto launch = [&](auto kernel) {
+    kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
+                                                                              (uint16_t*)h_out, n_tokens, n_joints);
+  };
+  if (dtype == MP_DTYPE_BF16) launch(embed_joints_kernel<Bf16>); else launch(embed_joints_kernel<Fp16>);
   return check_launch("embed_joints_kernel");
 }
 
 int mp_embed_segments(const float* in2d, const float* W, const float* b, const float* spos, const float* ln_gamma, const float* ln_beta,
-                      float ln_eps, void* x_out, void* h_out, int64_t n_frames, int in_features, int n_segments, int C,
+                      float ln_eps, float* x_out, void* h_out, int64_t n_frames, int in_features, int n_segments, int C, int dtype,
                       mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == kSegC, MP_EUNSUPPORTED, "mp_embed_segments: C=%d (built for 128)", C);
   MP_REQUIRE(in2d && W && b && spos && ln_gamma && ln_beta && x_out && h_out && n_frames >= 0, MP_EINVAL, "mp_embed_segments: bad arguments");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_embed_segments: unknown dtype %d", dtype);
   MP_REQUIRE(in_features >= 1 && in_features <= 128 && n_segments >= 1 && n_segments <= 64, MP_EINVAL, "mp_embed_segments: bad sizes");
+  MP_REQUIRE(aligned16(x_out) && aligned16(h_out), MP_EALIGN, "mp_embed_segments: x_out / h_out must be 16-byte aligned");
   if (n_frames == 0) return MP_OK;
   const size_t smem = (size_t)in_features * kSegC * sizeof(float);
   int gx = (int)((n_frames + kTokWarps - 1) / kTokWarps);
   const int cap = sm_count() * 2 / n_segments + 1;
   if (gx > cap) gx = cap;
-  embed_segments_kernel<<<dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream>>>(
-      in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, (__nv_bfloat16*)x_out, (__nv_bfloat16*)h_out, n_frames, in_features, n_segments);
+  auto launch = [&](auto kernel) {
+    kernel<<<dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream>>>(in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
+                                                                                 (uint16_t*)h_out, n_frames, in_features, n_segments);
+  };
+  if (dtype == MP_DTYPE_BF16) launch(embed_segments_kernel<Bf16>); else launch(embed_segments_kernel<Fp16>);
   return check_launch("embed_segments_kernel");
 }
 
-int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
+int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
                  const float* hw, const float* hbias, const float* score_w, const float* score_b, float* rot, float* logits,
                  int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score, mp_stream_t stream) {
   using namespace mp;
@@ -442,6 +462,7 @@ int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta,
   MP_REQUIRE(!with_score || (score_w && score_b && logits), MP_EINVAL, "mp_heads_fwd: score head pointers required");
   MP_REQUIRE(n_hyp >= 1 && n_hyp <= 16 && (out_dim == 6 || out_dim == 4), MP_EINVAL, "mp_heads_fwd: bad n_hyp/out_dim");
   MP_REQUIRE(n_clips >= 0 && n_frames >= 1, MP_EINVAL, "mp_heads_fwd: bad sizes");
+  MP_REQUIRE(aligned16(x), MP_EALIGN, "mp_heads_fwd: x must be 16-byte aligned");
   if (n_clips == 0) return MP_OK;
   const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
   const size_t smem = ((size_t)KO * kHeadC + 2 * KO + (size_t)kTokWarps * n_hyp * kJ * out_dim) * sizeof(float);
@@ -450,25 +471,26 @@ int mp_heads_fwd(const void* x, const float* post_gamma, const float* post_beta,
   int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
   const int64_t cap = (int64_t)sm_count() * (smem > 110 * 1024 ? 1 : 2);
   if (ctas > cap) ctas = cap;
-  heads_fwd_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias, score_w, score_b, rot, logits, n_clips, (int)n_frames,
-      n_hyp, out_dim, with_score);
+  heads_fwd_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias, score_w,
+                                                                              score_b, rot, logits, n_clips, (int)n_frames, n_hyp, out_dim,
+                                                                              with_score);
   return check_launch("heads_fwd_kernel");
 }
 
-int mp_bones_head(const void* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
+int mp_bones_head(const float* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,
                   const float* hw, const float* hbias, float* bone_len, int64_t n_clips, int64_t n_frames, int n_segments, int C,
                   void* workspace, size_t workspace_bytes, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == kSegC, MP_EUNSUPPORTED, "mp_bones_head: C=%d (built for 128)", C);
   MP_REQUIRE(x && post_gamma && post_beta && hg && hb && hw && hbias && bone_len && workspace, MP_EINVAL, "mp_bones_head: null pointer");
+  MP_REQUIRE(aligned16(x), MP_EALIGN, "mp_bones_head: x must be 16-byte aligned");
   const int64_t n_tokens = n_clips * n_frames * n_segments;
   MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * sizeof(float), MP_EWORKSPACE, "mp_bones_head: workspace too small");
   if (n_tokens == 0) return MP_OK;
   float* values = reinterpret_cast<float*>(workspace);
-  bones_value_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, post_gamma, post_beta,
-                                                                                         post_eps, hg, hb, hw, hbias, values, n_tokens);
+  bones_value_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
+                                                                                         values, n_tokens);
   MP_CHECK(check_launch("bones_value_kernel"));
   const int64_t n_out = n_clips * n_segments;
   bones_mean_kernel<<<(int)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream>>>(values, bone_len, n_clips, (int)n_frames, n_segments);

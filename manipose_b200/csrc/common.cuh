@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -58,14 +59,44 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
-}
+// ---- the two 16-bit operand formats of the backbone (MP_DTYPE_BF16 / MP_DTYPE_FP16): same tensor-core rate and bytes,
+// fp16 carries 3 more mantissa bits (conversions saturate to +-65504 instead of overflowing to inf) --------------------
+struct Bf16 {
+  using T = __nv_bfloat16;
+  static constexpr uint32_t kUmmaFmt = 1;   // tcgen05 instruction-descriptor a/b format: BF16
+  static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+  }
+  static __device__ __forceinline__ float round1(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+  static __device__ __forceinline__ T from_float(float x) { return __float2bfloat16_rn(x); }
+};
+struct Fp16 {
+  using T = __half;
+  static constexpr uint32_t kUmmaFmt = 0;   // F16
+  static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+  }
+  static __device__ __forceinline__ float round1(float x) {
+    const uint32_t p = pack2(x, 0.f);
+    return unpack2(p).x;
+  }
+  static __device__ __forceinline__ T from_float(float x) {
+    const uint32_t p = pack2(x, 0.f);
+    return __ushort_as_half((unsigned short)(p & 0xffffu));
+  }
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -50,10 +50,11 @@ int require_sm100() {
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+template <typename D>
+__global__ void cast_f32_16_kernel(const float* __restrict__ src, typename D::T* __restrict__ dst, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+  for (; i < n; i += stride) dst[i] = D::from_float(src[i]);
 }
 
 }  // namespace mp
@@ -83,14 +84,18 @@ int mp_set_skeleton(int num_joints, const int32_t* parents, const float* ops) {
   return MP_OK;
 }
 
-int mp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mp_stream_t stream) {
+int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stream_t stream) {
   MP_CHECK(mp::require_sm100());
-  MP_REQUIRE(n >= 0 && (n == 0 || (src && dst)), MP_EINVAL, "mp_cast_f32_to_bf16: bad arguments");
+  MP_REQUIRE(n >= 0 && (n == 0 || (src && dst)), MP_EINVAL, "mp_cast_f32_to_16: bad arguments");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_cast_f32_to_16: unknown dtype %d", dtype);
   if (n == 0) return MP_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  mp::cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
-  return mp::check_launch("cast_f32_bf16_kernel");
+  if (dtype == MP_DTYPE_BF16)
+    mp::cast_f32_16_kernel<mp::Bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  else
+    mp::cast_f32_16_kernel<mp::Fp16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+  return mp::check_launch("cast_f32_16_kernel");
 }
 
 }  // extern "C"

@@ -1,20 +1,25 @@
-// nn.Linear on the 5th-generation tensor cores: Y[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias), bf16 in, fp32 accumulate.
+// nn.Linear on the 5th-generation tensor cores: Y[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias), 16-bit operands
+// (bf16 or fp16), fp32 accumulation in TMEM.
 //
 // Replaces the cuBLAS calls the reference issues through nn.Linear (paths under hpe/mh_so3_hpe/architectures/):
 //   mix_ste.py:246,257   attn.qkv   (C -> 3C, bias)
 //   mix_ste.py:249,280   attn.proj  (C -> C)   + residual add of Block.forward (mix_ste.py:353-355)
 //   mix_ste.py:209-222   mlp.fc1 + exact-erf GELU, mlp.fc2 + residual add (mix_ste.py:356-358)
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0   TMA producer   cp.async.bulk.tensor 2-D tiles of A (128 x 64) and W (BN x 64), 128-byte swizzle, into a
-//                           ring of kStages shared-memory stages; completion on `full` mbarriers
-//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage, accumulating in TMEM;
-//                           tcgen05.commit releases the stage (`empty`) and, after the last k-block, publishes the
-//                           accumulator (`tmem_full`)
-//   warp 2   TMEM allocator 2 x BN columns = two accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 4-7 epilogue      tcgen05.ld (32 lanes x 32 columns) -> +bias, GELU / residual -> per-warp shared-memory
-//                           transpose -> 16-byte coalesced bf16 stores; then arrives on `tmem_empty`
-// Tiles are ordered n-fastest so CTAs running at the same time share A rows in L2.
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised; every global access is a TMA tensor copy):
+//   warp 0     operand producer  cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128-byte swizzle, into a ring of
+//                                kStages shared-memory stages; completion on `full` mbarriers
+//   warp 1     MMA issuer        one thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage into one of TWO TMEM
+//                                accumulators; tcgen05.commit frees the stage and publishes the finished accumulator
+//   warp 2     TMEM allocator, then (residual epilogue) the residual loader: streams 128 x 32 fp32 boxes of the residual
+//                                into a ring of 4 output slots, running ahead across tile boundaries
+//   warps 4-11 epilogue          two groups of 4 warps (TMEM lane quadrant = warp % 4) take alternate 16 KB output boxes:
+//                                tcgen05.ld -> +bias (GELU | +residual read from the slot) -> swizzled st.shared into the slot
+//                                -> one thread issues the TMA store; the slot is recycled when the store has read it
+// Tiles are ordered n-fastest so CTAs running at the same time share A rows in L2.  M tails are zero-filled on load and
+// clipped on store by the tensor maps.
+#include <unordered_map>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -22,39 +27,48 @@ namespace mp {
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kBK = 64;                       // 64 bf16 = 128 bytes = one swizzle-128B atom row
-constexpr int kGemmThreads = 256;
-constexpr int kEpiWarps = 4;
-constexpr int kStagePad = 36;                 // floats per staged row (32 + 4: conflict-free float4 rows)
-constexpr int kEpiStageBytes = kEpiWarps * 32 * kStagePad * 4;   // 18432
+constexpr int kBK = 64;                       // 64 x 16-bit = 128 bytes = one swizzle-128B atom row
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kSlots = 4;                     // output / residual box ring
+constexpr int kBoxBytes = kBM * 128;          // 128 rows x 128 bytes
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
   static constexpr int kBBytes = BN * kBK * 2;             // 32 KB (BN=256) / 16 KB (BN=128)
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 4;
   static constexpr int kTmemCols = 2 * BN;                 // 512 / 256: power of two >= 32
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiStageBytes + 256 /*barriers*/;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kSlots * kBoxBytes + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN, int EPI>
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int BN, int EPI, typename D>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ bias,
-                 const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ Y, int M, int N, int K) {
+linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool kRes = (EPI == MP_EPI_RESIDUAL);
+  constexpr int kBoxCols = kRes ? 32 : 64;                 // fp32 vs 16-bit output: 128 bytes per row either way
+  constexpr int kBoxes = BN / kBoxCols;
+  static_assert(kBoxes % 2 == 0, "boxes alternate between the two epilogue groups");
+
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  float* epi_stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + kEpiStageBytes);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* slot_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slot_base + kSlots * kBoxBytes);
+  uint64_t* full = bars;                            // [kStages]  operands landed
+  uint64_t* empty = full + Cfg::kStages;            // [kStages]  operands consumed
+  uint64_t* tmem_full = empty + Cfg::kStages;       // [2]        accumulator complete
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]        accumulator drained
+  uint64_t* slot_full = tmem_empty + 2;             // [kSlots]   residual box landed
+  uint64_t* slot_empty = slot_full + kSlots;        // [kSlots]   TMA store has read the slot
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(slot_empty + kSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / BN;
@@ -65,6 +79,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_y);
+    if (kRes) ptx::prefetch_tmap(&tm_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -74,6 +90,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    for (int s = 0; s < kSlots; ++s) {
+      ptx::mbar_init(&slot_full[s], 1);
+      ptx::mbar_init(&slot_empty[s], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -88,7 +108,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
+      // ===================== operand producer =====================
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -109,7 +129,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc_16(kBM, BN, D::kUmmaFmt);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -126,8 +146,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t db = ptx::umma_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[stage]);                   // frees the stage when these MMAs have read it
           if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -142,75 +162,108 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
+  } else if (warp == 2) {
+    if (kRes && lane == 0) {
+      // ===================== residual loader =====================
+      uint32_t n = 0;   // running box index of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
+        for (int b = 0; b < kBoxes; ++b, ++n) {
+          const uint32_t slot = n % kSlots, use = n / kSlots;
+          ptx::mbar_wait(&slot_empty[slot], (use & 1) ^ 1);
+          ptx::mbar_expect_tx(&slot_full[slot], kBoxBytes);
+          ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &slot_full[slot], n_blk * BN + b * kBoxCols, m_blk * kBM);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int w = warp - 4;                      // == warp % 4: TMEM lanes [32w, 32w+32)
-    float* my_stage = epi_stage + w * 32 * kStagePad;
+    const int q = warp & 3;                      // TMEM lane quadrant: lanes [32q, 32q+32)
+    const int grp = (warp - 4) >> 2;             // 0: warps 4-7 (even boxes), 1: warps 8-11 (odd boxes)
+    const bool elected = ((warp - 4) & 3) == 0 && lane == 0;
+    const int row = 32 * q + lane;               // row of the 128-row tile owned by this thread
+    const uint32_t sw = (uint32_t)(row & 7);     // 128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t i = 0;                              // running box index of this group
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(32 * w) << 16) + (uint32_t)(acc * BN);
-      const int row0 = m_blk * kBM + 32 * w;
+      const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(t_addr + (uint32_t)(c * 32), r);
-        ptx::tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = __ldg(b4 + q);
-          float4 v;
-          v.x = __uint_as_float(r[4 * q + 0]) + bb.x;
-          v.y = __uint_as_float(r[4 * q + 1]) + bb.y;
-          v.z = __uint_as_float(r[4 * q + 2]) + bb.z;
-          v.w = __uint_as_float(r[4 * q + 3]) + bb.w;
-          if (EPI == MP_EPI_GELU) {
-            v.x = gelu_erf(v.x);
-            v.y = gelu_erf(v.y);
-            v.z = gelu_erf(v.z);
-            v.w = gelu_erf(v.w);
-          }
-          *reinterpret_cast<float4*>(my_stage + lane * kStagePad + 4 * q) = v;
+      for (int b = grp; b < kBoxes; b += 2, ++i) {
+        const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
+        uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+        const int col0 = n_blk * BN + b * kBoxCols;
+        if (kRes) {
+          ptx::mbar_wait(&slot_full[slot], use & 1);             // residual box has landed
+        } else {
+          ptx::mbar_wait(&slot_empty[slot], (use & 1) ^ 1);      // previous store from this slot has read it
         }
-        __syncwarp();
-        // transposed read-back: 4 lanes cover one row's 32 columns (8 each), 8 rows per pass
+        if (kRes) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 32), r);
+          ptx::tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + (lane >> 2), ch = lane & 3;
-          const int grow = row0 + rr;
-          const float4 lo = *reinterpret_cast<const float4*>(my_stage + rr * kStagePad + ch * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(my_stage + rr * kStagePad + ch * 8 + 4);
-          float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          if (grow < M) {
-            const size_t off = (size_t)grow * N + col0 + ch * 8;
-            if (EPI == MP_EPI_RESIDUAL) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(resid + off);
-              const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-              f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+          for (int c = 0; c < 8; ++c) {
+            float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4));
+            const float4 bb = __ldg(b4 + c);
+            float4 v = *p;
+            v.x += __uint_as_float(r[4 * c + 0]) + bb.x;
+            v.y += __uint_as_float(r[4 * c + 1]) + bb.y;
+            v.z += __uint_as_float(r[4 * c + 2]) + bb.z;
+            v.w += __uint_as_float(r[4 * c + 3]) + bb.w;
+            *p = v;
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + half * 32), r);
+            ptx::tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 b0 = __ldg(b4 + 2 * c), b1 = __ldg(b4 + 2 * c + 1);
+              float f[8] = {__uint_as_float(r[8 * c + 0]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
+                            __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w,
+                            __uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
+                            __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
+              if (EPI == MP_EPI_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+              }
+              uint4 o;
+              o.x = D::pack2(f[0], f[1]);
+              o.y = D::pack2(f[2], f[3]);
+              o.z = D::pack2(f[4], f[5]);
+              o.w = D::pack2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(srow + (((uint32_t)(half * 4 + c) ^ sw) << 4)) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]);
-            o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]);
-            o.w = pack_bf16x2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(Y + off) = o;
           }
         }
-        __syncwarp();
+        ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
+        named_bar_sync(1 + grp, 128);
+        if (elected) {
+          ptx::tma_store_2d(&tm_y, slot_base + slot * kBoxBytes, col0, m_blk * kBM);
+          ptx::bulk_commit();
+          if (i > 0) {
+            ptx::bulk_wait_read<1>();            // the group's previous store has finished reading its slot
+            ptx::mbar_arrive(&slot_empty[(uint32_t)grp + 2 * ((i - 1) & 1)]);
+          }
+        }
       }
       ptx::tc_fence_before();
+      __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (elected) ptx::bulk_wait<0>();            // all output writes complete before the CTA retires
   }
 
   __syncwarp();
@@ -238,71 +291,105 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major bf16 [rows, cols] with row stride ld elements; box = box_rows x 64 columns, 128-byte swizzle, OOB -> 0
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+struct TmapKey {
+  const void* ptr;
+  int64_t rows, cols;
+  int box_rows, type;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && type == o.type; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.box_rows * 31 + (size_t)k.type;
+    return h;
+  }
+};
+
+// Dense row-major [rows, cols]; box = box_rows x 128 bytes of columns, 128-byte swizzle, OOB reads -> 0, OOB writes dropped.
+// type: 0 = bf16, 1 = fp16, 2 = fp32.  Descriptors are pure functions of the key, so they are memoised per host thread.
+int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type) {
+  thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{ptr, rows, cols, box_rows, type};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return MP_OK;
+  }
   EncodeTiledFn fn = encode_fn();
   MP_REQUIRE(fn != nullptr, MP_EDEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  const int esz = type == 2 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MP_REQUIRE(r == CUDA_SUCCESS, MP_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
-             (long long)rows, (long long)cols, (long long)ld);
+  const CUtensorMapDataType dt = type == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (type == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MP_REQUIRE(r == CUDA_SUCCESS, MP_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld type=%d)", (int)r,
+             (long long)rows, (long long)cols, type);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
   return MP_OK;
 }
 
-template <int BN, int EPI>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const float* bias, const __nv_bfloat16* resid, __nv_bfloat16* Y, int M,
-                int N, int K, cudaStream_t stream) {
+template <int BN, int EPI, typename D>
+int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr, const float* bias, int M, int N,
+                  int K, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kernel = gemm_bf16_kernel<BN, EPI>;
+  auto kernel = linear_kernel<BN, EPI, D>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(linear_kernel): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = (N / BN) * ((M + kBM - 1) / kBM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, bias, resid, Y, M, N, K);
-  return check_launch("gemm_bf16_kernel");
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K);
+  return check_launch("linear_kernel");
 }
 
-template <int BN>
-int dispatch_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tw, const float* bias, const __nv_bfloat16* resid,
-                 __nv_bfloat16* Y, int M, int N, int K, cudaStream_t stream) {
+template <int BN, typename D>
+int dispatch_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr, const float* bias,
+                 int M, int N, int K, cudaStream_t stream) {
   switch (epilogue) {
-    case MP_EPI_BIAS: return launch_gemm<BN, MP_EPI_BIAS>(ta, tw, bias, resid, Y, M, N, K, stream);
-    case MP_EPI_GELU: return launch_gemm<BN, MP_EPI_GELU>(ta, tw, bias, resid, Y, M, N, K, stream);
-    case MP_EPI_RESIDUAL: return launch_gemm<BN, MP_EPI_RESIDUAL>(ta, tw, bias, resid, Y, M, N, K, stream);
+    case MP_EPI_BIAS: return launch_linear<BN, MP_EPI_BIAS, D>(ta, tw, ty, tr, bias, M, N, K, stream);
+    case MP_EPI_GELU: return launch_linear<BN, MP_EPI_GELU, D>(ta, tw, ty, tr, bias, M, N, K, stream);
+    case MP_EPI_RESIDUAL: return launch_linear<BN, MP_EPI_RESIDUAL, D>(ta, tw, ty, tr, bias, M, N, K, stream);
   }
-  return fail(MP_EINVAL, "mp_gemm_bf16: unknown epilogue %d", epilogue);
+  return fail(MP_EINVAL, "mp_linear: unknown epilogue %d", epilogue);
 }
 
 }  // namespace
 }  // namespace mp
 
-extern "C" int mp_gemm_bf16(const void* A, const void* W, const float* bias, const void* resid, void* Y, int64_t M, int64_t N,
-                            int64_t K, int epilogue, mp_stream_t stream) {
+extern "C" int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N, int64_t K,
+                         int epilogue, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(A && W && bias && Y, MP_EINVAL, "mp_gemm_bf16: null pointer");
+  MP_REQUIRE(A && W && bias && Y, MP_EINVAL, "mp_linear: null pointer");
   MP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && N >= 128 && N % 128 == 0 && K >= 64 && K % 64 == 0, MP_EINVAL,
-             "mp_gemm_bf16: unsupported shape M=%lld N=%lld K=%lld (N %% 128 == 0, K %% 64 == 0)", (long long)M, (long long)N, (long long)K);
-  MP_REQUIRE(epilogue != MP_EPI_RESIDUAL || resid != nullptr, MP_EINVAL, "mp_gemm_bf16: residual epilogue needs resid");
+             "mp_linear: unsupported shape M=%lld N=%lld K=%lld (N %% 128 == 0, K %% 64 == 0)", (long long)M, (long long)N, (long long)K);
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_linear: unknown dtype %d", dtype);
+  MP_REQUIRE(epilogue != MP_EPI_RESIDUAL || resid != nullptr, MP_EINVAL, "mp_linear: residual epilogue needs resid");
   MP_REQUIRE(aligned16(A) && aligned16(W) && aligned16(Y) && aligned16(resid) && aligned16(bias), MP_EALIGN,
-             "mp_gemm_bf16: pointers must be 16-byte aligned");
+             "mp_linear: pointers must be 16-byte aligned");
   if (M == 0) return MP_OK;
   const bool wide = (N % 256 == 0);
-  CUtensorMap ta, tw;
-  MP_CHECK(make_tmap(&ta, A, M, K, K, kBM));
-  MP_CHECK(make_tmap(&tw, W, N, K, K, wide ? 256 : 128));
-  if (wide)
-    return dispatch_epi<256>(epilogue, ta, tw, bias, (const __nv_bfloat16*)resid, (__nv_bfloat16*)Y, (int)M, (int)N, (int)K,
-                             (cudaStream_t)stream);
-  return dispatch_epi<128>(epilogue, ta, tw, bias, (const __nv_bfloat16*)resid, (__nv_bfloat16*)Y, (int)M, (int)N, (int)K,
-                           (cudaStream_t)stream);
+  const bool res = epilogue == MP_EPI_RESIDUAL;
+  CUtensorMap ta, tw, ty, tr;
+  MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
+  MP_CHECK(get_tmap(&tw, W, N, K, wide ? 256 : 128, dtype));
+  MP_CHECK(get_tmap(&ty, Y, M, N, kBM, res ? 2 : dtype));
+  if (res)
+    MP_CHECK(get_tmap(&tr, resid, M, N, kBM, 2));
+  else
+    tr = ty;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == MP_DTYPE_BF16) {
+    if (wide) return dispatch_epi<256, Bf16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
+    return dispatch_epi<128, Bf16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
+  }
+  if (wide) return dispatch_epi<256, Fp16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
+  return dispatch_epi<128, Fp16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
 }

@@ -248,27 +248,34 @@ def mpjpe(pred, gt):
 
 
 # ------------------------------------------------------------------------------------------------ backbone pieces
-def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+TORCH_DTYPE = {L.MP_DTYPE_BF16: torch.bfloat16, L.MP_DTYPE_FP16: torch.float16}
+DTYPE_CODE = {"bf16": L.MP_DTYPE_BF16, "fp16": L.MP_DTYPE_FP16, torch.bfloat16: L.MP_DTYPE_BF16, torch.float16: L.MP_DTYPE_FP16}
+
+
+def cast16(src: torch.Tensor, dtype: int, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 -> bf16 / fp16 (round to nearest even; fp16 saturates to +-65504)."""
     _need_cuda(src)
     src = _f32(src)
     if dst is None:
-        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    rc = L.load().mp_cast_f32_to_bf16(L.ptr(src), L.ptr(dst), src.numel(), L.stream_ptr())
-    L.check(rc, "mp_cast_f32_to_bf16")
+        dst = torch.empty(src.shape, dtype=TORCH_DTYPE[dtype], device=src.device)
+    rc = L.load().mp_cast_f32_to_16(L.ptr(src), L.ptr(dst), src.numel(), dtype, L.stream_ptr())
+    L.check(rc, "mp_cast_f32_to_16")
     _count()
     return dst
 
 
-def gemm(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]); a, w, out, resid bf16; bias fp32."""
+def linear(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias[N]); a, w 16-bit (same dtype); bias fp32;
+    out 16-bit (BIAS / GELU) or fp32 with resid fp32 (RESIDUAL; out may alias resid)."""
     m, k = a.shape
     n = w.shape[0]
+    dtype = DTYPE_CODE[a.dtype]
     timing = GEMM_TIMING
     if timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = L.load().mp_gemm_bf16(L.ptr(a), L.ptr(w), L.ptr(bias), L.ptr(resid), L.ptr(out), m, n, k, epilogue, L.stream_ptr())
-    L.check(rc, "mp_gemm_bf16")
+    rc = L.load().mp_linear(L.ptr(a), L.ptr(w), L.ptr(bias), L.ptr(resid), L.ptr(out), m, n, k, epilogue, dtype, L.stream_ptr())
+    L.check(rc, "mp_linear")
     _count()
     if timing is not None:
         e1.record()
@@ -276,32 +283,32 @@ def gemm(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
     return out
 
 
-def layernorm(x_in, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6):
+def layernorm(x_in, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, dtype=L.MP_DTYPE_BF16):
     n_tokens, c = x_in.shape
     pg, pb = post if post is not None else (None, None)
     lg, lb = ln if ln is not None else (None, None)
     rc = L.load().mp_layernorm(L.ptr(x_in), L.ptr(x_out), L.ptr(h_out), L.ptr(pg), L.ptr(pb), post_eps, L.ptr(pos), pos_div, pos_mod,
-                               L.ptr(lg), L.ptr(lb), ln_eps, n_tokens, c, L.stream_ptr())
+                               L.ptr(lg), L.ptr(lb), ln_eps, n_tokens, c, dtype, L.stream_ptr())
     L.check(rc, "mp_layernorm")
     _count()
 
 
-def embed_joints(x2d, w, b, spos, ln_g, ln_b, ln_eps, x_out, h_out, n_tokens, n_joints, c):
+def embed_joints(x2d, w, b, spos, ln_g, ln_b, ln_eps, x_out, h_out, n_tokens, n_joints, c, dtype):
     rc = L.load().mp_embed_joints(L.ptr(x2d), L.ptr(w), L.ptr(b), L.ptr(spos), L.ptr(ln_g), L.ptr(ln_b), ln_eps, L.ptr(x_out),
-                                  L.ptr(h_out), n_tokens, n_joints, c, L.stream_ptr())
+                                  L.ptr(h_out), n_tokens, n_joints, c, dtype, L.stream_ptr())
     L.check(rc, "mp_embed_joints")
     _count()
 
 
-def embed_segments(x2d, w, b, spos, ln_g, ln_b, ln_eps, x_out, h_out, n_frames, in_features, n_segments, c):
+def embed_segments(x2d, w, b, spos, ln_g, ln_b, ln_eps, x_out, h_out, n_frames, in_features, n_segments, c, dtype):
     rc = L.load().mp_embed_segments(L.ptr(x2d), L.ptr(w), L.ptr(b), L.ptr(spos), L.ptr(ln_g), L.ptr(ln_b), ln_eps, L.ptr(x_out),
-                                    L.ptr(h_out), n_frames, in_features, n_segments, c, L.stream_ptr())
+                                    L.ptr(h_out), n_frames, in_features, n_segments, c, dtype, L.stream_ptr())
     L.check(rc, "mp_embed_segments")
     _count()
 
 
 def attention(qkv, out, n_clips, n_frames, n_tok, c, n_heads, mode):
-    rc = L.load().mp_attention(L.ptr(qkv), L.ptr(out), n_clips, n_frames, n_tok, c, n_heads, mode, L.stream_ptr())
+    rc = L.load().mp_attention(L.ptr(qkv), L.ptr(out), n_clips, n_frames, n_tok, c, n_heads, mode, DTYPE_CODE[qkv.dtype], L.stream_ptr())
     L.check(rc, "mp_attention")
     _count()
     return out
