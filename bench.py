@@ -246,7 +246,7 @@ def run_gpu(args):
     e2e_value = frames * args.steps / (ms_e2e / 1000.0)
 
     if rank == 0:
-        cpu_value, cpu_threads, cpu_reps = cpu_forward_rate(clips=4, reps=3)
+        cpu_value, cpu_threads, cpu_reps = (0.0, 0, 0) if args.skip_cpu_baseline else cpu_forward_rate(clips=4, reps=3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--clips", type=int, default=1024, help="clips per GPU per step (BASELINE config 3: 1024)")
     ap.add_argument("--micro-batch-clips", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit operand format of the backbone")
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: do not time the CPU oracle")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -118,6 +118,8 @@ class MixSTE(nn.Module):
     # 16-bit format of everything that feeds a tensor-core contraction ("bf16": BASELINE config 3; "fp16": same speed and
     # bytes, 3 more mantissa bits — needed for the 0.05 mm end-to-end MPJPE gate)
     compute_dtype = "bf16"
+    # fuse the residual Linear with the LayerNorms that follow it (C = 512 only); False keeps the separate kernels
+    fuse_layernorm = True
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
@@ -217,18 +219,30 @@ class MixSTE(nn.Module):
         for i in range(depth):
             blocks.append((self.STEblocks[i], 4 * i, L.MP_ATTN_SPATIAL, self.Spatial_norm))
             blocks.append((self.TTEblocks[i], 4 * (depth + i), L.MP_ATTN_TEMPORAL, self.Temporal_norm))
+        fused = c == 512 and self.fuse_layernorm     # residual GEMM + LayerNorms in one kernel (CTA pairs, N = 512)
         for bi, (blk, wi, mode, post) in enumerate(blocks):
+            last = bi + 1 == len(blocks)
+            nxt = None if last else blocks[bi + 1][0]
+            pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
             ops.linear(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
             ops.attention(qkv, h, n_clips, n_frames, n_tok, c, heads, mode)
-            ops.linear(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
-            ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
+            if fused:
+                ops.linear_ln(h, w[wi + 1], blk.attn.proj.bias, x, x, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps)
+            else:
+                ops.linear(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+                ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
             ops.linear(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
-            ops.linear(hid, w[wi + 3], blk.mlp.fc2.bias, x, L.MP_EPI_RESIDUAL, resid=x)
-            if bi + 1 < len(blocks):
-                nxt = blocks[bi + 1][0]
-                pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
-                ops.layernorm(x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
-                              ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
+            if fused:
+                if last:
+                    ops.linear_ln(hid, w[wi + 3], blk.mlp.fc2.bias, x, x, None)
+                else:
+                    ops.linear_ln(hid, w[wi + 3], blk.mlp.fc2.bias, x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos,
+                                  pos_div=n_tok, pos_mod=n_frames, ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps)
+            else:
+                ops.linear(hid, w[wi + 3], blk.mlp.fc2.bias, x, L.MP_EPI_RESIDUAL, resid=x)
+                if not last:
+                    ops.layernorm(x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
+                                  ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
         return x
 
     def _check_input(self, x: torch.Tensor):

@@ -18,6 +18,8 @@
 //                                -> one thread issues the TMA store; the slot is recycled when the store has read it
 // Tiles are ordered n-fastest so CTAs running at the same time share A rows in L2.  M tails are zero-filled on load and
 // clipped on store by the tensor maps.
+#include <stdlib.h>
+
 #include <unordered_map>
 
 #include "common.cuh"
@@ -275,12 +277,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   }
 }
 
-// ---- tensor maps ---------------------------------------------------------------------------------------------------
+}  // namespace
+
+// ---- tensor maps (shared with gemm2.cu) ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn encode_fn() {
+static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* p = nullptr;
@@ -332,6 +336,10 @@ int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int 
   return MP_OK;
 }
 
+int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream);  // gemm2.cu
+
+namespace {
+
 template <int BN, int EPI, typename D>
 int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr, const float* bias, int M, int N,
                   int K, cudaStream_t stream) {
@@ -377,6 +385,9 @@ extern "C" int mp_linear(const void* A, const void* W, const float* bias, const 
   if (M == 0) return MP_OK;
   const bool wide = (N % 256 == 0);
   const bool res = epilogue == MP_EPI_RESIDUAL;
+  // CTA pairs halve the weight traffic out of L2; MANIPOSE_SINGLE_CTA=1 keeps the one-CTA kernel (A/B measurements)
+  static const bool single_only = getenv("MANIPOSE_SINGLE_CTA") != nullptr;
+  if (wide && !res && !single_only) return pair_linear(A, W, bias, Y, (int)M, (int)N, (int)K, epilogue, dtype, (cudaStream_t)stream);
   CUtensorMap ta, tw, ty, tr;
   MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
   MP_CHECK(get_tmap(&tw, W, N, K, wide ? 256 : 128, dtype));

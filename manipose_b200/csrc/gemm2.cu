@@ -1,0 +1,653 @@
+// CTA-pair (cta_group::2) tensor-core kernels for the C = 512 rotation backbone: two SMs of one TPC compute a 256-row tile
+// together, each CTA feeding 128 rows of A and HALF of the weight rows, so every weight byte is pulled out of L2 once per pair
+// instead of once per CTA (the single-CTA kernel in gemm.cu is L2-bandwidth bound at ~11 TB/s of operand traffic).
+//
+//   pair_linear_kernel     Y[M,N] (16-bit) = act(A W^T + b), N % 256 == 0      256 x 256 tile, two TMEM accumulators
+//                          (qkv: mix_ste.py:246,257; fc1 + GELU: mix_ste.py:209-222)
+//   pair_linear_ln_kernel  N = 512 = the whole row: x = resid + A W^T + b      256 x 512 tile, one TMEM accumulator
+//                          (proj / fc2 + residual add of Block.forward, mix_ste.py:352-358), optionally followed IN THE EPILOGUE by
+//                            x = LN_post(x) (+ temporal pos-embed)             shared Spatial_norm / Temporal_norm, mix_ste.py:143,149,154,166,170
+//                            h = LN_pre(x) as 16-bit                            norm2 of this block / norm1 of the next, mix_ste.py:353,356
+//                          so the LayerNorm kernels and their extra pass over the residual stream disappear.
+//
+// Roles per CTA (384 threads): warp 0 operand producer (TMA), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator + residual
+// box loader, warps 4-11 epilogue (TMEM lane quadrant = warp % 4; column half / alternate boxes = (warp - 4) / 4).  Barriers that the
+// leader's MMA thread waits on (`full`, `tmem_empty`) live in the leader CTA and are arrived on remotely by the peer; barriers the
+// MMA thread signals (`empty`, `tmem_full`) are multicast tcgen05.commit arrivals into both CTAs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mp {
+
+int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type);   // gemm.cu
+
+namespace {
+
+constexpr int kBM = 128;                      // rows per CTA (256 per pair)
+constexpr int kBK = 64;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kSlots = 4;
+constexpr int kBoxBytes = kBM * 128;
+constexpr int kABytes = kBM * kBK * 2;        // 16 KB
+constexpr int kWHalfBytes = 128 * kBK * 2;    // 16 KB: the 128 weight rows this CTA contributes to one N = 256 instruction
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct PairBars {
+  uint64_t* full;        // [stages]  leader: operands of both CTAs landed (count 2 + tx bytes)
+  uint64_t* empty;       // [stages]  each CTA: stage consumed (multicast commit)
+  uint64_t* tmem_full;   // [2]       each CTA: accumulator complete (multicast commit)
+  uint64_t* tmem_empty;  // [2]       leader: accumulator drained by the 16 epilogue warps of the pair
+  uint64_t* slot_full;   // [kSlots]  residual box landed
+  uint64_t* slot_empty;  // [kSlots]  slot free again
+};
+
+template <int kStages>
+__device__ __forceinline__ PairBars carve_bars(uint8_t* p) {
+  PairBars b;
+  b.full = reinterpret_cast<uint64_t*>(p);
+  b.empty = b.full + kStages;
+  b.tmem_full = b.empty + kStages;
+  b.tmem_empty = b.tmem_full + 2;
+  b.slot_full = b.tmem_empty + 2;
+  b.slot_empty = b.slot_full + kSlots;
+  return b;
+}
+
+template <int kStages>
+__device__ __forceinline__ void init_bars(const PairBars& b) {
+  for (int s = 0; s < kStages; ++s) {
+    ptx::mbar_init(&b.full[s], 2);
+    ptx::mbar_init(&b.empty[s], 1);
+  }
+  for (int a = 0; a < 2; ++a) {
+    ptx::mbar_init(&b.tmem_full[a], 1);
+    ptx::mbar_init(&b.tmem_empty[a], 2 * kEpiWarps);
+  }
+  for (int s = 0; s < kSlots; ++s) {
+    ptx::mbar_init(&b.slot_full[s], 1);
+    ptx::mbar_init(&b.slot_empty[s], 1);
+  }
+  ptx::fence_mbar_init();
+}
+
+// ===================================================================================== Y = act(A W^T + b), 16-bit out
+template <int EPI, typename D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+                   const float* __restrict__ bias, int M, int N, int K) {
+  constexpr int kStages = 5;
+  constexpr int kStageBytes = kABytes + kWHalfBytes;     // 32 KB per CTA per stage
+  constexpr int BN = 256;
+  constexpr int kBoxes = 4;                              // 64-column 16-bit boxes per tile
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint8_t* slot_base = smem + kStages * kStageBytes;
+  const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.slot_empty + kSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_blocks = N / BN;
+  const int m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
+  const int num_tiles = n_blocks * m_pairs;
+  const int k_blocks = K / kBK;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_y);
+  }
+  if (warp == 1 && lane == 0) init_bars<kStages>(bars);
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== operand producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m_pair = tile / n_blocks, n_blk = tile - m_pair * n_blocks;
+        const int row_a = m_pair * 2 * kBM + (int)rank * kBM;
+        const int row_w = n_blk * BN + (int)rank * 128;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * kStageBytes;
+          const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
+          ptx::mbar_expect_tx_cluster(full_leader, kStageBytes);
+          ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
+          ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, row_w);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer (leader CTA) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_16(2 * kBM, BN, D::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        ptx::mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars.full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t da = ptx::umma_desc_sw128(sa);
+          const uint64_t db = ptx::umma_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_pair(&bars.empty[stage]);
+          if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[acc]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const bool elected = ((warp - 4) & 3) == 0 && lane == 0;
+    const int row = 32 * q + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t i = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m_pair = tile / n_blocks, n_blk = tile - m_pair * n_blocks;
+      const int row0 = m_pair * 2 * kBM + (int)rank * kBM;
+      ptx::mbar_wait(&bars.tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int b = grp; b < kBoxes; b += 2, ++i) {
+        const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
+        uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+        const int col0 = n_blk * BN + b * 64;
+        ptx::mbar_wait(&bars.slot_empty[slot], (use & 1) ^ 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + half * 32), r);
+          ptx::tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 b0 = __ldg(b4 + 2 * c), b1 = __ldg(b4 + 2 * c + 1);
+            float f[8] = {__uint_as_float(r[8 * c + 0]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
+                          __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w,
+                          __uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
+                          __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
+            if (EPI == MP_EPI_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            }
+            uint4 o;
+            o.x = D::pack2(f[0], f[1]);
+            o.y = D::pack2(f[2], f[3]);
+            o.z = D::pack2(f[4], f[5]);
+            o.w = D::pack2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(srow + (((uint32_t)(half * 4 + c) ^ sw) << 4)) = o;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);
+        if (elected) {
+          ptx::tma_store_2d(&tm_y, slot_base + slot * kBoxBytes, col0, row0);
+          ptx::bulk_commit();
+          if (i > 0) {
+            ptx::bulk_wait_read<1>();
+            ptx::mbar_arrive(&bars.slot_empty[(uint32_t)grp + 2 * ((i - 1) & 1)]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&bars.tmem_empty[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (elected) ptx::bulk_wait<0>();
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();     // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ===================================================================================== x = resid + A W^T + b (+ LayerNorms), N = 512
+struct LnArgs {
+  const float* bias;
+  const float* post_g;   // NULL: no post-norm
+  const float* post_b;
+  const float* pos;      // NULL or [pos_mod, 512]
+  const float* ln_g;     // NULL: no pre-norm / h output
+  const float* ln_b;
+  float post_eps, ln_eps;
+  int pos_div, pos_mod;
+};
+
+// combine (mean, M2) of the two 256-column halves of a row
+__device__ __forceinline__ void row_stats_exchange(float2* sx, int grp, int row, float mean_h, float m2_h, float eps, float& mean, float& rstd) {
+  sx[grp * kBM + row] = make_float2(mean_h, m2_h);
+  named_bar_sync(3, 256);
+  const float2 o = sx[(grp ^ 1) * kBM + row];
+  named_bar_sync(3, 256);      // both halves have read before the buffer is reused
+  const float delta = o.x - mean_h;
+  mean = 0.5f * (mean_h + o.x);
+  const float m2 = m2_h + o.y + delta * delta * 128.0f;   // n_a n_b / (n_a + n_b) = 256 * 256 / 512
+  rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
+}
+
+template <typename D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
+                      const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, LnArgs args, int M, int K) {
+  constexpr int kStages = 3;
+  constexpr int kStageBytes = kABytes + 2 * kWHalfBytes;   // 48 KB: A + this CTA's share of both N = 256 halves
+  constexpr int kN = 512;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint8_t* slot_base = smem + kStages * kStageBytes;
+  const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.slot_empty + kSlots);
+  float2* sx = reinterpret_cast<float2*>(tmem_holder + 4);           // [2][128] row statistics exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = (M + 2 * kBM - 1) / (2 * kBM);
+  const int k_blocks = K / kBK;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const bool has_post = args.post_g != nullptr, has_ln = args.ln_g != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_r);
+    ptx::prefetch_tmap(&tm_x);
+    if (has_ln) ptx::prefetch_tmap(&tm_h);
+  }
+  if (warp == 1 && lane == 0) init_bars<kStages>(bars);
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== operand producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int row_a = tile * 2 * kBM + (int)rank * kBM;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * kStageBytes;
+          const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
+          ptx::mbar_expect_tx_cluster(full_leader, kStageBytes);
+          ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
+          ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, (int)rank * 128);                      // W rows of columns [0, 256)
+          ptx::tma_load_2d_pair(sa + kABytes + kWHalfBytes, &tm_w, full_leader, kb * kBK, 256 + (int)rank * 128);  // columns [256, 512)
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_16(2 * kBM, 256, D::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        ptx::mbar_wait(&bars.tmem_empty[0], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars.full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t da = ptx::umma_desc_sw128(sa);
+          const uint64_t db0 = ptx::umma_desc_sw128(sa + kABytes);
+          const uint64_t db1 = ptx::umma_desc_sw128(sa + kABytes + kWHalfBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            ptx::umma_f16_pair(tmem_base, da + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
+            ptx::umma_f16_pair(tmem_base + 256u, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, accum);
+          }
+          ptx::umma_commit_pair(&bars.empty[stage]);
+          if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[0]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===================== residual loader =====================
+      // Per tile and column half g, the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h boxes.
+      // Use u of half g lives in slot g + 2 (u & 1); every tile contributes an even number of uses per slot, so parities restart.
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int row0 = tile * 2 * kBM + (int)rank * kBM;
+        for (int j = 0; j < 8; ++j) {
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t slot = (uint32_t)g + 2 * (j & 1);
+            ptx::mbar_wait(&bars.slot_empty[slot], ((j >> 1) & 1) ^ 1);
+            ptx::mbar_expect_tx(&bars.slot_full[slot], kBoxBytes);
+            ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], g * 256 + j * 32, row0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;             // column half [256 grp, 256 grp + 256)
+    const bool elected = ((warp - 4) & 3) == 0 && lane == 0;
+    const int row = 32 * q + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256);
+    uint32_t acc_phase = 0;
+    int pending = -1;                            // slot whose TMA store may still be reading shared memory
+
+    // after a slot's content has been handed to a TMA store: recycle the PREVIOUS store's slot (its read is done by now)
+    auto after_store = [&](uint32_t slot) {
+      ptx::bulk_commit();
+      if (pending >= 0) {
+        ptx::bulk_wait_read<1>();
+        ptx::mbar_arrive(&bars.slot_empty[pending]);
+      }
+      pending = (int)slot;
+    };
+
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int row0 = tile * 2 * kBM + (int)rank * kBM;
+      const int grow = row0 + row;
+      ptx::mbar_wait(&bars.tmem_full[0], acc_phase);
+      ptx::tc_fence_after();
+      uint32_t u = 0;                            // slot-use index of this half within the tile
+
+      // ---- pass A: v = acc + bias + resid; shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j, ++u) {
+        const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+        uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+        ptx::mbar_wait(&bars.slot_full[slot], (j >> 1) & 1);
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
+        ptx::tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(args.bias + grp * 256 + j * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4));
+          const float4 bb = __ldg(b4 + c);
+          float4 v = *p;
+          v.x += __uint_as_float(r[4 * c + 0]) + bb.x;
+          v.y += __uint_as_float(r[4 * c + 1]) + bb.y;
+          v.z += __uint_as_float(r[4 * c + 2]) + bb.z;
+          v.w += __uint_as_float(r[4 * c + 3]) + bb.w;
+          if (j == 0 && c == 0) shift = v.x;
+          const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          r[4 * c + 0] = __float_as_uint(v.x);
+          r[4 * c + 1] = __float_as_uint(v.y);
+          r[4 * c + 2] = __float_as_uint(v.z);
+          r[4 * c + 3] = __float_as_uint(v.w);
+          if (!has_post) *p = v;
+        }
+        if (has_post || has_ln) ptx::tmem_st32(t_row + (uint32_t)(j * 32), r);
+        if (!has_post) ptx::fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);            // every thread of the half is done with the residual box
+        if (elected) {
+          if (!has_post) {
+            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, grp * 256 + j * 32, row0);
+            after_store(slot);
+          } else {
+            ptx::mbar_arrive(&bars.slot_empty[slot]);
+          }
+        }
+      }
+      float mean = 0.f, rstd = 0.f;
+      if (has_post || has_ln) {
+        ptx::tmem_st_wait();
+        const float mh = shift + s1 * (1.0f / 256.0f);
+        const float m2h = fmaxf(s2 - s1 * s1 * (1.0f / 256.0f), 0.f);
+        row_stats_exchange(sx, grp, row, mh, m2h, has_post ? args.post_eps : args.ln_eps, mean, rstd);
+      }
+
+      // ---- pass B (post-norm): y = LN_post(v) (+ pos-embed) -> x_out and back to TMEM, statistics of y
+      if (has_post) {
+        const float* pos_row = args.pos ? args.pos + (size_t)((grow / args.pos_div) % args.pos_mod) * kN : nullptr;
+        s1 = 0.f;
+        s2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j, ++u) {
+          const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+          uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+          ptx::mbar_wait(&bars.slot_empty[slot], ((u >> 1) & 1) ^ 1);
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
+          ptx::tmem_ld_wait();
+          const int col = grp * 256 + j * 32;
+          const float4* g4 = reinterpret_cast<const float4*>(args.post_g + col);
+          const float4* be4 = reinterpret_cast<const float4*>(args.post_b + col);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 gg = __ldg(g4 + c), bb = __ldg(be4 + c);
+            float4 y;
+            y.x = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, gg.x, bb.x);
+            y.y = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, gg.y, bb.y);
+            y.z = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, gg.z, bb.z);
+            y.w = fmaf((__uint_as_float(r[4 * c + 3]) - mean) * rstd, gg.w, bb.w);
+            if (pos_row != nullptr && grow < M) {
+              const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + col) + c);
+              y.x += pe.x;
+              y.y += pe.y;
+              y.z += pe.z;
+              y.w += pe.w;
+            }
+            if (j == 0 && c == 0) shift = y.x;
+            const float d0 = y.x - shift, d1 = y.y - shift, d2 = y.z - shift, d3 = y.w - shift;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            r[4 * c + 0] = __float_as_uint(y.x);
+            r[4 * c + 1] = __float_as_uint(y.y);
+            r[4 * c + 2] = __float_as_uint(y.z);
+            r[4 * c + 3] = __float_as_uint(y.w);
+            *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4)) = y;
+          }
+          if (has_ln) ptx::tmem_st32(t_row + (uint32_t)(j * 32), r);
+          ptx::fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
+            after_store(slot);
+          }
+        }
+        if (has_ln) {
+          ptx::tmem_st_wait();
+          const float mh = shift + s1 * (1.0f / 256.0f);
+          const float m2h = fmaxf(s2 - s1 * s1 * (1.0f / 256.0f), 0.f);
+          row_stats_exchange(sx, grp, row, mh, m2h, args.ln_eps, mean, rstd);
+        }
+      }
+
+      // ---- pass C (pre-norm): h = LN_pre(x) as 16-bit, 64-column boxes
+      if (has_ln) {
+#pragma unroll 1
+        for (int jj = 0; jj < 4; ++jj, ++u) {
+          const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+          uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+          ptx::mbar_wait(&bars.slot_empty[slot], ((u >> 1) & 1) ^ 1);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            ptx::tmem_ld32(t_row + (uint32_t)(jj * 64 + half * 32), r);
+            ptx::tmem_ld_wait();
+            const int col = grp * 256 + jj * 64 + half * 32;
+            const float4* g4 = reinterpret_cast<const float4*>(args.ln_g + col);
+            const float4* be4 = reinterpret_cast<const float4*>(args.ln_b + col);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 g0 = __ldg(g4 + 2 * c), g1 = __ldg(g4 + 2 * c + 1), b0 = __ldg(be4 + 2 * c), b1 = __ldg(be4 + 2 * c + 1);
+              uint4 o;
+              o.x = D::pack2(fmaf((__uint_as_float(r[8 * c + 0]) - mean) * rstd, g0.x, b0.x), fmaf((__uint_as_float(r[8 * c + 1]) - mean) * rstd, g0.y, b0.y));
+              o.y = D::pack2(fmaf((__uint_as_float(r[8 * c + 2]) - mean) * rstd, g0.z, b0.z), fmaf((__uint_as_float(r[8 * c + 3]) - mean) * rstd, g0.w, b0.w));
+              o.z = D::pack2(fmaf((__uint_as_float(r[8 * c + 4]) - mean) * rstd, g1.x, b1.x), fmaf((__uint_as_float(r[8 * c + 5]) - mean) * rstd, g1.y, b1.y));
+              o.w = D::pack2(fmaf((__uint_as_float(r[8 * c + 6]) - mean) * rstd, g1.z, b1.z), fmaf((__uint_as_float(r[8 * c + 7]) - mean) * rstd, g1.w, b1.w));
+              *reinterpret_cast<uint4*>(srow + (((uint32_t)(half * 4 + c) ^ sw) << 4)) = o;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            ptx::tma_store_2d(&tm_h, slot_base + slot * kBoxBytes, grp * 256 + jj * 64, row0);
+            after_store(slot);
+          }
+        }
+      }
+      // ---- end of tile: the last store's slot must be free before the loader refills it, TMEM is drained
+      if (elected && pending >= 0) {
+        ptx::bulk_wait_read<0>();
+        ptx::mbar_arrive(&bars.slot_empty[pending]);
+        pending = -1;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&bars.tmem_empty[0]), 0));
+      acc_phase ^= 1;
+    }
+    if (elected) ptx::bulk_wait<0>();
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
+constexpr int kPairLnSmem = 1024 + 3 * (kABytes + 2 * kWHalfBytes) + kSlots * kBoxBytes + 512 + 2 * kBM * 8;
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(MP_ELAUNCH, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  return MP_OK;
+}
+
+int pair_grid(int tiles) {
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  return 2 * pairs;
+}
+
+}  // namespace
+
+// Y = act(A W^T + b) on CTA pairs; called by mp_linear for N % 256 == 0 non-residual epilogues.
+int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream) {
+  CUtensorMap ta, tw, ty;
+  MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
+  MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
+  MP_CHECK(get_tmap(&ty, Y, M, N, kBM, dtype));
+  const int tiles = (N / 256) * ((M + 255) / 256);
+  const int grid = pair_grid(tiles);
+  auto launch = [&](auto kernel) -> int {
+    MP_CHECK(set_smem(kernel, kPairLinearSmem));
+    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K);
+    return check_launch("pair_linear_kernel");
+  };
+  const bool bf = dtype == MP_DTYPE_BF16;
+  if (epilogue == MP_EPI_GELU) return bf ? launch(pair_linear_kernel<MP_EPI_GELU, Bf16>) : launch(pair_linear_kernel<MP_EPI_GELU, Fp16>);
+  return bf ? launch(pair_linear_kernel<MP_EPI_BIAS, Bf16>) : launch(pair_linear_kernel<MP_EPI_BIAS, Fp16>);
+}
+
+}  // namespace mp
+
+extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, const float* resid, float* x_out, void* h_out,
+                            const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
+                            int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, int64_t M, int64_t N, int64_t K,
+                            int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(A && W && bias && resid && x_out, MP_EINVAL, "mp_linear_ln: null pointer");
+  MP_REQUIRE(N == 512, MP_EUNSUPPORTED, "mp_linear_ln: N=%lld (the fused residual + LayerNorm epilogue is built for N = 512 rows)", (long long)N);
+  MP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && K >= 64 && K % 64 == 0, MP_EINVAL, "mp_linear_ln: unsupported shape M=%lld K=%lld", (long long)M, (long long)K);
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_linear_ln: unknown dtype %d", dtype);
+  MP_REQUIRE((post_gamma == nullptr) == (post_beta == nullptr) && (ln_gamma == nullptr) == (ln_beta == nullptr), MP_EINVAL,
+             "mp_linear_ln: gamma/beta go together");
+  MP_REQUIRE(!ln_gamma || h_out, MP_EINVAL, "mp_linear_ln: h_out required with the pre-norm");
+  MP_REQUIRE(!pos_embed || (post_gamma && pos_div >= 1 && pos_mod >= 1), MP_EINVAL, "mp_linear_ln: pos_embed needs the post-norm and pos_div/pos_mod >= 1");
+  MP_REQUIRE(aligned16(A) && aligned16(W) && aligned16(bias) && aligned16(resid) && aligned16(x_out) && aligned16(h_out) &&
+                 aligned16(post_gamma) && aligned16(post_beta) && aligned16(ln_gamma) && aligned16(ln_beta) && aligned16(pos_embed),
+             MP_EALIGN, "mp_linear_ln: pointers must be 16-byte aligned");
+  if (M == 0) return MP_OK;
+  CUtensorMap ta, tw, tr, tx, th;
+  MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
+  MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
+  MP_CHECK(get_tmap(&tr, resid, M, N, kBM, 2));
+  MP_CHECK(get_tmap(&tx, x_out, M, N, kBM, 2));
+  if (ln_gamma)
+    MP_CHECK(get_tmap(&th, h_out, M, N, kBM, dtype));
+  else
+    th = tx;
+  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
+  const int tiles = (int)((M + 255) / 256);
+  const int grid = pair_grid(tiles);
+  auto launch = [&](auto kernel) -> int {
+    MP_CHECK(set_smem(kernel, kPairLnSmem));
+    kernel<<<grid, kThreads, kPairLnSmem, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, args, (int)M, (int)K);
+    return check_launch("pair_linear_ln_kernel");
+  };
+  return dtype == MP_DTYPE_BF16 ? launch(pair_linear_ln_kernel<Bf16>) : launch(pair_linear_ln_kernel<Fp16>);
+}

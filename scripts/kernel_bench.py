@@ -51,6 +51,17 @@ def main():
             out[f"gemm_{name}_M{m}" + ("" if fl else "_warmL2")] = {"ms": med, "best_ms": best, "tflops": fl_ops / med / 1e9, "gbs": byt / med / 1e6}
         t_ref, _ = timeit(lambda: torch.matmul(a, w.t()), flush_l2=True)
         out[f"cublas_{name}_M{m}"] = {"ms": t_ref, "tflops": 2.0 * m * n * k / t_ref / 1e9}
+    for name, k in (("proj+ln2", 512), ("fc2+post+ln1", 1024)):
+        a = torch.randn(m, k, generator=g, device=dev).bfloat16()
+        w = (torch.randn(512, k, generator=g, device=dev) / math.sqrt(k)).bfloat16()
+        b = torch.randn(512, generator=g, device=dev)
+        xx = torch.randn(m, 512, generator=g, device=dev)
+        hh = torch.empty(m, 512, dtype=torch.bfloat16, device=dev)
+        pp = [torch.randn(512, generator=g, device=dev) for _ in range(4)]
+        post = (pp[0], pp[1]) if k == 1024 else None
+        med, best = timeit(lambda: ops.linear_ln(a, w, b, xx, xx, hh, post=post, ln=(pp[2], pp[3])))
+        byt = (m * k + 512 * k) * 2 + m * 512 * (8 + 2)
+        out[f"fused_{name}_M{m}"] = {"ms": med, "best_ms": best, "tflops": 2.0 * m * 512 * k / med / 1e9, "gbs": byt / med / 1e6}
     qkv = torch.randn(m, 1536, generator=g, device=dev).bfloat16()
     o = torch.empty(m, 512, dtype=torch.bfloat16, device=dev)
     for mode, nm in ((1, "temporal"), (0, "spatial")):

@@ -77,6 +77,42 @@ def test_linear_is_deterministic_and_persistent_over_many_tiles():
     torch.testing.assert_close(x, want, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("m,k", [(4131, 512), (1000, 1024), (256, 512), (255, 512), (257, 1024), (1, 512), (66096, 512)])
+@pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln"])
+def test_linear_ln_fused_epilogue(m, k, mode, dtype):
+    """mp_linear_ln (CTA pairs, residual add + LayerNorms in the epilogue) vs fp32 torch on the same 16-bit operands."""
+    from manipose_b200 import ops
+    td = DT[dtype]
+    n, n_tok, n_frames = 512, 17, 27
+    gen = torch.Generator(device="cuda").manual_seed(m + k)
+    a = torch.randn(m, k, generator=gen, device="cuda").to(td)
+    w = (torch.randn(n, k, generator=gen, device="cuda") / math.sqrt(k)).to(td)
+    bias = torch.randn(n, generator=gen, device="cuda")
+    resid = torch.randn(m, n, generator=gen, device="cuda") * 1.5 + 0.3
+    pg, pb, lg, lb = (torch.randn(n, generator=gen, device="cuda") for _ in range(4))
+    pos = torch.randn(n_frames, n, generator=gen, device="cuda")
+    x_ref = resid + a.float() @ w.float().t() + bias
+    post = (pg, pb) if mode.startswith("post") else None
+    use_pos = mode == "post_pos_ln"
+    ln = (lg, lb) if mode != "plain" else None
+    if post is not None:
+        x_ref = F.layer_norm(x_ref, (n,), pg, pb, 1e-6)
+        if use_pos:
+            rows = torch.arange(m, device="cuda")
+            x_ref = x_ref + pos[(rows // n_tok) % n_frames]
+    h_ref = F.layer_norm(x_ref, (n,), lg, lb, 1e-6) if ln is not None else None
+    x = resid.clone()
+    h = torch.full((m, n), float("nan"), dtype=td, device="cuda") if ln is not None else None
+    ops.linear_ln(a, w, bias, x, x, h, post=post, post_eps=1e-6, pos=pos if use_pos else None, pos_div=n_tok, pos_mod=n_frames, ln=ln,
+                  ln_eps=1e-6)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(x, x_ref, rtol=2e-4, atol=2e-4)
+    if ln is not None:
+        assert not torch.isnan(h.float()).any()
+        torch.testing.assert_close(h.float(), h_ref, rtol=RTOL[dtype], atol=RTOL[dtype])
+
+
 def _attn_ref(qkv, n_clips, n_frames, n_tok, c, heads, temporal):
     hd = c // heads
     x = qkv.float().reshape(n_clips, n_frames, n_tok, 3, heads, hd)
