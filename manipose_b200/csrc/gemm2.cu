@@ -370,14 +370,23 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   } else if (warp == 2) {
     if (lane == 0) {
       // ===================== residual loader =====================
-      // Per tile and column half g, the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h boxes.
-      // Use u of half g lives in slot g + 2 (u & 1); every tile contributes an even number of uses per slot, so parities restart.
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      // Per tile and column half g, the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h boxes;
+      // use u of half g lives in slot g + 2 (u & 1) and completes one phase of slot_empty[slot] when the slot is free again.
+      // The loader only fills the first 8 uses of a tile but must observe EVERY phase in order (a parity wait is only meaningful
+      // for the very next phase), so it counts the completions it has seen per slot.
+      const uint32_t uses_per_slot = (8u + (has_post ? 8u : 0u) + (has_ln ? 4u : 0u)) / 2u;
+      uint32_t seen[kSlots] = {0, 0, 0, 0};
+      uint32_t tt = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tt) {
         const int row0 = tile * 2 * kBM + (int)rank * kBM;
         for (int j = 0; j < 8; ++j) {
           for (int g = 0; g < 2; ++g) {
             const uint32_t slot = (uint32_t)g + 2 * (j & 1);
-            ptx::mbar_wait(&bars.slot_empty[slot], ((j >> 1) & 1) ^ 1);
+            const uint32_t need = tt * uses_per_slot + (uint32_t)(j >> 1);   // completed uses of this slot before it may be refilled
+            while (seen[slot] < need) {
+              ptx::mbar_wait(&bars.slot_empty[slot], seen[slot] & 1);
+              ++seen[slot];
+            }
             ptx::mbar_expect_tx(&bars.slot_full[slot], kBoxBytes);
             ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], g * 256 + j * 32, row0);
           }
