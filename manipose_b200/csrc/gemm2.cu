@@ -42,6 +42,7 @@ struct PairBars {
   uint64_t* tmem_empty;  // [2]       leader: accumulator drained by the 16 epilogue warps of the pair
   uint64_t* slot_full;   // [kSlots]  residual box landed
   uint64_t* slot_empty;  // [kSlots]  slot free again
+  uint64_t* tile_done;   // [1]       both column halves have finished a tile's epilogue (every slot is free)
 };
 
 template <int kStages>
@@ -53,6 +54,7 @@ __device__ __forceinline__ PairBars carve_bars(uint8_t* p) {
   b.tmem_empty = b.tmem_full + 2;
   b.slot_full = b.tmem_empty + 2;
   b.slot_empty = b.slot_full + kSlots;
+  b.tile_done = b.slot_empty + kSlots;
   return b;
 }
 
@@ -70,6 +72,7 @@ __device__ __forceinline__ void init_bars(const PairBars& b) {
     ptx::mbar_init(&b.slot_full[s], 1);
     ptx::mbar_init(&b.slot_empty[s], 1);
   }
+  ptx::mbar_init(b.tile_done, 2);
   ptx::fence_mbar_init();
 }
 
@@ -88,7 +91,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint8_t* stage_base = smem;
   uint8_t* slot_base = smem + kStages * kStageBytes;
   const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.slot_empty + kSlots);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.tile_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -285,7 +288,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   uint8_t* stage_base = smem;
   uint8_t* slot_base = smem + kStages * kStageBytes;
   const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.slot_empty + kSlots);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.tile_done + 1);
   float2* sx = reinterpret_cast<float2*>(tmem_holder + 4);           // [2][128] row statistics exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -371,22 +374,18 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     if (lane == 0) {
       // ===================== residual loader =====================
       // Per tile and column half g, the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h boxes;
-      // use u of half g lives in slot g + 2 (u & 1) and completes one phase of slot_empty[slot] when the slot is free again.
-      // The loader only fills the first 8 uses of a tile but must observe EVERY phase in order (a parity wait is only meaningful
-      // for the very next phase), so it counts the completions it has seen per slot.
-      const uint32_t uses_per_slot = (8u + (has_post ? 8u : 0u) + (has_ln ? 4u : 0u)) / 2u;
-      uint32_t seen[kSlots] = {0, 0, 0, 0};
+      // use u of half g lives in slot g + 2 (u & 1) and completes one phase of slot_empty[slot] when the slot is free again (an even
+      // number of phases per slot and tile, so parities restart with every tile).  A parity wait is only meaningful for the very
+      // next phase, and the loader does not take part in the store-only uses: within a tile it follows slot_empty in lockstep
+      // (uses 2..7), across tiles it waits for `tile_done`, which both halves arrive on after their last store has been read.
       uint32_t tt = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tt) {
         const int row0 = tile * 2 * kBM + (int)rank * kBM;
+        if (tt > 0) ptx::mbar_wait(bars.tile_done, (tt - 1) & 1);
         for (int j = 0; j < 8; ++j) {
           for (int g = 0; g < 2; ++g) {
             const uint32_t slot = (uint32_t)g + 2 * (j & 1);
-            const uint32_t need = tt * uses_per_slot + (uint32_t)(j >> 1);   // completed uses of this slot before it may be refilled
-            while (seen[slot] < need) {
-              ptx::mbar_wait(&bars.slot_empty[slot], seen[slot] & 1);
-              ++seen[slot];
-            }
+            if (j >= 2) ptx::mbar_wait(&bars.slot_empty[slot], ((j >> 1) & 1) ^ 1);
             ptx::mbar_expect_tx(&bars.slot_full[slot], kBoxBytes);
             ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], g * 256 + j * 32, row0);
           }
@@ -563,10 +562,13 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
       }
       // ---- end of tile: the last store's slot must be free before the loader refills it, TMEM is drained
-      if (elected && pending >= 0) {
-        ptx::bulk_wait_read<0>();
-        ptx::mbar_arrive(&bars.slot_empty[pending]);
-        pending = -1;
+      if (elected) {
+        if (pending >= 0) {
+          ptx::bulk_wait_read<0>();
+          ptx::mbar_arrive(&bars.slot_empty[pending]);
+          pending = -1;
+        }
+        ptx::mbar_arrive(bars.tile_done);
       }
       ptx::tc_fence_before();
       __syncwarp();
