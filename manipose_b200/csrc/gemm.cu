@@ -45,14 +45,13 @@ struct GemmCfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kSlots * kBoxBytes + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int BN, int EPI, typename D>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K) {
+              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K, int dbg) {
   using Cfg = GemmCfg<BN>;
   constexpr bool kRes = (EPI == MP_EPI_RESIDUAL);
   constexpr int kBoxCols = kRes ? 32 : 64;                 // fp32 vs 16-bit output: 128 bytes per row either way
@@ -149,7 +148,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (!(dbg & 2)) ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[stage]);                   // frees the stage when these MMAs have read it
           if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -195,6 +194,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int b = grp; b < kBoxes; b += 2, ++i) {
+        if (!kRes && (dbg & 1)) continue;        // measurement knob: drain nothing
         const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
         const int col0 = n_blk * BN + b * kBoxCols;
@@ -220,11 +220,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             *p = v;
           }
         } else {
+          uint32_t r0[32], r1[32];               // both 32-column halves of the box in flight before one wait
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + 32), r1);
+          ptx::tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + half * 32), r);
-            ptx::tmem_ld_wait();
+            const uint32_t(&r)[32] = half == 0 ? r0 : r1;
             const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -353,7 +355,8 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMa
   }
   const int tiles = (N / BN) * ((M + kBM - 1) / kBM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K);
+  static const int dbg = getenv("MANIPOSE_DBG") ? atoi(getenv("MANIPOSE_DBG")) : 0;
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K, dbg);
   return check_launch("linear_kernel");
 }
 

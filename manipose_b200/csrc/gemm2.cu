@@ -14,6 +14,8 @@
 // box loader, warps 4-11 epilogue (TMEM lane quadrant = warp % 4; column half / alternate boxes = (warp - 4) / 4).  Barriers that the
 // leader's MMA thread waits on (`full`, `tmem_empty`) live in the leader CTA and are arrived on remotely by the peer; barriers the
 // MMA thread signals (`empty`, `tmem_full`) are multicast tcgen05.commit arrivals into both CTAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,11 +34,10 @@ constexpr int kBoxBytes = kBM * 128;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kWHalfBytes = 128 * kBK * 2;    // 16 KB: the 128 weight rows this CTA contributes to one N = 256 instruction
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct PairBars {
-  uint64_t* full;        // [stages]  leader: operands of both CTAs landed (count 2 + tx bytes)
+  uint64_t* full;        // [stages]  leader: operands of both CTAs landed (one arrival that expects the bytes of BOTH CTAs)
   uint64_t* empty;       // [stages]  each CTA: stage consumed (multicast commit)
   uint64_t* tmem_full;   // [2]       each CTA: accumulator complete (multicast commit)
   uint64_t* tmem_empty;  // [2]       leader: accumulator drained by the 16 epilogue warps of the pair
@@ -61,7 +62,7 @@ __device__ __forceinline__ PairBars carve_bars(uint8_t* p) {
 template <int kStages>
 __device__ __forceinline__ void init_bars(const PairBars& b) {
   for (int s = 0; s < kStages; ++s) {
-    ptx::mbar_init(&b.full[s], 2);
+    ptx::mbar_init(&b.full[s], 1);
     ptx::mbar_init(&b.empty[s], 1);
   }
   for (int a = 0; a < 2; ++a) {
@@ -80,7 +81,7 @@ __device__ __forceinline__ void init_bars(const PairBars& b) {
 template <int EPI, typename D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-                   const float* __restrict__ bias, int M, int N, int K) {
+                   const float* __restrict__ bias, int M, int N, int K, int dbg) {
   constexpr int kStages = 5;
   constexpr int kStageBytes = kABytes + kWHalfBytes;     // 32 KB per CTA per stage
   constexpr int BN = 256;
@@ -130,7 +131,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * kStageBytes;
           const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
-          ptx::mbar_expect_tx_cluster(full_leader, kStageBytes);
+          if (leader) ptx::mbar_expect_tx(&bars.full[stage], 2 * kStageBytes);   // the peer's loads complete_tx on this barrier too
           ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
           ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, row_w);
           if (++stage == kStages) {
@@ -159,7 +160,8 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint64_t da = ptx::umma_desc_sw128(sa);
           const uint64_t db = ptx::umma_desc_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k)
+            if (!(dbg & 2)) ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           ptx::umma_commit_pair(&bars.empty[stage]);
           if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[acc]);
           if (++stage == kStages) {
@@ -191,15 +193,18 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int b = grp; b < kBoxes; b += 2, ++i) {
+        if (dbg & 1) continue;                   // measurement knob: drain nothing
         const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
         const int col0 = n_blk * BN + b * 64;
         ptx::mbar_wait(&bars.slot_empty[slot], (use & 1) ^ 1);
+        uint32_t r0[32], r1[32];               // both 32-column halves of the box in flight before one wait
+        ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
+        ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + 32), r1);
+        ptx::tmem_ld_wait();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + half * 32), r);
-          ptx::tmem_ld_wait();
+          const uint32_t(&r)[32] = half == 0 ? r0 : r1;
           const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -327,7 +332,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * kStageBytes;
           const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
-          ptx::mbar_expect_tx_cluster(full_leader, kStageBytes);
+          if (leader) ptx::mbar_expect_tx(&bars.full[stage], 2 * kStageBytes);   // the peer's loads complete_tx on this barrier too
           ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
           ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, (int)rank * 128);                      // W rows of columns [0, 256)
           ptx::tma_load_2d_pair(sa + kABytes + kWHalfBytes, &tm_w, full_leader, kb * kBK, 256 + (int)rank * 128);  // columns [256, 512)
@@ -615,7 +620,8 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
   const int grid = pair_grid(tiles);
   auto launch = [&](auto kernel) -> int {
     MP_CHECK(set_smem(kernel, kPairLinearSmem));
-    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K);
+    static const int dbg = getenv("MANIPOSE_DBG") ? atoi(getenv("MANIPOSE_DBG")) : 0;
+    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K, dbg);
     return check_launch("pair_linear_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
