@@ -190,61 +190,77 @@ attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ ou
 }
 
 // ------------------------------------------------------------------------------------------------------ spatial
-// One CTA per frame, one warp per head.  The frame's [n_tok, 3C] block is contiguous in global memory.
+// Work item = one (frame, head): n_tok rows of q, k and v, 2 * HD bytes each.  Every WARP streams its own items through a
+// private double buffer (cp.async for item i+1 in flight while item i is computed), so there is no block-level barrier and
+// the 8 warps of a CTA keep ~50 KB of loads in flight per SM.  The output tile is transposed through the dead q rows.
+constexpr int kSWarps = 8;
+
 template <int HD, typename D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSWarps * 32)
 attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int64_t n_seq, int n_tok, int C, int n_heads) {
+  constexpr int LD = HD * 2 + 16;           // padded row bytes
+  constexpr int CH = HD / 8;                // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem[];
-  const int LD = 3 * C * 2 + 16;            // padded row bytes; row n_tok is an all-zero row for padded tokens
-  const int CH = 3 * C / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int buf_bytes = 3 * n_tok * LD;
+  uint8_t* wbase = smem + (size_t)warp * (2 * buf_bytes + LD);
+  uint8_t* zero_row = wbase + 2 * buf_bytes;
+  for (int i = lane; i < LD / 16; i += 32) *reinterpret_cast<uint4*>(zero_row + i * 16) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+
   const float scale_log2 = rsqrtf((float)HD) * kLog2e;
-
-  for (int i = threadIdx.x; i < LD / 16; i += blockDim.x) *reinterpret_cast<uint4*>(smem + (size_t)n_tok * LD + i * 16) = make_uint4(0, 0, 0, 0);
-
-  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
-    const uint16_t* src = qkv + (size_t)seq * n_tok * 3 * C;
-    __syncthreads();   // previous iteration's readers are done
-    for (int i = threadIdx.x; i < n_tok * CH; i += blockDim.x) {
-      const int r = i / CH, ch = i - r * CH;
-      ptx::cp_async16(smem + (size_t)r * LD + ch * 16, src + (size_t)r * 3 * C + ch * 8);
+  const int64_t n_items = n_seq * n_heads;
+  const int64_t stride = (int64_t)gridDim.x * kSWarps;
+  const int chunks = 3 * n_tok * CH;
+  auto row_ptr = [=](const uint8_t* b, int r) { return r < n_tok ? b + (size_t)r * LD : (const uint8_t*)zero_row; };
+  auto issue = [&](int64_t item, uint8_t* buf) {
+    const int64_t seq = item / n_heads;
+    const int head = (int)(item - seq * n_heads);
+    const uint16_t* src = qkv + (size_t)seq * n_tok * 3 * C + head * HD;
+    for (int i = lane; i < chunks; i += 32) {
+      const int ch = i % CH, r = (i / CH) % n_tok, sel = i / (CH * n_tok);
+      ptx::cp_async16(buf + (size_t)(sel * n_tok + r) * LD + ch * 16, src + (size_t)r * 3 * C + sel * C + ch * 8);
     }
     ptx::cp_async_commit();
-    ptx::cp_async_wait<0>();
-    __syncthreads();
+  };
 
-    if (warp < n_heads) {
-      const int head = warp;
-      const uint8_t* qb = smem + (size_t)head * HD * 2;
-      const uint8_t* kb = qb + (size_t)C * 2;
-      const uint8_t* vb = kb + (size_t)C * 2;
-      const uint8_t* zero_row = smem + (size_t)n_tok * LD;
-      // rows past n_tok read the zero row (the column offset still lands inside it)
-      auto row_ptr = [=](const uint8_t* b, int r) { return r < n_tok ? b + (size_t)r * LD : zero_row + (b - smem) % LD; };
-      for (int mt = 0; mt * 16 < n_tok; ++mt) {
-        float o[HD / 8][4], l[2];
-        attend_tile<HD, D>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
-        const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
-        __syncwarp();
-        // the q columns of this head and these rows are only ever read by this warp: overwrite them with the output
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
-        uint8_t* w0 = smem + (size_t)r0 * LD + (size_t)head * HD * 2;
-        uint8_t* w1 = smem + (size_t)r1 * LD + (size_t)head * HD * 2;
+  int64_t item = (int64_t)blockIdx.x * kSWarps + warp;
+  int cur = 0;
+  if (item < n_items) issue(item, wbase);
+  for (; item < n_items; item += stride, cur ^= 1) {
+    uint8_t* buf = wbase + cur * buf_bytes;
+    if (item + stride < n_items) {
+      issue(item + stride, wbase + (cur ^ 1) * buf_bytes);
+      ptx::cp_async_wait<1>();
+    } else {
+      ptx::cp_async_wait<0>();
+    }
+    __syncwarp();
+    const uint8_t* qb = buf;
+    const uint8_t* kb = buf + (size_t)n_tok * LD;
+    const uint8_t* vb = kb + (size_t)n_tok * LD;
+    for (int mt = 0; mt * 16 < n_tok; ++mt) {
+      float o[HD / 8][4], l[2];
+      attend_tile<HD, D>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
+      const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+      __syncwarp();                          // all lanes hold their q fragments of this tile: its rows may be overwritten
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
-          if (r0 < n_tok) *reinterpret_cast<uint32_t*>(w0 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][0] * inv0, o[i][1] * inv0);
-          if (r1 < n_tok) *reinterpret_cast<uint32_t*>(w1 + (i * 8 + 2 * t) * 2) = D::pack2(o[i][2] * inv1, o[i][3] * inv1);
-        }
+      for (int i = 0; i < HD / 8; ++i) {
+        if (r0 < n_tok) *reinterpret_cast<uint32_t*>(buf + (size_t)r0 * LD + (i * 8 + 2 * t) * 2) = D::pack2(o[i][0] * inv0, o[i][1] * inv0);
+        if (r1 < n_tok) *reinterpret_cast<uint32_t*>(buf + (size_t)r1 * LD + (i * 8 + 2 * t) * 2) = D::pack2(o[i][2] * inv1, o[i][3] * inv1);
       }
     }
-    __syncthreads();
-    uint16_t* dst = out + (size_t)seq * n_tok * C;
-    const int OCH = C / 8;
-    for (int i = threadIdx.x; i < n_tok * OCH; i += blockDim.x) {
-      const int r = i / OCH, ch = i - r * OCH;
-      *reinterpret_cast<uint4*>(dst + (size_t)r * C + ch * 8) = *reinterpret_cast<const uint4*>(smem + (size_t)r * LD + ch * 16);
+    __syncwarp();
+    const int64_t seq = item / n_heads;
+    const int head = (int)(item - seq * n_heads);
+    uint16_t* dst = out + (size_t)seq * n_tok * C + head * HD;
+    for (int i = lane; i < n_tok * CH; i += 32) {
+      const int r = i / CH, ch = i - r * CH;
+      *reinterpret_cast<uint4*>(dst + (size_t)r * C + ch * 8) = *reinterpret_cast<const uint4*>(buf + (size_t)r * LD + ch * 16);
     }
+    __syncwarp();                            // the buffer is refilled by the load issued in the next iteration
   }
 }
 
@@ -287,14 +303,17 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   }
   MP_REQUIRE(mode == MP_ATTN_SPATIAL, MP_EINVAL, "mp_attention: unknown mode %d", mode);
   MP_REQUIRE(n_tok <= 32, MP_EUNSUPPORTED, "mp_attention: spatial sequences longer than 32 tokens are not built (got %d)", n_tok);
-  const size_t smem = (size_t)(n_tok + 1) * (3 * C * 2 + 16);
+  const size_t smem = (size_t)kSWarps * ((size_t)2 * 3 * n_tok + 1) * (hd * 2 + 16);
+  MP_REQUIRE(smem <= 227 * 1024, MP_EUNSUPPORTED, "mp_attention: %d spatial tokens need %zu bytes of shared memory", n_tok, smem);
   const int64_t n_seq = n_clips * n_frames;
-  const int per_sm = (int)(200 * 1024 / (smem + 1024));
-  int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
-  if (grid > n_seq) grid = n_seq;
+  const int64_t n_items = n_seq * n_heads;
+  int per_sm = (int)(220 * 1024 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > (n_items + kSWarps - 1) / kSWarps) grid = (n_items + kSWarps - 1) / kSWarps;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)grid, 256, smem, s>>>(in, o, n_seq, n_tok, C, n_heads);
+    kernel<<<(unsigned)grid, kSWarps * 32, smem, s>>>(in, o, n_seq, n_tok, C, n_heads);
   };
   if (hd == 64) {
     if (bf) launch(attn_spatial_kernel<64, Bf16>); else launch(attn_spatial_kernel<64, Fp16>);

@@ -238,8 +238,28 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
 
 // -------------------------------------------------------------------------------------------------- hypothesis heads
 // LN_k(x) W_k^T + b_k = rstd * (x . (g_k*W_k) - mean * sum(g_k*W_k)) + (W_k beta_k + b_k): the K LayerNorms share the
-// token statistics, so the K heads are ONE [512 x K*O] projection with folded weights held in shared memory.
+// token statistics, so the K heads are ONE [512 x K*O] fp32 projection with folded weights held in shared memory.
+// A warp walks the 17 tokens of a frame four at a time: every folded-weight float4 read from shared memory feeds 16 FMAs
+// (4 tokens x 4 channels), and the 4 x O partial sums of a head are reduced across the 32 lanes with one transposing
+// butterfly (31 shuffles for up to 32 values) that leaves value i in lane i.
 constexpr int kHeadC = 512;
+constexpr int kHeadTok = 4;
+
+// allreduce-free reduction of 32 per-lane values: afterwards lane l holds sum over lanes of vals[l]
+__device__ __forceinline__ float transpose_reduce32(float (&vals)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? vals[i] : vals[i + step];
+      const float keep = up ? vals[i + step] : vals[i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return vals[0];
+}
+
 __global__ void __launch_bounds__(kTokWarps * 32)
 heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
                  const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
@@ -247,12 +267,11 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
                  int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
   using R = Row<kHeadC>;
   extern __shared__ __align__(16) float sm[];
-  const int O = out_dim + (with_score ? 1 : 0);  // outputs per head
+  const int O = out_dim + (with_score ? 1 : 0);  // outputs per head (<= 7, so 4 tokens x O <= 28 values per butterfly)
   const int KO = n_hyp * O;
-  float* wf = sm;                        // [KO][512] folded weights g_k[c] * W_k[o][c]
+  float* wf = sm;                          // [KO][512] folded weights g_k[c] * W_k[o][c]
   float* csum = wf + (size_t)KO * kHeadC;  // [KO] sum_c wf
-  float* dconst = csum + KO;             // [KO] W_k beta_k + b_k
-  float* stage = dconst + KO;            // [warps][n_hyp][17*out_dim] rot staging
+  float* dconst = csum + KO;               // [KO] W_k beta_k + b_k
 
   for (int i = threadIdx.x; i < KO * kHeadC; i += blockDim.x) {
     const int c = i % kHeadC, ko = i / kHeadC, k = ko / O;
@@ -276,8 +295,6 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rot_per_pose = kJ * out_dim;
-  float* my_stage = stage + (size_t)warp * n_hyp * rot_per_pose;
   float pg[R::kPer], pb[R::kPer];
   R::load_f32(post_g, lane, pg);
   R::load_f32(post_b, lane, pb);
@@ -285,48 +302,76 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
   for (int64_t fr = (int64_t)blockIdx.x * kTokWarps + warp; fr < total_frames; fr += (int64_t)gridDim.x * kTokWarps) {
     const int64_t b = fr / n_frames;
     const int t = (int)(fr - b * n_frames);
-    float logit_acc = 0.f;  // lane k (< n_hyp) accumulates its head's logit
-    for (int j = 0; j < kJ; ++j) {
-      float v[R::kPer];
-      R::load_x(x + (fr * kJ + j) * kHeadC, lane, v);
-      float mean, rstd;
-      R::stats(v, post_eps, mean, rstd);
-      R::normalize(v, mean, rstd, pg, pb);   // Temporal_norm (eps 1e-6), kept in fp32
-      R::stats(v, 1e-5f, mean, rstd);        // shared statistics of the K head LayerNorms (eps 1e-5)
-      for (int ko = 0; ko < KO; ++ko) {
-        const float* wrow = wf + (size_t)ko * kHeadC;
-        float acc = 0.f;
+    float logit_acc = 0.f;                 // lane k (< n_hyp) accumulates its head's logit
+    for (int j0 = 0; j0 < kJ; j0 += kHeadTok) {
+      // ---- four tokens: Temporal_norm (eps 1e-6) in fp32, then the shared statistics of the K head LayerNorms (eps 1e-5)
+      float v[kHeadTok][R::kPer], mean[kHeadTok], rstd[kHeadTok];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 a = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8);
-          const float4 c4 = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8 + 4);
-          acc = fmaf(v[h * 8 + 0], a.x, acc);
-          acc = fmaf(v[h * 8 + 1], a.y, acc);
-          acc = fmaf(v[h * 8 + 2], a.z, acc);
-          acc = fmaf(v[h * 8 + 3], a.w, acc);
-          acc = fmaf(v[h * 8 + 4], c4.x, acc);
-          acc = fmaf(v[h * 8 + 5], c4.y, acc);
-          acc = fmaf(v[h * 8 + 6], c4.z, acc);
-          acc = fmaf(v[h * 8 + 7], c4.w, acc);
+      for (int q = 0; q < kHeadTok; ++q) {
+        const int j = j0 + q < kJ ? j0 + q : kJ - 1;         // the tail group re-reads joint 16; its results are discarded
+        R::load_x(x + (fr * kJ + j) * kHeadC, lane, v[q]);
+        float m, r;
+        R::stats(v[q], post_eps, m, r);
+        R::normalize(v[q], m, r, pg, pb);
+        R::stats(v[q], 1e-5f, mean[q], rstd[q]);
+      }
+      for (int k = 0; k < n_hyp; ++k) {
+        float vals[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) vals[i] = 0.f;
+#pragma unroll
+        for (int o = 0; o < 7; ++o) {
+          if (o < O) {
+            const float* wrow = wf + (size_t)(k * O + o) * kHeadC;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 a = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8);
+              const float4 c4 = *reinterpret_cast<const float4*>(wrow + h * 256 + lane * 8 + 4);
+#pragma unroll
+              for (int q = 0; q < kHeadTok; ++q) {
+                float acc = vals[q * 7 + o];
+                acc = fmaf(v[q][h * 8 + 0], a.x, acc);
+                acc = fmaf(v[q][h * 8 + 1], a.y, acc);
+                acc = fmaf(v[q][h * 8 + 2], a.z, acc);
+                acc = fmaf(v[q][h * 8 + 3], a.w, acc);
+                acc = fmaf(v[q][h * 8 + 4], c4.x, acc);
+                acc = fmaf(v[q][h * 8 + 5], c4.y, acc);
+                acc = fmaf(v[q][h * 8 + 6], c4.z, acc);
+                acc = fmaf(v[q][h * 8 + 7], c4.w, acc);
+                vals[q * 7 + o] = acc;
+              }
+            }
+          }
         }
-        acc = warp_sum(acc);
-        const float val = fmaf(rstd, acc - mean * csum[ko], dconst[ko]);
-        const int k = ko / O, o = ko - k * O;
-        if (o < out_dim) {
-          if (lane == 0) my_stage[k * rot_per_pose + j * out_dim + o] = val;
-        } else if (lane == k) {
-          logit_acc = fmaf(score_w[k * kJ + j], val, logit_acc);   // score_head: Linear(17 -> 1)
+        // value index q * 7 + o lands in lane q * 7 + o
+        const float total = transpose_reduce32(vals, lane);
+        const int q7 = lane / 7, o7 = lane - q7 * 7;
+        const int j = j0 + q7;
+        float contrib = 0.f;
+        if (q7 < kHeadTok && o7 < O && j < kJ) {
+          float mq = mean[0], rq = rstd[0];
+#pragma unroll
+          for (int q = 1; q < kHeadTok; ++q)
+            if (q7 == q) {
+              mq = mean[q];
+              rq = rstd[q];
+            }
+          const int ko = k * O + o7;
+          const float val = fmaf(rq, total - mq * csum[ko], dconst[ko]);
+          if (o7 < out_dim) {
+            rot[((((size_t)b * n_hyp + k) * n_frames + t) * kJ + j) * out_dim + o7] = val;
+          } else {
+            contrib = score_w[k * kJ + j] * val;               // score_head: Linear(17 -> 1)
+          }
+        }
+        if (with_score) {
+          const float s4 = __shfl_sync(0xffffffffu, contrib, out_dim) + __shfl_sync(0xffffffffu, contrib, 7 + out_dim) +
+                           __shfl_sync(0xffffffffu, contrib, 14 + out_dim) + __shfl_sync(0xffffffffu, contrib, 21 + out_dim);
+          if (lane == k) logit_acc += s4;
         }
       }
     }
-    __syncwarp();
-    // rot[b, k, t, :, :] is 17*out_dim contiguous floats per (b,k,t)
-    for (int k = 0; k < n_hyp; ++k) {
-      float* dst = rot + (((size_t)b * n_hyp + k) * n_frames + t) * rot_per_pose;
-      for (int i = lane; i < rot_per_pose; i += 32) dst[i] = my_stage[k * rot_per_pose + i];
-    }
     if (with_score && lane < n_hyp) logits[((size_t)b * n_hyp + lane) * n_frames + t] = logit_acc + score_b[lane];
-    __syncwarp();
   }
 }
 
@@ -465,7 +510,7 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
   MP_REQUIRE(aligned16(x), MP_EALIGN, "mp_heads_fwd: x must be 16-byte aligned");
   if (n_clips == 0) return MP_OK;
   const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
-  const size_t smem = ((size_t)KO * kHeadC + 2 * KO + (size_t)kTokWarps * n_hyp * kJ * out_dim) * sizeof(float);
+  const size_t smem = ((size_t)KO * kHeadC + 2 * KO) * sizeof(float);
   MP_REQUIRE(smem <= 227 * 1024, MP_EUNSUPPORTED, "mp_heads_fwd: n_hyp=%d needs %zu bytes of shared memory", n_hyp, smem);
   cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;

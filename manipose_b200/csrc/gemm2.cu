@@ -30,6 +30,8 @@ constexpr int kBK = 64;
 constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kSlots = 4;
+constexpr int kLnStages = 2;                  // pair_linear_ln_kernel: operand stages ...
+constexpr int kLnSlots = 8;                   // ... and box-ring slots (4 per column half)
 constexpr int kBoxBytes = kBM * 128;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kWHalfBytes = 128 * kBK * 2;    // 16 KB: the 128 weight rows this CTA contributes to one N = 256 instruction
@@ -46,7 +48,7 @@ struct PairBars {
   uint64_t* tile_done;   // [1]       both column halves have finished a tile's epilogue (every slot is free)
 };
 
-template <int kStages>
+template <int kStages, int kNumSlots>
 __device__ __forceinline__ PairBars carve_bars(uint8_t* p) {
   PairBars b;
   b.full = reinterpret_cast<uint64_t*>(p);
@@ -54,12 +56,12 @@ __device__ __forceinline__ PairBars carve_bars(uint8_t* p) {
   b.tmem_full = b.empty + kStages;
   b.tmem_empty = b.tmem_full + 2;
   b.slot_full = b.tmem_empty + 2;
-  b.slot_empty = b.slot_full + kSlots;
-  b.tile_done = b.slot_empty + kSlots;
+  b.slot_empty = b.slot_full + kNumSlots;
+  b.tile_done = b.slot_empty + kNumSlots;
   return b;
 }
 
-template <int kStages>
+template <int kStages, int kNumSlots>
 __device__ __forceinline__ void init_bars(const PairBars& b) {
   for (int s = 0; s < kStages; ++s) {
     ptx::mbar_init(&b.full[s], 1);
@@ -69,7 +71,7 @@ __device__ __forceinline__ void init_bars(const PairBars& b) {
     ptx::mbar_init(&b.tmem_full[a], 1);
     ptx::mbar_init(&b.tmem_empty[a], 2 * kEpiWarps);
   }
-  for (int s = 0; s < kSlots; ++s) {
+  for (int s = 0; s < kNumSlots; ++s) {
     ptx::mbar_init(&b.slot_full[s], 1);
     ptx::mbar_init(&b.slot_empty[s], 1);
   }
@@ -91,7 +93,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   uint8_t* slot_base = smem + kStages * kStageBytes;
-  const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
+  const PairBars bars = carve_bars<kStages, kSlots>(slot_base + kSlots * kBoxBytes);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.tile_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,7 +110,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     ptx::prefetch_tmap(&tm_w);
     ptx::prefetch_tmap(&tm_y);
   }
-  if (warp == 1 && lane == 0) init_bars<kStages>(bars);
+  if (warp == 1 && lane == 0) init_bars<kStages, kSlots>(bars);
   if (warp == 2) {
     ptx::tmem_alloc(tmem_holder, 512);
     ptx::tmem_relinquish();
@@ -284,15 +286,18 @@ template <typename D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
                       const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, LnArgs args, int M, int K) {
-  constexpr int kStages = 3;
+  // The K loop is short (8 or 16 k-blocks) and the epilogue moves 5 bytes per output element, so shared memory goes to the
+  // box ring (4 slots per column half keep ~128 KB of residual loads / output stores in flight per SM), not to operand stages.
+  constexpr int kStages = kLnStages;
   constexpr int kStageBytes = kABytes + 2 * kWHalfBytes;   // 48 KB: A + this CTA's share of both N = 256 halves
   constexpr int kN = 512;
+  constexpr int kGS = kLnSlots / 2;                        // slots per column half
 
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();             // 128-byte-swizzle tiles need the 1024-byte alignment the declaration asks for
   uint8_t* stage_base = smem;
   uint8_t* slot_base = smem + kStages * kStageBytes;
-  const PairBars bars = carve_bars<kStages>(slot_base + kSlots * kBoxBytes);
+  const PairBars bars = carve_bars<kStages, kLnSlots>(slot_base + kLnSlots * kBoxBytes);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars.tile_done + 1);
   float2* sx = reinterpret_cast<float2*>(tmem_holder + 4);           // [2][128] row statistics exchange
 
@@ -311,7 +316,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     ptx::prefetch_tmap(&tm_x);
     if (has_ln) ptx::prefetch_tmap(&tm_h);
   }
-  if (warp == 1 && lane == 0) init_bars<kStages>(bars);
+  if (warp == 1 && lane == 0) init_bars<kStages, kLnSlots>(bars);
   if (warp == 2) {
     ptx::tmem_alloc(tmem_holder, 512);
     ptx::tmem_relinquish();
@@ -378,19 +383,23 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   } else if (warp == 2) {
     if (lane == 0) {
       // ===================== residual loader =====================
-      // Per tile and column half g, the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h boxes;
-      // use u of half g lives in slot g + 2 (u & 1) and completes one phase of slot_empty[slot] when the slot is free again (an even
-      // number of phases per slot and tile, so parities restart with every tile).  A parity wait is only meaningful for the very
-      // next phase, and the loader does not take part in the store-only uses: within a tile it follows slot_empty in lockstep
-      // (uses 2..7), across tiles it waits for `tile_done`, which both halves arrive on after their last store has been read.
+      // Per tile and column half g the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h
+      // boxes.  Uses are numbered with a running counter n per half: use n lives in slot g * kGS + n % kGS and completes phase
+      // n / kGS of slot_empty[slot] when that slot is free again.  A parity wait only distinguishes "the previous phase" from
+      // "the one before", and the loader skips the store-only uses, so across tiles it waits for `tile_done` (both halves arrive
+      // after their last store has been read: every slot is free) and within a tile only for uses kGS.. (lockstep again).
+      const uint32_t uses = 8u + (has_post ? 8u : 0u) + (has_ln ? 4u : 0u);
       uint32_t tt = 0;
+      uint32_t full_par = 0;                     // parity bit of slot_full per slot (flips with every load into the slot)
+      (void)full_par;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tt) {
         const int row0 = tile * 2 * kBM + (int)rank * kBM;
         if (tt > 0) ptx::mbar_wait(bars.tile_done, (tt - 1) & 1);
         for (int j = 0; j < 8; ++j) {
+          const uint32_t n = tt * uses + (uint32_t)j;
           for (int g = 0; g < 2; ++g) {
-            const uint32_t slot = (uint32_t)g + 2 * (j & 1);
-            if (j >= 2) ptx::mbar_wait(&bars.slot_empty[slot], ((j >> 1) & 1) ^ 1);
+            const uint32_t slot = (uint32_t)(g * kGS) + n % kGS;
+            if (j >= kGS) ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
             ptx::mbar_expect_tx(&bars.slot_full[slot], kBoxBytes);
             ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], g * 256 + j * 32, row0);
           }
@@ -407,6 +416,8 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256);
     uint32_t acc_phase = 0;
     int pending = -1;                            // slot whose TMA store may still be reading shared memory
+    uint32_t n = 0;                              // running slot-use counter of this column half (see the loader)
+    uint32_t full_par = 0;                       // parity of the next slot_full phase, one bit per slot of this half
 
     // after a slot's content has been handed to a TMA store: recycle the PREVIOUS store's slot (its read is done by now)
     auto after_store = [&](uint32_t slot) {
@@ -423,15 +434,15 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const int grow = row0 + row;
       ptx::mbar_wait(&bars.tmem_full[0], acc_phase);
       ptx::tc_fence_after();
-      uint32_t u = 0;                            // slot-use index of this half within the tile
 
       // ---- pass A: v = acc + bias + resid; shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j, ++u) {
-        const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+      for (int j = 0; j < 8; ++j, ++n) {
+        const uint32_t ls = n % kGS, slot = (uint32_t)(grp * kGS) + ls;
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
-        ptx::mbar_wait(&bars.slot_full[slot], (j >> 1) & 1);
+        ptx::mbar_wait(&bars.slot_full[slot], (full_par >> ls) & 1);
+        full_par ^= 1u << ls;
         uint32_t r[32];
         ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
         ptx::tmem_ld_wait();
@@ -481,10 +492,10 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         s1 = 0.f;
         s2 = 0.f;
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j, ++u) {
-          const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+        for (int j = 0; j < 8; ++j, ++n) {
+          const uint32_t slot = (uint32_t)(grp * kGS) + n % kGS;
           uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
-          ptx::mbar_wait(&bars.slot_empty[slot], ((u >> 1) & 1) ^ 1);
+          ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
           uint32_t r[32];
           ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
           ptx::tmem_ld_wait();
@@ -535,10 +546,10 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       // ---- pass C (pre-norm): h = LN_pre(x) as 16-bit, 64-column boxes
       if (has_ln) {
 #pragma unroll 1
-        for (int jj = 0; jj < 4; ++jj, ++u) {
-          const uint32_t slot = (uint32_t)grp + 2 * (u & 1);
+        for (int jj = 0; jj < 4; ++jj, ++n) {
+          const uint32_t slot = (uint32_t)(grp * kGS) + n % kGS;
           uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
-          ptx::mbar_wait(&bars.slot_empty[slot], ((u >> 1) & 1) ^ 1);
+          ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
@@ -593,7 +604,8 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 }
 
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
-constexpr int kPairLnSmem = 1024 + 3 * (kABytes + 2 * kWHalfBytes) + kSlots * kBoxBytes + 512 + 2 * kBM * 8;
+constexpr int kPairLnSmem = kLnStages * (kABytes + 2 * kWHalfBytes) + kLnSlots * kBoxBytes + 256 + 2 * kBM * 8;
+static_assert(kPairLnSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
