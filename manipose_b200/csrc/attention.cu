@@ -24,26 +24,37 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// One 16-row query tile against keys [0, n_keys_pad) held in shared memory.
-//   q_rows: smem address of query row 0 of this tile (row stride `ld` bytes); k_rows / v_rows: key / value row 0.
-//   Rows are addressed through row_ptr(base, r) so callers can redirect padding rows to a zero row.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// One 16-row query tile against keys [0, n_keys_pad) held in shared memory with a constant row stride of LD bytes (rows
+// [n_keys, n_keys_pad) must be zero).  q_addr / k_addr / v_addr are shared-window addresses of row 0 of the tile / of key 0.
+// Every ldmatrix address is base + per-lane offset + compile-time constant.  Softmax runs in the exp2 domain on the RAW
+// scores (the scale is folded into one FMA per element); keys are masked only in the chunk that contains padding.
 // Result: o[HD/8][4] (unnormalised) and l[2] (row sums) in the mma C-fragment layout (rows g and g+8).
-template <int HD, typename D, typename RowPtr>
-__device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, const uint8_t* k_base, const uint8_t* v_base, int n_keys,
-                                            int n_keys_pad, float scale_log2, RowPtr row_ptr, int lane, float (&o)[HD / 8][4],
-                                            float (&l)[2]) {
+template <int HD, int LD, typename D>
+__device__ __forceinline__ void attend_tile(uint32_t q_addr, uint32_t k_addr, uint32_t v_addr, int n_keys, int n_keys_pad,
+                                            float scale_log2, int lane, float (&o)[HD / 8][4], float (&l)[2]) {
   constexpr int KS = HD / 16;   // k-steps over the head dimension
   constexpr int NT = HD / 8;    // output n-tiles
-  const int g = lane >> 2, t = lane & 3;
+  const int t = lane & 3;
+  // per-lane offsets of the three ldmatrix address patterns
+  const uint32_t q_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 16);   // A: {r0-7,klo},{r8-15,klo},{r0-7,khi},{r8-15,khi}
+  const uint32_t k_off = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * LD + ((lane >> 3) & 1) * 16);   // B: {n0-7,klo},{n0-7,khi},{n8-15,klo},{n8-15,khi}
+  const uint32_t v_off = q_off;                                                                       // B^T via .trans: same pattern as A
 
   uint32_t qf[KS][4];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    // A fragment (16 x 16): matrices {rows 0-7, k lo}, {rows 8-15, k lo}, {rows 0-7, k hi}, {rows 8-15, k hi}
-    const int r = q_row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int kc = ks * 16 + (lane >> 4) * 8;
-    ptx::ldmatrix_x4(qf[ks], row_ptr(q_base, r) + kc * 2);
-  }
+  for (int ks = 0; ks < KS; ++ks) ldsm_x4(qf[ks], q_addr + q_off + ks * 32);
 
   float m[2] = {-INFINITY, -INFINITY};
   l[0] = l[1] = 0.f;
@@ -51,6 +62,8 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
   for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 
   for (int key0 = 0; key0 < n_keys_pad; key0 += 32) {
+    const uint32_t kc_addr = k_addr + k_off + (uint32_t)(key0 * LD);
+    const uint32_t vc_addr = v_addr + v_off + (uint32_t)(key0 * LD);
     float s[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -58,47 +71,42 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
-        // B fragments of two key n-tiles: {keys +0..7, k lo}, {keys +0..7, k hi}, {keys +8..15, k lo}, {keys +8..15, k hi}
         uint32_t kf[4];
-        const int kr = key0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
-        const int kc = ks * 16 + ((lane >> 3) & 1) * 8;
-        ptx::ldmatrix_x4(kf, row_ptr(k_base, kr) + kc * 2);
+        ldsm_x4(kf, kc_addr + np * 16 * LD + ks * 32);
         ptx::mma_16816<D>(s[np * 2 + 0], qf[ks], kf[0], kf[1]);
         ptx::mma_16816<D>(s[np * 2 + 1], qf[ks], kf[2], kf[3]);
       }
     }
-    // scale into the exp2 domain, mask padded keys
-    float cmax[2] = {-INFINITY, -INFINITY};
+    if (key0 + 32 > n_keys) {   // warp-uniform: only the last chunk holds padded keys
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = key0 + nt * 8 + 2 * t + (e & 1);
-        const float v = key < n_keys ? s[nt][e] * scale_log2 : -INFINITY;
-        s[nt][e] = v;
-        cmax[e >> 1] = fmaxf(cmax[e >> 1], v);
-      }
+        for (int e = 0; e < 4; ++e)
+          if (key0 + nt * 8 + 2 * t + (e & 1) >= n_keys) s[nt][e] = -INFINITY;
     }
-    float corr[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float mn = fmaxf(m[h], quad_max(cmax[h]));   // finite: every 32-key chunk starts below n_keys
-      corr[h] = exp2f(m[h] - mn);
-      m[h] = mn;
-      l[h] *= corr[h];
-    }
+    float cmax0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+    float cmax1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+    cmax0 = fmaxf(cmax0, fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
+    cmax1 = fmaxf(cmax1, fmaxf(fmaxf(s[2][2], s[2][3]), fmaxf(s[3][2], s[3][3])));
+    const float mn0 = fmaxf(m[0], quad_max(cmax0)), mn1 = fmaxf(m[1], quad_max(cmax1));   // finite: every chunk starts below n_keys
+    const float corr0 = fast_exp2((m[0] - mn0) * scale_log2), corr1 = fast_exp2((m[1] - mn1) * scale_log2);
+    m[0] = mn0;
+    m[1] = mn1;
+    const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
+    l[0] *= corr0;
+    l[1] *= corr1;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      o[i][0] *= corr[0];
-      o[i][1] *= corr[0];
-      o[i][2] *= corr[1];
-      o[i][3] *= corr[1];
+      o[i][0] *= corr0;
+      o[i][1] *= corr0;
+      o[i][2] *= corr1;
+      o[i][3] *= corr1;
     }
     uint32_t pf[2][4];   // P as A fragments for the two 16-key k-steps of this chunk
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      const float p0 = exp2f(s[nt][0] - m[0]), p1 = exp2f(s[nt][1] - m[0]);
-      const float p2 = exp2f(s[nt][2] - m[1]), p3 = exp2f(s[nt][3] - m[1]);
+      const float p0 = fast_exp2(fmaf(s[nt][0], scale_log2, ms0)), p1 = fast_exp2(fmaf(s[nt][1], scale_log2, ms0));
+      const float p2 = fast_exp2(fmaf(s[nt][2], scale_log2, ms1)), p3 = fast_exp2(fmaf(s[nt][3], scale_log2, ms1));
       l[0] += p0 + p1;
       l[1] += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = D::pack2(p0, p1);
@@ -108,11 +116,8 @@ __device__ __forceinline__ void attend_tile(const uint8_t* q_base, int q_row0, c
     for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
       for (int dp = 0; dp < NT / 2; ++dp) {
-        // V^T fragments via ldmatrix.trans: {keys +0..7, dims d}, {keys +8..15, dims d}, {keys +0..7, dims d+8}, {keys +8..15, dims d+8}
         uint32_t vf[4];
-        const int vr = key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int vc = dp * 16 + (lane >> 4) * 8;
-        ptx::ldmatrix_x4_trans(vf, row_ptr(v_base, vr) + vc * 2);
+        ldsm_x4_t(vf, vc_addr + kk * 16 * LD + dp * 32);
         ptx::mma_16816<D>(o[dp * 2 + 0], pf[kk], vf[0], vf[1]);
         ptx::mma_16816<D>(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
       }
@@ -163,13 +168,12 @@ attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ ou
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const float scale_log2 = rsqrtf((float)HD) * kLog2e;
-  auto row_ptr = [](const uint8_t* b, int r) { return b + (size_t)r * LD; };
   uint16_t* obase = out + ((size_t)clip * n_frames * n_tok + tok) * C + head * HD;
   const size_t orow_stride = (size_t)n_tok * C;
 
   for (int mt = warp; mt * 16 < n_frames; mt += kTWarps) {
     float o[HD / 8][4], l[2];
-    attend_tile<HD, D>(sq, mt * 16, sk, sv, n_frames, Tp, scale_log2, row_ptr, lane, o, l);
+    attend_tile<HD, LD, D>(smem_u32(sq) + (uint32_t)(mt * 16 * LD), smem_u32(sk), smem_u32(sv), n_frames, Tp, scale_log2, lane, o, l);
     const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
     // this warp's 16 query rows are dead: reuse them to transpose the output tile
     __syncwarp();
@@ -203,24 +207,23 @@ attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int buf_bytes = 3 * n_tok * LD;
-  uint8_t* wbase = smem + (size_t)warp * (2 * buf_bytes + LD);
-  uint8_t* zero_row = wbase + 2 * buf_bytes;
-  for (int i = lane; i < LD / 16; i += 32) *reinterpret_cast<uint4*>(zero_row + i * 16) = make_uint4(0, 0, 0, 0);
+  constexpr int kRows = 32;                  // rows per matrix; rows [n_tok, 32) stay zero (loads only touch rows < n_tok)
+  constexpr int buf_bytes = 3 * kRows * LD;
+  uint8_t* wbase = smem + (size_t)warp * 2 * buf_bytes;
+  for (int i = lane; i < 2 * buf_bytes / 16; i += 32) *reinterpret_cast<uint4*>(wbase + i * 16) = make_uint4(0, 0, 0, 0);
   __syncwarp();
 
   const float scale_log2 = rsqrtf((float)HD) * kLog2e;
   const int64_t n_items = n_seq * n_heads;
   const int64_t stride = (int64_t)gridDim.x * kSWarps;
   const int chunks = 3 * n_tok * CH;
-  auto row_ptr = [=](const uint8_t* b, int r) { return r < n_tok ? b + (size_t)r * LD : (const uint8_t*)zero_row; };
   auto issue = [&](int64_t item, uint8_t* buf) {
     const int64_t seq = item / n_heads;
     const int head = (int)(item - seq * n_heads);
     const uint16_t* src = qkv + (size_t)seq * n_tok * 3 * C + head * HD;
     for (int i = lane; i < chunks; i += 32) {
       const int ch = i % CH, r = (i / CH) % n_tok, sel = i / (CH * n_tok);
-      ptx::cp_async16(buf + (size_t)(sel * n_tok + r) * LD + ch * 16, src + (size_t)r * 3 * C + sel * C + ch * 8);
+      ptx::cp_async16(buf + (size_t)(sel * kRows + r) * LD + ch * 16, src + (size_t)r * 3 * C + sel * C + ch * 8);
     }
     ptx::cp_async_commit();
   };
@@ -237,12 +240,10 @@ attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out
       ptx::cp_async_wait<0>();
     }
     __syncwarp();
-    const uint8_t* qb = buf;
-    const uint8_t* kb = buf + (size_t)n_tok * LD;
-    const uint8_t* vb = kb + (size_t)n_tok * LD;
+    const uint32_t qb = smem_u32(buf), kb = qb + kRows * LD, vb = kb + kRows * LD;
     for (int mt = 0; mt * 16 < n_tok; ++mt) {
       float o[HD / 8][4], l[2];
-      attend_tile<HD, D>(qb, mt * 16, kb, vb, n_tok, (n_tok + 31) & ~31, scale_log2, row_ptr, lane, o, l);
+      attend_tile<HD, LD, D>(qb + (uint32_t)(mt * 16 * LD), kb, vb, n_tok, kRows, scale_log2, lane, o, l);
       const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
       __syncwarp();                          // all lanes hold their q fragments of this tile: its rows may be overwritten
       const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -303,7 +304,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   }
   MP_REQUIRE(mode == MP_ATTN_SPATIAL, MP_EINVAL, "mp_attention: unknown mode %d", mode);
   MP_REQUIRE(n_tok <= 32, MP_EUNSUPPORTED, "mp_attention: spatial sequences longer than 32 tokens are not built (got %d)", n_tok);
-  const size_t smem = (size_t)kSWarps * ((size_t)2 * 3 * n_tok + 1) * (hd * 2 + 16);
+  const size_t smem = (size_t)kSWarps * 2 * 3 * 32 * (hd * 2 + 16);
   MP_REQUIRE(smem <= 227 * 1024, MP_EUNSUPPORTED, "mp_attention: %d spatial tokens need %zu bytes of shared memory", n_tok, smem);
   const int64_t n_seq = n_clips * n_frames;
   const int64_t n_items = n_seq * n_heads;
