@@ -7,10 +7,15 @@
 // Both kernels keep Q, K and V of their sequences in shared memory (16-byte cp.async, +16-byte row padding so ldmatrix
 // is bank-conflict free), compute S = QK^T and O = PV on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) with
 // an online softmax in the exp2 domain, and write O through shared memory as 16-byte coalesced rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace mp {
+
+int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type);  // gemm.cu
+
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -193,6 +198,187 @@ attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ ou
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ temporal, tcgen05
+// head_dim 64.  One CTA per (clip, token, head, 128-query tile), two CTAs per SM so the loads of one overlap the softmax of the other:
+//   TMA   Q tile [128 x 64] and K [Tp x 64] (K-major), V [Tp x 64] (MN-major B operand) straight out of the [clip, frame, token, 3C]
+//         activation through a 4-D tensor map (frames of one track, zero-filled past the clip end)
+//   MMA   S[128 x Tp] = Q K^T into TMEM (tcgen05.mma, one thread)
+//   4 softmax warps: thread = query row, reads its S row from TMEM (no shuffles), writes P (16-bit) over the dead Q / K tiles as the
+//         K-major A operand of the second MMA
+//   MMA   O[128 x 64] = P V into TMEM (aliasing S), read back, scaled by 1 / rowsum, staged and written with one TMA store.
+constexpr int kTcThreads = 160;   // 4 softmax warps + 1 TMA / MMA warp
+
+template <typename D>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
+                        int n_frames, int n_tok, int C, int n_heads, int m_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  // [ Q 16 KB | K 32 KB | +16 KB ] = 64 KB, later P (4 k-blocks of [128 x 64] 16-bit), later the O staging tile; then V 32 KB
+  uint8_t* sq = smem;
+  uint8_t* sk = smem + 16384;
+  uint8_t* sp = smem;
+  uint8_t* sv = smem + 65536;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int item = blockIdx.x;
+  const int mt = item % m_tiles;
+  item /= m_tiles;
+  const int head = item % n_heads;
+  item /= n_heads;
+  const int tok = item % n_tok;
+  const int clip = item / n_tok;
+  const int Tp = (n_frames + 31) & ~31;        // keys padded to the softmax chunk (and a legal UMMA N)
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_kv);
+    ptx::prefetch_tmap(&tm_o);
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, 128);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads
+      ptx::mbar_expect_tx(bar_qk, 16384 + (uint32_t)Tp * 128);
+      ptx::tma_load_4d(sq, &tm_q, bar_qk, head * 64, tok, mt * 128, clip);
+      ptx::tma_load_4d(sk, &tm_kv, bar_qk, C + head * 64, tok, 0, clip);
+      ptx::mbar_expect_tx(bar_v, (uint32_t)Tp * 128);
+      ptx::tma_load_4d(sv, &tm_kv, bar_v, 2 * C + head * 64, tok, 0, clip);
+      // ---- S = Q K^T
+      ptx::mbar_wait(bar_qk, 0);
+      ptx::tc_fence_after();
+      {
+        const uint32_t idesc = ptx::umma_idesc_16(128, Tp, D::kUmmaFmt);
+        const uint64_t da = ptx::umma_desc_sw128(smem_u32(sq));
+        const uint64_t db = ptx::umma_desc_sw128(smem_u32(sk));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        ptx::umma_commit(bar_s);
+      }
+      // ---- O = P V   (A = P: K-major k-blocks of 64 keys, 16 KB apart; B = V: MN-major, 16 keys = 2048 bytes per k-step)
+      ptx::mbar_wait(bar_p, 0);
+      ptx::mbar_wait(bar_v, 0);
+      ptx::tc_fence_after();
+      {
+        const uint32_t idesc = ptx::umma_idesc_16_bmn(128, 64, D::kUmmaFmt);
+        const uint32_t pa = smem_u32(sp), va = smem_u32(sv);
+        const int ksteps = Tp / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = ptx::umma_desc_sw128(pa + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32));
+          const uint64_t db = ptx::umma_desc_mn_sw128(va + (uint32_t)(k * 2048));
+          ptx::umma_f16(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(bar_o);
+      }
+    }
+  } else {
+    // ---- softmax: thread = query row r of this tile <-> TMEM lane r
+    const int row = threadIdx.x;                       // 0..127
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
+    const float scale_log2 = 0.125f * kLog2e;          // head_dim 64
+    const int n_chunks = Tp / 32;
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    float mx = -INFINITY;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+      ptx::tmem_ld_wait();
+      if ((c + 1) * 32 <= n_frames) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < n_frames) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    }
+    const float ms = -mx * scale_log2;
+    float sum = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+      ptx::tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, ms));
+        p[i] = (c * 32 + i < n_frames) ? e : 0.f;
+        sum += p[i];
+      }
+      // keys [32c, 32c+32) = half of k-block c/2: 64 bytes = chunks (c & 1) * 4 .. +4 of the 128-byte row
+      uint8_t* prow = sp + (size_t)(c >> 1) * 16384 + (size_t)row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = D::pack2(p[8 * q + 0], p[8 * q + 1]);
+        o.y = D::pack2(p[8 * q + 2], p[8 * q + 3]);
+        o.z = D::pack2(p[8 * q + 4], p[8 * q + 5]);
+        o.w = D::pack2(p[8 * q + 6], p[8 * q + 7]);
+        *reinterpret_cast<uint4*>(prow + (((uint32_t)((c & 1) * 4 + q) ^ sw) << 4)) = o;
+      }
+    }
+    ptx::tc_fence_before();            // S has been read: the second MMA may overwrite its columns
+    ptx::fence_proxy_async_smem();     // P is visible to the tensor core (async proxy)
+    ptx::mbar_arrive(bar_p);
+    // ---- O
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.0f / sum;
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld32(t_row, r0);
+    ptx::tmem_ld32(t_row + 32u, r1);
+    ptx::tmem_ld_wait();
+    uint8_t* orow = smem + (size_t)row * 128;          // P is dead: stage the [128 x 64] output tile over it
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+      const int b = (q & 3) * 8;
+      uint4 o;
+      o.x = D::pack2(__uint_as_float(r[b + 0]) * inv, __uint_as_float(r[b + 1]) * inv);
+      o.y = D::pack2(__uint_as_float(r[b + 2]) * inv, __uint_as_float(r[b + 3]) * inv);
+      o.z = D::pack2(__uint_as_float(r[b + 4]) * inv, __uint_as_float(r[b + 5]) * inv);
+      o.w = D::pack2(__uint_as_float(r[b + 6]) * inv, __uint_as_float(r[b + 7]) * inv);
+      *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
+    }
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+      ptx::tma_store_4d(&tm_o, smem, head * 64, tok, mt * 128, clip);
+      ptx::bulk_commit();
+      ptx::bulk_wait<0>();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------ spatial
 // Work item = one (frame, head): n_tok rows of q, k and v, 2 * HD bytes each.  Every WARP streams its own items through a
 // private double buffer (cp.async for item i+1 in flight while item i is computed), so there is no block-level barrier and
@@ -288,6 +474,23 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
     MP_REQUIRE(n_frames <= 256, MP_EUNSUPPORTED, "mp_attention: temporal sequences longer than 256 frames are not built (got %lld)",
                (long long)n_frames);
     const int Tp = ((int)n_frames + 31) & ~31;
+    static const bool legacy = getenv("MANIPOSE_ATTN_MMA_SYNC") != nullptr;   // A/B switch: the mma.sync kernel below
+    if (hd == 64 && !legacy) {
+      const int m_tiles = ((int)n_frames + 127) / 128;
+      CUtensorMap tq, tkv, to;
+      MP_CHECK(get_tmap_track(&tq, qkv, n_clips, n_frames, n_tok, 3 * C, 128, dtype));
+      MP_CHECK(get_tmap_track(&tkv, qkv, n_clips, n_frames, n_tok, 3 * C, Tp, dtype));
+      MP_CHECK(get_tmap_track(&to, out, n_clips, n_frames, n_tok, C, 128, dtype));
+      const int64_t ctas = n_clips * n_tok * n_heads * m_tiles;
+      MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+      const int smem_tc = 98304 + 64;
+      auto launch_tc = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
+        kernel<<<(unsigned)ctas, kTcThreads, smem_tc, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, m_tiles);
+      };
+      if (bf) launch_tc(attn_temporal_tc_kernel<Bf16>); else launch_tc(attn_temporal_tc_kernel<Fp16>);
+      return check_launch("attn_temporal_tc_kernel");
+    }
     const size_t smem = (size_t)3 * Tp * (hd * 2 + 16);
     const int64_t ctas = n_clips * n_tok * n_heads;
     MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");

@@ -153,6 +153,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, uint32_t fmt)
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// 4-D tiled TMA load / store (coordinates innermost first)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// Shared-memory matrix descriptor for an MN-major operand with 128-byte swizzle: rows are the K index (128 bytes = 64 MN elements
+// each), 8-row groups SBO = 1024 bytes apart (cute canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units; one MN group).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;      // SBO: byte distance between 8-row (K) groups
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor with an MN-major B operand (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_16_bmn(int m, int n, uint32_t fmt) { return umma_idesc_16(m, n, fmt) | (1u << 16); }
+
 // ---------------------------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
