@@ -368,7 +368,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     if (threadIdx.x == 0) {
       ptx::tma_store_4d(&tm_o, smem, head * 64, tok, mt * 128, clip);
       ptx::bulk_commit();
-      ptx::bulk_wait<0>();
+      ptx::bulk_wait_read<0>();      // shared memory must outlive the store's read; the global write completes on its own
     }
   }
   ptx::tc_fence_before();
