@@ -14,6 +14,7 @@
 
 namespace mp {
 
+int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type);  // gemm.cu
 int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type);  // gemm.cu
 
 namespace {
@@ -379,6 +380,183 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ spatial, tcgen05
+// head_dim 64, n_tok <= 32.  G = (128 / n_tok) * n_tok consecutive tokens (7 frames of 17 joints) form one 128-row tile: the same
+// rows are the queries and the keys, S = Q K^T is a [128 x 128] tcgen05 MMA of which only the block diagonal (same frame) is
+// kept.  The softmax thread of row i reads just the 32-column chunks that contain its frame's columns, writes the (mostly zero)
+// 16-bit P row over the dead Q / K tiles, and O = P V uses V as the MN-major operand.  48 KB of shared memory and 128 TMEM
+// columns per CTA: four CTAs per SM overlap loads, softmax and stores.  Rows [G, 128) of a tile belong to the next tile and are
+// not stored.
+template <typename D>
+__global__ void __launch_bounds__(kTcThreads, 4)
+attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_o, int64_t n_rows, int n_tok, int C,
+                       int n_heads, int G) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sq = smem;                 // [128 x 64] queries; later P k-block 0
+  uint8_t* sk = smem + 16384;         // [128 x 64] keys;    later P k-block 1
+  uint8_t* sv = smem + 32768;         // [128 x 64] values (MN-major B operand)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x % n_heads;
+  const int tile = blockIdx.x / n_heads;
+  const int row0 = tile * G;          // multiple of n_tok: frame f of the tile owns tile-local columns [f * n_tok, (f + 1) * n_tok)
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    ptx::prefetch_tmap(&tm_o);
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, 128);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 128);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(bar_qk, 32768);
+      ptx::tma_load_2d(sq, &tm_in, bar_qk, head * 64, row0);
+      ptx::tma_load_2d(sk, &tm_in, bar_qk, C + head * 64, row0);
+      ptx::mbar_expect_tx(bar_v, 16384);
+      ptx::tma_load_2d(sv, &tm_in, bar_v, 2 * C + head * 64, row0);
+      ptx::mbar_wait(bar_qk, 0);
+      ptx::tc_fence_after();
+      {
+        constexpr uint32_t idesc = ptx::umma_idesc_16(128, 128, D::kUmmaFmt);
+        const uint64_t da = ptx::umma_desc_sw128(smem_u32(sq));
+        const uint64_t db = ptx::umma_desc_sw128(smem_u32(sk));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        ptx::umma_commit(bar_s);
+      }
+      ptx::mbar_wait(bar_p, 0);
+      ptx::mbar_wait(bar_v, 0);
+      ptx::tc_fence_after();
+      {
+        constexpr uint32_t idesc = ptx::umma_idesc_16_bmn(128, 64, D::kUmmaFmt);
+        const uint32_t pa = smem_u32(smem), va = smem_u32(sv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = ptx::umma_desc_sw128(pa + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32));
+          const uint64_t db = ptx::umma_desc_mn_sw128(va + (uint32_t)(k * 2048));
+          ptx::umma_f16(tmem_base, da, db, idesc, k != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(bar_o);
+      }
+    }
+  } else {
+    const int row = threadIdx.x;                       // tile-local query row <-> TMEM lane
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
+    const float scale_log2 = 0.125f * kLog2e;
+    // columns of this row's frame, clipped to the keys that exist; rows past the end of the tensor get an empty window
+    const int a = (row / n_tok) * n_tok;
+    int b = a + n_tok;
+    if (b > 128) b = 128;
+    if ((int64_t)row0 + b > n_rows) b = (int)(n_rows - row0);
+    const bool live = (int64_t)row0 + row < n_rows && b > a;
+    // warp-uniform range of 32-column chunks that covers the windows of rows [32 warp, 32 warp + 32)
+    const int c_lo = ((32 * warp) / n_tok * n_tok) / 32;
+    int c_hi = (((32 * warp + 31) / n_tok + 1) * n_tok + 31) / 32;
+    if (c_hi > 4) c_hi = 4;
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    float mx = -INFINITY;
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int j = c * 32 + i;
+        if (j >= a && j < b) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    }
+    const float ms = live ? -mx * scale_log2 : 0.f;
+    float sum = 0.f;
+    for (int c = 0; c < 4; ++c) {
+      float p[32];
+      if (c >= c_lo && c < c_hi) {
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = c * 32 + i;
+          const bool in = live && j >= a && j < b;
+          const float e = fast_exp2(fmaf(in ? __uint_as_float(r[i]) : 0.f, scale_log2, ms));
+          p[i] = in ? e : 0.f;
+          sum += p[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i] = 0.f;
+      }
+      uint8_t* prow = smem + (size_t)(c >> 1) * 16384 + (size_t)row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = D::pack2(p[8 * q + 0], p[8 * q + 1]);
+        o.y = D::pack2(p[8 * q + 2], p[8 * q + 3]);
+        o.z = D::pack2(p[8 * q + 4], p[8 * q + 5]);
+        o.w = D::pack2(p[8 * q + 6], p[8 * q + 7]);
+        *reinterpret_cast<uint4*>(prow + (((uint32_t)((c & 1) * 4 + q) ^ sw) << 4)) = o;
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(bar_p);
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    const float inv = live ? 1.0f / sum : 0.f;
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld32(t_row, r0);
+    ptx::tmem_ld32(t_row + 32u, r1);
+    ptx::tmem_ld_wait();
+    uint8_t* orow = smem + (size_t)row * 128;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+      const int bb = (q & 3) * 8;
+      uint4 o;
+      o.x = D::pack2(__uint_as_float(r[bb + 0]) * inv, __uint_as_float(r[bb + 1]) * inv);
+      o.y = D::pack2(__uint_as_float(r[bb + 2]) * inv, __uint_as_float(r[bb + 3]) * inv);
+      o.z = D::pack2(__uint_as_float(r[bb + 4]) * inv, __uint_as_float(r[bb + 5]) * inv);
+      o.w = D::pack2(__uint_as_float(r[bb + 6]) * inv, __uint_as_float(r[bb + 7]) * inv);
+      *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
+    }
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+      ptx::tma_store_2d(&tm_o, smem, head * 64, row0);     // box of G rows: rows [G, 128) belong to the next tile
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------ spatial
 // Work item = one (frame, head): n_tok rows of q, k and v, 2 * HD bytes each.  Every WARP streams its own items through a
 // private double buffer (cp.async for item i+1 in flight while item i is computed), so there is no block-level barrier and
@@ -507,6 +685,23 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   }
   MP_REQUIRE(mode == MP_ATTN_SPATIAL, MP_EINVAL, "mp_attention: unknown mode %d", mode);
   MP_REQUIRE(n_tok <= 32, MP_EUNSUPPORTED, "mp_attention: spatial sequences longer than 32 tokens are not built (got %d)", n_tok);
+  static const bool legacy_s = getenv("MANIPOSE_ATTN_MMA_SYNC") != nullptr;
+  if (hd == 64 && !legacy_s) {
+    const int G = (128 / n_tok) * n_tok;
+    const int64_t n_rows = n_clips * n_frames * n_tok;
+    const int64_t tiles = (n_rows + G - 1) / G;
+    MP_REQUIRE(tiles * n_heads < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+    CUtensorMap tin, to;
+    MP_CHECK(get_tmap(&tin, qkv, n_rows, 3 * C, 128, dtype));
+    MP_CHECK(get_tmap(&to, out, n_rows, C, G, dtype));
+    const int smem_tc = 49152 + 64;
+    auto launch_tc = [&](auto kernel) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
+      kernel<<<(unsigned)(tiles * n_heads), kTcThreads, smem_tc, s>>>(tin, to, n_rows, n_tok, C, n_heads, G);
+    };
+    if (bf) launch_tc(attn_spatial_tc_kernel<Bf16>); else launch_tc(attn_spatial_tc_kernel<Fp16>);
+    return check_launch("attn_spatial_tc_kernel");
+  }
   const size_t smem = (size_t)kSWarps * 2 * 3 * 32 * (hd * 2 + 16);
   MP_REQUIRE(smem <= 227 * 1024, MP_EUNSUPPORTED, "mp_attention: %d spatial tokens need %zu bytes of shared memory", n_tok, smem);
   const int64_t n_seq = n_clips * n_frames;

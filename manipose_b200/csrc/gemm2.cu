@@ -30,8 +30,6 @@ constexpr int kBK = 64;
 constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kSlots = 4;
-constexpr int kLnStages = 2;                  // pair_linear_ln_kernel: operand stages ...
-constexpr int kLnSlots = 8;                   // ... and box-ring slots (4 per column half)
 constexpr int kBoxBytes = kBM * 128;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kWHalfBytes = 128 * kBK * 2;    // 16 KB: the 128 weight rows this CTA contributes to one N = 256 instruction
@@ -282,7 +280,7 @@ __device__ __forceinline__ void row_stats_exchange(float2* sx, int grp, int row,
   rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
 }
 
-template <typename D>
+template <typename D, int kLnStages, int kLnSlots>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
                       const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, LnArgs args, int M, int K) {
@@ -604,8 +602,8 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 }
 
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
-constexpr int kPairLnSmem = kLnStages * (kABytes + 2 * kWHalfBytes) + kLnSlots * kBoxBytes + 256 + 2 * kBM * 8;
-static_assert(kPairLnSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+constexpr int pair_ln_smem(int stages, int slots) { return stages * (kABytes + 2 * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
+static_assert(pair_ln_smem(2, 8) <= 232448 && pair_ln_smem(3, 4) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -673,10 +671,15 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
-  auto launch = [&](auto kernel) -> int {
-    MP_CHECK(set_smem(kernel, kPairLnSmem));
-    kernel<<<grid, kThreads, kPairLnSmem, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, args, (int)M, (int)K);
+  // shared memory split between operand stages and the box ring: 2 stages + 8 slots for K = 512 (the epilogue dominates), 3 stages +
+  // 4 slots for K = 1024 (measured: 246 vs 267 us at 32 clips); MANIPOSE_LN_CFG=1 / 2 forces one of them
+  static const int cfg = getenv("MANIPOSE_LN_CFG") ? atoi(getenv("MANIPOSE_LN_CFG")) : 0;
+  auto launch = [&](auto kernel, int smem_bytes) -> int {
+    MP_CHECK(set_smem(kernel, smem_bytes));
+    kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, args, (int)M, (int)K);
     return check_launch("pair_linear_ln_kernel");
   };
-  return dtype == MP_DTYPE_BF16 ? launch(pair_linear_ln_kernel<Bf16>) : launch(pair_linear_ln_kernel<Fp16>);
+  const bool bf = dtype == MP_DTYPE_BF16;
+  if (cfg == 1 || (cfg == 0 && K >= 1024)) return bf ? launch(pair_linear_ln_kernel<Bf16, 3, 4>, pair_ln_smem(3, 4)) : launch(pair_linear_ln_kernel<Fp16, 3, 4>, pair_ln_smem(3, 4));
+  return bf ? launch(pair_linear_ln_kernel<Bf16, 2, 8>, pair_ln_smem(2, 8)) : launch(pair_linear_ln_kernel<Fp16, 2, 8>, pair_ln_smem(2, 8));
 }
