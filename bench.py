@@ -44,6 +44,35 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 132192 rows = 32 clips) from the
+# committed `ncu --set full` capture profiles/r1_pair_linear_ln_full.csv; algorithmic bytes of the same launch: 810.7 MB
+PROFILED_TRAFFIC_LN = {"bytes_per_launch": 755.5e6, "algorithmic_bytes": 810.7e6, "launch": "proj + norm2, M=132192, K=512", "source": "profiles/r1_pair_linear_ln_full.csv"}
+
+
+def roofline_object(dom, rl, peaks, step_tflops, traffic):
+    """Roofline of the dominant kernel family (by measured share of the step) + the other family and the whole step for context.
+    linear_ln (residual GEMM with fused LayerNorms, 5-7 B per output element) is HBM-bound; linear (qkv, fc1) is tensor-bound."""
+    if dom is None:
+        return None
+    out = {}
+    if dom == "linear_ln":
+        a = rl[dom]["gbs"]
+        out = {"bound": "hbm", "kernel": "pair_linear_ln_kernel (tcgen05 cta_group::2 residual GEMM + fused LayerNorm epilogue: proj / fc2)",
+               "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "traffic": traffic.get(dom),
+               "peak_source": f"{peaks['src']} (STREAM-style copy)"}
+    else:
+        a = rl[dom]["tflops"]
+        out = {"bound": "tensor", "kernel": "pair_linear_kernel (tcgen05 cta_group::2: qkv, fc1 + GELU)", "achieved": a,
+               "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": a / peaks["bf16_sustained"], "traffic": traffic.get(dom),
+               "peak_source": f"{peaks['src']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})"}
+    out["share_of_step"] = rl[dom]["share_of_step"]
+    out["avg_launch_us"] = rl[dom]["avg_us"]
+    out["families"] = rl
+    out["whole_step"] = {"achieved": step_tflops, "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_sustained"],
+                         "flops": "algorithmic matmul flops of the whole forward / step time, vs the sustained bf16 peak"}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -233,11 +262,25 @@ def run_gpu(args):
     frames = B * T * world
     value = frames * args.steps / (ms / 1000.0)
 
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in sampled)
-    gemm_flops = sum(f for _, _, f in sampled)
     peaks = measured_peaks()
-    achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    fam = {}
+    for a, b, fl, by, tag in sampled:
+        f = fam.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        f["ms"] += a.elapsed_time(b)
+        f["flops"] += fl
+        f["bytes"] += by
+        f["n"] += 1
     step_tflops = flops_per_frame() * B * T * args.steps / (ms / 1000.0) / 1e12   # per GPU (max-over-ranks time)
+    # share of the step spent in each sampled family, extrapolated from the sampled micro-batches (1 in 16)
+    n_mb = max(1, counter["n"])
+    sampled_mb = max(1, (n_mb + 15) // 16)
+    rl = {}
+    for tag, f in fam.items():
+        t_s = f["ms"] / 1000.0
+        rl[tag] = {"launches_sampled": f["n"], "avg_us": f["ms"] * 1000.0 / f["n"], "tflops": f["flops"] / t_s / 1e12,
+                   "gbs": f["bytes"] / t_s / 1e9, "share_of_step": f["ms"] * (n_mb / sampled_mb) / ms}
+    dom = max(rl, key=lambda k: rl[k]["share_of_step"]) if rl else None
+    traffic = {"linear_ln": PROFILED_TRAFFIC_LN, "linear": None}
 
     # ---- end to end through the public API with host buffers
     for _ in range(2):
@@ -261,13 +304,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": (out_host[0].numel() + out_host[1].numel()) * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "kernel": "linear_kernel (tcgen05, all 4 Linear shapes of the rotation blocks)",
-                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_sustained"] if achieved else 0.0, "traffic": None,
-                         "peak_source": f"{peaks['src']} (sustained cuBLAS bf16; burst {peaks['bf16_burst']})",
-                         "sampled_launches": len(sampled), "gemm_share_of_step": None,
-                         "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
-                                        "flops": "algorithmic matmul flops of the whole forward / step time"}},
+            "roofline": roofline_object(dom, rl, peaks, step_tflops, traffic),
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": f"best of {cpu_reps} passes over 4 clips x {T} frames (972 frames) of the same workload, fp32, torch CPU"},
         }

@@ -13,7 +13,8 @@ J = 17
 BONES = 16
 
 # Kernel launches issued through this module (bench.py reports it as gpu_launches) and an optional sampling hook:
-# when GEMM_TIMING is a list, gemm() brackets its launch with CUDA events and appends (start, end, flops).
+# when GEMM_TIMING is a list, linear() / linear_ln() bracket their launch with CUDA events and append
+# (start, end, algorithmic flops, algorithmic bytes, kernel family).
 LAUNCHES = 0
 GEMM_TIMING = None
 
@@ -279,7 +280,9 @@ def linear(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
     _count()
     if timing is not None:
         e1.record()
-        timing.append((e0, e1, 2.0 * m * n * k))
+        esz = 4 if epilogue == L.MP_EPI_RESIDUAL else 2
+        byts = 2.0 * (m * k + n * k) + esz * m * n * (2 if epilogue == L.MP_EPI_RESIDUAL else 1)
+        timing.append((e0, e1, 2.0 * m * n * k, byts, "linear"))
     return out
 
 
@@ -299,7 +302,8 @@ def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=Non
     _count()
     if timing is not None:
         e1.record()
-        timing.append((e0, e1, 2.0 * m * n * k))
+        byts = 2.0 * (m * k + n * k) + 8.0 * m * n + (2.0 * m * n if ln is not None else 0.0)
+        timing.append((e0, e1, 2.0 * m * n * k, byts, "linear_ln"))
 
 
 def layernorm(x_in, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, dtype=L.MP_DTYPE_BF16):
