@@ -45,8 +45,8 @@ def measured_peaks():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 132192 rows = 32 clips) from the
-# committed `ncu --set full` capture profiles/r1_pair_linear_ln_full.csv; algorithmic bytes of the same launch: 810.7 MB
-PROFILED_TRAFFIC_LN = {"bytes_per_launch": 755.5e6, "algorithmic_bytes": 810.7e6, "launch": "proj + norm2, M=132192, K=512", "source": "profiles/r1_pair_linear_ln_full.csv"}
+# committed `ncu --set full` capture profiles/r1_pair_linear_full.csv; algorithmic bytes of the same launch: 810.7 MB
+PROFILED_TRAFFIC_LN = {"bytes_per_launch": 755.7e6, "algorithmic_bytes": 810.7e6, "launch": "proj + norm2, M=132192, K=512", "source": "profiles/r1_pair_linear_full.csv"}
 
 
 def roofline_object(dom, rl, peaks, step_tflops, traffic):
