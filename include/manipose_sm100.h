@@ -53,7 +53,8 @@ int mp_set_skeleton(int num_joints, const int32_t* host_parents, const float* ho
  * compute_rotation_matrix_from_ortho6d (utils/rotation_tools.py:35-57) + build_t_pose_from_bone_lengths
  * (pose_decoder.py:98-120) + forward_kinematics (utils/forward_kinematics.py:6-48), fused with the
  * softmax over hypotheses of RMCLRotMixSTE.forward (rmcl_manifold_mix_ste.py:262).
- *   rot6d   [n_clips*n_hyp*n_frames, 17, 6] fp32   (the reference's "(B H L) J D" flattening)
+ *   rot6d   [n_clips*n_hyp*n_frames, 17, rot_rep_dim] fp32, rot_rep_dim 6 (Gram-Schmidt) or 4 (R_theta R_phi,
+ *           rotation_tools.py:60-116)   (the reference's "(B H L) J D" flattening)
  *   bone_len[n_clips, 16] fp32 (signed)             pose n uses clip n / (n_hyp*n_frames)
  *   root    [n_poses, 3] or NULL (= zeros, what the reference passes)
  *   logits  [n_clips, n_hyp, n_frames] or NULL; scores (same shape) = softmax over n_hyp

@@ -22,10 +22,12 @@
 namespace mp {
 namespace {
 
-constexpr int kIn = kJ * 6;    // 102 floats per pose in
+template <int RD>
+constexpr int in_floats() { return kJ * RD; }   // 102 (6-D) / 68 (4-D) floats per pose in
 constexpr int kOut = kJ * 3;   // 51 floats per pose out
 constexpr int kTile = 32;      // poses per warp tile
-constexpr int kTileInBytes = kTile * kIn * 4;    // 13056
+template <int RD>
+constexpr int tile_in_bytes() { return kTile * kJ * RD * 4; }   // 13056 / 8704
 constexpr int kTileOutBytes = kTile * kOut * 4;  // 6528
 constexpr int kWarpsPerCta = 4;
 
@@ -71,24 +73,61 @@ struct PoseState {
   float t[kJ][2];    // T-pose x / y coordinates (z is identically 0)
 };
 
-template <bool kExact, int j>
+// v / max(sqrt(v.v), 1e-8) for a 2-vector (compute_rotation_matrix_from_ortho4d uses normalize_vector on [M,2] rows)
+template <bool kExact>
+__device__ __forceinline__ void normalize2(float& x, float& y) {
+  if (kExact) {
+    const float m = fmaxf(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), 1e-8f);
+    x = __fdiv_rn(x, m);
+    y = __fdiv_rn(y, m);
+  } else {
+    const float s = x * x + y * y;
+    const float inv = (s >= 1e-16f) ? rsqrtf(s) : 1e8f;
+    x *= inv;
+    y *= inv;
+  }
+}
+
+// local rotation of joint j, row-major r[row][col]
+template <bool kExact, int RD>
+__device__ __forceinline__ void local_rotation(const float* __restrict__ a, float (&r)[9]) {
+  using A = Arith<kExact>;
+  if constexpr (RD == 6) {
+    // ---- 6-D -> rotation matrix with columns [x y z]  (rotation_tools.py:35-57)
+    const float2 v01 = *reinterpret_cast<const float2*>(a + 0);
+    const float2 v23 = *reinterpret_cast<const float2*>(a + 2);
+    const float2 v45 = *reinterpret_cast<const float2*>(a + 4);
+    float x0 = v01.x, x1 = v01.y, x2 = v23.x;
+    const float b0 = v23.y, b1 = v45.x, b2 = v45.y;
+    A::normalize(x0, x1, x2);
+    float z0, z1, z2;
+    A::cross(x0, x1, x2, b0, b1, b2, z0, z1, z2);
+    A::normalize(z0, z1, z2);
+    float y0, y1, y2;
+    A::cross(z0, z1, z2, x0, x1, x2, y0, y1, y2);
+    r[0] = x0; r[1] = y0; r[2] = z0;
+    r[3] = x1; r[4] = y1; r[5] = z1;
+    r[6] = x2; r[7] = y2; r[8] = z2;
+  } else {
+    // ---- 4-D -> R_theta R_phi  (rotation_tools.py:60-116): (c_t, s_t) = n(a[0:2]), (c_p, s_p) = n(a[2:4]);
+    //   R_theta = [[s_t, c_t, 0], [-c_t, s_t, 0], [0, 0, 1]],  R_phi = [[1, 0, 0], [0, c_p, -s_p], [0, s_p, c_p]]
+    // (the products with the exact 0 / 1 entries of the reference's bmm are exact, so these six products are all there is)
+    const float2 th = *reinterpret_cast<const float2*>(a + 0);
+    const float2 ph = *reinterpret_cast<const float2*>(a + 2);
+    float ct = th.x, st = th.y, cp = ph.x, sp = ph.y;
+    normalize2<kExact>(ct, st);
+    normalize2<kExact>(cp, sp);
+    r[0] = st;  r[1] = A::mul(ct, cp); r[2] = -A::mul(ct, sp);
+    r[3] = -ct; r[4] = A::mul(st, cp); r[5] = -A::mul(st, sp);
+    r[6] = 0.f; r[7] = sp;             r[8] = cp;
+  }
+}
+
+template <bool kExact, int RD, int j>
 __device__ __forceinline__ void decode_joint(PoseState& st, const float* __restrict__ lane_in, const float* __restrict__ len) {
   using A = Arith<kExact>;
-  // ---- 6-D -> rotation matrix with columns [x y z]  (rotation_tools.py:35-57)
-  const float2 v01 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 0);
-  const float2 v23 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 2);
-  const float2 v45 = *reinterpret_cast<const float2*>(lane_in + j * 6 + 4);
-  float x0 = v01.x, x1 = v01.y, x2 = v23.x;
-  const float b0 = v23.y, b1 = v45.x, b2 = v45.y;
-  A::normalize(x0, x1, x2);
-  float z0, z1, z2;
-  A::cross(x0, x1, x2, b0, b1, b2, z0, z1, z2);
-  A::normalize(z0, z1, z2);
-  float y0, y1, y2;
-  A::cross(z0, z1, z2, x0, x1, x2, y0, y1, y2);
-  // local rotation, row-major: r[row][col], col 0 = x, 1 = y, 2 = z
-  const float r[9] = {x0, y0, z0, x1, y1, z1, x2, y2, z2};
-
+  float r[9];
+  local_rotation<kExact, RD>(lane_in + j * RD, r);
   if constexpr (j == 0) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) st.rw[0][i] = r[i];
@@ -123,7 +162,7 @@ __device__ __forceinline__ void decode_joint(PoseState& st, const float* __restr
       }
     }
   }
-  if constexpr (j + 1 < kJ) decode_joint<kExact, j + 1>(st, lane_in, len);
+  if constexpr (j + 1 < kJ) decode_joint<kExact, RD, j + 1>(st, lane_in, len);
 }
 
 // softmax over the hypothesis dim, one (clip, frame) per thread, grid-stride
@@ -142,11 +181,13 @@ __device__ __forceinline__ void softmax_hyp_rows(const float* __restrict__ logit
   }
 }
 
-template <bool kExact>
+template <bool kExact, int RD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
                    const float* __restrict__ logits, float* __restrict__ poses, float* __restrict__ scores, uint32_t n_poses,
                    uint32_t poses_per_clip, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames, int bulk_in, int bulk_out) {
+  constexpr int kIn = in_floats<RD>();
+  constexpr int kTileInBytes = tile_in_bytes<RD>();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,7 +249,7 @@ decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
       } else {
         st.pos[0] = st.pos[1] = st.pos[2] = 0.f;
       }
-      decode_joint<kExact, 0>(st, tile + lane * kIn, len);
+      decode_joint<kExact, RD, 0>(st, tile + lane * kIn, len);
     }
     __syncwarp();  // every lane is done reading the tile: reuse it for the output
 
@@ -292,15 +333,29 @@ __device__ __forceinline__ void normalize_bwd(const float (&u)[3], float n, bool
   gv[2] = (gu[2] - u[2] * d) / n;
 }
 
-template <int j, int c>
+template <int RD, int j, int c>
 struct Children;
 
-template <int j>
+template <int RD, int j>
 __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], float (&g_rwp)[9], float (&g_posp)[3]) {
   // ---- forward recompute for this joint
-  float x[3], y[3], z[3], w[3], na, nw;
-  gs_forward(ctx.r6 + j * 6, x, z, y, na, nw, w);
-  const float r[9] = {x[0], y[0], z[0], x[1], y[1], z[1], x[2], y[2], z[2]};
+  float x[3], y[3], z[3], w[3], na, nw;      // 6-D intermediates
+  float ct, st, cp, sp, nt, np_;             // 4-D intermediates
+  float r[9];
+  if constexpr (RD == 6) {
+    gs_forward(ctx.r6 + j * 6, x, z, y, na, nw, w);
+    r[0] = x[0]; r[1] = y[0]; r[2] = z[0];
+    r[3] = x[1]; r[4] = y[1]; r[5] = z[1];
+    r[6] = x[2]; r[7] = y[2]; r[8] = z[2];
+  } else {
+    const float* a4 = ctx.r6 + j * 4;
+    nt = fmaxf(sqrtf(a4[0] * a4[0] + a4[1] * a4[1]), 1e-8f);
+    np_ = fmaxf(sqrtf(a4[2] * a4[2] + a4[3] * a4[3]), 1e-8f);
+    ct = a4[0] / nt; st = a4[1] / nt; cp = a4[2] / np_; sp = a4[3] / np_;
+    r[0] = st;  r[1] = ct * cp; r[2] = -ct * sp;
+    r[3] = -ct; r[4] = st * cp; r[5] = -st * sp;
+    r[6] = 0.f; r[7] = sp;      r[8] = cp;
+  }
   float rw[9];
   if constexpr (j == 0) {
 #pragma unroll
@@ -315,7 +370,7 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
   float g_rw[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float g_pos[3] = {ctx.gp[j * 3 + 0], ctx.gp[j * 3 + 1], ctx.gp[j * 3 + 2]};
   // ---- children accumulate into g_rw / g_pos
-  Children<j, j + 1>::run(ctx, rw, g_rw, g_pos);
+  Children<RD, j, j + 1>::run(ctx, rw, g_rw, g_pos);
 
   float g_r[9];
   if constexpr (j == 0) {
@@ -342,6 +397,20 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
         g_rwp[row * 3 + col] += g_rw[row * 3 + 0] * r[col * 3 + 0] + g_rw[row * 3 + 1] * r[col * 3 + 1] + g_rw[row * 3 + 2] * r[col * 3 + 2];
         g_r[row * 3 + col] = rwp[0 * 3 + row] * g_rw[0 * 3 + col] + rwp[1 * 3 + row] * g_rw[1 * 3 + col] + rwp[2 * 3 + row] * g_rw[2 * 3 + col];
       }
+  }
+  if constexpr (RD == 4) {
+    // ---- 4-D backward: R = [[s_t, c_t c_p, -c_t s_p], [-c_t, s_t c_p, -s_t s_p], [0, s_p, c_p]]
+    const float g_ct = g_r[1] * cp - g_r[2] * sp - g_r[3];
+    const float g_st = g_r[0] + g_r[4] * cp - g_r[5] * sp;
+    const float g_cp = g_r[1] * ct + g_r[4] * st + g_r[8];
+    const float g_sp = -g_r[2] * ct - g_r[5] * st + g_r[7];
+    const float dt = nt <= 1e-8f ? 0.f : ct * g_ct + st * g_st;
+    const float dp = np_ <= 1e-8f ? 0.f : cp * g_cp + sp * g_sp;
+    ctx.r6[j * 4 + 0] = (g_ct - ct * dt) / nt;
+    ctx.r6[j * 4 + 1] = (g_st - st * dt) / nt;
+    ctx.r6[j * 4 + 2] = (g_cp - cp * dp) / np_;
+    ctx.r6[j * 4 + 3] = (g_sp - sp * dp) / np_;
+    return;
   }
   // ---- Gram-Schmidt backward (rotation_tools.py:35-57): columns of G_R are the gradients of x, y, z
   float gx[3] = {g_r[0], g_r[3], g_r[6]};
@@ -373,25 +442,30 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
   ctx.r6[j * 6 + 5] = gb[2];
 }
 
-template <int j, int c>
+template <int RD, int j, int c>
 struct Children {
   static __device__ __forceinline__ void run(BwdCtx& ctx, const float (&rw)[9], float (&g_rw)[9], float (&g_pos)[3]) {
-    if constexpr (parent_of(c) == j) bwd_joint<c>(ctx, rw, g_rw, g_pos);
-    Children<j, c + 1>::run(ctx, rw, g_rw, g_pos);
+    if constexpr (parent_of(c) == j) bwd_joint<RD, c>(ctx, rw, g_rw, g_pos);
+    Children<RD, j, c + 1>::run(ctx, rw, g_rw, g_pos);
   }
 };
-template <int j>
-struct Children<j, kJ> {
+template <int RD, int j>
+struct Children<RD, j, kJ> {
   static __device__ __forceinline__ void run(BwdCtx&, const float (&)[9], float (&)[9], float (&)[3]) {}
 };
 
 constexpr int kBwdWarps = 4;
-constexpr int kBwdWarpBytes = kTileInBytes + kTileOutBytes;   // rot6d / grad_rot6d tile + grad_poses tile
+template <int RD>
+constexpr int bwd_warp_bytes() { return tile_in_bytes<RD>() + kTileOutBytes; }   // rot / grad_rot tile + grad_poses tile
 
+template <int RD>
 __global__ void __launch_bounds__(kBwdWarps * 32, 2)
 decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ grad_poses,
                    float* __restrict__ grad_rot6d, float* __restrict__ grad_bone_len, float* __restrict__ grad_root, uint32_t n_poses,
                    uint32_t poses_per_clip, int bulk_ok) {
+  constexpr int kIn = in_floats<RD>();
+  constexpr int kTileInBytes = tile_in_bytes<RD>();
+  constexpr int kBwdWarpBytes = bwd_warp_bytes<RD>();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tile = reinterpret_cast<float*>(smem_raw + warp * kBwdWarpBytes);
@@ -443,7 +517,7 @@ decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
     if (active) {
       const float ident[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
       float g_dummy[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      bwd_joint<0>(ctx, ident, g_dummy, g_root);
+      bwd_joint<RD, 0>(ctx, ident, g_dummy, g_root);
       if (grad_root != nullptr) {
         grad_root[(size_t)pose * 3 + 0] = g_root[0];
         grad_root[(size_t)pose * 3 + 1] = g_root[1];
@@ -493,8 +567,6 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   MP_CHECK(require_sm100());
   // reference: assert rot_rep_dim in [4, 6] (pose_decoder.py:27-30)
   MP_REQUIRE(rot_rep_dim == 4 || rot_rep_dim == 6, MP_EINVAL, "Unsupported rotations representation dimension: %d", rot_rep_dim);
-  MP_REQUIRE(rot_rep_dim == 6, MP_EUNSUPPORTED,
-             "rot_rep_dim=4 (compute_rotation_matrix_from_ortho4d) is not built: no BASELINE config uses it");
   MP_REQUIRE(n_clips >= 0 && n_hyp >= 1 && n_frames >= 1, MP_EINVAL, "mp_decoder_fwd: bad sizes");
   const int64_t n_poses = n_clips * n_hyp * n_frames;
   if (n_poses == 0) return MP_OK;
@@ -504,7 +576,7 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   MP_REQUIRE(aligned16(bone_len), MP_EALIGN, "mp_decoder_fwd: bone_len must be 16-byte aligned");
 
   const int bulk_in = aligned16(rot6d), bulk_out = aligned16(poses);   // unaligned views fall back to coalesced LDG / STG
-  const size_t smem = (size_t)kWarpsPerCta * kTileInBytes + kWarpsPerCta * sizeof(uint64_t);
+  const size_t smem = (size_t)kWarpsPerCta * (rot_rep_dim == 6 ? tile_in_bytes<6>() : tile_in_bytes<4>()) + kWarpsPerCta * sizeof(uint64_t);
   const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
   int64_t ctas = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   const int64_t max_ctas = (int64_t)sm_count() * 4;
@@ -515,10 +587,12 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
         rot6d, bone_len, root, logits, poses, scores, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), (uint32_t)n_clips,
         (uint32_t)n_hyp, (uint32_t)n_frames, bulk_in, bulk_out);
   };
-  if (flags & MP_DEC_FAST)
-    launch(decoder_fwd_kernel<false>);
-  else
-    launch(decoder_fwd_kernel<true>);
+  const bool fast = (flags & MP_DEC_FAST) != 0;
+  if (rot_rep_dim == 6) {
+    if (fast) launch(decoder_fwd_kernel<false, 6>); else launch(decoder_fwd_kernel<true, 6>);
+  } else {
+    if (fast) launch(decoder_fwd_kernel<false, 4>); else launch(decoder_fwd_kernel<true, 4>);
+  }
   return check_launch("decoder_fwd_kernel");
 }
 
@@ -527,21 +601,23 @@ int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(rot_rep_dim == 4 || rot_rep_dim == 6, MP_EINVAL, "Unsupported rotations representation dimension: %d", rot_rep_dim);
-  MP_REQUIRE(rot_rep_dim == 6, MP_EUNSUPPORTED, "rot_rep_dim=4 is not built: no BASELINE config uses it");
   MP_REQUIRE(n_clips >= 0 && n_hyp >= 1 && n_frames >= 1, MP_EINVAL, "mp_decoder_bwd: bad sizes");
   const int64_t n_poses = n_clips * n_hyp * n_frames;
   if (n_poses == 0) return MP_OK;
   MP_REQUIRE(n_poses < (int64_t)1 << 31, MP_EINVAL, "mp_decoder_bwd: %lld poses exceed 2^31", (long long)n_poses);
   MP_REQUIRE(rot6d && bone_len && grad_poses && grad_rot6d && grad_bone_len, MP_EINVAL, "mp_decoder_bwd: null pointer");
   const int bulk_ok = aligned16(rot6d) && aligned16(grad_poses) && aligned16(grad_rot6d);
-  const size_t smem = (size_t)kBwdWarps * kBwdWarpBytes + kBwdWarps * sizeof(uint64_t);
+  const size_t smem = (size_t)kBwdWarps * (rot_rep_dim == 6 ? bwd_warp_bytes<6>() : bwd_warp_bytes<4>()) + kBwdWarps * sizeof(uint64_t);
   const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
   int64_t ctas = (n_tiles + kBwdWarps - 1) / kBwdWarps;
   const int64_t max_ctas = (int64_t)sm_count() * 2;
   if (ctas > max_ctas) ctas = max_ctas;
-  cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  decoder_bwd_kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(
-      rot6d, bone_len, grad_poses, grad_rot6d, grad_bone_len, grad_root, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), bulk_ok);
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(rot6d, bone_len, grad_poses, grad_rot6d, grad_bone_len, grad_root,
+                                                                         (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), bulk_ok);
+  };
+  if (rot_rep_dim == 6) launch(decoder_bwd_kernel<6>); else launch(decoder_bwd_kernel<4>);
   return check_launch("decoder_bwd_kernel");
 }
 

@@ -153,7 +153,8 @@ def pose_decoder(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor,
 
 def pose_decoder_ieee(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Tensor, root_positions: torch.Tensor,
                       parents=H36M17_PARENTS, operators=H36M17_T_POSE_OPERATORS) -> torch.Tensor:
-    """The same algorithm as ``pose_decoder`` (rot_rep_dim = 6) restated in numpy float32, where every +, -, *, / and sqrt is
+    """The same algorithm as ``pose_decoder`` (6-D, or 4-D when the last dim is 4: rotation_tools.py:60-116, whose products with
+    the exact 0 / 1 entries of R_theta and R_phi are exact) restated in numpy float32, where every +, -, *, / and sqrt is
     one correctly-rounded IEEE-754 operation and nothing is fused or reassociated: sum of squares as (x^2 + y^2) + z^2
     (rotation_tools.py:6-17), cross products as two products and a subtraction (:21-32), 3x3 products as
     ((a0 b0 + a1 b1) + a2 b2) (forward_kinematics.py:31-40), T-pose by cumulative adds with the offset recovered by
@@ -183,12 +184,25 @@ def pose_decoder_ieee(rotations_repr: torch.Tensor, bones_lengths_repr: torch.Te
     rw = [None] * nj     # world rotations as [row][col] lists of [N] arrays
     pos = [None] * nj
     tp = [None] * nj     # T-pose x / y
+    rd = r.shape[2]
+    assert rd in (4, 6), f"Unsupported rotations representation dimension: {rd}"
+    zero = np.zeros(n, np.float32)
+
+    def normalize2(x, y):
+        m = np.maximum(np.sqrt(x * x + y * y), eps)
+        return x / m, y / m
+
     for j in range(nj):
-        a = [r[:, j, i] for i in range(6)]
-        x = normalize(a[0], a[1], a[2])
-        z = normalize(*cross(x, (a[3], a[4], a[5])))
-        y = cross(z, x)
-        rl = [[x[i], y[i], z[i]] for i in range(3)]          # rows of the local rotation, columns [x y z]
+        a = [r[:, j, i] for i in range(rd)]
+        if rd == 6:
+            x = normalize(a[0], a[1], a[2])
+            z = normalize(*cross(x, (a[3], a[4], a[5])))
+            y = cross(z, x)
+            rl = [[x[i], y[i], z[i]] for i in range(3)]      # rows of the local rotation, columns [x y z]
+        else:
+            ct, st = normalize2(a[0], a[1])
+            cp, sp = normalize2(a[2], a[3])
+            rl = [[st, ct * cp, -(ct * sp)], [-ct, st * cp, -(st * sp)], [zero, sp, cp]]
         if parents[j] == -1:
             rw[j] = rl
             pos[j] = [root[:, 0], root[:, 1], root[:, 2]]

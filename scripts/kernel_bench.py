@@ -85,12 +85,54 @@ def main():
     for exact in (True, False):
         med, best = timeit(lambda: ops.decoder_fwd(rot, bones, None, logits, nc, k, t, 6, exact))
         out[f"decoder_fwd_{'exact' if exact else 'fast'}_1M"] = {"ms": med, "best_ms": best, "gbs": 620.0 * n / med / 1e6, "gposes_s": n / med / 1e6}
+    # decoder backward: reads rot6d 408 + grad_pose 204, writes grad_rot6d 408 (+ per-clip bone-length grads)
+    gp = torch.randn(n, 17, 3, generator=g, device=dev)
+    grot = torch.empty_like(rot)
+    gbone = torch.zeros(nc, 16, device=dev)
+    def dec_bwd():
+        gbone.zero_()
+        L.check(L.load().mp_decoder_bwd(L.ptr(rot), L.ptr(bones), L.ptr(gp), L.ptr(grot), L.ptr(gbone), None, nc, k, t, 6, L.stream_ptr()), "bwd")
+    med, best = timeit(dec_bwd)
+    out["decoder_bwd_1M"] = {"ms": med, "best_ms": best, "gbs": 1020.0 * n / med / 1e6, "gposes_s": n / med / 1e6}
     y = 0.3 * torch.randn(1024, 243, 17, 3, generator=g, device=dev)
     hyp = y[:, None] + 0.1 * torch.randn(1024, 5, 243, 17, 3, generator=g, device=dev)
     sc = torch.softmax(torch.randn(1024, 5, 243, generator=g, device=dev), 1)
     w = torch.tensor([1, 1, 2.5, 2.5, 1, 2.5, 2.5, 1, 1, 1, 1.5, 1.5, 4, 4, 1.5, 4, 4.0], device=dev)
+    nfr = 1024 * 243
     med, best = timeit(lambda: ops.loss_terms(hyp, sc, y, w, False, 0.1, 2.0, 0.5))
-    out["loss_fwd_B1024"] = {"ms": med, "gbs": 1252.0 * 1024 * 243 / med / 1e6}
+    out["loss_fwd_B1024"] = {"ms": med, "gbs": 1252.0 * nfr / med / 1e6, "gframes_s": nfr / med / 1e6}
+    hg = hyp.clone().requires_grad_()
+    sg = sc.clone().requires_grad_()
+    terms = ops.loss_terms(hg, sg, y, w, False, 0.1, 2.0, 0.5)[0]
+    gt = torch.zeros(8, device=dev)
+    gt[4] = 1.0
+    med, best = timeit(lambda: torch.autograd.grad(terms, (hg, sg), gt, retain_graph=True))
+    out["loss_bwd_B1024"] = {"ms": med, "gbs": 2292.0 * nfr / med / 1e6, "gframes_s": nfr / med / 1e6}
+    med, best = timeit(lambda: ops.wta_fwd(hyp, y, w, False))
+    out["wta_fwd_B1024"] = {"ms": med, "gbs": (204.0 * 6 + 12) * nfr / med / 1e6}
+    for mode, nm, byt in ((0, "weighted_ave", 204.0 * 6 + 20), (1, "best_score", 204.0 * 2 + 28), (2, "oracle", 204.0 * 8 + 12)):
+        med, best = timeit(lambda: ops.aggregate(hyp, sc, y, mode))
+        out[f"aggregate_{nm}_B1024"] = {"ms": med, "gbs": byt * nfr / med / 1e6}
+    pred = ops.aggregate(hyp, sc, None, 0)[0]
+    med, best = timeit(lambda: ops.mpjpe(pred, y))
+    out["mpjpe_B1024"] = {"ms": med, "gbs": 408.0 * nfr / med / 1e6}
+    # the same rows on the host cores with the CPU oracle (reference algorithm), bounded samples
+    if "--cpu" in sys.argv:
+        import time
+        from oracle import manipose_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu = {}
+        nb = 103   # 103 clips x 5 x 243 = 125,145 poses (1/8 of config 2)
+        rc, bc = rot[:nb * k * t].cpu(), bones[:nb].cpu().unsqueeze(-1)
+        t0 = time.perf_counter(); O.pose_decoder(rc, bc, torch.zeros(nb * k * t, 3)); dt = time.perf_counter() - t0
+        cpu["decoder_fwd"] = {"s": dt, "mposes_s": nb * k * t / dt / 1e6, "sample": f"{nb * k * t} poses"}
+        hc, scc, yc = hyp[:128].cpu(), sc[:128].cpu().unsqueeze(-1), y[:128].cpu()
+        t0 = time.perf_counter(); O.training_loss(hc, scc, yc); dt = time.perf_counter() - t0
+        cpu["loss_fwd"] = {"s": dt, "mframes_s": 128 * 243 / dt / 1e6, "sample": "128 clips x 243 frames"}
+        hcg = hc.clone().requires_grad_()
+        t0 = time.perf_counter(); O.training_loss(hcg, scc, yc)[0].backward(); dt = time.perf_counter() - t0
+        cpu["loss_fwd_bwd"] = {"s": dt, "mframes_s": 128 * 243 / dt / 1e6, "sample": "128 clips x 243 frames"}
+        out["cpu_oracle"] = {"threads": torch.get_num_threads(), **cpu}
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     print(json.dumps({"clips": clips, "tokens": m, "peaks": {k: peaks.get(k) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained")}, "kernels": out}, indent=1))
 

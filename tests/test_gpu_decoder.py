@@ -132,15 +132,35 @@ def test_full_size_properties():
     assert torch.equal(poses[whole].cpu(), O.pose_decoder_ieee(rot[whole].cpu(), bones[c0:c0 + 2].cpu().unsqueeze(-1), torch.zeros(2 * k * t, 3)))
 
 
-def test_rot_rep_dim_errors_match_the_reference():
+def test_rot_rep_dim_4_and_errors_match_the_reference():
+    """rot_rep_dim = 4 (compute_rotation_matrix_from_ortho4d, rotation_tools.py:60-116): reference fixture, IEEE restatement,
+    backward vs the oracle's autograd; any other dimension fails like the reference's assert (pose_decoder.py:27-30)."""
     import manipose_b200 as mb
     from manipose_b200 import ops
+    g = _load("decoder.pt")
+    poses, _ = ops.decoder_fwd(g["rot4d"].cuda(), g["bones"].reshape(4, 16).cuda(), None, None, 4, 1, 5, rot_rep_dim=4)
+    assert _rel(poses.cpu(), g["poses_4d"]) <= RTOL_TIGHT
+    assert torch.equal(poses.cpu(), O.pose_decoder_ieee(g["rot4d"], g["bones"], torch.zeros(20, 3)))
+    gen = torch.Generator().manual_seed(11)
+    n_clips, t = 3, 37
+    n = n_clips * t
+    rot = torch.randn(n, 17, 4, generator=gen)
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, 1, generator=gen)
+    root = torch.randn(n, 3, generator=gen)
+    gout = torch.randn(n, 17, 3, generator=gen)
+    assert torch.equal(ops.decoder_fwd(rot.cuda(), bones.reshape(n_clips, 16).cuda(), root.cuda(), None, n_clips, 1, t, rot_rep_dim=4)[0].cpu(),
+                       O.pose_decoder_ieee(rot, bones, root))
+    r_ref, b_ref = rot.clone().requires_grad_(), bones.clone().requires_grad_()
+    O.pose_decoder(r_ref, b_ref, root, rot_rep_dim=4).backward(gout)
+    dec = mb.PoseDecoder(mb.h36m17_skeleton(), rot_rep_dim=4)
+    r, b = rot.cuda().requires_grad_(), bones.cuda().requires_grad_()
+    dec(r, b, root.cuda()).backward(gout.cuda())
+    torch.testing.assert_close(r.grad.cpu(), r_ref.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(b.grad.cpu(), b_ref.grad, rtol=1e-4, atol=1e-4)
     with pytest.raises(AssertionError, match="Unsupported rotations representation dimension"):
         mb.PoseDecoder(mb.h36m17_skeleton(), rot_rep_dim=5)
     with pytest.raises(AssertionError):
         ops.decoder_fwd(torch.zeros(1, 17, 5, device="cuda"), torch.zeros(1, 16, device="cuda"), None, None, 1, 1, 1, rot_rep_dim=5)
-    with pytest.raises(NotImplementedError):
-        ops.decoder_fwd(torch.zeros(1, 17, 4, device="cuda"), torch.zeros(1, 16, device="cuda"), None, None, 1, 1, 1, rot_rep_dim=4)
 
 
 @pytest.mark.parametrize("n_clips,k,t", [(2, 5, 27), (3, 1, 40)])

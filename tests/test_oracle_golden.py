@@ -35,6 +35,8 @@ def test_decoder_ieee_restatement_is_pinned_to_the_reference():
         assert float((got[~ok] - want[~ok]).abs().max()) <= 1e-5
     ident = torch.tensor([1.0, 0, 0, 0, 1.0, 0]).expand(1, 17, 6).contiguous()
     assert torch.equal(O.pose_decoder_ieee(ident, g["kat_bones"], torch.zeros(1, 3)), g["kat_pose_identity"])
+    got4 = O.pose_decoder_ieee(g["rot4d"], g["bones"], torch.zeros(20, 3))        # 4-D representation (rotation_tools.py:60-116)
+    assert float((got4 - g["poses_4d"]).abs().max() / g["poses_4d"].abs().max()) <= 1e-6
 
 
 def test_decoder_known_answers():
