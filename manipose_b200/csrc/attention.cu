@@ -380,6 +380,234 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ temporal, tcgen05, persistent
+// One persistent CTA per SM walks (clip, token, head) items.  Both 128-query tiles of a head share ONE load of K and V; two groups of
+// four softmax warps work on the two tiles at the same time (S0 / S1 in the two halves of TMEM), and the Q / K of the NEXT item
+// are fetched by TMA while the current item is in its softmax.  Three 64 KB shared-memory regions rotate through the roles
+// {Q0 Q1 K of the current item, later P0 and the O0 staging tile} -> {P1 and the O1 staging tile} -> {Q0 Q1 K of the next item}.
+constexpr int kTc2Threads = 288;   // 2 x 4 softmax warps + 1 TMA / MMA warp
+
+template <typename D>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
+                         int n_frames, int n_tok, int C, int n_heads, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sv = smem + 3 * 65536;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * 65536 + 32768);
+  uint64_t* qk_full = bars + 0;    // [2] Q0 Q1 K of item n landed (parity n / 2 of barrier n & 1)
+  uint64_t* v_full = bars + 2;     // V of item n landed
+  uint64_t* s_full = bars + 3;     // [2] S_g complete
+  uint64_t* p_full = bars + 5;     // [2] P_g written by the 128 threads of group g
+  uint64_t* o_full = bars + 7;     // [2] O_g complete
+  uint64_t* g_done = bars + 9;     // [2] group g has drained O_g and its output store has read shared memory
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tp = (n_frames + 31) & ~31;
+  const int m_tiles = (n_frames + 127) / 128;      // 1 or 2
+
+  if (warp == 8 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_kv);
+    ptx::prefetch_tmap(&tm_o);
+    ptx::mbar_init(&qk_full[0], 1);
+    ptx::mbar_init(&qk_full[1], 1);
+    ptx::mbar_init(v_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&s_full[g], 1);
+      ptx::mbar_init(&p_full[g], 128);
+      ptx::mbar_init(&o_full[g], 1);
+      ptx::mbar_init(&g_done[g], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  auto decode = [&](int item, int& clip, int& tok, int& head) {
+    head = item % n_heads;
+    item /= n_heads;
+    tok = item % n_tok;
+    clip = item / n_tok;
+  };
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t qk_bytes = (uint32_t)(m_tiles * 16384 + Tp * 128);
+      auto load_qk = [&](int item, uint8_t* region, uint64_t* bar) {
+        int clip, tok, head;
+        decode(item, clip, tok, head);
+        ptx::mbar_expect_tx(bar, qk_bytes);
+        for (int g = 0; g < m_tiles; ++g) ptx::tma_load_4d(region + g * 16384, &tm_q, bar, head * 64, tok, g * 128, clip);
+        ptx::tma_load_4d(region + 32768, &tm_kv, bar, C + head * 64, tok, 0, clip);
+      };
+      auto load_v = [&](int item) {
+        int clip, tok, head;
+        decode(item, clip, tok, head);
+        ptx::mbar_expect_tx(v_full, (uint32_t)Tp * 128);
+        ptx::tma_load_4d(sv, &tm_kv, v_full, 2 * C + head * 64, tok, 0, clip);
+      };
+      const uint32_t idesc_s = ptx::umma_idesc_16(128, Tp, D::kUmmaFmt);
+      const uint32_t idesc_o = ptx::umma_idesc_16_bmn(128, 64, D::kUmmaFmt);
+      int cur = 0, p1 = 1, nxt = 2;
+      uint32_t n = 0;
+      int item = blockIdx.x;
+      if (item < n_items) {
+        load_qk(item, smem + cur * 65536, &qk_full[0]);
+        load_v(item);
+      }
+      for (; item < n_items; item += gridDim.x, ++n) {
+        const uint32_t par = n & 1, qpar = (n >> 1) & 1;
+        uint8_t* rc = smem + cur * 65536;
+        uint8_t* rp = smem + p1 * 65536;
+        if (n > 0) {
+          // both groups have drained item n-1: TMEM, the V buffer and the regions of P0 / P1 are free again
+          for (int g = 0; g < m_tiles; ++g) ptx::mbar_wait(&g_done[g], par ^ 1);
+          load_v(item);
+        }
+        ptx::mbar_wait(&qk_full[par], qpar);
+        ptx::tc_fence_after();
+        {
+          const uint64_t db = ptx::umma_desc_sw128(smem_u32(rc + 32768));
+          for (int g = 0; g < m_tiles; ++g) {
+            const uint64_t da = ptx::umma_desc_sw128(smem_u32(rc + g * 16384));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+            ptx::umma_commit(&s_full[g]);
+          }
+        }
+        if (item + (int)gridDim.x < n_items) load_qk(item + gridDim.x, smem + nxt * 65536, &qk_full[par ^ 1]);
+        ptx::mbar_wait(v_full, par);
+        for (int g = 0; g < m_tiles; ++g) {
+          ptx::mbar_wait(&p_full[g], par);
+          ptx::tc_fence_after();
+          const uint32_t pa = smem_u32(g == 0 ? rc : rp), va = smem_u32(sv);
+          const int ksteps = Tp / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = ptx::umma_desc_sw128(pa + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32));
+            const uint64_t db = ptx::umma_desc_mn_sw128(va + (uint32_t)(k * 2048));
+            ptx::umma_f16(tmem_base + (uint32_t)(g * 256), da, db, idesc_o, k != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&o_full[g]);
+        }
+        const int t = cur;
+        cur = nxt;
+        nxt = p1;
+        p1 = t;
+      }
+    }
+  } else {
+    const int g = warp >> 2;                            // softmax group = query tile
+    if (g < m_tiles) {
+      const int row = threadIdx.x & 127;                // tile-local query row <-> TMEM lane
+      const uint32_t sw = (uint32_t)(row & 7);
+      const uint32_t t_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g * 256);
+      const float scale_log2 = 0.125f * kLog2e;
+      const int n_chunks = Tp / 32;
+      int cur = 0, p1 = 1, nxt = 2;
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const uint32_t par = n & 1;
+        uint8_t* region = smem + (g == 0 ? cur : p1) * 65536;   // P_g, then the O_g staging tile
+        // S_g is complete; P0 overwrites Q and K, so group 0 also needs S1 (the other reader of K) to be complete
+        ptx::mbar_wait(&s_full[g], par);
+        if (g == 0 && m_tiles == 2) ptx::mbar_wait(&s_full[1], par);
+        ptx::tc_fence_after();
+        float mx = -INFINITY;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          if ((c + 1) * 32 <= n_frames) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < n_frames) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+        }
+        const float ms = -mx * scale_log2;
+        float sum = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, ms));
+            p[i] = (c * 32 + i < n_frames) ? e : 0.f;
+            sum += p[i];
+          }
+          uint8_t* prow = region + (size_t)(c >> 1) * 16384 + (size_t)row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = D::pack2(p[8 * q + 0], p[8 * q + 1]);
+            o.y = D::pack2(p[8 * q + 2], p[8 * q + 3]);
+            o.z = D::pack2(p[8 * q + 4], p[8 * q + 5]);
+            o.w = D::pack2(p[8 * q + 6], p[8 * q + 7]);
+            *reinterpret_cast<uint4*>(prow + (((uint32_t)((c & 1) * 4 + q) ^ sw) << 4)) = o;
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&p_full[g]);
+        // ---- O_g
+        ptx::mbar_wait(&o_full[g], par);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / sum;
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(t_row, r0);
+        ptx::tmem_ld32(t_row + 32u, r1);
+        ptx::tmem_ld_wait();
+        uint8_t* orow = region + (size_t)row * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+          const int b = (q & 3) * 8;
+          uint4 o;
+          o.x = D::pack2(__uint_as_float(r[b + 0]) * inv, __uint_as_float(r[b + 1]) * inv);
+          o.y = D::pack2(__uint_as_float(r[b + 2]) * inv, __uint_as_float(r[b + 3]) * inv);
+          o.z = D::pack2(__uint_as_float(r[b + 4]) * inv, __uint_as_float(r[b + 5]) * inv);
+          o.w = D::pack2(__uint_as_float(r[b + 6]) * inv, __uint_as_float(r[b + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (row == 0) {
+          int clip, tok, head;
+          decode(item, clip, tok, head);
+          ptx::tma_store_4d(&tm_o, region, head * 64, tok, g * 128, clip);
+          ptx::bulk_commit();
+          ptx::bulk_wait_read<0>();
+          ptx::mbar_arrive(&g_done[g]);
+        }
+        const int t = cur;
+        cur = nxt;
+        nxt = p1;
+        p1 = t;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------ spatial, tcgen05
 // head_dim 64, n_tok <= 32.  G = (128 / n_tok) * n_tok consecutive tokens (7 frames of 17 joints) form one 128-row tile: the same
 // rows are the queries and the keys, S = Q K^T is a [128 x 128] tcgen05 MMA of which only the block diagonal (same frame) is
@@ -661,6 +889,18 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       MP_CHECK(get_tmap_track(&to, out, n_clips, n_frames, n_tok, C, 128, dtype));
       const int64_t ctas = n_clips * n_tok * n_heads * m_tiles;
       MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+      static const bool one_shot = getenv("MANIPOSE_ATTN_TC1") != nullptr;   // A/B switch: one CTA per (head, query tile)
+      if (!one_shot) {
+        const int n_items = (int)(n_clips * n_tok * n_heads);
+        const int smem_p = 3 * 65536 + 32768 + 256;
+        const int grid = n_items < sm_count() ? n_items : sm_count();
+        auto launch_p = [&](auto kernel) {
+          cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+          kernel<<<grid, kTc2Threads, smem_p, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
+        };
+        if (bf) launch_p(attn_temporal_tc2_kernel<Bf16>); else launch_p(attn_temporal_tc2_kernel<Fp16>);
+        return check_launch("attn_temporal_tc2_kernel");
+      }
       const int smem_tc = 98304 + 64;
       auto launch_tc = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
