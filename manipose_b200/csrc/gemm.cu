@@ -51,7 +51,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 template <int BN, int EPI, typename D>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K, int dbg) {
+              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   constexpr bool kRes = (EPI == MP_EPI_RESIDUAL);
   constexpr int kBoxCols = kRes ? 32 : 64;                 // fp32 vs 16-bit output: 128 bytes per row either way
@@ -148,7 +148,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            if (!(dbg & 2)) ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[stage]);                   // frees the stage when these MMAs have read it
           if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -194,7 +194,6 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int b = grp; b < kBoxes; b += 2, ++i) {
-        if (!kRes && (dbg & 1)) continue;        // measurement knob: drain nothing
         const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
         const int col0 = n_blk * BN + b * kBoxCols;
@@ -373,8 +372,7 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMa
   }
   const int tiles = (N / BN) * ((M + kBM - 1) / kBM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  static const int dbg = getenv("MANIPOSE_DBG") ? atoi(getenv("MANIPOSE_DBG")) : 0;
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K, dbg);
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K);
   return check_launch("linear_kernel");
 }
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ void init_bars(const PairBars& b) {
 template <int EPI, typename D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-                   const float* __restrict__ bias, int M, int N, int K, int dbg) {
+                   const float* __restrict__ bias, int M, int N, int K) {
   constexpr int kStages = 5;
   constexpr int kStageBytes = kABytes + kWHalfBytes;     // 32 KB per CTA per stage
   constexpr int BN = 256;
@@ -161,7 +161,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint64_t db = ptx::umma_desc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            if (!(dbg & 2)) ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           ptx::umma_commit_pair(&bars.empty[stage]);
           if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[acc]);
           if (++stage == kStages) {
@@ -193,7 +193,6 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int b = grp; b < kBoxes; b += 2, ++i) {
-        if (dbg & 1) continue;                   // measurement knob: drain nothing
         const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
         const int col0 = n_blk * BN + b * 64;
@@ -630,8 +629,7 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
   const int grid = pair_grid(tiles);
   auto launch = [&](auto kernel) -> int {
     MP_CHECK(set_smem(kernel, kPairLinearSmem));
-    static const int dbg = getenv("MANIPOSE_DBG") ? atoi(getenv("MANIPOSE_DBG")) : 0;
-    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K, dbg);
+    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K);
     return check_launch("pair_linear_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
