@@ -14,7 +14,7 @@
 
 namespace mp {
 
-int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type);  // gemm.cu
+int get_tmap_clip_rows(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t rows_per_clip, int64_t cols, int box_rows, int type);  // gemm.cu
 int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type);  // gemm.cu
 
 namespace {
@@ -631,11 +631,12 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 // kept.  The softmax thread of row i reads just the 32-column chunks that contain its frame's columns, writes the (mostly zero)
 // 16-bit P row over the dead Q / K tiles, and O = P V uses V as the MN-major operand.  48 KB of shared memory and 128 TMEM
 // columns per CTA: four CTAs per SM overlap loads, softmax and stores.  Rows [G, 128) of a tile belong to the next tile and are
-// not stored.
+// not stored.  Tiles are laid out per CLIP (3-D tensor maps clip the last tile of a clip), so a clip's result does not depend on
+// which other clips share its micro-batch.
 template <typename D>
 __global__ void __launch_bounds__(kTcThreads, 4)
-attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_o, int64_t n_rows, int n_tok, int C,
-                       int n_heads, int G) {
+attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_o, int n_rows, int n_tok, int C,
+                       int n_heads, int G, int tiles_per_clip) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sq = smem;                 // [128 x 64] queries; later P k-block 0
@@ -651,8 +652,9 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x % n_heads;
-  const int tile = blockIdx.x / n_heads;
-  const int row0 = tile * G;          // multiple of n_tok: frame f of the tile owns tile-local columns [f * n_tok, (f + 1) * n_tok)
+  const int tile = (blockIdx.x / n_heads) % tiles_per_clip;
+  const int clip = blockIdx.x / (n_heads * tiles_per_clip);
+  const int row0 = tile * G;          // clip-relative, multiple of n_tok: frame f of the tile owns tile-local columns [f * n_tok, (f + 1) * n_tok)
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tm_in);
@@ -676,10 +678,10 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
   if (warp == 4) {
     if (lane == 0) {
       ptx::mbar_expect_tx(bar_qk, 32768);
-      ptx::tma_load_2d(sq, &tm_in, bar_qk, head * 64, row0);
-      ptx::tma_load_2d(sk, &tm_in, bar_qk, C + head * 64, row0);
+      ptx::tma_load_3d(sq, &tm_in, bar_qk, head * 64, row0, clip);
+      ptx::tma_load_3d(sk, &tm_in, bar_qk, C + head * 64, row0, clip);
       ptx::mbar_expect_tx(bar_v, 16384);
-      ptx::tma_load_2d(sv, &tm_in, bar_v, 2 * C + head * 64, row0);
+      ptx::tma_load_3d(sv, &tm_in, bar_v, 2 * C + head * 64, row0, clip);
       ptx::mbar_wait(bar_qk, 0);
       ptx::tc_fence_after();
       {
@@ -714,8 +716,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     const int a = (row / n_tok) * n_tok;
     int b = a + n_tok;
     if (b > 128) b = 128;
-    if ((int64_t)row0 + b > n_rows) b = (int)(n_rows - row0);
-    const bool live = (int64_t)row0 + row < n_rows && b > a;
+    if (row0 + b > n_rows) b = n_rows - row0;       // n_rows = rows of one clip
+    const bool live = row0 + row < n_rows && b > a;
     // warp-uniform range of 32-column chunks that covers the windows of rows [32 warp, 32 warp + 32)
     const int c_lo = ((32 * warp) / n_tok * n_tok) / 32;
     int c_hi = (((32 * warp + 31) / n_tok + 1) * n_tok + 31) / 32;
@@ -789,7 +791,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     ptx::fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 0) {
-      ptx::tma_store_2d(&tm_o, smem, head * 64, row0);     // box of G rows: rows [G, 128) belong to the next tile
+      ptx::tma_store_3d(&tm_o, smem, head * 64, row0, clip);   // box of G rows: rows [G, 128) belong to the next tile
       ptx::bulk_commit();
       ptx::bulk_wait_read<0>();
     }
@@ -945,16 +947,17 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   static const bool legacy_s = getenv("MANIPOSE_ATTN_MMA_SYNC") != nullptr;
   if (hd == 64 && !legacy_s) {
     const int G = (128 / n_tok) * n_tok;
-    const int64_t n_rows = n_clips * n_frames * n_tok;
-    const int64_t tiles = (n_rows + G - 1) / G;
-    MP_REQUIRE(tiles * n_heads < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+    const int64_t rows_per_clip = n_frames * n_tok;
+    const int64_t tiles_per_clip = (rows_per_clip + G - 1) / G;
+    MP_REQUIRE(n_clips * tiles_per_clip * n_heads < ((int64_t)1 << 31) && rows_per_clip < ((int64_t)1 << 30), MP_EINVAL, "mp_attention: too many sequences");
     CUtensorMap tin, to;
-    MP_CHECK(get_tmap(&tin, qkv, n_rows, 3 * C, 128, dtype));
-    MP_CHECK(get_tmap(&to, out, n_rows, C, G, dtype));
+    MP_CHECK(get_tmap_clip_rows(&tin, qkv, n_clips, rows_per_clip, 3 * C, 128, dtype));
+    MP_CHECK(get_tmap_clip_rows(&to, out, n_clips, rows_per_clip, C, G, dtype));
     const int smem_tc = 49152 + 64;
     auto launch_tc = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
-      kernel<<<(unsigned)(tiles * n_heads), kTcThreads, smem_tc, s>>>(tin, to, n_rows, n_tok, C, n_heads, G);
+      kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s>>>(tin, to, (int)rows_per_clip, n_tok, C, n_heads, G,
+                                                                                       (int)tiles_per_clip);
     };
     if (bf) launch_tc(attn_spatial_tc_kernel<Bf16>); else launch_tc(attn_spatial_tc_kernel<Fp16>);
     return check_launch("attn_spatial_tc_kernel");

@@ -355,6 +355,24 @@ int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n
   return MP_OK;
 }
 
+// 3-D view [clips][rows_per_clip][cols] of a 16-bit activation with a box of `box_rows` rows x 64 columns of ONE clip: rows past the end
+// of the clip are zero-filled on load and dropped on store, so a tile never touches another clip (results do not depend on how clips
+// are grouped into micro-batches).
+int get_tmap_clip_rows(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t rows_per_clip, int64_t cols, int box_rows, int type) {
+  EncodeTiledFn fn = encode_fn();
+  MP_REQUIRE(fn != nullptr, MP_EDEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_clip, (cuuint64_t)n_clips};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows_per_clip * cols * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = type == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MP_REQUIRE(r == CUDA_SUCCESS, MP_EINVAL, "cuTensorMapEncodeTiled(clip rows) failed with CUresult %d (clips=%lld rows=%lld cols=%lld box=%d)", (int)r,
+             (long long)n_clips, (long long)rows_per_clip, (long long)cols, box_rows);
+  return MP_OK;
+}
+
 int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream);  // gemm2.cu
 
 namespace {
