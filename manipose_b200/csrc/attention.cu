@@ -382,11 +382,10 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 
 // ------------------------------------------------------------------------------------------------------ temporal, tcgen05, persistent
 // One persistent CTA per SM walks (clip, token, head) items.  Both 128-query tiles of a head share ONE load of K and V; two groups of
-// EIGHT softmax warps work on the two tiles at the same time (S0 / S1 in the two halves of TMEM; within a group two threads share
-// a query row, one per half of the keys, so four softmax warps per scheduler hide the MUFU / TMEM latencies), and the Q / K of
-// the NEXT item are fetched by TMA while the current item is in its softmax.  Three 64 KB shared-memory regions rotate through
-// the roles {Q0 Q1 K of the current item, later P0 and the O0 staging tile} -> {P1 and the O1 staging tile} -> {Q0 Q1 K of the next}.
-constexpr int kTc2Threads = 544;   // 2 x 8 softmax warps + 1 TMA / MMA warp
+// four softmax warps work on the two tiles at the same time (S0 / S1 in the two halves of TMEM), and the Q / K of the NEXT item
+// are fetched by TMA while the current item is in its softmax.  Three 64 KB shared-memory regions rotate through the roles
+// {Q0 Q1 K of the current item, later P0 and the O0 staging tile} -> {P1 and the O1 staging tile} -> {Q0 Q1 K of the next item}.
+constexpr int kTc2Threads = 288;   // 2 x 4 softmax warps + 1 TMA / MMA warp
 
 template <typename D>
 __global__ void __launch_bounds__(kTc2Threads, 1)
@@ -395,12 +394,11 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sv = smem + 3 * 65536;
-  float* xchg = reinterpret_cast<float*>(smem + 3 * 65536 + 32768);   // [2 groups][2 halves][128 rows]: row max, later row sum
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * 65536 + 32768 + 2048);
-  uint64_t* qk_full = bars + 0;    // [2] Q0 Q1 K of item n landed (phase n / 2 of barrier n & 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * 65536 + 32768);
+  uint64_t* qk_full = bars + 0;    // [2] Q0 Q1 K of item n landed (parity n / 2 of barrier n & 1)
   uint64_t* v_full = bars + 2;     // V of item n landed
   uint64_t* s_full = bars + 3;     // [2] S_g complete
-  uint64_t* p_full = bars + 5;     // [2] P_g written by the 256 threads of group g
+  uint64_t* p_full = bars + 5;     // [2] P_g written by the 128 threads of group g
   uint64_t* o_full = bars + 7;     // [2] O_g complete
   uint64_t* g_done = bars + 9;     // [2] group g has drained O_g and its output store has read shared memory
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
@@ -409,7 +407,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   const int Tp = (n_frames + 31) & ~31;
   const int m_tiles = (n_frames + 127) / 128;      // 1 or 2
 
-  if (warp == 16 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tm_q);
     ptx::prefetch_tmap(&tm_kv);
     ptx::prefetch_tmap(&tm_o);
@@ -418,7 +416,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     ptx::mbar_init(v_full, 1);
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&s_full[g], 1);
-      ptx::mbar_init(&p_full[g], 256);
+      ptx::mbar_init(&p_full[g], 128);
       ptx::mbar_init(&o_full[g], 1);
       ptx::mbar_init(&g_done[g], 1);
     }
@@ -440,7 +438,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     clip = item / n_tok;
   };
 
-  if (warp == 16) {
+  if (warp == 8) {
     if (lane == 0) {
       const uint32_t qk_bytes = (uint32_t)(m_tiles * 16384 + Tp * 128);
       auto load_qk = [&](int item, uint8_t* region, uint64_t* bar) {
@@ -507,18 +505,13 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       }
     }
   } else {
-    const int g = warp >> 3;                            // softmax group = query tile
+    const int g = warp >> 2;                            // softmax group = query tile
     if (g < m_tiles) {
-      const int half = (warp >> 2) & 1;                 // which half of the key chunks (and of the output columns) this thread owns
-      const int row = 32 * (warp & 3) + lane;           // tile-local query row <-> TMEM lane
+      const int row = threadIdx.x & 127;                // tile-local query row <-> TMEM lane
       const uint32_t sw = (uint32_t)(row & 7);
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g * 256);
       const float scale_log2 = 0.125f * kLog2e;
       const int n_chunks = Tp / 32;
-      const int c_mid = (n_chunks + 1) >> 1;
-      const int c_lo = half == 0 ? 0 : c_mid, c_hi = half == 0 ? c_mid : n_chunks;
-      float* my_x = xchg + (g * 2 + half) * 128 + row;
-      const float* other_x = xchg + (g * 2 + (half ^ 1)) * 128 + row;
       int cur = 0, p1 = 1, nxt = 2;
       uint32_t n = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
@@ -528,43 +521,21 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         ptx::mbar_wait(&s_full[g], par);
         if (g == 0 && m_tiles == 2) ptx::mbar_wait(&s_full[1], par);
         ptx::tc_fence_after();
-        float mx = -INFINITY;
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
-          ptx::tmem_ld_wait();
-          if ((c + 1) * 32 <= n_frames) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < n_frames) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-        }
-        *my_x = mx;
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-        mx = fmaxf(mx, *other_x);
-        const float ms = -mx * scale_log2;
-        float sum = 0.f;
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
-          ptx::tmem_ld_wait();
+        // ---- softmax in ONE pass over the S row (reading TMEM is the limiter: 64 B/clk per SM).  The shift is the maximum of the
+        // first 32 keys, a lower bound of the row maximum: P = 2^(scale (s - shift)) is then >= 1 at the true maximum, and the
+        // normalisation by the row sum removes the shift again.  If some exponent leaves the range that is safe for the 16-bit P
+        // (kSafeExp), the row is redone with its true maximum (rare; per thread, no divergence cost for the others).
+        constexpr float kSafeExp = D::kUmmaFmt == 1 ? 60.0f : 13.0f;   // bf16 has the fp32 exponent range, fp16 tops out at 2^16
+        float sum = 0.f, emax = -INFINITY, ms;
+        auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& e_hi, float& acc) {
           float p[32];
-          if ((c + 1) * 32 <= n_frames) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              p[i] = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, ms));
-              sum += p[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, ms));
-              p[i] = (c * 32 + i < n_frames) ? e : 0.f;
-              sum += p[i];
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
+            const bool live = (c + 1) * 32 <= n_frames || c * 32 + i < n_frames;
+            e_hi = fmaxf(e_hi, live ? e : -INFINITY);
+            p[i] = live ? fast_exp2(e) : 0.f;
+            acc += p[i];
           }
           uint8_t* prow = region + (size_t)(c >> 1) * 16384 + (size_t)row * 128;
 #pragma unroll
@@ -576,33 +547,61 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             o.w = D::pack2(p[8 * q + 6], p[8 * q + 7]);
             *reinterpret_cast<uint4*>(prow + (((uint32_t)((c & 1) * 4 + q) ^ sw) << 4)) = o;
           }
+        };
+        {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row, r);
+          ptx::tmem_ld_wait();
+          float m0 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < n_frames) m0 = fmaxf(m0, __uint_as_float(r[i]));
+          ms = -m0 * scale_log2;
+          emit(r, 0, ms, emax, sum);
+          for (int c = 1; c < n_chunks; ++c) {
+            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            emit(r, c, ms, emax, sum);
+          }
+        }
+        if (emax > kSafeExp) {
+          ms -= emax;                     // shift by the true row maximum: every exponent <= 0
+          sum = 0.f;
+          float unused = -INFINITY;
+          uint32_t r[32];
+          for (int c = 0; c < n_chunks; ++c) {
+            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            emit(r, c, ms, unused, sum);
+          }
         }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&p_full[g]);
-        // ---- O_g: the two threads of a row combine their partial sums and each drains 32 of the 64 output columns
+        // ---- O_g
         ptx::mbar_wait(&o_full[g], par);
         ptx::tc_fence_after();
-        *my_x = sum;                                   // every thread of the group has read the row maxima long ago (p_full needs all 256)
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-        const float inv = 1.0f / (sum + *other_x);
-        uint32_t r0[32];
-        ptx::tmem_ld32(t_row + (uint32_t)(half * 32), r0);
+        const float inv = 1.0f / sum;
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(t_row, r0);
+        ptx::tmem_ld32(t_row + 32u, r1);
         ptx::tmem_ld_wait();
         uint8_t* orow = region + (size_t)row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+          const int b = (q & 3) * 8;
           uint4 o;
-          o.x = D::pack2(__uint_as_float(r0[8 * q + 0]) * inv, __uint_as_float(r0[8 * q + 1]) * inv);
-          o.y = D::pack2(__uint_as_float(r0[8 * q + 2]) * inv, __uint_as_float(r0[8 * q + 3]) * inv);
-          o.z = D::pack2(__uint_as_float(r0[8 * q + 4]) * inv, __uint_as_float(r0[8 * q + 5]) * inv);
-          o.w = D::pack2(__uint_as_float(r0[8 * q + 6]) * inv, __uint_as_float(r0[8 * q + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + (((uint32_t)(half * 4 + q) ^ sw) << 4)) = o;
+          o.x = D::pack2(__uint_as_float(r[b + 0]) * inv, __uint_as_float(r[b + 1]) * inv);
+          o.y = D::pack2(__uint_as_float(r[b + 2]) * inv, __uint_as_float(r[b + 3]) * inv);
+          o.z = D::pack2(__uint_as_float(r[b + 4]) * inv, __uint_as_float(r[b + 5]) * inv);
+          o.w = D::pack2(__uint_as_float(r[b + 6]) * inv, __uint_as_float(r[b + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
         }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-        if (half == 0 && row == 0) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (row == 0) {
           int clip, tok, head;
           decode(item, clip, tok, head);
           ptx::tma_store_4d(&tm_o, region, head * 64, tok, g * 128, clip);
@@ -911,7 +910,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       static const bool one_shot = getenv("MANIPOSE_ATTN_TC1") != nullptr;   // A/B switch: one CTA per (head, query tile)
       if (!one_shot) {
         const int n_items = (int)(n_clips * n_tok * n_heads);
-        const int smem_p = 3 * 65536 + 32768 + 2048 + 256;
+        const int smem_p = 3 * 65536 + 32768 + 256;
         const int grid = n_items < sm_count() ? n_items : sm_count();
         auto launch_p = [&](auto kernel) {
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);

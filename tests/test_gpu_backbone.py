@@ -147,6 +147,28 @@ def test_attention_vs_fp32(n_clips, n_frames, n_tok, c, temporal, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_temporal_attention_outlier_keys_take_the_exact_softmax_path(dtype):
+    """The single-pass softmax shifts by the maximum of the first 32 keys; a late key with a much larger score forces the guarded
+    redo with the true row maximum (attention.cu).  Also covers a row whose first keys are the outliers (large negative exponents)."""
+    from manipose_b200 import ops
+    td = DT[dtype]
+    n_clips, n_frames, n_tok, c = 1, 243, 17, 512
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n = n_clips * n_frames * n_tok
+    qkv = torch.randn(n, 3 * c, generator=gen, device="cuda")
+    v = qkv.view(n_clips, n_frames, n_tok, 3, c)
+    v[:, 200, :, 1] *= 12.0      # keys of frame 200: scores ~12x larger than the rest (exponent > 13 for many rows)
+    v[:, 3, 5:9, 1] *= 20.0      # and early outliers on some tracks
+    qkv = qkv.to(td)
+    out = torch.full((n, c), float("nan"), dtype=td, device="cuda")
+    ops.attention(qkv, out, n_clips, n_frames, n_tok, c, 8, 1)
+    ref = _attn_ref(qkv, n_clips, n_frames, n_tok, c, 8, True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), ref, rtol=2 * RTOL[dtype], atol=2 * RTOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("c", [512, 128])
 def test_layernorm_family(c, dtype):
     from manipose_b200 import ops
