@@ -524,7 +524,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         // ---- softmax in ONE pass over the S row (reading TMEM is the limiter: 64 B/clk per SM).  The shift is the maximum of the
         // first 32 keys, a lower bound of the row maximum: P = 2^(scale (s - shift)) is then >= 1 at the true maximum, and the
         // normalisation by the row sum removes the shift again.  If some exponent leaves the range that is safe for the 16-bit P
-        // (kSafeExp), the row is redone with its true maximum (rare; per thread, no divergence cost for the others).
+        // (kSafeExp), the warp redoes its rows with their true maxima (rare).
         constexpr float kSafeExp = D::kUmmaFmt == 1 ? 60.0f : 13.0f;   // bf16 has the fp32 exponent range, fp16 tops out at 2^16
         float sum = 0.f, emax = -INFINITY, ms;
         auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& e_hi, float& acc) {
@@ -564,7 +564,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             emit(r, c, ms, emax, sum);
           }
         }
-        if (emax > kSafeExp) {
+        if (__any_sync(0xffffffffu, emax > kSafeExp)) {   // tcgen05.ld is warp-collective: the whole warp redoes its 32 rows
           ms -= emax;                     // shift by the true row maximum: every exponent <= 0
           sum = 0.f;
           float unused = -INFINITY;
