@@ -203,6 +203,39 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
 /* fp32 -> 16-bit (weight shadows refreshed by the host wrapper after optimizer.step()). */
 int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stream_t stream);
 
+/* ---- backward (training) entry points -------------------------------------------------------------------------------
+ * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
+ * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:
+ *   dgrad  dX[M,K] = dY[M,N] W[N,K]      -> mp_linear(A = dY, W = transposed 16-bit shadow [K,N])
+ *   wgrad  dW[N,K] += dY^T X             -> mp_linear(A = dY^T [N,Mpad], W = X^T [K,Mpad], resid = Y = dW, MP_EPI_RESIDUAL)
+ * with the operand transposes (and the bias gradient, a column sum of dY) done by mp_transpose16. */
+
+/* LayerNorm backward: dx = LN'(x; gamma, eps)(dy) [+ dres]; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics; both NULL to skip).
+ * dy is fp32 (dy_is_16bit = 0) or `dtype` 16-bit; gamma NULL = no affine; dx may alias dres.  C in {512, 128}. */
+int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_is_16bit, const float* dres, float* dx,
+                     float* dgamma, float* dbeta, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
+/* exact-erf GELU on a 16-bit pre-activation (training keeps the pre-activation): a = gelu(u); du = da * gelu'(u).  n % 8 == 0. */
+int mp_gelu_fwd(const void* u, void* a, int64_t n, int dtype, mp_stream_t stream);
+int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, mp_stream_t stream);
+/* Attention backward (Attention.forward, mix_ste.py:257-275): qkv [tokens,3C], o / dout [tokens,C] -> dqkv [tokens,3C], all 16-bit,
+ * same token layout and modes as mp_attention; P is recomputed, nothing of size L x L is stored.  head_dim 64 or 16, L <= 256. */
+int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C,
+                     int n_heads, int mode, int dtype, mp_stream_t stream);
+/* dst[C,Mpad] = src[M,C]^T (zero padded), colsum[C] += column sums of src (NULL to skip).  C % 64 == 0, Mpad % 64 == 0. */
+int mp_transpose16(const void* src, void* dst, float* colsum, int64_t M, int64_t C, int64_t Mpad, int dtype, mp_stream_t stream);
+/* out[(row / div) % mod, :] += x[row, :]  (gradients of Spatial_pos_embed / Temporal_pos_embed, mix_ste.py:137,149). */
+int mp_group_rowsum(const float* x, float* out, int64_t n_rows, int C, int64_t div, int64_t mod, mp_stream_t stream);
+/* dW[n_out,n_in] += dy^T in, db[n_out] += column sums of dy; fp32, n_in in {2,3,34,51} (Spatial_patch_to_embedding, joints_to_segments_proj). */
+int mp_small_wgrad(const float* dy, const float* in, float* dW, float* db, int64_t n_rows, int n_out, int n_in, mp_stream_t stream);
+/* Stochastic depth (timm DropPath on both residual branches, mix_ste.py:334-336,352-358): out = x + s[token] * y (y 16-bit branch
+ * output, s = keep mask / keep_prob of the token's sample), and the backward operand out16 = 16-bit(s[token] * g) (s NULL: plain cast). */
+int mp_residual_rowscale(const float* x, const void* y, const float* s, float* out, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
+int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
+/* torch.optim.Adam step (L2-style weight_decay, bias correction, step counted from 1) over one flat fp32 buffer; grad is read as
+ * grad * grad_scale (1 / world_size after a SUM all-reduce). */
+int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int64_t step, float grad_scale, mp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import train_ops as T
 from .mix_ste import MixSTE
 from .pose_decoder import PoseDecoder
 
@@ -42,10 +43,32 @@ class BonesMixSTE(MixSTE):
         ops.bones_head(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, norm.weight, norm.bias,
                        lin.weight, lin.bias, out, n_clips, self.num_frame, self.num_bones, self.embed_dim, self._head_ws)
 
+    def _embed_backward(self, x2d, dx0, n_clips):
+        """Gradients of joints_to_segments_proj and Spatial_pos_embed (manifold_mix_ste.py:139-148) from dx0 [frames*S, C]."""
+        lin = self.joints_to_segments_proj
+        n_rows = n_clips * self.num_frame
+        T.small_wgrad(dx0.view(n_rows, self.num_bones * self.embed_dim), x2d.reshape(n_rows, lin.in_features), T.grad_of(lin.weight),
+                      T.grad_of(lin.bias))
+        T.group_rowsum(dx0, T.grad_of(self.Spatial_pos_embed), 1, self.num_bones)
+
+    def bone_lengths_with_grad(self, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable bone lengths [B, S] of the whole batch (Temporal_norm -> head LayerNorm(1e-5) -> Linear(C -> 1) -> mean over
+        time); the head Linear is zero-padded to 128 outputs so that it runs on the tensor-core Linear kernel with fp32 output."""
+        b, l = x.shape[:2]
+        feat = self.trunk_autograd(x, b)
+        norm, lin = self.head[0], self.head[1]
+        y = T.layer_norm(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps)
+        z = T.layer_norm(y, norm.weight, norm.bias, norm.eps, out16=ops.DTYPE_CODE[self.compute_dtype])
+        w = torch.cat([lin.weight, lin.weight.new_zeros(127, self.embed_dim)])
+        bias = torch.cat([lin.bias, lin.bias.new_zeros(127)])
+        return T.linear_f32(z, w, bias)[:, 0].reshape(b, l, self.num_bones).mean(dim=1)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ops._need_cuda(x)
         b, l, j, _ = self._check_input(x)
         x = ops._f32(x)
+        if self._grad_mode():
+            return self.bone_lengths_with_grad(x).unsqueeze(-1)
         out = torch.empty((b, self.num_bones), dtype=torch.float32, device=x.device)
         mb = self.clips_per_micro_batch()
         for s in range(0, b, mb):

@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .. import ops
+from .. import train_ops as T
 
 
 class DropPath(nn.Module):
@@ -108,6 +109,24 @@ class Block(nn.Module):
 
 def _version_key(params) -> Tuple:
     return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class _TrunkFn(torch.autograd.Function):
+    """Autograd node of a whole MixSTE trunk.  Parameter gradients are accumulated into ``p.grad`` by the backward sweep itself
+    (like fused weight-gradient accumulation in Megatron-style trainers), so the only tensor input is an ``anchor`` parameter
+    that makes the output require grad; its returned gradient is None."""
+
+    @staticmethod
+    def forward(ctx, module, x2d, n_clips, anchor):
+        feat, tape = module._train_forward(x2d, n_clips)
+        ctx.module, ctx.tape = module, tape
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        ctx.module._train_backward(ctx.tape, ops._f32(dfeat))
+        ctx.tape = None
+        return None, None, None, None
 
 
 class MixSTE(nn.Module):
@@ -201,8 +220,8 @@ class MixSTE(nn.Module):
         x2d: fp32 [n_clips, L, J, in_chans] (contiguous).  Returns the fp32 [n_clips*L*tokens, C] output of the last temporal
         block BEFORE ``Temporal_norm`` (the head kernels apply it, fused with their own LayerNorm)."""
         if self.training and any(isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0 for b in self.STEblocks):
-            raise NotImplementedError("training-mode stochastic depth through the fused trunk is not built yet; "
-                                      "call model.eval() (inference) or construct with drop_path_rate=0")
+            raise NotImplementedError("the fused inference trunk has no stochastic depth: call model.eval(), or run the forward "
+                                      "with gradients enabled (the training trunk applies DropPath)")
         n_frames = self.num_frame
         n_tok, c, heads = self.num_tokens, self.embed_dim, self.num_heads
         n_tokens = n_clips * n_frames * n_tok
@@ -246,6 +265,160 @@ class MixSTE(nn.Module):
                                   ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
         return x
 
+    # ------------------------------------------------------------------------------------------ training path
+    def _grad_mode(self) -> bool:
+        """True when a forward must record what the backward sweep needs (any parameter wants a gradient)."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _shadow_weights_t(self) -> List[torch.Tensor]:
+        """Transposed 16-bit shadows [K, N] of the GEMM weights (operand of dgrad = dY W), refreshed with the shadows."""
+        w = self._shadow_weights()
+        if getattr(self, "_shadow_t_key", None) != self._shadow_key:
+            self._shadow_t_list = [T.transpose16(x, torch.empty((x.shape[1], x.shape[0]), dtype=x.dtype, device=x.device)) for x in w]
+            self._shadow_t_key = self._shadow_key
+        return self._shadow_t_list
+
+    def _block_list(self):
+        depth = self.block_depth
+        blocks = []
+        for i in range(depth):
+            blocks.append((self.STEblocks[i], 4 * i, L.MP_ATTN_SPATIAL, self.Spatial_norm))
+            blocks.append((self.TTEblocks[i], 4 * (depth + i), L.MP_ATTN_TEMPORAL, self.Temporal_norm))
+        return blocks
+
+    def _droppath_scale(self, blk, mode, n_clips: int, device) -> Optional[torch.Tensor]:
+        """Per-token branch scale of timm's DropPath (mix_ste.py:334-336): Bernoulli(keep) / keep per sample of the block's batch —
+        a (clip, frame) in spatial blocks, a (clip, token) track in temporal blocks.  None when the block keeps everything."""
+        dp = blk.drop_path
+        if not (self.training and isinstance(dp, DropPath) and dp.drop_prob > 0.0):
+            return None
+        keep = 1.0 - dp.drop_prob
+        n_frames, n_tok = self.num_frame, self.num_tokens
+        shape = (n_clips, n_frames, 1) if mode == L.MP_ATTN_SPATIAL else (n_clips, 1, n_tok)
+        mask = torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(keep)
+        if keep > 0.0 and dp.scale_by_keep:
+            mask.div_(keep)
+        return mask.expand(n_clips, n_frames, n_tok).reshape(-1).contiguous()
+
+    def _train_forward(self, x2d: torch.Tensor, n_clips: int):
+        """The trunk with every tensor the backward sweep needs kept on a tape (no aliasing, no fused residual+LayerNorm):
+        per block x0 (input), h1 = norm1(x0), qkv, o (attention out), x1, h2 = norm2(x1), u (fc1 pre-activation), a = gelu(u), x2."""
+        n_frames, n_tok, c, heads = self.num_frame, self.num_tokens, self.embed_dim, self.num_heads
+        n_tokens = n_clips * n_frames * n_tok
+        dev = x2d.device
+        dt = ops.DTYPE_CODE[self.compute_dtype]
+        td = ops.TORCH_DTYPE[dt]
+        hidden = self.STEblocks[0].mlp.fc1.out_features
+        w = self._shadow_weights()
+        f32 = lambda: torch.empty((n_tokens, c), dtype=torch.float32, device=dev)
+        b16 = lambda cols: torch.empty((n_tokens, cols), dtype=td, device=dev)
+        x, h = f32(), b16(c)
+        self._embed(x2d, n_clips, n_frames, x, h)
+        blocks = self._block_list()
+        tape = {"x2d": x2d, "n_clips": n_clips, "blocks": []}
+        for bi, (blk, wi, mode, post) in enumerate(blocks):
+            last = bi + 1 == len(blocks)
+            s1 = self._droppath_scale(blk, mode, n_clips, dev)
+            s2 = self._droppath_scale(blk, mode, n_clips, dev)
+            qkv, o = b16(3 * c), b16(c)
+            ops.linear(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
+            ops.attention(qkv, o, n_clips, n_frames, n_tok, c, heads, mode)
+            x1 = f32()
+            if s1 is None:
+                ops.linear(o, w[wi + 1], blk.attn.proj.bias, x1, L.MP_EPI_RESIDUAL, resid=x)
+            else:
+                T.residual_rowscale(x, ops.linear(o, w[wi + 1], blk.attn.proj.bias, b16(c), L.MP_EPI_BIAS), s1, x1)
+            h2 = b16(c)
+            ops.layernorm(x1, None, h2, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
+            u, a = b16(hidden), b16(hidden)
+            ops.linear(h2, w[wi + 2], blk.mlp.fc1.bias, u, L.MP_EPI_BIAS)
+            T.gelu_fwd(u, a)
+            x2 = f32()
+            if s2 is None:
+                ops.linear(a, w[wi + 3], blk.mlp.fc2.bias, x2, L.MP_EPI_RESIDUAL, resid=x1)
+            else:
+                T.residual_rowscale(x1, ops.linear(a, w[wi + 3], blk.mlp.fc2.bias, b16(c), L.MP_EPI_BIAS), s2, x2)
+            rec = {"x0": x, "h1": h, "qkv": qkv, "o": o, "x1": x1, "h2": h2, "u": u, "a": a, "x2": x2, "s1": s1, "s2": s2,
+                   "pos": bi == 0}
+            tape["blocks"].append(rec)
+            if last:
+                x, h = x2, None
+            else:
+                nxt = blocks[bi + 1][0]
+                x3, h = f32(), b16(c)
+                pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
+                ops.layernorm(x2, x3, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
+                              ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
+                x = x3
+        return x, tape
+
+    def _embed_backward(self, x2d: torch.Tensor, dx0: torch.Tensor, n_clips: int) -> None:
+        """Gradients of Spatial_patch_to_embedding and Spatial_pos_embed (mix_ste.py:128-138) from dx0 [tokens, C]."""
+        lin = self.Spatial_patch_to_embedding
+        T.small_wgrad(dx0, x2d.reshape(-1, self.in_chans), T.grad_of(lin.weight), T.grad_of(lin.bias))
+        T.group_rowsum(dx0, T.grad_of(self.Spatial_pos_embed), 1, self.num_tokens)
+
+    def _train_backward(self, tape, dfeat: torch.Tensor) -> None:
+        """Reverse sweep over the tape: accumulates every parameter gradient of the trunk into ``p.grad`` (fp32).  dfeat is the
+        gradient w.r.t. the trunk output (the last block's x2, before Temporal_norm).  ``_on_block_grads(block)`` is called when
+        a block's parameter gradients are complete (the data-parallel reducer hooks in there)."""
+        n_clips = tape["n_clips"]
+        n_frames, n_tok, c, heads = self.num_frame, self.num_tokens, self.embed_dim, self.num_heads
+        hidden = self.STEblocks[0].mlp.fc1.out_features
+        dt = ops.DTYPE_CODE[self.compute_dtype]
+        td = ops.TORCH_DTYPE[dt]
+        w_t = self._shadow_weights_t()
+        blocks = self._block_list()
+        n_tokens = dfeat.shape[0]
+        dev = dfeat.device
+        if getattr(self, "_scratch", None) is None:
+            self._scratch = T.Scratch()
+        n_max, k_max = max(3 * c, hidden), max(c, hidden)
+        g = T.grad_of
+        b16 = lambda cols: torch.empty((n_tokens, cols), dtype=td, device=dev)
+        dx = dfeat.contiguous().clone()            # fp32 gradient of the residual stream, updated in place below
+        dy16, wide16 = b16(c), b16(max(3 * c, hidden))
+        flat = wide16.view(-1)
+        for bi in range(len(blocks) - 1, -1, -1):
+            blk, wi, mode, post = blocks[bi]
+            rec = tape["blocks"][bi]
+            last = bi + 1 == len(blocks)
+            if not last:
+                # x3 = post-norm(x2) (+ Temporal_pos_embed after the first block); dx currently is d/dx3
+                if rec["pos"]:
+                    T.group_rowsum(dx, g(self.Temporal_pos_embed), n_tok, n_frames)
+                T.layernorm_bwd(rec["x2"], post.weight, post.eps, dx, None, dx, g(post.weight), g(post.bias), dt)
+            # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1)))))
+            T.cast_rowscale(dx, rec["s2"], dy16)
+            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), g(blk.mlp.fc2.bias), self._scratch, n_max, k_max)
+            da = flat[:n_tokens * hidden].view(n_tokens, hidden)
+            T.dgrad(dy16, w_t[wi + 3], da)
+            T.gelu_bwd(rec["u"], da, da)
+            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), g(blk.mlp.fc1.bias), self._scratch, n_max, k_max)
+            T.dgrad(da, w_t[wi + 2], dy16)
+            T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt)
+            # ---- attention branch: x1 = x0 + s1 * proj(attention(qkv(norm1(x0))))
+            T.cast_rowscale(dx, rec["s1"], dy16)
+            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), g(blk.attn.proj.bias), self._scratch, n_max, k_max)
+            do = b16(c)
+            T.dgrad(dy16, w_t[wi + 1], do)
+            dqkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
+            T.attention_bwd(rec["qkv"], rec["o"], do, dqkv, n_clips, n_frames, n_tok, c, heads, mode)
+            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), g(blk.attn.qkv.bias), self._scratch, n_max, k_max)
+            T.dgrad(dqkv, w_t[wi + 0], dy16)
+            T.layernorm_bwd(rec["x0"], blk.norm1.weight, blk.norm1.eps, dy16, dx, dx, g(blk.norm1.weight), g(blk.norm1.bias), dt)
+            rec.clear()
+            hook = getattr(self, "_on_block_grads", None)
+            if hook is not None:
+                hook(blk)
+        self._embed_backward(tape["x2d"], dx, n_clips)
+
+    def trunk_autograd(self, x2d: torch.Tensor, n_clips: int) -> torch.Tensor:
+        """Differentiable trunk: same result as ``trunk`` (separate kernels instead of the fused residual+LayerNorm ones); its
+        backward runs ``_train_backward`` and writes parameter gradients straight into ``.grad``."""
+        anchor = next(p for p in self.parameters() if p.requires_grad)
+        return _TrunkFn.apply(self, x2d, n_clips, anchor)
+
     def _check_input(self, x: torch.Tensor):
         if x.dim() != 4:
             raise ValueError(f"expected x of shape [B, L, J, C], got {tuple(x.shape)}")
@@ -263,10 +436,10 @@ class MixSTE(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """mix_ste.py:175-191 with the plain head (LayerNorm eps 1e-5 + Linear): [B,L,J,in] -> [B,L,J,out_dim]."""
         ops._need_cuda(x)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("backward through the fused MixSTE trunk is not built yet (forward/inference only)")
         b, l, j, _ = self._check_input(x)
         x = ops._f32(x)
+        if self._grad_mode():
+            return self._forward_with_grad(x)
         out = torch.empty((b, 1, l, j, self.out_dim), dtype=torch.float32, device=x.device)
         mb = self.clips_per_micro_batch()
         norm, lin = self.head[0], self.head[1]
@@ -276,3 +449,17 @@ class MixSTE(nn.Module):
             ops.heads_fwd(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, norm.weight, norm.bias,
                           lin.weight, lin.bias, None, None, out[s:s + n], None, n, l, 1, self.out_dim, False)
         return out[:, 0]
+
+    def _forward_with_grad(self, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable forward of the plain head (Temporal_norm -> LayerNorm(1e-5) -> Linear), whole batch at once."""
+        b, l, j, _ = x.shape
+        feat = self.trunk_autograd(x, b)
+        norm, lin = self.head[0], self.head[1]
+        code = ops.DTYPE_CODE[self.compute_dtype]
+        y = T.layer_norm(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps)
+        z = T.layer_norm(y, norm.weight, norm.bias, norm.eps, out16=code)
+        n_pad = (self.out_dim + 127) // 128 * 128
+        w = torch.cat([lin.weight, lin.weight.new_zeros(n_pad - self.out_dim, self.embed_dim)])
+        bias = torch.cat([lin.bias, lin.bias.new_zeros(n_pad - self.out_dim)])
+        out = T.linear_f32(z, w, bias)[:, :self.out_dim]
+        return out.reshape(b, l, j, self.out_dim)

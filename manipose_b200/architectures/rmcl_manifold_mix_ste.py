@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .. import ops
+from .. import train_ops as T
 from .manifold_mix_ste import ManifoldMixSTE
 from .mix_ste import MixSTE, _version_key
 
@@ -69,11 +70,40 @@ class RMCLRotMixSTE(MixSTE):
         ops.heads_fwd(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, hg, hb, hw, hbias, sw, sb,
                       rot, logits, n_clips, self.num_frame, self.n_hyp, self.out_dim, True)
 
+    def hypotheses_with_grad(self, x: torch.Tensor):
+        """Differentiable K heads over the whole batch -> (rot [B,K,L,J,D], logits [B,K,L]).
+
+        LN_k(y) = yhat * gamma_k + beta_k shares yhat between the heads, so all K heads are one Linear with folded parameters
+        W_k * gamma_k, W_k beta_k + b_k (autograd unfolds the gradients), zero-padded to 128 outputs for the tensor-core Linear
+        kernel (fp32 output).  The score Linear(J -> 1) is a J-term dot product per frame and head."""
+        b, l, j, _ = x.shape
+        k, d1, c = self.n_hyp, self.out_dim + 1, self.embed_dim
+        feat = self.trunk_autograd(x, b)
+        y = T.layer_norm(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps)
+        one, zero = torch.ones(c, dtype=torch.float32, device=x.device), torch.zeros(c, dtype=torch.float32, device=x.device)
+        yhat = T.layer_norm(y, one, zero, self.head[0].norm.eps, out16=ops.DTYPE_CODE[self.compute_dtype])
+        gam = torch.stack([h.norm.weight for h in self.head])                     # [K, C]
+        bet = torch.stack([h.norm.bias for h in self.head])
+        w = torch.stack([h.prediction_head.weight for h in self.head])            # [K, D+1, C]
+        bias = torch.stack([h.prediction_head.bias for h in self.head])           # [K, D+1]
+        n_pad = (k * d1 + 127) // 128 * 128
+        wf = torch.cat([(w * gam[:, None, :]).reshape(k * d1, c), w.new_zeros(n_pad - k * d1, c)])
+        bf = torch.cat([((w * bet[:, None, :]).sum(-1) + bias).reshape(k * d1), w.new_zeros(n_pad - k * d1)])
+        out = T.linear_f32(yhat, wf, bf)[:, :k * d1].reshape(b, l, j, k, d1)
+        rot = out[..., :self.out_dim].permute(0, 3, 1, 2, 4)
+        sw = torch.stack([h.score_head.weight[0] for h in self.head])             # [K, J]
+        sb = torch.stack([h.score_head.bias[0] for h in self.head])               # [K]
+        logits = (out[..., self.out_dim] * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
+        return rot, logits
+
     def forward(self, x: torch.Tensor):
         """-> (hypothesis [B,K,L,J,D], scores [B,K,L,1])  (rmcl_manifold_mix_ste.py:239-264)."""
         ops._need_cuda(x)
         b, l, j, _ = self._check_input(x)
         x = ops._f32(x)
+        if self._grad_mode():
+            rot, logits = self.hypotheses_with_grad(x)
+            return rot, ops.softmax_hyp(logits.contiguous()).unsqueeze(-1)
         rot = torch.empty((b, self.n_hyp, l, j, self.out_dim), dtype=torch.float32, device=x.device)
         logits = torch.empty((b, self.n_hyp, l), dtype=torch.float32, device=x.device)
         mb = self.clips_per_micro_batch()
@@ -110,13 +140,16 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
         ops._need_cuda(x)
         rm, sm = self.rotations_module, self.segments_module
         b, l, j, _ = rm._check_input(x)
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward through the fused MixSTE trunk is not built yet (forward/inference only); "
-                                      "wrap the call in torch.no_grad() or model.eval()")
         ops.set_skeleton(*self.decoder._tables)
         x = ops._f32(x)
         k, d = self.n_hyp, rm.out_dim
         dev = x.device
+        if rm._grad_mode() or sm._grad_mode():
+            # differentiable path (training): whole batch at once, activations kept for the backward sweep
+            rot, logits = rm.hypotheses_with_grad(x)
+            bones = sm.bone_lengths_with_grad(x)
+            poses = ops.decode(rot.reshape(b * k * l, j, d), bones, None, b, k, l, d, self.decoder.exact).view(b, k, l, j, 3)
+            return poses, ops.softmax_hyp(logits.contiguous()).unsqueeze(-1)
         poses = torch.empty((b, k, l, j, 3), dtype=torch.float32, device=dev)
         scores = torch.empty((b, k, l, 1), dtype=torch.float32, device=dev)
         mb = min(rm.clips_per_micro_batch(), max(b, 1))

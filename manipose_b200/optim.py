@@ -1,0 +1,179 @@
+"""Flat fp32 parameter / gradient storage, fused Adam and the bucketed data-parallel gradient reducer.
+
+Reference: ``torch.optim.Adam(model.parameters(), lr=4e-5, weight_decay=1e-6)`` (hpe/main_h36m_lifting.py:755-761) under
+``nn.DataParallel``.  Here (training): one process per GPU; every parameter and its gradient are views into
+two flat fp32 buffers, so that
+
+* the backward sweep accumulates weight gradients in place (``train_ops.grad_of``),
+* gradient averaging is a handful of NCCL all-reduces over contiguous buckets (one per transformer block, launched from
+  the backward sweep as soon as a block's gradients are complete, so they overlap the rest of the backward), and
+* the optimizer step is ONE kernel (``mp_adam_step``) over the flat buffers.
+
+``FusedAdam`` follows ``torch.optim.Adam`` numerics (L2-style weight decay, bias correction) and exposes ``param_groups`` so
+``ReduceLROnPlateau`` (main_h36m_lifting.py:763-771) works unchanged.  ``FlatParameters`` and ``GradientReducer`` are device
+agnostic (the world-size-2 gloo tests run them on CPU); only ``FusedAdam.step`` needs the sm_100a library.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+_ALIGN = 64   # floats: every parameter starts on a 256-byte boundary (TMA / vector alignment of the gradient GEMMs)
+
+
+class FlatParameters:
+    """Re-homes the parameters of ``module`` (already on their final device) into one flat buffer; ``p.grad`` become views of a
+    second one.  ``state_dict`` / ``load_state_dict`` keep working (they copy in place)."""
+
+    def __init__(self, module: nn.Module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("module has no trainable parameters")
+        dev = params[0].device
+        self.params = params
+        self.offsets: Dict[int, Tuple[int, int]] = {}
+        off = 0
+        for p in params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise ValueError("FlatParameters needs fp32 parameters on one device")
+            self.offsets[id(p)] = (off, p.numel())
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p in params:
+                o, n = self.offsets[id(p)]
+                view = self.flat_param[o:o + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self.attach_grads()
+
+    def attach_grads(self) -> None:
+        for p in self.params:
+            o, n = self.offsets[id(p)]
+            g = self.flat_grad[o:o + n].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+        self.attach_grads()
+
+    def span(self, params: Sequence[torch.Tensor]) -> Tuple[int, int]:
+        """[start, stop) of the flat buffers covering ``params`` (they must be contiguous in registration order)."""
+        spans = sorted(self.offsets[id(p)] for p in params)
+        start = spans[0][0]
+        stop = spans[-1][0] + (spans[-1][1] + _ALIGN - 1) // _ALIGN * _ALIGN
+        return start, min(stop, self.numel)
+
+
+class GradientReducer:
+    """Sum-all-reduce of ``flat_grad`` in contiguous buckets.  ``bucket_ready(i)`` launches bucket i asynchronously (NCCL runs it on
+    its own stream after the work already queued on the current stream); ``finish()`` launches whatever was not reduced yet and
+    waits.  The 1 / world_size averaging is folded into the optimizer step (``FusedAdam.step(grad_scale=...)``)."""
+
+    def __init__(self, flat_grad: torch.Tensor, buckets: List[Tuple[int, int]], group=None):
+        self.flat_grad = flat_grad
+        self.buckets = list(buckets)
+        self.group = group
+        self._handles = []
+        self._done = [False] * len(self.buckets)
+        covered = sorted(self.buckets)
+        if covered[0][0] != 0 or covered[-1][1] != flat_grad.numel() or any(a[1] != b[0] for a, b in zip(covered, covered[1:])):
+            raise ValueError("buckets must tile the flat gradient buffer")
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def bucket_ready(self, i: int) -> None:
+        if self._done[i]:
+            raise RuntimeError(f"gradient bucket {i} reduced twice in one step")
+        self._done[i] = True
+        if self.world_size > 1:
+            a, b = self.buckets[i]
+            self._handles.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> float:
+        """Reduces the remaining buckets, waits for all of them, returns the factor that turns the sums into means."""
+        for i, done in enumerate(self._done):
+            if not done:
+                self.bucket_ready(i)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self._done = [False] * len(self.buckets)
+        return 1.0 / self.world_size
+
+
+def block_buckets(flat: FlatParameters, model: nn.Module) -> Tuple[List[Tuple[int, int]], Dict[int, int]]:
+    """One bucket per transformer block of the rotations backbone (2.1 M parameters each) plus the gaps between them (embeddings,
+    shared norms, heads, the small bone-length backbone).  Returns (buckets, {id(block): bucket index})."""
+    spans = []
+    rot = getattr(model, "rotations_module", model)
+    for blk in list(getattr(rot, "STEblocks", [])) + list(getattr(rot, "TTEblocks", [])):
+        ps = [p for p in blk.parameters() if p.requires_grad]
+        if ps:
+            spans.append((flat.span(ps), id(blk)))
+    spans.sort()
+    buckets, index, cursor = [], {}, 0
+    for (a, b), key in spans:
+        if a > cursor:
+            buckets.append((cursor, a))
+        index[key] = len(buckets)
+        buckets.append((a, b))
+        cursor = b
+    if cursor < flat.numel:
+        buckets.append((cursor, flat.numel))
+    return buckets, index
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (no amsgrad) as one kernel over flat parameter / gradient / moment buffers."""
+
+    def __init__(self, module: nn.Module, lr: float = 4e-5, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, group=None, overlap_reduce: bool = True):
+        self._module = module
+        self.flat = FlatParameters(module)
+        super().__init__(self.flat.params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.exp_avg = torch.zeros_like(self.flat.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat.flat_param)
+        self.step_count = 0
+        buckets, index = block_buckets(self.flat, module)
+        self.reducer = GradientReducer(self.flat.flat_grad, buckets, group)
+        self._bucket_of_block = index
+        if overlap_reduce:
+            rot = getattr(module, "rotations_module", None)
+            if rot is not None:
+                rot._on_block_grads = self._block_done
+
+    def _block_done(self, blk: nn.Module) -> None:
+        i = self._bucket_of_block.get(id(blk))
+        if i is not None and self.reducer.world_size > 1:
+            self.reducer.bucket_ready(i)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:   # gradients are views of the flat buffer: never set to None
+        self.flat.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import train_ops as T
+        loss = closure() if closure is not None else None
+        scale = self.reducer.finish()
+        g = self.param_groups[0]
+        self.step_count += 1
+        T.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
+                    g["eps"], g["weight_decay"], self.step_count, scale)
+        self._invalidate_shadows()
+        return loss
+
+    def _invalidate_shadows(self) -> None:
+        """The kernel wrote the parameters behind autograd's back (their ``_version`` did not move): drop the cached 16-bit weight
+        shadows / stacked head tensors so that the next forward rebuilds them."""
+        for m in self._module.modules():
+            if hasattr(m, "_shadow_key"):
+                m._shadow_key = None
+            if hasattr(m, "_head_key"):
+                m._head_key = None

@@ -1,0 +1,216 @@
+"""Backward-pass wrappers over the C ABI (include/manipose_sm100.h, "backward (training) entry points").
+
+The reference differentiates the MixSTE blocks with torch autograd (hpe/mh_so3_hpe/architectures/mix_ste.py:194-368); here
+the backward of the trunk is an explicit reverse sweep (architectures/mix_ste.py::MixSTE._train_backward) over these
+kernels, and the two autograd Functions below cover the small pieces around it (hypothesis heads, bone-length head).
+No CPU fallback: every function needs CUDA tensors and the built library.
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+_zeros_cache = {}
+
+
+def zeros_f32(n: int, device) -> torch.Tensor:
+    """A shared read-only fp32 zero vector (bias operand of the backward GEMMs)."""
+    key = (str(device), n)
+    z = _zeros_cache.get(key)
+    if z is None:
+        z = torch.zeros(n, dtype=torch.float32, device=device)
+        _zeros_cache[key] = z
+    return z
+
+
+def pad64(m: int) -> int:
+    return (m + 63) // 64 * 64
+
+
+def layernorm_bwd(x, gamma, eps, dy, dres, dx, dgamma, dbeta, dtype):
+    """dx = LN'(x)(dy) [+ dres]; dgamma / dbeta accumulate (None to skip).  dy fp32 or 16-bit."""
+    n_tokens, c = x.shape
+    rc = L.load().mp_layernorm_bwd(L.ptr(x), L.ptr(gamma), float(eps), L.ptr(dy), int(dy.dtype != torch.float32), L.ptr(dres), L.ptr(dx),
+                                   L.ptr(dgamma), L.ptr(dbeta), n_tokens, c, dtype, L.stream_ptr())
+    L.check(rc, "mp_layernorm_bwd")
+    ops._count()
+    return dx
+
+
+def gelu_fwd(u, a):
+    L.check(L.load().mp_gelu_fwd(L.ptr(u), L.ptr(a), u.numel(), ops.DTYPE_CODE[u.dtype], L.stream_ptr()), "mp_gelu_fwd")
+    ops._count()
+    return a
+
+
+def gelu_bwd(u, da, du):
+    L.check(L.load().mp_gelu_bwd(L.ptr(u), L.ptr(da), L.ptr(du), u.numel(), ops.DTYPE_CODE[u.dtype], L.stream_ptr()), "mp_gelu_bwd")
+    ops._count()
+    return du
+
+
+def attention_bwd(qkv, o, dout, dqkv, n_clips, n_frames, n_tok, c, n_heads, mode):
+    rc = L.load().mp_attention_bwd(L.ptr(qkv), L.ptr(o), L.ptr(dout), L.ptr(dqkv), n_clips, n_frames, n_tok, c, n_heads, mode,
+                                   ops.DTYPE_CODE[qkv.dtype], L.stream_ptr())
+    L.check(rc, "mp_attention_bwd")
+    ops._count()
+    return dqkv
+
+
+def transpose16(src, dst, colsum=None):
+    """dst[C, Mpad] = src[M, C]^T zero padded; colsum[C] += column sums of src."""
+    m, c = src.shape
+    rc = L.load().mp_transpose16(L.ptr(src), L.ptr(dst), L.ptr(colsum), m, c, dst.shape[1], ops.DTYPE_CODE[src.dtype], L.stream_ptr())
+    L.check(rc, "mp_transpose16")
+    ops._count()
+    return dst
+
+
+def group_rowsum(x, out, div, mod):
+    n_rows, c = x.shape
+    L.check(L.load().mp_group_rowsum(L.ptr(x), L.ptr(out), n_rows, c, div, mod, L.stream_ptr()), "mp_group_rowsum")
+    ops._count()
+
+
+def small_wgrad(dy, inp, dw, db):
+    n_rows, n_out = dy.shape
+    L.check(L.load().mp_small_wgrad(L.ptr(dy), L.ptr(inp), L.ptr(dw), L.ptr(db), n_rows, n_out, inp.shape[1], L.stream_ptr()), "mp_small_wgrad")
+    ops._count()
+
+
+def residual_rowscale(x, y16, s, out):
+    n_tokens, c = x.shape
+    rc = L.load().mp_residual_rowscale(L.ptr(x), L.ptr(y16), L.ptr(s), L.ptr(out), n_tokens, c, ops.DTYPE_CODE[y16.dtype], L.stream_ptr())
+    L.check(rc, "mp_residual_rowscale")
+    ops._count()
+    return out
+
+
+def cast_rowscale(g, s, out16):
+    n_tokens, c = g.shape
+    rc = L.load().mp_cast_rowscale(L.ptr(g), L.ptr(s), L.ptr(out16), n_tokens, c, ops.DTYPE_CODE[out16.dtype], L.stream_ptr())
+    L.check(rc, "mp_cast_rowscale")
+    ops._count()
+    return out16
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    rc = L.load().mp_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
+                               float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), L.stream_ptr())
+    L.check(rc, "mp_adam_step")
+    ops._count()
+
+
+def grad_of(p: torch.Tensor) -> torch.Tensor:
+    """The fp32 buffer the backward kernels accumulate into (``p.grad``; created zeroed when missing, like autograd would)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class Scratch:
+    """Transposed-operand scratch of the weight-gradient GEMMs: dY^T [n_max, Mpad] and X^T [k_max, Mpad] (16-bit)."""
+
+    def __init__(self):
+        self.key = None
+
+    def get(self, n_tokens, n_max, k_max, dtype, device):
+        mpad = pad64(n_tokens)
+        key = (mpad, n_max, k_max, dtype, str(device))
+        if key != self.key:
+            self.tdy = torch.empty((n_max, mpad), dtype=dtype, device=device)
+            self.tact = torch.empty((k_max, mpad), dtype=dtype, device=device)
+            self.key = key
+        return self.tdy, self.tact
+
+
+def wgrad(dy16, act16, dw, db, scratch: Scratch, n_max: int, k_max: int):
+    """dw[N,K] += dy16[M,N]^T act16[M,K]; db[N] += column sums of dy16 (db None to skip).
+
+    tcgen05 path: both operands are transposed so that the token dim is the contraction dim, then mp_linear accumulates
+    into the fp32 gradient through its residual epilogue."""
+    m, n = dy16.shape
+    k = act16.shape[1]
+    tdy, tact = scratch.get(m, n_max, k_max, dy16.dtype, dy16.device)
+    transpose16(dy16, tdy[:n], db)
+    transpose16(act16, tact[:k])
+    ops.linear(tdy[:n], tact[:k], zeros_f32(k_max, dy16.device), dw, L.MP_EPI_RESIDUAL, resid=dw)
+
+
+def dgrad(dy16, w_t16, out16):
+    """out16[M,K] = dy16[M,N] @ W[N,K], with the transposed 16-bit weight shadow w_t16 [K,N]."""
+    return ops.linear(dy16, w_t16, zeros_f32(max(w_t16.shape[0], 2048), dy16.device), out16, L.MP_EPI_BIAS)
+
+
+# ------------------------------------------------------------------------------------------------ small autograd pieces
+class LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x fp32 [M,C]; gamma, beta, eps) as fp32 (``out16`` None) or as a 16-bit GEMM operand."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out16):
+        x = ops._f32(x)
+        m, c = x.shape
+        if out16 is None:
+            y = torch.empty_like(x)
+            ops.layernorm(x, y, None, post=(gamma, beta), post_eps=eps)
+        else:
+            y = torch.empty((m, c), dtype=ops.TORCH_DTYPE[out16], device=x.device)
+            ops.layernorm(x, None, y, ln=(gamma, beta), ln_eps=eps, dtype=out16)
+        ctx.save_for_backward(x, gamma)
+        ctx.eps, ctx.code = eps, out16 if out16 is not None else L.MP_DTYPE_BF16
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        need_affine = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dg = torch.zeros_like(gamma) if need_affine else None
+        db = torch.zeros_like(gamma) if need_affine else None
+        layernorm_bwd(x, gamma, ctx.eps, dy, None, dx, dg, db, ctx.code)
+        return dx, dg, db, None, None
+
+
+class LinearF32Fn(torch.autograd.Function):
+    """y fp32 [M,N] = a16 [M,K] @ W[N,K]^T + b  with W, b fp32 parameters (cast to 16-bit inside); N % 128 == 0.
+    Used for the (zero-padded) hypothesis heads and the bone-length head, whose outputs must stay fp32."""
+
+    @staticmethod
+    def forward(ctx, a16, w, b):
+        code = ops.DTYPE_CODE[a16.dtype]
+        w16 = ops.cast16(w.detach(), code)
+        m, n = a16.shape[0], w.shape[0]
+        y = torch.zeros((m, n), dtype=torch.float32, device=a16.device)
+        ops.linear(a16, w16, ops._f32(b.detach()), y, L.MP_EPI_RESIDUAL, resid=y)
+        ctx.save_for_backward(a16, w16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a16, w16 = ctx.saved_tensors
+        code = ops.DTYPE_CODE[a16.dtype]
+        m, k = a16.shape
+        n = w16.shape[0]
+        dy16 = ops.cast16(dy.contiguous(), code)
+        dw = torch.zeros((n, k), dtype=torch.float32, device=a16.device)
+        db = torch.zeros(n, dtype=torch.float32, device=a16.device)
+        wgrad(dy16, a16, dw, db, _fn_scratch, n, k)
+        w_t = torch.empty((k, n), dtype=a16.dtype, device=a16.device)
+        transpose16(w16, w_t)
+        da = torch.empty((m, k), dtype=a16.dtype, device=a16.device)
+        dgrad(dy16, w_t, da)
+        return da, dw, db
+
+
+_fn_scratch = Scratch()
+
+
+def layer_norm(x, gamma, beta, eps, out16: Optional[int] = None):
+    return LayerNormFn.apply(x, gamma, beta, eps, out16)
+
+
+def linear_f32(a16, w, b):
+    return LinearF32Fn.apply(a16, w, b)

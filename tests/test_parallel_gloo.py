@@ -62,3 +62,48 @@ def test_shard_range_is_balanced():
             assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import manipose_b200 as mb
+    from manipose_b200.optim import FlatParameters, GradientReducer, block_buckets
+    torch.manual_seed(0)                                               # same replica on every rank
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=2, depth_rot=2, depth_seg=1)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = FlatParameters(m)
+    assert all(torch.equal(v, sd0[k]) for k, v in m.state_dict().items())          # re-homing keeps the values
+    buckets, index = block_buckets(flat, m)
+    assert len(index) == 4 and buckets[0][0] == 0 and buckets[-1][1] == flat.numel
+    red = GradientReducer(flat.flat_grad, buckets)
+    g = torch.Generator().manual_seed(100 + rank)                      # rank-specific "gradients" written through p.grad
+    local = {}
+    for name, p in m.named_parameters():
+        local[name] = torch.randn(p.shape, generator=g)
+        p.grad.copy_(local[name])
+    # blocks report in backward order (as MixSTE._train_backward does), the rest is swept up by finish()
+    rot = m.rotations_module
+    for blk in reversed([b for pair in zip(rot.STEblocks, rot.TTEblocks) for b in pair]):
+        red.bucket_ready(index[id(blk)])
+    scale = red.finish()
+    assert scale == 1.0 / world
+    torch.save({n: p.grad.clone() for n, p in m.named_parameters()}, os.path.join(out_dir, f"g{rank}.pt"))
+    torch.save(local, os.path.join(out_dir, f"l{rank}.pt"))
+    flat.zero_grad()
+    assert float(flat.flat_grad.abs().sum()) == 0.0 and all(p.grad.data_ptr() >= flat.flat_grad.data_ptr() for p in m.parameters())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_world2_gloo(tmp_path):
+    """Training exchange step: per-block buckets of the flat gradient buffer are sum-all-reduced; every rank ends
+    with the same sums, equal to the sum of the per-rank gradients."""
+    world = 2
+    mp_.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    reduced = [torch.load(tmp_path / f"g{r}.pt") for r in range(world)]
+    local = [torch.load(tmp_path / f"l{r}.pt") for r in range(world)]
+    for name in reduced[0]:
+        want = local[0][name] + local[1][name]
+        assert torch.allclose(reduced[0][name], want, rtol=1e-6, atol=1e-6), name
+        assert torch.equal(reduced[0][name], reduced[1][name]), name
