@@ -314,6 +314,113 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- training step (BASELINE config 4)
+def run_train(args):
+    """--config 4: one data-parallel training step at the 3DHP shape (T=27, 30 clips per GPU, K=5):
+    forward + default objective + backward + bucketed gradient all-reduce + Adam, weak-scaled.  Not the headline line (that is
+    config 3); printed as its own JSON line with the same timing rules."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import manipose_b200 as mb
+    from manipose_b200 import metrics, ops
+    from manipose_b200.optim import FusedAdam
+
+    t4, b4 = 27, (args.clips if args.clips != 1024 else 30)
+    torch.manual_seed(42)                      # identical replicas
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=t4, n_hyp=K, drop_path_rate=args.drop_path)
+    model = model.to(dev).train().set_compute_dtype(args.dtype)
+    opt = FusedAdam(model, lr=4e-5, weight_decay=1e-6)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x = (0.3 * torch.randn(b4, t4, J, 2, generator=gen)).to(dev)
+    y = 0.3 * torch.randn(b4, t4, J, 3, generator=gen)
+    y[:, :, 0] = 0
+    y = y.to(dev)
+    loss_box = [None]
+
+    def step():
+        opt.zero_grad()
+        poses, scores = model(x)
+        loss, _ = metrics.losses.training_loss(poses, scores, y)
+        loss.backward()
+        opt.step()
+        loss_box[0] = loss.detach()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    run = step
+    graph = None
+    if args.cuda_graph:
+        # the step is shape-static: capture forward + loss + backward + reduce + Adam once, replay it (removes ~10^3 launches of host work)
+        sync_all()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        run = graph.replay
+        for _ in range(2):
+            run()
+    steps = max(args.steps, 20)
+    launches0 = ops.LAUNCHES
+    step()
+    launches = ops.LAUNCHES - launches0
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(run, steps)
+    # the same step without the exchange (reducer sees a world of 1): the difference is the exposed all-reduce time
+    ms_local = None
+    if world > 1 and graph is None:
+        red = opt.reducer
+        type(red).world_size = property(lambda self: 1)
+        ms_local = timed(run, steps)
+    frames = b4 * t4 * world
+    value = frames * steps / (ms / 1000.0)
+    peaks = measured_peaks()
+    tflops = 3.0 * flops_per_frame(t4, K) * b4 * t4 * steps / (ms / 1000.0) / 1e12
+    n_params = sum(p.numel() for p in model.parameters())
+    if rank == 0:
+        line = {"metric": "train_frames_per_sec_T27_3DHP", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"ManiPose training step (forward + wta/bce/velocity/smoothness objective + backward + gradient all-reduce + Adam), "
+                                       f"T={t4}, K={K}, J={J}, {b4} clips/GPU = BASELINE config 4; drop_path_rate {args.drop_path}",
+                           "clips_per_gpu": b4, "frames_per_step": frames, "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce of "
+                           f"{n_params} fp32 gradients ({n_params * 4 / 1e6:.1f} MB) overlapped with the backward sweep",
+                           "cuda_graph": bool(args.cuda_graph), "gflop_per_frame_fwd_bwd": 3.0 * flops_per_frame(t4, K) / 1e9},
+                "gpu_launches": launches * steps, "clocks": clocks.summary(), "loss": float(loss_box[0]),
+                "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": tflops / peaks["bf16_sustained"], "traffic": None,
+                             "note": "whole step: 3 x forward matmul flops / step time; the step is launch / latency bound at 810 frames"},
+                "allreduce": None if ms_local is None else {"exposed_ms_per_step": (ms - ms_local) / steps, "ms_per_step_without": ms_local / steps}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -324,9 +431,14 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit operand format of the backbone")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: do not time the CPU oracle")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: T=243 inference (headline); 4: T=27 training step")
+    ap.add_argument("--drop-path", type=float, default=0.1, help="config 4: stochastic depth rate (drivers use 0.1)")
+    ap.add_argument("--cuda-graph", action="store_true", help="config 4: capture the whole training step in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4:
+        run_train(args)
     else:
         run_gpu(args)
 

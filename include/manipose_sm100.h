@@ -134,8 +134,10 @@ enum { MP_DTYPE_BF16 = 0, /* BASELINE config 3: "bf16 backbone" */
  *   MP_EPI_BIAS:     Y[M,N] (16-bit) = A[M,K] W[N,K]^T + bias[N]
  *   MP_EPI_GELU:     Y[M,N] (16-bit) = GELU_erf(A W^T + bias)                       (nn.GELU, mix_ste.py:200)
  *   MP_EPI_RESIDUAL: Y[M,N] (fp32)   = resid[M,N] (fp32) + A W^T + bias             (Block.forward, mix_ste.py:352-358)
+ *   MP_EPI_ACCUMULATE: Y[M,N] (fp32) += A W^T  (bias ignored, may be NULL): the contraction is split over the SMs and the partial
+ *                    tiles are added with TMA reduce stores (fp32 adds in L2, order not fixed) — weight gradients, few tiles, long K
  * A, W 16-bit dense row-major (row strides K); bias fp32; K % 64 == 0, N % 128 == 0; Y may alias resid. */
-enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2 };
+enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2, MP_EPI_ACCUMULATE = 3 };
 int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N,
               int64_t K, int epilogue, int dtype, mp_stream_t stream);
 
@@ -207,7 +209,7 @@ int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stre
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:
  *   dgrad  dX[M,K] = dY[M,N] W[N,K]      -> mp_linear(A = dY, W = transposed 16-bit shadow [K,N])
- *   wgrad  dW[N,K] += dY^T X             -> mp_linear(A = dY^T [N,Mpad], W = X^T [K,Mpad], resid = Y = dW, MP_EPI_RESIDUAL)
+ *   wgrad  dW[N,K] += dY^T X             -> mp_linear(A = dY^T [N,Mpad], W = X^T [K,Mpad], Y = dW, MP_EPI_ACCUMULATE)
  * with the operand transposes (and the bias gradient, a column sum of dY) done by mp_transpose16. */
 
 /* LayerNorm backward: dx = LN'(x; gamma, eps)(dy) [+ dres]; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics; both NULL to skip).
@@ -232,9 +234,10 @@ int mp_small_wgrad(const float* dy, const float* in, float* dW, float* db, int64
 int mp_residual_rowscale(const float* x, const void* y, const float* s, float* out, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
 int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
 /* torch.optim.Adam step (L2-style weight_decay, bias correction, step counted from 1) over one flat fp32 buffer; grad is read as
- * grad * grad_scale (1 / world_size after a SUM all-reduce). */
+ * grad * grad_scale (1 / world_size after a SUM all-reduce).  step_dev (device int64, may be NULL): when given, the step count is read
+ * from it (value before this step) and incremented afterwards, so a captured CUDA graph of the step stays correct on replay. */
 int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int64_t step, float grad_scale, mp_stream_t stream);
+                 float weight_decay, int64_t step, int64_t* step_dev, float grad_scale, mp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ MP_EINVAL, MP_EUNSUPPORTED, MP_EDEVICE, MP_ELAUNCH, MP_EALIGN, MP_EWORKSPACE = -
 MP_DEC_EXACT, MP_DEC_FAST = 0, 1
 MP_TERM_WTA, MP_TERM_BCE, MP_TERM_VEL, MP_TERM_SMOOTH, MP_TERM_TOTAL, MP_LOSS_NTERMS = 0, 1, 2, 3, 4, 8
 MP_AGG_WEIGHTED_AVE, MP_AGG_BEST_SCORE, MP_AGG_ORACLE = 0, 1, 2
-MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL = 0, 1, 2
+MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL, MP_EPI_ACCUMULATE = 0, 1, 2, 3
 MP_ATTN_SPATIAL, MP_ATTN_TEMPORAL = 0, 1
 MP_DTYPE_BF16, MP_DTYPE_FP16 = 0, 1
 
@@ -57,7 +57,7 @@ SIGNATURES = {
     "mp_small_wgrad": (I, [P, P, P, P, I64, I, I, P]),
     "mp_residual_rowscale": (I, [P, P, P, P, I64, I, I, P]),
     "mp_cast_rowscale": (I, [P, P, P, I64, I, I, P]),
-    "mp_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
+    "mp_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, I64, P, F, P]),
 }
 
 _lib = None

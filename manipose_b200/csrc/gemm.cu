@@ -51,10 +51,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 template <int BN, int EPI, typename D>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K) {
+              const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K, int splits) {
   using Cfg = GemmCfg<BN>;
   constexpr bool kRes = (EPI == MP_EPI_RESIDUAL);
-  constexpr int kBoxCols = kRes ? 32 : 64;                 // fp32 vs 16-bit output: 128 bytes per row either way
+  constexpr bool kAcc = (EPI == MP_EPI_ACCUMULATE);        // Y (fp32) += A W^T, split-K: partial tiles are added by TMA reduce stores
+  constexpr int kBoxCols = (kRes || kAcc) ? 32 : 64;       // fp32 vs 16-bit output: 128 bytes per row either way
   constexpr int kBoxes = BN / kBoxCols;
   static_assert(kBoxes % 2 == 0, "boxes alternate between the two epilogue groups");
 
@@ -74,8 +75,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blocks = N / BN;
   const int m_blocks = (M + kBM - 1) / kBM;
-  const int num_tiles = n_blocks * m_blocks;
   const int k_blocks = K / kBK;
+  // work items: (tile, k-split).  splits == 1 except for MP_EPI_ACCUMULATE, where few output tiles with a long contraction (weight
+  // gradients: the contraction runs over tokens) are spread over all SMs
+  const int k_per = (k_blocks + splits - 1) / splits;
+  const int num_tiles = n_blocks * m_blocks * splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -112,9 +116,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       // ===================== operand producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / splits, sp = item - tile * splits;
         const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb_end = min(k_blocks, (sp + 1) * k_per);
+        for (int kb = sp * k_per; kb < kb_end; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -135,11 +141,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int sp = item % splits;
+        const int kb_begin = sp * k_per, kb_end = min(k_blocks, kb_begin + k_per);
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
@@ -148,10 +156,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           ptx::umma_commit(&empty[stage]);                   // frees the stage when these MMAs have read it
-          if (kb == k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+          if (kb == kb_end - 1) ptx::umma_commit(&tmem_full[acc]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -167,7 +175,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     if (kRes && lane == 0) {
       // ===================== residual loader =====================
       uint32_t n = 0;   // running box index of this CTA
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / splits;
         const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
         for (int b = 0; b < kBoxes; ++b, ++n) {
           const uint32_t slot = n % kSlots, use = n / kSlots;
@@ -187,7 +196,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t i = 0;                              // running box index of this group
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / splits;
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -218,6 +228,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             v.w += __uint_as_float(r[4 * c + 3]) + bb.w;
             *p = v;
           }
+        } else if (kAcc) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 32), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(srow + (((uint32_t)c ^ sw) << 4)) = make_uint4(r[4 * c + 0], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         } else {
           uint32_t r0[32], r1[32];               // both 32-column halves of the box in flight before one wait
           ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
@@ -250,7 +267,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1 + grp, 128);
         if (elected) {
-          ptx::tma_store_2d(&tm_y, slot_base + slot * kBoxBytes, col0, m_blk * kBM);
+          if (kAcc)
+            ptx::tma_reduce_add_2d(&tm_y, slot_base + slot * kBoxBytes, col0, m_blk * kBM);
+          else
+            ptx::tma_store_2d(&tm_y, slot_base + slot * kBoxBytes, col0, m_blk * kBM);
           ptx::bulk_commit();
           if (i > 0) {
             ptx::bulk_wait_read<1>();            // the group's previous store has finished reading its slot
@@ -389,8 +409,19 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMa
     attr_set = true;
   }
   const int tiles = (N / BN) * ((M + kBM - 1) / kBM);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K);
+  int splits = 1;
+  if (EPI == MP_EPI_ACCUMULATE) {
+    // split the contraction so that tiles x splits fills the SMs; every split gets at least 4 k-blocks and none is empty
+    const int k_blocks = K / kBK;
+    int want = sm_count() / tiles;
+    if (want > k_blocks / 4) want = k_blocks / 4;
+    if (want < 1) want = 1;
+    const int k_per = (k_blocks + want - 1) / want;
+    splits = (k_blocks + k_per - 1) / k_per;
+  }
+  const int items = tiles * splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K, splits);
   return check_launch("linear_kernel");
 }
 
@@ -401,6 +432,7 @@ int dispatch_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tw, con
     case MP_EPI_BIAS: return launch_linear<BN, MP_EPI_BIAS, D>(ta, tw, ty, tr, bias, M, N, K, stream);
     case MP_EPI_GELU: return launch_linear<BN, MP_EPI_GELU, D>(ta, tw, ty, tr, bias, M, N, K, stream);
     case MP_EPI_RESIDUAL: return launch_linear<BN, MP_EPI_RESIDUAL, D>(ta, tw, ty, tr, bias, M, N, K, stream);
+    case MP_EPI_ACCUMULATE: return launch_linear<BN, MP_EPI_ACCUMULATE, D>(ta, tw, ty, tr, bias, M, N, K, stream);
   }
   return fail(MP_EINVAL, "mp_linear: unknown epilogue %d", epilogue);
 }
@@ -412,7 +444,7 @@ extern "C" int mp_linear(const void* A, const void* W, const float* bias, const 
                          int epilogue, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(A && W && bias && Y, MP_EINVAL, "mp_linear: null pointer");
+  MP_REQUIRE(A && W && Y && (bias || epilogue == MP_EPI_ACCUMULATE), MP_EINVAL, "mp_linear: null pointer");
   MP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && N >= 128 && N % 128 == 0 && K >= 64 && K % 64 == 0, MP_EINVAL,
              "mp_linear: unsupported shape M=%lld N=%lld K=%lld (N %% 128 == 0, K %% 64 == 0)", (long long)M, (long long)N, (long long)K);
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_linear: unknown dtype %d", dtype);
@@ -422,13 +454,14 @@ extern "C" int mp_linear(const void* A, const void* W, const float* bias, const 
   if (M == 0) return MP_OK;
   const bool wide = (N % 256 == 0);
   const bool res = epilogue == MP_EPI_RESIDUAL;
+  const bool f32_out = res || epilogue == MP_EPI_ACCUMULATE;
   // CTA pairs halve the weight traffic out of L2; MANIPOSE_SINGLE_CTA=1 keeps the one-CTA kernel (A/B measurements)
   static const bool single_only = getenv("MANIPOSE_SINGLE_CTA") != nullptr;
-  if (wide && !res && !single_only) return pair_linear(A, W, bias, Y, (int)M, (int)N, (int)K, epilogue, dtype, (cudaStream_t)stream);
+  if (wide && !f32_out && !single_only) return pair_linear(A, W, bias, Y, (int)M, (int)N, (int)K, epilogue, dtype, (cudaStream_t)stream);
   CUtensorMap ta, tw, ty, tr;
   MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
   MP_CHECK(get_tmap(&tw, W, N, K, wide ? 256 : 128, dtype));
-  MP_CHECK(get_tmap(&ty, Y, M, N, kBM, res ? 2 : dtype));
+  MP_CHECK(get_tmap(&ty, Y, M, N, kBM, f32_out ? 2 : dtype));
   if (res)
     MP_CHECK(get_tmap(&tr, resid, M, N, kBM, 2));
   else

@@ -162,19 +162,25 @@ __device__ __forceinline__ void store_row16(uint16_t* __restrict__ p, const floa
 }
 template <int HD>
 __device__ __forceinline__ float dot_smem(const float (&a)[HD], const float* __restrict__ row) {
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int c = 0; c < HD / 4; ++c) {
     const float4 k = reinterpret_cast<const float4*>(row)[c];
     s0 = fmaf(a[4 * c + 0], k.x, s0);
     s1 = fmaf(a[4 * c + 1], k.y, s1);
-    s0 = fmaf(a[4 * c + 2], k.z, s0);
-    s1 = fmaf(a[4 * c + 3], k.w, s1);
+    s2 = fmaf(a[4 * c + 2], k.z, s2);
+    s3 = fmaf(a[4 * c + 3], k.w, s3);
   }
-  return s0 + s1;
+  return (s0 + s1) + (s2 + s3);
 }
 
 constexpr int kAttnBwdThreads = 256;
+// shared-memory row stride in floats: +4 turns the 32-way bank conflict of "thread t writes row t" into 4-way and keeps float4 alignment
+template <int HD>
+struct AttnBwdSmem {
+  static constexpr int kLd = HD + 4;
+  static constexpr size_t kBytes = (size_t)(2 * kAttnBwdThreads * kLd + 2 * kAttnBwdThreads) * sizeof(float);
+};
 
 template <int HD, typename D>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
@@ -182,9 +188,10 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
                      uint16_t* __restrict__ dqkv, int n_items, int L, int G, int n_heads, int C, int n_tok, int n_frames, int temporal,
                      float scale) {
   extern __shared__ __align__(16) float sm[];
-  float* buf_a = sm;                                // [256][HD]: K, then scale * Q
-  float* buf_b = sm + kAttnBwdThreads * HD;         // [256][HD]: V, then dO
-  float* s_lse = sm + 2 * kAttnBwdThreads * HD;     // [256]
+  constexpr int LD = AttnBwdSmem<HD>::kLd;
+  float* buf_a = sm;                                // [256][LD]: K, then scale * Q
+  float* buf_b = sm + kAttnBwdThreads * LD;         // [256][LD]: V, then dO
+  float* s_lse = sm + 2 * kAttnBwdThreads * LD;     // [256]
   float* s_dd = s_lse + kAttnBwdThreads;            // [256]
   const int t = threadIdx.x;
   const int g = t / L, i = t - g * L;
@@ -211,9 +218,9 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     if (active) {
       float kv[HD];
       load_row16<HD, D>(qrow + C, kv, 1.f);
-      store_smem_row<HD>(buf_a + t * HD, kv);
+      store_smem_row<HD>(buf_a + t * LD, kv);
       load_row16<HD, D>(qrow + 2 * C, kv, 1.f);
-      store_smem_row<HD>(buf_b + t * HD, kv);
+      store_smem_row<HD>(buf_b + t * LD, kv);
       load_row16<HD, D>(o + tok * C + head * HD, kv, 1.f);
       load_row16<HD, D>(qrow, q, scale);
       load_row16<HD, D>(dout + tok * C + head * HD, dO, 1.f);
@@ -224,7 +231,7 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     if (active) {
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < L; ++j) {
-        const float s = dot_smem<HD>(q, buf_a + (r0 + j) * HD);
+        const float s = dot_smem<HD>(q, buf_a + (r0 + j) * LD);
         const float mn = fmaxf(m, s);
         l = l * __expf(m - mn) + __expf(s - mn);
         m = mn;
@@ -235,10 +242,10 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
 #pragma unroll
       for (int c = 0; c < HD; ++c) dq[c] = 0.f;
       for (int j = 0; j < L; ++j) {
-        const float* kr = buf_a + (r0 + j) * HD;
+        const float* kr = buf_a + (r0 + j) * LD;
         const float s = dot_smem<HD>(q, kr);
         const float p = __expf(s - m) * inv;
-        const float dp = dot_smem<HD>(dO, buf_b + (r0 + j) * HD);
+        const float dp = dot_smem<HD>(dO, buf_b + (r0 + j) * LD);
         const float ds = p * (dp - dd);
 #pragma unroll
         for (int c = 0; c < HD / 4; ++c) {
@@ -253,8 +260,8 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     }
     __syncthreads();                                 // everybody is done with K / V
     if (active) {
-      store_smem_row<HD>(buf_a + t * HD, q);         // scale * Q
-      store_smem_row<HD>(buf_b + t * HD, dO);
+      store_smem_row<HD>(buf_a + t * LD, q);         // scale * Q
+      store_smem_row<HD>(buf_b + t * LD, dO);
       s_lse[t] = lse;
       s_dd[t] = dd;
     }
@@ -275,8 +282,8 @@ attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
         dv[c] = 0.f;
       }
       for (int ii = 0; ii < L; ++ii) {
-        const float* qr = buf_a + (r0 + ii) * HD;
-        const float* dor = buf_b + (r0 + ii) * HD;
+        const float* qr = buf_a + (r0 + ii) * LD;
+        const float* dor = buf_b + (r0 + ii) * LD;
         const float s = dot_smem<HD>(k, qr);
         const float p = __expf(s - s_lse[r0 + ii]);
         const float dp = dot_smem<HD>(v, dor);
@@ -401,9 +408,16 @@ cast_rowscale_kernel(const float* __restrict__ g, const float* __restrict__ s, u
 }
 
 // -------------------------------------------------------------------------------------------------- Adam (torch.optim.Adam semantics)
+// step_dev != NULL: the step count lives on the device (value before this step; adam_bump_kernel increments it afterwards), so a
+// captured CUDA graph of the training step advances the bias correction on every replay.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
-                                                   float bc2_sqrt, float grad_scale) {
+                                                   float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev) {
+  if (step_dev) {
+    const double t = (double)(*step_dev + 1);
+    bc1 = (float)(1.0 - pow((double)beta1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = fmaf(weight_decay, pi, g[i] * grad_scale);
@@ -415,6 +429,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     p[i] = pi - (lr / bc1) * (mi / denom);
   }
 }
+
+__global__ void adam_bump_kernel(int64_t* step_dev) { *step_dev += 1; }
 
 int stream_grid(int64_t n, int per_cta) {
   int64_t ctas = (n + per_cta - 1) / per_cta;
@@ -438,7 +454,9 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_layernorm_bwd: unknown dtype %d", dtype);
   MP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(dres), MP_EALIGN, "mp_layernorm_bwd: rows must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
-  const int grid = token_grid(n_tokens);
+  // every CTA ends with 2 C atomics on the same dgamma / dbeta words: keep the grid at two CTAs per SM when they are wanted
+  int grid = token_grid(n_tokens);
+  if (dgamma && grid > 2 * sm_count()) grid = 2 * sm_count();
   auto launch = [&](auto kernel) {
     kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, eps, dy, dres, dx, dgamma, dbeta, n_tokens);
   };
@@ -500,7 +518,7 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
   const int grid = (int)((n_items + G - 1) / G);
   const float scale = 1.0f / sqrtf((float)hd);
   auto launch = [&](auto kernel, int HD) -> int {
-    const size_t smem = (size_t)(2 * kAttnBwdThreads * HD + 2 * kAttnBwdThreads) * sizeof(float);
+    const size_t smem = HD == 64 ? AttnBwdSmem<64>::kBytes : AttnBwdSmem<16>::kBytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_kernel): %s", cudaGetErrorString(e));
     kernel<<<grid, kAttnBwdThreads, smem, (cudaStream_t)stream>>>((const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout, (uint16_t*)dqkv,
@@ -598,16 +616,25 @@ int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens
 }
 
 int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int64_t step, float grad_scale, mp_stream_t stream) {
+                 float weight_decay, int64_t step, int64_t* step_dev, float grad_scale, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, MP_EINVAL, "mp_adam_step: bad arguments (step counts from 1)");
+  MP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), MP_EINVAL,
+             "mp_adam_step: bad arguments (step counts from 1, or pass the device counter)");
   if (n == 0) return MP_OK;
-  const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  float bc1 = 1.f, bc2_sqrt = 1.f;
+  if (!step_dev) {
+    bc1 = 1.0f - (float)pow((double)beta1, (double)step);
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  }
   adam_kernel<<<stream_grid(n, 1024), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                                       bc1, bc2_sqrt, grad_scale);
-  return check_launch("adam_kernel");
+                                                                       bc1, bc2_sqrt, grad_scale, step_dev);
+  MP_CHECK(check_launch("adam_kernel"));
+  if (step_dev) {
+    adam_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    return check_launch("adam_bump_kernel");
+  }
+  return MP_OK;
 }
 
 }  // extern "C"

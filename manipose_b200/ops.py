@@ -138,10 +138,22 @@ def softmax_hyp(logits: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ losses / metrics
+_weights_cache = {}
+
+
 def _weights_dev(weights, device):
+    """Per-joint loss weights on the device.  Host tensors (STANDARD_H36M_WEIGHTS is one) are uploaded once and cached by value, so
+    the loss can run inside a CUDA-graph capture (no pageable host copy in the step)."""
     if weights is None:
         return None
-    return _f32(weights.to(device))
+    if weights.is_cuda:
+        return _f32(weights)
+    key = (str(device), tuple(float(v) for v in weights.tolist()))
+    w = _weights_cache.get(key)
+    if w is None:
+        w = _f32(weights.to(device))
+        _weights_cache[key] = w
+    return w
 
 
 def loss_workspace(device, b, k, t):

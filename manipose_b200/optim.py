@@ -141,6 +141,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg = torch.zeros_like(self.flat.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat.flat_param)
         self.step_count = 0
+        # the authoritative step count lives on the device so that a CUDA-graph capture of the training step advances it on replay
+        self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.flat_param.device)
         buckets, index = block_buckets(self.flat, module)
         self.reducer = GradientReducer(self.flat.flat_grad, buckets, group)
         self._bucket_of_block = index
@@ -165,7 +167,7 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self.step_count += 1
         T.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
-                    g["eps"], g["weight_decay"], self.step_count, scale)
+                    g["eps"], g["weight_decay"], self.step_count, scale, step_dev=self.step_dev)
         self._invalidate_shadows()
         return loss
 

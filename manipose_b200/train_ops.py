@@ -96,11 +96,12 @@ def cast_rowscale(g, s, out16):
     return out16
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
+    """``step`` counts from 1 on the host; with ``step_dev`` (int64 device scalar) the count lives on the device instead."""
     rc = L.load().mp_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
-                               float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), L.stream_ptr())
+                               float(beta2), float(eps), float(weight_decay), int(step), L.ptr(step_dev), float(grad_scale), L.stream_ptr())
     L.check(rc, "mp_adam_step")
-    ops._count()
+    ops._count(1 if step_dev is None else 2)
 
 
 def grad_of(p: torch.Tensor) -> torch.Tensor:
@@ -129,14 +130,14 @@ class Scratch:
 def wgrad(dy16, act16, dw, db, scratch: Scratch, n_max: int, k_max: int):
     """dw[N,K] += dy16[M,N]^T act16[M,K]; db[N] += column sums of dy16 (db None to skip).
 
-    tcgen05 path: both operands are transposed so that the token dim is the contraction dim, then mp_linear accumulates
-    into the fp32 gradient through its residual epilogue."""
+    tcgen05 path: both operands are transposed so that the token dim is the contraction dim, then mp_linear(MP_EPI_ACCUMULATE)
+    splits that contraction over the SMs and adds the partial tiles into the fp32 gradient with TMA reduce stores."""
     m, n = dy16.shape
     k = act16.shape[1]
     tdy, tact = scratch.get(m, n_max, k_max, dy16.dtype, dy16.device)
     transpose16(dy16, tdy[:n], db)
     transpose16(act16, tact[:k])
-    ops.linear(tdy[:n], tact[:k], zeros_f32(k_max, dy16.device), dw, L.MP_EPI_RESIDUAL, resid=dw)
+    ops.linear(tdy[:n], tact[:k], None, dw, L.MP_EPI_ACCUMULATE)
 
 
 def dgrad(dy16, w_t16, out16):
