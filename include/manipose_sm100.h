@@ -220,7 +220,8 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
 int mp_gelu_fwd(const void* u, void* a, int64_t n, int dtype, mp_stream_t stream);
 int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, mp_stream_t stream);
 /* Attention backward (Attention.forward, mix_ste.py:257-275): qkv [tokens,3C], o / dout [tokens,C] -> dqkv [tokens,3C], all 16-bit,
- * same token layout and modes as mp_attention; P is recomputed, nothing of size L x L is stored.  head_dim 64 or 16, L <= 256. */
+ * same token layout and modes as mp_attention; mma.sync tensor cores, P is recomputed, nothing of size L x L is stored.  head_dim 64 or
+ * 16, L <= 256. */
 int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C,
                      int n_heads, int mode, int dtype, mp_stream_t stream);
 /* dst[C,Mpad] = src[M,C]^T (zero padded), colsum[C] += column sums of src (NULL to skip).  C % 64 == 0, Mpad % 64 == 0. */

@@ -313,13 +313,17 @@ struct BwdCtx {
 __device__ __forceinline__ void gs_forward(const float* a6, float (&x)[3], float (&z)[3], float (&y)[3], float& na, float& nw,
                                            float (&w)[3]) {
   const float a0 = a6[0], a1 = a6[1], a2 = a6[2], b0 = a6[3], b1 = a6[4], b2 = a6[5];
+  // the backward recompute needs x, y, z to gradient accuracy, not bit-exactly: one reciprocal per normalisation instead of three
+  // IEEE divisions (the kernel is issue-bound: ~5k instructions per pose)
   na = fmaxf(sqrtf(a0 * a0 + a1 * a1 + a2 * a2), 1e-8f);
-  x[0] = a0 / na; x[1] = a1 / na; x[2] = a2 / na;
+  const float ina = 1.0f / na;
+  x[0] = a0 * ina; x[1] = a1 * ina; x[2] = a2 * ina;
   w[0] = x[1] * b2 - x[2] * b1;
   w[1] = x[2] * b0 - x[0] * b2;
   w[2] = x[0] * b1 - x[1] * b0;
   nw = fmaxf(sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), 1e-8f);
-  z[0] = w[0] / nw; z[1] = w[1] / nw; z[2] = w[2] / nw;
+  const float inw = 1.0f / nw;
+  z[0] = w[0] * inw; z[1] = w[1] * inw; z[2] = w[2] * inw;
   y[0] = z[1] * x[2] - z[2] * x[1];
   y[1] = z[2] * x[0] - z[0] * x[2];
   y[2] = z[0] * x[1] - z[1] * x[0];
@@ -328,9 +332,10 @@ __device__ __forceinline__ void gs_forward(const float* a6, float (&x)[3], float
 // gradient of v / max(|v|, 1e-8) given the normalised vector u, the clamped norm n and the upstream gradient gu
 __device__ __forceinline__ void normalize_bwd(const float (&u)[3], float n, bool clamped, const float (&gu)[3], float (&gv)[3]) {
   const float d = clamped ? 0.f : (u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2]);
-  gv[0] = (gu[0] - u[0] * d) / n;
-  gv[1] = (gu[1] - u[1] * d) / n;
-  gv[2] = (gu[2] - u[2] * d) / n;
+  const float inv = 1.0f / n;
+  gv[0] = (gu[0] - u[0] * d) * inv;
+  gv[1] = (gu[1] - u[1] * d) * inv;
+  gv[2] = (gu[2] - u[2] * d) * inv;
 }
 
 template <int RD, int j, int c>
@@ -454,7 +459,7 @@ struct Children<RD, j, kJ> {
   static __device__ __forceinline__ void run(BwdCtx&, const float (&)[9], float (&)[9], float (&)[3]) {}
 };
 
-constexpr int kBwdWarps = 4;
+constexpr int kBwdWarps = 5;   // 19.6 KB of staging per warp: 2 CTAs x 5 warps fill the 227 KB of shared memory
 template <int RD>
 constexpr int bwd_warp_bytes() { return tile_in_bytes<RD>() + kTileOutBytes; }   // rot / grad_rot tile + grad_poses tile
 

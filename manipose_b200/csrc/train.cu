@@ -9,7 +9,10 @@
 //   mix_ste.py:257-275  Attention.forward: softmax(q k^T * scale) v per head               attention_bwd
 //   mix_ste.py:128-150  embeddings + position embeddings                                   small_wgrad, group_rowsum
 //   hpe/main_h36m_lifting.py:755-761  torch.optim.Adam(lr, weight_decay) step              adam
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 #include "row.cuh"
 
 namespace mp {
@@ -127,184 +130,294 @@ __global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ u, 
   }
 }
 
-// -------------------------------------------------------------------------------------------------- attention backward
-// One thread per (item, row): item = (sequence, head), sequence = a frame (spatial, L = tokens) or a (clip, token) track
-// (temporal, L = frames); G = 256 / L items per CTA.  fp32 SIMT with recomputation (no L x L matrix is stored):
-//   pass 1 (thread = query row i):  lse_i, D_i = dO_i . O_i, dQ_i = scale * sum_j dS_ij K_j,  dS_ij = P_ij (dO_i . V_j - D_i)
-//   pass 2 (thread = key row j):    dV_j = sum_i P_ij dO_i,  dK_j = scale * sum_i dS_ij Q_i   (head_dim 64: two column halves)
-// K / V (pass 1) and scale * Q / dO (pass 2) of all rows of the CTA sit in shared memory as fp32 and are read as broadcasts.
-template <int HD, typename D>
-__device__ __forceinline__ void load_row16(const uint16_t* __restrict__ p, float (&v)[HD], float mul) {
-#pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + c);
-    const float2 a = D::unpack2(u.x), b = D::unpack2(u.y), e = D::unpack2(u.z), f = D::unpack2(u.w);
-    v[8 * c + 0] = a.x * mul; v[8 * c + 1] = a.y * mul; v[8 * c + 2] = b.x * mul; v[8 * c + 3] = b.y * mul;
-    v[8 * c + 4] = e.x * mul; v[8 * c + 5] = e.y * mul; v[8 * c + 6] = f.x * mul; v[8 * c + 7] = f.y * mul;
-  }
+// -------------------------------------------------------------------------------------------------- attention backward on tensor cores
+// mma.sync m16n8k16, P recomputed (nothing of size L x L is stored): one CTA per (sequence, head) -- a frame (spatial, L = tokens) or a
+// (clip, token) track (temporal, L = frames) -- with Q / K / V / dO of the sequence in
+// shared memory as 16-bit rows (+16 bytes of padding: conflict-free ldmatrix), each warp owns 16-row tiles:
+//   sweep 0 (rows = queries)  lse_i = log2 sum_j exp2(s_ij * scale * log2 e)                         S = Q K^T
+//   sweep A (rows = queries)  dS = P o (dO V^T - D_i),  dQ = scale * dS K                            P = exp2(S' - lse_i)
+//   sweep B (rows = keys)     P^T = exp2((K Q^T)' - lse_i), dS^T = P^T o (V dO^T - D_i),  dV = P^T dO,  dK = scale * dS^T Q
+// P and dS go from the accumulator layout straight into A fragments (16-bit), as in the forward kernel (attention.cu::attend_tile).
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-template <int N>
-__device__ __forceinline__ void store_smem_row(float* __restrict__ dst, const float (&v)[N]) {
-#pragma unroll
-  for (int c = 0; c < N / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-template <int N, typename D>
-__device__ __forceinline__ void store_row16(uint16_t* __restrict__ p, const float (&v)[N], float mul) {
-#pragma unroll
-  for (int c = 0; c < N / 8; ++c) {
-    uint4 u;
-    u.x = D::pack2(v[8 * c + 0] * mul, v[8 * c + 1] * mul);
-    u.y = D::pack2(v[8 * c + 2] * mul, v[8 * c + 3] * mul);
-    u.z = D::pack2(v[8 * c + 4] * mul, v[8 * c + 5] * mul);
-    u.w = D::pack2(v[8 * c + 6] * mul, v[8 * c + 7] * mul);
-    reinterpret_cast<uint4*>(p)[c] = u;
-  }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-template <int HD>
-__device__ __forceinline__ float dot_smem(const float (&a)[HD], const float* __restrict__ row) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int c = 0; c < HD / 4; ++c) {
-    const float4 k = reinterpret_cast<const float4*>(row)[c];
-    s0 = fmaf(a[4 * c + 0], k.x, s0);
-    s1 = fmaf(a[4 * c + 1], k.y, s1);
-    s2 = fmaf(a[4 * c + 2], k.z, s2);
-    s3 = fmaf(a[4 * c + 3], k.w, s3);
-  }
-  return (s0 + s1) + (s2 + s3);
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-constexpr int kAttnBwdThreads = 256;
-// shared-memory row stride in floats: +4 turns the 32-way bank conflict of "thread t writes row t" into 4-way and keeps float4 alignment
-template <int HD>
-struct AttnBwdSmem {
-  static constexpr int kLd = HD + 4;
-  static constexpr size_t kBytes = (size_t)(2 * kAttnBwdThreads * kLd + 2 * kAttnBwdThreads) * sizeof(float);
-};
-
-template <int HD, typename D>
-__global__ void __launch_bounds__(kAttnBwdThreads, 1)
-attention_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
-                     uint16_t* __restrict__ dqkv, int n_items, int L, int G, int n_heads, int C, int n_tok, int n_frames, int temporal,
-                     float scale) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int LD = AttnBwdSmem<HD>::kLd;
-  float* buf_a = sm;                                // [256][LD]: K, then scale * Q
-  float* buf_b = sm + kAttnBwdThreads * LD;         // [256][LD]: V, then dO
-  float* s_lse = sm + 2 * kAttnBwdThreads * LD;     // [256]
-  float* s_dd = s_lse + kAttnBwdThreads;            // [256]
-  const int t = threadIdx.x;
-  const int g = t / L, i = t - g * L;
-  const int item = blockIdx.x * G + g;
-  const bool active = g < G && item < n_items;
-  int64_t tok = 0;
-  int head = 0;
-  if (active) {
-    head = item % n_heads;
-    const int seq = item / n_heads;
-    if (temporal) {
-      const int clip = seq / n_tok, tj = seq - clip * n_tok;
-      tok = ((int64_t)clip * n_frames + i) * n_tok + tj;
-    } else {
-      tok = (int64_t)seq * n_tok + i;
-    }
-  }
-  const uint16_t* qrow = qkv + tok * 3 * C + head * HD;
-  const int r0 = g * L;
-
-  float lse = 0.f, dd = 0.f;
-  {
-    float q[HD], dO[HD];
-    if (active) {
-      float kv[HD];
-      load_row16<HD, D>(qrow + C, kv, 1.f);
-      store_smem_row<HD>(buf_a + t * LD, kv);
-      load_row16<HD, D>(qrow + 2 * C, kv, 1.f);
-      store_smem_row<HD>(buf_b + t * LD, kv);
-      load_row16<HD, D>(o + tok * C + head * HD, kv, 1.f);
-      load_row16<HD, D>(qrow, q, scale);
-      load_row16<HD, D>(dout + tok * C + head * HD, dO, 1.f);
+// log2-domain log-sum-exp of the 16 score rows of one tile against columns [0, n_cols): returns rows g (lse[0]) and g + 8 (lse[1])
+template <int HD, int LD, typename D>
+__device__ __forceinline__ void lse_tile(uint32_t a_addr, uint32_t b_addr, int n_cols, int n_cols_pad, float scale_log2, int lane, float (&lse)[2]) {
+  constexpr int KS = HD / 16;
+  const int t = lane & 3;
+  const uint32_t q_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 16);
+  const uint32_t k_off = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * LD + ((lane >> 3) & 1) * 16);
+  uint32_t af[KS][4];
 #pragma unroll
-      for (int c = 0; c < HD; ++c) dd = fmaf(dO[c], kv[c], dd);
-    }
-    __syncthreads();
-    if (active) {
-      float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < L; ++j) {
-        const float s = dot_smem<HD>(q, buf_a + (r0 + j) * LD);
-        const float mn = fmaxf(m, s);
-        l = l * __expf(m - mn) + __expf(s - mn);
-        m = mn;
+  for (int ks = 0; ks < KS; ++ks) ldsm_x4(af[ks], a_addr + q_off + ks * 32);
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  for (int col0 = 0; col0 < n_cols_pad; col0 += 32) {
+    const uint32_t bc = b_addr + k_off + (uint32_t)(col0 * LD);
+    float sc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bf[4];
+        ldsm_x4(bf, bc + np * 16 * LD + ks * 32);
+        ptx::mma_16816<D>(sc[np * 2 + 0], af[ks], bf[0], bf[1]);
+        ptx::mma_16816<D>(sc[np * 2 + 1], af[ks], bf[2], bf[3]);
       }
-      const float inv = 1.0f / l;
-      lse = m + __logf(l);
-      float dq[HD];
+    }
+    if (col0 + 32 > n_cols) {
 #pragma unroll
-      for (int c = 0; c < HD; ++c) dq[c] = 0.f;
-      for (int j = 0; j < L; ++j) {
-        const float* kr = buf_a + (r0 + j) * LD;
-        const float s = dot_smem<HD>(q, kr);
-        const float p = __expf(s - m) * inv;
-        const float dp = dot_smem<HD>(dO, buf_b + (r0 + j) * LD);
-        const float ds = p * (dp - dd);
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int c = 0; c < HD / 4; ++c) {
-          const float4 k = reinterpret_cast<const float4*>(kr)[c];
-          dq[4 * c + 0] = fmaf(ds, k.x, dq[4 * c + 0]);
-          dq[4 * c + 1] = fmaf(ds, k.y, dq[4 * c + 1]);
-          dq[4 * c + 2] = fmaf(ds, k.z, dq[4 * c + 2]);
-          dq[4 * c + 3] = fmaf(ds, k.w, dq[4 * c + 3]);
+        for (int e = 0; e < 4; ++e)
+          if (col0 + nt * 8 + 2 * t + (e & 1) >= n_cols) sc[nt][e] = -INFINITY;
+    }
+    float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      c0 = fmaxf(c0, fmaxf(sc[nt][0], sc[nt][1]));
+      c1 = fmaxf(c1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    const float mn0 = fmaxf(m[0], quad_max(c0)), mn1 = fmaxf(m[1], quad_max(c1));
+    l[0] *= fast_exp2((m[0] - mn0) * scale_log2);
+    l[1] *= fast_exp2((m[1] - mn1) * scale_log2);
+    m[0] = mn0;
+    m[1] = mn1;
+    const float ms0 = -mn0 * scale_log2, ms1 = -mn1 * scale_log2;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      l[0] += fast_exp2(fmaf(sc[nt][0], scale_log2, ms0)) + fast_exp2(fmaf(sc[nt][1], scale_log2, ms0));
+      l[1] += fast_exp2(fmaf(sc[nt][2], scale_log2, ms1)) + fast_exp2(fmaf(sc[nt][3], scale_log2, ms1));
+    }
+  }
+  lse[0] = fmaf(m[0], scale_log2, log2f(quad_sum(l[0])));
+  lse[1] = fmaf(m[1], scale_log2, log2f(quad_sum(l[1])));
+}
+
+// One 16-row tile against all columns.  a1/a2: the tile's rows of the two "row side" operands (score GEMM, dP GEMM); b1/b2: row 0 of
+// the "column side" operands; x1/x2: row 0 of the operands contracted over the columns (x1 with P -> out1, only kByCol; x2 with dS ->
+// out2).  Statistics lse / dd are indexed by row (sweep A) or by column (sweep B, kByCol).  Padded columns contribute nothing.
+template <int HD, int LD, typename D, bool kByCol>
+__device__ __forceinline__ void bwd_sweep(uint32_t a1_addr, uint32_t a2_addr, uint32_t b1_addr, uint32_t b2_addr, uint32_t x1_addr,
+                                          uint32_t x2_addr, int n_cols, int n_cols_pad, float scale_log2, const float* __restrict__ lse,
+                                          const float* __restrict__ dd, int row0, int lane, float (&out1)[HD / 8][4], float (&out2)[HD / 8][4]) {
+  constexpr int KS = HD / 16, NT = HD / 8;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t q_off = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 16);
+  const uint32_t k_off = (uint32_t)(((lane & 7) + (lane >> 4) * 8) * LD + ((lane >> 3) & 1) * 16);
+  const uint32_t v_off = q_off;
+  uint32_t a1f[KS][4], a2f[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    ldsm_x4(a1f[ks], a1_addr + q_off + ks * 32);
+    ldsm_x4(a2f[ks], a2_addr + q_off + ks * 32);
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    out1[i][0] = out1[i][1] = out1[i][2] = out1[i][3] = 0.f;
+    out2[i][0] = out2[i][1] = out2[i][2] = out2[i][3] = 0.f;
+  }
+  float lr[2] = {0.f, 0.f}, dr[2] = {0.f, 0.f};
+  if (!kByCol) {
+    lr[0] = lse[row0 + g];
+    lr[1] = lse[row0 + g + 8];
+    dr[0] = dd[row0 + g];
+    dr[1] = dd[row0 + g + 8];
+  }
+  for (int col0 = 0; col0 < n_cols_pad; col0 += 32) {
+    const uint32_t b1c = b1_addr + k_off + (uint32_t)(col0 * LD);
+    const uint32_t b2c = b2_addr + k_off + (uint32_t)(col0 * LD);
+    float sc[4][4], dp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bf[4];
+        ldsm_x4(bf, b1c + np * 16 * LD + ks * 32);
+        ptx::mma_16816<D>(sc[np * 2 + 0], a1f[ks], bf[0], bf[1]);
+        ptx::mma_16816<D>(sc[np * 2 + 1], a1f[ks], bf[2], bf[3]);
+        ldsm_x4(bf, b2c + np * 16 * LD + ks * 32);
+        ptx::mma_16816<D>(dp[np * 2 + 0], a2f[ks], bf[0], bf[1]);
+        ptx::mma_16816<D>(dp[np * 2 + 1], a2f[ks], bf[2], bf[3]);
+      }
+    }
+    uint32_t pf[2][4], dsf[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float pe[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = col0 + nt * 8 + 2 * t + (e & 1);
+        const float l_ = kByCol ? lse[col] : lr[e >> 1];
+        const float d_ = kByCol ? dd[col] : dr[e >> 1];
+        float v = fast_exp2(fmaf(sc[nt][e], scale_log2, -l_));
+        if (col >= n_cols) v = 0.f;
+        pe[e] = v;
+        ds[e] = v * (dp[nt][e] - d_);
+      }
+      pf[nt >> 1][(nt & 1) * 2 + 0] = D::pack2(pe[0], pe[1]);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = D::pack2(pe[2], pe[3]);
+      dsf[nt >> 1][(nt & 1) * 2 + 0] = D::pack2(ds[0], ds[1]);
+      dsf[nt >> 1][(nt & 1) * 2 + 1] = D::pack2(ds[2], ds[3]);
+    }
+    const uint32_t x1c = x1_addr + v_off + (uint32_t)(col0 * LD);
+    const uint32_t x2c = x2_addr + v_off + (uint32_t)(col0 * LD);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+      for (int dpi = 0; dpi < NT / 2; ++dpi) {
+        uint32_t xf[4];
+        if (kByCol) {
+          ldsm_x4_t(xf, x1c + kk * 16 * LD + dpi * 32);
+          ptx::mma_16816<D>(out1[dpi * 2 + 0], pf[kk], xf[0], xf[1]);
+          ptx::mma_16816<D>(out1[dpi * 2 + 1], pf[kk], xf[2], xf[3]);
+        }
+        ldsm_x4_t(xf, x2c + kk * 16 * LD + dpi * 32);
+        ptx::mma_16816<D>(out2[dpi * 2 + 0], dsf[kk], xf[0], xf[1]);
+        ptx::mma_16816<D>(out2[dpi * 2 + 1], dsf[kk], xf[2], xf[3]);
+      }
+    }
+  }
+}
+
+constexpr int kAttnBwdMmaWarps = 8;
+
+template <int HD, typename D>
+__global__ void __launch_bounds__(kAttnBwdMmaWarps * 32)
+attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
+                         uint16_t* __restrict__ dqkv, int L, int Lp, int n_heads, int C, int n_tok, int n_frames, int temporal) {
+  constexpr int LD = HD * 2 + 16;
+  constexpr int CH = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem_b[];
+  uint8_t* sq = smem_b;
+  uint8_t* sk = sq + (size_t)Lp * LD;
+  uint8_t* sv = sk + (size_t)Lp * LD;
+  uint8_t* sdo = sv + (size_t)Lp * LD;
+  float* s_lse = reinterpret_cast<float*>(sdo + (size_t)Lp * LD);
+  float* s_dd = s_lse + Lp;
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(s_dd + Lp);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.x % n_heads, seq = blockIdx.x / n_heads;
+  int64_t tok0, tstride;
+  if (temporal) {
+    const int clip = seq / n_tok, tj = seq - clip * n_tok;
+    tok0 = (int64_t)clip * n_frames * n_tok + tj;
+    tstride = n_tok;
+  } else {
+    tok0 = (int64_t)seq * n_tok;
+    tstride = 1;
+  }
+  const uint16_t* qkv_base = qkv + tok0 * 3 * C + head * HD;
+  const uint16_t* do_base = dout + tok0 * C + head * HD;
+  const uint16_t* o_base = o + tok0 * C + head * HD;
+  uint16_t* dqkv_base = dqkv + tok0 * 3 * C + head * HD;
+  const int64_t qkv_stride = tstride * 3 * C, o_stride = tstride * C;
+
+  // ---- stage Q, K, V, dO rows [0, L); zero rows [L, Lp)
+  const int total = 4 * Lp * CH;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int ch = i % CH;
+    const int r = (i / CH) % Lp;
+    const int sel = i / (CH * Lp);
+    uint8_t* dst = smem_b + ((size_t)sel * Lp + r) * LD + ch * 16;
+    if (r < L) {
+      const uint16_t* src = sel < 3 ? qkv_base + (int64_t)r * qkv_stride + sel * C + ch * 8 : do_base + (int64_t)r * o_stride + ch * 8;
+      ptx::cp_async16(dst, src);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  ptx::cp_async_commit();
+  ptx::cp_async_wait<0>();
+  __syncthreads();
+  // ---- D_i = dO_i . O_i
+  for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
+    float acc = 0.f;
+    if (r < L) {
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sdo + (size_t)r * LD + ch * 16);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(o_base + (int64_t)r * o_stride) + ch);
+        const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 x = D::unpack2(au[k]), y = D::unpack2(bu[k]);
+          acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
         }
       }
-      store_row16<HD, D>(dqkv + tok * 3 * C + head * HD, dq, scale);
     }
-    __syncthreads();                                 // everybody is done with K / V
-    if (active) {
-      store_smem_row<HD>(buf_a + t * LD, q);         // scale * Q
-      store_smem_row<HD>(buf_b + t * LD, dO);
-      s_lse[t] = lse;
-      s_dd[t] = dd;
+    s_dd[r] = acc;
+    s_lse[r] = 0.f;
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)HD);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  // ---- sweep 0: log-sum-exp per query row
+  for (int mt = warp; mt * 16 < L; mt += n_warps) {
+    float lse[2];
+    lse_tile<HD, LD, D>(smem_u32(sq) + (uint32_t)(mt * 16 * LD), smem_u32(sk), L, Lp, scale_log2, lane, lse);
+    if (t == 0) {
+      s_lse[mt * 16 + g] = lse[0];
+      s_lse[mt * 16 + g + 8] = lse[1];
     }
   }
   __syncthreads();
-  if (!active) return;
-  {
-    constexpr int HH = HD >= 64 ? 32 : HD;           // columns of dK / dV accumulated per round
-    float k[HD], v[HD];
-    load_row16<HD, D>(qrow + C, k, 1.f);
-    load_row16<HD, D>(qrow + 2 * C, v, 1.f);
-#pragma unroll 1
-    for (int half = 0; half < HD / HH; ++half) {
-      float dk[HH], dv[HH];
+  uint8_t* stg = stage_base + (size_t)warp * 16 * LD;
+  auto store_tile = [&](const float (&v)[HD / 8][4], float mul, int mt, int col_off) {
+    __syncwarp();
 #pragma unroll
-      for (int c = 0; c < HH; ++c) {
-        dk[c] = 0.f;
-        dv[c] = 0.f;
-      }
-      for (int ii = 0; ii < L; ++ii) {
-        const float* qr = buf_a + (r0 + ii) * LD;
-        const float* dor = buf_b + (r0 + ii) * LD;
-        const float s = dot_smem<HD>(k, qr);
-        const float p = __expf(s - s_lse[r0 + ii]);
-        const float dp = dot_smem<HD>(v, dor);
-        const float ds = p * (dp - s_dd[r0 + ii]);
-#pragma unroll
-        for (int c = 0; c < HH / 4; ++c) {
-          const float4 a = reinterpret_cast<const float4*>(dor + half * HH)[c];
-          const float4 b = reinterpret_cast<const float4*>(qr + half * HH)[c];
-          dv[4 * c + 0] = fmaf(p, a.x, dv[4 * c + 0]);
-          dv[4 * c + 1] = fmaf(p, a.y, dv[4 * c + 1]);
-          dv[4 * c + 2] = fmaf(p, a.z, dv[4 * c + 2]);
-          dv[4 * c + 3] = fmaf(p, a.w, dv[4 * c + 3]);
-          dk[4 * c + 0] = fmaf(ds, b.x, dk[4 * c + 0]);
-          dk[4 * c + 1] = fmaf(ds, b.y, dk[4 * c + 1]);
-          dk[4 * c + 2] = fmaf(ds, b.z, dk[4 * c + 2]);
-          dk[4 * c + 3] = fmaf(ds, b.w, dk[4 * c + 3]);
-        }
-      }
-      store_row16<HH, D>(dqkv + tok * 3 * C + C + head * HD + half * HH, dk, 1.f);
-      store_row16<HH, D>(dqkv + tok * 3 * C + 2 * C + head * HD + half * HH, dv, 1.f);
+    for (int i = 0; i < HD / 8; ++i) {
+      *reinterpret_cast<uint32_t*>(stg + (size_t)g * LD + (i * 8 + 2 * t) * 2) = D::pack2(v[i][0] * mul, v[i][1] * mul);
+      *reinterpret_cast<uint32_t*>(stg + (size_t)(g + 8) * LD + (i * 8 + 2 * t) * 2) = D::pack2(v[i][2] * mul, v[i][3] * mul);
     }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+      const int rr = i / CH, ch = i % CH, r = mt * 16 + rr;
+      if (r < L)
+        *reinterpret_cast<uint4*>(dqkv_base + (int64_t)r * qkv_stride + col_off + ch * 8) = *reinterpret_cast<const uint4*>(stg + (size_t)rr * LD + ch * 16);
+    }
+  };
+  // ---- sweep A: dQ
+  for (int mt = warp; mt * 16 < L; mt += n_warps) {
+    float unused[HD / 8][4], dq[HD / 8][4];
+    const uint32_t ro = (uint32_t)(mt * 16 * LD);
+    bwd_sweep<HD, LD, D, false>(smem_u32(sq) + ro, smem_u32(sdo) + ro, smem_u32(sk), smem_u32(sv), 0u, smem_u32(sk), L, Lp, scale_log2, s_lse,
+                                s_dd, mt * 16, lane, unused, dq);
+    store_tile(dq, scale, mt, 0);
+  }
+  // ---- sweep B: dK, dV
+  for (int mt = warp; mt * 16 < L; mt += n_warps) {
+    float dv[HD / 8][4], dk[HD / 8][4];
+    const uint32_t ro = (uint32_t)(mt * 16 * LD);
+    bwd_sweep<HD, LD, D, true>(smem_u32(sk) + ro, smem_u32(sv) + ro, smem_u32(sq), smem_u32(sdo), smem_u32(sdo), smem_u32(sq), L, Lp, scale_log2,
+                               s_lse, s_dd, mt * 16, lane, dv, dk);
+    store_tile(dk, scale, mt, C);
+    store_tile(dv, 1.0f, mt, 2 * C);
   }
 }
 
@@ -508,26 +621,27 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
   MP_REQUIRE(C % n_heads == 0 && (hd == 64 || hd == 16), MP_EUNSUPPORTED, "mp_attention_bwd: head_dim %d (built for 64 and 16)", hd);
   const int temporal = mode == MP_ATTN_TEMPORAL;
   const int64_t L = temporal ? n_frames : n_tok;
-  MP_REQUIRE(L <= kAttnBwdThreads, MP_EUNSUPPORTED, "mp_attention_bwd: sequence length %lld > %d", (long long)L, kAttnBwdThreads);
+  MP_REQUIRE(L <= 256, MP_EUNSUPPORTED, "mp_attention_bwd: sequence length %lld > 256 (shared-memory resident sequence)", (long long)L);
   MP_REQUIRE(aligned16(qkv) && aligned16(o) && aligned16(dout) && aligned16(dqkv), MP_EALIGN, "mp_attention_bwd: pointers must be 16-byte aligned");
   const int64_t n_seq = temporal ? n_clips * n_tok : n_clips * n_frames;
   const int64_t n_items = n_seq * n_heads;
   MP_REQUIRE(n_items < ((int64_t)1 << 31), MP_EINVAL, "mp_attention_bwd: too many (sequence, head) items");
   if (n_items == 0) return MP_OK;
-  const int G = kAttnBwdThreads / (int)L;
-  const int grid = (int)((n_items + G - 1) / G);
-  const float scale = 1.0f / sqrtf((float)hd);
-  auto launch = [&](auto kernel, int HD) -> int {
-    const size_t smem = HD == 64 ? AttnBwdSmem<64>::kBytes : AttnBwdSmem<16>::kBytes;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_kernel): %s", cudaGetErrorString(e));
-    kernel<<<grid, kAttnBwdThreads, smem, (cudaStream_t)stream>>>((const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout, (uint16_t*)dqkv,
-                                                                  (int)n_items, (int)L, G, n_heads, C, n_tok, (int)n_frames, temporal, scale);
-    return check_launch("attention_bwd_kernel");
-  };
   const bool bf = dtype == MP_DTYPE_BF16;
-  if (hd == 64) return bf ? launch(attention_bwd_kernel<64, Bf16>, 64) : launch(attention_bwd_kernel<64, Fp16>, 64);
-  return bf ? launch(attention_bwd_kernel<16, Bf16>, 16) : launch(attention_bwd_kernel<16, Fp16>, 16);
+  const int Lp = ((int)L + 31) & ~31;
+  int n_warps = Lp / 16;
+  if (n_warps > kAttnBwdMmaWarps) n_warps = kAttnBwdMmaWarps;
+  auto launch_mma = [&](auto kernel, int HD) -> int {
+    const int LD = HD * 2 + 16;
+    const size_t smem = (size_t)4 * Lp * LD + (size_t)2 * Lp * sizeof(float) + (size_t)n_warps * 16 * LD;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_mma_kernel): %s", cudaGetErrorString(e));
+    kernel<<<(unsigned)n_items, n_warps * 32, smem, (cudaStream_t)stream>>>((const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout,
+                                                                           (uint16_t*)dqkv, (int)L, Lp, n_heads, C, n_tok, (int)n_frames, temporal);
+    return check_launch("attention_bwd_mma_kernel");
+  };
+  if (hd == 64) return bf ? launch_mma(attention_bwd_mma_kernel<64, Bf16>, 64) : launch_mma(attention_bwd_mma_kernel<64, Fp16>, 64);
+  return bf ? launch_mma(attention_bwd_mma_kernel<16, Bf16>, 16) : launch_mma(attention_bwd_mma_kernel<16, Fp16>, 16);
 }
 
 int mp_transpose16(const void* src, void* dst, float* colsum, int64_t M, int64_t C, int64_t Mpad, int dtype, mp_stream_t stream) {
