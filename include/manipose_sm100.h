@@ -224,6 +224,16 @@ int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, m
  * 16, L <= 256. */
 int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C,
                      int n_heads, int mode, int dtype, mp_stream_t stream);
+/* Weight gradient dW[n_out, k_in] (fp32) += dY[tokens, n_out]^T X[tokens, k_in] (16-bit), both operands read in place as MN-major
+ * UMMA operands (no transposed copies); the token contraction is split over the SMs, partial tiles added with TMA reduce stores.
+ * n_out % 128 == 0, k_in % 128 == 0. */
+int mp_wgrad(const void* dY, const void* X, float* dW, int64_t n_tokens, int64_t n_out, int64_t k_in, int dtype, mp_stream_t stream);
+/* colsum[C] (fp32) += column sums of a 16-bit [M, C] matrix (bias gradients). */
+int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream);
+/* Refresh the 16-bit shadows of n_weights GEMM weights in ONE launch (after an optimizer step).  table (device, int64[n_weights][5]) =
+ * {fp32 source pointer, 16-bit shadow [rows, cols] pointer, transposed shadow [cols, rows] pointer or 0, rows, cols}; rows, cols % 64 == 0;
+ * max_tiles = max over weights of rows * cols / 4096. */
+int mp_refresh_shadows(const int64_t* table, int n_weights, int max_tiles, int dtype, mp_stream_t stream);
 /* dst[C,Mpad] = src[M,C]^T (zero padded), colsum[C] += column sums of src (NULL to skip).  C % 64 == 0, Mpad % 64 == 0. */
 int mp_transpose16(const void* src, void* dst, float* colsum, int64_t M, int64_t C, int64_t Mpad, int dtype, mp_stream_t stream);
 /* out[(row / div) % mod, :] += x[row, :]  (gradients of Spatial_pos_embed / Temporal_pos_embed, mix_ste.py:137,149). */

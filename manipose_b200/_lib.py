@@ -52,6 +52,9 @@ SIGNATURES = {
     "mp_gelu_fwd": (I, [P, P, I64, I, P]),
     "mp_gelu_bwd": (I, [P, P, P, I64, I, P]),
     "mp_attention_bwd": (I, [P, P, P, P, I64, I64, I, I, I, I, I, P]),
+    "mp_wgrad": (I, [P, P, P, I64, I64, I64, I, P]),
+    "mp_colsum16": (I, [P, P, I64, I64, I, P]),
+    "mp_refresh_shadows": (I, [P, I, I, I, P]),
     "mp_transpose16": (I, [P, P, P, I64, I64, I64, I, P]),
     "mp_group_rowsum": (I, [P, P, I64, I, I64, I64, P]),
     "mp_small_wgrad": (I, [P, P, P, P, I64, I, I, P]),

@@ -185,14 +185,31 @@ class MixSTE(nn.Module):
         return out
 
     def _shadow_weights(self) -> List[torch.Tensor]:
-        """16-bit shadows of the GEMM weights, refreshed when a parameter changed (optimizer.step / load_state_dict)."""
+        """16-bit shadows of the GEMM weights, refreshed (ONE launch for all of them, mp_refresh_shadows) when a parameter changed
+        (optimizer.step / load_state_dict).  The buffers and the device-side table of pointers are allocated once."""
         params = self._gemm_params()
         dt = ops.DTYPE_CODE[self.compute_dtype]
         key = (dt,) + _version_key(params)
         if key != self._shadow_key:
-            self._shadow_list = [ops.cast16(p.detach(), dt) for p in params]
+            self._refresh_shadows(params, dt)
             self._shadow_key = key
         return self._shadow_list
+
+    def _refresh_shadows(self, params, dt) -> None:
+        want_t = getattr(self, "_shadow_want_t", False)
+        alloc_key = (dt, want_t) + tuple(p.data_ptr() for p in params)
+        if getattr(self, "_shadow_alloc_key", None) != alloc_key:
+            td, dev = ops.TORCH_DTYPE[dt], params[0].device
+            self._shadow_list = [torch.empty(p.shape, dtype=td, device=dev) for p in params]
+            self._shadow_t_list = [torch.empty((p.shape[1], p.shape[0]), dtype=td, device=dev) for p in params] if want_t else None
+            rows = [[p.data_ptr(), s.data_ptr(), self._shadow_t_list[i].data_ptr() if want_t else 0, p.shape[0], p.shape[1]]
+                    for i, (p, s) in enumerate(zip(params, self._shadow_list))]
+            self._shadow_table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            self._shadow_max_tiles = max(p.shape[0] * p.shape[1] // 4096 for p in params)
+            self._shadow_alloc_key = alloc_key
+        rc = L.load().mp_refresh_shadows(L.ptr(self._shadow_table), len(params), self._shadow_max_tiles, dt, L.stream_ptr())
+        L.check(rc, "mp_refresh_shadows")
+        ops._count()
 
     def _workspace(self, n_tokens: int, device) -> Dict[str, torch.Tensor]:
         c = self.embed_dim
@@ -271,11 +288,11 @@ class MixSTE(nn.Module):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _shadow_weights_t(self) -> List[torch.Tensor]:
-        """Transposed 16-bit shadows [K, N] of the GEMM weights (operand of dgrad = dY W), refreshed with the shadows."""
-        w = self._shadow_weights()
-        if getattr(self, "_shadow_t_key", None) != self._shadow_key:
-            self._shadow_t_list = [T.transpose16(x, torch.empty((x.shape[1], x.shape[0]), dtype=x.dtype, device=x.device)) for x in w]
-            self._shadow_t_key = self._shadow_key
+        """Transposed 16-bit shadows [K, N] of the GEMM weights (operand of dgrad = dY W), written by the same refresh launch."""
+        if not getattr(self, "_shadow_want_t", False):
+            self._shadow_want_t = True
+            self._shadow_key = None          # re-run the refresh with the transposed outputs in the table
+        self._shadow_weights()
         return self._shadow_t_list
 
     def _block_list(self):
@@ -371,9 +388,6 @@ class MixSTE(nn.Module):
         blocks = self._block_list()
         n_tokens = dfeat.shape[0]
         dev = dfeat.device
-        if getattr(self, "_scratch", None) is None:
-            self._scratch = T.Scratch()
-        n_max, k_max = max(3 * c, hidden), max(c, hidden)
         g = T.grad_of
         b16 = lambda cols: torch.empty((n_tokens, cols), dtype=td, device=dev)
         dx = dfeat.contiguous().clone()            # fp32 gradient of the residual stream, updated in place below
@@ -390,21 +404,21 @@ class MixSTE(nn.Module):
                 T.layernorm_bwd(rec["x2"], post.weight, post.eps, dx, None, dx, g(post.weight), g(post.bias), dt)
             # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1)))))
             T.cast_rowscale(dx, rec["s2"], dy16)
-            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), g(blk.mlp.fc2.bias), self._scratch, n_max, k_max)
+            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), g(blk.mlp.fc2.bias))
             da = flat[:n_tokens * hidden].view(n_tokens, hidden)
             T.dgrad(dy16, w_t[wi + 3], da)
             T.gelu_bwd(rec["u"], da, da)
-            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), g(blk.mlp.fc1.bias), self._scratch, n_max, k_max)
+            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), g(blk.mlp.fc1.bias))
             T.dgrad(da, w_t[wi + 2], dy16)
             T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt)
             # ---- attention branch: x1 = x0 + s1 * proj(attention(qkv(norm1(x0))))
             T.cast_rowscale(dx, rec["s1"], dy16)
-            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), g(blk.attn.proj.bias), self._scratch, n_max, k_max)
+            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), g(blk.attn.proj.bias))
             do = b16(c)
             T.dgrad(dy16, w_t[wi + 1], do)
             dqkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
             T.attention_bwd(rec["qkv"], rec["o"], do, dqkv, n_clips, n_frames, n_tok, c, heads, mode)
-            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), g(blk.attn.qkv.bias), self._scratch, n_max, k_max)
+            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), g(blk.attn.qkv.bias))
             T.dgrad(dqkv, w_t[wi + 0], dy16)
             T.layernorm_bwd(rec["x0"], blk.norm1.weight, blk.norm1.eps, dy16, dx, dx, g(blk.norm1.weight), g(blk.norm1.bias), dt)
             rec.clear()

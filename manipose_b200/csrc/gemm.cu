@@ -48,7 +48,10 @@ struct GemmCfg {
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int BN, int EPI, typename D>
+// kMn: both operands are MN-major -- A is [K, M] and W is [K, N] row-major in global memory (the contraction index is the ROW index):
+// D[M,N] += A^T W.  Used for weight gradients dW[N_out, K_in] += dY^T X with dY [tokens, N_out], X [tokens, K_in] read in place (no
+// transposed copies); tiles are staged as 64-row x 64-column boxes, one per 64-element MN atom, 8 KB apart.
+template <int BN, int EPI, typename D, bool kMn = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
               const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ bias, int M, int N, int K, int splits) {
@@ -124,8 +127,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           ptx::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * kBK, m_blk * kBM);
-          ptx::tma_load_2d(sa + Cfg::kABytes, &tm_w, &full[stage], kb * kBK, n_blk * BN);
+          if (kMn) {
+#pragma unroll
+            for (int a = 0; a < kBM / 64; ++a) ptx::tma_load_2d(sa + a * 8192, &tm_a, &full[stage], m_blk * kBM + a * 64, kb * kBK);
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) ptx::tma_load_2d(sa + Cfg::kABytes + b * 8192, &tm_w, &full[stage], n_blk * BN + b * 64, kb * kBK);
+          } else {
+            ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * kBK, m_blk * kBM);
+            ptx::tma_load_2d(sa + Cfg::kABytes, &tm_w, &full[stage], kb * kBK, n_blk * BN);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -136,7 +146,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = ptx::umma_idesc_16(kBM, BN, D::kUmmaFmt);
+      constexpr uint32_t idesc = kMn ? ptx::umma_idesc_16_abmn(kBM, BN, D::kUmmaFmt) : ptx::umma_idesc_16(kBM, BN, D::kUmmaFmt);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -151,12 +161,22 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
-          const uint64_t da = ptx::umma_desc_sw128(sa);
-          const uint64_t db = ptx::umma_desc_sw128(sa + Cfg::kABytes);
+          if (kMn) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // 16 contraction rows = two 8-row groups of 1024 bytes; MN atoms (64 elements) are 8 KB apart
+              const uint64_t da = ptx::umma_desc_mn_sw128_lbo(sa + (uint32_t)(k * 2048), 8192u);
+              const uint64_t db = ptx::umma_desc_mn_sw128_lbo(sa + (uint32_t)(Cfg::kABytes + k * 2048), 8192u);
+              ptx::umma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            const uint64_t da = ptx::umma_desc_sw128(sa);
+            const uint64_t db = ptx::umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty[stage]);                   // frees the stage when these MMAs have read it
           if (kb == kb_end - 1) ptx::umma_commit(&tmem_full[acc]);
@@ -437,6 +457,30 @@ int dispatch_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tw, con
   return fail(MP_EINVAL, "mp_linear: unknown epilogue %d", epilogue);
 }
 
+// dW[N_out, K_in] += dY^T X: operands read in place (MN-major), contraction over the tokens split across the SMs
+template <int BN, typename D>
+int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, int n_out, int k_in, int tokens_pad, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kernel = linear_kernel<BN, MP_EPI_ACCUMULATE, D, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(linear_kernel, wgrad): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = (k_in / BN) * (n_out / kBM);
+  const int k_blocks = tokens_pad / kBK;
+  int want = sm_count() / tiles;
+  if (want > k_blocks / 4) want = k_blocks / 4;
+  if (want < 1) want = 1;
+  const int k_per = (k_blocks + want - 1) / want;
+  const int splits = (k_blocks + k_per - 1) / k_per;
+  const int items = tiles * splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, ty, nullptr, n_out, k_in, tokens_pad, splits);
+  return check_launch("linear_kernel (wgrad)");
+}
+
 }  // namespace
 }  // namespace mp
 
@@ -473,4 +517,26 @@ extern "C" int mp_linear(const void* A, const void* W, const float* bias, const 
   }
   if (wide) return dispatch_epi<256, Fp16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
   return dispatch_epi<128, Fp16>(epilogue, ta, tw, ty, tr, bias, (int)M, (int)N, (int)K, s);
+}
+
+extern "C" int mp_wgrad(const void* dY, const void* X, float* dW, int64_t n_tokens, int64_t n_out, int64_t k_in, int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(dY && X && dW, MP_EINVAL, "mp_wgrad: null pointer");
+  MP_REQUIRE(n_tokens >= 0 && n_tokens < ((int64_t)1 << 31) && n_out >= 128 && n_out % 128 == 0 && k_in >= 128 && k_in % 128 == 0, MP_EINVAL,
+             "mp_wgrad: unsupported shape tokens=%lld n_out=%lld k_in=%lld (n_out %% 128 == 0, k_in %% 128 == 0)", (long long)n_tokens,
+             (long long)n_out, (long long)k_in);
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_wgrad: unknown dtype %d", dtype);
+  MP_REQUIRE(aligned16(dY) && aligned16(X) && aligned16(dW), MP_EALIGN, "mp_wgrad: pointers must be 16-byte aligned");
+  if (n_tokens == 0) return MP_OK;
+  CUtensorMap ta, tw, ty;
+  MP_CHECK(get_tmap(&ta, dY, n_tokens, n_out, 64, dtype));      // 64 tokens x 64 columns per box; token tails are zero-filled
+  MP_CHECK(get_tmap(&tw, X, n_tokens, k_in, 64, dtype));
+  MP_CHECK(get_tmap(&ty, dW, n_out, k_in, kBM, 2));
+  const int tokens_pad = (int)((n_tokens + kBK - 1) / kBK * kBK);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool wide = k_in % 256 == 0;
+  if (dtype == MP_DTYPE_BF16)
+    return wide ? launch_wgrad<256, Bf16>(ta, tw, ty, (int)n_out, (int)k_in, tokens_pad, s) : launch_wgrad<128, Bf16>(ta, tw, ty, (int)n_out, (int)k_in, tokens_pad, s);
+  return wide ? launch_wgrad<256, Fp16>(ta, tw, ty, (int)n_out, (int)k_in, tokens_pad, s) : launch_wgrad<128, Fp16>(ta, tw, ty, (int)n_out, (int)k_in, tokens_pad, s);
 }

@@ -194,6 +194,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+// Same, for an operand that spans several 64-element MN atoms: atom a starts lbo_bytes after atom a - 1 (cute canonical layout
+// ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements of 16 bits: LBO = stride between MN atoms, SBO = stride between 8-row K groups)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return umma_desc_mn_sw128(smem_addr) | ((uint64_t)(lbo_bytes >> 4) << 16);
+}
+// instruction descriptor with BOTH operands MN-major (a_major bit 15, b_major bit 16): D[M,N] += A^T-stored x B^T-stored, the
+// contraction index is the slow (row) index of both shared-memory tiles (weight gradients: rows are tokens)
+__host__ __device__ constexpr uint32_t umma_idesc_16_abmn(int m, int n, uint32_t fmt) {
+  return umma_idesc_16(m, n, fmt) | (1u << 15) | (1u << 16);
+}
 // instruction descriptor with an MN-major B operand (bit 16)
 __host__ __device__ constexpr uint32_t umma_idesc_16_bmn(int m, int n, uint32_t fmt) { return umma_idesc_16(m, n, fmt) | (1u << 16); }
 

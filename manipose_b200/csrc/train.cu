@@ -317,7 +317,8 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
   uint8_t* sk = sq + (size_t)Lp * LD;
   uint8_t* sv = sk + (size_t)Lp * LD;
   uint8_t* sdo = sv + (size_t)Lp * LD;
-  float* s_lse = reinterpret_cast<float*>(sdo + (size_t)Lp * LD);
+  uint8_t* so = sdo + (size_t)Lp * LD;          // forward output rows, only for D_i
+  float* s_lse = reinterpret_cast<float*>(so + (size_t)Lp * LD);
   float* s_dd = s_lse + Lp;
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(s_dd + Lp);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -338,15 +339,16 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
   uint16_t* dqkv_base = dqkv + tok0 * 3 * C + head * HD;
   const int64_t qkv_stride = tstride * 3 * C, o_stride = tstride * C;
 
-  // ---- stage Q, K, V, dO rows [0, L); zero rows [L, Lp)
-  const int total = 4 * Lp * CH;
+  // ---- stage Q, K, V, dO, O rows [0, L); zero rows [L, Lp)
+  const int total = 5 * Lp * CH;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int ch = i % CH;
     const int r = (i / CH) % Lp;
     const int sel = i / (CH * Lp);
     uint8_t* dst = smem_b + ((size_t)sel * Lp + r) * LD + ch * 16;
     if (r < L) {
-      const uint16_t* src = sel < 3 ? qkv_base + (int64_t)r * qkv_stride + sel * C + ch * 8 : do_base + (int64_t)r * o_stride + ch * 8;
+      const uint16_t* src = sel < 3 ? qkv_base + (int64_t)r * qkv_stride + sel * C + ch * 8
+                                    : (sel == 3 ? do_base : o_base) + (int64_t)r * o_stride + ch * 8;
       ptx::cp_async16(dst, src);
     } else {
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
@@ -362,7 +364,7 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
 #pragma unroll
       for (int ch = 0; ch < CH; ++ch) {
         const uint4 a = *reinterpret_cast<const uint4*>(sdo + (size_t)r * LD + ch * 16);
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(o_base + (int64_t)r * o_stride) + ch);
+        const uint4 b = *reinterpret_cast<const uint4*>(so + (size_t)r * LD + ch * 16);
         const uint32_t au[4] = {a.x, a.y, a.z, a.w}, bu[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -377,16 +379,6 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
   __syncthreads();
   const float scale = rsqrtf((float)HD);
   const float scale_log2 = scale * 1.4426950408889634f;
-  // ---- sweep 0: log-sum-exp per query row
-  for (int mt = warp; mt * 16 < L; mt += n_warps) {
-    float lse[2];
-    lse_tile<HD, LD, D>(smem_u32(sq) + (uint32_t)(mt * 16 * LD), smem_u32(sk), L, Lp, scale_log2, lane, lse);
-    if (t == 0) {
-      s_lse[mt * 16 + g] = lse[0];
-      s_lse[mt * 16 + g + 8] = lse[1];
-    }
-  }
-  __syncthreads();
   uint8_t* stg = stage_base + (size_t)warp * 16 * LD;
   auto store_tile = [&](const float (&v)[HD / 8][4], float mul, int mt, int col_off) {
     __syncwarp();
@@ -402,14 +394,24 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
         *reinterpret_cast<uint4*>(dqkv_base + (int64_t)r * qkv_stride + col_off + ch * 8) = *reinterpret_cast<const uint4*>(stg + (size_t)rr * LD + ch * 16);
     }
   };
-  // ---- sweep A: dQ
+  // ---- sweep 0 + A per 16-row query tile: log-sum-exp of the tile's rows (needed by every warp in sweep B), then dQ
   for (int mt = warp; mt * 16 < L; mt += n_warps) {
     float unused[HD / 8][4], dq[HD / 8][4];
     const uint32_t ro = (uint32_t)(mt * 16 * LD);
+    {
+      float lse[2];
+      lse_tile<HD, LD, D>(smem_u32(sq) + ro, smem_u32(sk), L, Lp, scale_log2, lane, lse);
+      if (t == 0) {
+        s_lse[mt * 16 + g] = lse[0];
+        s_lse[mt * 16 + g + 8] = lse[1];
+      }
+      __syncwarp();
+    }
     bwd_sweep<HD, LD, D, false>(smem_u32(sq) + ro, smem_u32(sdo) + ro, smem_u32(sk), smem_u32(sv), 0u, smem_u32(sk), L, Lp, scale_log2, s_lse,
                                 s_dd, mt * 16, lane, unused, dq);
     store_tile(dq, scale, mt, 0);
   }
+  __syncthreads();
   // ---- sweep B: dK, dV
   for (int mt = warp; mt * 16 < L; mt += n_warps) {
     float dv[HD / 8][4], dk[HD / 8][4];
@@ -448,6 +450,71 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __rest
   for (int k = 0; k < 16; ++k) {
     const int r = ty + 4 * k;
     dst[(c0 + r) * Mpad + m0 + tx] = tile[tx][r];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- weight shadows, one launch
+// After an optimizer step every GEMM weight needs its 16-bit shadow [N, K] (forward, wgrad-free) and the transposed shadow [K, N]
+// (dgrad).  table[w] = {src fp32 ptr, dst ptr, dst_t ptr, rows N, cols K} as int64; blockIdx.y = weight, blockIdx.x strides over its
+// 64 x 64 tiles.
+template <typename D>
+__global__ void __launch_bounds__(256) refresh_shadows_kernel(const int64_t* __restrict__ table) {
+  __shared__ uint16_t tile[64][66];
+  const int64_t* e = table + (int64_t)blockIdx.y * 5;
+  const float* src = reinterpret_cast<const float*>(e[0]);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(e[1]);
+  uint16_t* dst_t = reinterpret_cast<uint16_t*>(e[2]);
+  const int rows = (int)e[3], cols = (int)e[4];
+  const int tiles_c = cols / 64, n_tiles = (rows / 64) * tiles_c;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const int r0 = (tl / tiles_c) * 64, c0 = (tl % tiles_c) * 64;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int r = ty + 4 * k;
+      const uint16_t v = (uint16_t)(D::pack2(src[(size_t)(r0 + r) * cols + c0 + tx], 0.f) & 0xffffu);
+      tile[r][tx] = v;
+      dst[(size_t)(r0 + r) * cols + c0 + tx] = v;
+    }
+    __syncthreads();
+    if (dst_t != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int r = ty + 4 * k;
+        dst_t[(size_t)(c0 + r) * rows + r0 + tx] = tile[tx][r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- bias gradient
+// colsum[c] += sum_m src[m, c] over a 16-bit [M, C] matrix.  CTA = 64 columns (32 column pairs = one 128-byte row segment per warp
+// access) x a slab of rows; 8 row lanes per CTA are reduced in shared memory, then ONE atomic per column and CTA.
+template <typename D>
+__global__ void __launch_bounds__(256) colsum16_kernel(const uint32_t* __restrict__ src, float* __restrict__ colsum, int64_t M, int C2,
+                                                       int64_t rows_per_cta) {
+  __shared__ float red[8][64];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c2 = blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  float a0 = 0.f, a1 = 0.f;
+  if (c2 < C2) {
+    for (int64_t m = r0 + ry; m < r1; m += 8) {
+      const float2 v = D::unpack2(src[m * C2 + c2]);
+      a0 += v.x;
+      a1 += v.y;
+    }
+  }
+  red[ry][2 * cx] = a0;
+  red[ry][2 * cx + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < 2 * C2) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, t);
   }
 }
 
@@ -633,7 +700,7 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
   if (n_warps > kAttnBwdMmaWarps) n_warps = kAttnBwdMmaWarps;
   auto launch_mma = [&](auto kernel, int HD) -> int {
     const int LD = HD * 2 + 16;
-    const size_t smem = (size_t)4 * Lp * LD + (size_t)2 * Lp * sizeof(float) + (size_t)n_warps * 16 * LD;
+    const size_t smem = (size_t)5 * Lp * LD + (size_t)2 * Lp * sizeof(float) + (size_t)n_warps * 16 * LD;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_mma_kernel): %s", cudaGetErrorString(e));
     kernel<<<(unsigned)n_items, n_warps * 32, smem, (cudaStream_t)stream>>>((const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout,
@@ -657,6 +724,40 @@ int mp_transpose16(const void* src, void* dst, float* colsum, int64_t M, int64_t
   else
     transpose16_kernel<Fp16><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, (uint16_t*)dst, colsum, M, C, Mpad);
   return check_launch("transpose16_kernel");
+}
+
+int mp_refresh_shadows(const int64_t* table, int n_weights, int max_tiles, int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(table && n_weights >= 0 && max_tiles >= 1, MP_EINVAL, "mp_refresh_shadows: bad arguments");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_refresh_shadows: unknown dtype %d", dtype);
+  if (n_weights == 0) return MP_OK;
+  const int gx = max_tiles < 64 ? max_tiles : 64;
+  if (dtype == MP_DTYPE_BF16)
+    refresh_shadows_kernel<Bf16><<<dim3(gx, n_weights), 256, 0, (cudaStream_t)stream>>>(table);
+  else
+    refresh_shadows_kernel<Fp16><<<dim3(gx, n_weights), 256, 0, (cudaStream_t)stream>>>(table);
+  return check_launch("refresh_shadows_kernel");
+}
+
+int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(src && colsum && M >= 0 && C >= 2 && C % 2 == 0, MP_EINVAL, "mp_colsum16: bad arguments (C %% 2 == 0)");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_colsum16: unknown dtype %d", dtype);
+  if (M == 0) return MP_OK;
+  const int c2 = (int)(C / 2);
+  const int gx = (c2 + 31) / 32;
+  // about two CTAs per SM, at least 64 rows each (few atomics per column)
+  int64_t gy = (int64_t)sm_count() * 2 / gx + 1;
+  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+  const int64_t rows_per_cta = (M + gy - 1) / gy;
+  gy = (M + rows_per_cta - 1) / rows_per_cta;
+  if (dtype == MP_DTYPE_BF16)
+    colsum16_kernel<Bf16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, colsum, M, c2, rows_per_cta);
+  else
+    colsum16_kernel<Fp16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, colsum, M, c2, rows_per_cta);
+  return check_launch("colsum16_kernel");
 }
 
 int mp_group_rowsum(const float* x, float* out, int64_t n_rows, int C, int64_t div, int64_t mod, mp_stream_t stream) {

@@ -111,33 +111,24 @@ def grad_of(p: torch.Tensor) -> torch.Tensor:
     return p.grad
 
 
-class Scratch:
-    """Transposed-operand scratch of the weight-gradient GEMMs: dY^T [n_max, Mpad] and X^T [k_max, Mpad] (16-bit)."""
-
-    def __init__(self):
-        self.key = None
-
-    def get(self, n_tokens, n_max, k_max, dtype, device):
-        mpad = pad64(n_tokens)
-        key = (mpad, n_max, k_max, dtype, str(device))
-        if key != self.key:
-            self.tdy = torch.empty((n_max, mpad), dtype=dtype, device=device)
-            self.tact = torch.empty((k_max, mpad), dtype=dtype, device=device)
-            self.key = key
-        return self.tdy, self.tact
+def colsum16(src16, colsum):
+    m, c = src16.shape
+    L.check(L.load().mp_colsum16(L.ptr(src16), L.ptr(colsum), m, c, ops.DTYPE_CODE[src16.dtype], L.stream_ptr()), "mp_colsum16")
+    ops._count()
 
 
-def wgrad(dy16, act16, dw, db, scratch: Scratch, n_max: int, k_max: int):
+def wgrad(dy16, act16, dw, db):
     """dw[N,K] += dy16[M,N]^T act16[M,K]; db[N] += column sums of dy16 (db None to skip).
 
-    tcgen05 path: both operands are transposed so that the token dim is the contraction dim, then mp_linear(MP_EPI_ACCUMULATE)
-    splits that contraction over the SMs and adds the partial tiles into the fp32 gradient with TMA reduce stores."""
+    tcgen05 path: both operands are read in place as MN-major UMMA operands (rows = tokens = the contraction index), the token
+    contraction is split over the SMs and the partial tiles are added into the fp32 gradient with TMA reduce stores."""
     m, n = dy16.shape
     k = act16.shape[1]
-    tdy, tact = scratch.get(m, n_max, k_max, dy16.dtype, dy16.device)
-    transpose16(dy16, tdy[:n], db)
-    transpose16(act16, tact[:k])
-    ops.linear(tdy[:n], tact[:k], None, dw, L.MP_EPI_ACCUMULATE)
+    if db is not None:
+        colsum16(dy16, db)
+    rc = L.load().mp_wgrad(L.ptr(dy16), L.ptr(act16), L.ptr(dw), m, n, k, ops.DTYPE_CODE[dy16.dtype], L.stream_ptr())
+    L.check(rc, "mp_wgrad")
+    ops._count()
 
 
 def dgrad(dy16, w_t16, out16):
@@ -198,15 +189,12 @@ class LinearF32Fn(torch.autograd.Function):
         dy16 = ops.cast16(dy.contiguous(), code)
         dw = torch.zeros((n, k), dtype=torch.float32, device=a16.device)
         db = torch.zeros(n, dtype=torch.float32, device=a16.device)
-        wgrad(dy16, a16, dw, db, _fn_scratch, n, k)
+        wgrad(dy16, a16, dw, db)
         w_t = torch.empty((k, n), dtype=a16.dtype, device=a16.device)
         transpose16(w16, w_t)
         da = torch.empty((m, k), dtype=a16.dtype, device=a16.device)
         dgrad(dy16, w_t, da)
         return da, dw, db
-
-
-_fn_scratch = Scratch()
 
 
 def layer_norm(x, gamma, beta, eps, out16: Optional[int] = None):

@@ -111,7 +111,7 @@ def test_attention_bwd_vs_autograd(n_clips, n_frames, n_tok, c, temporal, dtype)
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("m,n,k", [(13770, 1536, 512), (13770, 512, 1024), (1000, 384, 128), (77, 128, 256), (12960, 128, 128)])
 def test_wgrad_dgrad_vs_fp32(m, n, k, dtype):
-    """dW += dY^T X through the transposes + tcgen05 Linear with in-place fp32 accumulation, db, and dX = dY W."""
+    """dW += dY^T X (MN-major UMMA operands, split-K with TMA reduce stores, in-place fp32 accumulation), db, and dX = dY W."""
     from manipose_b200 import train_ops as T
     td = DT[dtype]
     gen = torch.Generator(device="cuda").manual_seed(m + n)
@@ -121,8 +121,7 @@ def test_wgrad_dgrad_vs_fp32(m, n, k, dtype):
     dw0 = torch.randn(n, k, generator=gen, device="cuda")
     db0 = torch.randn(n, generator=gen, device="cuda")
     dw, db = dw0.clone(), db0.clone()
-    sc = T.Scratch()
-    T.wgrad(dy, x, dw, db, sc, max(n, 1536), max(k, 1024))
+    T.wgrad(dy, x, dw, db)
     torch.testing.assert_close(dw, dw0 + dy.float().t() @ x.float(), rtol=2e-3, atol=2e-2)
     torch.testing.assert_close(db, db0 + dy.float().sum(0), rtol=2e-3, atol=2e-2)
     w_t = T.transpose16(w, torch.empty((k, n), dtype=td, device="cuda"))
