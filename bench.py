@@ -147,6 +147,32 @@ def cpu_forward_rate(clips, reps, warm=True, budget_s=25.0):
     return clips * T / best, torch.get_num_threads(), done
 
 
+def cpu_train_rate(t, clips=2, budget_s=25.0):
+    """Reference algorithm on the host cores for the training step: forward + default objective + backward (torch autograd through
+    the fp32 oracle; no optimizer step) on a bounded sample, frames/s."""
+    import torch
+    from oracle import manipose_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.requires_grad_() for k, v in O.make_state_dict(num_frame=t, n_hyp=K, seed=42).items()}
+    g = torch.Generator().manual_seed(1234)
+    x = 0.3 * torch.randn(clips, t, J, 2, generator=g)
+    y = 0.3 * torch.randn(clips, t, J, 3, generator=g)
+    best, t_start, done = None, time.perf_counter(), 0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        poses, scores = O.rmcl_forward(x, sd)
+        loss, _ = O.training_loss(poses, scores, y)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        done += 1
+        if done > 1:                      # first pass warms the allocator
+            best = dt if best is None else min(best, dt)
+        if time.perf_counter() - t_start > budget_s and best is not None:
+            break
+    return {"value": clips * t / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"best of {done - 1} passes of forward + objective + backward (no optimizer) over {clips} clips x {t} frames, fp32, torch CPU autograd"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -333,7 +359,7 @@ def run_train(args):
     from manipose_b200 import metrics, ops
     from manipose_b200.optim import FusedAdam
 
-    t4, b4 = 27, (args.clips if args.clips != 1024 else 30)
+    t4, b4 = args.frames, (args.clips if args.clips != 1024 else 30)
     torch.manual_seed(42)                      # identical replicas
     model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=t4, n_hyp=K, drop_path_rate=args.drop_path)
     model = model.to(dev).train().set_compute_dtype(args.dtype)
@@ -401,8 +427,11 @@ def run_train(args):
     peaks = measured_peaks()
     tflops = 3.0 * flops_per_frame(t4, K) * b4 * t4 * steps / (ms / 1000.0) / 1e12
     n_params = sum(p.numel() for p in model.parameters())
+    cpu = None
+    if rank == 0 and not args.skip_cpu_baseline:
+        cpu = cpu_train_rate(t4)
     if rank == 0:
-        line = {"metric": "train_frames_per_sec_T27_3DHP", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        line = {"metric": f"train_frames_per_sec_T{t4}" + ("_3DHP" if t4 == 27 else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": f"ManiPose training step (forward + wta/bce/velocity/smoothness objective + backward + gradient all-reduce + Adam), "
@@ -414,7 +443,8 @@ def run_train(args):
                 "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                              "frac": tflops / peaks["bf16_sustained"], "traffic": None,
                              "note": "whole step: 3 x forward matmul flops / step time; the step is launch / latency bound at 810 frames"},
-                "allreduce": None if ms_local is None else {"exposed_ms_per_step": (ms - ms_local) / steps, "ms_per_step_without": ms_local / steps}}
+                "allreduce": None if ms_local is None else {"exposed_ms_per_step": (ms - ms_local) / steps, "ms_per_step_without": ms_local / steps},
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -433,6 +463,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: T=243 inference (headline); 4: T=27 training step")
     ap.add_argument("--drop-path", type=float, default=0.1, help="config 4: stochastic depth rate (drivers use 0.1)")
+    ap.add_argument("--frames", type=int, default=27, help="config 4: frames per clip (27 = 3DHP shape of BASELINE config 4; 243 = H36M)")
     ap.add_argument("--cuda-graph", action="store_true", help="config 4: capture the whole training step in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

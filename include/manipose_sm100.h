@@ -213,9 +213,10 @@ int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stre
  * with the operand transposes (and the bias gradient, a column sum of dY) done by mp_transpose16. */
 
 /* LayerNorm backward: dx = LN'(x; gamma, eps)(dy) [+ dres]; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics; both NULL to skip).
- * dy is fp32 (dy_is_16bit = 0) or `dtype` 16-bit; gamma NULL = no affine; dx may alias dres.  C in {512, 128}. */
+ * dy is fp32 (dy_is_16bit = 0) or `dtype` 16-bit; gamma NULL = no affine; dx may alias dres.  dx16 (may be NULL): also writes
+ * 16-bit(rowscale[token] * dx) — the operand of the next backward GEMM (rowscale NULL = 1).  C in {512, 128}. */
 int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_is_16bit, const float* dres, float* dx,
-                     float* dgamma, float* dbeta, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
+                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
 /* exact-erf GELU on a 16-bit pre-activation (training keeps the pre-activation): a = gelu(u); du = da * gelu'(u).  n % 8 == 0. */
 int mp_gelu_fwd(const void* u, void* a, int64_t n, int dtype, mp_stream_t stream);
 int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, mp_stream_t stream);

@@ -401,18 +401,21 @@ class MixSTE(nn.Module):
                 # x3 = post-norm(x2) (+ Temporal_pos_embed after the first block); dx currently is d/dx3
                 if rec["pos"]:
                     T.group_rowsum(dx, g(self.Temporal_pos_embed), n_tok, n_frames)
-                T.layernorm_bwd(rec["x2"], post.weight, post.eps, dx, None, dx, g(post.weight), g(post.bias), dt)
-            # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1)))))
-            T.cast_rowscale(dx, rec["s2"], dy16)
+                T.layernorm_bwd(rec["x2"], post.weight, post.eps, dx, None, dx, g(post.weight), g(post.bias), dt, dx16=dy16,
+                                rowscale=rec["s2"])
+            else:
+                T.cast_rowscale(dx, rec["s2"], dy16)
+            # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1))))); dy16 = 16-bit(s2 * dx)
             T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), g(blk.mlp.fc2.bias))
             da = flat[:n_tokens * hidden].view(n_tokens, hidden)
             T.dgrad(dy16, w_t[wi + 3], da)
             T.gelu_bwd(rec["u"], da, da)
             T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), g(blk.mlp.fc1.bias))
             T.dgrad(da, w_t[wi + 2], dy16)
-            T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt)
+            # norm2 backward reads dy16 (= d h2) and rewrites it with 16-bit(s1 * dx1), the operand of the attention branch
+            T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt, dx16=dy16,
+                            rowscale=rec["s1"])
             # ---- attention branch: x1 = x0 + s1 * proj(attention(qkv(norm1(x0))))
-            T.cast_rowscale(dx, rec["s1"], dy16)
             T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), g(blk.attn.proj.bias))
             do = b16(c)
             T.dgrad(dy16, w_t[wi + 1], do)

@@ -24,7 +24,8 @@ namespace {
 template <int C, bool kDy16, typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* dy,
-                     const float* dres, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t n_tokens) {
+                     const float* dres, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* dx16,
+                     const float* __restrict__ rowscale, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
   using R = Row<C>;
   __shared__ float acc[2][C];
   const int lane = threadIdx.x & 31;
@@ -70,6 +71,12 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       for (int i = 0; i < R::kPer; ++i) d[i] += r[i];
     }
     R::store_x(dx + tok * C, lane, d);
+    if (dx16) {   // the next backward GEMM's operand: 16-bit copy, scaled by the sample's stochastic-depth factor
+      const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
+#pragma unroll
+      for (int i = 0; i < R::kPer; ++i) d[i] *= sc;
+      R::template store_h<D>(dx16 + tok * C, lane, d);
+    }
   }
   if (dgamma) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -624,7 +631,7 @@ int stream_grid(int64_t n, int per_cta) {
 extern "C" {
 
 int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_is_16bit, const float* dres, float* dx,
-                     float* dgamma, float* dbeta, int64_t n_tokens, int C, int dtype, mp_stream_t stream) {
+                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, int64_t n_tokens, int C, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == 512 || C == 128, MP_EUNSUPPORTED, "mp_layernorm_bwd: C=%d (built for 512 and 128)", C);
@@ -632,21 +639,22 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   MP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr) && (gamma != nullptr || dgamma == nullptr), MP_EINVAL,
              "mp_layernorm_bwd: dgamma / dbeta come together and need gamma");
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_layernorm_bwd: unknown dtype %d", dtype);
-  MP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(dres), MP_EALIGN, "mp_layernorm_bwd: rows must be 16-byte aligned");
+  MP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(dres) && aligned16(dx16), MP_EALIGN,
+             "mp_layernorm_bwd: rows must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
   // every CTA ends with 2 C atomics on the same dgamma / dbeta words: keep the grid at two CTAs per SM when they are wanted
   int grid = token_grid(n_tokens);
   if (dgamma && grid > 2 * sm_count()) grid = 2 * sm_count();
   auto launch = [&](auto kernel) {
-    kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, eps, dy, dres, dx, dgamma, dbeta, n_tokens);
+    kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
   if (C == 512) {
-    if (!dy_is_16bit) launch(layernorm_bwd_kernel<512, false, Bf16>);
+    if (!dy_is_16bit) { if (bf) launch(layernorm_bwd_kernel<512, false, Bf16>); else launch(layernorm_bwd_kernel<512, false, Fp16>); }
     else if (bf) launch(layernorm_bwd_kernel<512, true, Bf16>);
     else launch(layernorm_bwd_kernel<512, true, Fp16>);
   } else {
-    if (!dy_is_16bit) launch(layernorm_bwd_kernel<128, false, Bf16>);
+    if (!dy_is_16bit) { if (bf) launch(layernorm_bwd_kernel<128, false, Bf16>); else launch(layernorm_bwd_kernel<128, false, Fp16>); }
     else if (bf) launch(layernorm_bwd_kernel<128, true, Bf16>);
     else launch(layernorm_bwd_kernel<128, true, Fp16>);
   }

@@ -29,11 +29,11 @@ def pad64(m: int) -> int:
     return (m + 63) // 64 * 64
 
 
-def layernorm_bwd(x, gamma, eps, dy, dres, dx, dgamma, dbeta, dtype):
-    """dx = LN'(x)(dy) [+ dres]; dgamma / dbeta accumulate (None to skip).  dy fp32 or 16-bit."""
+def layernorm_bwd(x, gamma, eps, dy, dres, dx, dgamma, dbeta, dtype, dx16=None, rowscale=None):
+    """dx = LN'(x)(dy) [+ dres]; dgamma / dbeta accumulate (None to skip).  dy fp32 or 16-bit.  dx16: also 16-bit(rowscale * dx)."""
     n_tokens, c = x.shape
     rc = L.load().mp_layernorm_bwd(L.ptr(x), L.ptr(gamma), float(eps), L.ptr(dy), int(dy.dtype != torch.float32), L.ptr(dres), L.ptr(dx),
-                                   L.ptr(dgamma), L.ptr(dbeta), n_tokens, c, dtype, L.stream_ptr())
+                                   L.ptr(dgamma), L.ptr(dbeta), L.ptr(dx16), L.ptr(rowscale), n_tokens, c, dtype, L.stream_ptr())
     L.check(rc, "mp_layernorm_bwd")
     ops._count()
     return dx
