@@ -32,6 +32,19 @@ constexpr int kMaxHyp = 32;
 
 __constant__ float c_ones17[kJ] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
 
+// One-MUFU square root / reciprocal square root (relative error ~2^-22) for the terms that are means or gradients; the per-hypothesis
+// WTA error keeps correctly rounded IEEE operations (winner indices must match the reference bit for bit).
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Copies floats [g0, g0+n) of `base` (16-byte aligned, `total` floats long) into sbuf so that element g0+i lands at
 // sbuf[shift + i]; returns shift in [0,3].  Whole 16-byte chunks go through cp.async, the array tail through LDG.
 __device__ __forceinline__ int stage_floats(float* sbuf, const float* __restrict__ base, size_t g0, uint32_t n, size_t total,
@@ -146,7 +159,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
               q = fmaf(dv, dv, q);
               sm = fmaf(w[j] * dvh, dvh, sm);
             }
-            vel += kSquared ? q : sqrtf(q);
+            vel += kSquared ? q : sqrt_approx(q);
           }
         }
       }
@@ -280,8 +293,8 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
               gj[1] = c_wta * w[j] * d1;
               gj[2] = c_wta * w[j] * d2;
             } else {
-              const float n = sqrtf(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
-              const float r = n > 0.f ? c_wta * w[j] / n : 0.f;
+              const float n2 = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+              const float r = n2 > 0.f ? c_wta * w[j] * rsqrt_approx(n2) : 0.f;
               gj[0] = r * d0;
               gj[1] = r * d1;
               gj[2] = r * d2;
@@ -295,8 +308,7 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
               dv[c] = dvh[c] - (yc[kF + j * 3 + c] - yc[j * 3 + c]);
               q = fmaf(dv[c], dv[c], q);
             }
-            const float n = sqrtf(q);
-            const float r = kSquared ? c_vel : (n > 0.f ? c_vel / n : 0.f);
+            const float r = kSquared ? c_vel : (q > 0.f ? c_vel * rsqrt_approx(q) : 0.f);
 #pragma unroll
             for (int c = 0; c < 3; ++c) gj[c] -= r * dv[c] + c_sm * w[j] * dvh[c];
           }
@@ -308,8 +320,7 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
               dv[c] = dvh[c] - (yc[j * 3 + c] - yc[j * 3 + c - kF]);
               q = fmaf(dv[c], dv[c], q);
             }
-            const float n = sqrtf(q);
-            const float r = kSquared ? c_vel : (n > 0.f ? c_vel / n : 0.f);
+            const float r = kSquared ? c_vel : (q > 0.f ? c_vel * rsqrt_approx(q) : 0.f);
 #pragma unroll
             for (int c = 0; c < 3; ++c) gj[c] += r * dv[c] + c_sm * w[j] * dvh[c];
           }
