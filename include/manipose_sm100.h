@@ -205,6 +205,16 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
 /* fp32 -> 16-bit (weight shadows refreshed by the host wrapper after optimizer.step()). */
 int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stream_t stream);
 
+/* Pose-consistency metrics (hpe/mh_so3_hpe/metrics/utils.py:4-20 measure_bones_length; regularizations.py:8-48
+ * segments_time_consistency = MPSCE; regularizations.py:103-140 sagittal_symmetry = MPSSE) over poses [n_clips, n_frames, 17, 3]:
+ *   seg_mean, seg_var [n_clips,16]: mean and unbiased variance over time of every bone length (bone b = joint b+1 -> its parent);
+ *   sym_abs, sym_sq [n_clips,6]:   mean over time of |len[left] - len[right]| and of its square, pairs (bones_left[i], bones_right[i]);
+ *   bone_len [n_clips,16,n_frames] or NULL: the bone lengths themselves (the reference's layout).
+ * workspace >= mp_pose_consistency_workspace_bytes(n_clips, n_frames). */
+size_t mp_pose_consistency_workspace_bytes(int64_t n_clips, int64_t n_frames);
+int mp_pose_consistency(const float* poses, int64_t n_clips, int64_t n_frames, float* seg_mean, float* seg_var, float* sym_abs, float* sym_sq,
+                        float* bone_len, void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:

@@ -9,6 +9,6 @@ from . import _lib
 from .architectures import MixSTE, ManifoldMixSTE, RMCLManifoldMixSTE, PoseDecoder
 from .data import Skeleton, h36m17_skeleton
 from . import metrics
-from .install import install
+from .install import install, load_checkpoint
 
-__all__ = ["MixSTE", "ManifoldMixSTE", "RMCLManifoldMixSTE", "PoseDecoder", "Skeleton", "h36m17_skeleton", "metrics", "install"]
+__all__ = ["MixSTE", "ManifoldMixSTE", "RMCLManifoldMixSTE", "PoseDecoder", "Skeleton", "h36m17_skeleton", "metrics", "install", "load_checkpoint"]

@@ -45,11 +45,13 @@ class Skeleton:
         for i, p in enumerate(self._parents):
             if p != -1:
                 self._children[p].append(i)
-        self._bones = tuple((int(p), j) for j, p in enumerate(self._parents) if p >= 0)
-        self._bones_names = tuple(f"{self._joints_names[p]}->{self._joints_names[j]}" for p, j in self._bones)
+        # (joint, joint_parent) tuples, like the reference (hpe/mh_so3_hpe/data/skeleton.py:100-103)
+        self._bones = tuple((j, int(p)) for j, p in enumerate(self._parents) if p >= 0)
+        self._bones_names = tuple(f"{self._joints_names[p]}->{self._joints_names[j]}" for j, p in self._bones)
         bone_index = {b: i for i, b in enumerate(self._bones)}
-        self._bones_left = tuple(bone_index[b] for b in self._bones if b[1] in self._joints_left)
-        self._bones_right = tuple(bone_index[b] for b in self._bones if b[1] in self._joints_right)
+        bone_parent = dict(self._bones)
+        self._bones_left = tuple(bone_index[(j, bone_parent[j])] for j in self._joints_left if j >= 0)       # skeleton.py:110-120
+        self._bones_right = tuple(bone_index[(j, bone_parent[j])] for j in self._joints_right if j >= 0)
 
     num_joints = property(lambda self: len(self._parents))
     num_bones = property(lambda self: len([p for p in self._parents if p >= 0]))

@@ -11,7 +11,10 @@ import sys
 
 _ARCH = ("MixSTE", "ManifoldMixSTE", "RMCLManifoldMixSTE")
 _METRICS = ("wta_l2_loss_and_activate_head", "wta_with_scoring_loss", "weighted_mpjpe_loss", "weighted_mse_loss",
-            "mean_velocity_error", "smoothness_regularization", "mpjpe_error", "STANDARD_H36M_WEIGHTS")
+            "mean_velocity_error", "smoothness_regularization", "mpjpe_error", "STANDARD_H36M_WEIGHTS",
+            "measure_bones_length", "segments_time_consistency", "segments_time_consistency_per_bone", "sagittal_symmetry",
+            "sagittal_symmetry_per_bone")
+_CONSISTENCY = ("segments_time_consistency", "segments_time_consistency_per_bone", "sagittal_symmetry", "sagittal_symmetry_per_bone")
 
 
 def install(package: str = "mh_so3_hpe") -> dict:
@@ -38,6 +41,16 @@ def install(package: str = "mh_so3_hpe") -> dict:
     rebind(f"{package}.architectures.pose_decoder", ("PoseDecoder",), A)
     rebind(f"{package}.metrics", _METRICS, M)
     rebind(f"{package}.metrics.losses", _METRICS, M)
-    rebind(f"{package}.metrics.regularizations", ("smoothness_regularization",), M)
+    rebind(f"{package}.metrics.regularizations", ("smoothness_regularization", "measure_bones_length") + _CONSISTENCY, M)
+    rebind(f"{package}.metrics.utils", ("measure_bones_length",), M)
     rebind(f"{package}.metrics.mean_joint_errors", ("mpjpe_error",), M)
     return replaced
+
+
+def load_checkpoint(model, checkpoint, strict: bool = True):
+    """Loads a reference checkpoint into a manipose_b200 model: unwraps the ``"model_pos"`` entry the drivers write
+    (hpe/main_h36m_lifting.py:755-761) and strips the ``module.`` prefix of weights saved from ``nn.DataParallel``."""
+    if isinstance(checkpoint, dict) and "model_pos" in checkpoint:
+        checkpoint = checkpoint["model_pos"]
+    sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in checkpoint.items()}
+    return model.load_state_dict(sd, strict=strict)

@@ -260,6 +260,28 @@ def mpjpe(pred, gt):
     return out
 
 
+def pose_consistency(poses: torch.Tensor, with_bone_lengths: bool = False):
+    """poses [B, L, 17, 3] -> (seg_mean [B,16], seg_var [B,16] (unbiased, over time), sym_abs [B,6], sym_sq [B,6], bone_len [B,16,L] | None)."""
+    _need_cuda(poses)
+    poses = _f32(poses)
+    if poses.dim() != 4 or poses.shape[-2:] != (J, 3):
+        raise ValueError(f"expected poses [B, L, 17, 3], got {tuple(poses.shape)}")
+    b, l = poses.shape[:2]
+    dev = poses.device
+    seg_mean = torch.empty((b, BONES), dtype=torch.float32, device=dev)
+    seg_var = torch.empty((b, BONES), dtype=torch.float32, device=dev)
+    sym_abs = torch.empty((b, 6), dtype=torch.float32, device=dev)
+    sym_sq = torch.empty((b, 6), dtype=torch.float32, device=dev)
+    bone_len = torch.empty((b, BONES, l), dtype=torch.float32, device=dev) if with_bone_lengths else None
+    nbytes = L.load().mp_pose_consistency_workspace_bytes(b, l)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
+    rc = L.load().mp_pose_consistency(L.ptr(poses), b, l, L.ptr(seg_mean), L.ptr(seg_var), L.ptr(sym_abs), L.ptr(sym_sq), L.ptr(bone_len),
+                                      L.ptr(ws), nbytes, L.stream_ptr())
+    L.check(rc, "mp_pose_consistency")
+    _count(2)
+    return seg_mean, seg_var, sym_abs, sym_sq, bone_len
+
+
 # ------------------------------------------------------------------------------------------------ backbone pieces
 TORCH_DTYPE = {L.MP_DTYPE_BF16: torch.bfloat16, L.MP_DTYPE_FP16: torch.float16}
 DTYPE_CODE = {"bf16": L.MP_DTYPE_BF16, "fp16": L.MP_DTYPE_FP16, torch.bfloat16: L.MP_DTYPE_BF16, torch.float16: L.MP_DTYPE_FP16}

@@ -171,6 +171,44 @@ class FusedAdam(torch.optim.Optimizer):
         self._invalidate_shadows()
         return loss
 
+    # ---- torch.optim.Adam checkpoint format (hpe/main_h36m_lifting.py:239-242 loads torch.load(path)["optimizer"] into the optimizer)
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam.state_dict()``: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` (copies of the flat
+        moment buffers), so checkpoints written here resume under the reference's optimizer and vice versa."""
+        step = int(self.step_dev.item())
+        state = {}
+        for i, p in enumerate(self.flat.params):
+            o, n = self.flat.offsets[id(p)]
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        groups[0]["params"] = list(range(len(self.flat.params)))
+        return {"state": state if step > 0 else {}, "param_groups": groups}
+
+    def load_state_dict(self, state_dict) -> None:
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.flat.params):
+            raise ValueError("optimizer state does not match this model (one parameter group over all parameters expected)")
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                self.param_groups[0][k] = groups[0][k]
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, idx in enumerate(groups[0]["params"]):
+            st = state_dict["state"].get(idx)
+            if st is None:
+                continue
+            p = self.flat.params[i]
+            o, n = self.flat.offsets[id(p)]
+            self.exp_avg[o:o + n].view(p.shape).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + n].view(p.shape).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}); one fused step count is kept")
+        self.step_count = steps.pop() if steps else 0
+        self.step_dev.fill_(self.step_count)
+
     def _invalidate_shadows(self) -> None:
         """The kernel wrote the parameters behind autograd's back (their ``_version`` did not move): drop the cached 16-bit weight
         shadows / stacked head tensors so that the next forward rebuilds them."""

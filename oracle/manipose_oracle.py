@@ -468,6 +468,44 @@ def mpjpe_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
     raise ValueError(f"Unexpected value for 'mode' encoutered: {mode}.")
 
 
+# --------------------------------------------------------------------------------------
+# pose-consistency metrics (bone lengths, MPSCE, MPSSE)
+# --------------------------------------------------------------------------------------
+H36M17_BONES = tuple((j, p) for j, p in enumerate(H36M17_PARENTS) if p >= 0)      # skeleton.py:100-103: (joint, parent)
+H36M17_BONES_LEFT = (3, 4, 5, 10, 11, 12)                                          # skeleton.py:110-120 on joints_left / joints_right
+H36M17_BONES_RIGHT = (0, 1, 2, 13, 14, 15)
+
+
+def measure_bones_length(joints_coords: torch.Tensor, bones=H36M17_BONES) -> torch.Tensor:
+    """hpe/mh_so3_hpe/metrics/utils.py:4-20: joints_coords [B,3,J,L] -> [B,num_bones,L]."""
+    b, three, n_joints, length = joints_coords.shape
+    assert three == 3 and n_joints == len(bones) + 1
+    out = torch.empty((b, len(bones), length), dtype=joints_coords.dtype)
+    for i, (j, p) in enumerate(bones):
+        out[:, i, :] = torch.sum((joints_coords[:, :, j, :] - joints_coords[:, :, p, :]) ** 2, axis=1).sqrt()
+    return out
+
+
+def segments_time_consistency(joints_coords: torch.Tensor, mode: str, per_bone: bool = False, bones=H36M17_BONES):
+    """regularizations.py:8-61: var (std for mode 'std') over time of the bone lengths, aggregated over (batch, bone) or over batch."""
+    lengths = measure_bones_length(joints_coords, bones)
+    stat = torch.std if mode == "std" else torch.var
+    agg = {"average": torch.mean, "std": torch.mean, "sum": torch.sum, "min": torch.min, "max": torch.max}[mode]
+    v = stat(lengths, dim=2)
+    return agg(v, dim=0) if per_bone else agg(v)
+
+
+def sagittal_symmetry(joints_coords: torch.Tensor, mode: str, squared: bool = True, per_bone: bool = False, bones=H36M17_BONES,
+                      left=H36M17_BONES_LEFT, right=H36M17_BONES_RIGHT):
+    """regularizations.py:103-157: |len[left] - len[right]| (squared by default), mean or sum."""
+    lengths = measure_bones_length(joints_coords, bones)
+    agg = {"average": torch.mean, "sum": torch.sum}[mode]
+    diff = (lengths[:, list(left), :] - lengths[:, list(right), :]).abs()
+    if squared:
+        diff = diff ** 2.0
+    return agg(diff.permute(0, 2, 1).reshape(-1, len(left)), dim=0) if per_bone else agg(diff)
+
+
 def pose_flip(x: torch.Tensor, left=H36M17_JOINTS_LEFT, right=H36M17_JOINTS_RIGHT) -> torch.Tensor:
     """hpe/mh_so3_hpe/augmentations/functional.py:7-28 — negate x coordinate, swap L/R joints (copy)."""
     out = x.clone()

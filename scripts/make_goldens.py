@@ -130,11 +130,33 @@ def forward_golden(ref):
     torch.save(out, os.path.join(OUT, "forward.pt"))
 
 
+def consistency_golden(ref):
+    """the reference's own bone-length / MPSCE / MPSSE functions on seeded poses."""
+    sk = ref.make_skeleton()
+    M = ref.metrics
+    out = {}
+    for tag, b, l in (("b3_l27", 3, 27), ("b1_l243", 1, 243), ("b2_l700", 2, 700)):
+        poses = 0.3 * torch.randn(b, l, 17, 3, generator=torch.Generator().manual_seed(b * 1000 + l))
+        jc = poses.permute(0, 3, 2, 1)
+        e = {"poses": poses, "bone_len": M.measure_bones_length(jc, sk.bones)}
+        for mode in ("average", "sum", "std", "min", "max"):
+            e[f"stc_{mode}"] = M.segments_time_consistency(jc, sk, mode)
+        for mode in ("average", "sum", "std"):
+            e[f"stc_pb_{mode}"] = M.segments_time_consistency_per_bone(jc, sk, mode)
+        for mode in ("average", "sum"):
+            for squared in (True, False):
+                e[f"sym_{mode}_{int(squared)}"] = M.sagittal_symmetry(jc, sk, mode, squared)
+                e[f"sym_pb_{mode}_{int(squared)}"] = M.sagittal_symmetry_per_bone(jc, sk, mode, squared)
+        out[tag] = e
+    torch.save(out, os.path.join(OUT, "consistency.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     decoder_golden(ref)
     loss_golden(ref)
     forward_golden(ref)
+    consistency_golden(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -107,3 +107,37 @@ def test_install_rebinds_reference_names():
         for qual, obj in replaced.items():
             modname, attr = qual.rsplit(".", 1)
             setattr(importlib.import_module(modname), attr, obj)
+
+
+def test_fused_adam_checkpoints_interoperate_with_torch_adam():
+    """optimizer state in torch.optim.Adam's checkpoint layout both ways, and reference-style model checkpoints
+    ("model_pos" wrapper, DataParallel "module." prefix).  Host logic only (the step kernel needs a GPU)."""
+    import torch
+    import manipose_b200 as mb
+    from manipose_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    kw = dict(num_frame=9, n_hyp=2, depth_rot=1, depth_seg=1)
+    ref = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), **kw)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=4e-5, weight_decay=1e-6)
+    for _ in range(3):                       # synthetic gradients: the reference optimizer's own CPU step
+        for p in ref.parameters():
+            p.grad = torch.randn_like(p)
+        opt_ref.step()
+    ckpt = {"model_pos": {"module." + k: v.clone() for k, v in ref.state_dict().items()}, "optimizer": opt_ref.state_dict()}
+
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), **kw)
+    mb.load_checkpoint(m, ckpt)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), ref.state_dict().values()))
+    opt = FusedAdam(m, lr=1e-3)
+    opt.load_state_dict(ckpt["optimizer"])
+    assert opt.param_groups[0]["lr"] == 4e-5 and opt.param_groups[0]["weight_decay"] == 1e-6
+    assert int(opt.step_dev) == 3
+    back = opt.state_dict()
+    want = opt_ref.state_dict()
+    assert back["param_groups"][0]["params"] == want["param_groups"][0]["params"]
+    for i, st in want["state"].items():
+        assert torch.equal(back["state"][i]["exp_avg"], st["exp_avg"]) and torch.equal(back["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+        assert float(back["state"][i]["step"]) == float(st["step"])
+    opt_ref2 = torch.optim.Adam(ref.parameters(), lr=1.0)
+    opt_ref2.load_state_dict(back)          # and the reference optimizer accepts what we write
+    assert opt_ref2.param_groups[0]["lr"] == 4e-5

@@ -158,3 +158,49 @@ def test_full_size_loss_properties():
     ref_tot, _ = O.training_loss(hyp[sl].cpu(), scores[sl].cpu(), y[sl].cpu())
     got_tot, _ = M.training_loss(hyp[sl].contiguous(), scores[sl].contiguous(), y[sl].contiguous())
     torch.testing.assert_close(got_tot.cpu(), ref_tot, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ pose consistency
+def _consistency_checks(poses_cpu, want, rtol=2e-5):
+    import manipose_b200 as mb
+    from manipose_b200 import metrics as M
+    sk = mb.h36m17_skeleton()
+    jc = poses_cpu.cuda().permute(0, 3, 2, 1)
+    # correctly rounded ops in the reference's order; torch's CPU sqrt is itself 1 ulp off on ~0.7 % of inputs
+    torch.testing.assert_close(M.measure_bones_length(jc, sk.bones).cpu(), want["bone_len"], rtol=3e-7, atol=0)
+    for mode in ("average", "sum", "std", "min", "max"):
+        torch.testing.assert_close(M.segments_time_consistency(jc, sk, mode).cpu(), want[f"stc_{mode}"], rtol=rtol, atol=1e-9)
+    for mode in ("average", "sum", "std"):
+        torch.testing.assert_close(M.segments_time_consistency_per_bone(jc, sk, mode).cpu(), want[f"stc_pb_{mode}"], rtol=rtol, atol=1e-9)
+    for mode in ("average", "sum"):
+        for squared in (True, False):
+            torch.testing.assert_close(M.sagittal_symmetry(jc, sk, mode, squared).cpu(), want[f"sym_{mode}_{int(squared)}"], rtol=rtol, atol=1e-9)
+            torch.testing.assert_close(M.sagittal_symmetry_per_bone(jc, sk, mode, squared).cpu(), want[f"sym_pb_{mode}_{int(squared)}"],
+                                       rtol=rtol, atol=1e-9)
+
+
+def test_pose_consistency_vs_reference_golden():
+    """Bone lengths to 1 ulp, MPSCE / MPSSE statistics within fp32 reduction-order tolerance of the frozen reference outputs."""
+    g = torch.load(os.path.join(GOLD, "consistency.pt"), weights_only=False)
+    for tag, e in g.items():
+        _consistency_checks(e["poses"], e)
+
+
+@pytest.mark.parametrize("b,l", [(1024, 243), (1, 248832), (5, 1)])
+def test_pose_consistency_vs_oracle_at_scale(b, l):
+    """BASELINE config 3 size (1024 clips x 243 frames), the drivers' "all frames as one sequence" MPSCE (one clip of 248,832 frames,
+    split over the SMs), and the single-frame edge (unbiased variance of one sample is NaN, like torch.var)."""
+    from manipose_b200 import ops
+    poses = 0.3 * torch.randn(b, l, 17, 3, generator=torch.Generator().manual_seed(b + l))
+    jc = poses.permute(0, 3, 2, 1)
+    lengths = O.measure_bones_length(jc)
+    seg_mean, seg_var, sym_abs, sym_sq, bone_len = ops.pose_consistency(poses.cuda(), with_bone_lengths=True)
+    torch.testing.assert_close(bone_len.cpu(), lengths, rtol=3e-7, atol=0)
+    torch.testing.assert_close(seg_mean.cpu(), lengths.double().mean(2).float(), rtol=1e-6, atol=1e-7)
+    if l == 1:
+        assert torch.isnan(seg_var).all()
+    else:
+        torch.testing.assert_close(seg_var.cpu(), lengths.double().var(2).float(), rtol=1e-4, atol=1e-9)
+    d = (lengths[:, list(O.H36M17_BONES_LEFT)] - lengths[:, list(O.H36M17_BONES_RIGHT)]).abs().double()
+    torch.testing.assert_close(sym_abs.cpu(), d.mean(2).float(), rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(sym_sq.cpu(), (d ** 2).mean(2).float(), rtol=1e-5, atol=1e-8)

@@ -123,3 +123,19 @@ def test_forward_golden_key_layout():
     want = dict(g["keys"])
     got = {n: tuple(t.shape) for n, t in O.make_state_dict(num_frame=27, n_hyp=5).items()}
     assert got == want and len(want) == 290
+
+
+def test_pose_consistency_oracle_matches_frozen_reference_outputs():
+    """bone lengths, MPSCE (segments_time_consistency) and MPSSE (sagittal_symmetry) frozen from the reference."""
+    g = torch.load(os.path.join(GOLD, "consistency.pt"), weights_only=False)
+    for tag, e in g.items():
+        jc = e["poses"].permute(0, 3, 2, 1)
+        assert torch.equal(O.measure_bones_length(jc), e["bone_len"]), tag
+        for mode in ("average", "sum", "std", "min", "max"):
+            assert torch.equal(O.segments_time_consistency(jc, mode), e[f"stc_{mode}"]), (tag, mode)
+        for mode in ("average", "sum", "std"):
+            assert torch.equal(O.segments_time_consistency(jc, mode, per_bone=True), e[f"stc_pb_{mode}"]), (tag, mode)
+        for mode in ("average", "sum"):
+            for squared in (True, False):
+                assert torch.equal(O.sagittal_symmetry(jc, mode, squared), e[f"sym_{mode}_{int(squared)}"])
+                assert torch.equal(O.sagittal_symmetry(jc, mode, squared, per_bone=True), e[f"sym_pb_{mode}_{int(squared)}"])

@@ -176,3 +176,23 @@ def test_pose_flip_vs_reference(ref):
     sk = ref.make_skeleton()
     (want,) = fn((x.clone(),), sk)   # in-place on a tuple of tensors (functional.py:11-27)
     assert torch.equal(O.pose_flip(x), want)
+
+
+@pytest.mark.parametrize("b,l", [(3, 27), (1, 243)])
+def test_pose_consistency_metrics_match_reference(ref, b, l):
+    """measure_bones_length / segments_time_consistency (MPSCE) / sagittal_symmetry (MPSSE) restatements."""
+    sk = ref.make_skeleton()
+    assert tuple((int(j), int(p)) for j, p in sk.bones) == O.H36M17_BONES
+    assert tuple(sk.bones_left) == O.H36M17_BONES_LEFT and tuple(sk.bones_right) == O.H36M17_BONES_RIGHT
+    poses = 0.3 * torch.randn(b, l, 17, 3, generator=torch.Generator().manual_seed(b + l))
+    jc = poses.permute(0, 3, 2, 1)
+    M = ref.metrics
+    assert torch.equal(O.measure_bones_length(jc), M.measure_bones_length(jc, sk.bones))
+    for mode in ("average", "sum", "std", "min", "max"):
+        assert torch.equal(O.segments_time_consistency(jc, mode), M.segments_time_consistency(jc, sk, mode))
+    for mode in ("average", "sum", "std"):
+        assert torch.equal(O.segments_time_consistency(jc, mode, per_bone=True), M.segments_time_consistency_per_bone(jc, sk, mode))
+    for mode in ("average", "sum"):
+        for squared in (True, False):
+            assert torch.equal(O.sagittal_symmetry(jc, mode, squared), M.sagittal_symmetry(jc, sk, mode, squared))
+            assert torch.equal(O.sagittal_symmetry(jc, mode, squared, per_bone=True), M.sagittal_symmetry_per_bone(jc, sk, mode, squared))
