@@ -44,9 +44,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 132192 rows = 32 clips) from the
-# committed `ncu --set full` capture profiles/r1_pair_linear_full.csv; algorithmic bytes of the same launch: 810.7 MB
-PROFILED_TRAFFIC_LN = {"bytes_per_launch": 755.7e6, "algorithmic_bytes": 810.7e6, "launch": "proj + norm2, M=132192, K=512", "source": "profiles/r1_pair_linear_full.csv"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 528,768 rows = the default 128-clip
+# micro-batch) from the committed `ncu --set full` capture profiles/r1_pair_linear_ln_full_128clips.csv; algorithmic bytes of that launch
+PROFILED_TRAFFIC_LN = {"bytes_per_launch": 3198.5e6, "algorithmic_bytes": 3249.3e6, "launch": "proj + norm2, M=528768 (128 clips), K=512",
+                       "source": "profiles/r1_pair_linear_ln_full_128clips.csv"}
 
 
 def roofline_object(dom, rl, peaks, step_tflops, traffic):
@@ -266,14 +267,15 @@ def run_gpu(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # ---- device-resident throughput, with the GEMM of every 16th micro-batch bracketed by CUDA events
+    # ---- device-resident throughput, with the GEMMs of one micro-batch in `sample_every` bracketed by CUDA events
     sampled = []
     orig_trunk = type(model.rotations_module).trunk
     counter = {"n": 0}
+    sample_every = 4          # bracket the GEMM launches of one micro-batch in four with CUDA events
 
     def trunk_sampled(self, x2d, n_clips):
         counter["n"] += 1
-        ops.GEMM_TIMING = sampled if counter["n"] % 16 == 1 else None
+        ops.GEMM_TIMING = sampled if counter["n"] % sample_every == 1 % sample_every else None
         try:
             return orig_trunk(self, x2d, n_clips)
         finally:
@@ -297,9 +299,9 @@ def run_gpu(args):
         f["bytes"] += by
         f["n"] += 1
     step_tflops = flops_per_frame() * B * T * args.steps / (ms / 1000.0) / 1e12   # per GPU (max-over-ranks time)
-    # share of the step spent in each sampled family, extrapolated from the sampled micro-batches (1 in 16)
+    # share of the step spent in each sampled family, extrapolated from the sampled micro-batches (1 in sample_every)
     n_mb = max(1, counter["n"])
-    sampled_mb = max(1, (n_mb + 15) // 16)
+    sampled_mb = max(1, (n_mb + sample_every - 1) // sample_every)
     rl = {}
     for tag, f in fam.items():
         t_s = f["ms"] / 1000.0

@@ -132,9 +132,10 @@ class _TrunkFn(torch.autograd.Function):
 class MixSTE(nn.Module):
     """mix_ste.py:12-191.  ``forward(x[B,L,J,in_chans]) -> [B,L,J,out_dim]``."""
 
-    # tokens per micro-batch of the trunk (32 clips of 243 x 17); activations of one micro-batch are 12*C bytes per token.
-    # Larger micro-batches amortise launches and tile-wave tails (measured: 339k / 365k / 383k frames/s at 8 / 16 / 32 clips)
-    micro_batch_tokens = 140000
+    # tokens per micro-batch of the trunk (128 clips of 243 x 17); activations of one micro-batch are 12*C bytes per token (3.2 GB).
+    # Larger micro-batches amortise launches and tile-wave tails (measured at 1024 clips: 339k / 365k / 383k frames/s at 8 / 16 / 32
+    # clips on the first GEMM kernels; 428k / 435k / 439k at 32 / 64 / 128 clips now)
+    micro_batch_tokens = 530000
     # 16-bit format of everything that feeds a tensor-core contraction ("bf16": BASELINE config 3; "fp16": same speed and
     # bytes, 3 more mantissa bits — needed for the 0.05 mm end-to-end MPJPE gate, see DESIGN.md §numerics)
     compute_dtype = "bf16"
