@@ -205,6 +205,12 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
 /* fp32 -> 16-bit (weight shadows refreshed by the host wrapper after optimizer.step()). */
 int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stream_t stream);
 
+/* Flip test-time-augmentation epilogue (hpe/eval_utils.py:83-142, augmentations/functional.py:7-28): hyp [2B,K,T,17,3] / scores [2B,K,T]
+ * where clips [B, 2B) are the forward of the horizontally flipped input; out [B,T,17,3] = (aggregate(hyp[b]) + unflip(aggregate(hyp[B+b]))) / 2
+ * for MP_AGG_WEIGHTED_AVE or MP_AGG_BEST_SCORE, unflip = negate x and swap left / right joints.  One launch instead of two aggregations, a
+ * flip and an average. */
+int mp_aggregate_tta(const float* hyp, const float* scores, int mode, float* out_pose, int64_t B, int64_t K, int64_t T, mp_stream_t stream);
+
 /* Pose-consistency metrics (hpe/mh_so3_hpe/metrics/utils.py:4-20 measure_bones_length; regularizations.py:8-48
  * segments_time_consistency = MPSCE; regularizations.py:103-140 sagittal_symmetry = MPSSE) over poses [n_clips, n_frames, 17, 3]:
  *   seg_mean, seg_var [n_clips,16]: mean and unbiased variance over time of every bone length (bone b = joint b+1 -> its parent);

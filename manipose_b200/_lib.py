@@ -37,6 +37,7 @@ SIGNATURES = {
     "mp_loss_fwd": (I, [P, P, P, P, I, F, F, F, P, P, P, I64, I64, I64, P, c_size_t, P]),
     "mp_loss_bwd": (I, [P, P, P, P, P, I, F, F, F, P, P, P, P, I64, I64, I64, P]),
     "mp_aggregate": (I, [P, P, P, I, P, P, P, I64, I64, I64, P]),
+    "mp_aggregate_tta": (I, [P, P, I, P, I64, I64, I64, P]),
     "mp_mpjpe_workspace_bytes": (c_size_t, [I64]),
     "mp_mpjpe": (I, [P, P, I64, P, P, c_size_t, P]),
     "mp_linear": (I, [P, P, P, P, P, I64, I64, I64, I, I, P]),

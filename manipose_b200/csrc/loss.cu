@@ -366,6 +366,58 @@ __global__ void aggregate_weighted_kernel(const float* __restrict__ hyp, const f
   }
 }
 
+// Flip test-time augmentation epilogue (hpe/eval_utils.py:83-142): hyp / scores hold 2B clips, the last B being the forward of the
+// horizontally flipped input; out[b] = (aggregate(hyp[b]) + unflip(aggregate(hyp[B + b]))) / 2, unflip = negate x and swap the left / right
+// joints (augmentations/functional.py:7-28).  Same operation order as aggregate_weighted_kernel / argmax + gather, so the result equals
+// the reference's separate steps bit for bit.
+__host__ __device__ constexpr int flip_joint(int j) {
+  constexpr int f[kJ] = {0, 4, 5, 6, 1, 2, 3, 7, 8, 9, 10, 14, 15, 16, 11, 12, 13};
+  return f[j];
+}
+template <bool kBestScore>
+__global__ void aggregate_tta_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out, uint32_t B,
+                                     uint32_t K, uint32_t T) {
+  const size_t n = (size_t)B * T * kF;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t bt = i / kF;
+    const uint32_t e = (uint32_t)(i - bt * kF);
+    const uint32_t j = e / 3, c = e - j * 3;
+    const uint32_t b = (uint32_t)(bt / T), t = (uint32_t)(bt - (size_t)b * T);
+    int jf = 0;
+#pragma unroll
+    for (int q = 0; q < kJ; ++q)
+      if ((int)j == q) jf = flip_joint(q);
+    const uint32_t ef = (uint32_t)jf * 3 + c;
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t bb = b + (h ? B : 0u);
+      const uint32_t el = h ? ef : e;
+      if (kBestScore) {
+        float best = scores[((size_t)bb * K) * T + t];
+        uint32_t bk = 0;
+        for (uint32_t k = 1; k < K; ++k) {
+          const float sc = scores[((size_t)bb * K + k) * T + t];
+          if (sc > best) {  // torch.argmax: first maximal index
+            best = sc;
+            bk = k;
+          }
+        }
+        v[h] = hyp[(((size_t)bb * K + bk) * T + t) * kF + el];
+      } else {
+        float acc = 0.f;
+        for (uint32_t k = 0; k < K; ++k) {
+          const size_t f = ((size_t)bb * K + k) * T + t;
+          acc = __fadd_rn(acc, __fmul_rn(hyp[f * kF + el], scores[f]));
+        }
+        v[h] = acc;
+      }
+    }
+    if (c == 0) v[1] = -v[1];
+    out[i] = __fmul_rn(__fadd_rn(v[0], v[1]), 0.5f);
+  }
+}
+
 __global__ void argmax_score_kernel(const float* __restrict__ scores, int64_t* __restrict__ idx, uint32_t B, uint32_t K, uint32_t T) {
   const size_t n = (size_t)B * T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -550,6 +602,23 @@ int mp_aggregate(const float* hyp, const float* scores, const float* y, int mode
   }
   gather_hyp_kernel<<<blocks, 256, 0, s>>>(hyp, out_idx, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
   return check_launch("gather_hyp_kernel");
+}
+
+int mp_aggregate_tta(const float* hyp, const float* scores, int mode, float* out_pose, int64_t B, int64_t K, int64_t T, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_CHECK(check_dims("mp_aggregate_tta", 2 * B, K, T));
+  MP_REQUIRE(hyp && out_pose, MP_EINVAL, "mp_aggregate_tta: null pointer");
+  MP_REQUIRE(scores != nullptr, MP_EINVAL, "Scores required to compute weighted hypothesis average.");
+  MP_REQUIRE(mode == MP_AGG_WEIGHTED_AVE || mode == MP_AGG_BEST_SCORE, MP_EINVAL, "Only best_score and weighted_ave modes are implemented.Got %d.", mode);
+  if (B == 0) return MP_OK;
+  const size_t n = (size_t)B * T * kF;
+  const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 8 ? (n + 255) / 256 : (size_t)sm_count() * 8);
+  if (mode == MP_AGG_WEIGHTED_AVE)
+    aggregate_tta_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+  else
+    aggregate_tta_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+  return check_launch("aggregate_tta_kernel");
 }
 
 size_t mp_mpjpe_workspace_bytes(int64_t) { return (size_t)mp::kMpjpeBlocks * sizeof(double); }

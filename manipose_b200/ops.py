@@ -244,6 +244,19 @@ def aggregate(hyp, scores=None, y=None, mode=L.MP_AGG_WEIGHTED_AVE):
     return pose, val, idx
 
 
+def aggregate_tta(hyp2, scores2, mode=L.MP_AGG_WEIGHTED_AVE):
+    """hyp2 [2B,K,T,17,3], scores2 [2B,K,T(,1)] (clips [B,2B) = forward of the flipped input) -> TTA prediction [B,T,17,3]."""
+    _need_cuda(hyp2, scores2)
+    hyp2, scores2 = _f32(hyp2), _f32(scores2)
+    b2, k, t = hyp2.shape[:3]
+    if b2 % 2 != 0:
+        raise ValueError("aggregate_tta expects the original and the flipped half stacked on dim 0")
+    out = torch.empty((b2 // 2, t, J, 3), dtype=torch.float32, device=hyp2.device)
+    L.check(L.load().mp_aggregate_tta(L.ptr(hyp2), L.ptr(scores2), mode, L.ptr(out), b2 // 2, k, t, L.stream_ptr()), "mp_aggregate_tta")
+    _count()
+    return out
+
+
 def mpjpe(pred, gt):
     """(sum, mean) of ||gt - pred||_2 over all 3-D points, as a 2-element fp32 device tensor."""
     _need_cuda(pred, gt)

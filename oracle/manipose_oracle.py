@@ -469,6 +469,19 @@ def mpjpe_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
 
 
 # --------------------------------------------------------------------------------------
+# evaluation epilogue with flip test-time augmentation
+# --------------------------------------------------------------------------------------
+def tta_prediction(x: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str = "weighted_ave") -> torch.Tensor:
+    """hpe/eval_utils.py:51-56,83-142 for the RMCL model: aggregate(model(x)), aggregate(model(pose_flip(x))) flipped back, averaged.
+    ``pose_flip`` (augmentations/functional.py:7-28) works in place on its argument; a copy is flipped here."""
+    poses, scores = rmcl_forward(x, sd)
+    pred = aggregate(poses, scores, mode)
+    poses_f, scores_f = rmcl_forward(pose_flip(x.clone()), sd)
+    pred_f = pose_flip(aggregate(poses_f, scores_f, mode).clone())
+    return (pred + pred_f) / 2
+
+
+# --------------------------------------------------------------------------------------
 # SURVEY.md §8f-3: pose-consistency metrics (bone lengths, MPSCE, MPSSE)
 # --------------------------------------------------------------------------------------
 H36M17_BONES = tuple((j, p) for j, p in enumerate(H36M17_PARENTS) if p >= 0)      # skeleton.py:100-103: (joint, parent)

@@ -151,6 +151,27 @@ def consistency_golden(ref):
     torch.save(out, os.path.join(OUT, "consistency.pt"))
 
 
+def tta_golden(ref):
+    """flip test-time augmentation exactly as hpe/eval_utils.py:51-142 composes the reference's own pieces."""
+    sys.path.insert(0, ROOT)
+    from oracle.manipose_oracle import make_state_dict
+    from mh_so3_hpe.augmentations.functional import pose_flip
+    sk = ref.make_skeleton()
+    sd = make_state_dict(num_frame=27, n_hyp=5, seed=5)
+    m = ref.architectures.RMCLManifoldMixSTE(sk, num_frame=27, n_hyp=5).eval()
+    m.load_state_dict(sd)
+    x = 0.3 * torch.randn(2, 27, 17, 2, generator=torch.Generator().manual_seed(31))
+    out = {"T": 27, "K": 5, "seed": 5, "x": x.clone()}
+    with torch.no_grad():
+        for mode in ("weighted_ave", "best_score"):
+            pred = m.aggregate(*m(x.clone()), mode=mode)
+            x_f = pose_flip(poses_tuple=(x.clone(),), skeleton=sk)[0]
+            pred_f = m.aggregate(*m(x_f), mode=mode)
+            pred_f = pose_flip(poses_tuple=(pred_f,), skeleton=sk)[0]
+            out[mode] = (pred + pred_f) / 2
+    torch.save(out, os.path.join(OUT, "tta.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -158,5 +179,6 @@ if __name__ == "__main__":
     loss_golden(ref)
     forward_golden(ref)
     consistency_golden(ref)
+    tta_golden(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

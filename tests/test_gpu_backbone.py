@@ -321,3 +321,41 @@ def test_default_config_forward_runs_at_t243():
     assert bool((poses[:, :, :, 0] == 0).all())
     with pytest.raises(RuntimeError):
         m(x[:, :100])   # T must equal num_frame, like the reference (Temporal_pos_embed shape)
+
+
+@pytest.mark.parametrize("mode", ["weighted_ave", "best_score"])
+def test_tta_epilogue(mode):
+    """flip test-time augmentation.  (a) the fused kernel equals the reference's separate steps (aggregate twice, flip
+    back, average) bit for bit on identical hypotheses; (b) end to end vs the fixture frozen from the reference."""
+    from manipose_b200 import ops, _lib as L
+    from manipose_b200.evaluation import lift_with_tta, flip_input
+    import manipose_b200 as mb
+    g = torch.load(os.path.join(GOLD, "tta.pt"), weights_only=False)
+    sd = O.make_state_dict(num_frame=g["T"], n_hyp=g["K"], seed=g["seed"])
+    m = _model_from_sd(sd, g["T"], g["K"], "fp16")
+    x = g["x"].cuda()
+    sk = mb.h36m17_skeleton()
+    assert torch.equal(flip_input(g["x"], sk), O.pose_flip(g["x"]))
+    with torch.no_grad():
+        poses, scores = m(torch.cat([x, flip_input(x, sk)]))
+    code = {"weighted_ave": L.MP_AGG_WEIGHTED_AVE, "best_score": L.MP_AGG_BEST_SCORE}[mode]
+    got = ops.aggregate_tta(poses, scores.reshape(scores.shape[:3]), code).cpu()
+    b = x.shape[0]
+    p, s = poses.cpu(), scores.cpu()
+    want = (O.aggregate(p[:b], s[:b], mode) + O.pose_flip(O.aggregate(p[b:], s[b:], mode))) / 2
+    if mode == "best_score":
+        assert torch.equal(got, want)
+    else:   # torch's CPU sum over the hypothesis dim is not strictly sequential for tail elements on every CPU (1 ulp), cf. test_gpu_loss
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-8)
+    # fused == the separate device steps (aggregate twice, flip back, average), bit for bit
+    sc = scores.reshape(scores.shape[:3])
+    a1 = ops.aggregate(poses[:b].contiguous(), sc[:b].contiguous(), None, code)[0]
+    a2 = ops.aggregate(poses[b:].contiguous(), sc[b:].contiguous(), None, code)[0]
+    assert torch.equal(got, ((a1 + flip_input(a2, sk)) / 2).cpu())
+    pred = lift_with_tta(m, x, mode).cpu()
+    assert torch.equal(pred, got)
+    # the synthetic N(0, 1/fan_in) weights amplify the 16-bit backbone error (cf. test_forward_vs_reference_golden); measured median 3.4e-3
+    err = (pred - g[mode]).norm(dim=-1)
+    assert float(err.median()) <= 8e-3
+    with pytest.raises(ValueError):
+        lift_with_tta(m, x, "oracle")

@@ -139,3 +139,12 @@ def test_pose_consistency_oracle_matches_frozen_reference_outputs():
             for squared in (True, False):
                 assert torch.equal(O.sagittal_symmetry(jc, mode, squared), e[f"sym_{mode}_{int(squared)}"])
                 assert torch.equal(O.sagittal_symmetry(jc, mode, squared, per_bone=True), e[f"sym_pb_{mode}_{int(squared)}"])
+
+
+def test_tta_prediction_matches_frozen_reference_composition():
+    """flip test-time augmentation (eval_utils.py:51-142) frozen from the reference's own model / pose_flip / aggregate."""
+    g = torch.load(os.path.join(GOLD, "tta.pt"), weights_only=False)
+    sd = O.make_state_dict(num_frame=g["T"], n_hyp=g["K"], seed=g["seed"])
+    with torch.no_grad():
+        for mode in ("weighted_ave", "best_score"):
+            torch.testing.assert_close(O.tta_prediction(g["x"], sd, mode), g[mode], rtol=0, atol=1e-6)

@@ -196,3 +196,20 @@ def test_pose_consistency_metrics_match_reference(ref, b, l):
         for squared in (True, False):
             assert torch.equal(O.sagittal_symmetry(jc, mode, squared), M.sagittal_symmetry(jc, sk, mode, squared))
             assert torch.equal(O.sagittal_symmetry(jc, mode, squared, per_bone=True), M.sagittal_symmetry_per_bone(jc, sk, mode, squared))
+
+
+@pytest.mark.parametrize("mode", ["weighted_ave", "best_score"])
+def test_tta_prediction_matches_reference_composition(ref, mode):
+    """the TTA branch of hpe/eval_utils.py:51-142 composed from the reference's model, pose_flip and aggregate."""
+    from mh_so3_hpe.augmentations.functional import pose_flip
+    sk = ref.make_skeleton()
+    torch.manual_seed(11)
+    m = ref.architectures.RMCLManifoldMixSTE(sk, num_frame=9, n_hyp=3, drop_path_rate=0.1).eval()
+    _perturb(m)
+    x = 0.3 * torch.randn(2, 9, 17, 2, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        pred = m.aggregate(*m(x.clone()), mode=mode)
+        pred_f = m.aggregate(*m(pose_flip(poses_tuple=(x.clone(),), skeleton=sk)[0]), mode=mode)
+        want = (pred + pose_flip(poses_tuple=(pred_f,), skeleton=sk)[0]) / 2
+        got = O.tta_prediction(x, m.state_dict(), mode)
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-6)
