@@ -217,3 +217,38 @@ class FusedAdam(torch.optim.Optimizer):
                 m._shadow_key = None
             if hasattr(m, "_head_key"):
                 m._head_key = None
+
+
+class CapturedTrainStep:
+    """One training step — zero_grad, forward, objective, backward, (single-GPU) Adam — captured once as a CUDA graph and replayed.
+
+    The step is shape-static (fixed batch and clip length) and every kernel launch, allocation and the optimizer's step counter live
+    on the device, so a replay is one ``cudaGraphLaunch`` instead of ~570 launches of host work (10.2 ms vs 13.7 ms per BASELINE
+    config 4 step on one B200).  Inputs are copied into static buffers before each replay; ``loss`` is a device scalar.
+    Multi-GPU runs keep the eager step (the NCCL reducer is not captured)."""
+
+    def __init__(self, model: nn.Module, optimizer: "FusedAdam", loss_fn, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+        if optimizer.reducer.world_size > 1:
+            raise NotImplementedError("CapturedTrainStep is single-GPU: the bucketed NCCL all-reduce is not captured")
+        self.x, self.y = x.clone(), y.clone()
+        self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        for _ in range(max(1, warmup)):          # allocates shadows, tensor maps, workspaces outside the capture
+            self._step()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+
+    def _step(self) -> None:
+        self.optimizer.zero_grad()
+        out = self.model(self.x)
+        loss = self.loss_fn(out, self.y)
+        loss.backward()
+        self.optimizer.step()
+        self.loss = loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss
