@@ -306,8 +306,9 @@ def test_captured_train_step_matches_eager_steps():
     graphed = [float(step(x, y)) for x, y in zip(xs, ys)]
     torch.cuda.synchronize()
     assert int(o2.step_dev) == 3
-    for a, b in zip(eager, graphed):
-        assert abs(a - b) <= 1e-4 * abs(a), (eager, graphed)
+    assert abs(eager[0] - graphed[0]) <= 1e-5 * abs(eager[0])     # same parameters, same arithmetic
+    for a, b in zip(eager, graphed):                                 # later steps: noise-signed first Adam updates (see below)
+        assert abs(a - b) <= 2e-3 * abs(a), (eager, graphed)
     # Adam's first steps move every element by ~lr * sign(g): elements with |g| ~ 0 take the sign of fp32 reduction noise, so the
     # moments (linear / quadratic in the gradients), not the parameters, are what must agree
     # (and after the first step those noise-signed updates perturb the next gradients at the 1e-3 level)
