@@ -221,6 +221,12 @@ size_t mp_pose_consistency_workspace_bytes(int64_t n_clips, int64_t n_frames);
 int mp_pose_consistency(const float* poses, int64_t n_clips, int64_t n_frames, float* seg_mean, float* seg_var, float* sym_abs, float* sym_sq,
                         float* bone_len, void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
+/* P-MPJPE, "Protocol #2" (hpe/mh_so3_hpe/metrics/mean_joint_errors.py:144-189): per frame, align pred [n_frames,17,3] to gt with the
+ * optimal similarity transform (Procrustes, reflections excluded), then out[0] = sum, out[1] = mean of the joint distances.
+ * workspace >= mp_p_mpjpe_workspace_bytes(n_frames). */
+size_t mp_p_mpjpe_workspace_bytes(int64_t n_frames);
+int mp_p_mpjpe(const float* pred, const float* gt, int64_t n_frames, float* out, void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:

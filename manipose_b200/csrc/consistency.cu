@@ -155,6 +155,185 @@ __global__ void consistency_finalize_kernel(const float* __restrict__ partials, 
   }
 }
 
+// -------------------------------------------------------------------------------------------------- P-MPJPE ("Protocol #2")
+// hpe/mh_so3_hpe/metrics/mean_joint_errors.py:144-189: per frame, the similarity transform (scale, rotation, translation) that best
+// aligns the prediction to the target (orthogonal Procrustes through the SVD of the 3 x 3 cross-covariance, reflections excluded),
+// then the mean joint distance.  The reference moves both tensors to the host and calls numpy's batched SVD; here one thread solves
+// one frame: Jacobi eigen-decomposition of H^T H (double precision), U = H V S^-1, R = V diag(1, 1, det) U^T.
+__device__ __forceinline__ void jacobi_eig3(double (&a)[3][3], double (&v)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off <= 1e-300 || off <= 1e-18 * (fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]))) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      const double apq = a[p][q];
+      if (fabs(apq) < 1e-300) continue;
+      const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+      const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {   // A <- A J (columns p, q)
+        const double akp = a[k][p], akq = a[k][q];
+        a[k][p] = c * akp - sn * akq;
+        a[k][q] = sn * akp + c * akq;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {   // A <- J^T A (rows p, q)
+        const double apk = a[p][k], aqk = a[q][k];
+        a[p][k] = c * apk - sn * aqk;
+        a[q][k] = sn * apk + c * aqk;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {   // V <- V J
+        const double vkp = v[k][p], vkq = v[k][q];
+        v[k][p] = c * vkp - sn * vkq;
+        v[k][q] = sn * vkp + c * vkq;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) p_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t n_frames,
+                                                              double* __restrict__ partials) {
+  __shared__ double red[4];
+  double acc = 0.0;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += (int64_t)gridDim.x * blockDim.x) {
+    const float* y = pred + f * (kJ * 3);     // "predicted"
+    const float* x = gt + f * (kJ * 3);       // "target"
+    double mux[3] = {0, 0, 0}, muy[3] = {0, 0, 0};
+    for (int j = 0; j < kJ; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mux[c] += x[j * 3 + c];
+        muy[c] += y[j * 3 + c];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      mux[c] /= kJ;
+      muy[c] /= kJ;
+    }
+    double nx = 0, ny = 0, h[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // H = X0^T Y0 (unnormalised; divided by nx * ny below)
+    for (int j = 0; j < kJ; ++j) {
+      double xc[3], yc[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        xc[c] = x[j * 3 + c] - mux[c];
+        yc[c] = y[j * 3 + c] - muy[c];
+        nx += xc[c] * xc[c];
+        ny += yc[c] * yc[c];
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[r][c] += xc[r] * yc[c];
+    }
+    nx = sqrt(nx);
+    ny = sqrt(ny);
+    const double inv = 1.0 / (nx * ny);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) h[r][c] *= inv;
+    // eigen-decomposition of H^T H = V S^2 V^T
+    double a[3][3], v[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[r][c] = h[0][r] * h[0][c] + h[1][r] * h[1][c] + h[2][r] * h[2][c];
+    jacobi_eig3(a, v);
+    // order the singular values descending (numpy's convention: the reflection fix flips the LAST one)
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (a[o0][o0] < a[o1][o1]) { const int t = o0; o0 = o1; o1 = t; }
+    if (a[o0][o0] < a[o2][o2]) { const int t = o0; o0 = o2; o2 = t; }
+    if (a[o1][o1] < a[o2][o2]) { const int t = o1; o1 = o2; o2 = t; }
+    const int ord[3] = {o0, o1, o2};
+    double sv[3], vv[3][3], uu[3][3];          // vv[:, i], uu[:, i] = i-th right / left singular vector
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      sv[i] = sqrt(fmax(a[ord[i]][ord[i]], 0.0));
+#pragma unroll
+      for (int r = 0; r < 3; ++r) vv[r][i] = v[r][ord[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double n = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        uu[r][i] = h[r][0] * vv[0][i] + h[r][1] * vv[1][i] + h[r][2] * vv[2][i];
+        n += uu[r][i] * uu[r][i];
+      }
+      n = n > 0 ? 1.0 / sqrt(n) : 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) uu[r][i] *= n;
+    }
+    // third left vector: H v3 / s3 when s3 is resolved, otherwise completed by the cross product (its sign is absorbed by the det fix)
+    {
+      double n = 0, w[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        w[r] = h[r][0] * vv[0][2] + h[r][1] * vv[1][2] + h[r][2] * vv[2][2];
+        n += w[r] * w[r];
+      }
+      if (sv[2] > 1e-9 * sv[0] && n > 0) {
+        n = 1.0 / sqrt(n);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) uu[r][2] = w[r] * n;
+      } else {
+        uu[0][2] = uu[1][0] * uu[2][1] - uu[2][0] * uu[1][1];
+        uu[1][2] = uu[2][0] * uu[0][1] - uu[0][0] * uu[2][1];
+        uu[2][2] = uu[0][0] * uu[1][1] - uu[1][0] * uu[0][1];
+      }
+    }
+    auto det3 = [](const double (&m)[3][3]) {
+      return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+             m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+    };
+    const double sgn = det3(vv) * det3(uu) < 0 ? -1.0 : 1.0;    // det(R) with R = V U^T
+    const double tr = sv[0] + sv[1] + sgn * sv[2];
+    double rot[3][3];                                             // R = V diag(1, 1, sgn) U^T
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rot[r][c] = vv[r][0] * uu[c][0] + vv[r][1] * uu[c][1] + sgn * vv[r][2] * uu[c][2];
+    const double scale = tr * nx / ny;
+    double t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) t[c] = mux[c] - scale * (muy[0] * rot[0][c] + muy[1] * rot[1][c] + muy[2] * rot[2][c]);
+    double e = 0;
+    for (int j = 0; j < kJ; ++j) {
+      double d2 = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double al = scale * (y[j * 3 + 0] * rot[0][c] + y[j * 3 + 1] * rot[1][c] + y[j * 3 + 2] * rot[2][c]) + t[c];
+        const double d = al - x[j * 3 + c];
+        d2 += d * d;
+      }
+      e += sqrt(d2);
+    }
+    acc += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) partials[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void p_mpjpe_finalize_kernel(const double* __restrict__ partials, int n, double n_points, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += partials[i];
+    out[0] = (float)s;
+    out[1] = (float)(s / n_points);
+  }
+}
+
+constexpr int kPmpjpeBlocks = 148 * 8;
+
 int slabs_for(int64_t n_clips, int64_t n_frames, int64_t* frames_per_slab) {
   // about four CTAs per SM in total, at least one pass of the CTA (256 frames) per slab
   int64_t want = ((int64_t)sm_count() * 4 + n_clips - 1) / (n_clips > 0 ? n_clips : 1);
@@ -193,6 +372,22 @@ int mp_pose_consistency(const float* poses, int64_t n_clips, int64_t n_frames, f
   MP_CHECK(check_launch("consistency_partial_kernel"));
   consistency_finalize_kernel<<<(unsigned)n_clips, 32, 0, (cudaStream_t)stream>>>(partials, slabs, n_frames, seg_mean, seg_var, sym_abs, sym_sq);
   return check_launch("consistency_finalize_kernel");
+}
+
+size_t mp_p_mpjpe_workspace_bytes(int64_t) { return (size_t)mp::kPmpjpeBlocks * sizeof(double); }
+
+int mp_p_mpjpe(const float* pred, const float* gt, int64_t n_frames, float* out, void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(pred && gt && out && workspace && n_frames >= 1, MP_EINVAL, "mp_p_mpjpe: bad arguments");
+  MP_REQUIRE(workspace_bytes >= mp_p_mpjpe_workspace_bytes(n_frames), MP_EWORKSPACE, "mp_p_mpjpe: workspace too small");
+  int blocks = (int)((n_frames + 127) / 128);
+  if (blocks > kPmpjpeBlocks) blocks = kPmpjpeBlocks;
+  double* partials = reinterpret_cast<double*>(workspace);
+  p_mpjpe_partial_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pred, gt, n_frames, partials);
+  MP_CHECK(check_launch("p_mpjpe_partial_kernel"));
+  p_mpjpe_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, blocks, (double)n_frames * kJ, out);
+  return check_launch("p_mpjpe_finalize_kernel");
 }
 
 }  // extern "C"

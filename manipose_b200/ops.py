@@ -273,6 +273,21 @@ def mpjpe(pred, gt):
     return out
 
 
+def p_mpjpe(pred, gt):
+    """(sum, mean) of the joint distances after per-frame Procrustes alignment, as a 2-element fp32 device tensor."""
+    _need_cuda(pred, gt)
+    pred, gt = _f32(pred), _f32(gt)
+    if pred.shape != gt.shape or pred.shape[-2:] != (J, 3):
+        raise AssertionError("predicted.shape == target.shape == [..., 17, 3]")
+    n = pred.numel() // (J * 3)
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    nbytes = L.load().mp_p_mpjpe_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
+    L.check(L.load().mp_p_mpjpe(L.ptr(pred), L.ptr(gt), n, L.ptr(out), L.ptr(ws), nbytes, L.stream_ptr()), "mp_p_mpjpe")
+    _count(2)
+    return out
+
+
 def pose_consistency(poses: torch.Tensor, with_bone_lengths: bool = False):
     """poses [B, L, 17, 3] -> (seg_mean [B,16], seg_var [B,16] (unbiased, over time), sym_abs [B,6], sym_sq [B,6], bone_len [B,16,L] | None)."""
     _need_cuda(poses)

@@ -469,6 +469,39 @@ def mpjpe_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
 
 
 # --------------------------------------------------------------------------------------
+# P-MPJPE ("Protocol #2")
+# --------------------------------------------------------------------------------------
+def p_mpjpe(predicted: torch.Tensor, target: torch.Tensor) -> float:
+    """hpe/mh_so3_hpe/metrics/mean_joint_errors.py:144-189: MPJPE after the optimal similarity alignment of every frame
+    (orthogonal Procrustes through numpy's batched SVD of X0^T Y0, reflections excluded)."""
+    import numpy as np
+    assert predicted.shape == target.shape and predicted.shape[-1] == 3
+    n_joints = predicted.shape[-2]
+    pr = predicted.contiguous().view(-1, n_joints, 3).detach().cpu().numpy()
+    tg = target.contiguous().view(-1, n_joints, 3).detach().cpu().numpy()
+    mu_x = np.mean(tg, axis=1, keepdims=True)
+    mu_y = np.mean(pr, axis=1, keepdims=True)
+    x0, y0 = tg - mu_x, pr - mu_y
+    norm_x = np.sqrt(np.sum(x0 ** 2, axis=(1, 2), keepdims=True))
+    norm_y = np.sqrt(np.sum(y0 ** 2, axis=(1, 2), keepdims=True))
+    x0 = x0 / norm_x
+    y0 = y0 / norm_y
+    h = np.matmul(x0.transpose(0, 2, 1), y0)
+    u, sv, vt = np.linalg.svd(h)
+    v = vt.transpose(0, 2, 1)
+    r = np.matmul(v, u.transpose(0, 2, 1))
+    sign_det = np.sign(np.expand_dims(np.linalg.det(r), axis=1))
+    v[:, :, -1] *= sign_det
+    sv[:, -1] *= sign_det.flatten()
+    r = np.matmul(v, u.transpose(0, 2, 1))
+    tr = np.expand_dims(np.sum(sv, axis=1, keepdims=True), axis=2)
+    a = tr * norm_x / norm_y
+    t = mu_x - a * np.matmul(mu_y, r)
+    aligned = a * np.matmul(pr, r) + t
+    return float(np.mean(np.linalg.norm(aligned - tg, axis=2)))
+
+
+# --------------------------------------------------------------------------------------
 # SURVEY.md §8f-1: evaluation epilogue with flip test-time augmentation
 # --------------------------------------------------------------------------------------
 def tta_prediction(x: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str = "weighted_ave") -> torch.Tensor:

@@ -172,6 +172,22 @@ def tta_golden(ref):
     torch.save(out, os.path.join(OUT, "tta.pt"))
 
 
+def procrustes_golden(ref):
+    """the reference's numpy P-MPJPE on seeded pose pairs (noisy, similarity-transformed, mirrored)."""
+    from mh_so3_hpe.metrics.mean_joint_errors import p_mpjpe
+    g = torch.Generator().manual_seed(17)
+    y = 0.3 * torch.randn(3, 27, 17, 3, generator=g)
+    y[:, :, 0] = 0
+    cases = {"noisy": (y + 0.05 * torch.randn(3, 27, 17, 3, generator=g), y)}
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    cases["similarity"] = (1.7 * y @ q + torch.tensor([0.3, -0.2, 0.9]) + 0.01 * torch.randn(3, 27, 17, 3, generator=g), y)
+    mirrored = y.clone()
+    mirrored[..., 0] *= -1
+    cases["mirrored"] = (mirrored + 0.02 * torch.randn(3, 27, 17, 3, generator=g), y)
+    out = {name: {"pred": p, "target": t, "p_mpjpe": float(p_mpjpe(p, t))} for name, (p, t) in cases.items()}
+    torch.save(out, os.path.join(OUT, "procrustes.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -180,5 +196,6 @@ if __name__ == "__main__":
     forward_golden(ref)
     consistency_golden(ref)
     tta_golden(ref)
+    procrustes_golden(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -204,3 +204,32 @@ def test_pose_consistency_vs_oracle_at_scale(b, l):
     d = (lengths[:, list(O.H36M17_BONES_LEFT)] - lengths[:, list(O.H36M17_BONES_RIGHT)]).abs().double()
     torch.testing.assert_close(sym_abs.cpu(), d.mean(2).float(), rtol=1e-5, atol=1e-8)
     torch.testing.assert_close(sym_sq.cpu(), (d ** 2).mean(2).float(), rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------ P-MPJPE
+def test_p_mpjpe_vs_reference_golden():
+    """MPJPE after per-frame Procrustes alignment vs the reference's numpy SVD implementation (noisy, similarity-transformed and
+    mirrored predictions: the last one exercises the det(R) = -1 branch)."""
+    from manipose_b200 import metrics as M
+    g = torch.load(os.path.join(GOLD, "procrustes.pt"), weights_only=False)
+    for name, e in g.items():
+        got = M.p_mpjpe(e["pred"].cuda(), e["target"].cuda())
+        assert abs(got - e["p_mpjpe"]) <= 2e-5 * e["p_mpjpe"], (name, got, e["p_mpjpe"])
+
+
+def test_p_mpjpe_vs_oracle_at_scale_and_invariance():
+    """62,208 frames (256 clips x 243) vs the numpy oracle, and the defining property: a similarity transform of the prediction
+    leaves the aligned error unchanged (and a perfect prediction up to similarity scores ~0)."""
+    from manipose_b200 import metrics as M
+    gen = torch.Generator().manual_seed(9)
+    y = 0.3 * torch.randn(256, 243, 17, 3, generator=gen)
+    pred = y + 0.03 * torch.randn(256, 243, 17, 3, generator=gen)
+    want = O.p_mpjpe(pred, y)
+    got = M.p_mpjpe(pred.cuda(), y.cuda())
+    assert abs(got - want) <= 2e-5 * want, (got, want)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+    if torch.det(q) < 0:
+        q[:, 0] *= -1
+    moved = (0.6 * pred @ q + torch.tensor([1.0, 2.0, -0.5])).cuda()
+    assert abs(M.p_mpjpe(moved, y.cuda()) - got) <= 1e-4 * got
+    assert M.p_mpjpe((2.5 * y @ q + 0.7).cuda(), y.cuda()) <= 1e-5

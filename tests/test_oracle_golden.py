@@ -148,3 +148,10 @@ def test_tta_prediction_matches_frozen_reference_composition():
     with torch.no_grad():
         for mode in ("weighted_ave", "best_score"):
             torch.testing.assert_close(O.tta_prediction(g["x"], sd, mode), g[mode], rtol=0, atol=1e-6)
+
+
+def test_p_mpjpe_oracle_matches_frozen_reference_outputs():
+    """Protocol #2 (MPJPE after Procrustes alignment) frozen from the reference's numpy implementation."""
+    g = torch.load(os.path.join(GOLD, "procrustes.pt"), weights_only=False)
+    for name, e in g.items():
+        assert abs(O.p_mpjpe(e["pred"], e["target"]) - e["p_mpjpe"]) <= 1e-6 * e["p_mpjpe"], name

@@ -213,3 +213,23 @@ def test_tta_prediction_matches_reference_composition(ref, mode):
         want = (pred + pose_flip(poses_tuple=(pred_f,), skeleton=sk)[0]) / 2
         got = O.tta_prediction(x, m.state_dict(), mode)
     torch.testing.assert_close(got, want, rtol=0, atol=1e-6)
+
+
+def _procrustes_cases():
+    g = torch.Generator().manual_seed(17)
+    y = 0.3 * torch.randn(3, 27, 17, 3, generator=g)
+    y[:, :, 0] = 0
+    cases = {"noisy": (y + 0.05 * torch.randn(3, 27, 17, 3, generator=g), y)}
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    cases["similarity"] = (1.7 * y @ q + torch.tensor([0.3, -0.2, 0.9]) + 0.01 * torch.randn(3, 27, 17, 3, generator=g), y)
+    mirrored = y.clone()
+    mirrored[..., 0] *= -1                                  # a reflection: the det(R) = -1 branch
+    cases["mirrored"] = (mirrored + 0.02 * torch.randn(3, 27, 17, 3, generator=g), y)
+    return cases
+
+
+def test_p_mpjpe_matches_reference(ref):
+    """Protocol #2 restatement vs the reference's numpy implementation (same calls, so bit-equal)."""
+    from mh_so3_hpe.metrics.mean_joint_errors import p_mpjpe
+    for name, (pred, y) in _procrustes_cases().items():
+        assert O.p_mpjpe(pred, y) == float(p_mpjpe(pred, y)), name
