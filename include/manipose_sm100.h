@@ -227,6 +227,12 @@ int mp_pose_consistency(const float* poses, int64_t n_clips, int64_t n_frames, f
 size_t mp_p_mpjpe_workspace_bytes(int64_t n_frames);
 int mp_p_mpjpe(const float* pred, const float* gt, int64_t n_frames, float* out, void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
+/* 3DPCK and AUC (hpe/mh_so3_hpe/metrics/pck.py:77-198, alignment 'none', no mask) over n_points 3-D points: out[0] = PCK at `threshold`
+ * (percent), out[1] = AUC over the thresholds linspace(0, 150, 31) (percent).  Exact integer counts behind both. */
+size_t mp_pck_auc_workspace_bytes(void);
+int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float threshold, float* out, void* workspace, size_t workspace_bytes,
+               mp_stream_t stream);
+
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:

@@ -332,6 +332,44 @@ __global__ void p_mpjpe_finalize_kernel(const double* __restrict__ partials, int
   }
 }
 
+// -------------------------------------------------------------------------------------------------- 3DPCK / AUC
+// hpe/mh_so3_hpe/metrics/pck.py:77-198 with alignment='none', mask=None: error = ||pred - gt||_2 per joint (fp32, numpy's operation
+// order), PCK = 100 * mean(error < threshold), AUC = 100 * mean over thresholds linspace(0, 150, 31) of mean(error < thr).  Counting is
+// integer work: every point lands in the histogram bin of the first threshold that exceeds its error; results are exact counts.
+constexpr int kAucBins = 32;      // bin j in [1, 31]: first threshold 5 j' > error is j' = j (31: none); bin 0 unused
+__global__ void __launch_bounds__(256) pck_hist_kernel(const float* __restrict__ pred, const float* __restrict__ gt, size_t n_points,
+                                                       float threshold, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int hist[kAucBins + 1];
+  if (threadIdx.x <= kAucBins) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (size_t)gridDim.x * blockDim.x) {
+    const float d0 = __fsub_rn(pred[i * 3 + 0], gt[i * 3 + 0]), d1 = __fsub_rn(pred[i * 3 + 1], gt[i * 3 + 1]),
+                d2 = __fsub_rn(pred[i * 3 + 2], gt[i * 3 + 2]);
+    const float e = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    int j = 31;
+#pragma unroll
+    for (int t = 30; t >= 0; --t)
+      if ((double)e < 5.0 * t) j = t;           // thresholds np.linspace(0, 150, 31) = 5 t exactly; numpy compares in double
+    atomicAdd(&hist[j], 1u);
+    if ((double)e < (double)threshold) atomicAdd(&hist[kAucBins], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x <= kAucBins && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+}
+__global__ void pck_finalize_kernel(const unsigned long long* __restrict__ counts, double n_points, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // pck_values[i] = float32(mean(error < 5 i)); AUC = mean of the 31 values (float64) * 100
+    double auc = 0.0;
+    unsigned long long below = 0;
+    for (int i = 0; i <= 30; ++i) {
+      below += counts[i];                       // points whose first exceeding threshold index is <= i, i.e. error < 5 i
+      auc += (double)(float)((double)below / n_points);
+    }
+    out[0] = (float)((double)(float)((double)counts[kAucBins] / n_points) * 100.0);
+    out[1] = (float)(auc / 31.0 * 100.0);
+  }
+}
+
 constexpr int kPmpjpeBlocks = 148 * 8;
 
 int slabs_for(int64_t n_clips, int64_t n_frames, int64_t* frames_per_slab) {
@@ -388,6 +426,25 @@ int mp_p_mpjpe(const float* pred, const float* gt, int64_t n_frames, float* out,
   MP_CHECK(check_launch("p_mpjpe_partial_kernel"));
   p_mpjpe_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, blocks, (double)n_frames * kJ, out);
   return check_launch("p_mpjpe_finalize_kernel");
+}
+
+size_t mp_pck_auc_workspace_bytes(void) { return (size_t)(mp::kAucBins + 1) * sizeof(unsigned long long); }
+
+int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float threshold, float* out, void* workspace, size_t workspace_bytes,
+               mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(pred && gt && out && workspace && n_points >= 1, MP_EINVAL, "mp_pck_auc: bad arguments");
+  MP_REQUIRE(workspace_bytes >= mp_pck_auc_workspace_bytes(), MP_EWORKSPACE, "mp_pck_auc: workspace too small");
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(workspace);
+  cudaError_t e = cudaMemsetAsync(counts, 0, mp_pck_auc_workspace_bytes(), (cudaStream_t)stream);
+  MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "mp_pck_auc: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  int64_t blocks = (n_points + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  pck_hist_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, threshold, counts);
+  MP_CHECK(check_launch("pck_hist_kernel"));
+  pck_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts, (double)n_points, out);
+  return check_launch("pck_finalize_kernel");
 }
 
 }  // extern "C"

@@ -288,6 +288,21 @@ def p_mpjpe(pred, gt):
     return out
 
 
+def pck_auc(pred, gt, threshold=150.0):
+    """(PCK at threshold, AUC over linspace(0, 150, 31)) in percent, as a 2-element fp32 device tensor."""
+    _need_cuda(pred, gt)
+    pred, gt = _f32(pred), _f32(gt)
+    if pred.shape != gt.shape or pred.shape[-1] != 3:
+        raise AssertionError("pred.shape == gt.shape == [..., 3]")
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    nbytes = L.load().mp_pck_auc_workspace_bytes()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
+    rc = L.load().mp_pck_auc(L.ptr(pred), L.ptr(gt), pred.numel() // 3, float(threshold), L.ptr(out), L.ptr(ws), nbytes, L.stream_ptr())
+    L.check(rc, "mp_pck_auc")
+    _count(2)
+    return out
+
+
 def pose_consistency(poses: torch.Tensor, with_bone_lengths: bool = False):
     """poses [B, L, 17, 3] -> (seg_mean [B,16], seg_var [B,16] (unbiased, over time), sym_abs [B,6], sym_sq [B,6], bone_len [B,16,L] | None)."""
     _need_cuda(poses)

@@ -501,6 +501,28 @@ def p_mpjpe(predicted: torch.Tensor, target: torch.Tensor) -> float:
     return float(np.mean(np.linalg.norm(aligned - tg, axis=2)))
 
 
+def keypoint_3d_pck(pred: torch.Tensor, gt: torch.Tensor, threshold: float = 150.0) -> float:
+    """hpe/mh_so3_hpe/metrics/pck.py:77-141 with alignment='none', mask=None: pred / gt [N, K, 3]."""
+    import numpy as np
+    p, g = pred.detach().cpu().numpy(), gt.detach().cpu().numpy()
+    mask = np.ones(g.shape[:2]).astype(bool)
+    error = np.linalg.norm(p - g, ord=2, axis=-1)
+    return float((error < threshold).astype(np.float32)[mask].mean() * 100)
+
+
+def keypoint_3d_auc(pred: torch.Tensor, gt: torch.Tensor) -> float:
+    """pck.py:144-198 with alignment='none', mask=None."""
+    import numpy as np
+    p, g = pred.detach().cpu().numpy(), gt.detach().cpu().numpy()
+    mask = np.ones(g.shape[:2]).astype(bool)
+    error = np.linalg.norm(p - g, ord=2, axis=-1)
+    thresholds = np.linspace(0., 150, 31)
+    pck_values = np.zeros(len(thresholds))
+    for i in range(len(thresholds)):
+        pck_values[i] = (error < thresholds[i]).astype(np.float32)[mask].mean()
+    return float(pck_values.mean() * 100)
+
+
 # --------------------------------------------------------------------------------------
 # SURVEY.md §8f-1: evaluation epilogue with flip test-time augmentation
 # --------------------------------------------------------------------------------------

@@ -185,6 +185,14 @@ def procrustes_golden(ref):
     mirrored[..., 0] *= -1
     cases["mirrored"] = (mirrored + 0.02 * torch.randn(3, 27, 17, 3, generator=g), y)
     out = {name: {"pred": p, "target": t, "p_mpjpe": float(p_mpjpe(p, t))} for name, (p, t) in cases.items()}
+    # 3DPCK / AUC (pck.py:77-198) on millimetre-scale points, including errors that sit exactly on thresholds
+    from mh_so3_hpe.metrics.pck import keypoint_3d_pck, keypoint_3d_auc
+    gt = 300.0 * torch.randn(400, 17, 3, generator=g)
+    pred = gt + 60.0 * torch.randn(400, 17, 3, generator=g)
+    pred[0, :, :] = gt[0, :, :]
+    pred[0, :, 0] += torch.arange(17, dtype=torch.float32) * 10.0          # errors 0, 10, ..., 160: exact multiples of 5
+    out["pck"] = {"pred": pred, "gt": gt, "pck150": float(keypoint_3d_pck(pred, gt, threshold=150)),
+                  "pck50": float(keypoint_3d_pck(pred, gt, threshold=50)), "auc": float(keypoint_3d_auc(pred, gt))}
     torch.save(out, os.path.join(OUT, "procrustes.pt"))
 
 

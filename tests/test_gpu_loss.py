@@ -213,8 +213,30 @@ def test_p_mpjpe_vs_reference_golden():
     from manipose_b200 import metrics as M
     g = torch.load(os.path.join(GOLD, "procrustes.pt"), weights_only=False)
     for name, e in g.items():
+        if name == "pck":
+            continue
         got = M.p_mpjpe(e["pred"].cuda(), e["target"].cuda())
         assert abs(got - e["p_mpjpe"]) <= 2e-5 * e["p_mpjpe"], (name, got, e["p_mpjpe"])
+
+
+def test_pck_auc_vs_reference_golden_and_oracle():
+    """3DPCK / AUC are counts: equal to the reference fixture (incl. errors exactly on thresholds) and to the numpy oracle at
+    4.2 M points, up to the float32 rounding of count / N."""
+    from manipose_b200 import metrics as M
+    e = torch.load(os.path.join(GOLD, "procrustes.pt"), weights_only=False)["pck"]
+    p, g = e["pred"].cuda(), e["gt"].cuda()
+    assert abs(M.keypoint_3d_pck(p, g, threshold=150) - e["pck150"]) <= 1e-5
+    assert abs(M.keypoint_3d_pck(p, g, threshold=50) - e["pck50"]) <= 1e-5
+    assert abs(M.keypoint_3d_auc(p, g) - e["auc"]) <= 1e-5
+    gen = torch.Generator().manual_seed(4)
+    gt = 300.0 * torch.randn(248832, 17, 3, generator=gen)
+    pred = gt + 70.0 * torch.randn(248832, 17, 3, generator=gen)
+    assert abs(M.keypoint_3d_pck(pred.cuda(), gt.cuda()) - O.keypoint_3d_pck(pred, gt)) <= 1e-4
+    assert abs(M.keypoint_3d_auc(pred.cuda(), gt.cuda()) - O.keypoint_3d_auc(pred, gt)) <= 1e-4
+    with pytest.raises(NotImplementedError):
+        M.keypoint_3d_pck(p, g, alignment="procrustes")
+    with pytest.raises(ValueError):
+        M.keypoint_3d_auc(p, g, alignment="affine")
 
 
 def test_p_mpjpe_vs_oracle_at_scale_and_invariance():

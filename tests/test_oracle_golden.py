@@ -154,4 +154,8 @@ def test_p_mpjpe_oracle_matches_frozen_reference_outputs():
     """Protocol #2 (MPJPE after Procrustes alignment) frozen from the reference's numpy implementation."""
     g = torch.load(os.path.join(GOLD, "procrustes.pt"), weights_only=False)
     for name, e in g.items():
+        if name == "pck":
+            assert O.keypoint_3d_pck(e["pred"], e["gt"], 150.0) == e["pck150"] and O.keypoint_3d_pck(e["pred"], e["gt"], 50.0) == e["pck50"]
+            assert O.keypoint_3d_auc(e["pred"], e["gt"]) == e["auc"]
+            continue
         assert abs(O.p_mpjpe(e["pred"], e["target"]) - e["p_mpjpe"]) <= 1e-6 * e["p_mpjpe"], name

@@ -233,3 +233,14 @@ def test_p_mpjpe_matches_reference(ref):
     from mh_so3_hpe.metrics.mean_joint_errors import p_mpjpe
     for name, (pred, y) in _procrustes_cases().items():
         assert O.p_mpjpe(pred, y) == float(p_mpjpe(pred, y)), name
+
+
+def test_pck_auc_match_reference(ref):
+    """3DPCK / AUC restatements (alignment 'none', no mask) vs the reference's numpy functions."""
+    from mh_so3_hpe.metrics.pck import keypoint_3d_pck, keypoint_3d_auc
+    g = torch.Generator().manual_seed(23)
+    gt = 300.0 * torch.randn(500, 17, 3, generator=g)                       # millimetres, like main_3dhp.py:880
+    pred = gt + 60.0 * torch.randn(500, 17, 3, generator=g)
+    for thr in (150.0, 50.0):
+        assert O.keypoint_3d_pck(pred, gt, thr) == float(keypoint_3d_pck(pred, gt, threshold=thr))
+    assert O.keypoint_3d_auc(pred, gt) == float(keypoint_3d_auc(pred, gt))
