@@ -233,6 +233,13 @@ size_t mp_pck_auc_workspace_bytes(void);
 int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float threshold, float* out, void* workspace, size_t workspace_bytes,
                mp_stream_t stream);
 
+/* Clip windowing on the device (PoseSequenceGenerator.__getitem__, hpe/mh_so3_hpe/data/generators.py:106-154; fixed starts, no missing
+ * joints): frames2d [N, n_joints, in_chans] / frames3d [N, n_joints, 3] hold all sequences back to back; table (device, int64[n_windows][3])
+ * = {first frame of the window's sequence, sequence length, start frame inside the sequence}; out2d [n_windows, n_frames, n_joints, in_chans],
+ * out3d [n_windows, n_frames, n_joints, 3]; frames past the end of the sequence replicate its last frame. */
+int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, float* out2d, float* out3d, int64_t n_windows,
+                      int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream);
+
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:

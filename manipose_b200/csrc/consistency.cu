@@ -370,6 +370,27 @@ __global__ void pck_finalize_kernel(const unsigned long long* __restrict__ count
   }
 }
 
+// -------------------------------------------------------------------------------------------------- clip windowing
+// PoseSequenceGenerator.__getitem__ (hpe/mh_so3_hpe/data/generators.py:106-154, non-random start, miss_type "no_miss") as a device-side
+// gather: all sequences live concatenated on the device, window w = table[w] = {first frame of its sequence, sequence length, start frame}
+// reads frames start .. start + T - 1 of that sequence, frames past the end replicate the last one (F.pad(mode="replicate"), :132-146).
+__global__ void gather_windows_kernel(const float* __restrict__ frames2d, const float* __restrict__ frames3d, const int64_t* __restrict__ table,
+                                      float* __restrict__ out2d, float* __restrict__ out3d, int64_t n_windows, int64_t T, int c2, int c3) {
+  const int per = c2 + c3;                     // floats per frame: 17 * 2 + 17 * 3
+  const int64_t total = n_windows * T * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % per);
+    const int64_t wl = i / per, w = wl / T, l = wl - w * T;
+    const int64_t off = table[w * 3 + 0], len = table[w * 3 + 1], start = table[w * 3 + 2];
+    int64_t f = start + l;
+    if (f > len - 1) f = len - 1;
+    if (e < c2)
+      out2d[wl * c2 + e] = frames2d[(off + f) * c2 + e];
+    else
+      out3d[wl * c3 + (e - c2)] = frames3d[(off + f) * c3 + (e - c2)];
+  }
+}
+
 constexpr int kPmpjpeBlocks = 148 * 8;
 
 int slabs_for(int64_t n_clips, int64_t n_frames, int64_t* frames_per_slab) {
@@ -445,6 +466,21 @@ int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float thres
   MP_CHECK(check_launch("pck_hist_kernel"));
   pck_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counts, (double)n_points, out);
   return check_launch("pck_finalize_kernel");
+}
+
+int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, float* out2d, float* out3d, int64_t n_windows,
+                      int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(frames2d && frames3d && table && out2d && out3d && n_windows >= 0 && n_frames >= 1 && n_joints >= 1 && in_chans >= 1, MP_EINVAL,
+             "mp_gather_windows: bad arguments");
+  if (n_windows == 0) return MP_OK;
+  const int c2 = n_joints * in_chans, c3 = n_joints * 3;
+  const int64_t total = n_windows * n_frames * (c2 + c3);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  gather_windows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frames2d, frames3d, table, out2d, out3d, n_windows, n_frames, c2, c3);
+  return check_launch("gather_windows_kernel");
 }
 
 }  // extern "C"

@@ -1,3 +1,4 @@
 from .skeleton import Skeleton, h36m17_skeleton, skeleton_tables
+from .windows import DeviceSequenceWindows
 
-__all__ = ["Skeleton", "h36m17_skeleton", "skeleton_tables"]
+__all__ = ["Skeleton", "h36m17_skeleton", "skeleton_tables", "DeviceSequenceWindows"]

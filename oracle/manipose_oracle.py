@@ -501,6 +501,20 @@ def p_mpjpe(predicted: torch.Tensor, target: torch.Tensor) -> float:
     return float(np.mean(np.linalg.norm(aligned - tg, axis=2)))
 
 
+def sequence_windows(poses_3d, poses_2d, seq_len: int, drop_last: bool = True):
+    """hpe/mh_so3_hpe/data/generators.py:83-154 (PoseSequenceGenerator with fixed starts and miss_type 'no_miss'): every item
+    (pose_2d [L,J,2], pose_3d [L,J,3]) in dataset order; the last, shorter window of a sequence is replicate-padded when drop_last is False."""
+    items = []
+    for p3, p2 in zip(poses_3d, poses_2d):
+        t3, t2 = torch.from_numpy(p3).float(), torch.from_numpy(p2).float()
+        n = t3.shape[0]
+        size = n // seq_len + (1 if (not drop_last and n % seq_len > 0) else 0)
+        for k in range(size):
+            idx = torch.clamp(torch.arange(k * seq_len, (k + 1) * seq_len), max=n - 1)      # replicate padding = clamp to the last frame
+            items.append((t2[idx], t3[idx]))
+    return items
+
+
 def keypoint_3d_pck(pred: torch.Tensor, gt: torch.Tensor, threshold: float = 150.0) -> float:
     """hpe/mh_so3_hpe/metrics/pck.py:77-141 with alignment='none', mask=None: pred / gt [N, K, 3]."""
     import numpy as np
@@ -534,6 +548,58 @@ def tta_prediction(x: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str = "we
     poses_f, scores_f = rmcl_forward(pose_flip(x.clone()), sd)
     pred_f = pose_flip(aggregate(poses_f, scores_f, mode).clone())
     return (pred + pred_f) / 2
+
+
+def evaluate(batches, sd: Dict[str, torch.Tensor], tta: bool, return_hyps: bool = False, compute_oracle: bool = True, forward=None):
+    """hpe/eval_utils.py:16-203 (``evaluate`` + ``evaluation_metrics``) for the RMCL model, bookkeeping included: per batch the
+    weighted-average prediction, the oracle figure (non-TTA: sum of the per-frame joint-MEAN errors divided by J once more, :57-64 — the
+    reference's normalisation quirk, kept), the best-score ("per-sample oracle") figure, their flip-TTA variants (:95-135), MPJPE
+    average / sum in mm; totals normalised as :186-197.  ``batches`` = iterable of (input_2d [B,L,J,2], target_3d [B,L,J,3]).
+    ``forward`` (x -> poses, scores) replaces the oracle forward when only the bookkeeping is under test."""
+    forward = forward or (lambda inp: rmcl_forward(inp, sd))
+    mpjpe_total, m_p3d, n, batch_no = 0.0, 0.0, 0, 0
+    oracle_total, psoracle_total = 0, 0
+    all_pred, all_target, all_oracle = [], [], []
+    for batch_no, (x, y) in enumerate(batches, start=1):
+        b, l, j, _ = y.shape
+        y = y.float()
+        poses, scores = forward(x.float())
+        hyp = concat_hyp_and_scores(poses, scores)
+        pred = aggregate(poses, scores, "weighted_ave")
+        if compute_oracle:
+            val, oracle_preds = aggregate(hyp[..., :-1], mode="oracle", ground_truth=y)
+            oracle_mpjpe = val.sum() / j
+            ps_preds = aggregate(hyp[..., :-1], scores=hyp[..., -1], mode="best_score")
+            ps_mpjpe = mpjpe_error(ps_preds, y, "sum") / j
+        if tta:
+            poses_f, scores_f = forward(pose_flip(x.float()))
+            pred_f = aggregate(poses_f, scores_f, "weighted_ave")
+            if compute_oracle:
+                hyp_f = pose_flip(poses_f)
+                _, oracle_f = aggregate(hyp_f, mode="oracle", ground_truth=y)
+                oracle_preds = (oracle_preds + oracle_f) / 2
+                oracle_mpjpe = mpjpe_error(oracle_preds, y, "sum") / j
+                ps_f = aggregate(hyp_f, scores=scores_f.expand(-1, -1, -1, j), mode="best_score")
+                ps_mpjpe = mpjpe_error((ps_preds + ps_f) / 2, y, "sum") / j
+            pred = (pred + pose_flip(pred_f)) / 2
+        n += b
+        if return_hyps:
+            hyp = hyp.clone()
+            hyp[..., :-1] *= 1000
+            all_pred.append(hyp)
+        else:
+            all_pred.append(pred * 1000)
+        mpjpe_total += (mpjpe_error(pred, y, "average") * 1000).item()
+        m_p3d += (mpjpe_error(pred, y, "sum") * 1000).numpy()
+        if compute_oracle:
+            oracle_total = oracle_total + oracle_mpjpe
+            psoracle_total = psoracle_total + ps_mpjpe
+            all_oracle.append(oracle_preds * 1000)
+        all_target.append(y)
+    performance = m_p3d / (n * l * j)
+    if not compute_oracle:
+        return all_pred, all_target, performance
+    return all_pred, all_target, performance, oracle_total / (n * l) * 1000, psoracle_total / (n * l) * 1000, all_oracle
 
 
 # --------------------------------------------------------------------------------------

@@ -359,3 +359,42 @@ def test_tta_epilogue(mode):
     assert float(err.median()) <= 8e-3
     with pytest.raises(ValueError):
         lift_with_tta(m, x, "oracle")
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_evaluate_drop_in(tta):
+    """``evaluate`` of hpe/eval_utils.py:16-203 (restated in the oracle, pinned to the unmodified reference in
+    tests/test_oracle_vs_reference.py).  (a) bookkeeping: on the SAME hypotheses (the device forward fed to the oracle's bookkeeping) every
+    returned quantity agrees to fp32 reduction order; (b) end to end vs the oracle's fp32 forward: MPJPE within the 0.05 mm gate (fp16)."""
+    import types
+    from manipose_b200.evaluation import evaluate
+    import manipose_b200 as mb
+    T, K = 27, 5
+    m, sd = _init42_model(T, K, "fp16")
+    sk = mb.h36m17_skeleton()
+    g = torch.Generator().manual_seed(21)
+    batches = [(0.3 * torch.randn(b, T, 17, 2, generator=g), 0.3 * torch.randn(b, T, 17, 3, generator=g)) for b in (3, 2)]
+    cfg = types.SimpleNamespace(train=types.SimpleNamespace(tta=tta))
+
+    def device_forward(x):
+        with torch.no_grad():
+            p, s = m(x.cuda())
+        return p.cpu(), s.cpu()
+
+    for return_hyps in (False, True):
+        got = evaluate(m, batches, "cuda", cfg, sk, return_hyps=return_hyps, compute_oracle=True)
+        want = O.evaluate(batches, sd, tta, return_hyps=return_hyps, compute_oracle=True, forward=device_forward)
+        assert len(got) == 6
+        for a, b in zip(got[0] + got[1] + got[5], want[0] + want[1] + want[5]):
+            assert a.is_cuda
+            torch.testing.assert_close(a.cpu(), b, rtol=1e-6, atol=1e-4)      # mm
+        for i in (2, 3, 4):
+            assert abs(float(got[i]) - float(want[i])) <= 1e-5 * abs(float(want[i])), i
+    got3 = evaluate(m, batches, "cuda", cfg, sk, compute_oracle=False)
+    assert len(got3) == 3 and abs(float(got3[2]) - float(got[2])) <= 1e-6 * float(got[2])
+    ref = O.evaluate(batches, sd, tta, compute_oracle=True)
+    assert abs(float(got[2]) - float(ref[2])) <= 0.05                         # north_star gate, mm
+    # oracle / best-score figures depend on per-frame hypothesis PICKS, which can flip under the 16-bit backbone error (measured: 0.051 / <0.05 mm)
+    assert abs(float(got[3]) - float(ref[3])) <= 0.25 and abs(float(got[4]) - float(ref[4])) <= 0.25
+    with pytest.raises(TypeError):
+        evaluate(torch.nn.Linear(2, 2), batches, "cuda", cfg, sk)

@@ -255,3 +255,25 @@ def test_p_mpjpe_vs_oracle_at_scale_and_invariance():
     moved = (0.6 * pred @ q + torch.tensor([1.0, 2.0, -0.5])).cuda()
     assert abs(M.p_mpjpe(moved, y.cuda()) - got) <= 1e-4 * got
     assert M.p_mpjpe((2.5 * y @ q + 0.7).cuda(), y.cuda()) <= 1e-5
+
+
+@pytest.mark.parametrize("drop_last", [True, False])
+def test_device_sequence_windows_vs_oracle(drop_last):
+    """the device-side window gather returns exactly the items of the reference generator (restated in the oracle and
+    pinned to it), including replicate-padded tails, ragged sequences shorter than one window, and arbitrary index order."""
+    import numpy as np
+    from manipose_b200.data import DeviceSequenceWindows
+    rng = np.random.default_rng(1)
+    lens = [243, 300, 27, 1000, 5, 486]
+    p3 = [rng.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    p2 = [rng.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    for seq_len in (243, 27):
+        items = O.sequence_windows(p3, p2, seq_len, drop_last)
+        w = DeviceSequenceWindows(p3, p2, seq_len=seq_len, drop_last=drop_last)
+        assert len(w) == len(items)
+        order = list(reversed(range(len(items))))
+        b2, b3 = w.batch(order)
+        assert torch.equal(b2.cpu(), torch.stack([items[i][0] for i in order])) and torch.equal(b3.cpu(), torch.stack([items[i][1] for i in order]))
+        got = [x for x in w.batches(4)]
+        assert sum(x[0].shape[0] for x in got) == len(items)
+        assert torch.equal(torch.cat([x[1] for x in got]).cpu(), torch.stack([it[1] for it in items]))

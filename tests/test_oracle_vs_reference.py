@@ -244,3 +244,63 @@ def test_pck_auc_match_reference(ref):
     for thr in (150.0, 50.0):
         assert O.keypoint_3d_pck(pred, gt, thr) == float(keypoint_3d_pck(pred, gt, threshold=thr))
     assert O.keypoint_3d_auc(pred, gt) == float(keypoint_3d_auc(pred, gt))
+
+
+@pytest.mark.parametrize("drop_last", [True, False])
+def test_sequence_windows_match_reference_generator(ref, drop_last):
+    """clip windowing of PoseSequenceGenerator (fixed starts, no missing joints), incl. the replicate-padded tail."""
+    import numpy as np
+    from mh_so3_hpe.data.generators import PoseSequenceGenerator
+    rng = np.random.default_rng(0)
+    lens = [27, 40, 9, 81, 5]
+    p3 = [rng.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    p2 = [rng.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    gen = PoseSequenceGenerator(p3, p2, None, seq_len=9, random_start=False, drop_last=drop_last, miss_type="no_miss")
+    items = O.sequence_windows(p3, p2, 9, drop_last)
+    assert len(items) == len(gen)
+    for i, (a2, a3) in enumerate(items):
+        r2, r3 = gen[i]
+        assert torch.equal(a2, r2) and torch.equal(a3, r3), i
+
+
+def _load_reference_evaluate():
+    """hpe/eval_utils.py imports omegaconf only for a type hint (:8): stub it, then import the module from the reference tree."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    from oracle.ref_loader import REFERENCE_ROOT
+    if "omegaconf" not in sys.modules:
+        om = types.ModuleType("omegaconf")
+        om.DictConfig = dict
+        sys.modules["omegaconf"] = om
+    spec = importlib.util.spec_from_file_location("_ref_eval_utils", os.path.join(REFERENCE_ROOT, "hpe", "eval_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("tta", [False, True])
+@pytest.mark.parametrize("return_hyps", [False, True])
+def test_evaluate_matches_reference(ref, tta, return_hyps):
+    """the whole of ``evaluate`` (hpe/eval_utils.py:16-203) — predictions, MPJPE, oracle and per-sample-oracle figures,
+    with and without flip TTA — run unmodified on CPU against the oracle's restatement of its bookkeeping."""
+    import types
+    ev = _load_reference_evaluate()
+    sk = ref.make_skeleton()
+    torch.manual_seed(11)
+    m = ref.architectures.RMCLManifoldMixSTE(sk, num_frame=9, n_hyp=3, drop_path_rate=0.1).eval()
+    _perturb(m)
+    g = torch.Generator().manual_seed(8)
+    batches = [(0.3 * torch.randn(b, 9, 17, 2, generator=g), 0.3 * torch.randn(b, 9, 17, 3, generator=g)) for b in (2, 3)]
+    cfg = types.SimpleNamespace(train=types.SimpleNamespace(tta=tta))
+    want = ev.evaluate(m, [(x.clone(), y.clone()) for x, y in batches], "cpu", cfg, sk, return_hyps=return_hyps, compute_oracle=True)
+    got = O.evaluate(batches, m.state_dict(), tta, return_hyps=return_hyps, compute_oracle=True)
+    assert len(want) == len(got) == 6
+    for a, b in zip(got[0] + got[1] + got[5], want[0] + want[1] + want[5]):
+        torch.testing.assert_close(a, b, rtol=0, atol=2e-3)           # mm
+    assert abs(float(got[2]) - float(want[2])) <= 1e-3
+    assert abs(float(got[3]) - float(want[3])) <= 1e-3 and abs(float(got[4]) - float(want[4])) <= 1e-3
+    want3 = ev.evaluate(m, [(x.clone(), y.clone()) for x, y in batches], "cpu", cfg, sk, return_hyps=return_hyps, compute_oracle=False)
+    got3 = O.evaluate(batches, m.state_dict(), tta, return_hyps=return_hyps, compute_oracle=False)
+    assert len(want3) == len(got3) == 3 and abs(float(got3[2]) - float(want3[2])) <= 1e-3
