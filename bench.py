@@ -449,6 +449,8 @@ def run_train(args):
                 "allreduce": None if ms_local is None else {"exposed_ms_per_step": (ms - ms_local) / steps, "ms_per_step_without": ms_local / steps},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    if graph is not None:
+        graph.close()                          # before the process group goes: NCCL waits for graphs holding its collectives
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -467,8 +469,10 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: T=243 inference (headline); 4: T=27 training step")
     ap.add_argument("--drop-path", type=float, default=0.1, help="config 4: stochastic depth rate (drivers use 0.1)")
     ap.add_argument("--frames", type=int, default=27, help="config 4: frames per clip (27 = 3DHP shape of BASELINE config 4; 243 = H36M)")
-    ap.add_argument("--cuda-graph", action="store_true", help="config 4: capture the whole training step in a CUDA graph")
+    ap.add_argument("--cuda-graph", action="store_true", help="config 4: capture the whole training step (NCCL all-reduces included) in a CUDA graph (default)")
+    ap.add_argument("--eager", action="store_true", help="config 4: launch the step eagerly instead (also reports the exposed all-reduce time)")
     args = ap.parse_args()
+    args.cuda_graph = not args.eager
     if args.impl == "reference":
         run_reference(args)
     elif args.config == 4:
