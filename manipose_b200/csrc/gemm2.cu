@@ -279,16 +279,26 @@ __device__ __forceinline__ void row_stats_exchange(float2* sx, int grp, int row,
   rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
 }
 
-template <typename D, int kLnStages, int kLnSlots>
+template <typename D, int kLnStages, int kLnSlots, bool kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
                       const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, LnArgs args, int M, int K) {
   // The K loop is short (8 or 16 k-blocks) and the epilogue moves 5 bytes per output element, so shared memory goes to the
-  // box ring (4 slots per column half keep ~128 KB of residual loads / output stores in flight per SM), not to operand stages.
+  // box ring (~128 KB of residual loads / output stores in flight per SM), not to operand stages.
+  //
+  // kSplit = false: one 512-column accumulation per tile (every k-block feeds both N = 256 halves, 48 KB stages); the tensor pipe
+  // idles during the epilogue and the epilogue warps during the main loop.
+  // kSplit = true: the two N = 256 halves are accumulated ONE AFTER THE OTHER (the K loop runs twice per tile, A is read twice -
+  // the second time out of L2; 32 KB stages), each into its own half of TMEM with its own full / empty barrier.  All eight
+  // epilogue warps work on one half at a time (warp group g owns columns [128 g, 128 g + 128) of the half), so the first pass over
+  // half 0 overlaps the MMAs of half 1, and half 0 is handed back to the MMA warp - which then starts the NEXT tile - while the
+  // last pass over half 1 is still running.  It wins when the main loop is short (K = 512: 663 -> 580 us at 128 clips); at
+  // K = 1024 the second read of A makes the main loop L2-bound (933 -> 1000 us), so fc2 keeps the single accumulation.
   constexpr int kStages = kLnStages;
-  constexpr int kStageBytes = kABytes + 2 * kWHalfBytes;   // 48 KB: A + this CTA's share of both N = 256 halves
+  constexpr int kStageBytes = kABytes + (kSplit ? 1 : 2) * kWHalfBytes;
+  constexpr int kHalves = kSplit ? 2 : 1;                  // accumulation passes per tile
   constexpr int kN = 512;
-  constexpr int kGS = kLnSlots / 2;                        // slots per column half
+  constexpr int kGS = kLnSlots / 2;                        // slots per warp group
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();             // 128-byte-swizzle tiles need the 1024-byte alignment the declaration asks for
@@ -330,17 +340,19 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       uint32_t phase = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         const int row_a = tile * 2 * kBM + (int)rank * kBM;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
-          uint8_t* sa = stage_base + stage * kStageBytes;
-          const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
-          if (leader) ptx::mbar_expect_tx(&bars.full[stage], 2 * kStageBytes);   // the peer's loads complete_tx on this barrier too
-          ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
-          ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, (int)rank * 128);                      // W rows of columns [0, 256)
-          ptx::tma_load_2d_pair(sa + kABytes + kWHalfBytes, &tm_w, full_leader, kb * kBK, 256 + (int)rank * 128);  // columns [256, 512)
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+        for (int half = 0; half < kHalves; ++half) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            ptx::mbar_wait(&bars.empty[stage], phase ^ 1);
+            uint8_t* sa = stage_base + stage * kStageBytes;
+            const uint32_t full_leader = ptx::mapa_shared(smem_u32(&bars.full[stage]), 0);
+            if (leader) ptx::mbar_expect_tx(&bars.full[stage], 2 * kStageBytes);   // the peer's loads complete_tx on this barrier too
+            ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
+            ptx::tma_load_2d_pair(sa + kABytes, &tm_w, full_leader, kb * kBK, half * 256 + (int)rank * 128);   // W rows of this half's columns
+            if constexpr (!kSplit) ptx::tma_load_2d_pair(sa + kABytes + kWHalfBytes, &tm_w, full_leader, kb * kBK, 256 + (int)rank * 128);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -352,26 +364,29 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        ptx::mbar_wait(&bars.tmem_empty[0], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(&bars.full[stage], phase);
+        for (int half = 0; half < kHalves; ++half) {
+          ptx::mbar_wait(&bars.tmem_empty[half], acc_phase ^ 1);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          const uint64_t da = ptx::umma_desc_sw128(sa);
-          const uint64_t db0 = ptx::umma_desc_sw128(sa + kABytes);
-          const uint64_t db1 = ptx::umma_desc_sw128(sa + kABytes + kWHalfBytes);
+          const uint32_t t_acc = tmem_base + (uint32_t)(half * 256);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            ptx::mbar_wait(&bars.full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+            const uint64_t da = ptx::umma_desc_sw128(sa);
+            const uint64_t db = ptx::umma_desc_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-            ptx::umma_f16_pair(tmem_base, da + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
-            ptx::umma_f16_pair(tmem_base + 256u, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, accum);
-          }
-          ptx::umma_commit_pair(&bars.empty[stage]);
-          if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[0]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+              ptx::umma_f16_pair(t_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accum);
+              if constexpr (!kSplit)
+                ptx::umma_f16_pair(t_acc + 256u, da + (uint64_t)(2 * k), ptx::umma_desc_sw128(sa + kABytes + kWHalfBytes) + (uint64_t)(2 * k), idesc, accum);
+            }
+            ptx::umma_commit_pair(&bars.empty[stage]);
+            if (kb == k_blocks - 1) ptx::umma_commit_pair(&bars.tmem_full[half]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         acc_phase ^= 1;
@@ -380,12 +395,14 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   } else if (warp == 2) {
     if (lane == 0) {
       // ===================== residual loader =====================
-      // Per tile and column half g the slot-use sequence is: 8 residual boxes, then (post-norm) 8 x boxes, then (pre-norm) 4 h
-      // boxes.  Uses are numbered with a running counter n per half: use n lives in slot g * kGS + n % kGS and completes phase
+      // Per tile and warp group g the slot-use sequence is: 8 residual boxes (4 of accumulator half 0, then 4 of half 1), then
+      // (post-norm) 8 x boxes, then (pre-norm) 4 h boxes; box j of a 32-column pass covers columns (j / 4) * 256 + g * 128 + (j % 4) * 32.
+      // Uses are numbered with a running counter n per group: use n lives in slot g * kGS + n % kGS and completes phase
       // n / kGS of slot_empty[slot] when that slot is free again.  A parity wait only distinguishes "the previous phase" from
       // "the one before", and the loader skips the store-only uses, so across tiles it waits for `tile_done` (both halves arrive
       // after their last store has been read: every slot is free) and within a tile only for uses kGS.. (lockstep again).
       const uint32_t uses = 8u + (has_post ? 8u : 0u) + (has_ln ? 4u : 0u);
+      auto box_col32 = [](int g, int j) { return kSplit ? (j >> 2) * 256 + g * 128 + (j & 3) * 32 : g * 256 + j * 32; };
       uint32_t tt = 0;
       uint32_t full_par = 0;                     // parity bit of slot_full per slot (flips with every load into the slot)
       (void)full_par;
@@ -398,7 +415,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             const uint32_t slot = (uint32_t)(g * kGS) + n % kGS;
             if (j >= kGS) ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
             ptx::mbar_expect_tx(&bars.slot_full[slot], kBoxBytes);
-            ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], g * 256 + j * 32, row0);
+            ptx::tma_load_2d(slot_base + slot * kBoxBytes, &tm_r, &bars.slot_full[slot], box_col32(g, j), row0);
           }
         }
       }
@@ -406,11 +423,11 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
-    const int grp = (warp - 4) >> 2;             // column half [256 grp, 256 grp + 256)
+    const int grp = (warp - 4) >> 2;             // warp group: columns [128 grp, 128 grp + 128) of each accumulator half
     const bool elected = ((warp - 4) & 3) == 0 && lane == 0;
     const int row = 32 * q + lane;
     const uint32_t sw = (uint32_t)(row & 7);
-    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(grp * 256);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16);   // + the output column
     uint32_t acc_phase = 0;
     int pending = -1;                            // slot whose TMA store may still be reading shared memory
     uint32_t n = 0;                              // running slot-use counter of this column half (see the loader)
@@ -426,24 +443,38 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       pending = (int)slot;
     };
 
+    // first output column of box j of a 32-column pass / of box jj of the 64-column pass of warp group grp
+    auto box_col32 = [&](int j) { return kSplit ? (j >> 2) * 256 + grp * 128 + (j & 3) * 32 : grp * 256 + j * 32; };
+    auto box_col64 = [&](int jj) { return kSplit ? (jj >> 1) * 256 + grp * 128 + (jj & 1) * 64 : grp * 256 + jj * 64; };
+    // hand accumulator half `half` back to the MMA warp (16 arrivals: every epilogue warp of both CTAs)
+    auto release_half = [&](int half) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&bars.tmem_empty[half]), 0));
+    };
+    const int last_pass = has_ln ? 2 : (has_post ? 1 : 0);   // the last pass that reads TMEM releases each half as it finishes it
+
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
       const int row0 = tile * 2 * kBM + (int)rank * kBM;
       const int grow = row0 + row;
-      ptx::mbar_wait(&bars.tmem_full[0], acc_phase);
-      ptx::tc_fence_after();
 
       // ---- pass A: v = acc + bias + resid; shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int j = 0; j < 8; ++j, ++n) {
         const uint32_t ls = n % kGS, slot = (uint32_t)(grp * kGS) + ls;
+        const int col = box_col32(j);
         uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+        if (j == 0 || (kSplit && j == 4)) {      // accumulator (half j / 4) complete
+          ptx::mbar_wait(&bars.tmem_full[j >> 2], acc_phase);
+          ptx::tc_fence_after();
+        }
         ptx::mbar_wait(&bars.slot_full[slot], (full_par >> ls) & 1);
         full_par ^= 1u << ls;
         uint32_t r[32];
-        ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
+        ptx::tmem_ld32(t_row + (uint32_t)col, r);
         ptx::tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(args.bias + grp * 256 + j * 32);
+        const float4* b4 = reinterpret_cast<const float4*>(args.bias + col);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4));
@@ -463,16 +494,20 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           r[4 * c + 3] = __float_as_uint(v.w);
           if (!has_post) *p = v;
         }
-        if (has_post || has_ln) ptx::tmem_st32(t_row + (uint32_t)(j * 32), r);
+        if (has_post || has_ln) ptx::tmem_st32(t_row + (uint32_t)col, r);
         if (!has_post) ptx::fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);            // every thread of the half is done with the residual box
+        named_bar_sync(1 + grp, 128);            // every thread of the group is done with the residual box
         if (elected) {
           if (!has_post) {
-            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, grp * 256 + j * 32, row0);
+            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
             after_store(slot);
           } else {
             ptx::mbar_arrive(&bars.slot_empty[slot]);
           }
+        }
+        if (last_pass == 0 && j == 7) {          // no later pass reads TMEM
+          release_half(0);
+          if constexpr (kSplit) release_half(1);
         }
       }
       float mean = 0.f, rstd = 0.f;
@@ -494,9 +529,9 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
           ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
           uint32_t r[32];
-          ptx::tmem_ld32(t_row + (uint32_t)(j * 32), r);
+          const int col = box_col32(j);
+          ptx::tmem_ld32(t_row + (uint32_t)col, r);
           ptx::tmem_ld_wait();
-          const int col = grp * 256 + j * 32;
           const float4* g4 = reinterpret_cast<const float4*>(args.post_g + col);
           const float4* be4 = reinterpret_cast<const float4*>(args.post_b + col);
 #pragma unroll
@@ -524,13 +559,14 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             r[4 * c + 3] = __float_as_uint(y.w);
             *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4)) = y;
           }
-          if (has_ln) ptx::tmem_st32(t_row + (uint32_t)(j * 32), r);
+          if (has_ln) ptx::tmem_st32(t_row + (uint32_t)col, r);
           ptx::fence_proxy_async_smem();
           named_bar_sync(1 + grp, 128);
           if (elected) {
             ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
             after_store(slot);
           }
+          if (last_pass == 1 && (kSplit ? (j & 3) == 3 : j == 7)) release_half(kSplit ? j >> 2 : 0);
         }
         if (has_ln) {
           ptx::tmem_st_wait();
@@ -550,9 +586,9 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
-            ptx::tmem_ld32(t_row + (uint32_t)(jj * 64 + half * 32), r);
+            const int col = box_col64(jj) + half * 32;
+            ptx::tmem_ld32(t_row + (uint32_t)col, r);
             ptx::tmem_ld_wait();
-            const int col = grp * 256 + jj * 64 + half * 32;
             const float4* g4 = reinterpret_cast<const float4*>(args.ln_g + col);
             const float4* be4 = reinterpret_cast<const float4*>(args.ln_b + col);
 #pragma unroll
@@ -569,9 +605,10 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ptx::fence_proxy_async_smem();
           named_bar_sync(1 + grp, 128);
           if (elected) {
-            ptx::tma_store_2d(&tm_h, slot_base + slot * kBoxBytes, grp * 256 + jj * 64, row0);
+            ptx::tma_store_2d(&tm_h, slot_base + slot * kBoxBytes, box_col64(jj), row0);
             after_store(slot);
           }
+          if (kSplit ? (jj & 1) : jj == 3) release_half(kSplit ? jj >> 1 : 0);
         }
       }
       // ---- end of tile: the last store's slot must be free before the loader refills it, TMEM is drained
@@ -583,9 +620,6 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
         ptx::mbar_arrive(bars.tile_done);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&bars.tmem_empty[0]), 0));
       acc_phase ^= 1;
     }
     if (elected) ptx::bulk_wait<0>();
@@ -601,8 +635,8 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 }
 
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
-constexpr int pair_ln_smem(int stages, int slots) { return stages * (kABytes + 2 * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
-static_assert(pair_ln_smem(2, 8) <= 232448 && pair_ln_smem(3, 4) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+constexpr int pair_ln_smem(int stages, int slots, bool split) { return stages * (kABytes + (split ? 1 : 2) * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
+static_assert(pair_ln_smem(4, 6, true) <= 232448 && pair_ln_smem(3, 4, false) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -669,8 +703,8 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
-  // shared memory split between operand stages and the box ring: 2 stages + 8 slots for K = 512 (the epilogue dominates), 3 stages +
-  // 4 slots for K = 1024 (measured: 246 vs 267 us at 32 clips); MANIPOSE_LN_CFG=1 / 2 forces one of them
+  // K = 512 (proj): split accumulation, 4 x 32 KB operand stages + 6 box slots; K = 1024 (fc2): single accumulation, 3 x 48 KB
+  // stages + 4 slots (see the kernel's header comment; MANIPOSE_LN_CFG=1 / 2 forces the split / the single variant)
   static const int cfg = getenv("MANIPOSE_LN_CFG") ? atoi(getenv("MANIPOSE_LN_CFG")) : 0;
   auto launch = [&](auto kernel, int smem_bytes) -> int {
     MP_CHECK(set_smem(kernel, smem_bytes));
@@ -678,6 +712,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     return check_launch("pair_linear_ln_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
-  if (cfg == 1 || (cfg == 0 && K >= 1024)) return bf ? launch(pair_linear_ln_kernel<Bf16, 3, 4>, pair_ln_smem(3, 4)) : launch(pair_linear_ln_kernel<Fp16, 3, 4>, pair_ln_smem(3, 4));
-  return bf ? launch(pair_linear_ln_kernel<Bf16, 2, 8>, pair_ln_smem(2, 8)) : launch(pair_linear_ln_kernel<Fp16, 2, 8>, pair_ln_smem(2, 8));
+  if (cfg == 1 || (cfg == 0 && K < 1024))
+    return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
+  return bf ? launch(pair_linear_ln_kernel<Bf16, 3, 4, false>, pair_ln_smem(3, 4, false)) : launch(pair_linear_ln_kernel<Fp16, 3, 4, false>, pair_ln_smem(3, 4, false));
 }
