@@ -45,9 +45,9 @@ def measured_peaks():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 528,768 rows = the default 128-clip
-# micro-batch) from the committed `ncu --set full` capture profiles/r1_pair_linear_ln_full_128clips.csv; algorithmic bytes of that launch
-PROFILED_TRAFFIC_LN = {"bytes_per_launch": 3198.5e6, "algorithmic_bytes": 3249.3e6, "launch": "proj + norm2, M=528768 (128 clips), K=512",
-                       "source": "profiles/r1_pair_linear_ln_full_128clips.csv"}
+# micro-batch) from the committed `ncu --set full` capture profiles/r1b_pair_linear_ln_full_128clips.csv; algorithmic bytes of that launch
+PROFILED_TRAFFIC_LN = {"bytes_per_launch": 3267.0e6, "algorithmic_bytes": 3249.3e6, "launch": "proj + norm2, M=528768 (128 clips), K=512",
+                       "source": "profiles/r1b_pair_linear_ln_full_128clips.csv"}
 
 
 def roofline_object(dom, rl, peaks, step_tflops, traffic):
