@@ -233,12 +233,14 @@ size_t mp_pck_auc_workspace_bytes(void);
 int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float threshold, float* out, void* workspace, size_t workspace_bytes,
                mp_stream_t stream);
 
-/* Clip windowing on the device (PoseSequenceGenerator.__getitem__, hpe/mh_so3_hpe/data/generators.py:106-154; fixed starts, no missing
- * joints): frames2d [N, n_joints, in_chans] / frames3d [N, n_joints, 3] hold all sequences back to back; table (device, int64[n_windows][3])
- * = {first frame of the window's sequence, sequence length, start frame inside the sequence}; out2d [n_windows, n_frames, n_joints, in_chans],
- * out3d [n_windows, n_frames, n_joints, 3]; frames past the end of the sequence replicate its last frame. */
-int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, float* out2d, float* out3d, int64_t n_windows,
-                      int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream);
+/* Clip windowing on the device (PoseSequenceGenerator.__getitem__, hpe/mh_so3_hpe/data/generators.py:106-219): frames2d [N, n_joints, in_chans] /
+ * frames3d [N, n_joints, 3] hold all sequences back to back; table (device, int64[n_windows][3]) = {first frame of the window's sequence,
+ * sequence length, start frame inside the sequence} (fixed starts :93-104 or the host-sampled random starts :121-127); out2d [n_windows,
+ * n_frames, n_joints, in_chans], out3d [n_windows, n_frames, n_joints, 3]; frames past the end of the sequence replicate its last frame
+ * (:132-146).  mask (nullable, float [n_windows, n_frames, n_joints]) = the occlusion pattern multiplied into the 2-D input (:166-215); noise
+ * (nullable, double [n_windows, n_frames, n_joints, in_chans]) = miss_type "noisy" (:206-210), added in fp64 and rounded once like the reference. */
+int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, const float* mask, const double* noise, float* out2d,
+                      float* out3d, int64_t n_windows, int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream);
 
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps

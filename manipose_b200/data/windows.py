@@ -3,8 +3,12 @@ Python DataLoader in the way of a path that lifts ~450 k frames/s.
 
 All sequences are uploaded once, back to back; a batch is one gather kernel (``mp_gather_windows``) driven by the same
 index -> (sequence, start frame) table the reference builds (generators.py:83-104), with the reference's replicate padding of the last,
-shorter window when ``drop_last`` is False.  Random starts, occlusion masks and noise (training-time augmentations of the generator)
-are not built: this is the deterministic evaluation / inference feed."""
+shorter window when ``drop_last`` is False.  The training-time randomness of the generator — random start frames (:121-127), the
+occlusion masks of every ``miss_type`` (:157-205) and the "noisy" input perturbation (:206-210) — is sampled ON THE HOST with the very RNG
+calls the reference makes, item by item in batch order, so a seeded run reproduces a seeded single-worker reference loader bit for bit;
+only the sampled parameters (start frame, mask, noise) travel to the device, where the gather applies them.  The generator's
+``transform`` hook (an arbitrary Python callable) is not carried over."""
+import math
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -15,11 +19,22 @@ from .. import ops
 
 
 class DeviceSequenceWindows:
+    possible_miss_types_rates = {            # generators.py:50-57
+        "no_miss": 0.2,
+        "random": 0.2,
+        "random_left_arm_right_leg": 0.4,
+        "structured_joint": 0.4,
+        "structured_frame": 0.2,
+    }
+
     def __init__(self, poses_3d: List[np.ndarray], poses_2d: List[np.ndarray], seq_len: int = 243, drop_last: bool = True,
-                 device: str = "cuda"):
+                 device: str = "cuda", random_start: bool = False, miss_type: str = "no_miss", miss_rate: float = 0.2,
+                 noise_sigma: float = 5):
         assert poses_3d is not None and len(poses_3d) == len(poses_2d)
         self.seq_len = int(seq_len)
         self.drop_last = drop_last
+        self.random_start = random_start
+        self.miss_type, self.miss_rate, self.noise_sigma = miss_type, miss_rate, noise_sigma
         lengths = [int(p.shape[0]) for p in poses_3d]
         offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64) if lengths else np.zeros(0, np.int64)
         rows = []
@@ -33,21 +48,69 @@ class DeviceSequenceWindows:
         dev = torch.device(device)
         self.frames_3d = torch.from_numpy(np.concatenate(poses_3d)).float().contiguous().to(dev)
         self.frames_2d = torch.from_numpy(np.concatenate(poses_2d)).float().contiguous().to(dev)
-        self.table_dev = self.table.to(dev)
 
     def __len__(self) -> int:
         return self.table.shape[0]
 
+    def _sample_mask(self):
+        """generators.py:157-210 for one item: -> (mask [L, J] float64 or None, noise [L, J, C] float64 or None), same numpy RNG calls."""
+        shape = (self.seq_len, self.n_joints)
+        if self.miss_type == "all":
+            miss_type = np.random.choice(list(self.possible_miss_types_rates.keys()))
+            miss_rate = self.possible_miss_types_rates[miss_type]
+        else:
+            miss_type, miss_rate = self.miss_type, self.miss_rate
+        if miss_type == "no_miss":
+            return None, None
+        if miss_type == "random":
+            mask = np.zeros(shape)
+            u = np.random.uniform(0.0, 1.0, size=shape)
+            mask[u > miss_rate] = 1.0
+            return mask, None
+        if miss_type == "random_left_arm_right_leg":
+            mask = np.ones(shape)
+            rand = np.random.choice(self.seq_len, size=math.floor(miss_rate * self.seq_len), replace=False).tolist()
+            for i in [1, 2, 3, 11, 12, 13]:
+                mask[rand, i] = 0.0
+            return mask, None
+        if miss_type in ("structured_joint", "structured_frame"):
+            mask = np.ones(shape)
+            occl_len = int(self.seq_len * miss_rate)
+            rand = np.random.choice(self.seq_len - occl_len, size=1, replace=False)
+            if miss_type == "structured_joint":
+                mask[rand[0]: rand[0] + occl_len, [1, 2, 3]] = 0.0
+            else:
+                mask[rand[0]: rand[0] + occl_len] = 0.0
+            return mask, None
+        if miss_type == "noisy":
+            return None, np.random.normal(0, self.noise_sigma, size=shape + (self.in_chans,))
+        raise ValueError(f"Unexpected miss_type: {self.miss_type}")
+
     def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (pose_2d [B, L, J, in_chans], pose_3d [B, L, J, 3]) on the device, equal to stacking the reference generator's items."""
+        """-> (pose_2d [B, L, J, in_chans], pose_3d [B, L, J, 3]) on the device, equal to stacking the reference generator's items
+        ``[gen[i] for i in indices]`` (with the same torch / numpy seeds when the generator is randomised)."""
         ops._need_cuda(self.frames_2d)
-        idx = torch.as_tensor(list(indices), dtype=torch.int64, device=self.table_dev.device)
-        rows = self.table_dev.index_select(0, idx).contiguous()
+        dev = self.frames_2d.device
+        idx = list(indices)
+        rows = self.table[idx].clone()
+        masks, noises = [], []
+        for r in range(rows.shape[0]):                                    # the reference's per-item order: start frame, then mask
+            if self.random_start:
+                rows[r, 2] = torch.randint(low=0, high=int(rows[r, 1]) - self.seq_len, size=(1,)).item()   # generators.py:121-127
+            m, nz = self._sample_mask()
+            masks.append(m)
+            noises.append(nz)
         b, t, j = rows.shape[0], self.seq_len, self.n_joints
-        out2d = torch.empty((b, t, j, self.in_chans), dtype=torch.float32, device=rows.device)
-        out3d = torch.empty((b, t, j, 3), dtype=torch.float32, device=rows.device)
-        rc = L.load().mp_gather_windows(L.ptr(self.frames_2d), L.ptr(self.frames_3d), L.ptr(rows), L.ptr(out2d), L.ptr(out3d), b, t, j,
-                                        self.in_chans, L.stream_ptr())
+        mask = noise = None
+        if any(m is not None for m in masks):
+            mask = torch.from_numpy(np.stack([np.ones((t, j)) if m is None else m for m in masks])).float().to(dev)
+        if any(nz is not None for nz in noises):
+            noise = torch.from_numpy(np.stack([np.zeros((t, j, self.in_chans)) if nz is None else nz for nz in noises])).double().to(dev)
+        rows = rows.contiguous().to(dev)
+        out2d = torch.empty((b, t, j, self.in_chans), dtype=torch.float32, device=dev)
+        out3d = torch.empty((b, t, j, 3), dtype=torch.float32, device=dev)
+        rc = L.load().mp_gather_windows(L.ptr(self.frames_2d), L.ptr(self.frames_3d), L.ptr(rows), L.ptr(mask), L.ptr(noise), L.ptr(out2d),
+                                        L.ptr(out3d), b, t, j, self.in_chans, L.stream_ptr())
         L.check(rc, "mp_gather_windows")
         ops._count()
         return out2d, out3d

@@ -501,17 +501,64 @@ def p_mpjpe(predicted: torch.Tensor, target: torch.Tensor) -> float:
     return float(np.mean(np.linalg.norm(aligned - tg, axis=2)))
 
 
-def sequence_windows(poses_3d, poses_2d, seq_len: int, drop_last: bool = True):
-    """hpe/mh_so3_hpe/data/generators.py:83-154 (PoseSequenceGenerator with fixed starts and miss_type 'no_miss'): every item
-    (pose_2d [L,J,2], pose_3d [L,J,3]) in dataset order; the last, shorter window of a sequence is replicate-padded when drop_last is False."""
-    items = []
-    for p3, p2 in zip(poses_3d, poses_2d):
-        t3, t2 = torch.from_numpy(p3).float(), torch.from_numpy(p2).float()
-        n = t3.shape[0]
+MISS_TYPE_RATES = {"no_miss": 0.2, "random": 0.2, "random_left_arm_right_leg": 0.4, "structured_joint": 0.4, "structured_frame": 0.2}
+
+
+def occlusion_mask(seq_len: int, n_joints: int, in_chans: int, miss_type: str, miss_rate: float, noise_sigma: float):
+    """hpe/mh_so3_hpe/data/generators.py:157-210 for one item, drawing from numpy's global RNG in the reference's order:
+    -> (mask [L, J] float64, noise [L, J, C] float64 or None)."""
+    import math
+    import numpy as np
+    shape = (seq_len, n_joints)
+    if miss_type == "all":
+        miss_type = np.random.choice(list(MISS_TYPE_RATES.keys()))
+        miss_rate = MISS_TYPE_RATES[miss_type]
+    mask, noise = np.ones(shape), None
+    if miss_type == "no_miss":
+        pass
+    elif miss_type == "random":
+        mask = (np.random.uniform(0.0, 1.0, size=shape) > miss_rate).astype(np.float64)
+    elif miss_type == "random_left_arm_right_leg":
+        frames = np.random.choice(seq_len, size=math.floor(miss_rate * seq_len), replace=False).tolist()
+        for joint in (1, 2, 3, 11, 12, 13):
+            mask[frames, joint] = 0.0
+    elif miss_type in ("structured_joint", "structured_frame"):
+        occl = int(seq_len * miss_rate)
+        first = np.random.choice(seq_len - occl, size=1, replace=False)[0]
+        if miss_type == "structured_joint":
+            mask[first:first + occl, [1, 2, 3]] = 0.0
+        else:
+            mask[first:first + occl] = 0.0
+    elif miss_type == "noisy":
+        noise = np.random.normal(0, noise_sigma, size=shape + (in_chans,))
+    else:
+        raise ValueError(f"Unexpected miss_type: {miss_type}")
+    return mask, noise
+
+
+def sequence_windows(poses_3d, poses_2d, seq_len: int, drop_last: bool = True, random_start: bool = False, miss_type: str = "no_miss",
+                     miss_rate: float = 0.2, noise_sigma: float = 5, indices=None):
+    """hpe/mh_so3_hpe/data/generators.py:83-219 (PoseSequenceGenerator): the items (pose_2d [L,J,C] * mask, pose_3d [L,J,3]) for ``indices``
+    (default: the whole dataset in order); the last, shorter window of a sequence is replicate-padded when drop_last is False; random
+    starts come from torch's global RNG, masks / noise from numpy's, per item in that order like the reference."""
+    table = []
+    for s, p3 in enumerate(poses_3d):
+        n = p3.shape[0]
         size = n // seq_len + (1 if (not drop_last and n % seq_len > 0) else 0)
-        for k in range(size):
-            idx = torch.clamp(torch.arange(k * seq_len, (k + 1) * seq_len), max=n - 1)      # replicate padding = clamp to the last frame
-            items.append((t2[idx], t3[idx]))
+        table += [(s, k * seq_len) for k in range(size)]
+    items = []
+    for i in (range(len(table)) if indices is None else indices):
+        s, start = table[i]
+        t3, t2 = torch.from_numpy(poses_3d[s]).float(), torch.from_numpy(poses_2d[s]).float()
+        n = t3.shape[0]
+        if random_start:
+            start = torch.randint(low=0, high=n - seq_len, size=(1,)).item()
+        idx = torch.clamp(torch.arange(start, start + seq_len), max=n - 1)          # replicate padding = clamp to the last frame
+        p2, p3 = t2[idx], t3[idx]
+        mask, noise = occlusion_mask(seq_len, p2.shape[1], p2.shape[2], miss_type, miss_rate, noise_sigma)
+        if noise is not None:
+            p2 = p2.double() + torch.from_numpy(noise)   # `pose_2d += noise` with a float64 ndarray re-binds pose_2d to the float64 sum; callers `.float()` it
+        items.append((p2 * torch.from_numpy(mask[..., None]).float(), p3))
     return items
 
 

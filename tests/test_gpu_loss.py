@@ -277,3 +277,29 @@ def test_device_sequence_windows_vs_oracle(drop_last):
         got = [x for x in w.batches(4)]
         assert sum(x[0].shape[0] for x in got) == len(items)
         assert torch.equal(torch.cat([x[1] for x in got]).cpu(), torch.stack([it[1] for it in items]))
+
+
+@pytest.mark.parametrize("miss_type", ["random", "random_left_arm_right_leg", "structured_joint", "structured_frame", "noisy", "all"])
+@pytest.mark.parametrize("random_start", [False, True])
+def test_device_sequence_windows_randomised_vs_oracle(miss_type, random_start):
+    """SURVEY.md §8f-4, training-time side: random start frames, every occlusion pattern and the noisy input, sampled on the host with the
+    reference's RNG calls and applied by the gather kernel, equal the oracle's items (pinned to the reference generator) under the same seeds."""
+    import numpy as np
+    from manipose_b200.data import DeviceSequenceWindows
+    rng = np.random.default_rng(2)
+    lens = [60, 300, 45, 100]
+    p3 = [rng.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    p2 = [rng.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    order = [3, 0, 9, 1, 5, 8, 2]
+    w = DeviceSequenceWindows(p3, p2, seq_len=27, drop_last=True, random_start=random_start, miss_type=miss_type, miss_rate=0.3, noise_sigma=0.05)
+    torch.manual_seed(9)
+    np.random.seed(9)
+    items = O.sequence_windows(p3, p2, 27, True, random_start, miss_type, 0.3, 0.05, indices=order)
+    torch.manual_seed(9)
+    np.random.seed(9)
+    b2, b3 = w.batch(order)
+    assert b2.dtype == torch.float32 and b2.shape == (len(order), 27, 17, 2)
+    assert torch.equal(b2.cpu(), torch.stack([it[0].float() for it in items]))      # "noisy" items are float64 in the reference; callers .float() them
+    assert torch.equal(b3.cpu(), torch.stack([it[1] for it in items]))
+    if miss_type not in ("noisy",):
+        assert miss_type == "all" or float((b2 == 0).float().mean()) > 0.01           # something was actually occluded

@@ -304,3 +304,27 @@ def test_evaluate_matches_reference(ref, tta, return_hyps):
     want3 = ev.evaluate(m, [(x.clone(), y.clone()) for x, y in batches], "cpu", cfg, sk, return_hyps=return_hyps, compute_oracle=False)
     got3 = O.evaluate(batches, m.state_dict(), tta, return_hyps=return_hyps, compute_oracle=False)
     assert len(want3) == len(got3) == 3 and abs(float(got3[2]) - float(want3[2])) <= 1e-3
+
+
+@pytest.mark.parametrize("miss_type", ["random", "random_left_arm_right_leg", "structured_joint", "structured_frame", "noisy", "all"])
+def test_randomised_sequence_windows_match_reference_generator(ref, miss_type):
+    """SURVEY.md §8f-4, training-time side of PoseSequenceGenerator: random start frames and every occlusion pattern, with torch's and
+    numpy's global RNGs seeded identically, reproduce the reference's items bit for bit."""
+    import numpy as np
+    from mh_so3_hpe.data.generators import PoseSequenceGenerator
+    rng = np.random.default_rng(3)
+    lens = [60, 45, 100]
+    p3 = [rng.standard_normal((n, 17, 3)) for n in lens]            # float64: the reference's in-place noise then cannot leak into the dataset
+    p2 = [rng.standard_normal((n, 17, 2)) for n in lens]
+    order = [4, 0, 7, 2, 5, 1]
+    for random_start in (False, True):
+        gen = PoseSequenceGenerator(p3, p2, None, seq_len=20, random_start=random_start, drop_last=True, miss_type=miss_type, miss_rate=0.3,
+                                    noise_sigma=0.05)
+        torch.manual_seed(5)
+        np.random.seed(5)
+        want = [gen[i] for i in order]
+        torch.manual_seed(5)
+        np.random.seed(5)
+        got = O.sequence_windows(p3, p2, 20, True, random_start, miss_type, 0.3, 0.05, indices=order)
+        for (a2, a3), (r2, r3) in zip(got, want):
+            assert torch.equal(a2, r2) and torch.equal(a3, r3)
