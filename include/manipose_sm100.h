@@ -142,15 +142,16 @@ int mp_linear(const void* A, const void* W, const float* bias, const float* resi
               int64_t K, int epilogue, int dtype, mp_stream_t stream);
 
 /* Residual Linear with the LayerNorms that follow it fused into the epilogue (N = 512 = one whole row per CTA pair):
- *   x = resid + A W^T + bias                       (Block.forward residual adds, mix_ste.py:352-358)
+ *   x = resid + s * (A W^T + bias)                 (Block.forward residual adds, mix_ste.py:352-358; s = row_scale[row], the per-sample
+ *                                                   DropPath factor of training, mix_ste.py:334-336 — NULL: s = 1)
  *   if post_gamma: x = LN(x; post_*) (+ pos_embed[(row / pos_div) % pos_mod])   (Spatial_norm / Temporal_norm, :143,149,154,166,170)
  *   x_out (fp32, may alias resid) = x
  *   if ln_gamma: h_out (16-bit) = LN(x; ln_*)      (norm2 of this block / norm1 of the next, :353,356)
  * Same results as mp_linear(MP_EPI_RESIDUAL) followed by mp_layernorm, without the extra passes over the residual stream. */
 int mp_linear_ln(const void* A, const void* W, const float* bias, const float* resid, float* x_out, void* h_out,
-                 const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed,
-                 int64_t pos_div, int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, int64_t M,
-                 int64_t N, int64_t K, int dtype, mp_stream_t stream);
+                 const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
+                 int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, int64_t M, int64_t N,
+                 int64_t K, int dtype, mp_stream_t stream);
 
 /* LayerNorm family (fp32 statistics over C in {128, 512}; one warp per token).
  *   x_in  [n_tokens, C] fp32
@@ -266,7 +267,7 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
  * UMMA operands (no transposed copies); the token contraction is split over the SMs, partial tiles added with TMA reduce stores.
  * n_out % 128 == 0, k_in % 128 == 0. */
 int mp_wgrad(const void* dY, const void* X, float* dW, int64_t n_tokens, int64_t n_out, int64_t k_in, int dtype, mp_stream_t stream);
-/* colsum[C] (fp32) += column sums of a 16-bit [M, C] matrix (bias gradients). */
+/* colsum[C] (fp32) += column sums of a 16-bit [M, C] matrix (bias gradients); C % 8 == 0, src 16-byte aligned. */
 int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream);
 /* Refresh the 16-bit shadows of n_weights GEMM weights in ONE launch (after an optimizer step).  table (device, int64[n_weights][5]) =
  * {fp32 source pointer, 16-bit shadow [rows, cols] pointer, transposed shadow [cols, rows] pointer or 0, rows, cols}; rows, cols % 64 == 0;

@@ -304,19 +304,36 @@ class MixSTE(nn.Module):
             blocks.append((self.TTEblocks[i], 4 * (depth + i), L.MP_ATTN_TEMPORAL, self.Temporal_norm))
         return blocks
 
-    def _droppath_scale(self, blk, mode, n_clips: int, device) -> Optional[torch.Tensor]:
-        """Per-token branch scale of timm's DropPath (mix_ste.py:334-336): Bernoulli(keep) / keep per sample of the block's batch —
-        a (clip, frame) in spatial blocks, a (clip, token) track in temporal blocks.  None when the block keeps everything."""
-        dp = blk.drop_path
-        if not (self.training and isinstance(dp, DropPath) and dp.drop_prob > 0.0):
-            return None
-        keep = 1.0 - dp.drop_prob
+    def _droppath_scales(self, blocks, n_clips: int, device):
+        """Per-token branch scales of timm's DropPath (mix_ste.py:334-336) for BOTH residual branches of every block of one forward:
+        Bernoulli(keep) / keep per sample of the block's batch — a (clip, frame) in spatial blocks, a (clip, token) track in temporal
+        blocks.  Returns [(s1, s2)] per block, entries None where the block keeps everything.  All masks of a forward come out of two
+        ``torch.rand`` calls (one per block kind): drawing them block by block cost ~110 tiny launches per training step."""
         n_frames, n_tok = self.num_frame, self.num_tokens
-        shape = (n_clips, n_frames, 1) if mode == L.MP_ATTN_SPATIAL else (n_clips, 1, n_tok)
-        mask = torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(keep)
-        if keep > 0.0 and dp.scale_by_keep:
-            mask.div_(keep)
-        return mask.expand(n_clips, n_frames, n_tok).reshape(-1).contiguous()
+        out = [[None, None] for _ in blocks]
+        want = {L.MP_ATTN_SPATIAL: [], L.MP_ATTN_TEMPORAL: []}
+        for bi, (blk, _, mode, _) in enumerate(blocks):
+            dp = blk.drop_path
+            if self.training and isinstance(dp, DropPath) and dp.drop_prob > 0.0:
+                keep = 1.0 - dp.drop_prob
+                inv = 1.0 / keep if (keep > 0.0 and dp.scale_by_keep) else 1.0
+                want[mode] += [(bi, 0, keep, inv), (bi, 1, keep, inv)]
+        cache = self.__dict__.setdefault("_dp_consts", {})
+        for mode, items in want.items():
+            if not items:
+                continue
+            key = (mode, str(device), tuple((k, i) for _, _, k, i in items))
+            if key not in cache:                 # built eagerly during warm-up, so a CUDA-graph capture of the step only sees device tensors
+                cache.clear() if len(cache) > 8 else None
+                cache[key] = (torch.tensor([k for _, _, k, _ in items], dtype=torch.float32, device=device).view(-1, 1, 1, 1),
+                              torch.tensor([i for _, _, _, i in items], dtype=torch.float32, device=device).view(-1, 1, 1, 1))
+            keep_t, inv_t = cache[key]
+            shape = (len(items), n_clips, n_frames, 1) if mode == L.MP_ATTN_SPATIAL else (len(items), n_clips, 1, n_tok)
+            mask = (torch.rand(shape, dtype=torch.float32, device=device) < keep_t) * inv_t
+            full = mask.expand(len(items), n_clips, n_frames, n_tok).reshape(len(items), -1).contiguous()
+            for r, (bi, slot, _, _) in enumerate(items):
+                out[bi][slot] = full[r]
+        return out
 
     def _train_forward(self, x2d: torch.Tensor, n_clips: int):
         """The trunk with every tensor the backward sweep needs kept on a tape (no aliasing, no fused residual+LayerNorm):
@@ -334,26 +351,32 @@ class MixSTE(nn.Module):
         self._embed(x2d, n_clips, n_frames, x, h)
         blocks = self._block_list()
         tape = {"x2d": x2d, "n_clips": n_clips, "blocks": []}
+        scales = self._droppath_scales(blocks, n_clips, dev)
         for bi, (blk, wi, mode, post) in enumerate(blocks):
             last = bi + 1 == len(blocks)
-            s1 = self._droppath_scale(blk, mode, n_clips, dev)
-            s2 = self._droppath_scale(blk, mode, n_clips, dev)
+            s1, s2 = scales[bi]
             qkv, o = b16(3 * c), b16(c)
             ops.linear(h, w[wi + 0], blk.attn.qkv.bias, qkv, L.MP_EPI_BIAS)
             ops.attention(qkv, o, n_clips, n_frames, n_tok, c, heads, mode)
-            x1 = f32()
-            if s1 is None:
-                ops.linear(o, w[wi + 1], blk.attn.proj.bias, x1, L.MP_EPI_RESIDUAL, resid=x)
+            x1, h2 = f32(), b16(c)
+            if c == 512:
+                # proj + DropPath-scaled residual add + norm2 in one kernel (x0 stays intact for the tape: resid != x_out)
+                ops.linear_ln(o, w[wi + 1], blk.attn.proj.bias, x, x1, h2, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps,
+                              row_scale=s1)
             else:
-                T.residual_rowscale(x, ops.linear(o, w[wi + 1], blk.attn.proj.bias, b16(c), L.MP_EPI_BIAS), s1, x1)
-            h2 = b16(c)
-            ops.layernorm(x1, None, h2, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
+                if s1 is None:
+                    ops.linear(o, w[wi + 1], blk.attn.proj.bias, x1, L.MP_EPI_RESIDUAL, resid=x)
+                else:
+                    T.residual_rowscale(x, ops.linear(o, w[wi + 1], blk.attn.proj.bias, b16(c), L.MP_EPI_BIAS), s1, x1)
+                ops.layernorm(x1, None, h2, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
             u, a = b16(hidden), b16(hidden)
             ops.linear(h2, w[wi + 2], blk.mlp.fc1.bias, u, L.MP_EPI_BIAS)
             T.gelu_fwd(u, a)
             x2 = f32()
             if s2 is None:
                 ops.linear(a, w[wi + 3], blk.mlp.fc2.bias, x2, L.MP_EPI_RESIDUAL, resid=x1)
+            elif c == 512:
+                ops.linear_ln(a, w[wi + 3], blk.mlp.fc2.bias, x1, x2, None, row_scale=s2)   # fc2 + DropPath-scaled residual add
             else:
                 T.residual_rowscale(x1, ops.linear(a, w[wi + 3], blk.mlp.fc2.bias, b16(c), L.MP_EPI_BIAS), s2, x2)
             rec = {"x0": x, "h1": h, "qkv": qkv, "o": o, "x1": x1, "h2": h2, "u": u, "a": a, "x2": x2, "s1": s1, "s2": s2,

@@ -263,6 +263,7 @@ struct LnArgs {
   const float* pos;      // NULL or [pos_mod, 512]
   const float* ln_g;     // NULL: no pre-norm / h output
   const float* ln_b;
+  const float* row_scale;   // NULL or [M]: x = resid + row_scale[row] * (A W^T + bias) (per-sample DropPath factor)
   float post_eps, ln_eps;
   int pos_div, pos_mod;
 };
@@ -458,8 +459,9 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const int row0 = tile * 2 * kBM + (int)rank * kBM;
       const int grow = row0 + row;
 
-      // ---- pass A: v = acc + bias + resid; shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
+      // ---- pass A: v = resid + scale * (acc + bias); shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      const float scale = (args.row_scale != nullptr && grow < M) ? __ldg(args.row_scale + grow) : 1.0f;
 #pragma unroll 1
       for (int j = 0; j < 8; ++j, ++n) {
         const uint32_t ls = n % kGS, slot = (uint32_t)(grp * kGS) + ls;
@@ -480,10 +482,10 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4));
           const float4 bb = __ldg(b4 + c);
           float4 v = *p;
-          v.x += __uint_as_float(r[4 * c + 0]) + bb.x;
-          v.y += __uint_as_float(r[4 * c + 1]) + bb.y;
-          v.z += __uint_as_float(r[4 * c + 2]) + bb.z;
-          v.w += __uint_as_float(r[4 * c + 3]) + bb.w;
+          v.x = fmaf(scale, __uint_as_float(r[4 * c + 0]) + bb.x, v.x);   // scale == 1: the same two roundings as v += acc + bias
+          v.y = fmaf(scale, __uint_as_float(r[4 * c + 1]) + bb.y, v.y);
+          v.z = fmaf(scale, __uint_as_float(r[4 * c + 2]) + bb.z, v.z);
+          v.w = fmaf(scale, __uint_as_float(r[4 * c + 3]) + bb.w, v.w);
           if (j == 0 && c == 0) shift = v.x;
           const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
           s1 += (d0 + d1) + (d2 + d3);
@@ -675,8 +677,8 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
 
 extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, const float* resid, float* x_out, void* h_out,
                             const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
-                            int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, int64_t M, int64_t N, int64_t K,
-                            int dtype, mp_stream_t stream) {
+                            int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, int64_t M,
+                            int64_t N, int64_t K, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(A && W && bias && resid && x_out, MP_EINVAL, "mp_linear_ln: null pointer");
@@ -700,7 +702,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     MP_CHECK(get_tmap(&th, h_out, M, N, kBM, dtype));
   else
     th = tx;
-  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
+  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, row_scale, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
   // K = 512 (proj): split accumulation, 4 x 32 KB operand stages + 6 box slots; K = 1024 (fc2): single accumulation, 3 x 48 KB

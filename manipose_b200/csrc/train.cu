@@ -496,31 +496,38 @@ __global__ void __launch_bounds__(256) refresh_shadows_kernel(const int64_t* __r
 }
 
 // -------------------------------------------------------------------------------------------------- bias gradient
-// colsum[c] += sum_m src[m, c] over a 16-bit [M, C] matrix.  CTA = 64 columns (32 column pairs = one 128-byte row segment per warp
-// access) x a slab of rows; 8 row lanes per CTA are reduced in shared memory, then ONE atomic per column and CTA.
+// colsum[c] += sum_m src[m, c] over a 16-bit [M, C] matrix, C % 8 == 0.  CTA = 64 columns (8 threads x one 16-byte load = one 128-byte
+// row segment) x a slab of rows; 32 row lanes per CTA with four independent loads in flight each, reduced in shared memory, then ONE
+// atomic per column and CTA.  (A first version read 4 bytes per thread with one load in flight: latency-bound at ~0.8 TB/s.)
 template <typename D>
-__global__ void __launch_bounds__(256) colsum16_kernel(const uint32_t* __restrict__ src, float* __restrict__ colsum, int64_t M, int C2,
+__global__ void __launch_bounds__(256) colsum16_kernel(const uint4* __restrict__ src, float* __restrict__ colsum, int64_t M, int C8,
                                                        int64_t rows_per_cta) {
-  __shared__ float red[8][64];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c2 = blockIdx.x * 32 + cx;
+  __shared__ float red[32][65];
+  const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+  const int c8 = blockIdx.x * 8 + cx;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = min(M, r0 + rows_per_cta);
-  float a0 = 0.f, a1 = 0.f;
-  if (c2 < C2) {
-    for (int64_t m = r0 + ry; m < r1; m += 8) {
-      const float2 v = D::unpack2(src[m * C2 + c2]);
-      a0 += v.x;
-      a1 += v.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto add = [&](const uint4& v) {
+    const float2 a = D::unpack2(v.x), b = D::unpack2(v.y), c = D::unpack2(v.z), d = D::unpack2(v.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  };
+  if (c8 < C8) {
+    int64_t m = r0 + ry;
+    for (; m + 96 < r1; m += 128) {
+      const uint4 v0 = src[m * C8 + c8], v1 = src[(m + 32) * C8 + c8], v2 = src[(m + 64) * C8 + c8], v3 = src[(m + 96) * C8 + c8];
+      add(v0); add(v1); add(v2); add(v3);
     }
+    for (; m < r1; m += 32) add(src[m * C8 + c8]);
   }
-  red[ry][2 * cx] = a0;
-  red[ry][2 * cx + 1] = a1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ry][8 * cx + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < 2 * C2) {
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < 8 * C8) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
     atomicAdd(colsum + blockIdx.x * 64 + threadIdx.x, t);
   }
 }
@@ -751,20 +758,21 @@ int mp_refresh_shadows(const int64_t* table, int n_weights, int max_tiles, int d
 int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(src && colsum && M >= 0 && C >= 2 && C % 2 == 0, MP_EINVAL, "mp_colsum16: bad arguments (C %% 2 == 0)");
+  MP_REQUIRE(src && colsum && M >= 0 && C >= 8 && C % 8 == 0, MP_EINVAL, "mp_colsum16: bad arguments (C %% 8 == 0)");
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_colsum16: unknown dtype %d", dtype);
+  MP_REQUIRE(aligned16(src), MP_EALIGN, "mp_colsum16: src must be 16-byte aligned");
   if (M == 0) return MP_OK;
-  const int c2 = (int)(C / 2);
-  const int gx = (c2 + 31) / 32;
-  // about two CTAs per SM, at least 64 rows each (few atomics per column)
-  int64_t gy = (int64_t)sm_count() * 2 / gx + 1;
-  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
+  const int c8 = (int)(C / 8);
+  const int gx = (c8 + 7) / 8;
+  // about four CTAs per SM, at least 128 rows each (few atomics per column)
+  int64_t gy = (int64_t)sm_count() * 4 / gx + 1;
+  if (gy > (M + 127) / 128) gy = (M + 127) / 128;
   const int64_t rows_per_cta = (M + gy - 1) / gy;
   gy = (M + rows_per_cta - 1) / rows_per_cta;
   if (dtype == MP_DTYPE_BF16)
-    colsum16_kernel<Bf16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, colsum, M, c2, rows_per_cta);
+    colsum16_kernel<Bf16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, colsum, M, c8, rows_per_cta);
   else
-    colsum16_kernel<Fp16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, colsum, M, c2, rows_per_cta);
+    colsum16_kernel<Fp16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, colsum, M, c8, rows_per_cta);
   return check_launch("colsum16_kernel");
 }
 

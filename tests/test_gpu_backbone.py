@@ -79,7 +79,7 @@ def test_linear_is_deterministic_and_persistent_over_many_tiles():
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("m,k", [(4131, 512), (1000, 1024), (256, 512), (255, 512), (257, 1024), (1, 512), (66096, 512)])
-@pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln"])
+@pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln", "ln_rowscale"])
 def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     """mp_linear_ln (CTA pairs, residual add + LayerNorms in the epilogue) vs fp32 torch on the same 16-bit operands."""
     from manipose_b200 import ops
@@ -92,7 +92,10 @@ def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     resid = torch.randn(m, n, generator=gen, device="cuda") * 1.5 + 0.3
     pg, pb, lg, lb = (torch.randn(n, generator=gen, device="cuda") for _ in range(4))
     pos = torch.randn(n_frames, n, generator=gen, device="cuda")
-    x_ref = resid + a.float() @ w.float().t() + bias
+    # per-row branch scale (training-time DropPath factor: 0 or 1 / keep per sample), constant over groups of 17 rows
+    scale = ((torch.rand((m + 16) // 17, generator=gen, device="cuda") < 0.8).float() / 0.8).repeat_interleave(17)[:m].contiguous() \
+        if mode == "ln_rowscale" else None
+    x_ref = resid + (a.float() @ w.float().t() + bias) * (scale[:, None] if scale is not None else 1.0)
     post = (pg, pb) if mode.startswith("post") else None
     use_pos = mode == "post_pos_ln"
     ln = (lg, lb) if mode != "plain" else None
@@ -105,7 +108,7 @@ def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     x = resid.clone()
     h = torch.full((m, n), float("nan"), dtype=td, device="cuda") if ln is not None else None
     ops.linear_ln(a, w, bias, x, x, h, post=post, post_eps=1e-6, pos=pos if use_pos else None, pos_div=n_tok, pos_mod=n_frames, ln=ln,
-                  ln_eps=1e-6)
+                  ln_eps=1e-6, row_scale=scale)
     torch.cuda.synchronize()
     torch.testing.assert_close(x, x_ref, rtol=2e-4, atol=2e-4)
     if ln is not None:

