@@ -144,14 +144,15 @@ int mp_linear(const void* A, const void* W, const float* bias, const float* resi
 /* Residual Linear with the LayerNorms that follow it fused into the epilogue (N = 512 = one whole row per CTA pair):
  *   x = resid + s * (A W^T + bias)                 (Block.forward residual adds, mix_ste.py:352-358; s = row_scale[row], the per-sample
  *                                                   DropPath factor of training, mix_ste.py:334-336 — NULL: s = 1)
+ *   if x_pre (fp32, needs post_gamma, own buffer): x_pre = x     (the pre-post-norm value: the training tape keeps both)
  *   if post_gamma: x = LN(x; post_*) (+ pos_embed[(row / pos_div) % pos_mod])   (Spatial_norm / Temporal_norm, :143,149,154,166,170)
  *   x_out (fp32, may alias resid) = x
  *   if ln_gamma: h_out (16-bit) = LN(x; ln_*)      (norm2 of this block / norm1 of the next, :353,356)
  * Same results as mp_linear(MP_EPI_RESIDUAL) followed by mp_layernorm, without the extra passes over the residual stream. */
 int mp_linear_ln(const void* A, const void* W, const float* bias, const float* resid, float* x_out, void* h_out,
                  const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
-                 int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, int64_t M, int64_t N,
-                 int64_t K, int dtype, mp_stream_t stream);
+                 int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, float* x_pre,
+                 int64_t M, int64_t N, int64_t K, int dtype, mp_stream_t stream);
 
 /* LayerNorm family (fp32 statistics over C in {128, 512}; one warp per token).
  *   x_in  [n_tokens, C] fp32

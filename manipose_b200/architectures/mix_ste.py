@@ -373,7 +373,15 @@ class MixSTE(nn.Module):
             ops.linear(h2, w[wi + 2], blk.mlp.fc1.bias, u, L.MP_EPI_BIAS)
             T.gelu_fwd(u, a)
             x2 = f32()
-            if s2 is None:
+            fused_tail = c == 512 and not last      # fc2 + DropPath-scaled residual + post-norm (+ pos-embed) + next norm1 in one launch
+            if fused_tail:
+                nxt = blocks[bi + 1][0]
+                x3, h_next = f32(), b16(c)
+                pos = self.Temporal_pos_embed if bi == 0 else None   # TTE_foward adds it once, after the first STE block
+                ops.linear_ln(a, w[wi + 3], blk.mlp.fc2.bias, x1, x3, h_next, post=(post.weight, post.bias), post_eps=post.eps, pos=pos,
+                              pos_div=n_tok, pos_mod=n_frames, ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, row_scale=s2,
+                              x_pre=x2)                              # x2 (before the post-norm) stays on the tape for its backward
+            elif s2 is None:
                 ops.linear(a, w[wi + 3], blk.mlp.fc2.bias, x2, L.MP_EPI_RESIDUAL, resid=x1)
             elif c == 512:
                 ops.linear_ln(a, w[wi + 3], blk.mlp.fc2.bias, x1, x2, None, row_scale=s2)   # fc2 + DropPath-scaled residual add
@@ -384,6 +392,8 @@ class MixSTE(nn.Module):
             tape["blocks"].append(rec)
             if last:
                 x, h = x2, None
+            elif fused_tail:
+                x, h = x3, h_next
             else:
                 nxt = blocks[bi + 1][0]
                 x3, h = f32(), b16(c)

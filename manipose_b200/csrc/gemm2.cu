@@ -263,6 +263,7 @@ struct LnArgs {
   const float* pos;      // NULL or [pos_mod, 512]
   const float* ln_g;     // NULL: no pre-norm / h output
   const float* ln_b;
+  int has_xpre;             // with the post-norm: also store the value BEFORE it (tm_p; the training tape needs both)
   const float* row_scale;   // NULL or [M]: x = resid + row_scale[row] * (A W^T + bias) (per-sample DropPath factor)
   float post_eps, ln_eps;
   int pos_div, pos_mod;
@@ -283,7 +284,8 @@ __device__ __forceinline__ void row_stats_exchange(float2* sx, int grp, int row,
 template <typename D, int kLnStages, int kLnSlots, bool kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
-                      const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, LnArgs args, int M, int K) {
+                      const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_p,
+                      LnArgs args, int M, int K) {
   // The K loop is short (8 or 16 k-blocks) and the epilogue moves 5 bytes per output element, so shared memory goes to the
   // box ring (~128 KB of residual loads / output stores in flight per SM), not to operand stages.
   //
@@ -316,6 +318,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   const int k_blocks = K / kBK;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const bool has_post = args.post_g != nullptr, has_ln = args.ln_g != nullptr;
+  const bool store_a = !has_post || args.has_xpre != 0;   // pass A hands its value to a TMA store (x_out, or x_pre ahead of the post-norm)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -323,6 +326,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     ptx::prefetch_tmap(&tm_r);
     ptx::prefetch_tmap(&tm_x);
     if (has_ln) ptx::prefetch_tmap(&tm_h);
+    if (has_post && store_a) ptx::prefetch_tmap(&tm_p);
   }
   if (warp == 1 && lane == 0) init_bars<kStages, kLnSlots>(bars);
   if (warp == 2) {
@@ -494,14 +498,14 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           r[4 * c + 1] = __float_as_uint(v.y);
           r[4 * c + 2] = __float_as_uint(v.z);
           r[4 * c + 3] = __float_as_uint(v.w);
-          if (!has_post) *p = v;
+          if (store_a) *p = v;
         }
         if (has_post || has_ln) ptx::tmem_st32(t_row + (uint32_t)col, r);
-        if (!has_post) ptx::fence_proxy_async_smem();
+        if (store_a) ptx::fence_proxy_async_smem();
         named_bar_sync(1 + grp, 128);            // every thread of the group is done with the residual box
         if (elected) {
-          if (!has_post) {
-            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
+          if (store_a) {
+            ptx::tma_store_2d(has_post ? &tm_p : &tm_x, slot_base + slot * kBoxBytes, col, row0);
             after_store(slot);
           } else {
             ptx::mbar_arrive(&bars.slot_empty[slot]);
@@ -677,8 +681,8 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
 
 extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, const float* resid, float* x_out, void* h_out,
                             const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
-                            int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, int64_t M,
-                            int64_t N, int64_t K, int dtype, mp_stream_t stream) {
+                            int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, float* x_pre,
+                            int64_t M, int64_t N, int64_t K, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(A && W && bias && resid && x_out, MP_EINVAL, "mp_linear_ln: null pointer");
@@ -688,12 +692,13 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   MP_REQUIRE((post_gamma == nullptr) == (post_beta == nullptr) && (ln_gamma == nullptr) == (ln_beta == nullptr), MP_EINVAL,
              "mp_linear_ln: gamma/beta go together");
   MP_REQUIRE(!ln_gamma || h_out, MP_EINVAL, "mp_linear_ln: h_out required with the pre-norm");
+  MP_REQUIRE(!x_pre || (post_gamma && aligned16(x_pre) && x_pre != x_out), MP_EINVAL, "mp_linear_ln: x_pre needs the post-norm and its own buffer");
   MP_REQUIRE(!pos_embed || (post_gamma && pos_div >= 1 && pos_mod >= 1), MP_EINVAL, "mp_linear_ln: pos_embed needs the post-norm and pos_div/pos_mod >= 1");
   MP_REQUIRE(aligned16(A) && aligned16(W) && aligned16(bias) && aligned16(resid) && aligned16(x_out) && aligned16(h_out) &&
                  aligned16(post_gamma) && aligned16(post_beta) && aligned16(ln_gamma) && aligned16(ln_beta) && aligned16(pos_embed),
              MP_EALIGN, "mp_linear_ln: pointers must be 16-byte aligned");
   if (M == 0) return MP_OK;
-  CUtensorMap ta, tw, tr, tx, th;
+  CUtensorMap ta, tw, tr, tx, th, tp;
   MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
   MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
   MP_CHECK(get_tmap(&tr, resid, M, N, kBM, 2));
@@ -702,7 +707,11 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     MP_CHECK(get_tmap(&th, h_out, M, N, kBM, dtype));
   else
     th = tx;
-  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, row_scale, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
+  if (x_pre)
+    MP_CHECK(get_tmap(&tp, x_pre, M, N, kBM, 2));
+  else
+    tp = tx;
+  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, x_pre != nullptr, row_scale, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
   // K = 512 (proj): split accumulation, 4 x 32 KB operand stages + 6 box slots; K = 1024 (fc2): single accumulation, 3 x 48 KB
@@ -710,7 +719,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   static const int cfg = getenv("MANIPOSE_LN_CFG") ? atoi(getenv("MANIPOSE_LN_CFG")) : 0;
   auto launch = [&](auto kernel, int smem_bytes) -> int {
     MP_CHECK(set_smem(kernel, smem_bytes));
-    kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, args, (int)M, (int)K);
+    kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, tp, args, (int)M, (int)K);
     return check_launch("pair_linear_ln_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;

@@ -363,9 +363,9 @@ def linear(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
     return out
 
 
-def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, row_scale=None):
-    """x_out = [LN_post](resid + s * (a @ w^T + bias)) [+ pos]; h_out = LN_pre(x_out) as 16-bit; s = row_scale[row] (fp32 [M]) or 1.
-    N must be 512 (fused epilogue)."""
+def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, row_scale=None, x_pre=None):
+    """x_out = [LN_post](resid + s * (a @ w^T + bias)) [+ pos]; h_out = LN_pre(x_out) as 16-bit; s = row_scale[row] (fp32 [M]) or 1;
+    x_pre (with post) also receives the value before LN_post.      N must be 512 (fused epilogue)."""
     m, k = a.shape
     n = w.shape[0]
     pg, pb = post if post is not None else (None, None)
@@ -375,7 +375,7 @@ def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=Non
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = L.load().mp_linear_ln(L.ptr(a), L.ptr(w), L.ptr(bias), L.ptr(resid), L.ptr(x_out), L.ptr(h_out), L.ptr(pg), L.ptr(pb), post_eps,
-                               L.ptr(pos), pos_div, pos_mod, L.ptr(lg), L.ptr(lb), ln_eps, L.ptr(row_scale), m, n, k, DTYPE_CODE[a.dtype], L.stream_ptr())
+                               L.ptr(pos), pos_div, pos_mod, L.ptr(lg), L.ptr(lb), ln_eps, L.ptr(row_scale), L.ptr(x_pre), m, n, k, DTYPE_CODE[a.dtype], L.stream_ptr())
     L.check(rc, "mp_linear_ln")
     _count()
     if timing is not None:

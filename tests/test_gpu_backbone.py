@@ -79,7 +79,7 @@ def test_linear_is_deterministic_and_persistent_over_many_tiles():
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("m,k", [(4131, 512), (1000, 1024), (256, 512), (255, 512), (257, 1024), (1, 512), (66096, 512)])
-@pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln", "ln_rowscale"])
+@pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln", "ln_rowscale", "post_ln_xpre"])
 def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     """mp_linear_ln (CTA pairs, residual add + LayerNorms in the epilogue) vs fp32 torch on the same 16-bit operands."""
     from manipose_b200 import ops
@@ -99,6 +99,7 @@ def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     post = (pg, pb) if mode.startswith("post") else None
     use_pos = mode == "post_pos_ln"
     ln = (lg, lb) if mode != "plain" else None
+    x_pre_ref = x_ref
     if post is not None:
         x_ref = F.layer_norm(x_ref, (n,), pg, pb, 1e-6)
         if use_pos:
@@ -107,10 +108,13 @@ def test_linear_ln_fused_epilogue(m, k, mode, dtype):
     h_ref = F.layer_norm(x_ref, (n,), lg, lb, 1e-6) if ln is not None else None
     x = resid.clone()
     h = torch.full((m, n), float("nan"), dtype=td, device="cuda") if ln is not None else None
+    x_pre = torch.full((m, n), float("nan"), device="cuda") if mode == "post_ln_xpre" else None
     ops.linear_ln(a, w, bias, x, x, h, post=post, post_eps=1e-6, pos=pos if use_pos else None, pos_div=n_tok, pos_mod=n_frames, ln=ln,
-                  ln_eps=1e-6, row_scale=scale)
+                  ln_eps=1e-6, row_scale=scale, x_pre=x_pre)
     torch.cuda.synchronize()
     torch.testing.assert_close(x, x_ref, rtol=2e-4, atol=2e-4)
+    if x_pre is not None:                           # the value before the post-norm (what the training tape keeps)
+        torch.testing.assert_close(x_pre, x_pre_ref, rtol=2e-4, atol=2e-4)
     if ln is not None:
         assert not torch.isnan(h.float()).any()
         torch.testing.assert_close(h.float(), h_ref, rtol=RTOL[dtype], atol=RTOL[dtype])
