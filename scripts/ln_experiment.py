@@ -1,5 +1,5 @@
 """Development aid: time the fused residual + LayerNorm GEMM (mp_linear_ln) alone.  Usage: python scripts/ln_experiment.py [clips ...]
-Environment knobs of the library (MANIPOSE_LN_GROUPS, MANIPOSE_LN_CFG) are read once per process."""
+The library reads MANIPOSE_LN_CFG once per process (1: split accumulation, 2: single accumulation, unset: by K)."""
 import json
 import math
 import os
@@ -32,7 +32,7 @@ def timeit(fn, iters=8):
 
 
 def main():
-    out = {"groups": os.environ.get("MANIPOSE_LN_GROUPS", "default")}
+    out = {"cfg": os.environ.get("MANIPOSE_LN_CFG", "default")}
     g = torch.Generator(device=dev).manual_seed(0)
     for clips in [int(a) for a in sys.argv[1:]] or [32]:
         m = clips * 243 * 17
