@@ -91,8 +91,9 @@ class RMCLRotMixSTE(MixSTE):
         bf = torch.cat([((w * bet[:, None, :]).sum(-1) + bias).reshape(k * d1), w.new_zeros(n_pad - k * d1)])
         out = T.linear_f32(yhat, wf, bf)[:, :k * d1].reshape(b, l, j, k, d1)
         rot = out[..., :self.out_dim].permute(0, 3, 1, 2, 4)
-        sw = torch.stack([h.score_head.weight[0] for h in self.head])             # [K, J]
-        sb = torch.stack([h.score_head.bias[0] for h in self.head])               # [K]
+        # reshape, not [0]: the backward of a view is free, the backward of an index is a zero fill + a copy per head
+        sw = torch.stack([h.score_head.weight.reshape(-1) for h in self.head])    # [K, J]
+        sb = torch.stack([h.score_head.bias.reshape(()) for h in self.head])      # [K]
         logits = (out[..., self.out_dim] * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
         return rot, logits
 
