@@ -15,7 +15,8 @@
 namespace mp {
 
 int get_tmap_clip_rows(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t rows_per_clip, int64_t cols, int box_rows, int type);  // gemm.cu
-int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type);  // gemm.cu
+int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type,
+                   int box_tok = 1);  // gemm.cu
 
 namespace {
 
@@ -632,7 +633,13 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 // columns per CTA: four CTAs per SM overlap loads, softmax and stores.  Rows [G, 128) of a tile belong to the next tile and are
 // not stored.  Tiles are laid out per CLIP (3-D tensor maps clip the last tile of a clip), so a clip's result does not depend on
 // which other clips share its micro-batch.
-template <typename D>
+//
+// kTracks = true: the same kernel as the TEMPORAL attention of short clips (n_frames <= 128, e.g. the T = 27 / 81 configurations).  A tile
+// holds P = 128 / n_frames whole (clip, token) tracks, fetched by ONE 4-D TMA box {64 columns, P tokens, n_frames frames, 1 clip}: tile row
+// r = frame * P + (token - first token), so the sequences are INTERLEAVED with period P and the softmax window of row r is the columns
+// j = r (mod P), j < P * n_frames.  (n_rows = n_frames, G = P here.)  The persistent two-tile kernel below is built for T = 243 and spends
+// the same fixed cost per (track, head) on 27 frames.
+template <typename D, bool kTracks>
 __global__ void __launch_bounds__(kTcThreads, 4)
 attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_o, int n_rows, int n_tok, int C,
                        int n_heads, int G, int tiles_per_clip) {
@@ -654,6 +661,8 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
   const int tile = (blockIdx.x / n_heads) % tiles_per_clip;
   const int clip = blockIdx.x / (n_heads * tiles_per_clip);
   const int row0 = tile * G;          // clip-relative, multiple of n_tok: frame f of the tile owns tile-local columns [f * n_tok, (f + 1) * n_tok)
+                                      // (kTracks: first token of the tile)
+  const int rows_valid = kTracks ? G * n_rows : 128;   // rows a track box fills; the rest of the 128-row tile is not touched by TMA
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tm_in);
@@ -676,11 +685,20 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
 
   if (warp == 4) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(bar_qk, 32768);
-      ptx::tma_load_3d(sq, &tm_in, bar_qk, head * 64, row0, clip);
-      ptx::tma_load_3d(sk, &tm_in, bar_qk, C + head * 64, row0, clip);
-      ptx::mbar_expect_tx(bar_v, 16384);
-      ptx::tma_load_3d(sv, &tm_in, bar_v, 2 * C + head * 64, row0, clip);
+      if constexpr (kTracks) {
+        const uint32_t box_bytes = (uint32_t)rows_valid * 128u;
+        ptx::mbar_expect_tx(bar_qk, 2 * box_bytes);
+        ptx::tma_load_4d(sq, &tm_in, bar_qk, head * 64, row0, 0, clip);
+        ptx::tma_load_4d(sk, &tm_in, bar_qk, C + head * 64, row0, 0, clip);
+        ptx::mbar_expect_tx(bar_v, box_bytes);
+        ptx::tma_load_4d(sv, &tm_in, bar_v, 2 * C + head * 64, row0, 0, clip);
+      } else {
+        ptx::mbar_expect_tx(bar_qk, 32768);
+        ptx::tma_load_3d(sq, &tm_in, bar_qk, head * 64, row0, clip);
+        ptx::tma_load_3d(sk, &tm_in, bar_qk, C + head * 64, row0, clip);
+        ptx::mbar_expect_tx(bar_v, 16384);
+        ptx::tma_load_3d(sv, &tm_in, bar_v, 2 * C + head * 64, row0, clip);
+      }
       ptx::mbar_wait(bar_qk, 0);
       ptx::tc_fence_after();
       {
@@ -712,15 +730,44 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
     const float scale_log2 = 0.125f * kLog2e;
     // columns of this row's frame, clipped to the keys that exist; rows past the end of the tensor get an empty window
-    const int a = (row / n_tok) * n_tok;
+    int a = (row / n_tok) * n_tok;
     int b = a + n_tok;
     if (b > 128) b = 128;
     if (row0 + b > n_rows) b = n_rows - row0;       // n_rows = rows of one clip
-    const bool live = row0 + row < n_rows && b > a;
+    bool live = row0 + row < n_rows && b > a;
     // warp-uniform range of 32-column chunks that covers the windows of rows [32 warp, 32 warp + 32)
-    const int c_lo = ((32 * warp) / n_tok * n_tok) / 32;
+    int c_lo = ((32 * warp) / n_tok * n_tok) / 32;
     int c_hi = (((32 * warp + 31) / n_tok + 1) * n_tok + 31) / 32;
     if (c_hi > 4) c_hi = 4;
+    uint32_t win[4] = {0u, 0u, 0u, 0u};            // bit i of win[c]: column 32 c + i belongs to this row's softmax window
+    if constexpr (kTracks) {
+      const int trk = row % G;                     // G = tracks per tile = interleave period
+      live = row < rows_valid && row0 + trk < n_tok;
+      c_lo = 0;
+      c_hi = (rows_valid + 31) / 32;
+      uint32_t pat = 0u;                           // ones at the multiples of the period
+      for (int i = 0; i < 32; i += G) pat |= 1u << i;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int start = ((trk - 32 * c) % G + G) % G;            // first i with (32 c + i) = trk (mod G)
+        const int left = rows_valid - 32 * c;                        // columns of this chunk that exist
+        const uint32_t range = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+        win[c] = (pat << start) & range;
+      }
+      // rows the track boxes do not fill hold stale shared memory: V must be zero there (0 * NaN), K / Q garbage only reaches masked entries
+      for (int r = rows_valid + row; r < 128; r += 128) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(sv + (size_t)r * 128 + q * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int lo = a - 32 * c, hi = b - 32 * c;                  // window [lo, hi) in chunk coordinates
+        const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : (hi > 0 ? (1u << hi) - 1u : 0u);
+        const uint32_t upto_lo = lo >= 32 ? 0xffffffffu : (lo > 0 ? (1u << lo) - 1u : 0u);
+        win[c] = upto_hi & ~upto_lo;
+      }
+    }
     ptx::mbar_wait(bar_s, 0);
     ptx::tc_fence_after();
     float mx = -INFINITY;
@@ -730,8 +777,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int j = c * 32 + i;
-        if (j >= a && j < b) mx = fmaxf(mx, __uint_as_float(r[i]));
+        if ((win[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
     }
     const float ms = live ? -mx * scale_log2 : 0.f;
@@ -744,8 +790,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int j = c * 32 + i;
-          const bool in = live && j >= a && j < b;
+          const bool in = live && ((win[c] >> i) & 1u);
           const float e = fast_exp2(fmaf(in ? __uint_as_float(r[i]) : 0.f, scale_log2, ms));
           p[i] = in ? e : 0.f;
           sum += p[i];
@@ -790,7 +835,10 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     ptx::fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 0) {
-      ptx::tma_store_3d(&tm_o, smem, head * 64, row0, clip);   // box of G rows: rows [G, 128) belong to the next tile
+      if constexpr (kTracks)
+        ptx::tma_store_4d(&tm_o, smem, head * 64, row0, 0, clip);   // box {64, P tokens, n_frames, 1}: tokens past the clip's last are dropped
+      else
+        ptx::tma_store_3d(&tm_o, smem, head * 64, row0, clip);   // box of G rows: rows [G, 128) belong to the next tile
       ptx::bulk_commit();
       ptx::bulk_wait_read<0>();
     }
@@ -899,6 +947,24 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
                (long long)n_frames);
     const int Tp = ((int)n_frames + 31) & ~31;
     static const bool legacy = getenv("MANIPOSE_ATTN_MMA_SYNC") != nullptr;   // A/B switch: the mma.sync kernel below
+    static const bool long_only = getenv("MANIPOSE_ATTN_TRACKS_OFF") != nullptr;   // A/B switch: always the T = 243 kernel
+    if (hd == 64 && !legacy && !long_only && n_frames <= 128) {
+      // short clips: P = 128 / T whole tracks per 128-row tile through the block-diagonal kernel (see attn_spatial_tc_kernel<.., true>)
+      const int P = 128 / (int)n_frames < n_tok ? 128 / (int)n_frames : n_tok;
+      const int64_t tiles_per_clip = (n_tok + P - 1) / P;
+      MP_REQUIRE(n_clips * tiles_per_clip * n_heads < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
+      CUtensorMap tin, to;
+      MP_CHECK(get_tmap_track(&tin, qkv, n_clips, n_frames, n_tok, 3 * C, (int)n_frames, dtype, P));
+      MP_CHECK(get_tmap_track(&to, out, n_clips, n_frames, n_tok, C, (int)n_frames, dtype, P));
+      const int smem_tc = 49152 + 64;
+      auto launch_tr = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
+        kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s>>>(tin, to, (int)n_frames, n_tok, C, n_heads, P,
+                                                                                         (int)tiles_per_clip);
+      };
+      if (bf) launch_tr(attn_spatial_tc_kernel<Bf16, true>); else launch_tr(attn_spatial_tc_kernel<Fp16, true>);
+      return check_launch("attn_spatial_tc_kernel<tracks>");
+    }
     if (hd == 64 && !legacy) {
       const int m_tiles = ((int)n_frames + 127) / 128;
       CUtensorMap tq, tkv, to;
@@ -958,7 +1024,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s>>>(tin, to, (int)rows_per_clip, n_tok, C, n_heads, G,
                                                                                        (int)tiles_per_clip);
     };
-    if (bf) launch_tc(attn_spatial_tc_kernel<Bf16>); else launch_tc(attn_spatial_tc_kernel<Fp16>);
+    if (bf) launch_tc(attn_spatial_tc_kernel<Bf16, false>); else launch_tc(attn_spatial_tc_kernel<Fp16, false>);
     return check_launch("attn_spatial_tc_kernel");
   }
   const size_t smem = (size_t)kSWarps * 2 * 3 * 32 * (hd * 2 + 16);

@@ -380,12 +380,13 @@ int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int 
 // 4-D view [clips][frames][tokens][cols] of a 16-bit activation (cols fastest) with a box of `box_frames` frames of ONE token and
 // 64 columns: the frames of one (clip, token) track land as a dense [box_frames x 128 B] swizzled tile, frames past the end of the clip
 // are zero-filled on load and dropped on store.  This is how temporal attention reads [clip, frame, token, C] without any transpose.
-int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type) {
+int get_tmap_track(CUtensorMap* out, const void* ptr, int64_t n_clips, int64_t n_frames, int64_t n_tok, int64_t cols, int box_frames, int type,
+                   int box_tok) {
   EncodeTiledFn fn = encode_fn();
   MP_REQUIRE(fn != nullptr, MP_EDEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)n_tok, (cuuint64_t)n_frames, (cuuint64_t)n_clips};
   cuuint64_t strides[3] = {(cuuint64_t)cols * 2, (cuuint64_t)n_tok * cols * 2, (cuuint64_t)n_frames * n_tok * cols * 2};
-  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_frames, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_tok, (cuuint32_t)box_frames, 1};   // smem rows: token fastest, then frame
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = type == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = fn(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
