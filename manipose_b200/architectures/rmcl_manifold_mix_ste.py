@@ -74,27 +74,15 @@ class RMCLRotMixSTE(MixSTE):
         """Differentiable K heads over the whole batch -> (rot [B,K,L,J,D], logits [B,K,L]).
 
         LN_k(y) = yhat * gamma_k + beta_k shares yhat between the heads, so all K heads are one Linear with folded parameters
-        W_k * gamma_k, W_k beta_k + b_k (autograd unfolds the gradients), zero-padded to 128 outputs for the tensor-core Linear
-        kernel (fp32 output).  The score Linear(J -> 1) is a J-term dot product per frame and head."""
+        W_k * gamma_k, W_k beta_k + b_k, zero-padded to 128 outputs for the tensor-core Linear kernel (fp32 output); the score
+        Linear(J -> 1) is a J-term dot product per frame and head (train_ops.FoldedHeadsFn: forward and hand-unfolded backward)."""
         b, l, j, _ = x.shape
         k, d1, c = self.n_hyp, self.out_dim + 1, self.embed_dim
         feat = self.trunk_autograd(x, b)
         y = T.layer_norm(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps)
         one, zero = torch.ones(c, dtype=torch.float32, device=x.device), torch.zeros(c, dtype=torch.float32, device=x.device)
         yhat = T.layer_norm(y, one, zero, self.head[0].norm.eps, out16=ops.DTYPE_CODE[self.compute_dtype])
-        gam = torch.stack([h.norm.weight for h in self.head])                     # [K, C]
-        bet = torch.stack([h.norm.bias for h in self.head])
-        w = torch.stack([h.prediction_head.weight for h in self.head])            # [K, D+1, C]
-        bias = torch.stack([h.prediction_head.bias for h in self.head])           # [K, D+1]
-        n_pad = (k * d1 + 127) // 128 * 128
-        wf = torch.cat([(w * gam[:, None, :]).reshape(k * d1, c), w.new_zeros(n_pad - k * d1, c)])
-        bf = torch.cat([((w * bet[:, None, :]).sum(-1) + bias).reshape(k * d1), w.new_zeros(n_pad - k * d1)])
-        out = T.linear_f32(yhat, wf, bf)[:, :k * d1].reshape(b, l, j, k, d1)
-        rot = out[..., :self.out_dim].permute(0, 3, 1, 2, 4)
-        # reshape, not [0]: the backward of a view is free, the backward of an index is a zero fill + a copy per head
-        sw = torch.stack([h.score_head.weight.reshape(-1) for h in self.head])    # [K, J]
-        sb = torch.stack([h.score_head.bias.reshape(()) for h in self.head])      # [K]
-        logits = (out[..., self.out_dim] * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
+        rot, logits = T.FoldedHeadsFn.apply(yhat, list(self.head), b, l, j, self.out_dim, self.head[0].norm.weight)
         return rot, logits
 
     def forward(self, x: torch.Tensor):

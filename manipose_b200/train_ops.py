@@ -197,6 +197,98 @@ class LinearF32Fn(torch.autograd.Function):
         return da, dw, db
 
 
+def stacked_grads(params) -> Optional[torch.Tensor]:
+    """One strided view [K, *shape] over the gradients of K same-shaped parameters when they sit at a constant stride in one
+    storage (the flat gradient buffer of ``optim.FlatParameters``: the K hypothesis heads are laid out one after the other), so K
+    per-parameter accumulations become one launch.  None when the layout does not allow it."""
+    grads = [grad_of(p) for p in params]
+    g0 = grads[0]
+    if len(grads) == 1:
+        return g0.unsqueeze(0)
+    base = g0.untyped_storage().data_ptr()
+    if any(g.untyped_storage().data_ptr() != base or not g.is_contiguous() or g.shape != g0.shape for g in grads):
+        return None
+    step = grads[1].storage_offset() - g0.storage_offset()
+    if step <= 0 or any(g.storage_offset() != g0.storage_offset() + i * step for i, g in enumerate(grads)):
+        return None
+    return torch.as_strided(g0, (len(grads),) + tuple(g0.shape), (step,) + tuple(g0.stride()), g0.storage_offset())
+
+
+def accumulate_stacked(params, stacked: torch.Tensor) -> None:
+    """grad(params[k]) += stacked[k] — one launch when the gradients form a strided stack, K otherwise."""
+    view = stacked_grads(params)
+    if view is not None:
+        view.add_(stacked.reshape(view.shape))
+    else:
+        for k, p in enumerate(params):
+            grad_of(p).add_(stacked[k].reshape(p.shape))
+
+
+class FoldedHeadsFn(torch.autograd.Function):
+    """The K hypothesis heads of RMCLRotMixSTE (rmcl_manifold_mix_ste.py:251-298) over a shared normalised input yhat [M, C] (16-bit):
+    LN_k(y) = yhat * gamma_k + beta_k, so all heads are ONE Linear with folded parameters W_k * gamma_k, W_k beta_k + b_k (zero-padded to
+    128 outputs for the tensor-core kernel, fp32 output), followed by the J-term score dot product.  Parameters are read from the
+    module, not passed through autograd: the backward unfolds the gradients itself and accumulates them straight into ``p.grad`` (one
+    launch per parameter KIND when the heads sit at a constant stride in the flat gradient buffer), like the trunk's reverse sweep —
+    the autograd version cost ~75 tiny launches per step (stack / select backward, zero fills, one AccumulateGrad add per tensor)."""
+
+    @staticmethod
+    def forward(ctx, yhat16, heads, b, l, j, out_dim, anchor):   # anchor: a head parameter, only there so that the outputs require grad
+        k, d1, c = len(heads), out_dim + 1, yhat16.shape[1]
+        code = ops.DTYPE_CODE[yhat16.dtype]
+        gam = torch.stack([h.norm.weight.detach() for h in heads])                       # [K, C]
+        bet = torch.stack([h.norm.bias.detach() for h in heads])
+        w = torch.stack([h.prediction_head.weight.detach() for h in heads])              # [K, D+1, C]
+        bias = torch.stack([h.prediction_head.bias.detach() for h in heads])             # [K, D+1]
+        sw = torch.stack([h.score_head.weight.detach().reshape(-1) for h in heads])      # [K, J]
+        sb = torch.stack([h.score_head.bias.detach().reshape(()) for h in heads])        # [K]
+        n_pad = (k * d1 + 127) // 128 * 128
+        wf = torch.zeros((n_pad, c), dtype=torch.float32, device=yhat16.device)
+        wf[:k * d1] = (w * gam[:, None, :]).reshape(k * d1, c)
+        bf = torch.zeros(n_pad, dtype=torch.float32, device=yhat16.device)
+        bf[:k * d1] = ((w * bet[:, None, :]).sum(-1) + bias).reshape(k * d1)
+        w16 = ops.cast16(wf, code)
+        m = yhat16.shape[0]
+        y = torch.zeros((m, n_pad), dtype=torch.float32, device=yhat16.device)
+        ops.linear(yhat16, w16, bf, y, L.MP_EPI_RESIDUAL, resid=y)
+        out = y[:, :k * d1].reshape(b, l, j, k, d1)
+        rot = out[..., :out_dim].permute(0, 3, 1, 2, 4)
+        score_in = out[..., out_dim]                                                     # [B, L, J, K]
+        logits = (score_in * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
+        ctx.heads, ctx.dims = heads, (b, l, j, k, d1, c, n_pad, out_dim)
+        ctx.save_for_backward(yhat16, w16, score_in, gam, bet, w, sw)
+        return rot, logits
+
+    @staticmethod
+    def backward(ctx, d_rot, d_logits):
+        yhat16, w16, score_in, gam, bet, w, sw = ctx.saved_tensors
+        heads = ctx.heads
+        b, l, j, k, d1, c, n_pad, out_dim = ctx.dims
+        code = ops.DTYPE_CODE[yhat16.dtype]
+        m = yhat16.shape[0]
+        dl = d_logits.permute(0, 2, 1)[:, :, None, :]                                    # [B, L, 1, K]
+        dy = torch.zeros((m, n_pad), dtype=torch.float32, device=yhat16.device)
+        d_out = dy[:, :k * d1].view(b, l, j, k, d1)
+        d_out[..., :out_dim] = d_rot.permute(0, 2, 3, 1, 4)
+        d_out[..., out_dim] = dl * sw.t()[None, None]
+        accumulate_stacked([h.score_head.weight for h in heads], (dl * score_in).sum((0, 1)).t())
+        accumulate_stacked([h.score_head.bias for h in heads], d_logits.sum((0, 2)))
+        dy16 = ops.cast16(dy, code)
+        dwf = torch.zeros((n_pad, c), dtype=torch.float32, device=yhat16.device)
+        dbf = torch.zeros(n_pad, dtype=torch.float32, device=yhat16.device)
+        wgrad(dy16, yhat16, dwf, dbf)
+        w_t = torch.empty((c, n_pad), dtype=yhat16.dtype, device=yhat16.device)
+        transpose16(w16, w_t)
+        da = torch.empty((m, c), dtype=yhat16.dtype, device=yhat16.device)
+        dgrad(dy16, w_t, da)
+        dw3, db2 = dwf[:k * d1].view(k, d1, c), dbf[:k * d1].view(k, d1)
+        accumulate_stacked([h.prediction_head.weight for h in heads], dw3 * gam[:, None, :])
+        accumulate_stacked([h.prediction_head.bias for h in heads], db2)
+        accumulate_stacked([h.norm.weight for h in heads], (dw3 * w).sum(1))
+        accumulate_stacked([h.norm.bias for h in heads], (db2[:, :, None] * w).sum(1))
+        return da, None, None, None, None, None, None
+
+
 def layer_norm(x, gamma, beta, eps, out16: Optional[int] = None):
     return LayerNormFn.apply(x, gamma, beta, eps, out16)
 
