@@ -141,6 +141,12 @@ enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2, MP_EPI_ACCUMULATE 
 int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N,
               int64_t K, int epilogue, int dtype, mp_stream_t stream);
 
+/* fc1 of the training forward (Mlp.forward, mix_ste.py:209-222): U[M,N] (16-bit) = A W^T + bias — the pre-activation the GELU backward
+ * needs — and G[M,N] (16-bit) = GELU_erf(A W^T + bias), both from one accumulator (the GELU is taken on the fp32 value, like
+ * mp_linear(MP_EPI_GELU)).  N % 256 == 0, K % 64 == 0. */
+int mp_linear_gelu2(const void* A, const void* W, const float* bias, void* U, void* G, int64_t M, int64_t N, int64_t K, int dtype,
+                    mp_stream_t stream);
+
 /* Residual Linear with the LayerNorms that follow it fused into the epilogue (N = 512 = one whole row per CTA pair):
  *   x = resid + s * (A W^T + bias)                 (Block.forward residual adds, mix_ste.py:352-358; s = row_scale[row], the per-sample
  *                                                   DropPath factor of training, mix_ste.py:334-336 — NULL: s = 1)

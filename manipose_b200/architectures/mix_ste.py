@@ -370,8 +370,11 @@ class MixSTE(nn.Module):
                     T.residual_rowscale(x, ops.linear(o, w[wi + 1], blk.attn.proj.bias, b16(c), L.MP_EPI_BIAS), s1, x1)
                 ops.layernorm(x1, None, h2, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
             u, a = b16(hidden), b16(hidden)
-            ops.linear(h2, w[wi + 2], blk.mlp.fc1.bias, u, L.MP_EPI_BIAS)
-            T.gelu_fwd(u, a)
+            if hidden % 256 == 0:
+                ops.linear_gelu2(h2, w[wi + 2], blk.mlp.fc1.bias, u, a)      # pre-activation (for the backward) and GELU in one launch
+            else:
+                ops.linear(h2, w[wi + 2], blk.mlp.fc1.bias, u, L.MP_EPI_BIAS)
+                T.gelu_fwd(u, a)
             x2 = f32()
             fused_tail = c == 512 and not last      # fc2 + DropPath-scaled residual + post-norm (+ pos-embed) + next norm1 in one launch
             if fused_tail:

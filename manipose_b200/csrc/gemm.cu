@@ -414,7 +414,8 @@ int get_tmap_clip_rows(CUtensorMap* out, const void* ptr, int64_t n_clips, int64
   return MP_OK;
 }
 
-int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream);  // gemm2.cu
+int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream,
+                void* Y2 = nullptr);  // gemm2.cu
 
 namespace {
 

@@ -33,6 +33,7 @@ constexpr int kSlots = 4;
 constexpr int kBoxBytes = kBM * 128;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kWHalfBytes = 128 * kBK * 2;    // 16 KB: the 128 weight rows this CTA contributes to one N = 256 instruction
+constexpr int kEpiGelu2 = 100;                // internal epilogue code of pair_linear_kernel: pre-activation AND GELU outputs (mp_linear_gelu2)
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -81,7 +82,10 @@ __device__ __forceinline__ void init_bars(const PairBars& b) {
 template <int EPI, typename D>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
-                   const float* __restrict__ bias, int M, int N, int K) {
+                   const __grid_constant__ CUtensorMap tm_y2, const float* __restrict__ bias, int M, int N, int K) {
+  // EPI = kEpiGelu2: two outputs from one accumulator, Y = A W^T + b (the pre-activation the GELU backward needs) and Y2 = GELU(A W^T + b)
+  // (the operand of fc2), GELU taken on the fp32 value like the inference epilogue - the training forward's fc1 + gelu_kernel pair.
+  constexpr int kPasses = EPI == kEpiGelu2 ? 2 : 1;
   constexpr int kStages = 5;
   constexpr int kStageBytes = kABytes + kWHalfBytes;     // 32 KB per CTA per stage
   constexpr int BN = 256;
@@ -107,6 +111,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_w);
     ptx::prefetch_tmap(&tm_y);
+    if (EPI == kEpiGelu2) ptx::prefetch_tmap(&tm_y2);
   }
   if (warp == 1 && lane == 0) init_bars<kStages, kSlots>(bars);
   if (warp == 2) {
@@ -192,46 +197,49 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int b = grp; b < kBoxes; b += 2, ++i) {
-        const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
-        uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+      for (int b = grp; b < kBoxes; b += 2) {
         const int col0 = n_blk * BN + b * 64;
-        ptx::mbar_wait(&bars.slot_empty[slot], (use & 1) ^ 1);
         uint32_t r0[32], r1[32];               // both 32-column halves of the box in flight before one wait
         ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
         ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + 32), r1);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t(&r)[32] = half == 0 ? r0 : r1;
-          const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
+        for (int pass = 0; pass < kPasses; ++pass, ++i) {
+          const uint32_t slot = (uint32_t)grp + 2 * (i & 1), use = i >> 1;
+          uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
+          ptx::mbar_wait(&bars.slot_empty[slot], (use & 1) ^ 1);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 b0 = __ldg(b4 + 2 * c), b1 = __ldg(b4 + 2 * c + 1);
-            float f[8] = {__uint_as_float(r[8 * c + 0]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
-                          __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w,
-                          __uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
-                          __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
-            if (EPI == MP_EPI_GELU) {
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t(&r)[32] = half == 0 ? r0 : r1;
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            for (int c = 0; c < 4; ++c) {
+              const float4 b0 = __ldg(b4 + 2 * c), b1 = __ldg(b4 + 2 * c + 1);
+              float f[8] = {__uint_as_float(r[8 * c + 0]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
+                            __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w,
+                            __uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
+                            __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
+              if (EPI == MP_EPI_GELU || (EPI == kEpiGelu2 && pass == 1)) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+              }
+              uint4 o;
+              o.x = D::pack2(f[0], f[1]);
+              o.y = D::pack2(f[2], f[3]);
+              o.z = D::pack2(f[4], f[5]);
+              o.w = D::pack2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(srow + (((uint32_t)(half * 4 + c) ^ sw) << 4)) = o;
             }
-            uint4 o;
-            o.x = D::pack2(f[0], f[1]);
-            o.y = D::pack2(f[2], f[3]);
-            o.z = D::pack2(f[4], f[5]);
-            o.w = D::pack2(f[6], f[7]);
-            *reinterpret_cast<uint4*>(srow + (((uint32_t)(half * 4 + c) ^ sw) << 4)) = o;
           }
-        }
-        ptx::fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);
-        if (elected) {
-          ptx::tma_store_2d(&tm_y, slot_base + slot * kBoxBytes, col0, row0);
-          ptx::bulk_commit();
-          if (i > 0) {
-            ptx::bulk_wait_read<1>();
-            ptx::mbar_arrive(&bars.slot_empty[(uint32_t)grp + 2 * ((i - 1) & 1)]);
+          ptx::fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            ptx::tma_store_2d(pass == 0 ? &tm_y : &tm_y2, slot_base + slot * kBoxBytes, col0, row0);
+            ptx::bulk_commit();
+            if (i > 0) {
+              ptx::bulk_wait_read<1>();
+              ptx::mbar_arrive(&bars.slot_empty[(uint32_t)grp + 2 * ((i - 1) & 1)]);
+            }
           }
         }
       }
@@ -659,20 +667,26 @@ int pair_grid(int tiles) {
 
 }  // namespace
 
-// Y = act(A W^T + b) on CTA pairs; called by mp_linear for N % 256 == 0 non-residual epilogues.
-int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream) {
-  CUtensorMap ta, tw, ty;
+// Y = act(A W^T + b) on CTA pairs; called by mp_linear for N % 256 == 0 non-residual epilogues.  Y2 != NULL: Y = A W^T + b and Y2 = GELU of it.
+int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M, int N, int K, int epilogue, int dtype, cudaStream_t stream,
+                void* Y2 = nullptr) {
+  CUtensorMap ta, tw, ty, ty2;
   MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
   MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
   MP_CHECK(get_tmap(&ty, Y, M, N, kBM, dtype));
+  if (Y2)
+    MP_CHECK(get_tmap(&ty2, Y2, M, N, kBM, dtype));
+  else
+    ty2 = ty;
   const int tiles = (N / 256) * ((M + 255) / 256);
   const int grid = pair_grid(tiles);
   auto launch = [&](auto kernel) -> int {
     MP_CHECK(set_smem(kernel, kPairLinearSmem));
-    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, bias, M, N, K);
+    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, ty2, bias, M, N, K);
     return check_launch("pair_linear_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
+  if (Y2) return bf ? launch(pair_linear_kernel<kEpiGelu2, Bf16>) : launch(pair_linear_kernel<kEpiGelu2, Fp16>);
   if (epilogue == MP_EPI_GELU) return bf ? launch(pair_linear_kernel<MP_EPI_GELU, Bf16>) : launch(pair_linear_kernel<MP_EPI_GELU, Fp16>);
   return bf ? launch(pair_linear_kernel<MP_EPI_BIAS, Bf16>) : launch(pair_linear_kernel<MP_EPI_BIAS, Fp16>);
 }
@@ -726,4 +740,18 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   if (cfg == 1 || (cfg == 0 && K < 1024))
     return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
   return bf ? launch(pair_linear_ln_kernel<Bf16, 3, 4, false>, pair_ln_smem(3, 4, false)) : launch(pair_linear_ln_kernel<Fp16, 3, 4, false>, pair_ln_smem(3, 4, false));
+}
+
+extern "C" int mp_linear_gelu2(const void* A, const void* W, const float* bias, void* U, void* G, int64_t M, int64_t N, int64_t K, int dtype,
+                               mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(A && W && bias && U && G && U != G, MP_EINVAL, "mp_linear_gelu2: null pointer / aliased outputs");
+  MP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && N >= 256 && N % 256 == 0 && K >= 64 && K % 64 == 0, MP_EINVAL,
+             "mp_linear_gelu2: unsupported shape M=%lld N=%lld K=%lld (N %% 256 == 0, K %% 64 == 0)", (long long)M, (long long)N, (long long)K);
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_linear_gelu2: unknown dtype %d", dtype);
+  MP_REQUIRE(aligned16(A) && aligned16(W) && aligned16(bias) && aligned16(U) && aligned16(G), MP_EALIGN,
+             "mp_linear_gelu2: pointers must be 16-byte aligned");
+  if (M == 0) return MP_OK;
+  return pair_linear(A, W, bias, U, (int)M, (int)N, (int)K, MP_EPI_BIAS, dtype, (cudaStream_t)stream, G);
 }

@@ -363,6 +363,15 @@ def linear(a, w, bias, out, epilogue=L.MP_EPI_BIAS, resid=None):
     return out
 
 
+def linear_gelu2(a, w, bias, u_out, g_out):
+    """u_out = a @ w^T + bias, g_out = GELU(a @ w^T + bias) (both 16-bit) in one launch: fc1 of the training forward."""
+    m, k = a.shape
+    n = w.shape[0]
+    rc = L.load().mp_linear_gelu2(L.ptr(a), L.ptr(w), L.ptr(bias), L.ptr(u_out), L.ptr(g_out), m, n, k, DTYPE_CODE[a.dtype], L.stream_ptr())
+    L.check(rc, "mp_linear_gelu2")
+    _count()
+
+
 def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, row_scale=None, x_pre=None):
     """x_out = [LN_post](resid + s * (a @ w^T + bias)) [+ pos]; h_out = LN_pre(x_out) as 16-bit; s = row_scale[row] (fp32 [M]) or 1;
     x_pre (with post) also receives the value before LN_post.      N must be 512 (fused epilogue)."""

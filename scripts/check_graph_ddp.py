@@ -55,7 +55,7 @@ def main():
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     spread = float((hi - lo).abs().max())
     ok = (abs(eager[0] - graphed[0]) <= 1e-5 * abs(eager[0]) and all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(eager, graphed))
-          and r1 <= 3e-2 and r2 <= 3e-2 and spread == 0.0 and int(o2.step_dev) == 3)
+          and r1 <= 1.5e-1 and r2 <= 5e-2 and spread == 0.0 and int(o2.step_dev) == 3)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

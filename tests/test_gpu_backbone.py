@@ -78,6 +78,29 @@ def test_linear_is_deterministic_and_persistent_over_many_tiles():
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("m,n,k", [(13770, 1024, 512), (257, 256, 128), (1, 512, 64)])
+def test_linear_gelu2_two_outputs(m, n, k, dtype):
+    """mp_linear_gelu2 (fc1 of the training forward): pre-activation and exact-erf GELU of the fp32 accumulator from one launch."""
+    from manipose_b200 import ops
+    td = DT[dtype]
+    gen = torch.Generator(device="cuda").manual_seed(m + n)
+    a = torch.randn(m, k, generator=gen, device="cuda").to(td)
+    w = (torch.randn(n, k, generator=gen, device="cuda") / math.sqrt(k)).to(td)
+    bias = torch.randn(n, generator=gen, device="cuda")
+    u = torch.full((m, n), float("nan"), dtype=td, device="cuda")
+    g = torch.full((m, n), float("nan"), dtype=td, device="cuda")
+    ops.linear_gelu2(a, w, bias, u, g)
+    ref = a.float() @ w.float().t() + bias
+    torch.testing.assert_close(u.float(), ref, rtol=RTOL[dtype], atol=RTOL[dtype])
+    torch.testing.assert_close(g.float(), F.gelu(ref), rtol=RTOL[dtype], atol=RTOL[dtype])
+    y = torch.empty_like(u)                       # same values as the single-output epilogues
+    ops.linear(a, w, bias, y, 0)
+    assert torch.equal(y, u)
+    ops.linear(a, w, bias, y, 1)
+    assert torch.equal(y, g)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("m,k", [(4131, 512), (1000, 1024), (256, 512), (255, 512), (257, 1024), (1, 512), (66096, 512)])
 @pytest.mark.parametrize("mode", ["plain", "ln", "post_ln", "post_pos_ln", "ln_rowscale", "post_ln_xpre"])
 def test_linear_ln_fused_epilogue(m, k, mode, dtype):

@@ -290,13 +290,15 @@ def test_captured_train_step_matches_eager_steps():
 
     m1, o1 = make()
     sd0 = {k: v.clone() for k, v in m1.state_dict().items()}
-    eager = []
+    eager, eager_m1 = [], None
     for x, y in zip(xs, ys):
         o1.zero_grad()
         loss = loss_fn(m1(x), y)
         loss.backward()
         o1.step()
         eager.append(float(loss.detach()))
+        if eager_m1 is None:
+            eager_m1 = (o1.exp_avg.clone(), o1.exp_avg_sq.clone())       # moments after ONE step: same parameters, same arithmetic
     m2, o2 = make()
     step = CapturedTrainStep(m2, o2, loss_fn, xs[0], ys[0], warmup=2)
     m2.load_state_dict(sd0)                      # undo the warm-up / capture updates: parameters, moments and the step counter
@@ -304,9 +306,15 @@ def test_captured_train_step_matches_eager_steps():
     o2.exp_avg_sq.zero_()
     o2.step_dev.zero_()
     o2._invalidate_shadows()
-    graphed = [float(step(x, y)) for x, y in zip(xs, ys)]
+    graphed, graph_m1 = [], None
+    for x, y in zip(xs, ys):
+        graphed.append(float(step(x, y)))
+        if graph_m1 is None:
+            graph_m1 = (o2.exp_avg.clone(), o2.exp_avg_sq.clone())
     torch.cuda.synchronize()
     assert int(o2.step_dev) == 3
+    # after the first step the two runs differ only by the order of fp32 atomics: the moments agree tightly
+    assert _rel(graph_m1[0], eager_m1[0]) <= 2e-3 and _rel(graph_m1[1], eager_m1[1]) <= 2e-3
     assert abs(eager[0] - graphed[0]) <= 1e-5 * abs(eager[0])     # same parameters, same arithmetic
     for a, b in zip(eager, graphed):                                 # later steps: noise-signed first Adam updates (see below)
         assert abs(a - b) <= 2e-3 * abs(a), (eager, graphed)
@@ -315,6 +323,6 @@ def test_captured_train_step_matches_eager_steps():
     # (and after the first step those noise-signed updates perturb the next gradients at the 1e-3 level)
     r1, r2 = _rel(o2.exp_avg, o1.exp_avg), _rel(o2.exp_avg_sq, o1.exp_avg_sq)
     print(f"captured vs eager after 3 steps: exp_avg rel-L2 {r1:.2e}, exp_avg_sq rel-L2 {r2:.2e}")
-    assert r1 <= 3e-2 and r2 <= 3e-2
+    assert r1 <= 1.5e-1 and r2 <= 5e-2          # measured 2e-2 .. 4e-2 / 6e-3: winner flips after the noise-signed first updates (chaotic)
     moved = float((m2.rotations_module.STEblocks[0].attn.qkv.weight.detach() - sd0["rotations_module.STEblocks.0.attn.qkv.weight"].cuda()).abs().mean())
     assert 0.5e-4 <= moved <= 4e-4             # three steps of ~lr = 1e-4 each
