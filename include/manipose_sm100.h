@@ -246,9 +246,12 @@ int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float thres
  * sequence length, start frame inside the sequence} (fixed starts :93-104 or the host-sampled random starts :121-127); out2d [n_windows,
  * n_frames, n_joints, in_chans], out3d [n_windows, n_frames, n_joints, 3]; frames past the end of the sequence replicate its last frame
  * (:132-146).  mask (nullable, float [n_windows, n_frames, n_joints]) = the occlusion pattern multiplied into the 2-D input (:166-215); noise
- * (nullable, double [n_windows, n_frames, n_joints, in_chans]) = miss_type "noisy" (:206-210), added in fp64 and rounded once like the reference. */
-int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, const float* mask, const double* noise, float* out2d,
-                      float* out3d, int64_t n_windows, int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream);
+ * (nullable, double [n_windows, n_frames, n_joints, in_chans]) = miss_type "noisy" (:206-210), added in fp64 and rounded once like the reference;
+ * flip (nullable, uint8 [n_windows]) with joint_perm (int32 [n_joints], left <-> right) = the PoseFlip transform of the training loader
+ * (augmentations/transforms.py:8-31), applied to both outputs before noise and mask like the reference (:150-151). */
+int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, const float* mask, const double* noise,
+                      const unsigned char* flip, const int* joint_perm, float* out2d, float* out3d, int64_t n_windows, int64_t n_frames,
+                      int n_joints, int in_chans, mp_stream_t stream);
 
 /* ---- backward (training) entry points -------------------------------------------------------------------------------
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps

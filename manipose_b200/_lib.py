@@ -50,7 +50,7 @@ SIGNATURES = {
     "mp_heads_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, I64, I64, I, I, I, P]),
     "mp_bones_head": (I, [P, P, P, F, P, P, P, P, P, I64, I64, I, I, P, c_size_t, P]),
     "mp_cast_f32_to_16": (I, [P, P, I64, I, P]),
-    "mp_gather_windows": (I, [P, P, P, P, P, P, P, I64, I64, I, I, P]),
+    "mp_gather_windows": (I, [P, P, P, P, P, P, P, P, P, I64, I64, I, I, P]),
     "mp_pck_auc_workspace_bytes": (c_size_t, []),
     "mp_pck_auc": (I, [P, P, I64, F, P, P, c_size_t, P]),
     "mp_p_mpjpe_workspace_bytes": (c_size_t, [I64]),

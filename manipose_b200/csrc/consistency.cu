@@ -376,8 +376,9 @@ __global__ void pck_finalize_kernel(const unsigned long long* __restrict__ count
 // gather: all sequences live concatenated on the device, window w = table[w] = {first frame of its sequence, sequence length, start frame}
 // reads frames start .. start + T - 1 of that sequence, frames past the end replicate the last one (F.pad(mode="replicate"), :132-146).
 __global__ void gather_windows_kernel(const float* __restrict__ frames2d, const float* __restrict__ frames3d, const int64_t* __restrict__ table,
-                                      const float* __restrict__ mask, const double* __restrict__ noise, float* __restrict__ out2d,
-                                      float* __restrict__ out3d, int64_t n_windows, int64_t T, int c2, int c3, int in_chans) {
+                                      const float* __restrict__ mask, const double* __restrict__ noise, const unsigned char* __restrict__ flip,
+                                      const int* __restrict__ perm, float* __restrict__ out2d, float* __restrict__ out3d, int64_t n_windows,
+                                      int64_t T, int c2, int c3, int in_chans) {
   const int per = c2 + c3;                     // floats per frame: 17 * 2 + 17 * 3
   const int64_t total = n_windows * T * per;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -386,15 +387,21 @@ __global__ void gather_windows_kernel(const float* __restrict__ frames2d, const 
     const int64_t off = table[w * 3 + 0], len = table[w * 3 + 1], start = table[w * 3 + 2];
     int64_t f = start + l;
     if (f > len - 1) f = len - 1;
+    // PoseFlip (augmentations/transforms.py:8-31 -> functional.py:7-28) of this window: horizontal coordinate negated, left / right joints swapped
+    const bool flipped = flip != nullptr && flip[w] != 0;
     if (e < c2) {
-      float v = frames2d[(off + f) * c2 + e];
+      const int j = e / in_chans, ch = e - j * in_chans;
+      float v = frames2d[(off + f) * c2 + (flipped ? perm[j] * in_chans + ch : e)];
+      if (flipped && ch == 0) v = -v;
       // miss_type "noisy" (:206-210): `pose_2d += noise` adds a float64 numpy array to a float32 tensor = one rounding of the fp64 sum
       if (noise != nullptr) v = (float)((double)v + noise[wl * c2 + e]);
       // occlusion mask per (frame, joint), broadcast over the coordinates (:212-215)
       if (mask != nullptr) v *= mask[wl * (c2 / in_chans) + e / in_chans];
       out2d[wl * c2 + e] = v;
     } else {
-      out3d[wl * c3 + (e - c2)] = frames3d[(off + f) * c3 + (e - c2)];
+      const int e3 = e - c2, j = e3 / 3, ch = e3 - j * 3;
+      const float v = frames3d[(off + f) * c3 + (flipped ? perm[j] * 3 + ch : e3)];
+      out3d[wl * c3 + e3] = (flipped && ch == 0) ? -v : v;
     }
   }
 }
@@ -476,19 +483,21 @@ int mp_pck_auc(const float* pred, const float* gt, int64_t n_points, float thres
   return check_launch("pck_finalize_kernel");
 }
 
-int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, const float* mask, const double* noise, float* out2d,
-                      float* out3d, int64_t n_windows, int64_t n_frames, int n_joints, int in_chans, mp_stream_t stream) {
+int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_t* table, const float* mask, const double* noise,
+                      const unsigned char* flip, const int* joint_perm, float* out2d, float* out3d, int64_t n_windows, int64_t n_frames,
+                      int n_joints, int in_chans, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(frames2d && frames3d && table && out2d && out3d && n_windows >= 0 && n_frames >= 1 && n_joints >= 1 && in_chans >= 1, MP_EINVAL,
              "mp_gather_windows: bad arguments");
+  MP_REQUIRE(flip == nullptr || joint_perm != nullptr, MP_EINVAL, "mp_gather_windows: flip flags need the joint permutation");
   if (n_windows == 0) return MP_OK;
   const int c2 = n_joints * in_chans, c3 = n_joints * 3;
   const int64_t total = n_windows * n_frames * (c2 + c3);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-  gather_windows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frames2d, frames3d, table, mask, noise, out2d, out3d, n_windows, n_frames,
-                                                                          c2, c3, in_chans);
+  gather_windows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frames2d, frames3d, table, mask, noise, flip, joint_perm, out2d, out3d,
+                                                                          n_windows, n_frames, c2, c3, in_chans);
   return check_launch("gather_windows_kernel");
 }
 

@@ -6,8 +6,11 @@ index -> (sequence, start frame) table the reference builds (generators.py:83-10
 shorter window when ``drop_last`` is False.  The training-time randomness of the generator — random start frames (:121-127), the
 occlusion masks of every ``miss_type`` (:157-205) and the "noisy" input perturbation (:206-210) — is sampled ON THE HOST with the very RNG
 calls the reference makes, item by item in batch order, so a seeded run reproduces a seeded single-worker reference loader bit for bit;
-only the sampled parameters (start frame, mask, noise) travel to the device, where the gather applies them.  The generator's
-``transform`` hook (an arbitrary Python callable) is not carried over."""
+only the sampled parameters (start frame, flip flag, mask, noise) travel to the device, where the gather applies them.  The generator's
+``transform`` hook is carried over for the one transform the drivers install — ``PoseFlip(skeleton, probability)``
+(augmentations/transforms.py:8-31, main_h36m_lifting.py:583-595) — as ``flip_probability``; arbitrary callables are not.
+(The reference's in-place ``pose_flip`` / noise write through to the dataset arrays when those are float32; the device feed leaves the
+uploaded sequences untouched.)"""
 import math
 from typing import List, Sequence, Tuple
 
@@ -29,12 +32,13 @@ class DeviceSequenceWindows:
 
     def __init__(self, poses_3d: List[np.ndarray], poses_2d: List[np.ndarray], seq_len: int = 243, drop_last: bool = True,
                  device: str = "cuda", random_start: bool = False, miss_type: str = "no_miss", miss_rate: float = 0.2,
-                 noise_sigma: float = 5):
+                 noise_sigma: float = 5, flip_probability=None, joints_left=(4, 5, 6, 11, 12, 13), joints_right=(1, 2, 3, 14, 15, 16)):
         assert poses_3d is not None and len(poses_3d) == len(poses_2d)
         self.seq_len = int(seq_len)
         self.drop_last = drop_last
         self.random_start = random_start
         self.miss_type, self.miss_rate, self.noise_sigma = miss_type, miss_rate, noise_sigma
+        self.flip_probability = flip_probability
         lengths = [int(p.shape[0]) for p in poses_3d]
         offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64) if lengths else np.zeros(0, np.int64)
         rows = []
@@ -48,6 +52,10 @@ class DeviceSequenceWindows:
         dev = torch.device(device)
         self.frames_3d = torch.from_numpy(np.concatenate(poses_3d)).float().contiguous().to(dev)
         self.frames_2d = torch.from_numpy(np.concatenate(poses_2d)).float().contiguous().to(dev)
+        perm = list(range(self.n_joints))
+        for a, b in zip(joints_left, joints_right):
+            perm[a], perm[b] = b, a
+        self.joint_perm = torch.tensor(perm, dtype=torch.int32, device=dev)
 
     def __len__(self) -> int:
         return self.table.shape[0]
@@ -93,10 +101,12 @@ class DeviceSequenceWindows:
         dev = self.frames_2d.device
         idx = list(indices)
         rows = self.table[idx].clone()
-        masks, noises = [], []
-        for r in range(rows.shape[0]):                                    # the reference's per-item order: start frame, then mask
+        masks, noises, flips = [], [], []
+        for r in range(rows.shape[0]):                                    # the reference's per-item order: start frame, transform, mask
             if self.random_start:
                 rows[r, 2] = torch.randint(low=0, high=int(rows[r, 1]) - self.seq_len, size=(1,)).item()   # generators.py:121-127
+            if self.flip_probability is not None:
+                flips.append(1 if torch.rand(1).item() <= self.flip_probability else 0)                    # transforms.py:26
             m, nz = self._sample_mask()
             masks.append(m)
             noises.append(nz)
@@ -106,11 +116,12 @@ class DeviceSequenceWindows:
             mask = torch.from_numpy(np.stack([np.ones((t, j)) if m is None else m for m in masks])).float().to(dev)
         if any(nz is not None for nz in noises):
             noise = torch.from_numpy(np.stack([np.zeros((t, j, self.in_chans)) if nz is None else nz for nz in noises])).double().to(dev)
+        flip = torch.tensor(flips, dtype=torch.uint8).to(dev) if flips and any(flips) else None
         rows = rows.contiguous().to(dev)
         out2d = torch.empty((b, t, j, self.in_chans), dtype=torch.float32, device=dev)
         out3d = torch.empty((b, t, j, 3), dtype=torch.float32, device=dev)
-        rc = L.load().mp_gather_windows(L.ptr(self.frames_2d), L.ptr(self.frames_3d), L.ptr(rows), L.ptr(mask), L.ptr(noise), L.ptr(out2d),
-                                        L.ptr(out3d), b, t, j, self.in_chans, L.stream_ptr())
+        rc = L.load().mp_gather_windows(L.ptr(self.frames_2d), L.ptr(self.frames_3d), L.ptr(rows), L.ptr(mask), L.ptr(noise), L.ptr(flip),
+                                        L.ptr(self.joint_perm), L.ptr(out2d), L.ptr(out3d), b, t, j, self.in_chans, L.stream_ptr())
         L.check(rc, "mp_gather_windows")
         ops._count()
         return out2d, out3d

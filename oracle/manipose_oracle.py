@@ -537,10 +537,11 @@ def occlusion_mask(seq_len: int, n_joints: int, in_chans: int, miss_type: str, m
 
 
 def sequence_windows(poses_3d, poses_2d, seq_len: int, drop_last: bool = True, random_start: bool = False, miss_type: str = "no_miss",
-                     miss_rate: float = 0.2, noise_sigma: float = 5, indices=None):
+                     miss_rate: float = 0.2, noise_sigma: float = 5, indices=None, flip_probability=None):
     """hpe/mh_so3_hpe/data/generators.py:83-219 (PoseSequenceGenerator): the items (pose_2d [L,J,C] * mask, pose_3d [L,J,3]) for ``indices``
     (default: the whole dataset in order); the last, shorter window of a sequence is replicate-padded when drop_last is False; random
-    starts come from torch's global RNG, masks / noise from numpy's, per item in that order like the reference."""
+    starts come from torch's global RNG, the PoseFlip transform's coin (augmentations/transforms.py:21-31, ``flip_probability``) from
+    torch's, masks / noise from numpy's, per item in that order like the reference."""
     table = []
     for s, p3 in enumerate(poses_3d):
         n = p3.shape[0]
@@ -555,6 +556,8 @@ def sequence_windows(poses_3d, poses_2d, seq_len: int, drop_last: bool = True, r
             start = torch.randint(low=0, high=n - seq_len, size=(1,)).item()
         idx = torch.clamp(torch.arange(start, start + seq_len), max=n - 1)          # replicate padding = clamp to the last frame
         p2, p3 = t2[idx], t3[idx]
+        if flip_probability is not None and torch.rand(1).item() <= flip_probability:
+            p2, p3 = pose_flip(p2), pose_flip(p3)
         mask, noise = occlusion_mask(seq_len, p2.shape[1], p2.shape[2], miss_type, miss_rate, noise_sigma)
         if noise is not None:
             p2 = p2.double() + torch.from_numpy(noise)   # `pose_2d += noise` with a float64 ndarray re-binds pose_2d to the float64 sum; callers `.float()` it

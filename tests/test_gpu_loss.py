@@ -303,3 +303,30 @@ def test_device_sequence_windows_randomised_vs_oracle(miss_type, random_start):
     assert torch.equal(b3.cpu(), torch.stack([it[1] for it in items]))
     if miss_type not in ("noisy",):
         assert miss_type == "all" or float((b2 == 0).float().mean()) > 0.01           # something was actually occluded
+
+
+@pytest.mark.parametrize("miss_type", ["no_miss", "random", "noisy"])
+def test_device_sequence_windows_pose_flip_vs_oracle(miss_type):
+    """The drivers' training loader (random starts + PoseFlip(0.5) + occlusion) through the device gather, same seeds as the oracle."""
+    import numpy as np
+    from manipose_b200.data import DeviceSequenceWindows
+    rng = np.random.default_rng(5)
+    lens = [60, 300, 45, 100]
+    p3 = [rng.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    p2 = [rng.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    order = [3, 0, 9, 1, 5, 8, 2, 4, 6, 7]
+    w = DeviceSequenceWindows(p3, p2, seq_len=27, drop_last=True, random_start=True, miss_type=miss_type, miss_rate=0.3, noise_sigma=0.05,
+                              flip_probability=0.5)
+    torch.manual_seed(12)
+    np.random.seed(12)
+    items = O.sequence_windows(p3, p2, 27, True, True, miss_type, 0.3, 0.05, indices=order, flip_probability=0.5)
+    torch.manual_seed(12)
+    np.random.seed(12)
+    b2, b3 = w.batch(order)
+    assert torch.equal(b2.cpu(), torch.stack([it[0].float() for it in items]))
+    assert torch.equal(b3.cpu(), torch.stack([it[1] for it in items]))
+    torch.manual_seed(12)
+    np.random.seed(12)
+    plain = O.sequence_windows(p3, p2, 27, True, True, "no_miss", 0.3, 0.05, indices=order, flip_probability=-1.0)   # same draws, never flips
+    n_flipped = sum(int(not torch.equal(a[1], b[1])) for a, b in zip(items, plain))
+    assert 0 < n_flipped < len(order)

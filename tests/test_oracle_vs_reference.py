@@ -328,3 +328,33 @@ def test_randomised_sequence_windows_match_reference_generator(ref, miss_type):
         got = O.sequence_windows(p3, p2, 20, True, random_start, miss_type, 0.3, 0.05, indices=order)
         for (a2, a3), (r2, r3) in zip(got, want):
             assert torch.equal(a2, r2) and torch.equal(a3, r3)
+
+
+@pytest.mark.parametrize("miss_type", ["no_miss", "random", "all"])
+def test_sequence_windows_with_pose_flip_transform_match_reference(ref, miss_type):
+    """The training loader of the drivers (main_h36m_lifting.py:583-595): random starts + PoseFlip(probability 0.5) + occlusion pattern."""
+    import numpy as np
+    from mh_so3_hpe.data.generators import PoseSequenceGenerator
+    from mh_so3_hpe.augmentations.transforms import PoseFlip
+    rng = np.random.default_rng(4)
+    lens = [60, 45, 100]
+    p3 = [rng.standard_normal((n, 17, 3)) for n in lens]            # float64: the reference's in-place flip then cannot leak into the dataset
+    p2 = [rng.standard_normal((n, 17, 2)) for n in lens]
+    order = [4, 0, 7, 2, 5, 1, 3, 6]
+    gen = PoseSequenceGenerator(p3, p2, None, seq_len=20, random_start=True, drop_last=True, miss_type=miss_type, miss_rate=0.3,
+                                transform=PoseFlip(skeleton=ref.make_skeleton(), probability=0.5))
+    torch.manual_seed(6)
+    np.random.seed(6)
+    want = [gen[i] for i in order]
+    torch.manual_seed(6)
+    np.random.seed(6)
+    got = O.sequence_windows(p3, p2, 20, True, True, miss_type, 0.3, 5, indices=order, flip_probability=0.5)
+    flipped = 0
+    for (a2, a3), (r2, r3) in zip(got, want):
+        assert torch.equal(a2, r2) and torch.equal(a3, r3)
+    # some, not all, items were flipped (the coin is shared between the two poses of an item)
+    torch.manual_seed(6)
+    np.random.seed(6)
+    plain = O.sequence_windows(p3, p2, 20, True, True, "no_miss", 0.3, 5, indices=order, flip_probability=-1.0)   # same draws, never flips
+    flipped = sum(int(not torch.equal(a[1], b[1])) for a, b in zip(got, plain))
+    assert 0 < flipped < len(order)
