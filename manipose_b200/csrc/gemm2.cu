@@ -519,7 +519,10 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             ptx::mbar_arrive(&bars.slot_empty[slot]);
           }
         }
-        if (last_pass == 0 && j == 7) {          // no later pass reads TMEM
+        // no later pass reads TMEM.  (Handing half 0 back already after box 3 of THIS pass - the same call as in passes B / C -
+        // raised 'misaligned address' on the device and was not chased further: without LayerNorms the model only uses the
+        // K = 1024 single-accumulation variant, where there is one hand-back per tile anyway.)
+        if (last_pass == 0 && j == 7) {
           release_half(0);
           if constexpr (kSplit) release_half(1);
         }
