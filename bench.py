@@ -459,6 +459,91 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- decoder alone (BASELINE config 2)
+def run_decoder(args):
+    """BASELINE config 2: 6D -> SO(3) + forward kinematics + hypothesis softmax on N = 824 x 5 x 243 = 1,001,160 synthetic
+    poses, fp32, one B200.  HBM roofline: 620 algorithmic bytes per pose (408 rot6d + 4 logit in, 204 pose + 4 score out)."""
+    import torch
+    import manipose_b200  # noqa: F401
+    from manipose_b200 import ops
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    nc, k, t = 824, K, T
+    n = nc * k * t
+    gen = torch.Generator().manual_seed(1234)
+    rot_host = torch.randn(n, J, 6, generator=gen).pin_memory()
+    bones_host = (0.1 + 0.4 * torch.rand(nc, 16, generator=gen)).pin_memory()
+    logits_host = torch.randn(nc, k, t, generator=gen).pin_memory()
+    rot, bones, logits = rot_host.to(dev), bones_host.to(dev), logits_host.to(dev)
+    poses_host, scores_host = torch.empty((n, J, 3)).pin_memory(), torch.empty((nc, k, t)).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > the 126 MB L2, written between timed launches
+    exact = not args.fast_decoder
+
+    def step_resident():
+        return ops.decoder_fwd(rot, bones, None, logits, nc, k, t, 6, exact)
+
+    def step_e2e():
+        p, sc = ops.decoder_fwd(rot_host.to(dev, non_blocking=True), bones_host.to(dev, non_blocking=True), None,
+                                logits_host.to(dev, non_blocking=True), nc, k, t, 6, exact)
+        poses_host.copy_(p, non_blocking=True)
+        scores_host.copy_(sc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    steps = max(args.steps, 2000)               # ~0.5 s of launches so that the clock sampler sees the region
+    launches0 = ops.LAUNCHES
+    ms_kernel = 0.0
+    with ClockSampler(0) as clocks:
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_resident()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_kernel += e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - launches0
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step_e2e()
+    ms_e2e = (time.perf_counter() - t0) * 1000.0 / 5
+    ms = ms_kernel / steps
+    peaks = measured_peaks()
+    gbs = 620.0 * n / (ms / 1000.0) / 1e9
+    cpu = None
+    if not args.skip_cpu_baseline:
+        from oracle import manipose_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        nb = 103                                  # 103 clips x 5 x 243 = 125,145 poses (1/8 of the workload)
+        rc, bc, zero = rot_host[:nb * k * t].clone(), bones_host[:nb].clone().unsqueeze(-1), torch.zeros(nb * k * t, 3)
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.pose_decoder(rc, bc, zero)
+            best = min(best, time.perf_counter() - t0)
+        cpu = {"value": nb * k * t / best, "unit": "poses/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"best of 3 passes over {nb * k * t} poses (1/8 of the workload), fp32, torch CPU (oracle.pose_decoder)"}
+    line = {"metric": "decoded_poses_per_sec_1M", "value": n / (ms / 1000.0), "unit": "poses/s", "n_gpus": 1, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"manifold decoder alone (6D -> SO(3) Gram-Schmidt, T-pose from bone lengths, forward kinematics, softmax over K) "
+                                   f"on {n} poses = {nc} clips x {k} x {t} = BASELINE config 2",
+                       "mode": "exact (bit-identical to the correctly rounded oracle)" if exact else "fast (one-MUFU reciprocals / rsqrt)",
+                       "l2": "256 MB written between timed launches (L2 flush)"},
+            "e2e": {"value": n / (ms_e2e / 1000.0), "unit": "poses/s", "h2d_bytes_per_step": (rot_host.numel() + bones_host.numel() + logits_host.numel()) * 4,
+                    "d2h_bytes_per_step": (poses_host.numel() + scores_host.numel()) * 4, "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "decoder_fwd_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_pose": 620,
+                         "peak_source": "measured (STREAM-style copy)" if peaks["src"] == "measured" else "fallback"},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -469,7 +554,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit operand format of the backbone")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: do not time the CPU oracle")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="3: T=243 inference (headline); 4: T=27 training step")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4],
+                    help="3: T=243 inference (headline); 4: T=27 training step; 2: manifold decoder alone on 1M poses")
+    ap.add_argument("--fast-decoder", action="store_true", help="config 2: the FAST decoder mode instead of the bit-exact one")
     ap.add_argument("--drop-path", type=float, default=0.1, help="config 4: stochastic depth rate (drivers use 0.1)")
     ap.add_argument("--frames", type=int, default=27, help="config 4: frames per clip (27 = 3DHP shape of BASELINE config 4; 243 = H36M)")
     ap.add_argument("--cuda-graph", action="store_true", help="config 4: capture the whole training step (NCCL all-reduces included) in a CUDA graph (default)")
@@ -480,6 +567,8 @@ def main():
         run_reference(args)
     elif args.config == 4:
         run_train(args)
+    elif args.config == 2:
+        run_decoder(args)
     else:
         run_gpu(args)
 
