@@ -60,39 +60,35 @@ class DeviceSequenceWindows:
     def __len__(self) -> int:
         return self.table.shape[0]
 
+    _LEFT_ARM_RIGHT_LEG = (1, 2, 3, 11, 12, 13)      # generators.py:184
+    _RIGHT_LEG = (1, 2, 3)                           # generators.py:196
+
     def _sample_mask(self):
-        """generators.py:157-210 for one item: -> (mask [L, J] float64 or None, noise [L, J, C] float64 or None), same numpy RNG calls."""
-        shape = (self.seq_len, self.n_joints)
-        if self.miss_type == "all":
-            miss_type = np.random.choice(list(self.possible_miss_types_rates.keys()))
-            miss_rate = self.possible_miss_types_rates[miss_type]
-        else:
-            miss_type, miss_rate = self.miss_type, self.miss_rate
-        if miss_type == "no_miss":
+        """One item's occlusion pattern (generators.py:157-210), drawn from numpy's global RNG with the reference's calls in the reference's
+        order: -> (keep [L, J] float64 or None when nothing is occluded, noise [L, J, C] float64 or None)."""
+        n_frames, n_joints = self.seq_len, self.n_joints
+        kind, rate = self.miss_type, self.miss_rate
+        if kind == "all":                                                  # one pattern per item, with that pattern's own rate
+            kind = np.random.choice(list(self.possible_miss_types_rates.keys()))
+            rate = self.possible_miss_types_rates[kind]
+        if kind == "no_miss":
             return None, None
-        if miss_type == "random":
-            mask = np.zeros(shape)
-            u = np.random.uniform(0.0, 1.0, size=shape)
-            mask[u > miss_rate] = 1.0
-            return mask, None
-        if miss_type == "random_left_arm_right_leg":
-            mask = np.ones(shape)
-            rand = np.random.choice(self.seq_len, size=math.floor(miss_rate * self.seq_len), replace=False).tolist()
-            for i in [1, 2, 3, 11, 12, 13]:
-                mask[rand, i] = 0.0
-            return mask, None
-        if miss_type in ("structured_joint", "structured_frame"):
-            mask = np.ones(shape)
-            occl_len = int(self.seq_len * miss_rate)
-            rand = np.random.choice(self.seq_len - occl_len, size=1, replace=False)
-            if miss_type == "structured_joint":
-                mask[rand[0]: rand[0] + occl_len, [1, 2, 3]] = 0.0
-            else:
-                mask[rand[0]: rand[0] + occl_len] = 0.0
-            return mask, None
-        if miss_type == "noisy":
-            return None, np.random.normal(0, self.noise_sigma, size=shape + (self.in_chans,))
-        raise ValueError(f"Unexpected miss_type: {self.miss_type}")
+        if kind == "noisy":
+            return None, np.random.normal(0, self.noise_sigma, size=(n_frames, n_joints, self.in_chans))
+        keep = np.ones((n_frames, n_joints))
+        if kind == "random":                                               # independent (frame, joint) drop-outs
+            keep = (np.random.uniform(0.0, 1.0, size=(n_frames, n_joints)) > rate).astype(np.float64)
+        elif kind == "random_left_arm_right_leg":                          # two limbs vanish in a random subset of the frames
+            frames = np.random.choice(n_frames, size=math.floor(rate * n_frames), replace=False)
+            keep[np.ix_(frames, self._LEFT_ARM_RIGHT_LEG)] = 0.0
+        elif kind in ("structured_joint", "structured_frame"):             # one contiguous span: the right leg only, or every joint
+            span = int(n_frames * rate)
+            first = int(np.random.choice(n_frames - span, size=1, replace=False)[0])
+            cols = list(self._RIGHT_LEG) if kind == "structured_joint" else slice(None)
+            keep[first:first + span, cols] = 0.0
+        else:
+            raise ValueError(f"Unexpected miss_type: {self.miss_type}")
+        return keep, None
 
     def batch(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (pose_2d [B, L, J, in_chans], pose_3d [B, L, J, 3]) on the device, equal to stacking the reference generator's items
