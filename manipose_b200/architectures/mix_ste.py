@@ -324,7 +324,8 @@ class MixSTE(nn.Module):
                 continue
             key = (mode, str(device), tuple((k, i) for _, _, k, i in items))
             if key not in cache:                 # built eagerly during warm-up, so a CUDA-graph capture of the step only sees device tensors
-                cache.clear() if len(cache) > 8 else None
+                if len(cache) > 8:
+                    cache.clear()
                 cache[key] = (torch.tensor([k for _, _, k, _ in items], dtype=torch.float32, device=device).view(-1, 1, 1, 1),
                               torch.tensor([i for _, _, _, i in items], dtype=torch.float32, device=device).view(-1, 1, 1, 1))
             keep_t, inv_t = cache[key]

@@ -77,7 +77,7 @@ class RMCLRotMixSTE(MixSTE):
         W_k * gamma_k, W_k beta_k + b_k, zero-padded to 128 outputs for the tensor-core Linear kernel (fp32 output); the score
         Linear(J -> 1) is a J-term dot product per frame and head (train_ops.FoldedHeadsFn: forward and hand-unfolded backward)."""
         b, l, j, _ = x.shape
-        k, d1, c = self.n_hyp, self.out_dim + 1, self.embed_dim
+        c = self.embed_dim
         feat = self.trunk_autograd(x, b)
         y = T.layer_norm(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps)
         one, zero = torch.ones(c, dtype=torch.float32, device=x.device), torch.zeros(c, dtype=torch.float32, device=x.device)

@@ -256,12 +256,12 @@ class FoldedHeadsFn(torch.autograd.Function):
         score_in = out[..., out_dim]                                                     # [B, L, J, K]
         logits = (score_in * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
         ctx.heads, ctx.dims = heads, (b, l, j, k, d1, c, n_pad, out_dim)
-        ctx.save_for_backward(yhat16, w16, score_in, gam, bet, w, sw)
+        ctx.save_for_backward(yhat16, w16, score_in, gam, w, sw)
         return rot, logits
 
     @staticmethod
     def backward(ctx, d_rot, d_logits):
-        yhat16, w16, score_in, gam, bet, w, sw = ctx.saved_tensors
+        yhat16, w16, score_in, gam, w, sw = ctx.saved_tensors
         heads = ctx.heads
         b, l, j, k, d1, c, n_pad, out_dim = ctx.dims
         code = ops.DTYPE_CODE[yhat16.dtype]
