@@ -141,3 +141,71 @@ def test_fused_adam_checkpoints_interoperate_with_torch_adam():
     opt_ref2 = torch.optim.Adam(ref.parameters(), lr=1.0)
     opt_ref2.load_state_dict(back)          # and the reference optimizer accepts what we write
     assert opt_ref2.param_groups[0]["lr"] == 4e-5
+
+
+def test_droppath_scales_follow_timm_semantics_on_cpu():
+    """Host logic of the training forward (no kernel involved): the batched DropPath factors are 0 or 1 / keep per SAMPLE of each block's
+    batch (timm DropPath under mix_ste.py:334-336): a (clip, frame) in spatial blocks, a (clip, token) track in temporal blocks; block 0
+    (Identity drop_path) gets none; eval mode gets none."""
+    import manipose_b200 as mb
+    from manipose_b200 import _lib as L
+    torch.manual_seed(0)
+    m = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=2, drop_path_rate=0.5).rotations_module
+    blocks = m._block_list()
+    n_clips, T_, J_ = 64, 9, 17
+    m.train()
+    scales = m._droppath_scales(blocks, n_clips, torch.device("cpu"))
+    assert len(scales) == len(blocks) and scales[0] == [None, None] and scales[1] == [None, None]     # dpr[0] = 0 for the first STE / TTE block
+    seen = 0
+    for (blk, _, mode, _), (s1, s2) in zip(blocks, scales):
+        if s1 is None:
+            continue
+        keep = 1.0 - blk.drop_path.drop_prob
+        for s in (s1, s2):
+            seen += 1
+            assert s.shape == (n_clips * T_ * J_,) and s.is_contiguous()
+            v = s.view(n_clips, T_, J_)
+            assert bool(((v == 0) | ((v - 1.0 / keep).abs() < 1e-6)).all())
+            if mode == L.MP_ATTN_SPATIAL:
+                assert torch.equal(v, v[:, :, :1].expand_as(v))          # one coin per (clip, frame)
+            else:
+                assert torch.equal(v, v[:, :1, :].expand_as(v))          # one coin per (clip, token) track
+        assert not torch.equal(s1, s2)                                    # the two residual branches draw independently
+    assert seen == 2 * (len(blocks) - 2)
+    last = scales[-1][0].view(n_clips, T_, J_)
+    assert 0.3 <= float((last > 0).float().mean()) <= 0.7                 # keep = 0.5 for the deepest block
+    m.eval()
+    assert all(s == [None, None] for s in m._droppath_scales(blocks, n_clips, torch.device("cpu")))
+
+
+def test_stacked_gradient_views_on_cpu():
+    """train_ops.stacked_grads / accumulate_stacked (gradient accumulation of the K hypothesis heads): one strided view over K
+    same-shaped gradients that sit at a constant stride of the flat gradient buffer, per-parameter adds otherwise."""
+    from manipose_b200 import train_ops as T
+    from manipose_b200.optim import FlatParameters
+
+    class Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.norm = torch.nn.LayerNorm(8)
+            self.lin = torch.nn.Linear(8, 3)
+
+    heads = torch.nn.ModuleList([Head() for _ in range(4)])
+    flat = FlatParameters(heads)
+    ws = [h.lin.weight for h in heads]
+    view = T.stacked_grads(ws)
+    assert view is not None and view.shape == (4, 3, 8)
+    add = torch.arange(4 * 3 * 8, dtype=torch.float32).view(4, 3, 8)
+    T.accumulate_stacked(ws, add)
+    T.accumulate_stacked(ws, add)
+    for k, w in enumerate(ws):
+        assert torch.equal(w.grad, 2 * add[k]) and w.grad.data_ptr() == flat.flat_grad.data_ptr() + 4 * flat.offsets[id(w)][0]
+    assert float(flat.flat_grad.sum()) == float(2 * add.sum())            # nothing was written outside the four weights
+    # scalars / biases and the fallback (gradients that do not form a strided stack)
+    bs = [h.lin.bias for h in heads]
+    T.accumulate_stacked(bs, torch.ones(4, 3))
+    assert all(torch.equal(b.grad, torch.ones(3)) for b in bs)
+    loose = [torch.nn.Parameter(torch.zeros(5)) for _ in range(3)]
+    assert T.stacked_grads(loose) is None
+    T.accumulate_stacked(loose, torch.ones(3, 5))
+    assert all(torch.equal(p.grad, torch.ones(5)) for p in loose)
