@@ -196,14 +196,76 @@ def procrustes_golden(ref):
     torch.save(out, os.path.join(OUT, "procrustes.pt"))
 
 
+def _load_reference_evaluate():
+    """hpe/eval_utils.py imports omegaconf only for a type hint (:8): stub it, then load the module from the reference tree."""
+    import importlib.util
+    import types
+    from oracle.ref_loader import REFERENCE_ROOT
+    if "omegaconf" not in sys.modules:
+        om = types.ModuleType("omegaconf")
+        om.DictConfig = dict
+        sys.modules["omegaconf"] = om
+    spec = importlib.util.spec_from_file_location("_ref_eval_utils", os.path.join(REFERENCE_ROOT, "hpe", "eval_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def evaluate_golden(ref):
+    """The whole of ``evaluate`` (hpe/eval_utils.py:16-203), unmodified, on synthetic weights loaded into the reference model."""
+    import types
+    from oracle import manipose_oracle as O
+    ev = _load_reference_evaluate()
+    sk = ref.make_skeleton()
+    t, k, seed = 9, 3, 5
+    m = ref.architectures.RMCLManifoldMixSTE(sk, num_frame=t, n_hyp=k, drop_path_rate=0.1).eval()
+    m.load_state_dict(O.make_state_dict(num_frame=t, n_hyp=k, seed=seed))
+    g = torch.Generator().manual_seed(8)
+    batches = [(0.3 * torch.randn(b, t, 17, 2, generator=g), 0.3 * torch.randn(b, t, 17, 3, generator=g)) for b in (2, 3)]
+    out = {"T": t, "K": k, "seed": seed, "batches": batches}
+    for tta in (False, True):
+        cfg = types.SimpleNamespace(train=types.SimpleNamespace(tta=tta))
+        res = ev.evaluate(m, [(x.clone(), y.clone()) for x, y in batches], "cpu", cfg, sk, return_hyps=False, compute_oracle=True)
+        out[f"tta{int(tta)}"] = {"predictions": [p.clone() for p in res[0]], "performance": float(res[2]), "oracle_mpjpe": float(res[3]),
+                                 "psoracle_mpjpe": float(res[4]), "oracle_preds": [p.clone() for p in res[5]]}
+    torch.save(out, os.path.join(OUT, "evaluate.pt"))
+
+
+def windows_golden(ref):
+    """Items of the reference ``PoseSequenceGenerator`` (hpe/mh_so3_hpe/data/generators.py:45-219) under fixed torch / numpy seeds: plain
+    windows with the replicate-padded tail, random starts, every occlusion pattern, the noisy input and the PoseFlip transform."""
+    import numpy as np
+    from mh_so3_hpe.data.generators import PoseSequenceGenerator
+    from mh_so3_hpe.augmentations.transforms import PoseFlip
+    rng = np.random.default_rng(3)
+    lens = [60, 45, 100, 7]
+    p3 = [rng.standard_normal((n, 17, 3)) for n in lens]     # float64: the reference's in-place noise / flip cannot leak into the arrays
+    p2 = [rng.standard_normal((n, 17, 2)) for n in lens]
+    out = {"p3": p3, "p2": p2, "seq_len": 20, "cases": []}
+    cases = [dict(drop_last=False, random_start=False, miss_type="no_miss", flip=None, order=list(range(12)))]
+    for mt in ("random", "random_left_arm_right_leg", "structured_joint", "structured_frame", "noisy", "all"):
+        cases.append(dict(drop_last=True, random_start=True, miss_type=mt, flip=None, order=[4, 0, 7, 2, 5, 1]))
+    cases.append(dict(drop_last=True, random_start=True, miss_type="random", flip=0.5, order=[4, 0, 7, 2, 5, 1, 3, 6]))
+    for i, c in enumerate(cases):
+        tr = PoseFlip(skeleton=ref.make_skeleton(), probability=c["flip"]) if c["flip"] is not None else None
+        seqs3 = p3[:3] if c["random_start"] else p3           # random starts need sequences longer than one window
+        seqs2 = p2[:3] if c["random_start"] else p2
+        gen = PoseSequenceGenerator(seqs3, seqs2, None, seq_len=20, random_start=c["random_start"], drop_last=c["drop_last"],
+                                    miss_type=c["miss_type"], miss_rate=0.3, noise_sigma=0.05, transform=tr)
+        torch.manual_seed(100 + i)
+        np.random.seed(100 + i)
+        items = [gen[j] for j in c["order"]]
+        out["cases"].append({**c, "n_seqs": len(seqs3), "seed": 100 + i, "length": len(gen),
+                             "items": [(torch.as_tensor(a).clone(), torch.as_tensor(b).clone()) for a, b in items]})
+    torch.save(out, os.path.join(OUT, "windows.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
-    decoder_golden(ref)
-    loss_golden(ref)
-    forward_golden(ref)
-    consistency_golden(ref)
-    tta_golden(ref)
-    procrustes_golden(ref)
+    makers = {"decoder": decoder_golden, "loss": loss_golden, "forward": forward_golden, "consistency": consistency_golden, "tta": tta_golden,
+              "procrustes": procrustes_golden, "evaluate": evaluate_golden, "windows": windows_golden}
+    for name in (sys.argv[1:] or list(makers)):          # python scripts/make_goldens.py [fixture ...]
+        makers[name](ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

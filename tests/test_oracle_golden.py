@@ -159,3 +159,35 @@ def test_p_mpjpe_oracle_matches_frozen_reference_outputs():
             assert O.keypoint_3d_auc(e["pred"], e["gt"]) == e["auc"]
             continue
         assert abs(O.p_mpjpe(e["pred"], e["target"]) - e["p_mpjpe"]) <= 1e-6 * e["p_mpjpe"], name
+
+
+def test_evaluate_oracle_matches_frozen_reference_outputs():
+    """the whole of ``evaluate`` (hpe/eval_utils.py:16-203) frozen from the unmodified reference — predictions, MPJPE, the
+    oracle and per-sample-oracle figures (with the reference's normalisation quirk), with and without flip TTA."""
+    g = torch.load(os.path.join(GOLD, "evaluate.pt"), weights_only=False)
+    sd = O.make_state_dict(num_frame=g["T"], n_hyp=g["K"], seed=g["seed"])
+    for tta in (False, True):
+        e = g[f"tta{int(tta)}"]
+        with torch.no_grad():
+            got = O.evaluate(g["batches"], sd, tta, return_hyps=False, compute_oracle=True)
+        for a, b in zip(got[0] + got[5], e["predictions"] + e["oracle_preds"]):
+            torch.testing.assert_close(a, b, rtol=0, atol=2e-3)          # mm
+        assert abs(float(got[2]) - e["performance"]) <= 1e-3
+        assert abs(float(got[3]) - e["oracle_mpjpe"]) <= 1e-3 and abs(float(got[4]) - e["psoracle_mpjpe"]) <= 1e-3
+
+
+def test_sequence_windows_oracle_matches_frozen_reference_items():
+    """items of the reference PoseSequenceGenerator under fixed torch / numpy seeds — replicate-padded tail, random starts,
+    every occlusion pattern, the noisy input (float64 like the reference returns it) and the PoseFlip transform — bit for bit."""
+    import numpy as np
+    g = torch.load(os.path.join(GOLD, "windows.pt"), weights_only=False)
+    assert len(g["cases"]) == 8
+    for c in g["cases"]:
+        p3, p2 = g["p3"][:c["n_seqs"]], g["p2"][:c["n_seqs"]]
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        items = O.sequence_windows(p3, p2, g["seq_len"], c["drop_last"], c["random_start"], c["miss_type"], 0.3, 0.05, indices=c["order"],
+                                   flip_probability=c["flip"])
+        assert len(O.sequence_windows(p3, p2, g["seq_len"], c["drop_last"])) == c["length"]
+        for (a2, a3), (r2, r3) in zip(items, c["items"]):
+            assert a2.dtype == r2.dtype and torch.equal(a2, r2) and torch.equal(a3, r3), c["miss_type"]
