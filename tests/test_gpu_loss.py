@@ -330,3 +330,24 @@ def test_device_sequence_windows_pose_flip_vs_oracle(miss_type):
     plain = O.sequence_windows(p3, p2, 27, True, True, "no_miss", 0.3, 0.05, indices=order, flip_probability=-1.0)   # same draws, never flips
     n_flipped = sum(int(not torch.equal(a[1], b[1])) for a, b in zip(items, plain))
     assert 0 < n_flipped < len(order)
+
+
+def test_device_sequence_windows_vs_frozen_reference_items():
+    """The device feed against items frozen from the UNMODIFIED reference generator (tests/golden/windows.pt): same seeds, same items
+    (float32 view of them: the reference hands float64 sequences / noisy items to a caller that calls .float())."""
+    import numpy as np
+    from manipose_b200.data import DeviceSequenceWindows
+    g = torch.load(os.path.join(GOLD, "windows.pt"), weights_only=False)
+    for c in g["cases"]:
+        p3, p2 = g["p3"][:c["n_seqs"]], g["p2"][:c["n_seqs"]]
+        w = DeviceSequenceWindows(p3, p2, seq_len=g["seq_len"], drop_last=c["drop_last"], random_start=c["random_start"],
+                                  miss_type=c["miss_type"], miss_rate=0.3, noise_sigma=0.05, flip_probability=c["flip"])
+        assert len(w) == c["length"]
+        torch.manual_seed(c["seed"])
+        np.random.seed(c["seed"])
+        b2, b3 = w.batch(c["order"])
+        want2 = torch.stack([it[0].double() for it in c["items"]])
+        want3 = torch.stack([it[1].float() for it in c["items"]])
+        assert torch.equal(b3.cpu(), want3), c["miss_type"]
+        # "noisy": the reference adds float64 noise to the float32 sequence and returns float64; the device rounds that sum once
+        assert torch.equal(b2.cpu(), want2.float()), c["miss_type"]
