@@ -111,3 +111,23 @@ def evaluate(model, loader, device, config, skeleton, return_hyps: bool = False,
     oracle_total = torch.stack(oracle_sums).sum() / (n * l) * 1000
     ps_total = torch.stack(ps_sums).sum() / (n * l) * 1000
     return all_pred, all_target, performance, oracle_total, ps_total, all_oracle
+
+
+def stack_lifted(predictions) -> "np.ndarray":
+    """Post-processing of ``lift_action`` (hpe/eval_utils.py:241-251): the per-batch predictions of ``evaluate`` (millimetres) -> one numpy
+    array in metres, frames flattened: [N*L, J, 3] for aggregated poses, [N*L, K, J, 4] (pose + score) for ``return_hyps``."""
+    import numpy as np
+    out = torch.cat(list(predictions), dim=0).detach().cpu().numpy()
+    if out.ndim == 4:
+        n, l, j, _ = out.shape
+        return out.reshape(n * l, j, 3) / 1000
+    out = np.transpose(out, (0, 2, 1, 3, 4))
+    n, l, _, j, _ = out.shape
+    out = out.reshape(n * l, -1, j, 4)
+    out[..., :-1] /= 1000
+    return out
+
+
+def lift_action(data_loader, model, device, config, skeleton, return_hyps):
+    """Drop-in for ``lift_action`` of hpe/eval_utils.py:226-251 (what hpe/viz.py calls): ``evaluate`` + ``stack_lifted``."""
+    return stack_lifted(evaluate(model=model, loader=data_loader, device=device, config=config, skeleton=skeleton, return_hyps=return_hyps)[0])

@@ -358,3 +358,24 @@ def test_sequence_windows_with_pose_flip_transform_match_reference(ref, miss_typ
     plain = O.sequence_windows(p3, p2, 20, True, True, "no_miss", 0.3, 5, indices=order, flip_probability=-1.0)   # same draws, never flips
     flipped = sum(int(not torch.equal(a[1], b[1])) for a, b in zip(got, plain))
     assert 0 < flipped < len(order)
+
+
+@pytest.mark.parametrize("return_hyps", [False, True])
+def test_lift_action_postprocessing_matches_reference(ref, return_hyps):
+    """``lift_action`` (hpe/eval_utils.py:226-251) = evaluate + a reshape to [N*L, ...] in metres: the product's ``stack_lifted`` applied to
+    the oracle's evaluate output equals the unmodified reference's lift_action on the same model (CPU, no kernel involved)."""
+    import types
+    import numpy as np
+    from manipose_b200.evaluation import stack_lifted
+    ev = _load_reference_evaluate()
+    sk = ref.make_skeleton()
+    torch.manual_seed(11)
+    m = ref.architectures.RMCLManifoldMixSTE(sk, num_frame=9, n_hyp=3, drop_path_rate=0.1).eval()
+    _perturb(m)
+    g = torch.Generator().manual_seed(8)
+    batches = [(0.3 * torch.randn(b, 9, 17, 2, generator=g), 0.3 * torch.randn(b, 9, 17, 3, generator=g)) for b in (2, 3)]
+    cfg = types.SimpleNamespace(train=types.SimpleNamespace(tta=False))
+    want = ev.lift_action([(x.clone(), y.clone()) for x, y in batches], m, "cpu", cfg, sk, return_hyps)
+    got = stack_lifted(O.evaluate(batches, m.state_dict(), False, return_hyps=return_hyps)[0])
+    assert got.shape == want.shape == ((45, 3, 17, 4) if return_hyps else (45, 17, 3))
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
