@@ -295,9 +295,11 @@ int mp_residual_rowscale(const float* x, const void* y, const float* s, float* o
 int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
 /* torch.optim.Adam step (L2-style weight_decay, bias correction, step counted from 1) over one flat fp32 buffer; grad is read as
  * grad * grad_scale (1 / world_size after a SUM all-reduce).  step_dev (device int64, may be NULL): when given, the step count is read
- * from it (value before this step) and incremented afterwards, so a captured CUDA graph of the step stays correct on replay. */
+ * from it (value before this step) and incremented afterwards, so a captured CUDA graph of the step stays correct on replay.
+ * lr_dev (device float, may be NULL): when given, the learning rate is read from it instead of `lr`, so an lr scheduler
+ * (CosineAnnealingLR / ReduceLROnPlateau, main_h36m_lifting.py:763-771) keeps working across replays of a captured step. */
 int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int64_t step, int64_t* step_dev, float grad_scale, mp_stream_t stream);
+                 float weight_decay, int64_t step, int64_t* step_dev, const float* lr_dev, float grad_scale, mp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -69,7 +69,7 @@ SIGNATURES = {
     "mp_small_wgrad": (I, [P, P, P, P, I64, I, I, P]),
     "mp_residual_rowscale": (I, [P, P, P, P, I64, I, I, P]),
     "mp_cast_rowscale": (I, [P, P, P, I64, I, I, P]),
-    "mp_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, I64, P, F, P]),
+    "mp_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, I64, P, P, F, P]),
 }
 
 _lib = None

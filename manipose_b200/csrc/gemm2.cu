@@ -263,6 +263,236 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
 }
 
+// ===================================================================================== Y = act(A W^T + b), A-stationary (K = 512)
+// pair_linear_kernel pulls A through L2 once per 256-column block of N (6 times for qkv, 4 for fc1) and W once per 256-row tile:
+// 64 bytes per SM-clock at the MMA rate, which is what the L2 slices deliver chip-wide (~6300 B/clk), so those launches run at the
+// L2 roof (qkv: 12 TB/s of operand traffic under ncu), not at the tensor roof.  With K = 512 the whole A tile of a CTA is
+// 128 x 512 x 2 B = 128 KB: this variant keeps it RESIDENT in shared memory for all the N blocks of a 256-row tile (8 k-block
+// buffers with their own full / empty barriers; a buffer is handed back during the last N block and refilled with the next tile's
+// k-block right away) and streams only W (4 x 16 KB stages).  Operand traffic per token drops from N/256 + N/256 KB to 1 + N/256 KB
+// (qkv 12 -> 7, fc1 8 -> 5).  What is left of shared memory holds ONE 16 KB output slot per epilogue group, so the epilogue computes a
+// box into registers first and only then waits for its slot.
+constexpr int kAsKB = 8;                                   // k-blocks of the resident A tile (K = 512)
+constexpr int kAsWStages = 4;
+constexpr int kAsSlots = 2;
+constexpr int kAsSmem = 1024 + kAsKB * kABytes + kAsWStages * kWHalfBytes + kAsSlots * kBoxBytes + 512;
+static_assert(kAsSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+
+template <int EPI, typename D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+                      const float* __restrict__ bias, int M, int N) {
+  constexpr int BN = 256;
+  constexpr int kBoxes = 4;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* w_base = a_base + kAsKB * kABytes;
+  uint8_t* slot_base = w_base + kAsWStages * kWHalfBytes;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(slot_base + kAsSlots * kBoxBytes);   // [stages] leader: W halves of both CTAs landed
+  uint64_t* w_empty = w_full + kAsWStages;                 // [stages] each CTA: stage consumed (multicast commit)
+  uint64_t* a_full = w_empty + kAsWStages;                 // [8]      leader: A k-block of both CTAs landed
+  uint64_t* a_empty = a_full + kAsKB;                      // [8]      each CTA: last N block has consumed the k-block (multicast commit)
+  uint64_t* tmem_full = a_empty + kAsKB;                   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                    // [2]      leader: drained by the 16 epilogue warps of the pair
+  uint64_t* slot_empty = tmem_empty + 2;                   // [2]      the group's TMA store has read its slot
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(slot_empty + kAsSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_blocks = N / BN;
+  const int m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kAsWStages; ++s) {
+      ptx::mbar_init(&w_full[s], 1);
+      ptx::mbar_init(&w_empty[s], 1);
+    }
+    for (int s = 0; s < kAsKB; ++s) {
+      ptx::mbar_init(&a_full[s], 1);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * kEpiWarps);
+    }
+    for (int s = 0; s < kAsSlots; ++s) ptx::mbar_init(&slot_empty[s], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== W producer (both CTAs: 128 of the 256 weight rows each) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs) {
+        for (int n_blk = 0; n_blk < n_blocks; ++n_blk) {
+          const int row_w = n_blk * BN + (int)rank * 128;
+          for (int kb = 0; kb < kAsKB; ++kb) {
+            ptx::mbar_wait(&w_empty[stage], phase ^ 1);
+            const uint32_t full_leader = ptx::mapa_shared(smem_u32(&w_full[stage]), 0);
+            if (leader) ptx::mbar_expect_tx(&w_full[stage], 2 * kWHalfBytes);   // the peer's load completes on this barrier too
+            ptx::tma_load_2d_pair(w_base + stage * kWHalfBytes, &tm_w, full_leader, kb * kBK, row_w);
+            if (++stage == kAsWStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ===================== A producer (both CTAs: own 128 rows, once per 256-row tile) =====================
+      uint32_t a_phase = 0;
+      for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs, a_phase ^= 1) {
+        const int row_a = m_pair * 2 * kBM + (int)rank * kBM;
+        for (int kb = 0; kb < kAsKB; ++kb) {
+          ptx::mbar_wait(&a_empty[kb], a_phase ^ 1);       // the previous tile's last N block is done with this buffer
+          const uint32_t full_leader = ptx::mapa_shared(smem_u32(&a_full[kb]), 0);
+          if (leader) ptx::mbar_expect_tx(&a_full[kb], 2 * kABytes);
+          ptx::tma_load_2d_pair(a_base + kb * kABytes, &tm_a, full_leader, kb * kBK, row_a);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer (leader CTA) =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_16(2 * kBM, BN, D::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs, a_phase ^= 1) {
+        for (int n_blk = 0; n_blk < n_blocks; ++n_blk) {
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < kAsKB; ++kb) {
+            if (n_blk == 0) ptx::mbar_wait(&a_full[kb], a_phase);
+            ptx::mbar_wait(&w_full[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t da = ptx::umma_desc_sw128(smem_u32(a_base + kb * kABytes));
+            const uint64_t db = ptx::umma_desc_sw128(smem_u32(w_base + stage * kWHalfBytes));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              ptx::umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(&w_empty[stage]);
+            if (n_blk == n_blocks - 1) ptx::umma_commit_pair(&a_empty[kb]);
+            if (kb == kAsKB - 1) ptx::umma_commit_pair(&tmem_full[acc]);
+            if (++stage == kAsWStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const bool elected = ((warp - 4) & 3) == 0 && lane == 0;
+    const int row = 32 * q + lane;
+    const uint32_t sw = (uint32_t)(row & 7);
+    uint8_t* srow = slot_base + grp * kBoxBytes + row * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t use = 0;                            // boxes this group has stored so far
+    for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs) {
+      const int row0 = m_pair * 2 * kBM + (int)rank * kBM;
+      for (int n_blk = 0; n_blk < n_blocks; ++n_blk) {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+        for (int b = grp; b < kBoxes; b += 2, ++use) {
+          const int col0 = n_blk * BN + b * 64;
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 64 + 32), r1);
+          ptx::tmem_ld_wait();
+          if (b + 2 >= kBoxes) {                 // last TMEM read of this accumulator by this warp: hand it back before the math
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          }
+          uint4 o[8];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t(&r)[32] = half == 0 ? r0 : r1;
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + half * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 b0 = __ldg(b4 + 2 * c), b1 = __ldg(b4 + 2 * c + 1);
+              float f[8] = {__uint_as_float(r[8 * c + 0]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
+                            __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w,
+                            __uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
+                            __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
+              if (EPI == MP_EPI_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+              }
+              o[half * 4 + c].x = D::pack2(f[0], f[1]);
+              o[half * 4 + c].y = D::pack2(f[2], f[3]);
+              o[half * 4 + c].z = D::pack2(f[4], f[5]);
+              o[half * 4 + c].w = D::pack2(f[6], f[7]);
+            }
+          }
+          if (use > 0) {                         // the group's previous store must have read the slot (its read overlapped the math above)
+            if (elected) {
+              ptx::bulk_wait_read<0>();
+              ptx::mbar_arrive(&slot_empty[grp]);
+            }
+            ptx::mbar_wait(&slot_empty[grp], (use - 1) & 1);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(srow + (((uint32_t)c ^ sw) << 4)) = o[c];
+          ptx::fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 128);
+          if (elected) {
+            ptx::tma_store_2d(&tm_y, slot_base + grp * kBoxBytes, col0, row0);
+            ptx::bulk_commit();
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    if (elected) ptx::bulk_wait<0>();
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();     // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ===================================================================================== x = resid + A W^T + b (+ LayerNorms), N = 512
 struct LnArgs {
   const float* bias;
@@ -681,6 +911,20 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
     MP_CHECK(get_tmap(&ty2, Y2, M, N, kBM, dtype));
   else
     ty2 = ty;
+  const bool bf = dtype == MP_DTYPE_BF16;
+  // K = 512 and at least two 256-column blocks: keep the A tile resident (pair_linear_as_kernel); MANIPOSE_PAIR_AS=0 forces the
+  // streaming kernel (A/B measurements)
+  static const int as_cfg = getenv("MANIPOSE_PAIR_AS") ? atoi(getenv("MANIPOSE_PAIR_AS")) : 1;
+  if (as_cfg != 0 && !Y2 && K == kAsKB * kBK && N >= 512) {
+    const int grid = pair_grid((M + 255) / 256);
+    auto launch_as = [&](auto kernel) -> int {
+      MP_CHECK(set_smem(kernel, kAsSmem));
+      kernel<<<grid, kThreads, kAsSmem, stream>>>(ta, tw, ty, bias, M, N);
+      return check_launch("pair_linear_as_kernel");
+    };
+    if (epilogue == MP_EPI_GELU) return bf ? launch_as(pair_linear_as_kernel<MP_EPI_GELU, Bf16>) : launch_as(pair_linear_as_kernel<MP_EPI_GELU, Fp16>);
+    return bf ? launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Bf16>) : launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Fp16>);
+  }
   const int tiles = (N / 256) * ((M + 255) / 256);
   const int grid = pair_grid(tiles);
   auto launch = [&](auto kernel) -> int {
@@ -688,7 +932,6 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
     kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, ty2, bias, M, N, K);
     return check_launch("pair_linear_kernel");
   };
-  const bool bf = dtype == MP_DTYPE_BF16;
   if (Y2) return bf ? launch(pair_linear_kernel<kEpiGelu2, Bf16>) : launch(pair_linear_kernel<kEpiGelu2, Fp16>);
   if (epilogue == MP_EPI_GELU) return bf ? launch(pair_linear_kernel<MP_EPI_GELU, Bf16>) : launch(pair_linear_kernel<MP_EPI_GELU, Fp16>);
   return bf ? launch(pair_linear_kernel<MP_EPI_BIAS, Bf16>) : launch(pair_linear_kernel<MP_EPI_BIAS, Fp16>);

@@ -606,7 +606,9 @@ cast_rowscale_kernel(const float* __restrict__ g, const float* __restrict__ s, u
 // captured CUDA graph of the training step advances the bias correction on every replay.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
-                                                   float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev) {
+                                                   float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev,
+                                                   const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = *lr_dev;      // the learning rate of a captured step lives on the device too (schedulers change it between replays)
   if (step_dev) {
     const double t = (double)(*step_dev + 1);
     bc1 = (float)(1.0 - pow((double)beta1, t));
@@ -847,7 +849,7 @@ int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens
 }
 
 int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int64_t step, int64_t* step_dev, float grad_scale, mp_stream_t stream) {
+                 float weight_decay, int64_t step, int64_t* step_dev, const float* lr_dev, float grad_scale, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), MP_EINVAL,
@@ -859,7 +861,7 @@ int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
     bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   }
   adam_kernel<<<stream_grid(n, 1024), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                                       bc1, bc2_sqrt, grad_scale, step_dev);
+                                                                       bc1, bc2_sqrt, grad_scale, step_dev, lr_dev);
   MP_CHECK(check_launch("adam_kernel"));
   if (step_dev) {
     adam_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);

@@ -90,7 +90,9 @@ class GradientReducer:
 
     def bucket_ready(self, i: int) -> None:
         if self._done[i]:
-            raise RuntimeError(f"gradient bucket {i} reduced twice in one step")
+            raise RuntimeError(f"gradient bucket {i} reduced twice in one step: two backward passes before one optimizer.step() "
+                               "(gradient accumulation) are not supported with overlap_reduce=True; build FusedAdam(..., "
+                               "overlap_reduce=False) to reduce once, in step()")
         self._done[i] = True
         if self.world_size > 1:
             a, b = self.buckets[i]
@@ -143,6 +145,10 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count = 0
         # the authoritative step count lives on the device so that a CUDA-graph capture of the training step advances it on replay
         self.step_dev = torch.zeros((), dtype=torch.int64, device=self.flat.flat_param.device)
+        # ... and so does the learning rate: a scheduler writes param_groups[0]["lr"] on the host, ``_sync_lr`` copies it over
+        # before the kernel (eager) / before each replay (``CapturedTrainStep``), the kernel reads the device value
+        self.lr_dev = torch.full((), float(lr), dtype=torch.float32, device=self.flat.flat_param.device)
+        self._lr_on_dev = float(lr)
         buckets, index = block_buckets(self.flat, module)
         self.reducer = GradientReducer(self.flat.flat_grad, buckets, group)
         self._bucket_of_block = index
@@ -150,6 +156,38 @@ class FusedAdam(torch.optim.Optimizer):
             rot = getattr(module, "rotations_module", None)
             if rot is not None:
                 rot._on_block_grads = self._block_done
+        self.broadcast_state()
+
+    def broadcast_state(self, src: int = 0) -> None:
+        """Data parallel: every replica starts from rank ``src``'s parameters, moments and step count (what torch DDP does at
+        construction; the reference's nn.DataParallel has a single copy).  Called from the constructor and ``load_state_dict``, so
+        the replicas agree even when the ranks were seeded differently or only one of them read the checkpoint."""
+        if self.reducer.world_size <= 1:
+            return
+        group = self.reducer.group
+        src_global = dist.get_global_rank(group, src) if group is not None else src
+        for t in (self.flat.flat_param, self.exp_avg, self.exp_avg_sq):
+            dist.broadcast(t, src=src_global, group=group)
+        step = self.step_dev.reshape(1).clone()
+        dist.broadcast(step, src=src_global, group=group)
+        self.step_dev.copy_(step[0])
+        self.step_count = int(step[0].item())
+        self._invalidate_shadows()
+
+    def _sync_lr(self) -> None:
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_dev:
+            self.lr_dev.fill_(lr)
+            self._lr_on_dev = lr
+
+    def _check_homes(self) -> None:
+        """The parameters must still be views of the flat buffer: model.to() / .half() / load_state_dict(assign=True) after the
+        optimizer was built re-home them, and the kernel would then update a buffer the model no longer reads."""
+        base, nbytes = self.flat.flat_param.data_ptr(), self.flat.flat_param.numel() * 4
+        for p in (self.flat.params[0], self.flat.params[-1]):
+            if not (base <= p.data_ptr() < base + nbytes):
+                raise RuntimeError("FusedAdam: the model's parameters no longer live in the optimizer's flat buffer (model.to() / .half() / "
+                                   "load_state_dict(assign=True) after FusedAdam(model)?); build the optimizer after moving the model")
 
     def _block_done(self, blk: nn.Module) -> None:
         i = self._bucket_of_block.get(id(blk))
@@ -163,11 +201,14 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         from . import train_ops as T
         loss = closure() if closure is not None else None
+        self._check_homes()
         scale = self.reducer.finish()
         g = self.param_groups[0]
         self.step_count += 1
+        if not (self.lr_dev.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self._sync_lr()                      # under capture the fill would be baked into the graph: CapturedTrainStep syncs before replays
         T.adam_step(self.flat.flat_param, self.flat.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
-                    g["eps"], g["weight_decay"], self.step_count, scale, step_dev=self.step_dev)
+                    g["eps"], g["weight_decay"], self.step_count, scale, step_dev=self.step_dev, lr_dev=self.lr_dev)
         self._invalidate_shadows()
         return loss
 
@@ -208,6 +249,7 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError(f"per-parameter step counts differ ({sorted(steps)}); one fused step count is kept")
         self.step_count = steps.pop() if steps else 0
         self.step_dev.fill_(self.step_count)
+        self.broadcast_state()
 
     def _invalidate_shadows(self) -> None:
         """The kernel wrote the parameters behind autograd's back (their ``_version`` did not move): drop the cached 16-bit weight
@@ -235,6 +277,12 @@ class CapturedTrainStep:
         self.x, self.y = x.clone(), y.clone()
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         distributed = optimizer.reducer.world_size > 1
+        # The warm-up steps are real optimizer steps on the example batch.  They must not leak into training (a resumed checkpoint
+        # would otherwise have been trained `warmup` extra steps on one batch): parameters, moments, the step count and the RNG
+        # stream (stochastic depth) are put back once the graph exists.
+        o = optimizer
+        saved = (o.flat.flat_param.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.step_dev.clone(), o.step_count,
+                 torch.cuda.get_rng_state(self.x.device))
         for _ in range(max(1, warmup)):          # allocates shadows, tensor maps, workspaces (and NCCL communicators) outside the capture
             self._step()
         torch.cuda.synchronize()
@@ -243,6 +291,14 @@ class CapturedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if distributed else "global"):
             self._step()
+        torch.cuda.synchronize()
+        o.flat.flat_param.copy_(saved[0])
+        o.exp_avg.copy_(saved[1])
+        o.exp_avg_sq.copy_(saved[2])
+        o.step_dev.copy_(saved[3])
+        o.step_count = saved[4]
+        torch.cuda.set_rng_state(saved[5], self.x.device)
+        o._invalidate_shadows()
 
     def _step(self) -> None:
         self.optimizer.zero_grad()
@@ -265,5 +321,7 @@ class CapturedTrainStep:
             raise RuntimeError("CapturedTrainStep was closed")
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        self.optimizer._sync_lr()                # a scheduler may have moved param_groups[0]["lr"] since the last replay
         self.graph.replay()
+        self.optimizer.step_count += 1           # host mirror of step_dev (state_dict reads the device value)
         return self.loss

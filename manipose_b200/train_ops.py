@@ -96,10 +96,12 @@ def cast_rowscale(g, s, out16):
     return out16
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
-    """``step`` counts from 1 on the host; with ``step_dev`` (int64 device scalar) the count lives on the device instead."""
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None, lr_dev=None):
+    """``step`` counts from 1 on the host; with ``step_dev`` (int64 device scalar) the count lives on the device instead, and with
+    ``lr_dev`` (fp32 device scalar) so does the learning rate."""
     rc = L.load().mp_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), float(lr), float(beta1),
-                               float(beta2), float(eps), float(weight_decay), int(step), L.ptr(step_dev), float(grad_scale), L.stream_ptr())
+                               float(beta2), float(eps), float(weight_decay), int(step), L.ptr(step_dev), L.ptr(lr_dev), float(grad_scale),
+                               L.stream_ptr())
     L.check(rc, "mp_adam_step")
     ops._count(1 if step_dev is None else 2)
 
@@ -256,12 +258,12 @@ class FoldedHeadsFn(torch.autograd.Function):
         score_in = out[..., out_dim]                                                     # [B, L, J, K]
         logits = (score_in * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
         ctx.heads, ctx.dims = heads, (b, l, j, k, d1, c, n_pad, out_dim)
-        ctx.save_for_backward(yhat16, w16, score_in, gam, w, sw)
+        ctx.save_for_backward(yhat16, w16, score_in, gam, bet, w, sw)
         return rot, logits
 
     @staticmethod
     def backward(ctx, d_rot, d_logits):
-        yhat16, w16, score_in, gam, w, sw = ctx.saved_tensors
+        yhat16, w16, score_in, gam, bet, w, sw = ctx.saved_tensors
         heads = ctx.heads
         b, l, j, k, d1, c, n_pad, out_dim = ctx.dims
         code = ops.DTYPE_CODE[yhat16.dtype]
@@ -282,7 +284,8 @@ class FoldedHeadsFn(torch.autograd.Function):
         da = torch.empty((m, c), dtype=yhat16.dtype, device=yhat16.device)
         dgrad(dy16, w_t, da)
         dw3, db2 = dwf[:k * d1].view(k, d1, c), dbf[:k * d1].view(k, d1)
-        accumulate_stacked([h.prediction_head.weight for h in heads], dw3 * gam[:, None, :])
+        # Wf = W * gamma and bf = W beta + b both depend on W: dL/dW[k,d,c] = dWf[k,d,c] gamma[k,c] + dbf[k,d] beta[k,c]
+        accumulate_stacked([h.prediction_head.weight for h in heads], dw3 * gam[:, None, :] + db2[:, :, None] * bet[:, None, :])
         accumulate_stacked([h.prediction_head.bias for h in heads], db2)
         accumulate_stacked([h.norm.weight for h in heads], (dw3 * w).sum(1))
         accumulate_stacked([h.norm.bias for h in heads], (db2[:, :, None] * w).sum(1))
