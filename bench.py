@@ -4,13 +4,19 @@
 
 A step is one pass of the lifting hot path (RMCLManifoldMixSTE.forward: MixSTE backbone -> K=5 hypothesis heads ->
 manifold decoder + hypothesis softmax) over one batch of B synthetic clips of T=243 frames, random-init weights
-(hpe/conf/config.yaml defaults, seed 42).  BASELINE config 3 (B=1024, bf16 backbone, fp32 decoder).  Multi-GPU:
-one process per GPU (torchrun), clips sharded, NO collective on the data path; weak scaling (B clips per GPU).
+(hpe/conf/config.yaml defaults, seed 42).  BASELINE config 3 (B=1024 clips IN TOTAL, bf16 backbone, fp32 decoder).  Multi-GPU:
+one process per GPU (torchrun), the 1024 clips sharded 1024/N per GPU ("scaling": "strong", as BASELINE config 3 /
+SURVEY.md §8d state it), NO collective on the data path; the weak-scaled figure (1024 clips per GPU) rides along as `weak`.
 
 The one JSON line carries: value (device-resident inputs), e2e (pinned-host inputs, H2D + forward + D2H of poses/scores
-inside the timed region), roofline for the dominant kernel (the tcgen05 GEMM, sampled with CUDA events inside the timed
-region) and cpu_baseline (the reference algorithm — oracle/manipose_oracle.py, a PyTorch-CPU restatement pinned to the
-reference — timed on the host cores on a bounded sample).  --impl reference times that CPU path alone.
+inside the timed region), roofline for the dominant kernel family (sampled with CUDA events inside the timed region),
+cpu_baseline (the reference algorithm — oracle/manipose_oracle.py, a PyTorch-CPU restatement pinned to the reference —
+timed on the host cores on a bounded sample), and, measured in the same run:
+  parity   |dMPJPE| (mm) and score-arg-max agreement of the TIMED dtype against the fp32 oracle on BASELINE config 1 inputs
+  fp16     the same workload with fp16 tensor-core operands (value, e2e, parity): the dtype that meets the 0.05 mm gate
+  train    BASELINE config 4 (T=27 training step, captured graph, data parallel with the NCCL gradient all-reduce)
+  decoder  BASELINE config 2 (manifold decoder alone on 1,001,160 poses; N = 1 only)
+--impl reference times the CPU path alone.  --config 4 / --config 2 print the training / decoder line alone.
 """
 import argparse
 import json
@@ -192,10 +198,15 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = clips * T * args.steps / dt
     sample = f"{clips} clips x {T} frames per step (of the {args.clips}-clip workload), fp32, torch CPU, {torch.get_num_threads()} threads"
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    strong = args.scaling == "strong"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1000.0, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1000.0, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ManiPose H36M lifting forward, T={T}, K={K}, J={J}, {args.clips} clips/GPU (BASELINE config 3)",
+            "config": {"workload": f"ManiPose H36M lifting forward (RMCLManifoldMixSTE, config.yaml defaults), T={T}, K={K}, J={J}, "
+                                   f"{args.clips} clips " + (f"in total, sharded {max(1, args.clips // max(world, 1))} per GPU" if strong else "per GPU")
+                                   + f" = BASELINE config 3; this CPU arm times a {clips}-clip SAMPLE of that workload per step on the host cores "
+                                   f"of rank 0 (frames/s of the reference algorithm does not depend on the batch size)",
                        "reference_arm": "reference algorithm restated in oracle/manipose_oracle.py (pinned to the unmodified reference; "
                                         "the reference itself is Python and needs timm/mup/.cuda() shims, SURVEY.md §8c)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
@@ -204,37 +215,22 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
+def _dist_env():
     import torch
     import torch.distributed as dist
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
 
-    from manipose_b200 import _build
-    if rank == 0 and not os.path.exists(os.path.join(ROOT, "manipose_b200", "libmanipose_sm100.so")):
-        _build.build(verbose=False)
-    if world > 1:
-        dist.barrier()
-    import manipose_b200 as mb
-    from manipose_b200 import ops
 
-    torch.manual_seed(42)
-    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=T, n_hyp=K, drop_path_rate=0.1)
-    model = model.to(dev).eval().set_compute_dtype(args.dtype)
-    if args.micro_batch_clips:
-        model.rotations_module.micro_batch_tokens = args.micro_batch_clips * T * J
-        model.segments_module.micro_batch_tokens = args.micro_batch_clips * T * J
-    B = args.clips
-    gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = (0.3 * torch.randn(B, T, J, 2, generator=gen)).pin_memory()
-    x_dev = x_host.to(dev)
-    out_host = (torch.empty((B, K, T, J, 3), dtype=torch.float32).pin_memory(), torch.empty((B, K, T, 1), dtype=torch.float32).pin_memory())
+def _make_timers(world, dev):
+    import torch
+    import torch.distributed as dist
 
     def sync_all():
         if world > 1:
@@ -242,6 +238,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """K calls bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -254,9 +251,58 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    return sync_all, timed
+
+
+def parity_config1(model, dtype, ref_cache):
+    """BASELINE config 1 inputs (4 clips x T=243, x = 0.3 randn seed 1234) through the benchmarked model at `dtype` and through the
+    fp32 CPU oracle on the same weights: |d MPJPE| in mm of the weighted-average aggregate (worst of three synthetic targets, the
+    construction of tests/test_gpu_backbone.py::test_end_to_end_mpjpe_gate_config1) and agreement of the score arg-max."""
+    import torch
+    from oracle import manipose_oracle as O
+    x = 0.3 * torch.randn(4, T, J, 2, generator=torch.Generator().manual_seed(1234))
+    if "ref" not in ref_cache:
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            pr, sr = O.rmcl_forward(x, sd)
+        ref_cache["ref"] = (O.aggregate(pr, sr, "weighted_ave"), sr)
+    agg_ref, scores_ref = ref_cache["ref"]
+    was = model.rotations_module.compute_dtype
+    model.set_compute_dtype(dtype)
+    with torch.no_grad():
+        poses, scores = model(x.to(next(model.parameters()).device))
+        agg = model.aggregate(poses, scores, "weighted_ave").cpu()
+    model.set_compute_dtype(was)
+    mm = lambda p, y: float((p - y).norm(dim=-1).mean() * 1000.0)
+    worst = 0.0
+    for seed in (5, 6, 7):
+        y = 0.3 * torch.randn(4, T, J, 3, generator=torch.Generator().manual_seed(seed))
+        worst = max(worst, abs(mm(agg, y) - mm(agg_ref, y)))
+    gate = {"fp16": 0.05, "bf16": 0.25}[dtype]
+    return {"dtype": dtype, "d_mpjpe_mm": worst, "gate_mm": gate, "gate_met": worst <= gate,
+            "gate_source": "north_star 0.05 mm end-to-end gate" if dtype == "fp16" else "bf16 backbone tolerance, stated separately (DESIGN.md §3)",
+            "score_argmax_agreement": float((scores.cpu().argmax(1) == scores_ref.argmax(1)).float().mean()),
+            "against": "fp32 CPU oracle (oracle/manipose_oracle.py) on the same weights, BASELINE config 1 inputs (4 clips x 243 frames)"}
+
+
+def measure_inference(model, B, dtype, args, world, rank, local_rank, dev, sample_kernels=True):
+    """`B` clips per GPU through RMCLManifoldMixSTE.forward at `dtype`: device-resident and end-to-end timing (max over ranks)."""
+    import torch
+    from manipose_b200 import ops
+    sync_all, timed = _make_timers(world, dev)
+    model.set_compute_dtype(dtype)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = (0.3 * torch.randn(B, T, J, 2, generator=gen)).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = (torch.empty((B, K, T, J, 3), dtype=torch.float32).pin_memory(), torch.empty((B, K, T, 1), dtype=torch.float32).pin_memory())
+
     def step_resident():
         with torch.no_grad():
-            return model(x_dev)
+            torch.cuda.nvtx.range_push("manipose.forward")
+            out = model(x_dev)
+            torch.cuda.nvtx.range_pop()
+            return out
 
     def step_e2e():
         with torch.no_grad():
@@ -271,7 +317,7 @@ def run_gpu(args):
     sampled = []
     orig_trunk = type(model.rotations_module).trunk
     counter = {"n": 0}
-    sample_every = 4          # bracket the GEMM launches of one micro-batch in four with CUDA events
+    sample_every = 4
 
     def trunk_sampled(self, x2d, n_clips):
         counter["n"] += 1
@@ -281,16 +327,22 @@ def run_gpu(args):
         finally:
             ops.GEMM_TIMING = None
 
-    model.rotations_module.trunk = trunk_sampled.__get__(model.rotations_module)
+    if sample_kernels:
+        model.rotations_module.trunk = trunk_sampled.__get__(model.rotations_module)
     launches0 = ops.LAUNCHES
+    steps = args.steps
     with ClockSampler(local_rank) as clocks:
-        ms = timed(step_resident, args.steps)
+        ms = timed(step_resident, steps)
+        if ms < 1500.0:                 # short regions (strong scaling at N = 8): repeat so that nvidia-smi sees the load
+            extra = int(1500.0 / max(ms / steps, 1e-3)) + 1
+            ms += timed(step_resident, extra)
+            steps += extra
     launches = ops.LAUNCHES - launches0
-    del model.rotations_module.trunk
+    if sample_kernels:
+        del model.rotations_module.trunk
     frames = B * T * world
-    value = frames * args.steps / (ms / 1000.0)
-
-    peaks = measured_peaks()
+    res = {"value": frames * steps / (ms / 1000.0), "ms_per_step": ms / steps, "steps": steps, "frames_per_step": frames,
+           "gpu_launches": launches, "clocks": clocks.summary(), "clips_per_gpu": B}
     fam = {}
     for a, b, fl, by, tag in sampled:
         f = fam.setdefault(tag, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
@@ -298,8 +350,6 @@ def run_gpu(args):
         f["flops"] += fl
         f["bytes"] += by
         f["n"] += 1
-    step_tflops = flops_per_frame() * B * T * args.steps / (ms / 1000.0) / 1e12   # per GPU (max-over-ranks time)
-    # share of the step spent in each sampled family, extrapolated from the sampled micro-batches (1 in sample_every)
     n_mb = max(1, counter["n"])
     sampled_mb = max(1, (n_mb + sample_every - 1) // sample_every)
     rl = {}
@@ -307,38 +357,108 @@ def run_gpu(args):
         t_s = f["ms"] / 1000.0
         rl[tag] = {"launches_sampled": f["n"], "avg_us": f["ms"] * 1000.0 / f["n"], "tflops": f["flops"] / t_s / 1e12,
                    "gbs": f["bytes"] / t_s / 1e9, "share_of_step": f["ms"] * (n_mb / sampled_mb) / ms}
-    dom = max(rl, key=lambda k: rl[k]["share_of_step"]) if rl else None
-    traffic = {"linear_ln": PROFILED_TRAFFIC_LN, "linear": None}
-
+    res["families"] = rl
+    res["step_tflops"] = flops_per_frame() * B * T * steps / (ms / 1000.0) / 1e12          # per GPU (max-over-ranks time)
     # ---- end to end through the public API with host buffers
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e_value = frames * args.steps / (ms_e2e / 1000.0)
+    e2e_steps = max(args.steps, 3)
+    ms_e2e = timed(step_e2e, e2e_steps)
+    res["e2e"] = {"value": frames * e2e_steps / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                  "d2h_bytes_per_step": (out_host[0].numel() + out_host[1].numel()) * 4, "ms_per_step": ms_e2e / e2e_steps}
+    return res
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world, rank, local_rank, dev = _dist_env()
+    from manipose_b200 import _build
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "manipose_b200", "libmanipose_sm100.so")):
+        _build.build(verbose=False)
+    if world > 1:
+        dist.barrier()
+    import manipose_b200 as mb
+
+    torch.manual_seed(42)
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=T, n_hyp=K, drop_path_rate=0.1)
+    model = model.to(dev).eval().set_compute_dtype(args.dtype)
+    if args.micro_batch_clips:
+        model.rotations_module.micro_batch_tokens = args.micro_batch_clips * T * J
+        model.segments_module.micro_batch_tokens = args.micro_batch_clips * T * J
+    total = args.clips
+    strong = args.scaling == "strong"
+    B = max(1, total // world) if strong else total
+    peaks = measured_peaks()
+    main = measure_inference(model, B, args.dtype, args, world, rank, local_rank, dev)
+    extras = {}
+    if not args.headline_only:
+        other = "fp16" if args.dtype == "bf16" else "bf16"
+        extras["other"] = measure_inference(model, B, other, args, world, rank, local_rank, dev, sample_kernels=False)
+        if world > 1 and strong:
+            extras["weak"] = measure_inference(model, total, args.dtype, args, world, rank, local_rank, dev, sample_kernels=False)
+    parity = {}
+    if rank == 0 and not args.headline_only:
+        cache = {}
+        parity[args.dtype] = parity_config1(model, args.dtype, cache)
+        other = "fp16" if args.dtype == "bf16" else "bf16"
+        parity[other] = parity_config1(model, other, cache)
+    model.set_compute_dtype(args.dtype)
+    micro = model.rotations_module.clips_per_micro_batch()
+    del model
+    torch.cuda.empty_cache()
+    train = None
+    if not args.headline_only:
+        train = measure_train(args, world, rank, local_rank, dev, with_cpu=False)
+    decoder = None
+    if rank == 0 and world == 1 and not args.headline_only:
+        decoder = measure_decoder(args, with_cpu=False)
 
     if rank == 0:
+        rl = main["families"]
+        dom = max(rl, key=lambda k: rl[k]["share_of_step"]) if rl else None
+        traffic = {"linear_ln": PROFILED_TRAFFIC_LN, "linear": None}
         # the CPU oracle is timed beside the GPU number at N = 1 only (the other ranks would sit in the barrier meanwhile)
         skip_cpu = args.skip_cpu_baseline or world > 1
         cpu_value, cpu_threads, cpu_reps = (0.0, 0, 0) if skip_cpu else cpu_forward_rate(clips=4, reps=3)
+        frames = main["frames_per_step"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-            "data": "synthetic",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": main["steps"], "warmup": max(args.warmup, 3),
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"ManiPose H36M lifting forward (RMCLManifoldMixSTE, config.yaml defaults), T={T}, K={K}, J={J}, "
-                                   f"{B} clips/GPU = BASELINE config 3; {args.dtype} tensor-core operands (fp32 accumulate, fp32 residual stream), fp32 decoder",
+                                   f"{total} clips " + (f"in total, sharded {B} per GPU" if strong else "per GPU") + " = BASELINE config 3; "
+                                   f"{args.dtype} tensor-core operands (fp32 accumulate, fp32 residual stream), fp32 decoder; the CPU arm "
+                                   f"(cpu_baseline / --impl reference) is timed on a 4-clip SAMPLE of this workload",
                        "clips_per_gpu": B, "frames_per_step": frames, "parallelism": f"clip-sharded x{world}, no collective",
-                       "micro_batch_clips": model.rotations_module.clips_per_micro_batch(),
+                       "micro_batch_clips": micro,
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "gflop_per_frame": flops_per_frame() / 1e9},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": (out_host[0].numel() + out_host[1].numel()) * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "clocks": clocks.summary(),
-            "roofline": roofline_object(dom, rl, peaks, step_tflops, traffic),
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
+            "clocks": main["clocks"],
+            "roofline": roofline_object(dom, rl, peaks, main["step_tflops"], traffic),
             "cpu_baseline": None if skip_cpu else {
                 "value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                 "sample": f"best of {cpu_reps} passes over 4 clips x {T} frames (972 frames) of the same workload, fp32, torch CPU"},
         }
+        if parity:
+            line["parity"] = parity[args.dtype]
+        if "other" in extras:
+            o = extras["other"]
+            other = "fp16" if args.dtype == "bf16" else "bf16"
+            line[other] = {"value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"], "e2e": o["e2e"], "clocks": o["clocks"],
+                           "whole_step": {"achieved": o["step_tflops"], "unit": "TFLOP/s", "frac": o["step_tflops"] / peaks["bf16_sustained"]},
+                           "parity": parity.get(other)}
+        if "weak" in extras:
+            wk = extras["weak"]
+            line["weak"] = {"value": wk["value"], "unit": UNIT, "clips_per_gpu": wk["clips_per_gpu"], "ms_per_step": wk["ms_per_step"],
+                            "e2e": wk["e2e"], "clocks": wk["clocks"], "scaling": "weak"}
+        if train is not None:
+            line["train"] = train
+        if decoder is not None:
+            line["decoder"] = decoder
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -346,26 +466,18 @@ def run_gpu(args):
 
 
 # ----------------------------------------------------------------------------------------------- training step (BASELINE config 4)
-def run_train(args):
-    """--config 4: one data-parallel training step at the 3DHP shape (T=27, 30 clips per GPU, K=5):
-    forward + default objective + backward + bucketed gradient all-reduce + Adam, weak-scaled.  Not the headline line (that is
-    config 3); printed as its own JSON line with the same timing rules."""
+def measure_train(args, world, rank, local_rank, dev, with_cpu=True):
+    """One data-parallel training step at the 3DHP shape (T=27, 30 clips per GPU, K=5): forward + default
+    objective + backward + bucketed gradient all-reduce + Adam, weak-scaled (30 clips per GPU, as nn.DataParallel's per-GPU batch
+    would be).  The step is ONE captured CUDA graph (--eager: kernel by kernel).  Returns the JSON object (on every rank)."""
     import torch
     import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     import manipose_b200 as mb
     from manipose_b200 import metrics, ops
-    from manipose_b200.optim import FusedAdam
+    from manipose_b200.optim import FusedAdam, GradientReducer
 
-    t4, b4 = args.frames, (args.clips if args.clips != 1024 else 30)
-    torch.manual_seed(42)                      # identical replicas
+    t4, b4 = args.frames, args.train_clips
+    torch.manual_seed(42)                      # identical replicas (FusedAdam broadcasts rank 0's state anyway)
     model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=t4, n_hyp=K, drop_path_rate=args.drop_path)
     model = model.to(dev).train().set_compute_dtype(args.dtype)
     opt = FusedAdam(model, lr=4e-5, weight_decay=1e-6)
@@ -375,6 +487,7 @@ def run_train(args):
     y[:, :, 0] = 0
     y = y.to(dev)
     loss_box = [None]
+    loss_fn = lambda out, yy: metrics.losses.training_loss(out[0], out[1], yy)[0]
 
     def step():
         opt.zero_grad()
@@ -384,90 +497,100 @@ def run_train(args):
         opt.step()
         loss_box[0] = loss.detach()
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
+    sync_all, timed = _make_timers(world, dev)
     for _ in range(max(args.warmup, 3)):
         step()
+    launches0 = ops.LAUNCHES
+    step()
+    launches = ops.LAUNCHES - launches0
     run = step
     graph = None
     if args.cuda_graph:
-        # the step is shape-static: capture forward + loss + backward + Adam once, replay it (removes ~600 launches of host work)
+        # the step is shape-static: capture forward + loss + backward + Adam once, replay it (removes ~500 launches of host work)
         from manipose_b200.optim import CapturedTrainStep
         sync_all()
-        graph = CapturedTrainStep(model, opt, lambda out, yy: metrics.losses.training_loss(out[0], out[1], yy)[0], x, y, warmup=1)
+        graph = CapturedTrainStep(model, opt, loss_fn, x, y, warmup=1)
 
         def run():
             loss_box[0] = graph(x, y)
         for _ in range(2):
             run()
     steps = max(args.steps, 20)
-    launches0 = ops.LAUNCHES
-    step()
-    launches = ops.LAUNCHES - launches0
     with ClockSampler(local_rank) as clocks:
         ms = timed(run, steps)
-    # the same step without the exchange (reducer sees a world of 1): the difference is the exposed all-reduce time
-    ms_local = None
-    if world > 1 and graph is None:
-        red = opt.reducer
-        type(red).world_size = property(lambda self: 1)
-        ms_local = timed(run, steps)
+        if ms < 2000.0:                        # ~10 ms steps: repeat until the 100 ms clock sampler has seen ~2 s of load
+            extra = int(2000.0 / max(ms / steps, 1e-3)) + 1
+            ms += timed(run, extra)
+            steps += extra
+    # the same step without the exchange (the reducer sees a world of 1): the difference is the exposed all-reduce time
+    ms_local, local_steps = None, 100
+    if world > 1:
+        orig = GradientReducer.world_size
+        GradientReducer.world_size = property(lambda self: 1)
+        try:
+            run_local, graph_local = step, None
+            if args.cuda_graph:
+                graph_local = CapturedTrainStep(model, opt, loss_fn, x, y, warmup=1)
+                run_local = lambda: graph_local(x, y)
+            for _ in range(2):
+                run_local()
+            ms_local = timed(run_local, local_steps)
+            if graph_local is not None:
+                graph_local.close()
+        finally:
+            GradientReducer.world_size = orig
+        opt.broadcast_state()                  # the replicas drifted apart during the exchange-free steps
     frames = b4 * t4 * world
     value = frames * steps / (ms / 1000.0)
     peaks = measured_peaks()
     tflops = 3.0 * flops_per_frame(t4, K) * b4 * t4 * steps / (ms / 1000.0) / 1e12
     n_params = sum(p.numel() for p in model.parameters())
     cpu = None
-    if rank == 0 and not args.skip_cpu_baseline and world == 1:
+    if rank == 0 and with_cpu and not args.skip_cpu_baseline and world == 1:
         cpu = cpu_train_rate(t4)
-    if rank == 0:
-        line = {"metric": f"train_frames_per_sec_T{t4}" + ("_3DHP" if t4 == 27 else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": f"ManiPose training step (forward + wta/bce/velocity/smoothness objective + backward + gradient all-reduce + Adam), "
-                                       f"T={t4}, K={K}, J={J}, {b4} clips/GPU = BASELINE config 4; drop_path_rate {args.drop_path}",
-                           "clips_per_gpu": b4, "frames_per_step": frames, "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce of "
-                           f"{n_params} fp32 gradients ({n_params * 4 / 1e6:.1f} MB) overlapped with the backward sweep",
-                           "cuda_graph": bool(args.cuda_graph), "gflop_per_frame_fwd_bwd": 3.0 * flops_per_frame(t4, K) / 1e9},
-                "gpu_launches": launches * steps, "clocks": clocks.summary(), "loss": float(loss_box[0]),
-                "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                             "frac": tflops / peaks["bf16_sustained"], "traffic": None,
-                             "note": "whole step: 3 x forward matmul flops / step time; the step is launch / latency bound at 810 frames"},
-                "allreduce": None if ms_local is None else {"exposed_ms_per_step": (ms - ms_local) / steps, "ms_per_step_without": ms_local / steps},
-                "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+    line = {"metric": f"train_frames_per_sec_T{t4}" + ("_3DHP" if t4 == 27 else ""), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"ManiPose training step (forward + wta/bce/velocity/smoothness objective + backward + gradient all-reduce + Adam), "
+                                   f"T={t4}, K={K}, J={J}, {b4} clips/GPU = BASELINE config 4; drop_path_rate {args.drop_path}",
+                       "clips_per_gpu": b4, "frames_per_step": frames, "parallelism": f"data-parallel x{world}, bucketed NCCL all-reduce of "
+                       f"{n_params} fp32 gradients ({n_params * 4 / 1e6:.1f} MB) overlapped with the backward sweep",
+                       "cuda_graph": bool(args.cuda_graph), "gflop_per_frame_fwd_bwd": 3.0 * flops_per_frame(t4, K) / 1e9},
+            "gpu_launches": launches * steps, "launches_per_step": launches, "clocks": clocks.summary(), "loss": float(loss_box[0]),
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / peaks["bf16_sustained"], "traffic": None,
+                         "note": "whole step: 3 x forward matmul flops / step time; the step is launch / latency bound at 810 frames per GPU"},
+            "allreduce": None if ms_local is None else {
+                "payload_mb": n_params * 4 / 1e6, "exposed_ms_per_step": ms / steps - ms_local / local_steps,
+                "ms_per_step_without_exchange": ms_local / local_steps,
+                "how": "same step re-captured with the reducer seeing a world of 1, timed for 100 steps; exposed = difference"},
+            "cpu_baseline": cpu}
     if graph is not None:
         graph.close()                          # before the process group goes: NCCL waits for graphs holding its collectives
+    del model, opt
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_train(args):
+    import torch.distributed as dist
+    world, rank, local_rank, dev = _dist_env()
+    line = measure_train(args, world, rank, local_rank, dev)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------- decoder alone (BASELINE config 2)
-def run_decoder(args):
+def measure_decoder(args, with_cpu=True):
     """BASELINE config 2: 6D -> SO(3) + forward kinematics + hypothesis softmax on N = 824 x 5 x 243 = 1,001,160 synthetic
     poses, fp32, one B200.  HBM roofline: 620 algorithmic bytes per pose (408 rot6d + 4 logit in, 204 pose + 4 score out)."""
     import torch
     import manipose_b200  # noqa: F401
     from manipose_b200 import ops
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     nc, k, t = 824, K, T
     n = nc * k * t
     gen = torch.Generator().manual_seed(1234)
@@ -494,7 +617,7 @@ def run_decoder(args):
     steps = max(args.steps, 2000)               # ~0.5 s of launches so that the clock sampler sees the region
     launches0 = ops.LAUNCHES
     ms_kernel = 0.0
-    with ClockSampler(0) as clocks:
+    with ClockSampler(dev.index or 0) as clocks:
         for _ in range(steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -515,7 +638,7 @@ def run_decoder(args):
     peaks = measured_peaks()
     gbs = 620.0 * n / (ms / 1000.0) / 1e9
     cpu = None
-    if not args.skip_cpu_baseline:
+    if with_cpu and not args.skip_cpu_baseline:
         from oracle import manipose_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)
         nb = 103                                  # 103 clips x 5 x 243 = 125,145 poses (1/8 of the workload)
@@ -541,7 +664,13 @@ def run_decoder(args):
                          "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_pose": 620,
                          "peak_source": "measured (STREAM-style copy)" if peaks["src"] == "measured" else "fallback"},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_decoder(args):
+    import torch
+    torch.cuda.set_device(0)
+    print(json.dumps(measure_decoder(args)), flush=True)
 
 
 def main():
@@ -549,7 +678,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clips", type=int, default=1024, help="clips per GPU per step (BASELINE config 3: 1024)")
+    ap.add_argument("--clips", type=int, default=1024, help="clips per step: in total (strong scaling, the default: BASELINE config 3 = 1024 "
+                    "clips sharded over the GPUs) or per GPU (--scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = --clips in total, 1024/N per GPU as BASELINE config 3 states; weak = --clips per GPU")
+    ap.add_argument("--train-clips", type=int, default=30, help="config 4: clips per GPU per training step")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="profiling runs: only the config-3 line at --dtype (no fp16 / weak / parity / train / decoder sub-objects)")
     ap.add_argument("--micro-batch-clips", type=int, default=0)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit operand format of the backbone")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: do not time the CPU oracle")

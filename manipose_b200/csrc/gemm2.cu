@@ -273,12 +273,11 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // (qkv 12 -> 7, fc1 8 -> 5).  What is left of shared memory holds ONE 16 KB output slot per epilogue group, so the epilogue computes a
 // box into registers first and only then waits for its slot.
 constexpr int kAsKB = 8;                                   // k-blocks of the resident A tile (K = 512)
-constexpr int kAsWStages = 4;
 constexpr int kAsSlots = 2;
-constexpr int kAsSmem = 1024 + kAsKB * kABytes + kAsWStages * kWHalfBytes + kAsSlots * kBoxBytes + 512;
-static_assert(kAsSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+constexpr int as_smem(int w_stages) { return 1024 + kAsKB * kABytes + w_stages * kWHalfBytes + kAsSlots * kBoxBytes + 512; }
+static_assert(as_smem(4) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
-template <int EPI, typename D>
+template <int EPI, typename D, int kAsWStages, bool kRotate>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
                       const float* __restrict__ bias, int M, int N) {
@@ -342,8 +341,9 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs) {
-        for (int n_blk = 0; n_blk < n_blocks; ++n_blk) {
-          const int row_w = n_blk * BN + (int)rank * 128;
+        for (int n_it = 0; n_it < n_blocks; ++n_it) {
+          const int n_blk = kRotate ? (n_it + pair_id) % n_blocks : n_it;   // pairs walk the N blocks in rotated order: the 74 pairs do
+          const int row_w = n_blk * BN + (int)rank * 128;                   // not all pull the same W lines out of L2 at the same time
           for (int kb = 0; kb < kAsKB; ++kb) {
             ptx::mbar_wait(&w_empty[stage], phase ^ 1);
             const uint32_t full_leader = ptx::mapa_shared(smem_u32(&w_full[stage]), 0);
@@ -421,7 +421,8 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     uint32_t use = 0;                            // boxes this group has stored so far
     for (int m_pair = pair_id; m_pair < m_pairs; m_pair += num_pairs) {
       const int row0 = m_pair * 2 * kBM + (int)rank * kBM;
-      for (int n_blk = 0; n_blk < n_blocks; ++n_blk) {
+      for (int n_it = 0; n_it < n_blocks; ++n_it) {
+        const int n_blk = kRotate ? (n_it + pair_id) % n_blocks : n_it;
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * BN);
@@ -917,13 +918,19 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
   static const int as_cfg = getenv("MANIPOSE_PAIR_AS") ? atoi(getenv("MANIPOSE_PAIR_AS")) : 1;
   if (as_cfg != 0 && !Y2 && K == kAsKB * kBK && N >= 512) {
     const int grid = pair_grid((M + 255) / 256);
-    auto launch_as = [&](auto kernel) -> int {
-      MP_CHECK(set_smem(kernel, kAsSmem));
-      kernel<<<grid, kThreads, kAsSmem, stream>>>(ta, tw, ty, bias, M, N);
+    auto launch_as = [&](auto kernel, int smem_bytes) -> int {
+      MP_CHECK(set_smem(kernel, smem_bytes));
+      kernel<<<grid, kThreads, smem_bytes, stream>>>(ta, tw, ty, bias, M, N);
       return check_launch("pair_linear_as_kernel");
     };
-    if (epilogue == MP_EPI_GELU) return bf ? launch_as(pair_linear_as_kernel<MP_EPI_GELU, Bf16>) : launch_as(pair_linear_as_kernel<MP_EPI_GELU, Fp16>);
-    return bf ? launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Bf16>) : launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Fp16>);
+    const bool gelu = epilogue == MP_EPI_GELU;
+#define MP_AS(ST, ROT)                                                                                                              \
+  (gelu ? (bf ? launch_as(pair_linear_as_kernel<MP_EPI_GELU, Bf16, ST, ROT>, as_smem(ST)) : launch_as(pair_linear_as_kernel<MP_EPI_GELU, Fp16, ST, ROT>, as_smem(ST))) \
+        : (bf ? launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Bf16, ST, ROT>, as_smem(ST)) : launch_as(pair_linear_as_kernel<MP_EPI_BIAS, Fp16, ST, ROT>, as_smem(ST))))
+    if (as_cfg == 2) return MP_AS(4, false);     // experiments: lockstep N order / 3 W stages
+    if (as_cfg == 3) return MP_AS(3, true);
+    return MP_AS(4, true);
+#undef MP_AS
   }
   const int tiles = (N / 256) * ((M + 255) / 256);
   const int grid = pair_grid(tiles);

@@ -232,9 +232,16 @@ def test_model_gradients_vs_oracle_autograd(T_, K, B, dtype):
     assert vals[len(vals) // 2] <= typical
 
 
-# The same comparison with the winner-takes-all flips REMOVED, so that the figure is the backward kernels' own rounding: the target of
-# every frame is one of the oracle's own hypotheses (k* = (clip + frame) mod K) plus 1 % noise, which puts the winner a wide margin
-# ahead of the other K - 1 hypotheses (random-init heads differ by O(1)); the test first proves that no winner moved.
+# The same comparison with the two effects that are NOT the backward kernels taken out, so that the figure pins the kernels themselves at
+# the benchmarked dtype:
+#   * winner flips: the target of every frame is one of the oracle's own hypotheses (k* = (clip + frame) mod K) with every joint
+#     displaced by 0.5 in a random direction, which keeps the winner a wide margin ahead of the other K - 1 hypotheses (smallest
+#     margin 0.14 against a forward error of a few 1e-3) while the residuals stay O(0.5), so the unit-vector gradients of the L2
+#     terms are as well conditioned as with a random target (a target AT a hypothesis would put the objective at a minimum, where
+#     any forward error dominates the gradient); the test first proves that no winner moved;
+#   * weight rounding: the block GEMM weights are made representable in the 16-bit format before BOTH runs, so the oracle linearises at
+#     the weights the tensor cores actually multiply by ("the oracle on bf16-rounded weights").
+# What remains is the rounding of the 16-bit activations and of the backward operands.
 GRAD_TOL_NO_FLIPS = {"bf16": (2e-2, 6e-2), "fp16": (5e-3, 2e-2)}
 
 
@@ -243,16 +250,21 @@ def test_model_gradients_without_winner_flips(dtype):
     from manipose_b200 import metrics, ops
     T_, K, B = 27, 5, 2
     sd = O.make_state_dict(num_frame=T_, n_hyp=K, seed=11)
-    # O(1) LayerNorm biases in the K heads: the folded-head backward has a term in beta that is zero at the default init
+    td = torch.bfloat16 if dtype == "bf16" else torch.float16
     gen = torch.Generator().manual_seed(5)
     for name in list(sd):
         if ".head." in name and name.endswith("norm.bias"):
+            # O(1) LayerNorm biases in the K heads: the folded-head backward has a term in beta that is zero at the default init
             sd[name] = torch.randn(sd[name].shape, generator=gen)
+        if "blocks." in name and name.endswith(("qkv.weight", "proj.weight", "fc1.weight", "fc2.weight")):
+            sd[name] = sd[name].to(td).float()
     x = 0.3 * torch.randn(B, T_, 17, 2, generator=gen)
     with torch.no_grad():
         poses0, _ = O.rmcl_forward(x, sd)
     pick = (torch.arange(B)[:, None] + torch.arange(T_)[None, :]) % K
-    y = poses0[torch.arange(B)[:, None], pick, torch.arange(T_)[None, :]] + 0.01 * torch.randn(B, T_, 17, 3, generator=gen)
+    offset = torch.randn(B, T_, 17, 3, generator=gen)
+    offset = 0.5 * offset / offset.norm(dim=-1, keepdim=True)
+    y = poses0[torch.arange(B)[:, None], pick, torch.arange(T_)[None, :]] + offset
     y[:, :, 0] = 0
     sd_ref = {k: v.clone().requires_grad_() for k, v in sd.items()}
     poses_ref, scores_ref = O.rmcl_forward(x, sd_ref)
