@@ -182,7 +182,9 @@ int mp_embed_segments(const float* in2d, const float* W, const float* b, const f
                       const float* ln_beta, float ln_eps, float* x_out, void* h_out, int64_t n_frames,
                       int in_features, int n_segments, int C, int dtype, mp_stream_t stream);
 
-/* Multi-head softmax attention (Attention.forward, mix_ste.py:255-282), tensor cores via mma.sync, fp32 softmax.
+/* Multi-head softmax attention (Attention.forward, mix_ste.py:255-282), fp32 softmax.  head_dim 64 (the C = 512 rotation
+ * backbone) runs on tcgen05 with TMEM accumulators (attn_spatial_tc_kernel, attn_temporal_tc2_kernel: S = Q K^T and O = P V as
+ * tcgen05.mma, operands by TMA); head_dim 16 (the C = 128 bone-length backbone, 1.7 % of the flops) on the mma.sync kernels.
  *   qkv [n_clips*n_frames*n_tok, 3*C] 16-bit, columns [q|k|v] x heads x head_dim (mix_ste.py:257-261)
  *   out [n_clips*n_frames*n_tok, C] 16-bit;  head_dim in {64, 16}; scale = head_dim^-0.5
  *   MP_ATTN_SPATIAL: sequences = the n_tok tokens of one frame;
@@ -193,7 +195,7 @@ int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, 
 
 /* K hypothesis heads (RMCLRotMixSTE.forward tail + MCLHead, rmcl_manifold_mix_ste.py:251-298), all fp32:
  *   x [n_frames_total*17, 512] fp32 = output of the last temporal block BEFORE Temporal_norm;
- *   applies Temporal_norm (post_*), then per head k: LN(eps 1e-5; hg/hb [K,512]) -> Linear(512 -> out_dim
+ *   applies Temporal_norm (post_*; both NULL: x is already normalised, MCLHead.forward on its own), then per head k: LN(eps 1e-5; hg/hb [K,512]) -> Linear(512 -> out_dim
  *   (+1 if with_score); hw [K, out_dim+1, 512], hbias [K, out_dim+1]) -> rot [B,K,T,17,out_dim] fp32 and,
  *   if with_score, logits[B,K,T] = score_w[K,17] . score_emb + score_b[K].
  *   with_score = 0 is MixSTE.head of the single-hypothesis model (mix_ste.py:123-126, K = 1). */
@@ -257,8 +259,10 @@ int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_
  * The reference differentiates Block / Attention / Mlp / LayerNorm with torch autograd (mix_ste.py:194-368) and steps
  * torch.optim.Adam (main_h36m_lifting.py:755-761).  Dense contractions of the backward pass reuse mp_linear:
  *   dgrad  dX[M,K] = dY[M,N] W[N,K]      -> mp_linear(A = dY, W = transposed 16-bit shadow [K,N])
- *   wgrad  dW[N,K] += dY^T X             -> mp_linear(A = dY^T [N,Mpad], W = X^T [K,Mpad], Y = dW, MP_EPI_ACCUMULATE)
- * with the operand transposes (and the bias gradient, a column sum of dY) done by mp_transpose16. */
+ *   wgrad  dW[N,K] += dY^T X             -> mp_wgrad: dY [tokens,N] and X [tokens,K] are read IN PLACE as MN-major tcgen05 operands
+ *                                           (rows = tokens = the contraction index), the token contraction is split over the SMs and
+ *                                           the partial tiles are added into dW with TMA reduce stores; no transposed copies exist.
+ * The bias gradient (a column sum of dY) is mp_colsum16; mp_transpose16 only builds the [K,N] weight shadows of the folded heads. */
 
 /* LayerNorm backward: dx = LN'(x; gamma, eps)(dy) [+ dres]; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics; both NULL to skip).
  * dy is fp32 (dy_is_16bit = 0) or `dtype` 16-bit; gamma NULL = no affine; dx may alias dres.  dx16 (may be NULL): also writes
@@ -300,6 +304,18 @@ int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens
  * (CosineAnnealingLR / ReduceLROnPlateau, main_h36m_lifting.py:763-771) keeps working across replays of a captured step. */
 int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int64_t step, int64_t* step_dev, const float* lr_dev, float grad_scale, mp_stream_t stream);
+
+/* Per-point / joint-wise / coordinate-wise errors of the evaluation drivers (mean_joint_errors.py:31-141: mpjpe_error(no_agg),
+ * mse_error, jointwise_error, jointwise_mse, coordwise_error; segments_len_err over the bone lengths of mp_pose_consistency).
+ *   mode MP_ERR_L2 / MP_ERR_SQ: pred, gt hold n_elem 3-D points; e_i = ||gt_i - pred_i||_2 (or its square)
+ *   mode MP_ERR_ABS / MP_ERR_DIFF: pred, gt hold n_elem scalars;   e_i = |gt_i - pred_i| (or the signed difference)
+ *   per_elem (may be NULL): e [n_elem] (the reference's mode "no_agg");
+ *   col_out  (may be NULL): [cols] with col_out[c] = scale * sum of e_i over i = c (mod cols) -- cols = 17 joints, 3 coordinates, or 1
+ *   for a plain sum / mean; deterministic (fp64 partials combined in a fixed order).  workspace: mp_point_errors_workspace_bytes. */
+enum { MP_ERR_L2 = 0, MP_ERR_SQ = 1, MP_ERR_ABS = 2, MP_ERR_DIFF = 3 };
+size_t mp_point_errors_workspace_bytes(int64_t n_elem, int cols);
+int mp_point_errors(const float* pred, const float* gt, int64_t n_elem, int cols, int mode, float scale, float* per_elem, float* col_out,
+                    void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
 #ifdef __cplusplus
 }

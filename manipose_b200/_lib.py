@@ -19,6 +19,7 @@ MP_AGG_WEIGHTED_AVE, MP_AGG_BEST_SCORE, MP_AGG_ORACLE = 0, 1, 2
 MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL, MP_EPI_ACCUMULATE = 0, 1, 2, 3
 MP_ATTN_SPATIAL, MP_ATTN_TEMPORAL = 0, 1
 MP_DTYPE_BF16, MP_DTYPE_FP16 = 0, 1
+MP_ERR_L2, MP_ERR_SQ, MP_ERR_ABS, MP_ERR_DIFF = 0, 1, 2, 3
 
 P, I64, F, I = c_void_p, c_int64, c_float, c_int
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "mp_p_mpjpe": (I, [P, P, I64, P, P, c_size_t, P]),
     "mp_pose_consistency_workspace_bytes": (c_size_t, [I64, I64]),
     "mp_pose_consistency": (I, [P, I64, I64, P, P, P, P, P, P, c_size_t, P]),
+    "mp_point_errors_workspace_bytes": (c_size_t, [I64, I]),
+    "mp_point_errors": (I, [P, P, I64, I, I, F, P, P, P, c_size_t, P]),
     "mp_layernorm_bwd": (I, [P, P, F, P, I, P, P, P, P, P, P, I64, I, I, P]),
     "mp_gelu_fwd": (I, [P, P, I64, I, P]),
     "mp_gelu_bwd": (I, [P, P, P, I64, I, P]),

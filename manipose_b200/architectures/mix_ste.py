@@ -38,14 +38,50 @@ class DropPath(nn.Module):
         return f"drop_prob={round(self.drop_prob, 3):0.3f}"
 
 
-def _no_standalone(name):
-    raise NotImplementedError(
-        f"{name}.forward is not a standalone entry point in manipose_b200: the block runs fused inside MixSTE.trunk "
-        "(sm_100a kernels, one [clip, frame, token, C] layout). Call the enclosing MixSTE / RMCLManifoldMixSTE.")
+# ---- standalone entry points of the block pieces (mix_ste.py:194-368).  The models run these fused inside MixSTE.trunk; the
+# reference also lets a caller invoke a Block / Attention / Mlp on its own, so these do too: inference only (no tape is kept),
+# fp32 in and out like the reference, the same kernels as the trunk (16-bit tensor-core operands, fp32 accumulation).
+def _standalone_input(module, name: str, x: torch.Tensor, c: int):
+    ops._need_cuda(x)
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise NotImplementedError(
+            f"{name}.forward on its own is inference-only in manipose_b200 (call it under torch.no_grad()); gradients flow through "
+            "the enclosing MixSTE / ManifoldMixSTE / RMCLManifoldMixSTE, whose backward sweep is hand-written")
+    if x.shape[-1] != c:
+        raise RuntimeError(f"{name}: expected {c} channels, got input of shape {tuple(x.shape)}")
+    return ops._f32(x).reshape(-1, c)
+
+
+def _w16(w: torch.Tensor, code: int) -> torch.Tensor:
+    return ops.cast16(w.detach(), code)
+
+
+def _bias(lin: nn.Linear) -> torch.Tensor:
+    return lin.bias.detach() if lin.bias is not None else torch.zeros(lin.out_features, dtype=torch.float32, device=lin.weight.device)
+
+
+def _mlp_into(mlp, h16: torch.Tensor, x_acc: torch.Tensor, code: int) -> None:
+    """x_acc (fp32 [M, C]) += fc2(gelu(fc1(h16)))."""
+    hid = torch.empty((h16.shape[0], mlp.fc1.out_features), dtype=h16.dtype, device=h16.device)
+    ops.linear(h16, _w16(mlp.fc1.weight, code), _bias(mlp.fc1), hid, L.MP_EPI_GELU)
+    ops.linear(hid, _w16(mlp.fc2.weight, code), _bias(mlp.fc2), x_acc, L.MP_EPI_RESIDUAL, resid=x_acc)
+
+
+def _attention_into(attn, h16: torch.Tensor, x_acc: torch.Tensor, n_seq: int, seq_len: int, code: int) -> None:
+    """x_acc (fp32 [n_seq * seq_len, C]) += proj(softmax(q k^T / sqrt(hd)) v), sequences of seq_len consecutive rows."""
+    c = attn.qkv.in_features
+    if seq_len > 256:
+        raise NotImplementedError(f"Attention: sequences longer than 256 tokens are not built (got {seq_len})")
+    qkv = torch.empty((h16.shape[0], 3 * c), dtype=h16.dtype, device=h16.device)
+    ops.linear(h16, _w16(attn.qkv.weight, code), _bias(attn.qkv), qkv, L.MP_EPI_BIAS)
+    o = torch.empty_like(h16)
+    ops.attention(qkv, o, n_seq, seq_len, 1, c, attn.num_heads, L.MP_ATTN_TEMPORAL)   # one "track" per sequence
+    ops.linear(o, _w16(attn.proj.weight, code), _bias(attn.proj), x_acc, L.MP_EPI_RESIDUAL, resid=x_acc)
 
 
 class Mlp(nn.Module):
-    """Parameter holder for mix_ste.py:194-222 (fc1 -> exact GELU -> fc2)."""
+    """mix_ste.py:194-222 (fc1 -> exact GELU -> fc2)."""
+    compute_dtype = "bf16"
 
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0, changedim=False,
                  currentdim=0, depth=0):
@@ -58,11 +94,17 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        _no_standalone("Mlp")
+        c = self.fc1.in_features
+        x2d = _standalone_input(self, "Mlp", x, c)
+        code = ops.DTYPE_CODE[self.compute_dtype]
+        out = torch.zeros((x2d.shape[0], self.fc2.out_features), dtype=torch.float32, device=x.device)
+        _mlp_into(self, ops.cast16(x2d, code), out, code)
+        return out.reshape(*x.shape[:-1], self.fc2.out_features)
 
 
 class Attention(nn.Module):
-    """Parameter holder for mix_ste.py:225-282."""
+    """mix_ste.py:225-282: x [B, N, C] -> [B, N, C]."""
+    compute_dtype = "bf16"
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0, comb=False, vis=False,
                  mup=False):
@@ -79,11 +121,19 @@ class Attention(nn.Module):
         self.vis = vis
 
     def forward(self, x, vis=False):
-        _no_standalone("Attention")
+        c = self.qkv.in_features
+        x2d = _standalone_input(self, "Attention", x, c)
+        if x.dim() != 3:
+            raise ValueError(f"Attention expects [B, N, C], got {tuple(x.shape)}")
+        code = ops.DTYPE_CODE[self.compute_dtype]
+        out = torch.zeros_like(x2d)
+        _attention_into(self, ops.cast16(x2d, code), out, x.shape[0], x.shape[1], code)
+        return out.reshape(x.shape)
 
 
 class Block(nn.Module):
-    """Parameter holder for mix_ste.py:285-368 (pre-LN attention + MLP, residual_scale = 1 without muP)."""
+    """mix_ste.py:285-368 (pre-LN attention + MLP, residual_scale = 1 without muP): x [B, N, C] -> [B, N, C]."""
+    compute_dtype = "bf16"
 
     def __init__(self, dim, num_heads, mlp_ratio=4.0, attention=Attention, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0,
                  drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, comb=False, changedim=False, currentdim=0, depth=0,
@@ -104,7 +154,20 @@ class Block(nn.Module):
         self.vis = vis
 
     def forward(self, x, vis=False):
-        _no_standalone("Block")
+        c = self.norm1.normalized_shape[0]
+        x2d = _standalone_input(self, "Block", x, c)
+        if x.dim() != 3:
+            raise ValueError(f"Block expects [B, N, C], got {tuple(x.shape)}")
+        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0:
+            raise NotImplementedError("Block.forward on its own has no stochastic depth: call .eval() (the training trunk applies DropPath)")
+        code = ops.DTYPE_CODE[self.compute_dtype]
+        acc = x2d.clone()                                     # the fp32 residual stream of this block
+        h = torch.empty(acc.shape, dtype=ops.TORCH_DTYPE[code], device=acc.device)
+        ops.layernorm(acc, None, h, ln=(self.norm1.weight, self.norm1.bias), ln_eps=self.norm1.eps, dtype=code)
+        _attention_into(self.attn, h, acc, x.shape[0], x.shape[1], code)
+        ops.layernorm(acc, None, h, ln=(self.norm2.weight, self.norm2.bias), ln_eps=self.norm2.eps, dtype=code)
+        _mlp_into(self.mlp, h, acc, code)
+        return acc.reshape(x.shape)
 
 
 def _version_key(params) -> Tuple:

@@ -27,8 +27,26 @@ class MCLHead(nn.Module):
         self.prediction_head = nn.Linear(embed_dim, out_dim + 1)
         self.score_head = nn.Linear(num_joints, 1)
 
-    def forward(self, x):
-        raise NotImplementedError("MCLHead runs fused over all K heads inside RMCLRotMixSTE (mp_heads_fwd)")
+    def forward(self, x: torch.Tensor):
+        """rmcl_manifold_mix_ste.py:290-298 on its own: x [B, L, J, C] (already through Temporal_norm) -> (rotations [B, L, J, D],
+        score logit [B, L, 1]).  The models run all K heads in one mp_heads_fwd launch; this is the same kernel with K = 1 and the
+        shared post-norm switched off.  Inference only, fp32 like the reference."""
+        ops._need_cuda(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("MCLHead.forward on its own is inference-only (call it under torch.no_grad()); gradients flow "
+                                      "through RMCLManifoldMixSTE")
+        if x.dim() != 4 or x.shape[2] != self.score_head.in_features:
+            raise ValueError(f"MCLHead expects [B, L, {self.score_head.in_features}, C], got {tuple(x.shape)}")
+        b, l, j, _ = x.shape
+        d = self.prediction_head.out_features - 1
+        x = ops._f32(x)
+        rot = torch.empty((b, 1, l, j, d), dtype=torch.float32, device=x.device)
+        logits = torch.empty((b, 1, l), dtype=torch.float32, device=x.device)
+        ops.heads_fwd(x.reshape(-1, x.shape[-1]), None, None, 0.0, self.norm.weight.detach().unsqueeze(0).contiguous(),
+                      self.norm.bias.detach().unsqueeze(0).contiguous(), self.prediction_head.weight.detach().unsqueeze(0).contiguous(),
+                      self.prediction_head.bias.detach().unsqueeze(0).contiguous(), self.score_head.weight.detach().contiguous(),
+                      self.score_head.bias.detach().contiguous(), rot, logits, b, l, 1, d, True)
+        return rot[:, 0], logits[:, 0].unsqueeze(-1)
 
 
 class RMCLRotMixSTE(MixSTE):

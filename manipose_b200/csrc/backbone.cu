@@ -204,8 +204,11 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pg[R::kPer], pb[R::kPer];
-  R::load_f32(post_g, lane, pg);
-  R::load_f32(post_b, lane, pb);
+  const bool has_post = post_g != nullptr;   // NULL: x already went through Temporal_norm (a standalone MCLHead.forward call)
+  if (has_post) {
+    R::load_f32(post_g, lane, pg);
+    R::load_f32(post_b, lane, pb);
+  }
   const int64_t total_frames = n_clips * n_frames;
   for (int64_t fr = (int64_t)blockIdx.x * kTokWarps + warp; fr < total_frames; fr += (int64_t)gridDim.x * kTokWarps) {
     const int64_t b = fr / n_frames;
@@ -218,9 +221,11 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
       for (int q = 0; q < kHeadTok; ++q) {
         const int j = j0 + q < kJ ? j0 + q : kJ - 1;         // the tail group re-reads joint 16; its results are discarded
         R::load_x(x + (fr * kJ + j) * kHeadC, lane, v[q]);
-        float m, r;
-        R::stats(v[q], post_eps, m, r);
-        R::normalize(v[q], m, r, pg, pb);
+        if (has_post) {
+          float m, r;
+          R::stats(v[q], post_eps, m, r);
+          R::normalize(v[q], m, r, pg, pb);
+        }
         R::stats(v[q], 1e-5f, mean[q], rstd[q]);
       }
       for (int k = 0; k < n_hyp; ++k) {
@@ -405,7 +410,7 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
                  int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(x && post_gamma && post_beta && hg && hb && hw && hbias && rot, MP_EINVAL, "mp_heads_fwd: null pointer");
+  MP_REQUIRE(x && hg && hb && hw && hbias && rot && (post_gamma == nullptr) == (post_beta == nullptr), MP_EINVAL, "mp_heads_fwd: null pointer");
   MP_REQUIRE(!with_score || (score_w && score_b && logits), MP_EINVAL, "mp_heads_fwd: score head pointers required");
   MP_REQUIRE(n_hyp >= 1 && n_hyp <= 16 && (out_dim == 6 || out_dim == 4), MP_EINVAL, "mp_heads_fwd: bad n_hyp/out_dim");
   MP_REQUIRE(n_clips >= 0 && n_frames >= 1, MP_EINVAL, "mp_heads_fwd: bad sizes");

@@ -31,7 +31,7 @@ point_errors_kernel(const float* __restrict__ pred, const float* __restrict__ gt
   __shared__ double sh[kErrThreads];
   const int64_t t0 = (int64_t)blockIdx.x * kErrThreads + threadIdx.x;
   double acc = 0.0;
-  for (int64_t i = t0; i < n_elem; i += stride) {      // stride % cols == 0: this thread stays in column t0 % cols
+  for (int64_t i = t0 < stride ? t0 : n_elem; i < n_elem; i += stride) {      // stride % cols == 0: this thread stays in column t0 % cols
     const float e = element_error<MODE>(pred, gt, i);
     if (per_elem) per_elem[i] = e;
     acc += (double)e;
@@ -57,15 +57,14 @@ __global__ void point_errors_finalize_kernel(const double* __restrict__ partials
   out[c] = (float)(s * scale);
 }
 
+// Grid and stride: the stride is the largest multiple of `cols` that the grid's threads cover; threads at or beyond it stay idle, so
+// every element index i = q * stride + r (r < stride) is visited exactly once, by thread r, whose column r % cols never changes.
 int err_grid(int64_t n_elem, int cols, int64_t* stride) {
   int64_t ctas = (n_elem + kErrThreads - 1) / kErrThreads;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  // the stride must be a multiple of cols: round the thread count up to one (threads beyond the grid simply do not exist; the loop
-  // bound n_elem keeps every element visited exactly once because each start index below `threads` is owned by one thread)
-  const int64_t threads = ctas * kErrThreads;
-  *stride = (threads + cols - 1) / cols * cols;
+  *stride = ctas * kErrThreads / cols * cols;
   return (int)ctas;
 }
 
@@ -97,15 +96,6 @@ int mp_point_errors(const float* pred, const float* gt, int64_t n_elem, int cols
   }
   int64_t stride;
   const int ctas = err_grid(n_elem, cols, &stride);
-  // a stride rounded up past the real thread count would leave start indices in [threads, stride) unvisited: shrink the grid's
-  // coverage instead by giving the last CTAs no elements -- i.e. require stride == threads, which err_grid guarantees when
-  // cols divides kErrThreads * ctas; otherwise fall back to a stride that is the least common multiple step below
-  const int64_t threads = (int64_t)ctas * kErrThreads;
-  if (stride != threads) {
-    // make the thread count itself a multiple of cols by using only `stride - cols` ... simpler: every thread t >= usable is idle
-    // (see the kernel: it starts at t0 and jumps by `usable`), with usable = floor(threads / cols) * cols
-    stride = threads / cols * cols;
-  }
   double* partials = nullptr;
   if (col_out) {
     MP_REQUIRE(workspace && workspace_bytes >= (size_t)ctas * cols * sizeof(double) && aligned16(workspace), MP_EWORKSPACE,

@@ -913,9 +913,12 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
   else
     ty2 = ty;
   const bool bf = dtype == MP_DTYPE_BF16;
-  // K = 512 and at least two 256-column blocks: keep the A tile resident (pair_linear_as_kernel); MANIPOSE_PAIR_AS=0 forces the
-  // streaming kernel (A/B measurements)
-  static const int as_cfg = getenv("MANIPOSE_PAIR_AS") ? atoi(getenv("MANIPOSE_PAIR_AS")) : 1;
+  // MANIPOSE_PAIR_AS=1 (K = 512, at least two 256-column blocks): the A-stationary variant (pair_linear_as_kernel).  Measured on
+  // B200 at 528,768 rows it is NOT faster than the streaming kernel (qkv 690 vs 676 us, fc1 602 vs 587 us; 731 / 620 us with all
+  // pairs walking N in lockstep, 721 / 607 us with 3 W stages), although it halves the operand traffic out of L2: these launches
+  // are not L2-bandwidth bound, and the 4 x 16 KB of W in flight that fit beside the resident A tile hide less latency than the
+  // streaming kernel's 5 x 32 KB.  Kept as an A/B switch (negative results); the default stays the streaming kernel.
+  static const int as_cfg = getenv("MANIPOSE_PAIR_AS") ? atoi(getenv("MANIPOSE_PAIR_AS")) : 0;
   if (as_cfg != 0 && !Y2 && K == kAsKB * kBK && N >= 512) {
     const int grid = pair_grid((M + 255) / 256);
     auto launch_as = [&](auto kernel, int smem_bytes) -> int {

@@ -13,7 +13,8 @@ _ARCH = ("MixSTE", "ManifoldMixSTE", "RMCLManifoldMixSTE")
 _METRICS = ("wta_l2_loss_and_activate_head", "wta_with_scoring_loss", "weighted_mpjpe_loss", "weighted_mse_loss",
             "mean_velocity_error", "smoothness_regularization", "mpjpe_error", "STANDARD_H36M_WEIGHTS",
             "measure_bones_length", "segments_time_consistency", "segments_time_consistency_per_bone", "sagittal_symmetry",
-            "sagittal_symmetry_per_bone", "p_mpjpe", "keypoint_3d_pck", "keypoint_3d_auc")
+            "sagittal_symmetry_per_bone", "p_mpjpe", "keypoint_3d_pck", "keypoint_3d_auc", "mse_error", "jointwise_error",
+            "jointwise_mse", "coordwise_error", "segments_len_err")
 _CONSISTENCY = ("segments_time_consistency", "segments_time_consistency_per_bone", "sagittal_symmetry", "sagittal_symmetry_per_bone")
 
 
@@ -43,7 +44,8 @@ def install(package: str = "mh_so3_hpe") -> dict:
     rebind(f"{package}.metrics.losses", _METRICS, M)
     rebind(f"{package}.metrics.regularizations", ("smoothness_regularization", "measure_bones_length") + _CONSISTENCY, M)
     rebind(f"{package}.metrics.utils", ("measure_bones_length",), M)
-    rebind(f"{package}.metrics.mean_joint_errors", ("mpjpe_error", "p_mpjpe"), M)
+    rebind(f"{package}.metrics.mean_joint_errors", ("mpjpe_error", "p_mpjpe", "mse_error", "jointwise_error", "jointwise_mse",
+                                                    "coordwise_error", "segments_len_err"), M)
     rebind(f"{package}.metrics.pck", ("keypoint_3d_pck", "keypoint_3d_auc"), M)
     return replaced
 

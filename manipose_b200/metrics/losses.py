@@ -40,10 +40,14 @@ def weighted_mpjpe_loss(prediction: torch.Tensor, target: torch.Tensor, weights:
     hyp, y = _as_hyp(prediction, target)
     if dims is None:
         if hyp.shape[1] != 1:
+            if torch.is_grad_enabled() and prediction.requires_grad:
+                # every hypothesis contributes (no winner): fold H into the batch, so that each (clip, hypothesis) is a single-
+                # hypothesis problem against its clip's target; the mean over (B*H, L) is the mean over (B, H, L)
+                b, h = hyp.shape[:2]
+                yy = y.unsqueeze(1).expand(b, h, *y.shape[1:]).reshape(b * h, *y.shape[1:])
+                return ops.loss_terms(hyp.reshape(b * h, 1, *hyp.shape[2:]), None, yy, weights, False)[0][L.MP_TERM_WTA]
             # mean over B,H,L of the per-hypothesis error == mean of per_hyp
             _, _, per_hyp = ops.wta_fwd(hyp, y, weights, False, per_hyp=True)
-            if torch.is_grad_enabled() and prediction.requires_grad:
-                raise NotImplementedError("weighted_mpjpe_loss over K > 1 hypotheses with gradients is not built")
             return per_hyp.mean()
         return ops.loss_terms(hyp, None, y, weights, False)[0][L.MP_TERM_WTA]
     if list(dims) == [3] and prediction.dim() == 5:
@@ -57,11 +61,18 @@ def weighted_mse_loss(prediction: torch.Tensor, target: torch.Tensor, weights: t
                       dims: Optional[List[int]] = None) -> torch.Tensor:
     """losses.py:46-72 (squared distances)."""
     if weights is None:
-        raise NotImplementedError("weighted_mse_loss without weights is F.mse_loss in the reference; not on the hot path")
+        if dims is not None:
+            raise NotImplementedError("weighted_mse_loss(weights=None, dims=...) is F.mse_loss over everything in the reference (dims ignored)")
+        # F.mse_loss(prediction, target) (losses.py:57-58) = the mean over every coordinate = the weighted form with unit weights
+        weights = torch.ones(target.shape[-2])
     assert weights.shape[0] == target.shape[-2]
     hyp, y = _as_hyp(prediction, target)
     if dims is None and hyp.shape[1] == 1:
         return ops.loss_terms(hyp, None, y, weights, True)[0][L.MP_TERM_WTA]
+    if dims is None:
+        b, h = hyp.shape[:2]
+        yy = y.unsqueeze(1).expand(b, h, *y.shape[1:]).reshape(b * h, *y.shape[1:])
+        return ops.loss_terms(hyp.reshape(b * h, 1, *hyp.shape[2:]), None, yy, weights, True)[0][L.MP_TERM_WTA]
     if dims is not None and list(dims) == [4, 3] and prediction.dim() == 5 and not (torch.is_grad_enabled() and prediction.requires_grad):
         return ops.wta_fwd(hyp, y, weights, True, per_hyp=True)[2]
     raise NotImplementedError(f"weighted_mse_loss(dims={dims}) on shape {tuple(prediction.shape)} is not built")

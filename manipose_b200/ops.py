@@ -303,6 +303,27 @@ def pck_auc(pred, gt, threshold=150.0):
     return out
 
 
+def point_errors(pred: torch.Tensor, gt: torch.Tensor, mode: int, cols: int = 0, scale: float = 1.0, per_elem: bool = False):
+    """Per-point / per-column errors (mean_joint_errors.py:31-141) in one streaming pass.  mode L2 / SQ: pred, gt [..., 3] points;
+    ABS / DIFF: scalars.  Returns (per-element errors [n] or None, scale * column sums [cols] or None)."""
+    _need_cuda(pred, gt)
+    pred, gt = _f32(pred), _f32(gt)
+    if pred.numel() != gt.numel():
+        raise AssertionError("batch_imp and batch_gt must hold the same number of values")
+    vec = 3 if mode in (L.MP_ERR_L2, L.MP_ERR_SQ) else 1
+    n = pred.numel() // vec
+    dev = pred.device
+    elems = torch.empty(n, dtype=torch.float32, device=dev) if per_elem else None
+    col = torch.empty(cols, dtype=torch.float32, device=dev) if cols > 0 else None
+    c = max(cols, 1)
+    nbytes = L.load().mp_point_errors_workspace_bytes(n, c) if cols > 0 else 0
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    rc = L.load().mp_point_errors(L.ptr(pred), L.ptr(gt), n, c, mode, float(scale), L.ptr(elems), L.ptr(col), L.ptr(ws), nbytes, L.stream_ptr())
+    L.check(rc, "mp_point_errors")
+    _count(2 if cols > 0 else 1)
+    return elems, col
+
+
 def pose_consistency(poses: torch.Tensor, with_bone_lengths: bool = False):
     """poses [B, L, 17, 3] -> (seg_mean [B,16], seg_var [B,16] (unbiased, over time), sym_abs [B,6], sym_sq [B,6], bone_len [B,16,L] | None)."""
     _need_cuda(poses)

@@ -652,6 +652,47 @@ def evaluate(batches, sd: Dict[str, torch.Tensor], tta: bool, return_hyps: bool 
     return all_pred, all_target, performance, oracle_total / (n * l) * 1000, psoracle_total / (n * l) * 1000, all_oracle
 
 
+def _agg(mode: str):
+    """mean_joint_errors.py:8-28: 'average' -> torch.mean, 'sum' -> torch.sum, 'no_agg' -> identity."""
+    if mode == "average":
+        return torch.mean
+    if mode == "sum":
+        return torch.sum
+    if mode == "no_agg":
+        return lambda x, dim=None: x
+    raise ValueError(f"Unexpected value for 'mode' encoutered: {mode}.")
+
+
+def mse_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
+    """mean_joint_errors.py:39-44: squared distance of every 3-D point."""
+    return _agg(mode)(torch.sum((gt.reshape(-1, 3) - pred.reshape(-1, 3)) ** 2, dim=1))
+
+
+def jointwise_error(pred: torch.Tensor, gt: torch.Tensor, mode: str, squared: bool = False):
+    """mean_joint_errors.py:47-80 (jointwise_error; squared=True: jointwise_mse): per-joint error aggregated over dim 0 -> [J]."""
+    j = gt.shape[-2]
+    d = gt.contiguous().view(-1, j, 3) - pred.contiguous().view(-1, j, 3)
+    e = torch.sum(d ** 2, dim=2) if squared else torch.norm(d, 2, 2)
+    return _agg(mode)(e, dim=0)
+
+
+def coordwise_error(pred: torch.Tensor, gt: torch.Tensor, mode: str):
+    """mean_joint_errors.py:132-141: |gt - pred| per coordinate aggregated over every point -> [3]."""
+    return _agg(mode)(torch.abs(gt.contiguous().view(-1, 3) - pred.contiguous().view(-1, 3)), dim=0)
+
+
+def segments_len_err(pred_jc: torch.Tensor, gt_jc: torch.Tensor, mode: str, signed: bool = True, bones=None):
+    """mean_joint_errors.py:83-129: gt - predicted bone lengths, inputs [B,3,J,L] -> scalar, or [B*L, num_bones] for 'no_agg'."""
+    bones = H36M17_BONES if bones is None else bones
+    b, _, _, l = pred_jc.shape
+    pl = measure_bones_length(pred_jc, bones).permute(0, 2, 1).reshape(b * l, -1)
+    gl = measure_bones_length(gt_jc, bones).permute(0, 2, 1).reshape(b * l, -1)
+    diff = gl - pl
+    if not signed:
+        diff = torch.abs(diff)
+    return _agg(mode)(diff)
+
+
 # --------------------------------------------------------------------------------------
 # SURVEY.md §8f-3: pose-consistency metrics (bone lengths, MPSCE, MPSSE)
 # --------------------------------------------------------------------------------------

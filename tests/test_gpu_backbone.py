@@ -200,6 +200,57 @@ def test_temporal_attention_outlier_keys_take_the_exact_softmax_path(dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("c,heads,n_seq,seq_len", [(512, 8, 6, 17), (512, 8, 3, 243), (128, 8, 5, 16)])
+def test_block_attention_mlp_forward_on_their_own(c, heads, n_seq, seq_len, dtype):
+    """Block / Attention / Mlp.forward as standalone entry points (mix_ste.py:216-222, 255-282, 352-358) against the fp32 oracle
+    restatement of the same modules on the same parameters: 16-bit operand rounding is the only difference."""
+    from manipose_b200.architectures.mix_ste import Block
+    torch.manual_seed(c + seq_len)
+    blk = Block(dim=c, num_heads=heads, mlp_ratio=2.0, qkv_bias=True, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).cuda().eval()
+    with torch.no_grad():
+        for p in blk.parameters():                      # LayerNorm affine parameters away from (1, 0)
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    for mod in (blk, blk.attn, blk.mlp):
+        mod.compute_dtype = dtype
+    sd = {"b." + k: v.detach().cpu() for k, v in blk.state_dict().items()}
+    x = torch.randn(n_seq, seq_len, c, generator=torch.Generator().manual_seed(1))
+    tol = 2e-2 if dtype == "bf16" else 3e-3
+    with torch.no_grad():
+        got = blk(x.cuda()).cpu()
+        want = O.block(x, sd, "b", heads)
+        assert got.shape == want.shape
+        assert _rel(got - x, want - x) <= tol          # the two branches, not the residual that dominates the norm
+        got = blk.attn(x.cuda()).cpu()
+        assert _rel(got, O.attention(x, sd, "b.attn", heads)) <= tol
+        got = blk.mlp(x.cuda()).cpu()
+        want = F.linear(F.gelu(F.linear(x, sd["b.mlp.fc1.weight"], sd["b.mlp.fc1.bias"])), sd["b.mlp.fc2.weight"], sd["b.mlp.fc2.bias"])
+        assert _rel(got, want) <= tol
+    with pytest.raises(NotImplementedError):           # gradients only flow through the enclosing model
+        blk(x.cuda())
+
+
+def test_mclhead_forward_on_its_own():
+    """MCLHead.forward (rmcl_manifold_mix_ste.py:290-298) through mp_heads_fwd with K = 1 and no shared post-norm: fp32 like the reference."""
+    from manipose_b200.architectures.rmcl_manifold_mix_ste import MCLHead
+    torch.manual_seed(3)
+    head = MCLHead(embed_dim=512, out_dim=6, num_joints=17).cuda().eval()
+    with torch.no_grad():
+        head.norm.weight.add_(0.1 * torch.randn_like(head.norm.weight))
+        head.norm.bias.add_(0.5 * torch.randn_like(head.norm.bias))
+    x = torch.randn(3, 9, 17, 512, generator=torch.Generator().manual_seed(2))
+    sd = {k: v.detach().cpu() for k, v in head.state_dict().items()}
+    with torch.no_grad():
+        rot, logit = head(x.cuda())
+    h = F.layer_norm(x, (512,), sd["norm.weight"], sd["norm.bias"], 1e-5)
+    pe = F.linear(h, sd["prediction_head.weight"], sd["prediction_head.bias"])
+    want_logit = F.linear(pe[..., -1], sd["score_head.weight"], sd["score_head.bias"])
+    assert rot.shape == (3, 9, 17, 6) and logit.shape == (3, 9, 1)
+    torch.testing.assert_close(rot.cpu(), pe[..., :-1], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(logit.cpu(), want_logit, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("c", [512, 128])
 def test_layernorm_family(c, dtype):
     from manipose_b200 import ops
@@ -429,3 +480,42 @@ def test_evaluate_drop_in(tta):
     assert abs(float(got[3]) - float(ref[3])) <= 0.25 and abs(float(got[4]) - float(ref[4])) <= 0.25
     with pytest.raises(TypeError):
         evaluate(torch.nn.Linear(2, 2), batches, "cuda", cfg, sk)
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_unmodified_reference_evaluate_drives_the_cuda_model(tta):
+    """The drop-in claim demonstrated rather than asserted: the UNMODIFIED hpe/eval_utils.py::evaluate (:16-203), imported from the
+    reference tree after ``manipose_b200.install()``, runs over the CUDA model — its isinstance checks, model.aggregate /
+    concat_hyp_and_scores calls, pose_flip and mpjpe_error all resolve to this package — and returns what the oracle's restatement of
+    the same function returns on the same hypotheses.  Needs a B200 AND the reference checkout (skipped on the driver's GPU box,
+    where /root/reference does not exist; run it where both are present)."""
+    from oracle.ref_loader import reference_available, load_reference
+    if not reference_available():
+        pytest.skip("/root/reference not present on this box")
+    import importlib
+    import types
+    import manipose_b200 as mb
+    load_reference()
+    replaced = mb.install()
+    try:
+        from tests.test_oracle_vs_reference import _load_reference_evaluate
+        ref_eval = _load_reference_evaluate()
+        T, K = 27, 5
+        m, sd = _init42_model(T, K, "fp16")
+        g = torch.Generator().manual_seed(21)
+        batches = [(0.3 * torch.randn(b, T, 17, 2, generator=g), 0.3 * torch.randn(b, T, 17, 3, generator=g)) for b in (3, 2)]
+        cfg = types.SimpleNamespace(train=types.SimpleNamespace(tta=tta))
+        got = ref_eval.evaluate(m, batches, "cuda", cfg, mb.h36m17_skeleton(), return_hyps=False, compute_oracle=True)
+
+        def device_forward(x):
+            with torch.no_grad():
+                p, s = m(x.cuda())
+            return p.cpu(), s.cpu()
+
+        want = O.evaluate(batches, sd, tta, return_hyps=False, compute_oracle=True, forward=device_forward)
+        for i in (2, 3, 4):
+            assert abs(float(got[i]) - float(want[i])) <= 1e-5 * abs(float(want[i])), i
+    finally:
+        for qual, obj in replaced.items():
+            modname, attr = qual.rsplit(".", 1)
+            setattr(importlib.import_module(modname), attr, obj)

@@ -160,6 +160,69 @@ def test_full_size_loss_properties():
     torch.testing.assert_close(got_tot.cpu(), ref_tot, rtol=1e-5, atol=1e-7)
 
 
+# ------------------------------------------------------------------------------------------------ joint-error analytics
+@pytest.mark.parametrize("shape", [(5, 27, 17, 3), (1, 1, 17, 3), (64, 243, 17, 3)])
+def test_joint_error_analytics_vs_oracle(shape):
+    """mse_error / jointwise_error / jointwise_mse / coordwise_error / segments_len_err / mpjpe_error(no_agg) through mp_point_errors,
+    in millimetres like the drivers (main_h36m_lifting.py:975-1057), inputs on the CPU (moved by the functions) or on the device."""
+    import manipose_b200 as mb
+    from manipose_b200 import metrics as M
+    sk = mb.h36m17_skeleton()
+    gen = torch.Generator().manual_seed(sum(shape))
+    pred = 300.0 * torch.randn(*shape, generator=gen)
+    gt = 300.0 * torch.randn(*shape, generator=gen)
+    pc, gc = pred.cuda(), gt.cuda()
+    for mode in ("average", "sum"):
+        rt = dict(rtol=2e-6, atol=0.0)       # fp64 partial sums here, fp32 pairwise sums in torch: agreement to fp32 rounding of the result
+        torch.testing.assert_close(M.mse_error(pc, gc, mode).cpu(), O.mse_error(pred, gt, mode), **rt)
+        torch.testing.assert_close(M.jointwise_error(pc, gc, mode).cpu(), O.jointwise_error(pred, gt, mode), **rt)
+        torch.testing.assert_close(M.jointwise_mse(pc, gc, mode).cpu(), O.jointwise_error(pred, gt, mode, squared=True), **rt)
+        torch.testing.assert_close(M.coordwise_error(pc, gc, mode).cpu(), O.coordwise_error(pred, gt, mode), **rt)
+        for signed in (True, False):
+            got = M.segments_len_err(batch_imp=pc.permute(0, 3, 2, 1), batch_gt=gc.permute(0, 3, 2, 1), skeleton=sk, mode=mode, signed=signed)
+            want = O.segments_len_err(pred.permute(0, 3, 2, 1), gt.permute(0, 3, 2, 1), mode, signed)
+            torch.testing.assert_close(got.cpu(), want, rtol=2e-5, atol=1e-3 if signed else 0.0)   # the signed sum cancels: absolute
+    # element-wise modes: the same fp32 operations per element -> equal up to sqrt rounding (1 ulp)
+    torch.testing.assert_close(M.mpjpe_error(pc, gc, "no_agg").cpu(), O.mpjpe_error(pred, gt, "no_agg"), rtol=2e-7, atol=0.0)
+    assert torch.equal(M.mse_error(pc, gc, "no_agg").cpu(), O.mse_error(pred, gt, "no_agg"))
+    torch.testing.assert_close(M.jointwise_error(pc, gc, "no_agg").cpu(), O.jointwise_error(pred, gt, "no_agg"), rtol=2e-7, atol=0.0)
+    assert torch.equal(M.coordwise_error(pc, gc, "no_agg").cpu(), O.coordwise_error(pred, gt, "no_agg"))
+    got = M.segments_len_err(batch_imp=pc.permute(0, 3, 2, 1), batch_gt=gc.permute(0, 3, 2, 1), skeleton=sk, mode="no_agg")
+    torch.testing.assert_close(got.cpu(), O.segments_len_err(pred.permute(0, 3, 2, 1), gt.permute(0, 3, 2, 1), "no_agg"), rtol=0.0, atol=1e-4)
+    # CPU tensors and numpy arrays are accepted (moved to the device), like the reference's callers pass them
+    torch.testing.assert_close(M.jointwise_error(pred, gt.numpy(), "average").cpu(), O.jointwise_error(pred, gt, "average"), rtol=2e-6, atol=0.0)
+    assert abs(M.keypoint_3d_pck(pred.numpy().reshape(-1, 17, 3), gt.numpy().reshape(-1, 17, 3)) - O.keypoint_3d_pck(pred.reshape(-1, 17, 3), gt.reshape(-1, 17, 3))) <= 1e-4
+    with pytest.raises(ValueError):
+        M.jointwise_error(pc, gc, "median")
+
+
+def test_weighted_losses_without_weights_and_over_all_hypotheses():
+    """Reference behaviours that used to raise here: weighted_mse_loss(weights=None) = F.mse_loss (losses.py:57-58) and
+    weighted_mpjpe_loss over K > 1 hypotheses with gradients (losses.py:14-43, every hypothesis contributes)."""
+    import torch.nn.functional as F
+    from manipose_b200 import metrics as M
+    gen = torch.Generator().manual_seed(3)
+    hyp = (0.3 * torch.randn(3, 4, 9, 17, 3, generator=gen)).cuda()
+    y = (0.3 * torch.randn(3, 9, 17, 3, generator=gen)).cuda()
+    w = M.STANDARD_H36M_WEIGHTS
+    one = hyp[:, 0].clone().requires_grad_()
+    got = M.weighted_mse_loss(one, y)
+    ref_in = hyp[:, 0].clone().requires_grad_()
+    want = F.mse_loss(ref_in, y)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=0.0)
+    got.backward()
+    want.backward()
+    torch.testing.assert_close(one.grad, ref_in.grad, rtol=1e-4, atol=1e-9)
+    h1 = hyp.clone().requires_grad_()
+    got = M.weighted_mpjpe_loss(h1, y[:, None].expand_as(hyp), w)
+    h2 = hyp.clone().requires_grad_()
+    want = torch.mean(w.cuda()[None, None, None, :] * torch.norm(h2 - y[:, None], p=2, dim=-1))
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=0.0)
+    got.backward()
+    want.backward()
+    torch.testing.assert_close(h1.grad, h2.grad, rtol=1e-4, atol=1e-9)
+
+
 # ------------------------------------------------------------------------------------------------ pose consistency (SURVEY.md §8f-3)
 def _consistency_checks(poses_cpu, want, rtol=2e-5):
     import manipose_b200 as mb

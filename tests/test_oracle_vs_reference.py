@@ -178,6 +178,24 @@ def test_pose_flip_vs_reference(ref):
     assert torch.equal(O.pose_flip(x), want)
 
 
+def test_joint_error_analytics_match_reference(ref):
+    """SURVEY.md §8f-3, the rest of mean_joint_errors.py:39-141: mse_error, jointwise_error, jointwise_mse, coordwise_error and
+    segments_len_err in the layouts the drivers call them with (main_h36m_lifting.py:975-1057)."""
+    sk = ref.make_skeleton()
+    gen = torch.Generator().manual_seed(17)
+    pred = 300.0 * torch.randn(5, 27, 17, 3, generator=gen)
+    gt = 300.0 * torch.randn(5, 27, 17, 3, generator=gen)
+    M = ref.metrics
+    for mode in ("average", "sum", "no_agg"):
+        assert torch.equal(O.mse_error(pred, gt, mode), M.mse_error(pred, gt, mode))
+        assert torch.equal(O.jointwise_error(pred, gt, mode), M.jointwise_error(pred, gt, mode))
+        assert torch.equal(O.jointwise_error(pred, gt, mode, squared=True), M.jointwise_mse(pred, gt, mode))
+        assert torch.equal(O.coordwise_error(pred, gt, mode), M.coordwise_error(pred, gt, mode))
+        for signed in (True, False):
+            want = M.segments_len_err(batch_imp=pred.permute(0, 3, 2, 1), batch_gt=gt.permute(0, 3, 2, 1), skeleton=sk, mode=mode, signed=signed)
+            assert torch.equal(O.segments_len_err(pred.permute(0, 3, 2, 1), gt.permute(0, 3, 2, 1), mode, signed), want)
+
+
 @pytest.mark.parametrize("b,l", [(3, 27), (1, 243)])
 def test_pose_consistency_metrics_match_reference(ref, b, l):
     """measure_bones_length / segments_time_consistency (MPSCE) / sagittal_symmetry (MPSSE) restatements."""
