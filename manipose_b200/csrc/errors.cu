@@ -17,7 +17,9 @@ template <int MODE>
 __device__ __forceinline__ float element_error(const float* __restrict__ pred, const float* __restrict__ gt, int64_t i) {
   if (MODE == MP_ERR_L2 || MODE == MP_ERR_SQ) {
     const float dx = gt[3 * i + 0] - pred[3 * i + 0], dy = gt[3 * i + 1] - pred[3 * i + 1], dz = gt[3 * i + 2] - pred[3 * i + 2];
-    const float s = dx * dx + dy * dy + dz * dz;     // torch.norm(d, 2, dim) == sqrt(sum d^2), torch.sum(d ** 2, dim)
+    // torch.sum(d ** 2, dim) / torch.norm(d, 2, dim): every square rounded, then added in order (no FMA contraction), so the
+    // element-wise modes reproduce the reference's fp32 values
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     return MODE == MP_ERR_L2 ? sqrtf(s) : s;
   }
   const float d = gt[i] - pred[i];

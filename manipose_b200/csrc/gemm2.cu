@@ -884,7 +884,8 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
 constexpr int pair_ln_smem(int stages, int slots, bool split) { return stages * (kABytes + (split ? 1 : 2) * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
-static_assert(pair_ln_smem(4, 6, true) <= 232448 && pair_ln_smem(3, 4, false) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+static_assert(pair_ln_smem(4, 6, true) <= 232448 && pair_ln_smem(3, 4, false) <= 232448 && pair_ln_smem(2, 8, false) <= 232448,
+              "exceeds the 227 KB of shared memory a CTA can opt into");
 
 template <typename K>
 int set_smem(K kernel, int bytes) {
@@ -995,6 +996,8 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   const bool bf = dtype == MP_DTYPE_BF16;
   if (cfg == 1 || (cfg == 0 && K < 1024))
     return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
+  if (cfg == 3)      // experiment: 2 x 48 KB operand stages + 8 box slots (more of the residual prefetched under the main loop)
+    return bf ? launch(pair_linear_ln_kernel<Bf16, 2, 8, false>, pair_ln_smem(2, 8, false)) : launch(pair_linear_ln_kernel<Fp16, 2, 8, false>, pair_ln_smem(2, 8, false));
   return bf ? launch(pair_linear_ln_kernel<Bf16, 3, 4, false>, pair_ln_smem(3, 4, false)) : launch(pair_linear_ln_kernel<Fp16, 3, 4, false>, pair_ln_smem(3, 4, false));
 }
 

@@ -377,9 +377,26 @@ def test_forward_vs_reference_golden():
     with torch.no_grad():
         poses, scores = m(e["x"].cuda())
     assert float((scores.cpu() - e["scores"]).abs().max()) <= BACKBONE_TOL["fp16"]["scores"]
-    # poses: compare where the 6-D -> SO(3) map is well conditioned (median error), the tail is dominated by near-degenerate joints
+    # rot6d straight out of the heads: relative L2 and worst element
     err = (poses.cpu() - e["poses"]).norm(dim=-1)
+    # conditioning of the 6-D -> SO(3) map per joint: the Gram-Schmidt normalisations divide by |a1| and by the norm of the part of a2
+    # orthogonal to a1, and a joint's position inherits the rotations of its ancestors, so the amplification of a joint is the largest
+    # 1 / min(|a1|, |a2 perp|) along its chain to the root
+    r = e["rot6d"]
+    a1, a2 = r[..., 0:3], r[..., 3:6]
+    n1 = a1 / a1.norm(dim=-1, keepdim=True)
+    a2p = a2 - (n1 * a2).sum(-1, keepdim=True) * n1
+    amp = 1.0 / torch.minimum(a1.norm(dim=-1), a2p.norm(dim=-1))
+    parents = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15]
+    chain = amp.clone()
+    for j in range(1, 17):
+        chain[..., j] = torch.maximum(chain[..., j], chain[..., parents[j]])
+    well = chain <= chain.median()
+    q = lambda t, f: float(t.flatten().kthvalue(max(1, int(f * t.numel())))[0])
+    print(f"pose error vs the reference fixture: median {float(err.median()):.2e}, p99 {q(err, .99):.2e}, max {float(err.max()):.2e}; "
+          f"well-conditioned half: p99 {q(err[well], .99):.2e}, max {float(err[well].max()):.2e}")
     assert float(err.median()) <= 2e-3
+    assert q(err[well], .99) <= 6e-3 and q(err, .99) <= 3e-2         # the tail, not only the median: a broken kernel does not hide in it
 
 
 def test_default_config_forward_runs_at_t243():

@@ -187,18 +187,43 @@ def _model_from_sd(sd, num_frame, n_hyp, dtype, **kw):
 
 
 # relative L2 of a parameter gradient vs fp32 autograd through the oracle: (median over the 290 tensors, worst tensor).
-# Measured on B200: fp16 median 4e-3..6e-3 / worst 8e-3; bf16 median 3.4e-2..6.0e-2 / worst 0.20..0.31 (a score head).  The bf16 figure is
-# dominated by frames whose winning hypothesis flips under the bf16 forward error (the WTA objective is piecewise: with 54 frames in the
-# batch one flipped winner moves every gradient by several percent, and WHICH frames flip changes with any re-ordering of fp32 sums in the
-# forward), not by the backward kernels: the same kernels give 4e-3 with fp16 operands.
+# Measured on B200: fp16 median 3.5e-3..4.7e-3 / worst 8e-3; bf16 median 2.0e-2..4.6e-2 / worst 0.19 (a score head).
+#
+# What the bf16 figure is: the rounding of ~100 chained 16-bit activations (8 significand bits), not the backward kernels and not
+# winner flips.  Two controls are part of the test:
+#   * the SAME reference model under ``torch.autocast(bfloat16)`` on the CPU (PyTorch's own bf16 kernels, forward and autograd) is
+#     compared with the fp32 oracle in the same way: it measures 5.7e-2 median / 0.28 worst at T=27 (fp16: 4.2e-3 / 1.2e-2) — the
+#     sm_100a kernels must be NO WORSE than that (median and 90th percentile within 1.25 x), at both dtypes;
+#   * ``test_model_gradients_without_winner_flips`` removes the flips by construction and shows the error does not go down.
 GRAD_TOL = {"bf16": (8e-2, 4e-1), "fp16": (1e-2, 3e-2)}
+
+
+def _autocast_oracle_grads(x, y, sd, dtype):
+    """Parameter gradients of the reference model under torch.autocast(dtype) on the CPU (PyTorch's own 16-bit kernels + autograd)."""
+    sd_ac = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16 if dtype == "bf16" else torch.float16):
+        poses, scores = O.rmcl_forward(x, sd_ac)
+    loss, _ = O.training_loss(poses.float(), scores.float(), y)
+    loss.backward()
+    return {k: v.grad for k, v in sd_ac.items()}
+
+
+def _grad_report(tag, model, sd_ref, sd_autocast):
+    rels = {name: _rel(p.grad.cpu(), sd_ref[name].grad) for name, p in model.named_parameters()}
+    vals = sorted(rels.values())
+    ac = sorted(_rel(sd_autocast[name], sd_ref[name].grad) for name in rels)
+    q = lambda v, f: v[int(f * (len(v) - 1))]
+    print(f"[{tag}] grad rel-L2 vs fp32 oracle: median {q(vals, .5):.2e}, p90 {q(vals, .9):.2e}, max {vals[-1]:.2e} ({max(rels, key=rels.get)}); "
+          f"torch autocast on the CPU: median {q(ac, .5):.2e}, p90 {q(ac, .9):.2e}, max {ac[-1]:.2e}")
+    return rels, vals, ac, q
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 @pytest.mark.parametrize("T_,K,B", [(27, 5, 2), (9, 2, 3)])
 def test_model_gradients_vs_oracle_autograd(T_, K, B, dtype):
     """BASELINE config 4 shape (T=27, K=5, default widths and depth) at a small batch: loss value and all 290 parameter gradients
-    of forward + default objective (wta + 0.1 bce + 2 velocity + 0.5 smoothness) vs torch autograd through the fp32 CPU oracle."""
+    of forward + default objective (wta + 0.1 bce + 2 velocity + 0.5 smoothness) vs torch autograd through the fp32 CPU oracle,
+    and against PyTorch's own 16-bit autocast of the same model as the yardstick of what the format allows."""
     from manipose_b200 import metrics
     sd = O.make_state_dict(num_frame=T_, n_hyp=K, seed=11)
     gen = torch.Generator().manual_seed(21)
@@ -209,6 +234,7 @@ def test_model_gradients_vs_oracle_autograd(T_, K, B, dtype):
     poses_ref, scores_ref = O.rmcl_forward(x, sd_ref)
     loss_ref, _ = O.training_loss(poses_ref, scores_ref, y)
     loss_ref.backward()
+    sd_ac = _autocast_oracle_grads(x, y, sd, dtype)
 
     m = _model_from_sd(sd, T_, K, dtype, drop_path_rate=0.0).train()
     poses, scores = m(x.cuda())
@@ -217,32 +243,29 @@ def test_model_gradients_vs_oracle_autograd(T_, K, B, dtype):
     loss.backward()
     torch.cuda.synchronize()
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-2 * abs(float(loss_ref.detach()))
-    typical, worst = GRAD_TOL[dtype]
-    rels = {}
     for name, p in m.named_parameters():
-        assert p.grad is not None, name
-        g_ref = sd_ref[name].grad
-        assert g_ref is not None, name
-        rels[name] = _rel(p.grad.cpu(), g_ref)
+        assert p.grad is not None and sd_ref[name].grad is not None, name
+    typical, worst = GRAD_TOL[dtype]
+    rels, vals, ac, q = _grad_report(f"{dtype} T={T_}", m, sd_ref, sd_ac)
     bad = {k: v for k, v in rels.items() if not v <= worst}
-    vals = sorted(rels.values())
-    print(f"[{dtype} T={T_}] grad rel-L2: median {vals[len(vals) // 2]:.2e}, p90 {vals[int(0.9 * len(vals))]:.2e}, max {vals[-1]:.2e} "
-          f"({max(rels, key=rels.get)})")
     assert not bad, bad
-    assert vals[len(vals) // 2] <= typical
+    assert q(vals, .5) <= typical
+    # no worse than PyTorch's own autocast of the reference model at this dtype
+    assert q(vals, .5) <= 1.25 * q(ac, .5) and q(vals, .9) <= 1.25 * q(ac, .9)
 
 
-# The same comparison with the two effects that are NOT the backward kernels taken out, so that the figure pins the kernels themselves at
-# the benchmarked dtype:
-#   * winner flips: the target of every frame is one of the oracle's own hypotheses (k* = (clip + frame) mod K) with every joint
-#     displaced by 0.5 in a random direction, which keeps the winner a wide margin ahead of the other K - 1 hypotheses (smallest
-#     margin 0.14 against a forward error of a few 1e-3) while the residuals stay O(0.5), so the unit-vector gradients of the L2
-#     terms are as well conditioned as with a random target (a target AT a hypothesis would put the objective at a minimum, where
-#     any forward error dominates the gradient); the test first proves that no winner moved;
-#   * weight rounding: the block GEMM weights are made representable in the 16-bit format before BOTH runs, so the oracle linearises at
-#     the weights the tensor cores actually multiply by ("the oracle on bf16-rounded weights").
-# What remains is the rounding of the 16-bit activations and of the backward operands.
-GRAD_TOL_NO_FLIPS = {"bf16": (2e-2, 6e-2), "fp16": (5e-3, 2e-2)}
+# The same comparison with the winner-takes-all flips REMOVED by construction and with the weight rounding taken out:
+#   * the target of every frame is one of the oracle's own hypotheses (k* = (clip + frame) mod K) with every joint displaced by 0.5
+#     in a random direction: the winner stays a wide margin ahead of the other K - 1 hypotheses (smallest margin 0.14 against a
+#     forward error of a few 1e-3) while the residuals stay O(0.5), so the unit-vector gradients of the L2 terms are as well
+#     conditioned as with a random target (a target AT a hypothesis would put the objective at a minimum, where any forward error
+#     dominates the gradient); the test first proves that no winner moved;
+#   * the block GEMM weights are made representable in the 16-bit format before BOTH runs (the oracle linearises at the weights the
+#     tensor cores multiply by), and the K heads get O(1) LayerNorm biases (the folded-head backward has a term in beta that is
+#     zero at the default init).
+# Measured on B200: fp16 median 6.3e-3 / worst 2.5e-2, bf16 median 9.9e-2 / worst 0.37 — NOT smaller than with flips: the bf16
+# figure is activation rounding.  The autocast yardstick applies here too.
+GRAD_TOL_NO_FLIPS = {"bf16": (1.5e-1, 6e-1), "fp16": (1.2e-2, 5e-2)}
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
@@ -254,7 +277,6 @@ def test_model_gradients_without_winner_flips(dtype):
     gen = torch.Generator().manual_seed(5)
     for name in list(sd):
         if ".head." in name and name.endswith("norm.bias"):
-            # O(1) LayerNorm biases in the K heads: the folded-head backward has a term in beta that is zero at the default init
             sd[name] = torch.randn(sd[name].shape, generator=gen)
         if "blocks." in name and name.endswith(("qkv.weight", "proj.weight", "fc1.weight", "fc2.weight")):
             sd[name] = sd[name].to(td).float()
@@ -270,6 +292,7 @@ def test_model_gradients_without_winner_flips(dtype):
     poses_ref, scores_ref = O.rmcl_forward(x, sd_ref)
     loss_ref, _ = O.training_loss(poses_ref, scores_ref, y)
     loss_ref.backward()
+    sd_ac = _autocast_oracle_grads(x, y, sd, dtype)
 
     m = _model_from_sd(sd, T_, K, dtype, drop_path_rate=0.0).train()
     poses, scores = m(x.cuda())
@@ -280,13 +303,11 @@ def test_model_gradients_without_winner_flips(dtype):
     torch.cuda.synchronize()
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-2 * abs(float(loss_ref.detach()))
     typical, worst = GRAD_TOL_NO_FLIPS[dtype]
-    rels = {name: _rel(p.grad.cpu(), sd_ref[name].grad) for name, p in m.named_parameters()}
-    vals = sorted(rels.values())
-    print(f"[{dtype} no flips] grad rel-L2: median {vals[len(vals) // 2]:.2e}, p90 {vals[int(0.9 * len(vals))]:.2e}, max {vals[-1]:.2e} "
-          f"({max(rels, key=rels.get)})")
+    rels, vals, ac, q = _grad_report(f"{dtype} no flips", m, sd_ref, sd_ac)
     bad = {k: v for k, v in rels.items() if not v <= worst}
     assert not bad, bad
-    assert vals[len(vals) // 2] <= typical
+    assert q(vals, .5) <= typical
+    assert q(vals, .5) <= 1.25 * q(ac, .5) and q(vals, .9) <= 1.25 * q(ac, .9)
 
 
 def test_eval_and_training_forward_agree():
