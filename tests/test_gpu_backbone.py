@@ -382,7 +382,8 @@ def test_forward_vs_reference_golden():
     # conditioning of the 6-D -> SO(3) map per joint: the Gram-Schmidt normalisations divide by |a1| and by the norm of the part of a2
     # orthogonal to a1, and a joint's position inherits the rotations of its ancestors, so the amplification of a joint is the largest
     # 1 / min(|a1|, |a2 perp|) along its chain to the root
-    r = e["rot6d"]
+    with torch.no_grad():
+        r = O.rotations_module(e["x"], sd)[0]      # the oracle's fp32 6-D vectors (pinned to the reference), for the conditioning only
     a1, a2 = r[..., 0:3], r[..., 3:6]
     n1 = a1 / a1.norm(dim=-1, keepdim=True)
     a2p = a2 - (n1 * a2).sum(-1, keepdim=True) * n1
