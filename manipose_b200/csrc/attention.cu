@@ -625,6 +625,265 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ temporal, tcgen05, P in TMEM
+// The T = 243 kernel, third version.  attn_temporal_tc2_kernel above serialises the phases of an item (S = Q K^T, softmax, O = P V,
+// drain) because P is staged through 128 KB of shared memory per item, which leaves room for ONE item's operands and makes the
+// two 128-query tiles run in lockstep: the tensor pipe waits for the softmax, the softmax warps wait for the MMAs and the loads.
+// Here the softmax writes P (16-bit, two values per column) back into TENSOR MEMORY over the S it has just read
+// (tcgen05.st) and O = P V takes its A operand from there (tcgen05.mma with a TMEM A operand, SASS UTCHMMA ... tmem[A]):
+//   * no shared memory for P: the operands of TWO items are resident (2 x {Q0, Q1, K, V} = 192 KB), loaded by their own warp, so an
+//     item's loads never sit on the critical path;
+//   * the two query tiles are DE-PHASED: the MMA thread issues S0(n), PV1(n-1), S1(n), PV0(n), ... so the softmax of one tile runs
+//     while the other tile is in its MMAs / drain, and the tensor pipe, the MUFU and the TMEM read port are shared instead of
+//     alternating between busy and idle.
+// TMEM: region g (256 columns) = S_g [128 x Tp] fp32 -> P_g in columns [0, Tp/2) -> O_g [128 x 64] fp32 in columns [128, 192).
+// The softmax keeps the packed P row in registers until the whole S row has been read (the guarded shift estimate may ask for a
+// second pass over S, so S must stay intact until then), then stores it with Tp/32 tcgen05.st.x16.
+constexpr int kTc3Threads = 320;   // 2 x 4 softmax warps + MMA warp + TMA warp
+constexpr int kTc3Opnd = 98304;    // Q0 16 KB | Q1 16 KB | K 32 KB | V 32 KB
+constexpr int kTc3Smem = 2 * kTc3Opnd + 2 * 16384 + 256;
+
+template <typename D>
+__global__ void __maxnreg__(200)
+attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
+                         int n_frames, int n_tok, int C, int n_heads, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* ostage = smem + 2 * kTc3Opnd;                                   // [2] 16 KB output staging tile of group g
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTc3Opnd + 2 * 16384);
+  uint64_t* qk_full = bars + 0;      // [2] Q0 Q1 K of the item in operand buffer b landed
+  uint64_t* v_full = bars + 2;       // [2] V landed
+  uint64_t* qk_free = bars + 4;      // [2] both S MMAs of the item have read Q / K (tcgen05.commit)
+  uint64_t* v_free = bars + 6;       // [2] both PV MMAs of the item have read V (tcgen05.commit)
+  uint64_t* s_full = bars + 8;       // [2] S_g complete
+  uint64_t* p_full = bars + 10;      // [2] P_g stored to TMEM by the 128 threads of group g
+  uint64_t* o_full = bars + 12;      // [2] O_g complete
+  uint64_t* r_free = bars + 14;      // [2] group g has read O_g out of TMEM: region g may take the next S_g
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tp = (n_frames + 31) & ~31;            // 160 .. 256 (the host routes n_frames <= 128 to the block-diagonal kernel)
+  const int n_chunks = Tp / 32;
+
+  if (warp == 8 && lane == 0) {
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_kv);
+    ptx::prefetch_tmap(&tm_o);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&qk_full[b], 1);
+      ptx::mbar_init(&v_full[b], 1);
+      ptx::mbar_init(&qk_free[b], 1);
+      ptx::mbar_init(&v_free[b], 1);
+      ptx::mbar_init(&s_full[b], 1);
+      ptx::mbar_init(&p_full[b], 128);
+      ptx::mbar_init(&o_full[b], 1);
+      ptx::mbar_init(&r_free[b], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  auto decode = [&](int item, int& clip, int& tok, int& head) {
+    head = item % n_heads;
+    item /= n_heads;
+    tok = item % n_tok;
+    clip = item / n_tok;
+  };
+
+  if (warp == 9) {
+    if (lane == 0) {
+      // ===================== operand loader: item n goes to buffer n & 1 =====================
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const uint32_t b = n & 1, use = n >> 1;
+        uint8_t* buf = smem + b * kTc3Opnd;
+        int clip, tok, head;
+        decode(item, clip, tok, head);
+        if (use > 0) ptx::mbar_wait(&qk_free[b], (use - 1) & 1);
+        ptx::mbar_expect_tx(&qk_full[b], (uint32_t)(2 * 16384 + Tp * 128));
+        ptx::tma_load_4d(buf, &tm_q, &qk_full[b], head * 64, tok, 0, clip);
+        ptx::tma_load_4d(buf + 16384, &tm_q, &qk_full[b], head * 64, tok, 128, clip);
+        ptx::tma_load_4d(buf + 32768, &tm_kv, &qk_full[b], C + head * 64, tok, 0, clip);
+        if (use > 0) ptx::mbar_wait(&v_free[b], (use - 1) & 1);
+        ptx::mbar_expect_tx(&v_full[b], (uint32_t)Tp * 128);
+        ptx::tma_load_4d(buf + 65536, &tm_kv, &v_full[b], 2 * C + head * 64, tok, 0, clip);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      // ===================== MMA issuer: S0(n), PV1(n-1), S1(n), PV0(n) =====================
+      const uint32_t idesc_s = ptx::umma_idesc_16(128, Tp, D::kUmmaFmt);
+      const uint32_t idesc_o = ptx::umma_idesc_16_bmn(128, 64, D::kUmmaFmt);
+      const int ksteps = Tp / 16;
+      auto issue_s = [&](int g, uint8_t* buf) {
+        const uint64_t da = ptx::umma_desc_sw128(smem_u32(buf + g * 16384));
+        const uint64_t db = ptx::umma_desc_sw128(smem_u32(buf + 32768));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, uint8_t* buf) {
+        const uint32_t va = smem_u32(buf + 65536);
+        const uint32_t region = tmem_base + (uint32_t)(g * 256);
+        for (int k = 0; k < ksteps; ++k)
+          ptx::umma_f16_ts(region + 128u, region + (uint32_t)(8 * k), ptx::umma_desc_mn_sw128(va + (uint32_t)(k * 2048)), idesc_o, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&o_full[g]);
+      };
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const uint32_t b = n & 1, use = n >> 1, par = n & 1;
+        uint8_t* buf = smem + b * kTc3Opnd;
+        uint8_t* prev = smem + (b ^ 1) * kTc3Opnd;
+        ptx::mbar_wait(&qk_full[b], use & 1);
+        if (n > 0) ptx::mbar_wait(&r_free[0], par ^ 1);        // O0(n-1) has been read: region 0 is free
+        ptx::tc_fence_after();
+        issue_s(0, buf);
+        if (n > 0) {
+          ptx::mbar_wait(&p_full[1], par ^ 1);                 // P1(n-1) is in TMEM (V(n-1) landed long ago: PV0(n-1) read it)
+          ptx::tc_fence_after();
+          issue_pv(1, prev);
+          ptx::umma_commit(&v_free[b ^ 1]);                    // last reader of V(n-1)
+          ptx::mbar_wait(&r_free[1], par ^ 1);                 // O1(n-1) has been read: region 1 is free
+          ptx::tc_fence_after();
+        }
+        issue_s(1, buf);
+        ptx::umma_commit(&qk_free[b]);                         // last reader of Q / K(n)
+        ptx::mbar_wait(&p_full[0], par);
+        ptx::mbar_wait(&v_full[b], use & 1);
+        ptx::tc_fence_after();
+        issue_pv(0, buf);
+      }
+      if (n > 0) {
+        const uint32_t last = n - 1;
+        ptx::mbar_wait(&p_full[1], last & 1);
+        ptx::tc_fence_after();
+        issue_pv(1, smem + (last & 1) * kTc3Opnd);
+      }
+    }
+  } else {
+    // ===================== softmax / drain: group g = query tile g, thread = one query row =====================
+    const int g = warp >> 2;
+    const int row = threadIdx.x & 127;                  // tile-local query row <-> TMEM lane
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g * 256);
+    const float scale_log2 = 0.125f * kLog2e;
+    constexpr float kSafeExp = D::kUmmaFmt == 1 ? 60.0f : 13.0f;   // bf16 has the fp32 exponent range, fp16 tops out at 2^16
+    uint8_t* stage = ostage + g * 16384;
+    uint8_t* orow = stage + (size_t)row * 128;
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const uint32_t par = n & 1;
+      ptx::mbar_wait(&s_full[g], par);
+      ptx::tc_fence_after();
+      // ---- softmax in ONE pass over the S row; the shift is the maximum of the first 32 keys (a lower bound of the row maximum, the
+      // normalisation by the row sum removes it again).  If some exponent leaves the range that is safe for the 16-bit P, the warp
+      // redoes its rows with their true maxima (tcgen05.ld is warp-collective).  P stays in registers until S is no longer needed.
+      uint32_t pk[128];
+      float sum = 0.f, emax = -INFINITY, ms;
+      auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& e_hi, float& acc) {
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
+          const bool live = (c + 1) * 32 <= n_frames || c * 32 + i < n_frames;
+          e_hi = fmaxf(e_hi, live ? e : -INFINITY);
+          p[i] = live ? fast_exp2(e) : 0.f;
+          acc += p[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[16 * c + i] = D::pack2(p[2 * i], p[2 * i + 1]);
+      };
+      {
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row, r);
+        ptx::tmem_ld_wait();
+        float m0 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(r[i]));     // n_frames > 128: the first 32 keys all exist
+        ms = -m0 * scale_log2;
+        emit(r, 0, ms, emax, sum);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) {
+          if (c < n_chunks) {
+            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            emit(r, c, ms, emax, sum);
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, emax > kSafeExp)) {
+        ms -= emax;                       // shift by the true row maximum: every exponent <= 0
+        sum = 0.f;
+        float unused = -INFINITY;
+        uint32_t r[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < n_chunks) {
+            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            emit(r, c, ms, unused, sum);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < n_chunks) ptx::tmem_st16(t_row + (uint32_t)(c * 16), &pk[16 * c]);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[g]);
+      // ---- O_g = P_g V: read it out of TMEM, hand the region back, normalise, stage, store
+      ptx::mbar_wait(&o_full[g], par);
+      ptx::tc_fence_after();
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(t_row + 128u, r0);
+      ptx::tmem_ld32(t_row + 160u, r1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&r_free[g]);
+      const float inv = 1.0f / sum;
+      if (n > 0) {                        // the previous store of this group must have read the staging tile
+        if (row == 0) ptx::bulk_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+        const int bq = (q & 3) * 8;
+        uint4 o;
+        o.x = D::pack2(__uint_as_float(r[bq + 0]) * inv, __uint_as_float(r[bq + 1]) * inv);
+        o.y = D::pack2(__uint_as_float(r[bq + 2]) * inv, __uint_as_float(r[bq + 3]) * inv);
+        o.z = D::pack2(__uint_as_float(r[bq + 4]) * inv, __uint_as_float(r[bq + 5]) * inv);
+        o.w = D::pack2(__uint_as_float(r[bq + 6]) * inv, __uint_as_float(r[bq + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (row == 0) {
+        int clip, tok, head;
+        decode(item, clip, tok, head);
+        ptx::tma_store_4d(&tm_o, stage, head * 64, tok, g * 128, clip);
+        ptx::bulk_commit();
+      }
+    }
+    if (row == 0) ptx::bulk_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------ spatial, tcgen05
 // head_dim 64, n_tok <= 32.  G = (128 / n_tok) * n_tok consecutive tokens (7 frames of 17 joints) form one 128-row tile: the same
 // rows are the queries and the keys, S = Q K^T is a [128 x 128] tcgen05 MMA of which only the block diagonal (same frame) is
@@ -974,6 +1233,17 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       const int64_t ctas = n_clips * n_tok * n_heads * m_tiles;
       MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
       static const bool one_shot = getenv("MANIPOSE_ATTN_TC1") != nullptr;   // A/B switch: one CTA per (head, query tile)
+      static const bool tc2 = getenv("MANIPOSE_ATTN_TC2") != nullptr;        // A/B switch: P staged through shared memory (tc2)
+      if (!one_shot && !tc2 && n_frames > 128) {
+        const int n_items = (int)(n_clips * n_tok * n_heads);
+        const int grid = n_items < sm_count() ? n_items : sm_count();
+        auto launch_3 = [&](auto kernel) {
+          cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc3Smem);
+          kernel<<<grid, kTc3Threads, kTc3Smem, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
+        };
+        if (bf) launch_3(attn_temporal_tc3_kernel<Bf16>); else launch_3(attn_temporal_tc3_kernel<Fp16>);
+        return check_launch("attn_temporal_tc3_kernel");
+      }
       if (!one_shot) {
         const int n_items = (int)(n_clips * n_tok * n_heads);
         const int smem_p = 3 * 65536 + 32768 + 256;

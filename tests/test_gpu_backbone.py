@@ -161,7 +161,8 @@ def _attn_ref(qkv, n_clips, n_frames, n_tok, c, heads, temporal):
 @pytest.mark.parametrize("n_clips,n_frames,n_tok,c,temporal", [
     (2, 243, 17, 512, True), (2, 243, 17, 512, False), (3, 27, 17, 512, True), (3, 27, 17, 512, False),
     (1, 81, 17, 512, True), (2, 243, 16, 128, True), (2, 243, 16, 128, False), (2, 9, 16, 128, True), (1, 1, 17, 512, True),
-    (2, 9, 17, 512, True), (2, 40, 17, 512, True), (2, 128, 17, 512, True), (1, 129, 17, 512, True), (2, 64, 3, 512, True)])
+    (2, 9, 17, 512, True), (2, 40, 17, 512, True), (2, 128, 17, 512, True), (1, 129, 17, 512, True), (2, 64, 3, 512, True),
+    (9, 243, 17, 512, True), (3, 200, 17, 512, True), (2, 160, 5, 512, True), (1, 256, 2, 512, True)])
 def test_attention_vs_fp32(n_clips, n_frames, n_tok, c, temporal, dtype):
     from manipose_b200 import ops
     td = DT[dtype]
