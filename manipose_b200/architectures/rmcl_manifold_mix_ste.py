@@ -83,10 +83,12 @@ class RMCLRotMixSTE(MixSTE):
 
     def hypotheses_into(self, x2d: torch.Tensor, n_clips: int, rot: torch.Tensor, logits: torch.Tensor) -> None:
         """One micro-batch: rot fp32 [n_clips, K, L, J, D], logits fp32 [n_clips, K, L]."""
-        feat = self.trunk(x2d, n_clips)
+        with ops.nvtx("manipose.rotations.trunk"):
+            feat = self.trunk(x2d, n_clips)
         hg, hb, hw, hbias, sw, sb = self._stacked_heads()
-        ops.heads_fwd(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, hg, hb, hw, hbias, sw, sb,
-                      rot, logits, n_clips, self.num_frame, self.n_hyp, self.out_dim, True)
+        with ops.nvtx("manipose.rotations.heads"):
+            ops.heads_fwd(feat, self.Temporal_norm.weight, self.Temporal_norm.bias, self.Temporal_norm.eps, hg, hb, hw, hbias, sw, sb,
+                          rot, logits, n_clips, self.num_frame, self.n_hyp, self.out_dim, True)
 
     def hypotheses_with_grad(self, x: torch.Tensor):
         """Differentiable K heads over the whole batch -> (rot [B,K,L,J,D], logits [B,K,L]).
@@ -170,10 +172,12 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
             n = min(mb, b - s)
             xs = x[s:s + n]
             rm.hypotheses_into(xs, n, rot[:n], logits[:n])
-            sm.bone_lengths_into(xs, n, bones[:n])
-            rc = lib.mp_decoder_fwd(L.ptr(rot), L.ptr(bones), None, L.ptr(logits), L.ptr(poses[s:s + n]), L.ptr(scores[s:s + n]),
-                                    n, k, l, d, L.MP_DEC_EXACT if self.decoder.exact else L.MP_DEC_FAST, L.stream_ptr())
-            L.check(rc, "mp_decoder_fwd")
+            with ops.nvtx("manipose.segments"):
+                sm.bone_lengths_into(xs, n, bones[:n])
+            with ops.nvtx("manipose.decoder"):
+                rc = lib.mp_decoder_fwd(L.ptr(rot), L.ptr(bones), None, L.ptr(logits), L.ptr(poses[s:s + n]), L.ptr(scores[s:s + n]),
+                                        n, k, l, d, L.MP_DEC_EXACT if self.decoder.exact else L.MP_DEC_FAST, L.stream_ptr())
+                L.check(rc, "mp_decoder_fwd")
         return poses, scores
 
     def concat_hyp_and_scores(self, hypothesis: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:

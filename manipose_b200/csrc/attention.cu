@@ -644,7 +644,7 @@ constexpr int kTc3Opnd = 98304;    // Q0 16 KB | Q1 16 KB | K 32 KB | V 32 KB
 constexpr int kTc3Smem = 2 * kTc3Opnd + 2 * 16384 + 256;
 
 template <typename D>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
                          int n_frames, int n_tok, int C, int n_heads, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];

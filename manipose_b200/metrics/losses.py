@@ -119,5 +119,6 @@ def training_loss(poses: torch.Tensor, scores: torch.Tensor, y: torch.Tensor, be
     forward and ONE backward launch: returns (total, terms[8]) with terms = [wta, bce, velocity, smoothness, total, ...]."""
     b, h, l = poses.shape[:3]
     sc = scores.reshape(b, h, l) if scores is not None else None
-    terms = ops.loss_terms(poses, sc, y, weights, squared, beta, vel_w, smooth_w)[0]
+    with ops.nvtx("manipose.loss"):
+        terms = ops.loss_terms(poses, sc, y, weights, squared, beta, vel_w, smooth_w)[0]
     return terms[L.MP_TERM_TOTAL], terms

@@ -398,7 +398,8 @@ def test_forward_vs_reference_golden():
     print(f"pose error vs the reference fixture: median {float(err.median()):.2e}, p99 {q(err, .99):.2e}, max {float(err.max()):.2e}; "
           f"well-conditioned half: p99 {q(err[well], .99):.2e}, max {float(err[well].max()):.2e}")
     assert float(err.median()) <= 2e-3
-    assert q(err[well], .99) <= 6e-3 and q(err, .99) <= 3e-2         # the tail, not only the median: a broken kernel does not hide in it
+    # measured on B200 (fp16): p99 4.9e-3 / max 6.8e-3 over all joints, p99 3.9e-3 on the well-conditioned half
+    assert q(err[well], .99) <= 6e-3 and q(err, .99) <= 1e-2 and float(err.max()) <= 2.5e-2   # the tail, not only the median
 
 
 def test_default_config_forward_runs_at_t243():
