@@ -639,12 +639,16 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 // TMEM: region g (256 columns) = S_g [128 x Tp] fp32 -> P_g in columns [0, Tp/2) -> O_g [128 x 64] fp32 in columns [128, 192).
 // The softmax keeps the packed P row in registers until the whole S row has been read (the guarded shift estimate may ask for a
 // second pass over S, so S must stay intact until then), then stores it with Tp/32 tcgen05.st.x16.
-constexpr int kTc3Threads = 320;   // 2 x 4 softmax warps + MMA warp + TMA warp
+// Registers: the register file is split over the four SM sub-partitions (16 K each), so a CTA of 9 - 12 warps can give every thread
+// at most 168 registers at launch.  The softmax threads hold a 128-register packed P row, so the kernel is launched with three
+// warpgroups (warps 10 and 11 only take part in the hand-over) and redistributes with setmaxnreg: the MMA / TMA warpgroup shrinks
+// to 40 registers, the two softmax warpgroups grow to 232 (8 x 32 x 232 + 4 x 32 x 40 = 12 x 32 x 168).
+constexpr int kTc3Threads = 384;   // 2 x 4 softmax warps + {MMA warp, TMA warp, 2 idle warps}
 constexpr int kTc3Opnd = 98304;    // Q0 16 KB | Q1 16 KB | K 32 KB | V 32 KB
 constexpr int kTc3Smem = 2 * kTc3Opnd + 2 * 16384 + 256;
 
 template <typename D>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kTc3Threads, 1)
 attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
                          int n_frames, int n_tok, int C, int n_heads, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -697,6 +701,7 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     clip = item / n_tok;
   };
 
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 9) {
     if (lane == 0) {
       // ===================== operand loader: item n goes to buffer n & 1 =====================
@@ -768,8 +773,9 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         issue_pv(1, smem + (last & 1) * kTc3Opnd);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================== softmax / drain: group g = query tile g, thread = one query row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int g = warp >> 2;
     const int row = threadIdx.x & 127;                  // tile-local query row <-> TMEM lane
     const uint32_t sw = (uint32_t)(row & 7);
