@@ -796,32 +796,52 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       float sum = 0.f, emax = -INFINITY, ms;
       auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& e_hi, float& acc) {
         float p[32];
+        float a4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four chains instead of one
+        if ((c + 1) * 32 <= n_frames) {   // warp-uniform: every key of the chunk exists (all chunks but the last): no masking
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
-          const bool live = (c + 1) * 32 <= n_frames || c * 32 + i < n_frames;
-          e_hi = fmaxf(e_hi, live ? e : -INFINITY);
-          p[i] = live ? fast_exp2(e) : 0.f;
-          acc += p[i];
+          for (int i = 0; i < 32; ++i) {
+            const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
+            m4[i & 3] = fmaxf(m4[i & 3], e);
+            p[i] = fast_exp2(e);
+            a4[i & 3] += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
+            const bool live = c * 32 + i < n_frames;
+            m4[i & 3] = fmaxf(m4[i & 3], live ? e : -INFINITY);
+            p[i] = live ? fast_exp2(e) : 0.f;
+            a4[i & 3] += p[i];
+          }
         }
+        e_hi = fmaxf(e_hi, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[16 * c + i] = D::pack2(p[2 * i], p[2 * i + 1]);
       };
       {
-        uint32_t r[32];
-        ptx::tmem_ld32(t_row, r);
+        // two register buffers: the TMEM load of chunk c + 1 is in flight while chunk c is processed
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld32(t_row, ra);
         ptx::tmem_ld_wait();
+        ptx::tmem_ld32(t_row + 32u, rb);                   // n_frames > 128: at least five chunks
         float m0 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(r[i]));     // n_frames > 128: the first 32 keys all exist
+        for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(ra[i]));     // the first 32 keys all exist
         ms = -m0 * scale_log2;
-        emit(r, 0, ms, emax, sum);
+        emit(ra, 0, ms, emax, sum);
 #pragma unroll
         for (int c = 1; c < 8; ++c) {
           if (c < n_chunks) {
-            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
             ptx::tmem_ld_wait();
-            emit(r, c, ms, emax, sum);
+            if (c & 1) {
+              if (c + 1 < n_chunks) ptx::tmem_ld32(t_row + (uint32_t)((c + 1) * 32), ra);
+              emit(rb, c, ms, emax, sum);
+            } else {
+              if (c + 1 < n_chunks) ptx::tmem_ld32(t_row + (uint32_t)((c + 1) * 32), rb);
+              emit(ra, c, ms, emax, sum);
+            }
           }
         }
       }
