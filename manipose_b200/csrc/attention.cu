@@ -781,7 +781,8 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g * 256);
     const float scale_log2 = 0.125f * kLog2e;
-    constexpr float kSafeExp = D::kUmmaFmt == 1 ? 60.0f : 13.0f;   // bf16 has the fp32 exponent range, fp16 tops out at 2^16
+    // largest row sum (hence largest P value) accepted from the estimated shift: bf16 has the fp32 exponent range, fp16 tops out at 65504
+    constexpr float kSafeSum = D::kUmmaFmt == 1 ? 1.1529215e18f /* 2^60 */ : 8192.0f;
     uint8_t* stage = ostage + g * 16384;
     uint8_t* orow = stage + (size_t)row * 128;
     uint32_t n = 0;
@@ -793,29 +794,24 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       // normalisation by the row sum removes it again).  If some exponent leaves the range that is safe for the 16-bit P, the warp
       // redoes its rows with their true maxima (tcgen05.ld is warp-collective).  P stays in registers until S is no longer needed.
       uint32_t pk[128];
-      float sum = 0.f, emax = -INFINITY, ms;
-      auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& e_hi, float& acc) {
+      float sum = 0.f, ms;
+      auto emit = [&](const uint32_t(&r)[32], int c, float shift, float& acc) {
         float p[32];
-        float a4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four chains instead of one
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};   // four chains instead of one
         if ((c + 1) * 32 <= n_frames) {   // warp-uniform: every key of the chunk exists (all chunks but the last): no masking
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
-            m4[i & 3] = fmaxf(m4[i & 3], e);
-            p[i] = fast_exp2(e);
+            p[i] = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, shift));
             a4[i & 3] += p[i];
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = fmaf(__uint_as_float(r[i]), scale_log2, shift);
-            const bool live = c * 32 + i < n_frames;
-            m4[i & 3] = fmaxf(m4[i & 3], live ? e : -INFINITY);
-            p[i] = live ? fast_exp2(e) : 0.f;
+            const float e = fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, shift));
+            p[i] = c * 32 + i < n_frames ? e : 0.f;
             a4[i & 3] += p[i];
           }
         }
-        e_hi = fmaxf(e_hi, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[16 * c + i] = D::pack2(p[2 * i], p[2 * i + 1]);
@@ -830,32 +826,44 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 #pragma unroll
         for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, __uint_as_float(ra[i]));     // the first 32 keys all exist
         ms = -m0 * scale_log2;
-        emit(ra, 0, ms, emax, sum);
+        emit(ra, 0, ms, sum);
 #pragma unroll
         for (int c = 1; c < 8; ++c) {
           if (c < n_chunks) {
             ptx::tmem_ld_wait();
             if (c & 1) {
               if (c + 1 < n_chunks) ptx::tmem_ld32(t_row + (uint32_t)((c + 1) * 32), ra);
-              emit(rb, c, ms, emax, sum);
+              emit(rb, c, ms, sum);
             } else {
               if (c + 1 < n_chunks) ptx::tmem_ld32(t_row + (uint32_t)((c + 1) * 32), rb);
-              emit(ra, c, ms, emax, sum);
+              emit(ra, c, ms, sum);
             }
           }
         }
       }
-      if (__any_sync(0xffffffffu, emax > kSafeExp)) {
-        ms -= emax;                       // shift by the true row maximum: every exponent <= 0
-        sum = 0.f;
-        float unused = -INFINITY;
+      // Every P value is at most the row sum: a sum within the safe range proves that no exponent left it (and a NaN / inf sum fails
+      // the comparison), without tracking the largest exponent element by element.
+      if (__any_sync(0xffffffffu, !(sum <= kSafeSum))) {
         uint32_t r[32];
+        float m = -INFINITY;              // true row maximum over the keys that exist
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < n_chunks) {
             ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
             ptx::tmem_ld_wait();
-            emit(r, c, ms, unused, sum);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < n_frames) m = fmaxf(m, __uint_as_float(r[i]));
+          }
+        }
+        ms = -m * scale_log2;             // every exponent <= 0
+        sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < n_chunks) {
+            ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            emit(r, c, ms, sum);
           }
         }
       }
