@@ -134,10 +134,11 @@ enum { MP_DTYPE_BF16 = 0, /* BASELINE config 3: "bf16 backbone" */
  *   MP_EPI_BIAS:     Y[M,N] (16-bit) = A[M,K] W[N,K]^T + bias[N]
  *   MP_EPI_GELU:     Y[M,N] (16-bit) = GELU_erf(A W^T + bias)                       (nn.GELU, mix_ste.py:200)
  *   MP_EPI_RESIDUAL: Y[M,N] (fp32)   = resid[M,N] (fp32) + A W^T + bias             (Block.forward, mix_ste.py:352-358)
+ *   MP_EPI_BIAS_F32: Y[M,N] (fp32)   = A W^T + bias                                  (the folded K-head projection: fp32 out)
  *   MP_EPI_ACCUMULATE: Y[M,N] (fp32) += A W^T  (bias ignored, may be NULL): the contraction is split over the SMs and the partial
  *                    tiles are added with TMA reduce stores (fp32 adds in L2, order not fixed) — weight gradients, few tiles, long K
  * A, W 16-bit dense row-major (row strides K); bias fp32; K % 64 == 0, N % 128 == 0; Y may alias resid. */
-enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2, MP_EPI_ACCUMULATE = 3 };
+enum { MP_EPI_BIAS = 0, MP_EPI_GELU = 1, MP_EPI_RESIDUAL = 2, MP_EPI_ACCUMULATE = 3, MP_EPI_BIAS_F32 = 4 };
 int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N,
               int64_t K, int epilogue, int dtype, mp_stream_t stream);
 
@@ -204,6 +205,13 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
                  const float* score_w, const float* score_b, float* rot, float* logits,
                  int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int with_score,
                  mp_stream_t stream);
+/* The same K heads on the tensor cores (the C = 512 model): xhat [n_frames_total*17, 512] 16-bit is the input ALREADY through
+ * Temporal_norm and the affine-free LayerNorm(eps 1e-5) the K heads share (mp_linear_ln writes it as its h output), wf16 [n_pad, 512]
+ * 16-bit / bf [n_pad] fp32 the folded parameters (row k*(D+1)+o: gamma_k (.) W_k[o], W_k[o] . beta_k + b_k[o]; rows past K*(D+1) zero):
+ * one tcgen05 GEMM with fp32 output into `workspace` ([tokens, n_pad] fp32), then the scatter into rot / the score dot product. */
+int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const float* score_w, const float* score_b, float* rot,
+                   float* logits, float* workspace, size_t workspace_bytes, int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim,
+                   int with_score, int n_pad, int dtype, mp_stream_t stream);
 /* Bone-length head (MixSTE.head + mean over time, mix_ste.py:123-126,187; manifold_mix_ste.py:150-154):
  *   x [n_clips*n_frames*16, 128] fp32 before Temporal_norm -> bone_len [n_clips,16] fp32.
  *   workspace >= n_clips*n_frames*16*4 bytes. */

@@ -16,7 +16,7 @@ MP_EINVAL, MP_EUNSUPPORTED, MP_EDEVICE, MP_ELAUNCH, MP_EALIGN, MP_EWORKSPACE = -
 MP_DEC_EXACT, MP_DEC_FAST = 0, 1
 MP_TERM_WTA, MP_TERM_BCE, MP_TERM_VEL, MP_TERM_SMOOTH, MP_TERM_TOTAL, MP_LOSS_NTERMS = 0, 1, 2, 3, 4, 8
 MP_AGG_WEIGHTED_AVE, MP_AGG_BEST_SCORE, MP_AGG_ORACLE = 0, 1, 2
-MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL, MP_EPI_ACCUMULATE = 0, 1, 2, 3
+MP_EPI_BIAS, MP_EPI_GELU, MP_EPI_RESIDUAL, MP_EPI_ACCUMULATE, MP_EPI_BIAS_F32 = 0, 1, 2, 3, 4
 MP_ATTN_SPATIAL, MP_ATTN_TEMPORAL = 0, 1
 MP_DTYPE_BF16, MP_DTYPE_FP16 = 0, 1
 MP_ERR_L2, MP_ERR_SQ, MP_ERR_ABS, MP_ERR_DIFF = 0, 1, 2, 3
@@ -49,6 +49,7 @@ SIGNATURES = {
     "mp_embed_segments": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, I, P]),
     "mp_attention": (I, [P, P, I64, I64, I, I, I, I, I, P]),
     "mp_heads_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, I64, I64, I, I, I, P]),
+    "mp_heads_fwd16": (I, [P, P, P, P, P, P, P, P, c_size_t, I64, I64, I, I, I, I, I, P]),
     "mp_bones_head": (I, [P, P, P, F, P, P, P, P, P, I64, I64, I, I, P, c_size_t, P]),
     "mp_cast_f32_to_16": (I, [P, P, I64, I, P]),
     "mp_gather_windows": (I, [P, P, P, P, P, P, P, P, P, I64, I64, I, I, P]),

@@ -295,11 +295,15 @@ class MixSTE(nn.Module):
                          blk0.norm1.weight, blk0.norm1.bias, blk0.norm1.eps, x, h, n_clips * n_frames * self.num_tokens,
                          self.num_tokens, self.embed_dim, ops.DTYPE_CODE[self.compute_dtype])
 
-    def trunk(self, x2d: torch.Tensor, n_clips: int) -> torch.Tensor:
+    def trunk(self, x2d: torch.Tensor, n_clips: int, head_norm_eps: Optional[float] = None) -> torch.Tensor:
         """STE_forward + TTE_foward + ST_foward (mix_ste.py:128-173) on one micro-batch.
 
         x2d: fp32 [n_clips, L, J, in_chans] (contiguous).  Returns the fp32 [n_clips*L*tokens, C] output of the last temporal
-        block BEFORE ``Temporal_norm`` (the head kernels apply it, fused with their own LayerNorm)."""
+        block BEFORE ``Temporal_norm`` (the head kernels apply it, fused with their own LayerNorm).
+
+        ``head_norm_eps`` (fused C = 512 trunk only): the last block's epilogue also applies ``Temporal_norm`` and the affine-free
+        LayerNorm(eps) that every head of the model shares, and the 16-bit normalised activations [tokens, C] are returned instead
+        (the A operand of the folded head projection, mp_heads_fwd16); the fp32 stream is not written out."""
         if self.training and any(isinstance(b.drop_path, DropPath) and b.drop_path.drop_prob > 0 for b in self.STEblocks):
             raise NotImplementedError("the fused inference trunk has no stochastic depth: call model.eval(), or run the forward "
                                       "with gradients enabled (the training trunk applies DropPath)")
@@ -334,6 +338,11 @@ class MixSTE(nn.Module):
                 ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
             ops.linear(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
             if fused:
+                if last and head_norm_eps is not None:
+                    one, zero = self._unit_affine(x.device)
+                    ops.linear_ln(hid, w[wi + 3], blk.mlp.fc2.bias, x, None, h, post=(post.weight, post.bias), post_eps=post.eps,
+                                  ln=(one, zero), ln_eps=head_norm_eps)
+                    return h
                 if last:
                     ops.linear_ln(hid, w[wi + 3], blk.mlp.fc2.bias, x, x, None)
                 else:
@@ -345,6 +354,13 @@ class MixSTE(nn.Module):
                     ops.layernorm(x, x, h, post=(post.weight, post.bias), post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames,
                                   ln=(nxt.norm1.weight, nxt.norm1.bias), ln_eps=nxt.norm1.eps, dtype=dt)
         return x
+
+    def _unit_affine(self, device):
+        ua = getattr(self, "_unit_affine_cache", None)
+        if ua is None or ua[0].device != device:
+            ua = (torch.ones(self.embed_dim, dtype=torch.float32, device=device), torch.zeros(self.embed_dim, dtype=torch.float32, device=device))
+            self._unit_affine_cache = ua
+        return ua
 
     # ------------------------------------------------------------------------------------------ training path
     def _grad_mode(self) -> bool:

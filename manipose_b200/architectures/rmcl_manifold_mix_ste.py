@@ -63,6 +63,7 @@ class RMCLRotMixSTE(MixSTE):
                                    for _ in range(self.n_hyp)])
         self._head_key = None
         self._head_stack = None
+        self._fold_key = None
 
     def _stacked_heads(self):
         """K heads as stacked fp32 tensors ([K,C], [K,C], [K,D+1,C], [K,D+1], [K,J], [K]), refreshed on parameter change."""
@@ -81,8 +82,43 @@ class RMCLRotMixSTE(MixSTE):
             self._head_key = key
         return self._head_stack
 
+    # K heads on the tensor cores (C = 512, fused trunk): False keeps the fp32 CUDA-core projection (mp_heads_fwd)
+    heads_on_tensor_cores = True
+
+    def _folded_heads(self):
+        """LN_k(y) = yhat * gamma_k + beta_k shares yhat between the heads, so the K heads are ONE Linear with folded parameters
+        W_k * gamma_k (16-bit, zero-padded to 128 rows) and W_k beta_k + b_k (fp32); refreshed when a head parameter changes."""
+        params = [p for h in self.head for p in h.parameters()]
+        key = (self.compute_dtype,) + _version_key(params)
+        if key != getattr(self, "_fold_key", None):
+            hg, hb, hw, hbias, sw, sb = self._stacked_heads()
+            with torch.no_grad():
+                k, d1, c = hw.shape
+                n_pad = (k * d1 + 127) // 128 * 128
+                wf = torch.zeros((n_pad, c), dtype=torch.float32, device=hw.device)
+                wf[:k * d1] = (hw * hg[:, None, :]).reshape(k * d1, c)
+                bf = torch.zeros(n_pad, dtype=torch.float32, device=hw.device)
+                bf[:k * d1] = ((hw * hb[:, None, :]).sum(-1) + hbias).reshape(k * d1)
+                self._fold = (ops.cast16(wf, ops.DTYPE_CODE[self.compute_dtype]), bf, sw, sb)
+            self._fold_key = key
+        return self._fold
+
     def hypotheses_into(self, x2d: torch.Tensor, n_clips: int, rot: torch.Tensor, logits: torch.Tensor) -> None:
         """One micro-batch: rot fp32 [n_clips, K, L, J, D], logits fp32 [n_clips, K, L]."""
+        eps = self.head[0].norm.eps
+        if (self.heads_on_tensor_cores and self.embed_dim == 512 and self.fuse_layernorm and self.num_tokens == ops.J
+                and all(h.norm.eps == eps for h in self.head)):
+            wf16, bf, sw, sb = self._folded_heads()
+            with ops.nvtx("manipose.rotations.trunk"):
+                xhat = self.trunk(x2d, n_clips, head_norm_eps=eps)
+            n_tokens = n_clips * self.num_frame * self.num_tokens
+            ws = getattr(self, "_heads_ws", None)
+            if ws is None or ws.numel() < n_tokens * wf16.shape[0] or ws.device != xhat.device:
+                ws = torch.empty(n_tokens * wf16.shape[0], dtype=torch.float32, device=xhat.device)
+                self._heads_ws = ws
+            with ops.nvtx("manipose.rotations.heads"):
+                ops.heads_fwd16(xhat, wf16, bf, sw, sb, rot, logits, ws, n_clips, self.num_frame, self.n_hyp, self.out_dim, True)
+            return
         with ops.nvtx("manipose.rotations.trunk"):
             feat = self.trunk(x2d, n_clips)
         hg, hb, hw, hbias, sw, sb = self._stacked_heads()

@@ -328,6 +328,42 @@ __global__ void bones_mean_kernel(const float* __restrict__ values, float* __res
   bone_len[i] = acc / (float)n_frames;
 }
 
+// K heads, second half of the tensor-core path (mp_heads_fwd16): y [frames * 17, ld] fp32 holds, per token, the K * (D + 1) outputs of the
+// folded projection (head k, output o at column k * (D + 1) + o).  One warp per frame: the 17 rows go through shared memory so that the
+// [17 x D] block of every head is written as one contiguous run, and the J-term score dot product (MCLHead.score_head,
+// rmcl_manifold_mix_ste.py:296-297) is a warp reduction.
+__global__ void __launch_bounds__(kTokWarps * 32)
+heads_finish_kernel(const float* __restrict__ y, int ld, const float* __restrict__ score_w, const float* __restrict__ score_b,
+                    float* __restrict__ rot, float* __restrict__ logits, int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
+  float* tile = sm + (size_t)warp * kJ * KO;          // [17][KO]
+  const int64_t total_frames = n_clips * n_frames;
+  for (int64_t fr = (int64_t)blockIdx.x * kTokWarps + warp; fr < total_frames; fr += (int64_t)gridDim.x * kTokWarps) {
+    const int64_t b = fr / n_frames;
+    const int t = (int)(fr - b * n_frames);
+    for (int i = lane; i < kJ * KO; i += 32) {
+      const int j = i / KO, c = i - j * KO;
+      tile[i] = y[(fr * kJ + j) * ld + c];
+    }
+    __syncwarp();
+    for (int k = 0; k < n_hyp; ++k) {
+      float* dst = rot + (((b * n_hyp + k) * n_frames + t) * kJ) * out_dim;
+      for (int i = lane; i < kJ * out_dim; i += 32) {
+        const int j = i / out_dim, o = i - j * out_dim;
+        dst[i] = tile[j * KO + k * O + o];
+      }
+      if (with_score) {
+        float acc = lane < kJ ? score_w[k * kJ + lane] * tile[lane * KO + k * O + out_dim] : 0.f;
+        acc = warp_sum(acc);
+        if (lane == 0) logits[(b * n_hyp + k) * n_frames + t] = acc + score_b[k];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 }  // namespace mp
 
@@ -427,6 +463,32 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
                                                                               score_b, rot, logits, n_clips, (int)n_frames, n_hyp, out_dim,
                                                                               with_score);
   return check_launch("heads_fwd_kernel");
+}
+
+int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const float* score_w, const float* score_b, float* rot,
+                   float* logits, float* workspace, size_t workspace_bytes, int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim,
+                   int with_score, int n_pad, int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(xhat16 && wf16 && bf && rot && workspace, MP_EINVAL, "mp_heads_fwd16: null pointer");
+  MP_REQUIRE(!with_score || (score_w && score_b && logits), MP_EINVAL, "mp_heads_fwd16: score head pointers required");
+  MP_REQUIRE(n_hyp >= 1 && n_hyp <= 16 && (out_dim == 6 || out_dim == 4 || out_dim == 3), MP_EINVAL, "mp_heads_fwd16: bad n_hyp/out_dim");
+  const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
+  MP_REQUIRE(n_pad >= KO && n_pad % 128 == 0, MP_EINVAL, "mp_heads_fwd16: n_pad=%d must be a multiple of 128 holding %d outputs", n_pad, KO);
+  MP_REQUIRE(n_clips >= 0 && n_frames >= 1, MP_EINVAL, "mp_heads_fwd16: bad sizes");
+  const int64_t n_tokens = n_clips * n_frames * kJ;
+  MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * n_pad * sizeof(float), MP_EWORKSPACE, "mp_heads_fwd16: workspace too small");
+  if (n_clips == 0) return MP_OK;
+  MP_CHECK(mp_linear(xhat16, wf16, bf, nullptr, workspace, n_tokens, n_pad, kHeadC, MP_EPI_BIAS_F32, dtype, stream));
+  const size_t smem = (size_t)kTokWarps * kJ * KO * sizeof(float);
+  MP_REQUIRE(smem <= 200 * 1024, MP_EUNSUPPORTED, "mp_heads_fwd16: n_hyp=%d needs %zu bytes of shared memory", n_hyp, smem);
+  cudaFuncSetAttribute(heads_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (ctas > cap) ctas = cap;
+  heads_finish_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(workspace, n_pad, score_w, score_b, rot, logits, n_clips,
+                                                                                 (int)n_frames, n_hyp, out_dim, with_score);
+  return check_launch("heads_finish_kernel");
 }
 
 int mp_bones_head(const float* x, const float* post_gamma, const float* post_beta, float post_eps, const float* hg, const float* hb,

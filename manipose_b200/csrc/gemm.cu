@@ -58,7 +58,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   using Cfg = GemmCfg<BN>;
   constexpr bool kRes = (EPI == MP_EPI_RESIDUAL);
   constexpr bool kAcc = (EPI == MP_EPI_ACCUMULATE);        // Y (fp32) += A W^T, split-K: partial tiles are added by TMA reduce stores
-  constexpr int kBoxCols = (kRes || kAcc) ? 32 : 64;       // fp32 vs 16-bit output: 128 bytes per row either way
+  constexpr bool kF32 = (EPI == MP_EPI_BIAS_F32);          // Y (fp32) = A W^T + bias
+  constexpr int kBoxCols = (kRes || kAcc || kF32) ? 32 : 64;   // fp32 vs 16-bit output: 128 bytes per row either way
   constexpr int kBoxes = BN / kBoxCols;
   static_assert(kBoxes % 2 == 0, "boxes alternate between the two epilogue groups");
 
@@ -255,6 +256,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(srow + (((uint32_t)c ^ sw) << 4)) = make_uint4(r[4 * c + 0], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        } else if (kF32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(b * 32), r);
+          ptx::tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 bb = __ldg(b4 + c);
+            float4 v;
+            v.x = __uint_as_float(r[4 * c + 0]) + bb.x;
+            v.y = __uint_as_float(r[4 * c + 1]) + bb.y;
+            v.z = __uint_as_float(r[4 * c + 2]) + bb.z;
+            v.w = __uint_as_float(r[4 * c + 3]) + bb.w;
+            *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4)) = v;
+          }
         } else {
           uint32_t r0[32], r1[32];               // both 32-column halves of the box in flight before one wait
           ptx::tmem_ld32(t_row + (uint32_t)(b * 64), r0);
@@ -455,6 +471,7 @@ int dispatch_epi(int epilogue, const CUtensorMap& ta, const CUtensorMap& tw, con
     case MP_EPI_GELU: return launch_linear<BN, MP_EPI_GELU, D>(ta, tw, ty, tr, bias, M, N, K, stream);
     case MP_EPI_RESIDUAL: return launch_linear<BN, MP_EPI_RESIDUAL, D>(ta, tw, ty, tr, bias, M, N, K, stream);
     case MP_EPI_ACCUMULATE: return launch_linear<BN, MP_EPI_ACCUMULATE, D>(ta, tw, ty, tr, bias, M, N, K, stream);
+    case MP_EPI_BIAS_F32: return launch_linear<BN, MP_EPI_BIAS_F32, D>(ta, tw, ty, tr, bias, M, N, K, stream);
   }
   return fail(MP_EINVAL, "mp_linear: unknown epilogue %d", epilogue);
 }
@@ -500,7 +517,7 @@ extern "C" int mp_linear(const void* A, const void* W, const float* bias, const 
   if (M == 0) return MP_OK;
   const bool wide = (N % 256 == 0);
   const bool res = epilogue == MP_EPI_RESIDUAL;
-  const bool f32_out = res || epilogue == MP_EPI_ACCUMULATE;
+  const bool f32_out = res || epilogue == MP_EPI_ACCUMULATE || epilogue == MP_EPI_BIAS_F32;
   // CTA pairs halve the weight traffic out of L2; MANIPOSE_SINGLE_CTA=1 keeps the one-CTA kernel (A/B measurements)
   static const bool single_only = getenv("MANIPOSE_SINGLE_CTA") != nullptr;
   if (wide && !f32_out && !single_only) return pair_linear(A, W, bias, Y, (int)M, (int)N, (int)K, epilogue, dtype, (cudaStream_t)stream);

@@ -504,6 +504,7 @@ struct LnArgs {
   const float* ln_b;
   int has_xpre;             // with the post-norm: also store the value BEFORE it (tm_p; the training tape needs both)
   const float* row_scale;   // NULL or [M]: x = resid + row_scale[row] * (A W^T + bias) (per-sample DropPath factor)
+  int no_x;                 // with post-norm AND pre-norm: do not store x_out (only h is wanted: the last block ahead of the heads)
   float post_eps, ln_eps;
   int pos_div, pos_mod;
 };
@@ -645,7 +646,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       // n / kGS of slot_empty[slot] when that slot is free again.  A parity wait only distinguishes "the previous phase" from
       // "the one before", and the loader skips the store-only uses, so across tiles it waits for `tile_done` (both halves arrive
       // after their last store has been read: every slot is free) and within a tile only for uses kGS.. (lockstep again).
-      const uint32_t uses = 8u + (has_post ? 8u : 0u) + (has_ln ? 4u : 0u);
+      const uint32_t uses = 8u + ((has_post && args.no_x == 0) ? 8u : 0u) + (has_ln ? 4u : 0u);
       auto box_col32 = [](int g, int j) { return kSplit ? (j >> 2) * 256 + g * 128 + (j & 3) * 32 : g * 256 + j * 32; };
       uint32_t tt = 0;
       uint32_t full_par = 0;                     // parity bit of slot_full per slot (flips with every load into the slot)
@@ -771,11 +772,12 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const float* pos_row = args.pos ? args.pos + (size_t)((grow / args.pos_div) % args.pos_mod) * kN : nullptr;
         s1 = 0.f;
         s2 = 0.f;
+        const bool store_b = args.no_x == 0;        // x_out wanted (false: only the statistics and the TMEM copy for pass C)
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j, ++n) {
+        for (int j = 0; j < 8; ++j) {
           const uint32_t slot = (uint32_t)(grp * kGS) + n % kGS;
           uint8_t* srow = slot_base + slot * kBoxBytes + row * 128;
-          ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
+          if (store_b) ptx::mbar_wait(&bars.slot_empty[slot], ((n / kGS) & 1) ^ 1);
           uint32_t r[32];
           const int col = box_col32(j);
           ptx::tmem_ld32(t_row + (uint32_t)col, r);
@@ -805,14 +807,17 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             r[4 * c + 1] = __float_as_uint(y.y);
             r[4 * c + 2] = __float_as_uint(y.z);
             r[4 * c + 3] = __float_as_uint(y.w);
-            *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4)) = y;
+            if (store_b) *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4)) = y;
           }
           if (has_ln) ptx::tmem_st32(t_row + (uint32_t)col, r);
-          ptx::fence_proxy_async_smem();
-          named_bar_sync(1 + grp, 128);
-          if (elected) {
-            ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
-            after_store(slot);
+          if (store_b) {
+            ptx::fence_proxy_async_smem();
+            named_bar_sync(1 + grp, 128);
+            if (elected) {
+              ptx::tma_store_2d(&tm_x, slot_base + slot * kBoxBytes, col, row0);
+              after_store(slot);
+            }
+            ++n;
           }
           if (last_pass == 1 && (kSplit ? (j & 3) == 3 : j == 7)) release_half(kSplit ? j >> 2 : 0);
         }
@@ -956,7 +961,8 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
                             int64_t M, int64_t N, int64_t K, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
-  MP_REQUIRE(A && W && bias && resid && x_out, MP_EINVAL, "mp_linear_ln: null pointer");
+  MP_REQUIRE(A && W && bias && resid, MP_EINVAL, "mp_linear_ln: null pointer");
+  MP_REQUIRE(x_out || (post_gamma && ln_gamma && !x_pre), MP_EINVAL, "mp_linear_ln: x_out may only be omitted with both LayerNorms (h_out is the result)");
   MP_REQUIRE(N == 512, MP_EUNSUPPORTED, "mp_linear_ln: N=%lld (the fused residual + LayerNorm epilogue is built for N = 512 rows)", (long long)N);
   MP_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && K >= 64 && K % 64 == 0, MP_EINVAL, "mp_linear_ln: unsupported shape M=%lld K=%lld", (long long)M, (long long)K);
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_linear_ln: unknown dtype %d", dtype);
@@ -973,7 +979,10 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
   MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
   MP_CHECK(get_tmap(&tr, resid, M, N, kBM, 2));
-  MP_CHECK(get_tmap(&tx, x_out, M, N, kBM, 2));
+  if (x_out)
+    MP_CHECK(get_tmap(&tx, x_out, M, N, kBM, 2));
+  else
+    tx = tr;        // never stored to (LnArgs.no_x)
   if (ln_gamma)
     MP_CHECK(get_tmap(&th, h_out, M, N, kBM, dtype));
   else
@@ -982,7 +991,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     MP_CHECK(get_tmap(&tp, x_pre, M, N, kBM, 2));
   else
     tp = tx;
-  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, x_pre != nullptr, row_scale, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
+  LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, x_pre != nullptr, row_scale, x_out == nullptr, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
   // K = 512 (proj): split accumulation, 4 x 32 KB operand stages + 6 box slots; K = 1024 (fc2): single accumulation, 3 x 48 KB

@@ -470,6 +470,15 @@ def heads_fwd(x, post_g, post_b, post_eps, hg, hb, hw, hbias, score_w, score_b, 
     _count()
 
 
+def heads_fwd16(xhat16, wf16, bf, score_w, score_b, rot, logits, workspace, n_clips, n_frames, n_hyp, out_dim, with_score):
+    """K heads on the tensor cores: xhat16 [tokens, 512] (normalised, 16-bit) x folded weights wf16 [n_pad, 512] -> rot / logits."""
+    rc = L.load().mp_heads_fwd16(L.ptr(xhat16), L.ptr(wf16), L.ptr(bf), L.ptr(score_w), L.ptr(score_b), L.ptr(rot), L.ptr(logits),
+                                 L.ptr(workspace), workspace.numel() * workspace.element_size(), n_clips, n_frames, n_hyp, out_dim,
+                                 int(with_score), wf16.shape[0], DTYPE_CODE[xhat16.dtype], L.stream_ptr())
+    L.check(rc, "mp_heads_fwd16")
+    _count(2)
+
+
 def bones_head(x, post_g, post_b, post_eps, hg, hb, hw, hbias, bone_len, n_clips, n_frames, n_segments, c, workspace):
     rc = L.load().mp_bones_head(L.ptr(x), L.ptr(post_g), L.ptr(post_b), post_eps, L.ptr(hg), L.ptr(hb), L.ptr(hw), L.ptr(hbias),
                                 L.ptr(bone_len), n_clips, n_frames, n_segments, c, L.ptr(workspace),

@@ -259,6 +259,8 @@ class FusedAdam(torch.optim.Optimizer):
                 m._shadow_key = None
             if hasattr(m, "_head_key"):
                 m._head_key = None
+            if hasattr(m, "_fold_key"):
+                m._fold_key = None
 
 
 class CapturedTrainStep:

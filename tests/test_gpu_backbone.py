@@ -231,6 +231,32 @@ def test_block_attention_mlp_forward_on_their_own(c, heads, n_seq, seq_len, dtyp
         blk(x.cuda())
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_heads_on_tensor_cores_vs_fp32_heads(dtype):
+    """The K heads as one folded 16-bit tcgen05 projection (mp_heads_fwd16: Temporal_norm + the shared affine-free LayerNorm in the last
+    block's epilogue, fp32 accumulation and output) against the fp32 CUDA-core heads (mp_heads_fwd) on the same trunk: the only
+    difference is the 16-bit rounding of the normalised input and of the folded weights."""
+    T, K, B = 27, 5, 3
+    sd = O.make_state_dict(num_frame=T, n_hyp=K, seed=3)
+    g = torch.Generator().manual_seed(9)
+    for name in list(sd):
+        if ".head." in name and name.endswith(("norm.bias", "norm.weight")):
+            sd[name] = sd[name] + 0.3 * torch.randn(sd[name].shape, generator=g)      # the folding has to carry gamma_k and beta_k
+    m = _model_from_sd(sd, T, K, dtype)
+    x = 0.3 * torch.randn(B, T, 17, 2, generator=g).cuda()
+    rm = m.rotations_module
+    with torch.no_grad():
+        rm.heads_on_tensor_cores = True
+        rot16, sc16 = rm(x)
+        rm.heads_on_tensor_cores = False
+        rot32, sc32 = rm(x)
+    tol = 1e-2 if dtype == "bf16" else 1.5e-3
+    assert _rel(rot16, rot32) <= tol, _rel(rot16, rot32)
+    assert float((sc16 - sc32).abs().max()) <= tol
+    rot_ref, sc_ref, _ = O.rotations_module(x.cpu(), sd)
+    assert _rel(rot16.cpu(), rot_ref) <= BACKBONE_TOL[dtype]["rot"]
+
+
 def test_mclhead_forward_on_its_own():
     """MCLHead.forward (rmcl_manifold_mix_ste.py:290-298) through mp_heads_fwd with K = 1 and no shared post-norm: fp32 like the reference."""
     from manipose_b200.architectures.rmcl_manifold_mix_ste import MCLHead
