@@ -319,11 +319,11 @@ def measure_inference(model, B, dtype, args, world, rank, local_rank, dev, sampl
     counter = {"n": 0}
     sample_every = 4
 
-    def trunk_sampled(self, x2d, n_clips):
+    def trunk_sampled(self, x2d, n_clips, **kw):
         counter["n"] += 1
         ops.GEMM_TIMING = sampled if counter["n"] % sample_every == 1 % sample_every else None
         try:
-            return orig_trunk(self, x2d, n_clips)
+            return orig_trunk(self, x2d, n_clips, **kw)
         finally:
             ops.GEMM_TIMING = None
 
