@@ -887,6 +887,388 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   }
 }
 
+// ===================================================================================== the same, 64 rows per CTA, two accumulators
+// pair_linear_ln_kernel keeps ONE 128 x 512 fp32 accumulator per CTA (all of TMEM), so a tile's epilogue (three passes, HBM bound)
+// and the next tile's main loop cannot overlap: with K = 1024 (fc2) the tensor pipe idles ~2/3 of the time and HBM idles during
+// the main loop (0.62 of the copy bandwidth).  Here the pair multiplies 128 rows per tile (tcgen05.mma.cta_group::2 with M = 128:
+// 64 rows per CTA, whose [64 x 256] fp32 result is folded over the 128 TMEM lanes - lanes 0-63 hold columns 0-127 of the
+// instruction's N = 256, lanes 64-127 columns 128-255 - so a 64 x 512 tile takes 256 TMEM columns), which leaves room for TWO
+// accumulators: the MMA warp runs one tile ahead of the epilogue.  W is pulled through L2 once per 128 rows instead of once per
+// 256 (8 instead of 4 KB per token), which these launches can afford (L2 throughput is at ~40 % in the 256-row kernels).
+//
+// Epilogue mapping: warp w has TMEM lanes 32 (w % 4)...; q = w % 4, grp = (w - 4) / 4, h = q / 2.  A thread owns row 32 (q & 1) + lane
+// of the CTA's 64 and the 128 CONTIGUOUS output columns [256 grp + 128 h, + 128) = four 32-column fp32 boxes (TMEM columns
+// acc * 256 + 128 grp + 32 j): four "column groups" cg = 2 grp + h of two warps each, row statistics combined four ways through
+// shared memory.  Boxes are 64 rows x 128 bytes (8 KB).  Residual boxes arrive through a load ring (kLoad slots per column group,
+// filled by the loader warp, which runs ahead into the next tile), results leave through one store slot per column group.
+constexpr int kRows64 = 64;
+constexpr int kBox64 = kRows64 * 128;                       // 8 KB
+constexpr int kA64 = kRows64 * kBK * 2;                      // 8 KB
+constexpr int kStage64 = kA64 + 2 * kWHalfBytes;             // 40 KB: A | W rows of output columns 0-255 | of columns 256-511
+
+template <typename D, int kStages, int kLoad>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
+                        const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_p,
+                        LnArgs args, int M, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* stage_base = smem;
+  uint8_t* load_base = smem + kStages * kStage64;              // [4][kLoad] residual boxes
+  uint8_t* store_base = load_base + 4 * kLoad * kBox64;        // [4] output boxes
+  uint64_t* full = reinterpret_cast<uint64_t*>(store_base + 4 * kBox64);   // [stages] leader: operands of both CTAs landed
+  uint64_t* empty = full + kStages;                            // [stages] each CTA: stage consumed (multicast commit)
+  uint64_t* tmem_full = empty + kStages;                       // [2] each CTA: accumulator complete (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;                        // [2] leader: drained by the 16 epilogue warps of the pair
+  uint64_t* load_full = tmem_empty + 2;                        // [4 * kLoad] residual box landed
+  uint64_t* load_empty = load_full + 4 * kLoad;                // [4 * kLoad] box consumed (and, if stored from, read by the store)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(load_empty + 4 * kLoad);
+  float2* sx = reinterpret_cast<float2*>(tmem_holder + 4);     // [4][64] row statistics exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = (M + 2 * kRows64 - 1) / (2 * kRows64);
+  const int k_blocks = K / kBK;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const bool has_post = args.post_g != nullptr, has_ln = args.ln_g != nullptr;
+  const bool store_a = !has_post || args.has_xpre != 0;        // pass A hands its value to a TMA store (x_out, or x_pre ahead of the post-norm)
+  const bool store_b = has_post && args.no_x == 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_w);
+    ptx::prefetch_tmap(&tm_r);
+    ptx::prefetch_tmap(&tm_x);
+    if (has_ln) ptx::prefetch_tmap(&tm_h);
+    if (has_post && store_a) ptx::prefetch_tmap(&tm_p);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * kEpiWarps);
+    }
+    for (int s = 0; s < 4 * kLoad; ++s) {
+      ptx::mbar_init(&load_full[s], 1);
+      ptx::mbar_init(&load_empty[s], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== operand producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int row_a = tile * 2 * kRows64 + (int)rank * kRows64;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * kStage64;
+          const uint32_t full_leader = ptx::mapa_shared(smem_u32(&full[stage]), 0);
+          if (leader) ptx::mbar_expect_tx(&full[stage], 2 * kStage64);   // the peer's loads complete_tx on this barrier too
+          ptx::tma_load_2d_pair(sa, &tm_a, full_leader, kb * kBK, row_a);
+          ptx::tma_load_2d_pair(sa + kA64, &tm_w, full_leader, kb * kBK, (int)rank * 128);
+          ptx::tma_load_2d_pair(sa + kA64 + kWHalfBytes, &tm_w, full_leader, kb * kBK, 256 + (int)rank * 128);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===================== MMA issuer: M = 128 per pair, two N = 256 instructions per k-step =====================
+      constexpr uint32_t idesc = ptx::umma_idesc_16(2 * kRows64, 256, D::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t t_acc = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStage64);
+          const uint64_t da = ptx::umma_desc_sw128(sa);
+          const uint64_t db0 = ptx::umma_desc_sw128(sa + kA64);
+          const uint64_t db1 = ptx::umma_desc_sw128(sa + kA64 + kWHalfBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            ptx::umma_f16_pair(t_acc, da + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
+            ptx::umma_f16_pair(t_acc + 128u, da + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, accum);
+          }
+          ptx::umma_commit_pair(&empty[stage]);
+          if (kb == k_blocks - 1) ptx::umma_commit_pair(&tmem_full[acc]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===================== residual loader: box j of column group cg of tile tt is load use nl = 4 tt + j of that group =====================
+      uint32_t tt = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tt) {
+        const int row0 = tile * 2 * kRows64 + (int)rank * kRows64;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t nl = tt * 4u + (uint32_t)j;
+          for (int cg = 0; cg < 4; ++cg) {
+            const uint32_t ls = (uint32_t)(cg * kLoad) + nl % kLoad;
+            if (nl >= (uint32_t)kLoad) ptx::mbar_wait(&load_empty[ls], ((nl / kLoad) & 1) ^ 1);
+            ptx::mbar_expect_tx(&load_full[ls], kBox64);
+            ptx::tma_load_2d(load_base + ls * kBox64, &tm_r, &load_full[ls], (cg >> 1) * 256 + (cg & 1) * 128 + j * 32, row0);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int h = q >> 1;
+    const int cg = 2 * grp + h;                          // column group: output columns [cbase, cbase + 128)
+    const int cbase = 256 * grp + 128 * h;
+    const int row = 32 * (q & 1) + lane;                 // row of the CTA's 64
+    const bool elected = (q & 1) == 0 && lane == 0;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * grp);   // + acc * 256 + 32 j
+    uint8_t* sslot = store_base + cg * kBox64;
+    uint8_t* srow_st = sslot + row * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0, tt = 0;
+    bool pending = false;                                // elected thread: a store from the group's store slot may still be reading it
+
+    // four-way combination of (mean, M2) over the 128-column quarters of a row
+    auto row_stats = [&](float mean_q, float m2_q, float eps, float& mean, float& rstd) {
+      sx[cg * kRows64 + row] = make_float2(mean_q, m2_q);
+      named_bar_sync(5, 256);
+      float2 p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = sx[i * kRows64 + row];
+      named_bar_sync(5, 256);                            // every quarter has read before the buffer is reused
+      mean = 0.25f * ((p[0].x + p[1].x) + (p[2].x + p[3].x));
+      float m2 = (p[0].y + p[1].y) + (p[2].y + p[3].y);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = p[i].x - mean;
+        m2 = fmaf(128.0f * d, d, m2);
+      }
+      rstd = rsqrtf(m2 * (1.0f / 512.0f) + eps);
+    };
+    // store `box` (already written to the group's store slot by all 64 threads) - called by everybody, acts in the elected thread
+    auto store_from_slot = [&](const CUtensorMap* map, int col, int row0) {
+      ptx::fence_proxy_async_smem();
+      named_bar_sync(1 + cg, 64);
+      if (elected) {
+        ptx::tma_store_2d(map, sslot, col, row0);
+        ptx::bulk_commit();
+        pending = true;
+      }
+    };
+    auto slot_writable = [&]() {                         // before anybody writes the store slot again
+      if (elected && pending) {
+        ptx::bulk_wait_read<0>();
+        pending = false;
+      }
+      named_bar_sync(1 + cg, 64);
+    };
+    const int last_pass = has_ln ? 2 : (has_post ? 1 : 0);
+    auto release_acc = [&]() {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+    };
+
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tt) {
+      const int row0 = tile * 2 * kRows64 + (int)rank * kRows64;
+      const int grow = row0 + row;
+      const uint32_t t_row = t_lane + (uint32_t)(acc * 256);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+
+      // ---- pass A: v = resid + scale * (acc + bias); shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      const float scale = (args.row_scale != nullptr && grow < M) ? __ldg(args.row_scale + grow) : 1.0f;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t nl = tt * 4u + (uint32_t)j;
+        const uint32_t ls = (uint32_t)(cg * kLoad) + nl % kLoad;
+        const int col = cbase + 32 * j;
+        uint8_t* lrow = load_base + ls * kBox64 + row * 128;
+        uint32_t r[32];
+        ptx::tmem_ld32(t_row + (uint32_t)(32 * j), r);
+        ptx::mbar_wait(&load_full[ls], (nl / kLoad) & 1);
+        ptx::tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(args.bias + col);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* p = reinterpret_cast<float4*>(lrow + (((uint32_t)c ^ sw) << 4));
+          const float4 bb = __ldg(b4 + c);
+          float4 v = *p;
+          v.x = fmaf(scale, __uint_as_float(r[4 * c + 0]) + bb.x, v.x);   // scale == 1: the same two roundings as v += acc + bias
+          v.y = fmaf(scale, __uint_as_float(r[4 * c + 1]) + bb.y, v.y);
+          v.z = fmaf(scale, __uint_as_float(r[4 * c + 2]) + bb.z, v.z);
+          v.w = fmaf(scale, __uint_as_float(r[4 * c + 3]) + bb.w, v.w);
+          if (j == 0 && c == 0) shift = v.x;
+          const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          r[4 * c + 0] = __float_as_uint(v.x);
+          r[4 * c + 1] = __float_as_uint(v.y);
+          r[4 * c + 2] = __float_as_uint(v.z);
+          r[4 * c + 3] = __float_as_uint(v.w);
+          if (store_a) *p = v;
+        }
+        if (has_post || has_ln) ptx::tmem_st32(t_row + (uint32_t)(32 * j), r);
+        if (store_a) ptx::fence_proxy_async_smem();
+        named_bar_sync(1 + cg, 64);                        // both warps of the column group are done with the residual box
+        if (elected) {
+          if (store_a) {                                   // x (or x_pre) leaves straight from the residual's slot
+            ptx::tma_store_2d(has_post ? &tm_p : &tm_x, load_base + ls * kBox64, col, row0);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<0>();
+          }
+          ptx::mbar_arrive(&load_empty[ls]);
+        }
+      }
+      if (last_pass == 0) release_acc();
+      float mean = 0.f, rstd = 0.f;
+      if (has_post || has_ln) {
+        ptx::tmem_st_wait();
+        const float mq = shift + s1 * (1.0f / 128.0f);
+        const float m2q = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+        row_stats(mq, m2q, has_post ? args.post_eps : args.ln_eps, mean, rstd);
+      }
+
+      // ---- pass B (post-norm): y = LN_post(v) (+ pos-embed) -> x_out and back to TMEM, statistics of y
+      if (has_post) {
+        const float* pos_row = args.pos ? args.pos + (size_t)((grow / args.pos_div) % args.pos_mod) * 512 : nullptr;
+        s1 = 0.f;
+        s2 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int col = cbase + 32 * j;
+          uint32_t r[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(32 * j), r);
+          ptx::tmem_ld_wait();
+          const float4* g4 = reinterpret_cast<const float4*>(args.post_g + col);
+          const float4* be4 = reinterpret_cast<const float4*>(args.post_b + col);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 gg = __ldg(g4 + c), bb = __ldg(be4 + c);
+            float4 y;
+            y.x = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, gg.x, bb.x);
+            y.y = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, gg.y, bb.y);
+            y.z = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, gg.z, bb.z);
+            y.w = fmaf((__uint_as_float(r[4 * c + 3]) - mean) * rstd, gg.w, bb.w);
+            if (pos_row != nullptr && grow < M) {
+              const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + col) + c);
+              y.x += pe.x;
+              y.y += pe.y;
+              y.z += pe.z;
+              y.w += pe.w;
+            }
+            if (j == 0 && c == 0) shift = y.x;
+            const float d0 = y.x - shift, d1 = y.y - shift, d2 = y.z - shift, d3 = y.w - shift;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            r[4 * c + 0] = __float_as_uint(y.x);
+            r[4 * c + 1] = __float_as_uint(y.y);
+            r[4 * c + 2] = __float_as_uint(y.z);
+            r[4 * c + 3] = __float_as_uint(y.w);
+          }
+          if (has_ln) ptx::tmem_st32(t_row + (uint32_t)(32 * j), r);
+          if (store_b) {
+            slot_writable();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(srow_st + (((uint32_t)c ^ sw) << 4)) = make_uint4(r[4 * c + 0], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+            store_from_slot(&tm_x, col, row0);
+          }
+        }
+        if (last_pass == 1) release_acc();
+        if (has_ln) {
+          ptx::tmem_st_wait();
+          const float mq = shift + s1 * (1.0f / 128.0f);
+          const float m2q = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+          row_stats(mq, m2q, args.ln_eps, mean, rstd);
+        }
+      }
+
+      // ---- pass C (pre-norm): h = LN_pre(x) as 16-bit, two 64-column boxes
+      if (has_ln) {
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld32(t_row + (uint32_t)(64 * jj), r0);
+          ptx::tmem_ld32(t_row + (uint32_t)(64 * jj + 32), r1);
+          ptx::tmem_ld_wait();
+          if (jj == 1) release_acc();                      // last TMEM read of the tile: the MMA warp may start tile + 2 here
+          uint4 o[8];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t(&r)[32] = half == 0 ? r0 : r1;
+            const int col = cbase + 64 * jj + 32 * half;
+            const float4* g4 = reinterpret_cast<const float4*>(args.ln_g + col);
+            const float4* be4 = reinterpret_cast<const float4*>(args.ln_b + col);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 g0 = __ldg(g4 + 2 * c), g1 = __ldg(g4 + 2 * c + 1), b0 = __ldg(be4 + 2 * c), b1 = __ldg(be4 + 2 * c + 1);
+              o[half * 4 + c].x = D::pack2(fmaf((__uint_as_float(r[8 * c + 0]) - mean) * rstd, g0.x, b0.x), fmaf((__uint_as_float(r[8 * c + 1]) - mean) * rstd, g0.y, b0.y));
+              o[half * 4 + c].y = D::pack2(fmaf((__uint_as_float(r[8 * c + 2]) - mean) * rstd, g0.z, b0.z), fmaf((__uint_as_float(r[8 * c + 3]) - mean) * rstd, g0.w, b0.w));
+              o[half * 4 + c].z = D::pack2(fmaf((__uint_as_float(r[8 * c + 4]) - mean) * rstd, g1.x, b1.x), fmaf((__uint_as_float(r[8 * c + 5]) - mean) * rstd, g1.y, b1.y));
+              o[half * 4 + c].w = D::pack2(fmaf((__uint_as_float(r[8 * c + 6]) - mean) * rstd, g1.z, b1.z), fmaf((__uint_as_float(r[8 * c + 7]) - mean) * rstd, g1.w, b1.w));
+            }
+          }
+          slot_writable();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(srow_st + (((uint32_t)c ^ sw) << 4)) = o[c];
+          store_from_slot(&tm_h, cbase + 64 * jj, row0);
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (elected) ptx::bulk_wait<0>();
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int pair_ln64_smem(int stages, int load) { return stages * kStage64 + (4 * load + 4) * kBox64 + 512 + 4 * kRows64 * 8; }
+static_assert(pair_ln64_smem(3, 2) <= 232448 && pair_ln64_smem(2, 3) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
 constexpr int pair_ln_smem(int stages, int slots, bool split) { return stages * (kABytes + (split ? 1 : 2) * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
 static_assert(pair_ln_smem(4, 6, true) <= 232448 && pair_ln_smem(3, 4, false) <= 232448 && pair_ln_smem(2, 8, false) <= 232448,
@@ -1003,6 +1385,34 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     return check_launch("pair_linear_ln_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
+  // 64-row tiles with two TMEM accumulators (main loop of the next tile under the epilogue): K >= 1024 (fc2) by default
+  // (MANIPOSE_LN_CFG = 4 / 5: always, with 3 stages + 2 load slots / 2 stages + 3 load slots per column group)
+  if (cfg == 4 || cfg == 5 || (cfg == 0 && K >= 1024)) {
+    CUtensorMap ta6, tr6, tx6, th6, tp6;
+    MP_CHECK(get_tmap(&ta6, A, M, K, kRows64, dtype));
+    MP_CHECK(get_tmap(&tr6, resid, M, N, kRows64, 2));
+    if (x_out)
+      MP_CHECK(get_tmap(&tx6, x_out, M, N, kRows64, 2));
+    else
+      tx6 = tr6;
+    if (ln_gamma)
+      MP_CHECK(get_tmap(&th6, h_out, M, N, kRows64, dtype));
+    else
+      th6 = tx6;
+    if (x_pre)
+      MP_CHECK(get_tmap(&tp6, x_pre, M, N, kRows64, 2));
+    else
+      tp6 = tx6;
+    const int grid64 = pair_grid((int)((M + 127) / 128));
+    auto launch64 = [&](auto kernel, int smem_bytes) -> int {
+      MP_CHECK(set_smem(kernel, smem_bytes));
+      kernel<<<grid64, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta6, tw, tr6, tx6, th6, tp6, args, (int)M, (int)K);
+      return check_launch("pair_linear_ln64_kernel");
+    };
+    if (cfg == 5)
+      return bf ? launch64(pair_linear_ln64_kernel<Bf16, 2, 3>, pair_ln64_smem(2, 3)) : launch64(pair_linear_ln64_kernel<Fp16, 2, 3>, pair_ln64_smem(2, 3));
+    return bf ? launch64(pair_linear_ln64_kernel<Bf16, 3, 2>, pair_ln64_smem(3, 2)) : launch64(pair_linear_ln64_kernel<Fp16, 3, 2>, pair_ln64_smem(3, 2));
+  }
   if (cfg == 1 || (cfg == 0 && K < 1024))
     return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
   if (cfg == 3)      // experiment: 2 x 48 KB operand stages + 8 box slots (more of the residual prefetched under the main loop)
