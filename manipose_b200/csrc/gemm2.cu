@@ -1376,8 +1376,8 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   LnArgs args{bias, post_gamma, post_beta, pos_embed, ln_gamma, ln_beta, x_pre != nullptr, row_scale, x_out == nullptr, post_eps, ln_eps, (int)pos_div, (int)pos_mod};
   const int tiles = (int)((M + 255) / 256);
   const int grid = pair_grid(tiles);
-  // K = 512 (proj): split accumulation, 4 x 32 KB operand stages + 6 box slots; K = 1024 (fc2): single accumulation, 3 x 48 KB
-  // stages + 4 slots (see the kernel's header comment; MANIPOSE_LN_CFG=1 / 2 forces the split / the single variant)
+  // 128-row kernels (MANIPOSE_LN_CFG=1 / 2 / 3): split accumulation with 4 x 32 KB operand stages + 6 box slots; single accumulation
+  // with 3 x 48 KB stages + 4 slots (see the kernel's header comment)
   static const int cfg = getenv("MANIPOSE_LN_CFG") ? atoi(getenv("MANIPOSE_LN_CFG")) : 0;
   auto launch = [&](auto kernel, int smem_bytes) -> int {
     MP_CHECK(set_smem(kernel, smem_bytes));
@@ -1385,9 +1385,12 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     return check_launch("pair_linear_ln_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
-  // 64-row tiles with two TMEM accumulators (main loop of the next tile under the epilogue): K >= 1024 (fc2) by default
-  // (MANIPOSE_LN_CFG = 4 / 5: always, with 3 stages + 2 load slots / 2 stages + 3 load slots per column group)
-  if (cfg == 4 || cfg == 5 || (cfg == 0 && K >= 1024)) {
+  // Default: 64-row tiles with two TMEM accumulators (the main loop of the next tile runs under the epilogue), 3 operand stages + 2
+  // residual slots per column group.  Measured at 528,768 rows (B200, L2 flushed): proj + norm2 539 us (6.03 TB/s = 0.94 of the copy
+  // bandwidth; the 128-row split-accumulation kernel: 580 us), fc2 + post-norm + norm1 750 us (5.05 TB/s = 0.78; the 128-row kernel:
+  // 942 us).  MANIPOSE_LN_CFG = 5: 2 stages + 3 residual slots (slower: 602 / 891 us); 1 / 2 / 3: the 128-row kernels (split /
+  // single accumulation / 2 stages + 8 slots), kept for A/B measurements.
+  if (cfg == 0 || cfg == 4 || cfg == 5) {
     CUtensorMap ta6, tr6, tx6, th6, tp6;
     MP_CHECK(get_tmap(&ta6, A, M, K, kRows64, dtype));
     MP_CHECK(get_tmap(&tr6, resid, M, N, kRows64, 2));
@@ -1413,7 +1416,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
       return bf ? launch64(pair_linear_ln64_kernel<Bf16, 2, 3>, pair_ln64_smem(2, 3)) : launch64(pair_linear_ln64_kernel<Fp16, 2, 3>, pair_ln64_smem(2, 3));
     return bf ? launch64(pair_linear_ln64_kernel<Bf16, 3, 2>, pair_ln64_smem(3, 2)) : launch64(pair_linear_ln64_kernel<Fp16, 3, 2>, pair_ln64_smem(3, 2));
   }
-  if (cfg == 1 || (cfg == 0 && K < 1024))
+  if (cfg == 1)
     return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
   if (cfg == 3)      // experiment: 2 x 48 KB operand stages + 8 box slots (more of the residual prefetched under the main loop)
     return bf ? launch(pair_linear_ln_kernel<Bf16, 2, 8, false>, pair_ln_smem(2, 8, false)) : launch(pair_linear_ln_kernel<Fp16, 2, 8, false>, pair_ln_smem(2, 8, false));
