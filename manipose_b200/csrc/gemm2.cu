@@ -1416,7 +1416,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
       return bf ? launch64(pair_linear_ln64_kernel<Bf16, 2, 3>, pair_ln64_smem(2, 3)) : launch64(pair_linear_ln64_kernel<Fp16, 2, 3>, pair_ln64_smem(2, 3));
     return bf ? launch64(pair_linear_ln64_kernel<Bf16, 3, 2>, pair_ln64_smem(3, 2)) : launch64(pair_linear_ln64_kernel<Fp16, 3, 2>, pair_ln64_smem(3, 2));
   }
-  if (cfg == 1)
+  if (cfg == 1 || (cfg == 9 && K < 1024))      // 9: the round-1 defaults (split accumulation for K = 512, single for K = 1024)
     return bf ? launch(pair_linear_ln_kernel<Bf16, 4, 6, true>, pair_ln_smem(4, 6, true)) : launch(pair_linear_ln_kernel<Fp16, 4, 6, true>, pair_ln_smem(4, 6, true));
   if (cfg == 3)      // experiment: 2 x 48 KB operand stages + 8 box slots (more of the residual prefetched under the main loop)
     return bf ? launch(pair_linear_ln_kernel<Bf16, 2, 8, false>, pair_ln_smem(2, 8, false)) : launch(pair_linear_ln_kernel<Fp16, 2, 8, false>, pair_ln_smem(2, 8, false));
