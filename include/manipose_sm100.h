@@ -161,6 +161,16 @@ int mp_linear_ln(const void* A, const void* W, const float* bias, const float* r
                  int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, const float* row_scale, float* x_pre,
                  int64_t M, int64_t N, int64_t K, int dtype, mp_stream_t stream);
 
+/* The whole MLP branch of a C = 512 block in one launch (Mlp.forward + residual add, mix_ste.py:216-222,356-358, + the LayerNorms
+ * of mp_linear_ln): x = resid + fc2(GELU_erf(fc1(h_in))) with the 1024-wide hidden activation kept on chip (TMEM / shared memory),
+ * then the same epilogue as mp_linear_ln.  h_in [M,512] 16-bit, W1 [1024,512], W2 [512,1024] 16-bit, b1 [1024], b2 [512] fp32.
+ * Same results as mp_linear(MP_EPI_GELU) followed by mp_linear_ln (the hidden activation is rounded to 16 bits in both).
+ * h_out may alias h_in (a tile's rows are resident on chip before any of them is written).  C = 512 and hidden = 1024 only. */
+int mp_mlp_ln(const void* h_in, const void* W1, const float* b1, const void* W2, const float* b2, const float* resid, float* x_out,
+              void* h_out, const float* post_gamma, const float* post_beta, float post_eps, const float* pos_embed, int64_t pos_div,
+              int64_t pos_mod, const float* ln_gamma, const float* ln_beta, float ln_eps, int64_t M, int64_t C, int64_t hidden, int dtype,
+              mp_stream_t stream);
+
 /* LayerNorm family (fp32 statistics over C in {128, 512}; one warp per token).
  *   x_in  [n_tokens, C] fp32
  *   if post_gamma != NULL: x = LN(x_in; post_gamma, post_beta, post_eps)       (shared Spatial_norm /

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mp_linear": (I, [P, P, P, P, P, I64, I64, I64, I, I, P]),
     "mp_linear_gelu2": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
     "mp_linear_ln": (I, [P, P, P, P, P, P, P, P, F, P, I64, I64, P, P, F, P, P, I64, I64, I64, I, P]),
+    "mp_mlp_ln": (I, [P, P, P, P, P, P, P, P, P, P, F, P, I64, I64, P, P, F, I64, I64, I64, I, P]),
     "mp_layernorm": (I, [P, P, P, P, P, F, P, I64, I64, P, P, F, I64, I, I, P]),
     "mp_embed_joints": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, P]),
     "mp_embed_segments": (I, [P, P, P, P, P, P, F, P, P, I64, I, I, I, I, P]),

@@ -204,6 +204,8 @@ class MixSTE(nn.Module):
     compute_dtype = "bf16"
     # fuse the residual Linear with the LayerNorms that follow it (C = 512 only); False keeps the separate kernels
     fuse_layernorm = True
+    # fc1 -> GELU -> fc2 + residual + LayerNorms in ONE launch, hidden activation on chip (C = 512, hidden = 1024 only)
+    fuse_mlp = True
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
@@ -336,6 +338,20 @@ class MixSTE(nn.Module):
             else:
                 ops.linear(h, w[wi + 1], blk.attn.proj.bias, x, L.MP_EPI_RESIDUAL, resid=x)
                 ops.layernorm(x, None, h, ln=(blk.norm2.weight, blk.norm2.bias), ln_eps=blk.norm2.eps, dtype=dt)
+            if fused and self.fuse_mlp and hidden_dim == 1024:
+                # h is read (a tile's 64 rows are resident in shared memory before anything of the tile is written) and rewritten in place
+                if last and head_norm_eps is not None:
+                    one, zero = self._unit_affine(x.device)
+                    ops.mlp_ln(h, w[wi + 2], blk.mlp.fc1.bias, w[wi + 3], blk.mlp.fc2.bias, x, None, h, post=(post.weight, post.bias),
+                               post_eps=post.eps, ln=(one, zero), ln_eps=head_norm_eps)
+                    return h
+                if last:
+                    ops.mlp_ln(h, w[wi + 2], blk.mlp.fc1.bias, w[wi + 3], blk.mlp.fc2.bias, x, x, None)
+                else:
+                    ops.mlp_ln(h, w[wi + 2], blk.mlp.fc1.bias, w[wi + 3], blk.mlp.fc2.bias, x, x, h, post=(post.weight, post.bias),
+                               post_eps=post.eps, pos=pos, pos_div=n_tok, pos_mod=n_frames, ln=(nxt.norm1.weight, nxt.norm1.bias),
+                               ln_eps=nxt.norm1.eps)
+                continue
             ops.linear(h, w[wi + 2], blk.mlp.fc1.bias, hid, L.MP_EPI_GELU)
             if fused:
                 if last and head_norm_eps is not None:

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ln_args.cuh"
 #include "ptx.cuh"
 
 namespace mp {
@@ -495,20 +496,6 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 }
 
 // ===================================================================================== x = resid + A W^T + b (+ LayerNorms), N = 512
-struct LnArgs {
-  const float* bias;
-  const float* post_g;   // NULL: no post-norm
-  const float* post_b;
-  const float* pos;      // NULL or [pos_mod, 512]
-  const float* ln_g;     // NULL: no pre-norm / h output
-  const float* ln_b;
-  int has_xpre;             // with the post-norm: also store the value BEFORE it (tm_p; the training tape needs both)
-  const float* row_scale;   // NULL or [M]: x = resid + row_scale[row] * (A W^T + bias) (per-sample DropPath factor)
-  int no_x;                 // with post-norm AND pre-norm: do not store x_out (only h is wanted: the last block ahead of the heads)
-  float post_eps, ln_eps;
-  int pos_div, pos_mod;
-};
-
 // combine (mean, M2) of the two 256-column halves of a row
 __device__ __forceinline__ void row_stats_exchange(float2* sx, int grp, int row, float mean_h, float m2_h, float eps, float& mean, float& rstd) {
   sx[grp * kBM + row] = make_float2(mean_h, m2_h);

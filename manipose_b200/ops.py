@@ -430,6 +430,28 @@ def linear_ln(a, w, bias, resid, x_out, h_out, post=None, post_eps=1e-6, pos=Non
         timing.append((e0, e1, 2.0 * m * n * k, byts, "linear_ln"))
 
 
+def mlp_ln(h_in, w1, b1, w2, b2, resid, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6):
+    """x_out = [LN_post](resid + fc2(gelu(fc1(h_in)))) [+ pos]; h_out = LN_pre(x_out) as 16-bit — the MLP branch of a C = 512 block in one
+    launch, the hidden activation never leaves the SM.  h_out may alias h_in."""
+    m, c = h_in.shape
+    hidden = w1.shape[0]
+    pg, pb = post if post is not None else (None, None)
+    lg, lb = ln if ln is not None else (None, None)
+    timing = GEMM_TIMING
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = L.load().mp_mlp_ln(L.ptr(h_in), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(resid), L.ptr(x_out), L.ptr(h_out), L.ptr(pg),
+                            L.ptr(pb), post_eps, L.ptr(pos), pos_div, pos_mod, L.ptr(lg), L.ptr(lb), ln_eps, m, c, hidden, DTYPE_CODE[h_in.dtype],
+                            L.stream_ptr())
+    L.check(rc, "mp_mlp_ln")
+    _count()
+    if timing is not None:
+        e1.record()
+        byts = 2.0 * (m * c + 2 * hidden * c) + (8.0 * m * c if x_out is not None else 4.0 * m * c) + (2.0 * m * c if ln is not None else 0.0)
+        timing.append((e0, e1, 4.0 * m * hidden * c, byts, "mlp"))
+
+
 def layernorm(x_in, x_out, h_out, post=None, post_eps=1e-6, pos=None, pos_div=1, pos_mod=1, ln=None, ln_eps=1e-6, dtype=L.MP_DTYPE_BF16):
     n_tokens, c = x_in.shape
     pg, pb = post if post is not None else (None, None)
