@@ -262,7 +262,12 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
           if (tt > 0) ptx::mbar_wait(&l_empty[cg], (2 * tt - 1) & 1);      // box 2 of the previous tile consumed
           ptx::mbar_expect_tx(&l_full[cg], kBox);
           ptx::tma_load_2d(l_base + cg * kBox, &tm_r, &l_full[cg], box_col(cg, 0), row0);
-          if (tt > 0) ptx::mbar_wait(&s_empty[cg], (3 * tt - 1) & 1);      // the previous tile's stores have left the slot
+          if (tt > 0) {
+            // a parity wait can only tell the previous completion from the one before it, so the three completions of a tile are
+            // waited for one by one: box 3 consumed, then the previous tile's stores have left the slot
+            ptx::mbar_wait(&s_empty[cg], (3 * tt - 2) & 1);
+            ptx::mbar_wait(&s_empty[cg], (3 * tt - 1) & 1);
+          }
           ptx::mbar_expect_tx(&s_full[cg], kBox);
           ptx::tma_load_2d(s_base + cg * kBox, &tm_r, &s_full[cg], box_col(cg, 1), row0);
         }
