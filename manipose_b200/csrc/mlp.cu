@@ -95,7 +95,7 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
   uint64_t* l_full = o_empty + 1;                                // [4]
   uint64_t* l_empty = l_full + 4;                                // [4]
   uint64_t* s_full = l_empty + 4;                                // [4]
-  uint64_t* s_empty = s_full + 4;                                // [4] three completions per tile: box 1 consumed, box 3 consumed, stores done
+  uint64_t* s_empty = s_full + 4;                                // [4] two completions per tile: box 1 consumed, stores done (end of tile)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + 4);
   float2* sx = reinterpret_cast<float2*>(tmem_holder + 4);       // [4][64] row statistics exchange
 
@@ -262,12 +262,7 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
           if (tt > 0) ptx::mbar_wait(&l_empty[cg], (2 * tt - 1) & 1);      // box 2 of the previous tile consumed
           ptx::mbar_expect_tx(&l_full[cg], kBox);
           ptx::tma_load_2d(l_base + cg * kBox, &tm_r, &l_full[cg], box_col(cg, 0), row0);
-          if (tt > 0) {
-            // a parity wait can only tell the previous completion from the one before it, so the three completions of a tile are
-            // waited for one by one: box 3 consumed, then the previous tile's stores have left the slot
-            ptx::mbar_wait(&s_empty[cg], (3 * tt - 2) & 1);
-            ptx::mbar_wait(&s_empty[cg], (3 * tt - 1) & 1);
-          }
+          if (tt > 0) ptx::mbar_wait(&s_empty[cg], (2 * tt - 1) & 1);      // the previous tile's stores have left the slot
           ptx::mbar_expect_tx(&s_full[cg], kBox);
           ptx::tma_load_2d(s_base + cg * kBox, &tm_r, &s_full[cg], box_col(cg, 1), row0);
         }
@@ -279,7 +274,7 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
           ptx::mbar_wait(&l_empty[cg], (2 * tt) & 1);
           ptx::mbar_expect_tx(&l_full[cg], kBox);
           ptx::tma_load_2d(l_base + cg * kBox, &tm_r, &l_full[cg], box_col(cg, 2), row0);
-          ptx::mbar_wait(&s_empty[cg], (3 * tt) & 1);
+          ptx::mbar_wait(&s_empty[cg], (2 * tt) & 1);                       // box 1 consumed
           ptx::mbar_expect_tx(&s_full[cg], kBox);
           ptx::tma_load_2d(s_base + cg * kBox, &tm_r, &s_full[cg], box_col(cg, 3), row0);
         }
@@ -434,7 +429,10 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
             ptx::bulk_commit();
             ptx::bulk_wait_read<0>();
           }
-          ptx::mbar_arrive(in_s ? &s_empty[cg] : &l_empty[cg]);
+          // Two completions per tile and barrier, each gated by a load the loader issues only after it has seen the previous one (a
+          // parity wait cannot tell completions two apart): L: box 0 / box 2 consumed; S: box 1 consumed / end of the tile (below) -
+          // box 3 leaving the S slot needs no event of its own.
+          if (j != 3) ptx::mbar_arrive(in_s ? &s_empty[cg] : &l_empty[cg]);
         }
       }
       if (last_pass == 0) release_o();
