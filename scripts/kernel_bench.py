@@ -69,6 +69,25 @@ def main():
         seq = T if mode == 1 else J
         fl_ops = 4.0 * m * seq * 512
         out[f"attn_{nm}"] = {"ms": med, "best_ms": best, "tflops": fl_ops / med / 1e9, "gbs": m * 2048 * 2 / med / 1e6}
+    # K = 5 hypothesis heads: fp32 CUDA-core kernel (mp_heads_fwd) vs the folded 16-bit tensor-core projection (mp_heads_fwd16)
+    kh, d1 = 5, 7
+    xf = torch.randn(m, 512, generator=g, device=dev)
+    xh = torch.randn(m, 512, generator=g, device=dev).bfloat16()
+    hp = [torch.randn(512, generator=g, device=dev) for _ in range(2)]
+    hg, hb = torch.randn(kh, 512, generator=g, device=dev), torch.randn(kh, 512, generator=g, device=dev)
+    hw, hbias = torch.randn(kh, d1, 512, generator=g, device=dev) * 0.02, torch.randn(kh, d1, generator=g, device=dev)
+    sw, sb = torch.randn(kh, 17, generator=g, device=dev), torch.randn(kh, generator=g, device=dev)
+    rot = torch.empty(clips, kh, T, J, 6, device=dev)
+    lg = torch.empty(clips, kh, T, device=dev)
+    med, _ = timeit(lambda: ops.heads_fwd(xf, hp[0], hp[1], 1e-6, hg, hb, hw, hbias, sw, sb, rot, lg, clips, T, kh, 6, True))
+    out["heads_fp32"] = {"ms": med, "gbs": (m * 2048 + rot.numel() * 4) / med / 1e6}
+    wf16 = torch.zeros(128, 512, device=dev).bfloat16()
+    bfold = torch.zeros(128, device=dev)
+    ws = torch.empty(m * 128, device=dev)
+    med, _ = timeit(lambda: ops.heads_fwd16(xh, wf16, bfold, sw, sb, rot, lg, ws, clips, T, kh, 6, True))
+    out["heads_tensor_core"] = {"ms": med, "gbs": (m * 1024 + rot.numel() * 4) / med / 1e6,
+                                "note": "algorithmic bytes: 16-bit normalised input + rot/logits out; the fp32 [tokens, 128] intermediate adds 2 x 512 B per token"}
+    del xf, xh, ws
     x = torch.randn(m, 512, generator=g, device=dev)
     h = torch.empty(m, 512, dtype=torch.bfloat16, device=dev)
     p = [torch.randn(512, generator=g, device=dev) for _ in range(4)]
