@@ -50,10 +50,13 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one pair_linear_ln_kernel launch (proj + norm2, M = 528,768 rows = the default 128-clip
-# micro-batch) from the committed `ncu --set full` capture profiles/r1b_pair_linear_ln_full_128clips.csv; algorithmic bytes of that launch
-PROFILED_TRAFFIC_LN = {"bytes_per_launch": 3267.0e6, "algorithmic_bytes": 3249.3e6, "launch": "proj + norm2, M=528768 (128 clips), K=512",
-                       "source": "profiles/r1b_pair_linear_ln_full_128clips.csv"}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the residual Linear + LayerNorm kernel (pair_linear_ln64_kernel, M = 528,768 rows
+# = the default 128-clip micro-batch) from the committed `ncu --set full` capture profiles/r2_ln64_tc3_full.csv, averaged over its two uses
+# per block like `achieved` (proj + norm2: 3.191 GB against 3.249 GB algorithmic; fc2 + post-norm + norm1: 3.734 GB against 3.791 GB)
+PROFILED_TRAFFIC_LN = {"bytes_per_launch": 3462.5e6, "algorithmic_bytes": 3520.2e6,
+                       "launches": {"proj + norm2 (K=512)": {"dram_bytes": 3191.0e6, "algorithmic_bytes": 3249.3e6, "us_under_ncu": 537.5},
+                                    "fc2 + post-norm + norm1 (K=1024)": {"dram_bytes": 3734.2e6, "algorithmic_bytes": 3790.7e6, "us_under_ncu": 746.7}},
+                       "launch": "M=528768 (128 clips)", "source": "profiles/r2_ln64_tc3_full.csv, profiles/r2_launch_and_kernel_summary.md"}
 
 
 def roofline_object(dom, rl, peaks, step_tflops, traffic):
@@ -64,7 +67,8 @@ def roofline_object(dom, rl, peaks, step_tflops, traffic):
     out = {}
     if dom == "linear_ln":
         a = rl[dom]["gbs"]
-        out = {"bound": "hbm", "kernel": "pair_linear_ln_kernel (tcgen05 cta_group::2 residual GEMM + fused LayerNorm epilogue: proj / fc2)",
+        out = {"bound": "hbm", "kernel": "pair_linear_ln64_kernel (tcgen05 cta_group::2 residual GEMM + fused LayerNorm epilogue on 64-row tiles, "
+                                        "two TMEM accumulators: proj / fc2)",
                "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "traffic": traffic.get(dom),
                "peak_source": f"{peaks['src']} (STREAM-style copy)"}
     else:
