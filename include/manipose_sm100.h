@@ -65,11 +65,14 @@ int mp_set_skeleton(int num_joints, const int32_t* host_parents, const float* ho
 int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root, const float* logits,
                    float* poses, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames,
                    int rot_rep_dim, int flags, mp_stream_t stream);
-/* Backward of the above w.r.t. rot6d, bone_len (summed over a clip's poses; the caller zeroes
- * grad_bone_len first) and root (grad_root may be NULL). Recomputes rotations from rot6d. */
+/* Backward of the above w.r.t. rot6d, bone_len (summed over a clip's poses in a fixed order: run-to-run identical; grad_bone_len
+ * [n_clips, 16] is overwritten) and root (grad_root may be NULL).  Recomputes rotations from rot6d.
+ * workspace >= mp_decoder_bwd_workspace_bytes(n_clips, n_hyp, n_frames): the per-tile partial rows of the bone-length sums. */
+size_t mp_decoder_bwd_workspace_bytes(int64_t n_clips, int64_t n_hyp, int64_t n_frames);
 int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_poses,
                    float* grad_rot6d, float* grad_bone_len, float* grad_root, int64_t n_clips,
-                   int64_t n_hyp, int64_t n_frames, int rot_rep_dim, mp_stream_t stream);
+                   int64_t n_hyp, int64_t n_frames, int rot_rep_dim, void* workspace,
+                   size_t workspace_bytes, mp_stream_t stream);
 /* softmax over n_hyp alone (scores_logits.softmax(dim=1), rmcl_manifold_mix_ste.py:262); [n_clips, n_hyp, n_frames]. */
 int mp_softmax_hyp_fwd(const float* logits, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames,
                        mp_stream_t stream);

@@ -30,7 +30,8 @@ SIGNATURES = {
     "mp_device_check": (I, []),
     "mp_set_skeleton": (I, [I, ctypes.POINTER(c_int32), ctypes.POINTER(c_float)]),
     "mp_decoder_fwd": (I, [P, P, P, P, P, P, I64, I64, I64, I, I, P]),
-    "mp_decoder_bwd": (I, [P, P, P, P, P, P, I64, I64, I64, I, P]),
+    "mp_decoder_bwd_workspace_bytes": (c_size_t, [I64, I64, I64]),
+    "mp_decoder_bwd": (I, [P, P, P, P, P, P, I64, I64, I64, I, P, c_size_t, P]),
     "mp_softmax_hyp_fwd": (I, [P, P, I64, I64, I64, P]),
     "mp_softmax_hyp_bwd": (I, [P, P, P, I64, I64, I64, P]),
     "mp_wta_fwd": (I, [P, P, P, I, P, P, P, I64, I64, I64, P]),

@@ -16,7 +16,10 @@
 // mul/add/sub, sqrt, max, three divisions, sequential k-loop of the 3x3 products), so poses are bit-identical to the
 // oracle's correctly-rounded restatement (oracle.pose_decoder_ieee) and within ~1e-7 relative of the torch-CPU reference
 // (whose vectorised sqrt is itself 1 ulp off on ~0.7 % of inputs).  FAST mode uses rsqrt and FMA contraction (<= 1e-6).
+#include <algorithm>
+
 #include "common.cuh"
+#include "ieee.cuh"
 #include "ptx.cuh"
 
 namespace mp {
@@ -31,16 +34,31 @@ constexpr int tile_in_bytes() { return kTile * kJ * RD * 4; }   // 13056 / 8704
 constexpr int kTileOutBytes = kTile * kOut * 4;  // 6528
 constexpr int kWarpsPerCta = 4;
 
-template <bool kExact>
+// Arithmetic modes: kFast (rsqrt, FMA contraction), kIeee (every operation one correctly rounded IEEE intrinsic: the reference's
+// sequence, with the range checks and slow paths of sqrt.rn / div.rn), kExact (the same results from the branch-free refinement
+// sequences of ieee.cuh; operands outside their range only raise `bad`, and the caller redoes that pose in kIeee mode).
+enum { kFast = 0, kIeee = 1, kExact = 2 };
+
+template <int kMode>
 struct Arith {
-  static __device__ __forceinline__ float mul(float a, float b) { return kExact ? __fmul_rn(a, b) : a * b; }
-  static __device__ __forceinline__ float add(float a, float b) { return kExact ? __fadd_rn(a, b) : a + b; }
-  static __device__ __forceinline__ float sub(float a, float b) { return kExact ? __fsub_rn(a, b) : a - b; }
+  static __device__ __forceinline__ float mul(float a, float b) { return kMode != kFast ? __fmul_rn(a, b) : a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return kMode != kFast ? __fadd_rn(a, b) : a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return kMode != kFast ? __fsub_rn(a, b) : a - b; }
   // v / max(sqrt(v.v), 1e-8)   (rotation_tools.py:6-17)
-  static __device__ __forceinline__ void normalize(float& x, float& y, float& z) {
-    if (kExact) {
-      float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-      float m = fmaxf(__fsqrt_rn(s), 1e-8f);
+  static __device__ __forceinline__ void normalize(float& x, float& y, float& z, uint32_t& bad) {
+    if (kMode == kExact) {
+      const float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      const float lo = fminf(fminf(fabsf(x), fabsf(y)), fabsf(z));
+      // one range check for the square root and the three divisions: s in [2^-80, 2^80], every |component| >= 2^-100
+      bad |= (uint32_t)((__float_as_uint(s) - 0x17800000u) > 0x50000000u) | (uint32_t)(__float_as_uint(lo) < 0x0d800000u);
+      const float m = fmaxf(ieee::sqrt_rn_core(s), 1e-8f);
+      const float r = ieee::rcp_refined(m);
+      x = ieee::div_rn_core(x, m, r);
+      y = ieee::div_rn_core(y, m, r);
+      z = ieee::div_rn_core(z, m, r);
+    } else if (kMode == kIeee) {
+      const float s = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      const float m = fmaxf(__fsqrt_rn(s), 1e-8f);
       x = __fdiv_rn(x, m);
       y = __fdiv_rn(y, m);
       z = __fdiv_rn(z, m);
@@ -71,12 +89,21 @@ struct PoseState {
   float rw[kJ][9];   // world rotations, row-major (leaves never stored: forward_kinematics.py:41-46)
   float pos[kOut];   // joint positions
   float t[kJ][2];    // T-pose x / y coordinates (z is identically 0)
+  uint32_t bad;      // kExact: some operand left the range of the branch-free sqrt / division sequences
 };
 
 // v / max(sqrt(v.v), 1e-8) for a 2-vector (compute_rotation_matrix_from_ortho4d uses normalize_vector on [M,2] rows)
-template <bool kExact>
-__device__ __forceinline__ void normalize2(float& x, float& y) {
-  if (kExact) {
+template <int kMode>
+__device__ __forceinline__ void normalize2(float& x, float& y, uint32_t& bad) {
+  if (kMode == kExact) {
+    const float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    const float lo = fminf(fabsf(x), fabsf(y));
+    bad |= (uint32_t)((__float_as_uint(s) - 0x17800000u) > 0x50000000u) | (uint32_t)(__float_as_uint(lo) < 0x0d800000u);   // see Arith::normalize
+    const float m = fmaxf(ieee::sqrt_rn_core(s), 1e-8f);
+    const float r = ieee::rcp_refined(m);
+    x = ieee::div_rn_core(x, m, r);
+    y = ieee::div_rn_core(y, m, r);
+  } else if (kMode == kIeee) {
     const float m = fmaxf(__fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), 1e-8f);
     x = __fdiv_rn(x, m);
     y = __fdiv_rn(y, m);
@@ -89,9 +116,9 @@ __device__ __forceinline__ void normalize2(float& x, float& y) {
 }
 
 // local rotation of joint j, row-major r[row][col]
-template <bool kExact, int RD>
-__device__ __forceinline__ void local_rotation(const float* __restrict__ a, float (&r)[9]) {
-  using A = Arith<kExact>;
+template <int kMode, int RD>
+__device__ __forceinline__ void local_rotation(const float* __restrict__ a, float (&r)[9], uint32_t& bad) {
+  using A = Arith<kMode>;
   if constexpr (RD == 6) {
     // ---- 6-D -> rotation matrix with columns [x y z]  (rotation_tools.py:35-57)
     const float2 v01 = *reinterpret_cast<const float2*>(a + 0);
@@ -99,10 +126,10 @@ __device__ __forceinline__ void local_rotation(const float* __restrict__ a, floa
     const float2 v45 = *reinterpret_cast<const float2*>(a + 4);
     float x0 = v01.x, x1 = v01.y, x2 = v23.x;
     const float b0 = v23.y, b1 = v45.x, b2 = v45.y;
-    A::normalize(x0, x1, x2);
+    A::normalize(x0, x1, x2, bad);
     float z0, z1, z2;
     A::cross(x0, x1, x2, b0, b1, b2, z0, z1, z2);
-    A::normalize(z0, z1, z2);
+    A::normalize(z0, z1, z2, bad);
     float y0, y1, y2;
     A::cross(z0, z1, z2, x0, x1, x2, y0, y1, y2);
     r[0] = x0; r[1] = y0; r[2] = z0;
@@ -115,19 +142,19 @@ __device__ __forceinline__ void local_rotation(const float* __restrict__ a, floa
     const float2 th = *reinterpret_cast<const float2*>(a + 0);
     const float2 ph = *reinterpret_cast<const float2*>(a + 2);
     float ct = th.x, st = th.y, cp = ph.x, sp = ph.y;
-    normalize2<kExact>(ct, st);
-    normalize2<kExact>(cp, sp);
+    normalize2<kMode>(ct, st, bad);
+    normalize2<kMode>(cp, sp, bad);
     r[0] = st;  r[1] = A::mul(ct, cp); r[2] = -A::mul(ct, sp);
     r[3] = -ct; r[4] = A::mul(st, cp); r[5] = -A::mul(st, sp);
     r[6] = 0.f; r[7] = sp;             r[8] = cp;
   }
 }
 
-template <bool kExact, int RD, int j>
+template <int kMode, int RD, int j>
 __device__ __forceinline__ void decode_joint(PoseState& st, const float* __restrict__ lane_in, const float* __restrict__ len) {
-  using A = Arith<kExact>;
+  using A = Arith<kMode>;
   float r[9];
-  local_rotation<kExact, RD>(lane_in + j * RD, r);
+  local_rotation<kMode, RD>(lane_in + j * RD, r, st.bad);
   if constexpr (j == 0) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) st.rw[0][i] = r[i];
@@ -162,7 +189,22 @@ __device__ __forceinline__ void decode_joint(PoseState& st, const float* __restr
       }
     }
   }
-  if constexpr (j + 1 < kJ) decode_joint<kExact, RD, j + 1>(st, lane_in, len);
+  if constexpr (j + 1 < kJ) decode_joint<kMode, RD, j + 1>(st, lane_in, len);
+}
+
+// The cold path of kExact: one pose with the IEEE intrinsics, out of line so that its 136 slow-path call sites stay out of the kernel's
+// instruction stream.  The 51 results go through local memory.
+template <int RD>
+__device__ __noinline__ void decode_pose_ieee(const float* __restrict__ lane_in, const float* __restrict__ len, float r0, float r1, float r2,
+                                              float* __restrict__ out) {
+  PoseState st;
+  st.bad = 0;
+  st.pos[0] = r0;
+  st.pos[1] = r1;
+  st.pos[2] = r2;
+  decode_joint<kIeee, RD, 0>(st, lane_in, len);
+#pragma unroll
+  for (int i = 0; i < kOut; ++i) out[i] = st.pos[i];
 }
 
 // softmax over the hypothesis dim, one (clip, frame) per thread, grid-stride
@@ -181,7 +223,7 @@ __device__ __forceinline__ void softmax_hyp_rows(const float* __restrict__ logit
   }
 }
 
-template <bool kExact, int RD>
+template <bool kBitExact, int RD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
                    const float* __restrict__ logits, float* __restrict__ poses, float* __restrict__ scores, uint32_t n_poses,
@@ -249,7 +291,15 @@ decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
       } else {
         st.pos[0] = st.pos[1] = st.pos[2] = 0.f;
       }
-      decode_joint<kExact, RD, 0>(st, tile + lane * kIn, len);
+      st.bad = 0;
+      const float r0 = st.pos[0], r1 = st.pos[1], r2 = st.pos[2];
+      decode_joint<(kBitExact ? kExact : kFast), RD, 0>(st, tile + lane * kIn, len);
+      if (kBitExact && st.bad) {   // rare (zero / denormal / huge components): redo this pose with the IEEE intrinsics
+        float redo[kOut];
+        decode_pose_ieee<RD>(tile + lane * kIn, len, r0, r1, r2, redo);
+#pragma unroll
+        for (int i = 0; i < kOut; ++i) st.pos[i] = redo[i];
+      }
     }
     __syncwarp();  // every lane is done reading the tile: reuse it for the output
 
@@ -310,29 +360,31 @@ struct BwdCtx {
   float glen[kBones];  // gradient w.r.t. the bone lengths (this pose's contribution)
 };
 
-__device__ __forceinline__ void gs_forward(const float* a6, float (&x)[3], float (&z)[3], float (&y)[3], float& na, float& nw,
-                                           float (&w)[3]) {
+// 1 / max(sqrt(s), 1e-8) and the clamp flag.  The backward recompute needs x, y, z to gradient accuracy, not bit-exactly: one MUFU.RSQ
+// (2^-22 relative) instead of an IEEE square root and division with their range checks and slow-path branches.
+__device__ __forceinline__ float inv_norm(float s, bool& clamped) {
+  clamped = !(s > 1e-16f);
+  return clamped ? 1e8f : ieee::mufu_rsq(s);
+}
+
+__device__ __forceinline__ void gs_forward(const float* a6, float (&x)[3], float (&z)[3], float (&y)[3], float& ina, float& inw,
+                                           bool& a_clamped, bool& w_clamped) {
   const float a0 = a6[0], a1 = a6[1], a2 = a6[2], b0 = a6[3], b1 = a6[4], b2 = a6[5];
-  // the backward recompute needs x, y, z to gradient accuracy, not bit-exactly: one reciprocal per normalisation instead of three
-  // IEEE divisions (the kernel is issue-bound: ~5k instructions per pose)
-  na = fmaxf(sqrtf(a0 * a0 + a1 * a1 + a2 * a2), 1e-8f);
-  const float ina = 1.0f / na;
+  ina = inv_norm(a0 * a0 + a1 * a1 + a2 * a2, a_clamped);
   x[0] = a0 * ina; x[1] = a1 * ina; x[2] = a2 * ina;
-  w[0] = x[1] * b2 - x[2] * b1;
-  w[1] = x[2] * b0 - x[0] * b2;
-  w[2] = x[0] * b1 - x[1] * b0;
-  nw = fmaxf(sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]), 1e-8f);
-  const float inw = 1.0f / nw;
-  z[0] = w[0] * inw; z[1] = w[1] * inw; z[2] = w[2] * inw;
+  const float w0 = x[1] * b2 - x[2] * b1;
+  const float w1 = x[2] * b0 - x[0] * b2;
+  const float w2 = x[0] * b1 - x[1] * b0;
+  inw = inv_norm(w0 * w0 + w1 * w1 + w2 * w2, w_clamped);
+  z[0] = w0 * inw; z[1] = w1 * inw; z[2] = w2 * inw;
   y[0] = z[1] * x[2] - z[2] * x[1];
   y[1] = z[2] * x[0] - z[0] * x[2];
   y[2] = z[0] * x[1] - z[1] * x[0];
 }
 
-// gradient of v / max(|v|, 1e-8) given the normalised vector u, the clamped norm n and the upstream gradient gu
-__device__ __forceinline__ void normalize_bwd(const float (&u)[3], float n, bool clamped, const float (&gu)[3], float (&gv)[3]) {
+// gradient of v / max(|v|, 1e-8) given the normalised vector u, the inverse of the clamped norm and the upstream gradient gu
+__device__ __forceinline__ void normalize_bwd(const float (&u)[3], float inv, bool clamped, const float (&gu)[3], float (&gv)[3]) {
   const float d = clamped ? 0.f : (u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2]);
-  const float inv = 1.0f / n;
   gv[0] = (gu[0] - u[0] * d) * inv;
   gv[1] = (gu[1] - u[1] * d) * inv;
   gv[2] = (gu[2] - u[2] * d) * inv;
@@ -344,19 +396,20 @@ struct Children;
 template <int RD, int j>
 __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], float (&g_rwp)[9], float (&g_posp)[3]) {
   // ---- forward recompute for this joint
-  float x[3], y[3], z[3], w[3], na, nw;      // 6-D intermediates
-  float ct, st, cp, sp, nt, np_;             // 4-D intermediates
+  float x[3], y[3], z[3], ina, inw;          // 6-D intermediates
+  float ct, st, cp, sp, int_, inp;           // 4-D intermediates
+  bool clamp_a, clamp_b;                     // norm clamped at 1e-8 (first / second normalisation)
   float r[9];
   if constexpr (RD == 6) {
-    gs_forward(ctx.r6 + j * 6, x, z, y, na, nw, w);
+    gs_forward(ctx.r6 + j * 6, x, z, y, ina, inw, clamp_a, clamp_b);
     r[0] = x[0]; r[1] = y[0]; r[2] = z[0];
     r[3] = x[1]; r[4] = y[1]; r[5] = z[1];
     r[6] = x[2]; r[7] = y[2]; r[8] = z[2];
   } else {
     const float* a4 = ctx.r6 + j * 4;
-    nt = fmaxf(sqrtf(a4[0] * a4[0] + a4[1] * a4[1]), 1e-8f);
-    np_ = fmaxf(sqrtf(a4[2] * a4[2] + a4[3] * a4[3]), 1e-8f);
-    ct = a4[0] / nt; st = a4[1] / nt; cp = a4[2] / np_; sp = a4[3] / np_;
+    int_ = inv_norm(a4[0] * a4[0] + a4[1] * a4[1], clamp_a);
+    inp = inv_norm(a4[2] * a4[2] + a4[3] * a4[3], clamp_b);
+    ct = a4[0] * int_; st = a4[1] * int_; cp = a4[2] * inp; sp = a4[3] * inp;
     r[0] = st;  r[1] = ct * cp; r[2] = -ct * sp;
     r[3] = -ct; r[4] = st * cp; r[5] = -st * sp;
     r[6] = 0.f; r[7] = sp;      r[8] = cp;
@@ -409,12 +462,12 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
     const float g_st = g_r[0] + g_r[4] * cp - g_r[5] * sp;
     const float g_cp = g_r[1] * ct + g_r[4] * st + g_r[8];
     const float g_sp = -g_r[2] * ct - g_r[5] * st + g_r[7];
-    const float dt = nt <= 1e-8f ? 0.f : ct * g_ct + st * g_st;
-    const float dp = np_ <= 1e-8f ? 0.f : cp * g_cp + sp * g_sp;
-    ctx.r6[j * 4 + 0] = (g_ct - ct * dt) / nt;
-    ctx.r6[j * 4 + 1] = (g_st - st * dt) / nt;
-    ctx.r6[j * 4 + 2] = (g_cp - cp * dp) / np_;
-    ctx.r6[j * 4 + 3] = (g_sp - sp * dp) / np_;
+    const float dt = clamp_a ? 0.f : ct * g_ct + st * g_st;
+    const float dp = clamp_b ? 0.f : cp * g_cp + sp * g_sp;
+    ctx.r6[j * 4 + 0] = (g_ct - ct * dt) * int_;
+    ctx.r6[j * 4 + 1] = (g_st - st * dt) * int_;
+    ctx.r6[j * 4 + 2] = (g_cp - cp * dp) * inp;
+    ctx.r6[j * 4 + 3] = (g_sp - sp * dp) * inp;
     return;
   }
   // ---- Gram-Schmidt backward (rotation_tools.py:35-57): columns of G_R are the gradients of x, y, z
@@ -430,7 +483,7 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
   gx[2] += gy[0] * z[1] - gy[1] * z[0];
   // z = w / max(|w|, eps)
   float gw[3];
-  normalize_bwd(z, nw, nw <= 1e-8f, gz, gw);
+  normalize_bwd(z, inw, clamp_b, gz, gw);
   // w = x x b
   const float b[3] = {ctx.r6[j * 6 + 3], ctx.r6[j * 6 + 4], ctx.r6[j * 6 + 5]};
   gx[0] += b[1] * gw[2] - b[2] * gw[1];
@@ -438,7 +491,7 @@ __device__ __forceinline__ void bwd_joint(BwdCtx& ctx, const float (&rwp)[9], fl
   gx[2] += b[0] * gw[1] - b[1] * gw[0];
   const float gb[3] = {gw[1] * x[2] - gw[2] * x[1], gw[2] * x[0] - gw[0] * x[2], gw[0] * x[1] - gw[1] * x[0]};
   float ga[3];
-  normalize_bwd(x, na, na <= 1e-8f, gx, ga);
+  normalize_bwd(x, ina, clamp_a, gx, ga);
   ctx.r6[j * 6 + 0] = ga[0];
   ctx.r6[j * 6 + 1] = ga[1];
   ctx.r6[j * 6 + 2] = ga[2];
@@ -459,14 +512,18 @@ struct Children<RD, j, kJ> {
   static __device__ __forceinline__ void run(BwdCtx&, const float (&)[9], float (&)[9], float (&)[3]) {}
 };
 
-constexpr int kBwdWarps = 5;   // 19.6 KB of staging per warp: 2 CTAs x 5 warps fill the 227 KB of shared memory
+constexpr int kBwdWarps = 11;  // 19.6 KB of staging per warp: one CTA of 11 independent warps fills the 227 KB of shared memory
 template <int RD>
 constexpr int bwd_warp_bytes() { return tile_in_bytes<RD>() + kTileOutBytes; }   // rot / grad_rot tile + grad_poses tile
 
+// Bone-length gradients are summed over a clip's poses in a fixed order: every warp tile writes one partial row (16 bones) per clip it
+// touches into glen_part[clip][tile - first tile of the clip], and bone_grad_reduce_kernel adds a clip's rows front to back.
+__host__ __device__ __forceinline__ uint32_t glen_slots(uint32_t poses_per_clip) { return (poses_per_clip + kTile - 2) / kTile + 1; }
+
 template <int RD>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+__global__ void __launch_bounds__(kBwdWarps * 32, 1)
 decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ grad_poses,
-                   float* __restrict__ grad_rot6d, float* __restrict__ grad_bone_len, float* __restrict__ grad_root, uint32_t n_poses,
+                   float* __restrict__ grad_rot6d, float* __restrict__ glen_part, float* __restrict__ grad_root, uint32_t n_poses,
                    uint32_t poses_per_clip, int bulk_ok) {
   constexpr int kIn = in_floats<RD>();
   constexpr int kTileInBytes = tile_in_bytes<RD>();
@@ -484,7 +541,7 @@ decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
 
   const uint32_t n_tiles = (n_poses + kTile - 1) / kTile;
   uint32_t phase = 0;
-  for (uint32_t tile_idx = blockIdx.x * kBwdWarps + warp; tile_idx < n_tiles; tile_idx += gridDim.x * kBwdWarps) {
+  for (uint32_t tile_idx = warp * gridDim.x + blockIdx.x; tile_idx < n_tiles; tile_idx += gridDim.x * kBwdWarps) {   // few tiles: one per SM first
     const uint32_t pose0 = tile_idx * kTile;
     const uint32_t n_here = min((uint32_t)kTile, n_poses - pose0);
     const bool full = bulk_ok && (n_here == kTile);
@@ -529,18 +586,17 @@ decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
         grad_root[(size_t)pose * 3 + 2] = g_root[2];
       }
     }
-    // bone-length gradient: sum over the clip's poses.  Lanes of one warp almost always share a clip.
-    const uint32_t clip0 = __shfl_sync(0xffffffffu, clip, 0);
-    const bool uniform = __all_sync(0xffffffffu, clip == clip0);
-    if (uniform) {
+    // bone-length gradient: one partial row per clip this tile touches (almost always one), butterfly sums in a fixed order
+    const uint32_t clip_first = pose0 / poses_per_clip, clip_last = (pose0 + n_here - 1) / poses_per_clip;
+    const uint32_t slots = glen_slots(poses_per_clip);
+    for (uint32_t c = clip_first; c <= clip_last; ++c) {
+      const bool mine = active && clip == c;
+      float* row = glen_part + ((size_t)c * slots + (tile_idx - (c * poses_per_clip) / kTile)) * kBones;
 #pragma unroll
       for (int i = 0; i < kBones; ++i) {
-        const float s = warp_sum(ctx.glen[i]);
-        if (lane == 0) atomicAdd(grad_bone_len + (size_t)clip0 * kBones + i, s);
+        const float sum = warp_sum(mine ? ctx.glen[i] : 0.f);
+        if (lane == i) row[i] = sum;
       }
-    } else if (active) {
-#pragma unroll
-      for (int i = 0; i < kBones; ++i) atomicAdd(grad_bone_len + (size_t)clip * kBones + i, ctx.glen[i]);
     }
 
     if (full) {
@@ -558,6 +614,19 @@ decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
       __syncwarp();
     }
   }
+}
+
+// grad_bone_len[clip][bone] = sum of the clip's partial rows, front to back
+__global__ void bone_grad_reduce_kernel(const float* __restrict__ glen_part, float* __restrict__ grad_bone_len, uint32_t n_clips,
+                                        uint32_t poses_per_clip) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_clips * kBones) return;
+  const uint32_t c = idx / kBones, i = idx - c * kBones;
+  const uint32_t first = (c * poses_per_clip) / kTile, last = ((c + 1) * poses_per_clip - 1) / kTile;
+  const float* row = glen_part + (size_t)c * glen_slots(poses_per_clip) * kBones + i;
+  float sum = 0.f;
+  for (uint32_t t = first; t <= last; ++t) sum += row[(size_t)(t - first) * kBones];
+  grad_bone_len[idx] = sum;
 }
 
 }  // namespace
@@ -601,8 +670,14 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   return check_launch("decoder_fwd_kernel");
 }
 
+size_t mp_decoder_bwd_workspace_bytes(int64_t n_clips, int64_t n_hyp, int64_t n_frames) {
+  if (n_clips <= 0 || n_hyp <= 0 || n_frames <= 0) return 0;
+  return (size_t)n_clips * mp::glen_slots((uint32_t)(n_hyp * n_frames)) * mp::kBones * sizeof(float);
+}
+
 int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_poses, float* grad_rot6d, float* grad_bone_len,
-                   float* grad_root, int64_t n_clips, int64_t n_hyp, int64_t n_frames, int rot_rep_dim, mp_stream_t stream) {
+                   float* grad_root, int64_t n_clips, int64_t n_hyp, int64_t n_frames, int rot_rep_dim, void* workspace,
+                   size_t workspace_bytes, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(rot_rep_dim == 4 || rot_rep_dim == 6, MP_EINVAL, "Unsupported rotations representation dimension: %d", rot_rep_dim);
@@ -611,19 +686,25 @@ int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_
   if (n_poses == 0) return MP_OK;
   MP_REQUIRE(n_poses < (int64_t)1 << 31, MP_EINVAL, "mp_decoder_bwd: %lld poses exceed 2^31", (long long)n_poses);
   MP_REQUIRE(rot6d && bone_len && grad_poses && grad_rot6d && grad_bone_len, MP_EINVAL, "mp_decoder_bwd: null pointer");
+  MP_REQUIRE(workspace && workspace_bytes >= mp_decoder_bwd_workspace_bytes(n_clips, n_hyp, n_frames), MP_EINVAL,
+             "mp_decoder_bwd: workspace of %zu bytes, need %zu", workspace_bytes, mp_decoder_bwd_workspace_bytes(n_clips, n_hyp, n_frames));
   const int bulk_ok = aligned16(rot6d) && aligned16(grad_poses) && aligned16(grad_rot6d);
   const size_t smem = (size_t)kBwdWarps * (rot_rep_dim == 6 ? bwd_warp_bytes<6>() : bwd_warp_bytes<4>()) + kBwdWarps * sizeof(uint64_t);
   const int64_t n_tiles = (n_poses + kTile - 1) / kTile;
-  int64_t ctas = (n_tiles + kBwdWarps - 1) / kBwdWarps;
-  const int64_t max_ctas = (int64_t)sm_count() * 2;
-  if (ctas > max_ctas) ctas = max_ctas;
+  // small problems (the training step decodes a few thousand poses): spread the tiles over all SMs rather than 11 to a CTA
+  int64_t ctas = std::min<int64_t>(n_tiles, sm_count());
+  float* part = static_cast<float*>(workspace);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(rot6d, bone_len, grad_poses, grad_rot6d, grad_bone_len, grad_root,
+    kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(rot6d, bone_len, grad_poses, grad_rot6d, part, grad_root,
                                                                          (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), bulk_ok);
   };
   if (rot_rep_dim == 6) launch(decoder_bwd_kernel<6>); else launch(decoder_bwd_kernel<4>);
-  return check_launch("decoder_bwd_kernel");
+  MP_CHECK(check_launch("decoder_bwd_kernel"));
+  const int64_t n_out = n_clips * kBones;
+  bone_grad_reduce_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream>>>(part, grad_bone_len, (uint32_t)n_clips,
+                                                                                           (uint32_t)(n_hyp * n_frames));
+  return check_launch("bone_grad_reduce_kernel");
 }
 
 int mp_softmax_hyp_fwd(const float* logits, float* scores, int64_t n_clips, int64_t n_hyp, int64_t n_frames, mp_stream_t stream) {

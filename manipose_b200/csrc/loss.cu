@@ -9,25 +9,30 @@
 //   architectures/rmcl_manifold_mix_ste.py:121-185 poses_from_hyp_idx / aggregate
 //   metrics/mean_joint_errors.py:31-36 mpjpe_error
 //
-// Layout: hyp [B,K,T,17,3], y [B,T,17,3].  A warp owns 32 consecutive frames of one clip; for each hypothesis it
-// stages the 32(+halo) contiguous frames (204 B each) of hyp and y into shared memory with 16-byte cp.async, then lane t
-// reduces frame t reading with stride 51 floats (bank-conflict free).  Per-hypothesis errors use exactly the IEEE
-// operation sequence of PyTorch's CPU kernels (FMA chain in the 3-norm, the 8-lane sum order of its reduction, the
-// divide by 17), so winner indices are bit-identical to the oracle's on identical inputs.  Scalar terms are reduced
-// warp -> per-warp double partial -> one fixed-order finalize block (deterministic, no atomics).
+// Layout: hyp [B,K,T,17,3], y [B,T,17,3].  A warp owns a tile of consecutive frames of one clip; for each hypothesis one lane pulls the
+// tile (+ halo frames, 204 B each, 16-byte aligned-down start) into shared memory with ONE bulk async copy (mbarrier completion), the
+// copy of hypothesis k+1 in flight while lane t reduces frame t of hypothesis k reading with stride 51 floats (bank-conflict free).
+// Per-hypothesis errors reproduce the IEEE operation sequence of PyTorch's CPU kernels (FMA chain in the 3-norm, the 8-lane sum order of
+// its reduction, the divide by 17) so winner indices are bit-identical to the oracle's on identical inputs; the correctly rounded square
+// roots and divisions are the branch-free sequences of ieee.cuh, and a frame with an operand outside their range (an exact zero
+// distance, denormals) is redone with the IEEE intrinsics.  Scalar terms are reduced warp -> per-warp double partial -> one fixed-order
+// finalize block (deterministic, no atomics).
 #include "common.cuh"
+#include "ieee.cuh"
 #include "ptx.cuh"
 
 namespace mp {
 namespace {
 
 constexpr int kF = kJ * 3;                 // 51 floats per frame
-constexpr int kTileFrames = 32;
+constexpr int kTileFrames = 32;            // forward: frames per warp tile
+constexpr int kBwdFrames = 31;             // backward: output frames per warp tile (lane L owns frame t0 - 1 + L and the pair (t, t+1))
 constexpr int kStageFloats = 34 * kF + 10; // 32 frames + halo each side + alignment shift; 1744 = multiple of 4 floats (16 B)
-static_assert(kStageFloats % 4 == 0, "stage buffers must stay 16-byte aligned for cp.async");
+static_assert(kStageFloats % 4 == 0, "stage buffers must stay 16-byte aligned for the bulk copies");
 constexpr int kStageBytes = kStageFloats * 4;
-constexpr int kLossWarps = 8;
-constexpr int kMaxPartialWarps = 148 * 2 * kLossWarps;
+constexpr int kLossWarps = 10;             // one CTA of 10 independent warps per SM: 3 stage buffers each = 209 KB of shared memory
+constexpr int kBufsPerWarp = 3;            // y + two hypothesis buffers
+constexpr int kMaxPartialWarps = 148 * 2 * 16;
 constexpr int kMaxHyp = 32;
 
 __constant__ float c_ones17[kJ] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
@@ -45,28 +50,26 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
   return y;
 }
 
-// Copies floats [g0, g0+n) of `base` (16-byte aligned, `total` floats long) into sbuf so that element g0+i lands at
-// sbuf[shift + i]; returns shift in [0,3].  Whole 16-byte chunks go through cp.async, the array tail through LDG.
-__device__ __forceinline__ int stage_floats(float* sbuf, const float* __restrict__ base, size_t g0, uint32_t n, size_t total,
-                                            int lane) {
+// Brings floats [g0, g0+n) of `base` (16-byte aligned, `total` floats long) into sbuf so that element g0+i lands at sbuf[shift + i];
+// returns shift in [0,3].  Whole 16-byte chunks leave as one bulk copy issued by lane 0; only a tile that touches the last, partial
+// chunk of the array is copied by the lanes.  Either way `bar` (count 1) completes once the data is visible.
+__device__ __forceinline__ int stage_tile(float* sbuf, uint64_t* bar, const float* __restrict__ base, size_t g0, uint32_t n, size_t total,
+                                          int lane) {
   const size_t a0 = g0 & ~(size_t)3;
   const int shift = (int)(g0 - a0);
-  const uint32_t nchunks = (shift + n + 3) >> 2;
-  for (uint32_t c = lane; c < nchunks; c += 32) {
-    const size_t gi = a0 + 4 * (size_t)c;
-    if (gi + 4 <= total) {
-      ptx::cp_async16(sbuf + 4 * c, base + gi);
-    } else {
-      for (int q = 0; q < 4; ++q)
-        if (gi + q < total) sbuf[4 * c + q] = base[gi + q];
+  const uint32_t nfl = (shift + n + 3) & ~3u;
+  if (a0 + nfl <= total) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(bar, nfl * 4);
+      ptx::bulk_g2s(sbuf, base + a0, nfl * 4, bar);
     }
+  } else {
+    for (uint32_t i = lane; i < shift + n; i += 32)
+      if (a0 + i < total) sbuf[i] = base[a0 + i];
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar);
   }
   return shift;
-}
-__device__ __forceinline__ void stage_wait() {
-  ptx::cp_async_commit();
-  ptx::cp_async_wait<0>();
-  __syncwarp();
 }
 
 // sum of 17 values in the order of PyTorch's CPU reduction over a contiguous inner dim of size 17:
@@ -78,23 +81,25 @@ __device__ __forceinline__ float sum17_torch_order(const float (&v)[kJ]) {
   return acc;
 }
 
-// e = mean_j w_j * ||h_j - y_j||  (unsquared) or mean_j mean_c w_j (h - y)^2 (squared), bit-exact vs torch CPU.
+// e = mean_j w_j * ||h_j - y_j||  (unsquared) or mean_j mean_c w_j (h - y)^2 (squared), bit-exact vs torch CPU: the IEEE intrinsics,
+// out of line (the cold path of frame_error_core)
 template <bool kSquared>
-__device__ __forceinline__ float frame_error(const float* __restrict__ h, const float* __restrict__ yy, const float* __restrict__ w) {
+__device__ __noinline__ float frame_error_ieee(const float* __restrict__ h, const float* __restrict__ yy, const float* __restrict__ weights) {
   float v[kJ];
 #pragma unroll
   for (int j = 0; j < kJ; ++j) {
+    const float wj = weights ? weights[j] : 1.0f;
     const float d0 = __fsub_rn(h[j * 3 + 0], yy[j * 3 + 0]);
     const float d1 = __fsub_rn(h[j * 3 + 1], yy[j * 3 + 1]);
     const float d2 = __fsub_rn(h[j * 3 + 2], yy[j * 3 + 2]);
     if (kSquared) {
-      const float q0 = __fmul_rn(w[j], __fmul_rn(d0, d0));
-      const float q1 = __fmul_rn(w[j], __fmul_rn(d1, d1));
-      const float q2 = __fmul_rn(w[j], __fmul_rn(d2, d2));
+      const float q0 = __fmul_rn(wj, __fmul_rn(d0, d0));
+      const float q1 = __fmul_rn(wj, __fmul_rn(d1, d1));
+      const float q2 = __fmul_rn(wj, __fmul_rn(d2, d2));
       v[j] = __fdiv_rn(__fadd_rn(__fadd_rn(q0, q1), q2), 3.0f);
     } else {
       const float s = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
-      v[j] = __fmul_rn(w[j], __fsqrt_rn(s));
+      v[j] = __fmul_rn(wj, __fsqrt_rn(s));
     }
   }
   return __fdiv_rn(sum17_torch_order(v), 17.0f);
@@ -104,65 +109,125 @@ struct LossDims {
   uint32_t B, K, T;
 };
 
+struct WarpStage {
+  float* ybuf;
+  float* hbuf[2];
+  uint64_t* ybar;
+  uint64_t* hbar[2];
+  uint32_t yphase, hphase[2];
+  __device__ __forceinline__ void init(uint8_t* smem_raw, int warp, int lane, int n_warps) {
+    float* base = reinterpret_cast<float*>(smem_raw + (size_t)warp * kBufsPerWarp * kStageBytes);
+    ybuf = base;
+    hbuf[0] = base + kStageFloats;
+    hbuf[1] = base + 2 * kStageFloats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_warps * kBufsPerWarp * kStageBytes) + warp * 3;
+    ybar = bars;
+    hbar[0] = bars + 1;
+    hbar[1] = bars + 2;
+    yphase = hphase[0] = hphase[1] = 0;
+    if (lane == 0) {
+      ptx::mbar_init(ybar, 1);
+      ptx::mbar_init(hbar[0], 1);
+      ptx::mbar_init(hbar[1], 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+  }
+};
+constexpr size_t loss_smem_bytes() { return (size_t)kLossWarps * kBufsPerWarp * kStageBytes + kLossWarps * 3 * sizeof(uint64_t); }
+
 // ------------------------------------------------------------------------------------------------ forward
 template <bool kSquared, bool kAllTerms>
-__global__ void __launch_bounds__(kLossWarps * 32, 2)
+__global__ void __launch_bounds__(kLossWarps * 32, 1)
 loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, LossDims d, float* __restrict__ wta_val, int64_t* __restrict__ wta_idx,
                 float* __restrict__ per_hyp, double* __restrict__ partials) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* ybuf = reinterpret_cast<float*>(smem_raw + (size_t)warp * 2 * kStageBytes);
-  float* hbuf = ybuf + kStageFloats;
+  WarpStage st;
+  st.init(smem_raw, warp, lane, kLossWarps);
 
   float w[kJ];
 #pragma unroll
   for (int j = 0; j < kJ; ++j) w[j] = weights ? weights[j] : c_ones17[j];
+  const float r17 = ieee::rcp_refined(17.0f), r3 = ieee::rcp_refined(3.0f);
 
   const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
   const uint32_t n_items = d.B * tiles_per_clip;
   const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
   double acc_wta = 0, acc_bce = 0, acc_vel = 0, acc_sm = 0;
 
-  for (uint32_t item = blockIdx.x * kLossWarps + warp; item < n_items; item += gridDim.x * kLossWarps) {
+  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kLossWarps) {
     const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kTileFrames;
     const uint32_t nf = min((uint32_t)kTileFrames, d.T - t0);
     const uint32_t nload = kAllTerms ? min((uint32_t)kTileFrames + 1, d.T - t0) : nf;
     const bool valid = lane < nf;
     const bool has_next = kAllTerms && (t0 + lane + 1 < d.T);
 
-    __syncwarp();
-    const int sy = stage_floats(ybuf, y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
+    __syncwarp();   // every lane is done with the previous item's buffers
+    const int sy = stage_tile(st.ybuf, st.ybar, y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
+    int sh_cur = stage_tile(st.hbuf[0], st.hbar[0], hyp, (((size_t)b * d.K) * d.T + t0) * kF, nload * kF, h_total, lane);
+    ptx::mbar_wait(st.ybar, st.yphase);
+    st.yphase ^= 1;
+    const float* yp = st.ybuf + sy + lane * kF;
     float best = INFINITY, vel = 0.f, sm = 0.f;
     int best_k = 0;
     for (uint32_t k = 0; k < d.K; ++k) {
-      __syncwarp();
-      const int sh = stage_floats(hbuf, hyp, (((size_t)b * d.K + k) * d.T + t0) * kF, nload * kF, h_total, lane);
-      stage_wait();
+      const int cur = k & 1;
+      int sh_next = 0;
+      if (k + 1 < d.K)   // buffer cur^1 was read for hypothesis k-1: every lane passed the __syncwarp at the end of that iteration
+        sh_next = stage_tile(st.hbuf[cur ^ 1], st.hbar[cur ^ 1], hyp, (((size_t)b * d.K + k + 1) * d.T + t0) * kF, nload * kF, h_total, lane);
+      ptx::mbar_wait(st.hbar[cur], st.hphase[cur]);
+      st.hphase[cur] ^= 1;
+      const float* hp = st.hbuf[cur] + sh_cur + lane * kF;
+
+      // ---- frame t of hypothesis k: WTA error (exact) + velocity / smoothness of the pair (t, t+1)
+      float v[kJ];
+      float smin = INFINITY, smax = 0.f, vk = 0.f, sk = 0.f;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const float h0 = hp[j * 3 + 0], h1 = hp[j * 3 + 1], h2 = hp[j * 3 + 2];
+        const float y0 = yp[j * 3 + 0], y1 = yp[j * 3 + 1], y2 = yp[j * 3 + 2];
+        const float d0 = __fsub_rn(h0, y0), d1 = __fsub_rn(h1, y1), d2 = __fsub_rn(h2, y2);
+        float s;
+        if (kSquared) {
+          const float q0 = __fmul_rn(w[j], __fmul_rn(d0, d0));
+          const float q1 = __fmul_rn(w[j], __fmul_rn(d1, d1));
+          const float q2 = __fmul_rn(w[j], __fmul_rn(d2, d2));
+          s = __fadd_rn(__fadd_rn(q0, q1), q2);
+          v[j] = ieee::div_rn_core(s, 3.0f, r3);
+        } else {
+          s = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+          v[j] = __fmul_rn(w[j], ieee::sqrt_rn_core(s));
+        }
+        smin = fminf(smin, s);
+        smax = fmaxf(smax, s);
+        if (kAllTerms) {
+          const float a0 = hp[kF + j * 3 + 0] - h0, a1 = hp[kF + j * 3 + 1] - h1, a2 = hp[kF + j * 3 + 2] - h2;   // hypothesis velocity
+          const float e0 = a0 - (yp[kF + j * 3 + 0] - y0), e1 = a1 - (yp[kF + j * 3 + 1] - y1), e2 = a2 - (yp[kF + j * 3 + 2] - y2);
+          const float q = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+          vk += kSquared ? q : sqrt_approx(q);
+          sk = fmaf(w[j], fmaf(a2, a2, fmaf(a1, a1, a0 * a0)), sk);
+        }
+      }
+      const float tot = sum17_torch_order(v);
+      float e = ieee::div_rn_core(tot, 17.0f, r17);
+      // every square-root / division operand in [2^-100, 2^100), or the frame is redone with the IEEE intrinsics
+      const bool in_range = __float_as_uint(smin) >= 0x0d800000u && __float_as_uint(smax) < 0x71800000u && ieee::mag_in_range(tot);
+      if (valid && !in_range) e = frame_error_ieee<kSquared>(hp, yp, weights);
       if (valid) {
-        const float* hp = hbuf + sh + lane * kF;
-        const float* yp = ybuf + sy + lane * kF;
-        const float e = frame_error<kSquared>(hp, yp, w);
         if (per_hyp) per_hyp[((size_t)b * d.K + k) * d.T + t0 + lane] = e;
         if (k == 0 || e < best) {  // torch.min(dim=1): lowest index on ties
           best = e;
           best_k = (int)k;
         }
-        if (has_next) {
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            float q = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float dvh = hp[kF + j * 3 + c] - hp[j * 3 + c];
-              const float dv = dvh - (yp[kF + j * 3 + c] - yp[j * 3 + c]);
-              q = fmaf(dv, dv, q);
-              sm = fmaf(w[j] * dvh, dvh, sm);
-            }
-            vel += kSquared ? q : sqrt_approx(q);
-          }
-        }
       }
+      if (kAllTerms) {
+        vel += (valid && has_next) ? vk : 0.f;
+        sm += (valid && has_next) ? sk : 0.f;
+      }
+      sh_cur = sh_next;
+      __syncwarp();   // hbuf[cur] is free for hypothesis k+2
     }
     float bce = 0.f;
     if (valid) {
@@ -179,11 +244,11 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
       best = 0.f;
     }
     if (kAllTerms) {
-      const float r0 = warp_sum(best), r1 = warp_sum(bce), r2 = warp_sum(vel), r3 = warp_sum(sm);
+      const float r0 = warp_sum(best), r1 = warp_sum(bce), r2 = warp_sum(vel), r3s = warp_sum(sm);
       acc_wta += r0;
       acc_bce += r1;
       acc_vel += r2;
-      acc_sm += r3;
+      acc_sm += r3s;
     }
   }
   if (kAllTerms && lane == 0) {
@@ -231,16 +296,19 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partials, int n_
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// Lane L of a tile owns frame f = t0 - 1 + L and the frame pair (f, f+1): it computes the pair's velocity / smoothness "flux"
+// F = d(terms)/d(h[f+1]) = -d(terms)/d(h[f]) ONCE, and the gradient of frame f is  wta part - F(f) + F(f-1), the second flux coming
+// from lane L-1 by shuffle.  Lane 0 only supplies the flux into the tile's first frame, so a tile writes 31 frames.
 template <bool kSquared>
-__global__ void __launch_bounds__(kLossWarps * 32, 2)
+__global__ void __launch_bounds__(kLossWarps * 32, 1)
 loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, const int64_t* __restrict__ wta_idx, LossDims d, float beta, float vel_w,
                 float smooth_w, const float* __restrict__ grad_terms, const float* __restrict__ grad_wta_val,
                 float* __restrict__ grad_hyp, float* __restrict__ grad_scores) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* ybuf = reinterpret_cast<float*>(smem_raw + (size_t)warp * 2 * kStageBytes);
-  float* hbuf = ybuf + kStageFloats;
+  WarpStage st;
+  st.init(smem_raw, warp, lane, kLossWarps);
 
   float w[kJ];
 #pragma unroll
@@ -259,91 +327,92 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
   const float c_sm = (float)(g_sm * 2.0 / (pairs * 3.0));
   const float c_bce = (float)(g_bce / (bt * d.K));
 
-  const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
+  const uint32_t tiles_per_clip = (d.T + kBwdFrames - 1) / kBwdFrames;
   const uint32_t n_items = d.B * tiles_per_clip;
   const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
 
-  for (uint32_t item = blockIdx.x * kLossWarps + warp; item < n_items; item += gridDim.x * kLossWarps) {
-    const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kTileFrames;
-    const uint32_t nf = min((uint32_t)kTileFrames, d.T - t0);
-    const uint32_t lo = t0 > 0 ? t0 - 1 : 0, hi = min(d.T, t0 + kTileFrames + 1);
-    const uint32_t t = t0 + lane;
-    const bool valid = lane < nf;
-    const bool has_prev = valid && t >= 1, has_next = valid && (t + 1 < d.T);
-    const int64_t kstar = valid ? wta_idx[(size_t)b * d.T + t] : -1;
-    const float c_wta = valid ? (wta_mean + (grad_wta_val ? grad_wta_val[(size_t)b * d.T + t] : 0.f)) * wta_scale : 0.f;
+  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kLossWarps) {
+    const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kBwdFrames;
+    const uint32_t nf = min((uint32_t)kBwdFrames, d.T - t0);            // frames written: t0 .. t0+nf-1 (lanes 1 .. nf)
+    const uint32_t lo = t0 > 0 ? t0 - 1 : 0, hi = min(d.T, t0 + nf + 1);   // frames staged
+    const int f = (int)t0 - 1 + lane;                                   // this lane's frame (lane 0: the frame before the tile)
+    const bool in_clip = f >= 0 && f < (int)d.T;
+    const bool writes = lane >= 1 && lane <= (int)nf;
+    const bool has_pair = in_clip && (f + 1 < (int)d.T) && lane <= (int)nf;   // pair (f, f+1) touches a frame of this tile
+    const int row = in_clip ? f - (int)lo : 0;                          // frame f sits at row `row` of the staged tile
+    const int64_t kstar = writes ? wta_idx[(size_t)b * d.T + f] : -1;
+    const float c_wta = writes ? (wta_mean + (grad_wta_val ? grad_wta_val[(size_t)b * d.T + f] : 0.f)) * wta_scale : 0.f;
 
     __syncwarp();
-    const int sy = stage_floats(ybuf, y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
+    const int sy = stage_tile(st.ybuf, st.ybar, y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
+    int sh_cur = stage_tile(st.hbuf[0], st.hbar[0], hyp, (((size_t)b * d.K) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+    ptx::mbar_wait(st.ybar, st.yphase);
+    st.yphase ^= 1;
+    const float* yc = st.ybuf + sy + row * kF;
     for (uint32_t k = 0; k < d.K; ++k) {
-      __syncwarp();
-      const int sh = stage_floats(hbuf, hyp, (((size_t)b * d.K + k) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
-      stage_wait();
+      const int cur = k & 1;
+      int sh_next = 0;
+      if (k + 1 < d.K)
+        sh_next = stage_tile(st.hbuf[cur ^ 1], st.hbar[cur ^ 1], hyp, (((size_t)b * d.K + k + 1) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+      ptx::mbar_wait(st.hbar[cur], st.hphase[cur]);
+      st.hphase[cur] ^= 1;
+      const float* hc = st.hbuf[cur] + sh_cur + row * kF;
+      const bool winner = writes && (int64_t)k == kstar;
+
       float g[kF];
-      if (valid) {
-        const float* hc = hbuf + sh + (t - lo) * kF;
-        const float* yc = ybuf + sy + (t - lo) * kF;
 #pragma unroll
-        for (int j = 0; j < kJ; ++j) {
-          float gj[3] = {0.f, 0.f, 0.f};
-          if ((int64_t)k == kstar) {
-            const float d0 = hc[j * 3 + 0] - yc[j * 3 + 0], d1 = hc[j * 3 + 1] - yc[j * 3 + 1], d2 = hc[j * 3 + 2] - yc[j * 3 + 2];
-            if (kSquared) {
-              gj[0] = c_wta * w[j] * d0;
-              gj[1] = c_wta * w[j] * d1;
-              gj[2] = c_wta * w[j] * d2;
-            } else {
-              const float n2 = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
-              const float r = n2 > 0.f ? c_wta * w[j] * rsqrt_approx(n2) : 0.f;
-              gj[0] = r * d0;
-              gj[1] = r * d1;
-              gj[2] = r * d2;
-            }
-          }
-          if (has_next) {  // pair (t, t+1): this frame enters with a minus sign
-            float dvh[3], dv[3], q = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              dvh[c] = hc[kF + j * 3 + c] - hc[j * 3 + c];
-              dv[c] = dvh[c] - (yc[kF + j * 3 + c] - yc[j * 3 + c]);
-              q = fmaf(dv[c], dv[c], q);
-            }
-            const float r = kSquared ? c_vel : (q > 0.f ? c_vel * rsqrt_approx(q) : 0.f);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) gj[c] -= r * dv[c] + c_sm * w[j] * dvh[c];
-          }
-          if (has_prev) {  // pair (t-1, t): plus sign
-            float dvh[3], dv[3], q = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              dvh[c] = hc[j * 3 + c] - hc[j * 3 + c - kF];
-              dv[c] = dvh[c] - (yc[j * 3 + c] - yc[j * 3 + c - kF]);
-              q = fmaf(dv[c], dv[c], q);
-            }
-            const float r = kSquared ? c_vel : (q > 0.f ? c_vel * rsqrt_approx(q) : 0.f);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) gj[c] += r * dv[c] + c_sm * w[j] * dvh[c];
-          }
-          g[j * 3 + 0] = gj[0];
-          g[j * 3 + 1] = gj[1];
-          g[j * 3 + 2] = gj[2];
+      for (int j = 0; j < kJ; ++j) {
+        const float h0 = hc[j * 3 + 0], h1 = hc[j * 3 + 1], h2 = hc[j * 3 + 2];
+        const float y0 = yc[j * 3 + 0], y1 = yc[j * 3 + 1], y2 = yc[j * 3 + 2];
+        const float d0 = h0 - y0, d1 = h1 - y1, d2 = h2 - y2;
+        // winner-takes-all part of this frame
+        float r;
+        if (kSquared) {
+          r = c_wta * w[j];
+        } else {
+          const float n2 = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+          r = n2 > 0.f ? c_wta * w[j] * rsqrt_approx(n2) : 0.f;
         }
-        if (grad_scores) {
-          const size_t si = ((size_t)b * d.K + k) * d.T + t;
-          const float s = scores[si];
-          const float tgt = ((int64_t)k == kstar) ? 1.f : 0.f;
-          // binary_cross_entropy_backward: (input - target) / max((1 - input) * input, 1e-12)
-          grad_scores[si] = c_bce * (s - tgt) / fmaxf((1.f - s) * s, 1e-12f);
+        r = winner ? r : 0.f;
+        // flux of the pair (f, f+1)
+        const float a0 = hc[kF + j * 3 + 0] - h0, a1 = hc[kF + j * 3 + 1] - h1, a2 = hc[kF + j * 3 + 2] - h2;
+        const float e0 = a0 - (yc[kF + j * 3 + 0] - y0), e1 = a1 - (yc[kF + j * 3 + 1] - y1), e2 = a2 - (yc[kF + j * 3 + 2] - y2);
+        float rv;
+        if (kSquared) {
+          rv = c_vel;
+        } else {
+          const float q = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+          rv = q > 0.f ? c_vel * rsqrt_approx(q) : 0.f;
         }
+        const float cs = c_sm * w[j];
+        float f0 = fmaf(rv, e0, cs * a0), f1 = fmaf(rv, e1, cs * a1), f2 = fmaf(rv, e2, cs * a2);
+        f0 = has_pair ? f0 : 0.f;
+        f1 = has_pair ? f1 : 0.f;
+        f2 = has_pair ? f2 : 0.f;
+        const float p0 = __shfl_up_sync(0xffffffffu, f0, 1), p1 = __shfl_up_sync(0xffffffffu, f1, 1), p2 = __shfl_up_sync(0xffffffffu, f2, 1);
+        g[j * 3 + 0] = fmaf(r, d0, p0 - f0);
+        g[j * 3 + 1] = fmaf(r, d1, p1 - f1);
+        g[j * 3 + 2] = fmaf(r, d2, p2 - f2);
       }
-      __syncwarp();  // all lanes done reading hbuf: reuse it to transpose the gradient tile
-      if (valid) {
+      if (writes && grad_scores) {
+        const size_t si = ((size_t)b * d.K + k) * d.T + f;
+        const float s = scores[si];
+        const float tgt = winner ? 1.f : 0.f;
+        // binary_cross_entropy_backward: (input - target) / max((1 - input) * input, 1e-12)
+        grad_scores[si] = c_bce * (s - tgt) / fmaxf((1.f - s) * s, 1e-12f);
+      }
+      __syncwarp();  // all lanes done reading hbuf[cur]: reuse it to transpose the gradient tile
+      float* tb = st.hbuf[cur];
+      if (writes) {
 #pragma unroll
-        for (int i = 0; i < kF; ++i) hbuf[lane * kF + i] = g[i];
+        for (int i = 0; i < kF; ++i) tb[(lane - 1) * kF + i] = g[i];
       }
       __syncwarp();
       float* gout = grad_hyp + (((size_t)b * d.K + k) * d.T + t0) * kF;
-      for (uint32_t i = lane; i < nf * kF; i += 32) gout[i] = hbuf[i];
+      for (uint32_t i = lane; i < nf * kF; i += 32) gout[i] = tb[i];
+      ptx::fence_proxy_async_smem();   // the next bulk copy into this buffer follows generic-proxy writes to it
+      sh_cur = sh_next;
+      __syncwarp();
     }
   }
 }
@@ -482,11 +551,11 @@ int check_dims(const char* who, int64_t B, int64_t K, int64_t T) {
   return MP_OK;
 }
 
-int loss_grid(int64_t B, int64_t T) {
-  const int64_t items = B * ((T + kTileFrames - 1) / kTileFrames);
-  int64_t ctas = (items + kLossWarps - 1) / kLossWarps;
-  const int64_t cap = (int64_t)sm_count() * 2;
-  return (int)(ctas < cap ? ctas : cap);
+// one CTA per SM; with few tiles (the training step) one tile per SM before a second warp of any CTA gets one
+int loss_grid(int64_t B, int64_t T, int frames_per_tile) {
+  const int64_t items = B * ((T + frames_per_tile - 1) / frames_per_tile);
+  const int64_t cap = (int64_t)sm_count();
+  return (int)(items < cap ? items : cap);
 }
 
 }  // namespace
@@ -508,8 +577,8 @@ int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int
   MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
              "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
-  const int grid = loss_grid(B, T);
+  const size_t smem = loss_smem_bytes();
+  const int grid = loss_grid(B, T, kTileFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
@@ -534,8 +603,8 @@ int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const flo
   MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
              "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
-  const int grid = loss_grid(B, T);
+  const size_t smem = loss_smem_bytes();
+  const int grid = loss_grid(B, T, kTileFrames);
   double* partials = reinterpret_cast<double*>(workspace);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -560,8 +629,8 @@ int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const flo
   MP_REQUIRE(grad_scores == nullptr || scores != nullptr, MP_EINVAL, "mp_loss_bwd: scores required for grad_scores");
   MP_REQUIRE(aligned16(hyp) && aligned16(y), MP_EALIGN, "mp_loss_bwd: hyp and y must be 16-byte aligned");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = (size_t)kLossWarps * 2 * kStageBytes;
-  const int grid = loss_grid(B, T);
+  const size_t smem = loss_smem_bytes();
+  const int grid = loss_grid(B, T, kBwdFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,

@@ -110,12 +110,14 @@ class _DecoderFn(torch.autograd.Function):
         n_clips, n_hyp, n_frames, d = ctx.dims
         g = _f32(g)
         g_rot = torch.empty_like(rot6d)
-        g_bone = torch.zeros(ctx.bone_shape, dtype=torch.float32, device=rot6d.device)
+        g_bone = torch.empty(ctx.bone_shape, dtype=torch.float32, device=rot6d.device)
         g_root = torch.empty((n_clips * n_hyp * n_frames, 3), dtype=torch.float32, device=rot6d.device) if ctx.root_grad else None
+        wsb = L.load().mp_decoder_bwd_workspace_bytes(n_clips, n_hyp, n_frames)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=rot6d.device)
         rc = L.load().mp_decoder_bwd(L.ptr(rot6d), L.ptr(bone_len), L.ptr(g), L.ptr(g_rot), L.ptr(g_bone), L.ptr(g_root),
-                                     n_clips, n_hyp, n_frames, d, L.stream_ptr())
+                                     n_clips, n_hyp, n_frames, d, L.ptr(ws), wsb, L.stream_ptr())
         L.check(rc, "mp_decoder_bwd")
-        _count()
+        _count(2)
         return g_rot, g_bone, g_root, None, None, None, None, None
 
 

@@ -108,9 +108,11 @@ def main():
     gp = torch.randn(n, 17, 3, generator=g, device=dev)
     grot = torch.empty_like(rot)
     gbone = torch.zeros(nc, 16, device=dev)
+    dwsb = L.load().mp_decoder_bwd_workspace_bytes(nc, k, t)
+    dws = torch.empty(dwsb, dtype=torch.uint8, device=dev)
     def dec_bwd():
         gbone.zero_()
-        L.check(L.load().mp_decoder_bwd(L.ptr(rot), L.ptr(bones), L.ptr(gp), L.ptr(grot), L.ptr(gbone), None, nc, k, t, 6, L.stream_ptr()), "bwd")
+        L.check(L.load().mp_decoder_bwd(L.ptr(rot), L.ptr(bones), L.ptr(gp), L.ptr(grot), L.ptr(gbone), None, nc, k, t, 6, L.ptr(dws), dwsb, L.stream_ptr()), "bwd")
     med, best = timeit(dec_bwd)
     out["decoder_bwd_1M"] = {"ms": med, "best_ms": best, "gbs": 1020.0 * n / med / 1e6, "gposes_s": n / med / 1e6}
     y = 0.3 * torch.randn(1024, 243, 17, 3, generator=g, device=dev)
