@@ -27,12 +27,14 @@ namespace {
 constexpr int kF = kJ * 3;                 // 51 floats per frame
 constexpr int kTileFrames = 32;            // forward: frames per warp tile
 constexpr int kBwdFrames = 31;             // backward: output frames per warp tile (lane L owns frame t0 - 1 + L and the pair (t, t+1))
-constexpr int kStageFloats = 34 * kF + 10; // 32 frames + halo each side + alignment shift; 1744 = multiple of 4 floats (16 B)
+constexpr int kStageFloats = 33 * kF + 5;  // 33 frames (tile + halo) + alignment shift, rounded to a multiple of 4 floats (16 B): 1688
 static_assert(kStageFloats % 4 == 0, "stage buffers must stay 16-byte aligned for the bulk copies");
 constexpr int kStageBytes = kStageFloats * 4;
-constexpr int kLossWarps = 10;             // one CTA of 10 independent warps per SM: 3 stage buffers each = 209 KB of shared memory
-constexpr int kBufsPerWarp = 3;            // y + two hypothesis buffers
-constexpr int kMaxPartialWarps = 148 * 2 * 16;
+// One CTA of independent warps per SM, shared memory split into per-warp stage buffers.  Forward: the ground-truth frame lives in
+// registers, two hypothesis buffers per warp; backward: y + two hypothesis buffers (its registers hold the 51 gradients).
+constexpr int kFwdWarps = 12, kFwdBufs = 2;
+constexpr int kBwdWarps = 11, kBwdBufs = 3;
+constexpr int kMaxPartialWarps = 148 * 2 * 16;   // >= SMs x kFwdWarps
 constexpr int kMaxHyp = 32;
 
 __constant__ float c_ones17[kJ] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
@@ -109,43 +111,41 @@ struct LossDims {
   uint32_t B, K, T;
 };
 
+template <int kBufs>
 struct WarpStage {
-  float* ybuf;
-  float* hbuf[2];
-  uint64_t* ybar;
-  uint64_t* hbar[2];
-  uint32_t yphase, hphase[2];
+  float* buf[kBufs];
+  uint64_t* bar[kBufs];
+  uint32_t phase[kBufs];
   __device__ __forceinline__ void init(uint8_t* smem_raw, int warp, int lane, int n_warps) {
-    float* base = reinterpret_cast<float*>(smem_raw + (size_t)warp * kBufsPerWarp * kStageBytes);
-    ybuf = base;
-    hbuf[0] = base + kStageFloats;
-    hbuf[1] = base + 2 * kStageFloats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_warps * kBufsPerWarp * kStageBytes) + warp * 3;
-    ybar = bars;
-    hbar[0] = bars + 1;
-    hbar[1] = bars + 2;
-    yphase = hphase[0] = hphase[1] = 0;
-    if (lane == 0) {
-      ptx::mbar_init(ybar, 1);
-      ptx::mbar_init(hbar[0], 1);
-      ptx::mbar_init(hbar[1], 1);
-      ptx::fence_mbar_init();
+    float* base = reinterpret_cast<float*>(smem_raw + (size_t)warp * kBufs * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_warps * kBufs * kStageBytes) + warp * kBufs;
+#pragma unroll
+    for (int i = 0; i < kBufs; ++i) {
+      buf[i] = base + i * kStageFloats;
+      bar[i] = bars + i;
+      phase[i] = 0;
+      if (lane == 0) ptx::mbar_init(bar[i], 1);
     }
+    if (lane == 0) ptx::fence_mbar_init();
     __syncwarp();
   }
+  __device__ __forceinline__ void wait(int i) {
+    ptx::mbar_wait(bar[i], phase[i]);
+    phase[i] ^= 1;
+  }
 };
-constexpr size_t loss_smem_bytes() { return (size_t)kLossWarps * kBufsPerWarp * kStageBytes + kLossWarps * 3 * sizeof(uint64_t); }
+constexpr size_t loss_smem_bytes(int warps, int bufs) { return (size_t)warps * bufs * (kStageBytes + sizeof(uint64_t)); }
 
 // ------------------------------------------------------------------------------------------------ forward
 template <bool kSquared, bool kAllTerms>
-__global__ void __launch_bounds__(kLossWarps * 32, 1)
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
 loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, LossDims d, float* __restrict__ wta_val, int64_t* __restrict__ wta_idx,
                 float* __restrict__ per_hyp, double* __restrict__ partials) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpStage st;
-  st.init(smem_raw, warp, lane, kLossWarps);
+  WarpStage<kFwdBufs> st;
+  st.init(smem_raw, warp, lane, kFwdWarps);
 
   float w[kJ];
 #pragma unroll
@@ -157,7 +157,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
   const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
   double acc_wta = 0, acc_bce = 0, acc_vel = 0, acc_sm = 0;
 
-  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kLossWarps) {
+  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kFwdWarps) {
     const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kTileFrames;
     const uint32_t nf = min((uint32_t)kTileFrames, d.T - t0);
     const uint32_t nload = kAllTerms ? min((uint32_t)kTileFrames + 1, d.T - t0) : nf;
@@ -165,21 +165,29 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
     const bool has_next = kAllTerms && (t0 + lane + 1 < d.T);
 
     __syncwarp();   // every lane is done with the previous item's buffers
-    const int sy = stage_tile(st.ybuf, st.ybar, y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
-    int sh_cur = stage_tile(st.hbuf[0], st.hbar[0], hyp, (((size_t)b * d.K) * d.T + t0) * kF, nload * kF, h_total, lane);
-    ptx::mbar_wait(st.ybar, st.yphase);
-    st.yphase ^= 1;
-    const float* yp = st.ybuf + sy + lane * kF;
+    // ground truth: through buffer 1 into registers (frame t and, for the pair terms, its difference to frame t+1)
+    const int sy = stage_tile(st.buf[1], st.bar[1], y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
+    int sh_cur = stage_tile(st.buf[0], st.bar[0], hyp, (((size_t)b * d.K) * d.T + t0) * kF, nload * kF, h_total, lane);
+    st.wait(1);
+    float yr[kF], dy[kAllTerms ? kF : 1];
+    {
+      const float* yp = st.buf[1] + sy + lane * kF;
+#pragma unroll
+      for (int i = 0; i < kF; ++i) {
+        yr[i] = yp[i];
+        if (kAllTerms) dy[i] = yp[kF + i] - yr[i];
+      }
+    }
+    __syncwarp();   // buffer 1 is free for hypothesis 1
     float best = INFINITY, vel = 0.f, sm = 0.f;
     int best_k = 0;
     for (uint32_t k = 0; k < d.K; ++k) {
       const int cur = k & 1;
       int sh_next = 0;
       if (k + 1 < d.K)   // buffer cur^1 was read for hypothesis k-1: every lane passed the __syncwarp at the end of that iteration
-        sh_next = stage_tile(st.hbuf[cur ^ 1], st.hbar[cur ^ 1], hyp, (((size_t)b * d.K + k + 1) * d.T + t0) * kF, nload * kF, h_total, lane);
-      ptx::mbar_wait(st.hbar[cur], st.hphase[cur]);
-      st.hphase[cur] ^= 1;
-      const float* hp = st.hbuf[cur] + sh_cur + lane * kF;
+        sh_next = stage_tile(st.buf[cur ^ 1], st.bar[cur ^ 1], hyp, (((size_t)b * d.K + k + 1) * d.T + t0) * kF, nload * kF, h_total, lane);
+      st.wait(cur);
+      const float* hp = st.buf[cur] + sh_cur + lane * kF;
 
       // ---- frame t of hypothesis k: WTA error (exact) + velocity / smoothness of the pair (t, t+1)
       float v[kJ];
@@ -187,8 +195,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
 #pragma unroll
       for (int j = 0; j < kJ; ++j) {
         const float h0 = hp[j * 3 + 0], h1 = hp[j * 3 + 1], h2 = hp[j * 3 + 2];
-        const float y0 = yp[j * 3 + 0], y1 = yp[j * 3 + 1], y2 = yp[j * 3 + 2];
-        const float d0 = __fsub_rn(h0, y0), d1 = __fsub_rn(h1, y1), d2 = __fsub_rn(h2, y2);
+        const float d0 = __fsub_rn(h0, yr[j * 3 + 0]), d1 = __fsub_rn(h1, yr[j * 3 + 1]), d2 = __fsub_rn(h2, yr[j * 3 + 2]);
         float s;
         if (kSquared) {
           const float q0 = __fmul_rn(w[j], __fmul_rn(d0, d0));
@@ -204,7 +211,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
         smax = fmaxf(smax, s);
         if (kAllTerms) {
           const float a0 = hp[kF + j * 3 + 0] - h0, a1 = hp[kF + j * 3 + 1] - h1, a2 = hp[kF + j * 3 + 2] - h2;   // hypothesis velocity
-          const float e0 = a0 - (yp[kF + j * 3 + 0] - y0), e1 = a1 - (yp[kF + j * 3 + 1] - y1), e2 = a2 - (yp[kF + j * 3 + 2] - y2);
+          const float e0 = a0 - dy[j * 3 + 0], e1 = a1 - dy[j * 3 + 1], e2 = a2 - dy[j * 3 + 2];
           const float q = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
           vk += kSquared ? q : sqrt_approx(q);
           sk = fmaf(w[j], fmaf(a2, a2, fmaf(a1, a1, a0 * a0)), sk);
@@ -214,7 +221,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
       float e = ieee::div_rn_core(tot, 17.0f, r17);
       // every square-root / division operand in [2^-100, 2^100), or the frame is redone with the IEEE intrinsics
       const bool in_range = __float_as_uint(smin) >= 0x0d800000u && __float_as_uint(smax) < 0x71800000u && ieee::mag_in_range(tot);
-      if (valid && !in_range) e = frame_error_ieee<kSquared>(hp, yp, weights);
+      if (valid && !in_range) e = frame_error_ieee<kSquared>(hp, y + ((size_t)b * d.T + t0 + lane) * kF, weights);
       if (valid) {
         if (per_hyp) per_hyp[((size_t)b * d.K + k) * d.T + t0 + lane] = e;
         if (k == 0 || e < best) {  // torch.min(dim=1): lowest index on ties
@@ -227,7 +234,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
         sm += (valid && has_next) ? sk : 0.f;
       }
       sh_cur = sh_next;
-      __syncwarp();   // hbuf[cur] is free for hypothesis k+2
+      __syncwarp();   // buf[cur] is free for hypothesis k+2
     }
     float bce = 0.f;
     if (valid) {
@@ -252,7 +259,7 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
     }
   }
   if (kAllTerms && lane == 0) {
-    double* p = partials + (size_t)(blockIdx.x * kLossWarps + warp) * 4;
+    double* p = partials + (size_t)(blockIdx.x * kFwdWarps + warp) * 4;
     p[0] = acc_wta;
     p[1] = acc_bce;
     p[2] = acc_vel;
@@ -300,15 +307,15 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partials, int n_
 // F = d(terms)/d(h[f+1]) = -d(terms)/d(h[f]) ONCE, and the gradient of frame f is  wta part - F(f) + F(f-1), the second flux coming
 // from lane L-1 by shuffle.  Lane 0 only supplies the flux into the tile's first frame, so a tile writes 31 frames.
 template <bool kSquared>
-__global__ void __launch_bounds__(kLossWarps * 32, 1)
+__global__ void __launch_bounds__(kBwdWarps * 32, 1)
 loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, const int64_t* __restrict__ wta_idx, LossDims d, float beta, float vel_w,
                 float smooth_w, const float* __restrict__ grad_terms, const float* __restrict__ grad_wta_val,
                 float* __restrict__ grad_hyp, float* __restrict__ grad_scores) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpStage st;
-  st.init(smem_raw, warp, lane, kLossWarps);
+  WarpStage<kBwdBufs> st;   // buf[0]: y, buf[1], buf[2]: hypotheses
+  st.init(smem_raw, warp, lane, kBwdWarps);
 
   float w[kJ];
 #pragma unroll
@@ -331,7 +338,7 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
   const uint32_t n_items = d.B * tiles_per_clip;
   const size_t y_total = (size_t)d.B * d.T * kF, h_total = y_total * d.K;
 
-  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kLossWarps) {
+  for (uint32_t item = warp * gridDim.x + blockIdx.x; item < n_items; item += gridDim.x * kBwdWarps) {
     const uint32_t b = item / tiles_per_clip, t0 = (item - b * tiles_per_clip) * kBwdFrames;
     const uint32_t nf = min((uint32_t)kBwdFrames, d.T - t0);            // frames written: t0 .. t0+nf-1 (lanes 1 .. nf)
     const uint32_t lo = t0 > 0 ? t0 - 1 : 0, hi = min(d.T, t0 + nf + 1);   // frames staged
@@ -344,19 +351,17 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
     const float c_wta = writes ? (wta_mean + (grad_wta_val ? grad_wta_val[(size_t)b * d.T + f] : 0.f)) * wta_scale : 0.f;
 
     __syncwarp();
-    const int sy = stage_tile(st.ybuf, st.ybar, y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
-    int sh_cur = stage_tile(st.hbuf[0], st.hbar[0], hyp, (((size_t)b * d.K) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
-    ptx::mbar_wait(st.ybar, st.yphase);
-    st.yphase ^= 1;
-    const float* yc = st.ybuf + sy + row * kF;
+    const int sy = stage_tile(st.buf[0], st.bar[0], y, ((size_t)b * d.T + lo) * kF, (hi - lo) * kF, y_total, lane);
+    int sh_cur = stage_tile(st.buf[1], st.bar[1], hyp, (((size_t)b * d.K) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+    st.wait(0);
+    const float* yc = st.buf[0] + sy + row * kF;
     for (uint32_t k = 0; k < d.K; ++k) {
-      const int cur = k & 1;
+      const int cur = 1 + (k & 1), nxt = 3 - cur;
       int sh_next = 0;
       if (k + 1 < d.K)
-        sh_next = stage_tile(st.hbuf[cur ^ 1], st.hbar[cur ^ 1], hyp, (((size_t)b * d.K + k + 1) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
-      ptx::mbar_wait(st.hbar[cur], st.hphase[cur]);
-      st.hphase[cur] ^= 1;
-      const float* hc = st.hbuf[cur] + sh_cur + row * kF;
+        sh_next = stage_tile(st.buf[nxt], st.bar[nxt], hyp, (((size_t)b * d.K + k + 1) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+      st.wait(cur);
+      const float* hc = st.buf[cur] + sh_cur + row * kF;
       const bool winner = writes && (int64_t)k == kstar;
 
       float g[kF];
@@ -402,14 +407,20 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
         grad_scores[si] = c_bce * (s - tgt) / fmaxf((1.f - s) * s, 1e-12f);
       }
       __syncwarp();  // all lanes done reading hbuf[cur]: reuse it to transpose the gradient tile
-      float* tb = st.hbuf[cur];
+      float* tb = st.buf[cur];
       if (writes) {
 #pragma unroll
         for (int i = 0; i < kF; ++i) tb[(lane - 1) * kF + i] = g[i];
       }
       __syncwarp();
       float* gout = grad_hyp + (((size_t)b * d.K + k) * d.T + t0) * kF;
-      for (uint32_t i = lane; i < nf * kF; i += 32) gout[i] = tb[i];
+      if (nf == kBwdFrames) {
+#pragma unroll
+        for (int i = 0; i < (kBwdFrames * kF + 31) / 32; ++i)
+          if (i * 32 + lane < kBwdFrames * kF) gout[i * 32 + lane] = tb[i * 32 + lane];
+      } else {
+        for (uint32_t i = lane; i < nf * kF; i += 32) gout[i] = tb[i];
+      }
       ptx::fence_proxy_async_smem();   // the next bulk copy into this buffer follows generic-proxy writes to it
       sh_cur = sh_next;
       __syncwarp();
@@ -418,21 +429,29 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
 }
 
 // ------------------------------------------------------------------------------------------------ aggregation
-__global__ void aggregate_weighted_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out,
-                                          uint32_t B, uint32_t K, uint32_t T) {
+// Index math of the element-wise aggregation kernels: out element i = (b, r) with r the offset inside clip b's [T,17,3] block, so the
+// hypothesis element is hyp[(b K + k) T 51 + r] and its score scores[(b K + k) T + r / 51]: one runtime division per element, 32-bit
+// whenever the output has fewer than 2^32 elements.
+template <typename I>
+__device__ __forceinline__ void aggregate_weighted_body(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out,
+                                                        uint32_t B, uint32_t K, uint32_t T) {
   // torch.sum(hyp * scores.unsqueeze(-1), dim=1): products rounded, accumulated k = 0..K-1 left to right
-  const size_t n = (size_t)B * T * kF;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t bt = i / kF;
-    const uint32_t e = (uint32_t)(i - bt * kF);
-    const uint32_t b = (uint32_t)(bt / T), t = (uint32_t)(bt - (size_t)b * T);
+  const I clip = (I)T * kF, n = (I)B * clip;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (I)gridDim.x * blockDim.x) {
+    const I b = i / clip, r = i - b * clip, t = r / kF;
+    const float* hp = hyp + (size_t)b * K * clip + r;
+    const float* sp = scores + (size_t)b * K * T + t;
     float acc = 0.f;
-    for (uint32_t k = 0; k < K; ++k) {
-      const size_t f = ((size_t)b * K + k) * T + t;
-      acc = __fadd_rn(acc, __fmul_rn(hyp[f * kF + e], scores[f]));
-    }
+    for (uint32_t k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(hp[(size_t)k * clip], sp[(size_t)k * T]));
     out[i] = acc;
   }
+}
+__global__ void aggregate_weighted_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out,
+                                          uint32_t B, uint32_t K, uint32_t T) {
+  if ((uint64_t)B * T * kF < (1ull << 32))
+    aggregate_weighted_body<uint32_t>(hyp, scores, out, B, K, T);
+  else
+    aggregate_weighted_body<uint64_t>(hyp, scores, out, B, K, T);
 }
 
 // Flip test-time augmentation epilogue (hpe/eval_utils.py:83-142): hyp / scores hold 2B clips, the last B being the forward of the
@@ -487,45 +506,74 @@ __global__ void aggregate_tta_kernel(const float* __restrict__ hyp, const float*
   }
 }
 
-__global__ void argmax_score_kernel(const float* __restrict__ scores, int64_t* __restrict__ idx, uint32_t B, uint32_t K, uint32_t T) {
-  const size_t n = (size_t)B * T;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t b = (uint32_t)(i / T), t = (uint32_t)(i - (size_t)b * T);
-    float best = scores[((size_t)b * K) * T + t];
-    int bk = 0;
-    for (uint32_t k = 1; k < K; ++k) {
-      const float s = scores[((size_t)b * K + k) * T + t];
-      if (s > best) {  // torch.argmax: first maximal index
-        best = s;
-        bk = (int)k;
-      }
+__device__ __forceinline__ int argmax_score(const float* __restrict__ sp, uint32_t K, uint32_t T) {
+  float best = sp[0];
+  int bk = 0;
+  for (uint32_t k = 1; k < K; ++k) {
+    const float s = sp[(size_t)k * T];
+    if (s > best) {  // torch.argmax: first maximal index
+      best = s;
+      bk = (int)k;
     }
-    idx[i] = bk;
+  }
+  return bk;
+}
+
+__global__ void argmax_score_kernel(const float* __restrict__ scores, int64_t* __restrict__ idx, uint32_t B, uint32_t K, uint32_t T) {
+  const uint32_t n = B * T;   // check_dims: B T < 2^31
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t b = i / T, t = i - b * T;
+    idx[i] = argmax_score(scores + (size_t)b * K * T + t, K, T);
   }
 }
 
+// out[b,t] = hyp[b, idx[b,t], t]
+template <typename I>
+__device__ __forceinline__ void gather_hyp_body(const float* __restrict__ hyp, const int64_t* __restrict__ idx, float* __restrict__ out,
+                                                uint32_t B, uint32_t K, uint32_t T) {
+  const I clip = (I)T * kF, n = (I)B * clip;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (I)gridDim.x * blockDim.x) {
+    const I b = i / clip, r = i - b * clip, t = r / kF;
+    const int64_t k = idx[(size_t)b * T + t];
+    out[i] = hyp[((size_t)b * K + (size_t)k) * clip + r];
+  }
+}
 __global__ void gather_hyp_kernel(const float* __restrict__ hyp, const int64_t* __restrict__ idx, float* __restrict__ out, uint32_t B,
                                   uint32_t K, uint32_t T) {
-  const size_t n = (size_t)B * T * kF;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t bt = i / kF;
-    const uint32_t e = (uint32_t)(i - bt * kF);
-    const uint32_t b = (uint32_t)(bt / T), t = (uint32_t)(bt - (size_t)b * T);
-    const int64_t k = idx[bt];
-    out[i] = hyp[(((size_t)b * K + (size_t)k) * T + t) * kF + e];
-  }
+  if ((uint64_t)B * T * kF < (1ull << 32))
+    gather_hyp_body<uint32_t>(hyp, idx, out, B, K, T);
+  else
+    gather_hyp_body<uint64_t>(hyp, idx, out, B, K, T);
 }
 
 // ------------------------------------------------------------------------------------------------ MPJPE
 constexpr int kMpjpeBlocks = 148 * 4;
+__device__ __forceinline__ double point_dist(float g0, float g1, float g2, float p0, float p1, float p2) {
+  const float d0 = g0 - p0, d1 = g1 - p1, d2 = g2 - p2;
+  return (double)__fsqrt_rn(__fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+}
+// kVec: both arrays 16-byte aligned -> a thread takes 4 points = 3 x 16 bytes of each array per step
+template <bool kVec>
 __global__ void mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ gt, size_t n_points,
                                      double* __restrict__ partials) {
   __shared__ double red[8];
   double acc = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (size_t)gridDim.x * blockDim.x) {
-    const float d0 = gt[i * 3 + 0] - pred[i * 3 + 0], d1 = gt[i * 3 + 1] - pred[i * 3 + 1], d2 = gt[i * 3 + 2] - pred[i * 3 + 2];
-    acc += (double)__fsqrt_rn(__fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0))));
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n_quads = kVec ? n_points / 4 : 0;
+  if (kVec) {
+    const float4* p4 = reinterpret_cast<const float4*>(pred);
+    const float4* g4 = reinterpret_cast<const float4*>(gt);
+    for (size_t q = tid; q < n_quads; q += stride) {
+      const float4 pa = p4[q * 3], pb = p4[q * 3 + 1], pc = p4[q * 3 + 2];
+      const float4 ga = g4[q * 3], gb = g4[q * 3 + 1], gc = g4[q * 3 + 2];
+      acc += point_dist(ga.x, ga.y, ga.z, pa.x, pa.y, pa.z);
+      acc += point_dist(ga.w, gb.x, gb.y, pa.w, pb.x, pb.y);
+      acc += point_dist(gb.z, gb.w, gc.x, pb.z, pb.w, pc.x);
+      acc += point_dist(gc.y, gc.z, gc.w, pc.y, pc.z, pc.w);
+    }
   }
+  for (size_t i = n_quads * 4 + tid; i < n_points; i += stride)
+    acc += point_dist(gt[i * 3 + 0], gt[i * 3 + 1], gt[i * 3 + 2], pred[i * 3 + 0], pred[i * 3 + 1], pred[i * 3 + 2]);
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -535,10 +583,12 @@ __global__ void mpjpe_partial_kernel(const float* __restrict__ pred, const float
     partials[blockIdx.x] = s;
   }
 }
+// one warp, fixed order: lane l adds partials l, l+32, ..., then a butterfly
 __global__ void mpjpe_finalize_kernel(const double* __restrict__ partials, int n, double n_points, float* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0;
-    for (int i = 0; i < n; ++i) s += partials[i];
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += 32) s += partials[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
     out[0] = (float)s;
     out[1] = (float)(s / n_points);
   }
@@ -577,11 +627,11 @@ int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int
   MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
              "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = loss_smem_bytes();
+  const size_t smem = loss_smem_bytes(kFwdWarps, kFwdBufs);
   const int grid = loss_grid(B, T, kTileFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
+    kernel<<<grid, kFwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
   };
   if (squared)
     launch(loss_fwd_kernel<true, false>);
@@ -603,19 +653,19 @@ int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const flo
   MP_REQUIRE(!(squared && joint_weights == nullptr), MP_EINVAL,
              "squared WTA loss without joint weights is an error in the reference (F.mse_loss returns a scalar)");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = loss_smem_bytes();
+  const size_t smem = loss_smem_bytes(kFwdWarps, kFwdBufs);
   const int grid = loss_grid(B, T, kTileFrames);
   double* partials = reinterpret_cast<double*>(workspace);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, d, wta_val, wta_idx, nullptr, partials);
+    kernel<<<grid, kFwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, d, wta_val, wta_idx, nullptr, partials);
   };
   if (squared)
     launch(loss_fwd_kernel<true, true>);
   else
     launch(loss_fwd_kernel<false, true>);
   MP_CHECK(check_launch("loss_fwd_kernel"));
-  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid * kLossWarps, d, squared, beta, vel_w, smooth_w, terms);
+  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid * kFwdWarps, d, squared, beta, vel_w, smooth_w, terms);
   return check_launch("loss_finalize_kernel");
 }
 
@@ -629,11 +679,11 @@ int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const flo
   MP_REQUIRE(grad_scores == nullptr || scores != nullptr, MP_EINVAL, "mp_loss_bwd: scores required for grad_scores");
   MP_REQUIRE(aligned16(hyp) && aligned16(y), MP_EALIGN, "mp_loss_bwd: hyp and y must be 16-byte aligned");
   const LossDims d{(uint32_t)B, (uint32_t)K, (uint32_t)T};
-  const size_t smem = loss_smem_bytes();
+  const size_t smem = loss_smem_bytes(kBwdWarps, kBwdBufs);
   const int grid = loss_grid(B, T, kBwdFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kLossWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
+    kernel<<<grid, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
                                                                    grad_terms, grad_wta_val, grad_hyp, grad_scores);
   };
   if (squared)
@@ -701,7 +751,13 @@ int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, v
   int blocks = (int)((n_points + 255) / 256);
   if (blocks > kMpjpeBlocks) blocks = kMpjpeBlocks;
   double* partials = reinterpret_cast<double*>(workspace);
-  mpjpe_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+  if (aligned16(pred) && aligned16(gt)) {
+    blocks = (int)((n_points / 4 + 255) / 256);
+    blocks = blocks < 1 ? 1 : (blocks > kMpjpeBlocks ? kMpjpeBlocks : blocks);
+    mpjpe_partial_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+  } else {
+    mpjpe_partial_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+  }
   MP_CHECK(check_launch("mpjpe_partial_kernel"));
   mpjpe_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, blocks, (double)n_points, out);
   return check_launch("mpjpe_finalize_kernel");
