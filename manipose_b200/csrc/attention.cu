@@ -1216,7 +1216,332 @@ attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ backward, tcgen05
+// Reverse mode of the block-diagonal kernel above (same tiles: 7 frames of 17 joints, or P whole tracks of a short clip, per 128-row
+// tile; head_dim 64): five [128 x 128 x 64]-class tcgen05 MMAs per (tile, head) instead of one mma.sync CTA per (sequence, head).
+//   TMA   Q, K, V (from qkv) and dO tiles [128 x 64]
+//   MMA   S = Q K^T -> TMEM[0,128),  dP = dO V^T -> TMEM[128,256)
+//   4 softmax warps, thread = query row i: e = exp2(scale (S - max)) written back over S (tcgen05.st), D_i = sum_j P_ij dP_ij
+//         (= dO_i . O_i, so the forward output is not read), then P and dS = scale P (dP - D) as 16-bit rows (zeros outside the row's
+//         window and for rows of other tiles) into shared memory: K-major A operands that the MN-major descriptors read transposed
+//   MMA   dV = P^T dO -> TMEM[0,64),  dK = dS^T Q -> TMEM[64,128),  dQ = dS K -> TMEM[128,192)
+//   epilogue: three [128 x 64] tiles staged over the dead Q / K / dO tiles, one TMA store each into the [.., 3C] gradient.
+// 112 KB of shared memory and 256 TMEM columns: two CTAs per SM.
+constexpr int kBwdTcSmem = 7 * 16384 + 64;
+
+template <typename D, bool kTracks>
+__global__ void __launch_bounds__(kTcThreads, 2)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
+                   int n_rows, int n_tok, int C, int n_heads, int G, int tiles_per_clip) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sq = smem;                   // [128 x 64] queries;        later the dQ staging tile
+  uint8_t* sk = smem + 16384;           // [128 x 64] keys;           later dK
+  uint8_t* sdo = smem + 32768;          // [128 x 64] output grads;   later dV
+  uint8_t* sv = smem + 49152;           // [128 x 64] values;         later P k-block 0 (P k-block 1 follows at +16384)
+  uint8_t* sp = sv;                     // [128 x 128] P, two k-blocks of [128 x 64]
+  uint8_t* sds = smem + 81920;          // [128 x 128] dS, two k-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * 16384);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_vdo = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x % n_heads;
+  const int tile = (blockIdx.x / n_heads) % tiles_per_clip;
+  const int clip = blockIdx.x / (n_heads * tiles_per_clip);
+  const int row0 = tile * G;
+  const int rows_valid = kTracks ? G * n_rows : 128;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    ptx::prefetch_tmap(&tm_do);
+    ptx::prefetch_tmap(&tm_dqkv);
+    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_vdo, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_p, 128);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      if constexpr (kTracks) {
+        const uint32_t box_bytes = (uint32_t)rows_valid * 128u;
+        ptx::mbar_expect_tx(bar_qk, 2 * box_bytes);
+        ptx::tma_load_4d(sq, &tm_in, bar_qk, head * 64, row0, 0, clip);
+        ptx::tma_load_4d(sk, &tm_in, bar_qk, C + head * 64, row0, 0, clip);
+        ptx::mbar_expect_tx(bar_vdo, 2 * box_bytes);
+        ptx::tma_load_4d(sv, &tm_in, bar_vdo, 2 * C + head * 64, row0, 0, clip);
+        ptx::tma_load_4d(sdo, &tm_do, bar_vdo, head * 64, row0, 0, clip);
+      } else {
+        ptx::mbar_expect_tx(bar_qk, 32768);
+        ptx::tma_load_3d(sq, &tm_in, bar_qk, head * 64, row0, clip);
+        ptx::tma_load_3d(sk, &tm_in, bar_qk, C + head * 64, row0, clip);
+        ptx::mbar_expect_tx(bar_vdo, 32768);
+        ptx::tma_load_3d(sv, &tm_in, bar_vdo, 2 * C + head * 64, row0, clip);
+        ptx::tma_load_3d(sdo, &tm_do, bar_vdo, head * 64, row0, clip);
+      }
+      constexpr uint32_t idesc_kk = ptx::umma_idesc_16(128, 128, D::kUmmaFmt);
+      ptx::mbar_wait(bar_qk, 0);
+      ptx::tc_fence_after();
+      {
+        const uint64_t da = ptx::umma_desc_sw128(smem_u32(sq));
+        const uint64_t db = ptx::umma_desc_sw128(smem_u32(sk));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k != 0 ? 1u : 0u);
+      }
+      ptx::mbar_wait(bar_vdo, 0);
+      ptx::tc_fence_after();
+      {
+        const uint64_t da = ptx::umma_desc_sw128(smem_u32(sdo));
+        const uint64_t db = ptx::umma_desc_sw128(smem_u32(sv));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + 128u, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k != 0 ? 1u : 0u);
+        ptx::umma_commit(bar_s);
+      }
+      ptx::mbar_wait(bar_p, 0);
+      ptx::tc_fence_after();
+      {
+        // contraction over the 128 query rows, 16 per instruction (2048 bytes of either tile); the two 64-column halves of P / dS are
+        // MN atoms 16 KB apart
+        constexpr uint32_t idesc_t = ptx::umma_idesc_16_abmn(128, 64, D::kUmmaFmt);
+        const uint32_t pa = smem_u32(sp), dsa = smem_u32(sds), doa = smem_u32(sdo), qa = smem_u32(sq), ka = smem_u32(sk);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_f16(tmem_base, ptx::umma_desc_mn_sw128_lbo(pa + (uint32_t)(k * 2048), 16384u), ptx::umma_desc_mn_sw128(doa + (uint32_t)(k * 2048)),
+                        idesc_t, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_f16(tmem_base + 64u, ptx::umma_desc_mn_sw128_lbo(dsa + (uint32_t)(k * 2048), 16384u),
+                        ptx::umma_desc_mn_sw128(qa + (uint32_t)(k * 2048)), idesc_t, k != 0 ? 1u : 0u);
+        // dQ = dS K: contraction over the 128 key columns of dS (K-major A, as P in the forward), K rows as the MN-major B operand
+        constexpr uint32_t idesc_q = ptx::umma_idesc_16_bmn(128, 64, D::kUmmaFmt);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_f16(tmem_base + 128u, ptx::umma_desc_sw128(dsa + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32)),
+                        ptx::umma_desc_mn_sw128(ka + (uint32_t)(k * 2048)), idesc_q, k != 0 ? 1u : 0u);
+        ptx::umma_commit(bar_o);
+      }
+    }
+  } else {
+    const int row = threadIdx.x;                       // tile-local query row <-> TMEM lane
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(32 * warp) << 16);
+    const float scale = 0.125f, scale_log2 = 0.125f * kLog2e;
+    int a = (row / n_tok) * n_tok;
+    int b = a + n_tok;
+    if (b > 128) b = 128;
+    if (row0 + b > n_rows) b = n_rows - row0;
+    bool live = row < G && row0 + row < n_rows && b > a;   // rows [G, 128) are the next tile's: no contribution to this tile's dK / dV
+    int c_lo = ((32 * warp) / n_tok * n_tok) / 32;
+    int c_hi = (((32 * warp + 31) / n_tok + 1) * n_tok + 31) / 32;
+    if (c_hi > 4) c_hi = 4;
+    uint32_t win[4] = {0u, 0u, 0u, 0u};            // bit i of win[c]: column 32 c + i belongs to this row's softmax window
+    if constexpr (kTracks) {
+      const int trk = row % G;                     // G = tracks per tile = interleave period
+      live = row < rows_valid && row0 + trk < n_tok;
+      c_lo = 0;
+      c_hi = (rows_valid + 31) / 32;
+      uint32_t pat = 0u;
+      for (int i = 0; i < 32; i += G) pat |= 1u << i;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int start = ((trk - 32 * c) % G + G) % G;
+        const int left = rows_valid - 32 * c;
+        const uint32_t range = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+        win[c] = (pat << start) & range;
+      }
+      // rows the track boxes do not fill hold stale shared memory: as contraction rows of dV / dK / dQ they must be zero (0 * NaN)
+      for (int r = rows_valid + row; r < 128; r += 128) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          *reinterpret_cast<uint4*>(sq + (size_t)r * 128 + q * 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(sk + (size_t)r * 128 + q * 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(sdo + (size_t)r * 128 + q * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int lo = a - 32 * c, hi = b - 32 * c;
+        const uint32_t upto_hi = hi >= 32 ? 0xffffffffu : (hi > 0 ? (1u << hi) - 1u : 0u);
+        const uint32_t upto_lo = lo >= 32 ? 0xffffffffu : (lo > 0 ? (1u << lo) - 1u : 0u);
+        win[c] = upto_hi & ~upto_lo;
+      }
+    }
+    if (!live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) win[c] = 0u;
+    }
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    // ---- row maximum over the window
+    float mx = -INFINITY;
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if ((win[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+    const float ms = live ? -mx * scale_log2 : 0.f;
+    // ---- e = exp2(scale (s - max)) back over S, row sum, and sum_j e_j dP_j
+    float sum = 0.f, edp = 0.f;
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t r[32], g[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+      ptx::tmem_ld32(t_row + 128u + (uint32_t)(c * 32), g);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool in = (win[c] >> i) & 1u;
+        const float e = in ? fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, ms)) : 0.f;
+        sum += e;
+        edp = fmaf(e, in ? __uint_as_float(g[i]) : 0.f, edp);
+        r[i] = __float_as_uint(e);
+      }
+      ptx::tmem_st32(t_row + (uint32_t)(c * 32), r);
+    }
+    ptx::tmem_st_wait();
+    const float inv = live ? 1.0f / sum : 0.f;
+    const float dsum = edp * inv;                      // D_i
+    // ---- P and dS rows (16-bit), all 128 columns
+    for (int c = 0; c < 4; ++c) {
+      float pv[32], dv[32];
+      if (c >= c_lo && c < c_hi) {
+        uint32_t r[32], g[32];
+        ptx::tmem_ld32(t_row + (uint32_t)(c * 32), r);
+        ptx::tmem_ld32(t_row + 128u + (uint32_t)(c * 32), g);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool in = (win[c] >> i) & 1u;
+          const float pr = __uint_as_float(r[i]) * inv;      // e is 0 outside the window
+          pv[i] = pr;
+          dv[i] = in ? pr * (__uint_as_float(g[i]) - dsum) * scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pv[i] = dv[i] = 0.f;
+      }
+      const size_t off = (size_t)(c >> 1) * 16384 + (size_t)row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o, d4;
+        o.x = D::pack2(pv[8 * q + 0], pv[8 * q + 1]);
+        o.y = D::pack2(pv[8 * q + 2], pv[8 * q + 3]);
+        o.z = D::pack2(pv[8 * q + 4], pv[8 * q + 5]);
+        o.w = D::pack2(pv[8 * q + 6], pv[8 * q + 7]);
+        d4.x = D::pack2(dv[8 * q + 0], dv[8 * q + 1]);
+        d4.y = D::pack2(dv[8 * q + 2], dv[8 * q + 3]);
+        d4.z = D::pack2(dv[8 * q + 4], dv[8 * q + 5]);
+        d4.w = D::pack2(dv[8 * q + 6], dv[8 * q + 7]);
+        const uint32_t chunk = (((uint32_t)((c & 1) * 4 + q) ^ sw) << 4);
+        *reinterpret_cast<uint4*>(sp + off + chunk) = o;
+        *reinterpret_cast<uint4*>(sds + off + chunk) = d4;
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(bar_p);
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    // ---- dV | dK | dQ: TMEM columns [0,64) [64,128) [128,192) -> staging tiles sdo | sk | sq
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(t_row + (uint32_t)(m * 64), r0);
+      ptx::tmem_ld32(t_row + (uint32_t)(m * 64) + 32u, r1);
+      ptx::tmem_ld_wait();
+      uint8_t* orow = (m == 0 ? sdo : (m == 1 ? sk : sq)) + (size_t)row * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t(&r)[32] = q < 4 ? r0 : r1;
+        const int bb = (q & 3) * 8;
+        uint4 o;
+        o.x = D::pack2(__uint_as_float(r[bb + 0]), __uint_as_float(r[bb + 1]));
+        o.y = D::pack2(__uint_as_float(r[bb + 2]), __uint_as_float(r[bb + 3]));
+        o.z = D::pack2(__uint_as_float(r[bb + 4]), __uint_as_float(r[bb + 5]));
+        o.w = D::pack2(__uint_as_float(r[bb + 6]), __uint_as_float(r[bb + 7]));
+        *reinterpret_cast<uint4*>(orow + (((uint32_t)q ^ sw) << 4)) = o;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) {
+      if constexpr (kTracks) {
+        ptx::tma_store_4d(&tm_dqkv, sq, head * 64, row0, 0, clip);
+        ptx::tma_store_4d(&tm_dqkv, sk, C + head * 64, row0, 0, clip);
+        ptx::tma_store_4d(&tm_dqkv, sdo, 2 * C + head * 64, row0, 0, clip);
+      } else {
+        ptx::tma_store_3d(&tm_dqkv, sq, head * 64, row0, clip);
+        ptx::tma_store_3d(&tm_dqkv, sk, C + head * 64, row0, clip);
+        ptx::tma_store_3d(&tm_dqkv, sdo, 2 * C + head * 64, row0, clip);
+      }
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
 }  // namespace
+
+// mp_attention_bwd (train.cu) for head_dim 64: spatial sequences of <= 32 tokens, temporal tracks of <= 128 frames.
+int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads, int temporal,
+                     int dtype, cudaStream_t s) {
+  const bool bf = dtype == MP_DTYPE_BF16;
+  CUtensorMap tin, tdo, tdq;
+  if (temporal) {
+    const int P = 128 / (int)n_frames < n_tok ? 128 / (int)n_frames : n_tok;
+    const int64_t tiles_per_clip = (n_tok + P - 1) / P;
+    MP_REQUIRE(n_clips * tiles_per_clip * n_heads < ((int64_t)1 << 31), MP_EINVAL, "mp_attention_bwd: too many sequences");
+    MP_CHECK(get_tmap_track(&tin, qkv, n_clips, n_frames, n_tok, 3 * C, (int)n_frames, dtype, P));
+    MP_CHECK(get_tmap_track(&tdo, dout, n_clips, n_frames, n_tok, C, (int)n_frames, dtype, P));
+    MP_CHECK(get_tmap_track(&tdq, dqkv, n_clips, n_frames, n_tok, 3 * C, (int)n_frames, dtype, P));
+    auto launch = [&](auto kernel) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
+      kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s>>>(tin, tdo, tdq, (int)n_frames, n_tok, C, n_heads, P,
+                                                                                          (int)tiles_per_clip);
+    };
+    if (bf) launch(attn_bwd_tc_kernel<Bf16, true>); else launch(attn_bwd_tc_kernel<Fp16, true>);
+    return check_launch("attn_bwd_tc_kernel<tracks>");
+  }
+  const int G = (128 / n_tok) * n_tok;
+  const int64_t rows_per_clip = n_frames * n_tok;
+  const int64_t tiles_per_clip = (rows_per_clip + G - 1) / G;
+  MP_REQUIRE(n_clips * tiles_per_clip * n_heads < ((int64_t)1 << 31) && rows_per_clip < ((int64_t)1 << 30), MP_EINVAL, "mp_attention_bwd: too many sequences");
+  MP_CHECK(get_tmap_clip_rows(&tin, qkv, n_clips, rows_per_clip, 3 * C, 128, dtype));
+  MP_CHECK(get_tmap_clip_rows(&tdo, dout, n_clips, rows_per_clip, C, 128, dtype));
+  MP_CHECK(get_tmap_clip_rows(&tdq, dqkv, n_clips, rows_per_clip, 3 * C, G, dtype));
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
+    kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s>>>(tin, tdo, tdq, (int)rows_per_clip, n_tok, C, n_heads, G,
+                                                                                        (int)tiles_per_clip);
+  };
+  if (bf) launch(attn_bwd_tc_kernel<Bf16, false>); else launch(attn_bwd_tc_kernel<Fp16, false>);
+  return check_launch("attn_bwd_tc_kernel");
+}
+
 }  // namespace mp
 
 extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads, int mode,

@@ -16,6 +16,9 @@
 #include "row.cuh"
 
 namespace mp {
+
+int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads,
+                     int temporal, int dtype, cudaStream_t s);  // attention.cu
 namespace {
 
 // -------------------------------------------------------------------------------------------------- LayerNorm backward
@@ -711,6 +714,10 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
   const int64_t n_items = n_seq * n_heads;
   MP_REQUIRE(n_items < ((int64_t)1 << 31), MP_EINVAL, "mp_attention_bwd: too many (sequence, head) items");
   if (n_items == 0) return MP_OK;
+  // head_dim 64 and short sequences: the tcgen05 block-diagonal kernel (attention.cu); MANIPOSE_ATTN_BWD_MMA keeps the mma.sync one (A/B)
+  static const bool legacy = getenv("MANIPOSE_ATTN_BWD_MMA") != nullptr;
+  if (hd == 64 && !legacy && (temporal ? n_frames <= 128 : n_tok <= 32))
+    return attention_bwd_tc(qkv, dout, dqkv, n_clips, n_frames, n_tok, C, n_heads, temporal, dtype, (cudaStream_t)stream);
   const bool bf = dtype == MP_DTYPE_BF16;
   const int Lp = ((int)L + 31) & ~31;
   int n_warps = Lp / 16;

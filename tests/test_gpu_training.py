@@ -86,7 +86,8 @@ def _attn(qkv, n_clips, n_frames, n_tok, c, heads, temporal):
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("n_clips,n_frames,n_tok,c,temporal", [
     (3, 27, 17, 512, True), (3, 27, 17, 512, False), (1, 243, 17, 512, True), (2, 243, 17, 512, False), (2, 81, 16, 128, True),
-    (2, 27, 16, 128, False), (1, 1, 17, 512, True), (5, 9, 17, 512, False)])
+    (2, 27, 16, 128, False), (1, 1, 17, 512, True), (5, 9, 17, 512, False), (2, 81, 17, 512, True), (1, 128, 17, 512, True),
+    (2, 50, 17, 512, True), (1, 3, 17, 512, False)])
 def test_attention_bwd_vs_autograd(n_clips, n_frames, n_tok, c, temporal, dtype):
     from manipose_b200 import ops, train_ops as T
     td = DT[dtype]
