@@ -141,6 +141,8 @@ constexpr int kTWarps = 8;
 template <int HD, typename D>
 __global__ void __launch_bounds__(kTWarps * 32, 2)
 attn_temporal_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int n_frames, int n_tok, int C, int n_heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LD = HD * 2 + 16;           // padded row bytes
   constexpr int CH = HD / 8;                // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem[];
@@ -214,6 +216,7 @@ template <typename D>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
                         int n_frames, int n_tok, int C, int n_heads, int m_tiles) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // [ Q 16 KB | K 32 KB | +16 KB ] = 64 KB, later P (4 k-blocks of [128 x 64] 16-bit), later the O staging tile; then V 32 KB
@@ -258,6 +261,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -392,6 +396,7 @@ template <typename D>
 __global__ void __launch_bounds__(kTc2Threads, 1)
 attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
                          int n_frames, int n_tok, int C, int n_heads, int n_items) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sv = smem + 3 * 65536;
@@ -431,6 +436,7 @@ attn_temporal_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   auto decode = [&](int item, int& clip, int& tok, int& head) {
     head = item % n_heads;
@@ -651,6 +657,7 @@ template <typename D>
 __global__ void __launch_bounds__(kTc3Threads, 1)
 attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_o,
                          int n_frames, int n_tok, int C, int n_heads, int n_items) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ostage = smem + 2 * kTc3Opnd;                                   // [2] 16 KB output staging tile of group g
@@ -693,6 +700,7 @@ attn_temporal_tc3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   auto decode = [&](int item, int& clip, int& tok, int& head) {
     head = item % n_heads;
@@ -936,6 +944,7 @@ template <typename D, bool kTracks>
 __global__ void __launch_bounds__(kTcThreads, 4)
 attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_o, int n_rows, int n_tok, int C,
                        int n_heads, int G, int tiles_per_clip) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sq = smem;                 // [128 x 64] queries; later P k-block 0
@@ -975,6 +984,7 @@ attn_spatial_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -1153,6 +1163,8 @@ constexpr int kSWarps = 8;
 template <int HD, typename D>
 __global__ void __launch_bounds__(kSWarps * 32)
 attn_spatial_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int64_t n_seq, int n_tok, int C, int n_heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LD = HD * 2 + 16;           // padded row bytes
   constexpr int CH = HD / 8;                // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1233,6 +1245,7 @@ template <typename D, bool kTracks>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
                    int n_rows, int n_tok, int C, int n_heads, int G, int tiles_per_clip) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sq = smem;                   // [128 x 64] queries;        later the dQ staging tile
@@ -1275,6 +1288,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -1520,7 +1534,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_cl
     MP_CHECK(get_tmap_track(&tdq, dqkv, n_clips, n_frames, n_tok, 3 * C, (int)n_frames, dtype, P));
     auto launch = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
-      kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s>>>(tin, tdo, tdq, (int)n_frames, n_tok, C, n_heads, P,
+      launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, (int)n_frames, n_tok, C, n_heads, P,
                                                                                           (int)tiles_per_clip);
     };
     if (bf) launch(attn_bwd_tc_kernel<Bf16, true>); else launch(attn_bwd_tc_kernel<Fp16, true>);
@@ -1535,7 +1549,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_cl
   MP_CHECK(get_tmap_clip_rows(&tdq, dqkv, n_clips, rows_per_clip, 3 * C, G, dtype));
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
-    kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s>>>(tin, tdo, tdq, (int)rows_per_clip, n_tok, C, n_heads, G,
+    launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, (int)rows_per_clip, n_tok, C, n_heads, G,
                                                                                         (int)tiles_per_clip);
   };
   if (bf) launch(attn_bwd_tc_kernel<Bf16, false>); else launch(attn_bwd_tc_kernel<Fp16, false>);
@@ -1577,7 +1591,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       const int smem_tc = 49152 + 64;
       auto launch_tr = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
-        kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s>>>(tin, to, (int)n_frames, n_tok, C, n_heads, P,
+        launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s, tin, to, (int)n_frames, n_tok, C, n_heads, P,
                                                                                          (int)tiles_per_clip);
       };
       if (bf) launch_tr(attn_spatial_tc_kernel<Bf16, true>); else launch_tr(attn_spatial_tc_kernel<Fp16, true>);
@@ -1598,7 +1612,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
         const int grid = n_items < sm_count() ? n_items : sm_count();
         auto launch_3 = [&](auto kernel) {
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc3Smem);
-          kernel<<<grid, kTc3Threads, kTc3Smem, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
+          launch_k(kernel, grid, kTc3Threads, kTc3Smem, s, tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
         };
         if (bf) launch_3(attn_temporal_tc3_kernel<Bf16>); else launch_3(attn_temporal_tc3_kernel<Fp16>);
         return check_launch("attn_temporal_tc3_kernel");
@@ -1609,7 +1623,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
         const int grid = n_items < sm_count() ? n_items : sm_count();
         auto launch_p = [&](auto kernel) {
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
-          kernel<<<grid, kTc2Threads, smem_p, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
+          launch_k(kernel, grid, kTc2Threads, smem_p, s, tq, tkv, to, (int)n_frames, n_tok, C, n_heads, n_items);
         };
         if (bf) launch_p(attn_temporal_tc2_kernel<Bf16>); else launch_p(attn_temporal_tc2_kernel<Fp16>);
         return check_launch("attn_temporal_tc2_kernel");
@@ -1617,7 +1631,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
       const int smem_tc = 98304 + 64;
       auto launch_tc = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
-        kernel<<<(unsigned)ctas, kTcThreads, smem_tc, s>>>(tq, tkv, to, (int)n_frames, n_tok, C, n_heads, m_tiles);
+        launch_k(kernel, (unsigned)ctas, kTcThreads, smem_tc, s, tq, tkv, to, (int)n_frames, n_tok, C, n_heads, m_tiles);
       };
       if (bf) launch_tc(attn_temporal_tc_kernel<Bf16>); else launch_tc(attn_temporal_tc_kernel<Fp16>);
       return check_launch("attn_temporal_tc_kernel");
@@ -1627,7 +1641,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
     MP_REQUIRE(ctas < ((int64_t)1 << 31), MP_EINVAL, "mp_attention: too many sequences");
     auto launch = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kernel<<<(unsigned)ctas, kTWarps * 32, smem, s>>>(in, o, (int)n_frames, n_tok, C, n_heads);
+      launch_k(kernel, (unsigned)ctas, kTWarps * 32, smem, s, in, o, (int)n_frames, n_tok, C, n_heads);
     };
     if (hd == 64) {
       if (bf) launch(attn_temporal_kernel<64, Bf16>); else launch(attn_temporal_kernel<64, Fp16>);
@@ -1650,7 +1664,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
     const int smem_tc = 49152 + 64;
     auto launch_tc = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
-      kernel<<<(unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s>>>(tin, to, (int)rows_per_clip, n_tok, C, n_heads, G,
+      launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, smem_tc, s, tin, to, (int)rows_per_clip, n_tok, C, n_heads, G,
                                                                                        (int)tiles_per_clip);
     };
     if (bf) launch_tc(attn_spatial_tc_kernel<Bf16, false>); else launch_tc(attn_spatial_tc_kernel<Fp16, false>);
@@ -1666,7 +1680,7 @@ extern "C" int mp_attention(const void* qkv, void* out, int64_t n_clips, int64_t
   if (grid > (n_items + kSWarps - 1) / kSWarps) grid = (n_items + kSWarps - 1) / kSWarps;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)grid, kSWarps * 32, smem, s>>>(in, o, n_seq, n_tok, C, n_heads);
+    launch_k(kernel, (unsigned)grid, kSWarps * 32, smem, s, in, o, n_seq, n_tok, C, n_heads);
   };
   if (hd == 64) {
     if (bf) launch(attn_spatial_kernel<64, Bf16>); else launch(attn_spatial_kernel<64, Fp16>);

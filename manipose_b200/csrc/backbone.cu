@@ -23,6 +23,8 @@ layernorm_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, uint
                  const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps, const float* __restrict__ pos,
                  int64_t pos_div, int64_t pos_mod, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                  int64_t n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<C>;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(kTokWarps * 32)
 embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
                     const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                     float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_tokens, int n_joints) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<512>;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
@@ -104,6 +108,8 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
                       const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                       float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_frames, int in_features,
                       int n_segments) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<kSegC>;
   extern __shared__ __align__(16) float wt[];  // [in_features][128]
   const int seg = blockIdx.y;
@@ -173,6 +179,8 @@ heads_fwd_kernel(const float* __restrict__ x, const float* __restrict__ post_g, 
                  const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
                  const float* __restrict__ score_w, const float* __restrict__ score_b, float* __restrict__ rot, float* __restrict__ logits,
                  int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<kHeadC>;
   extern __shared__ __align__(16) float sm[];
   const int O = out_dim + (with_score ? 1 : 0);  // outputs per head (<= 7, so 4 tokens x O <= 28 values per butterfly)
@@ -294,6 +302,8 @@ __global__ void __launch_bounds__(kTokWarps * 32)
 bones_value_kernel(const float* __restrict__ x, const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps,
                    const float* __restrict__ hg, const float* __restrict__ hb, const float* __restrict__ hw, const float* __restrict__ hbias,
                    float* __restrict__ values, int64_t n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<kSegC>;
   const int lane = threadIdx.x & 31;
   float pg[R::kPer], pb[R::kPer], g[R::kPer], bt[R::kPer], w[R::kPer];
@@ -319,6 +329,8 @@ bones_value_kernel(const float* __restrict__ x, const float* __restrict__ post_g
   }
 }
 __global__ void bones_mean_kernel(const float* __restrict__ values, float* __restrict__ bone_len, int64_t n_clips, int n_frames, int n_seg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_clips * n_seg) return;
   const int64_t b = i / n_seg;
@@ -335,6 +347,8 @@ __global__ void bones_mean_kernel(const float* __restrict__ values, float* __res
 __global__ void __launch_bounds__(kTokWarps * 32)
 heads_finish_kernel(const float* __restrict__ y, int ld, const float* __restrict__ score_w, const float* __restrict__ score_b,
                     float* __restrict__ rot, float* __restrict__ logits, int64_t n_clips, int n_frames, int n_hyp, int out_dim, int with_score) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
@@ -387,7 +401,7 @@ int mp_layernorm(const float* x_in, float* x_out, void* h_out, const float* post
   if (n_tokens == 0) return MP_OK;
   const int grid = token_grid(n_tokens);
   auto launch = [&](auto kernel) {
-    kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x_in, x_out, (uint16_t*)h_out, post_gamma, post_beta, post_eps, pos_embed,
+    launch_k(kernel, grid, kTokWarps * 32, 0, (cudaStream_t)stream, x_in, x_out, (uint16_t*)h_out, post_gamma, post_beta, post_eps, pos_embed,
                                                               pos_div, pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
@@ -411,7 +425,7 @@ int mp_embed_joints(const float* in2d, const float* W, const float* b, const flo
              "mp_embed_joints: x_out / h_out must be 16-byte aligned, in2d 8-byte aligned");
   if (n_tokens == 0) return MP_OK;
   auto launch = [&](auto kernel) {
-    kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
+    launch_k(kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
                                                                               (uint16_t*)h_out, n_tokens, n_joints);
   };
   if (dtype == MP_DTYPE_BF16) launch(embed_joints_kernel<Bf16>); else launch(embed_joints_kernel<Fp16>);
@@ -434,7 +448,7 @@ int mp_embed_segments(const float* in2d, const float* W, const float* b, const f
   const int cap = sm_count() * 2 / n_segments + 1;
   if (gx > cap) gx = cap;
   auto launch = [&](auto kernel) {
-    kernel<<<dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream>>>(in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
+    launch_k(kernel, dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream, in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
                                                                                  (uint16_t*)h_out, n_frames, in_features, n_segments);
   };
   if (dtype == MP_DTYPE_BF16) launch(embed_segments_kernel<Bf16>); else launch(embed_segments_kernel<Fp16>);
@@ -459,7 +473,7 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
   int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
   const int64_t cap = (int64_t)sm_count() * (smem > 110 * 1024 ? 1 : 2);
   if (ctas > cap) ctas = cap;
-  heads_fwd_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias, score_w,
+  launch_k(heads_fwd_kernel, (int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream, x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias, score_w,
                                                                               score_b, rot, logits, n_clips, (int)n_frames, n_hyp, out_dim,
                                                                               with_score);
   return check_launch("heads_fwd_kernel");
@@ -486,7 +500,7 @@ int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const 
   int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (ctas > cap) ctas = cap;
-  heads_finish_kernel<<<(int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream>>>(workspace, n_pad, score_w, score_b, rot, logits, n_clips,
+  launch_k(heads_finish_kernel, (int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream, workspace, n_pad, score_w, score_b, rot, logits, n_clips,
                                                                                  (int)n_frames, n_hyp, out_dim, with_score);
   return check_launch("heads_finish_kernel");
 }
@@ -503,11 +517,11 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
   MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * sizeof(float), MP_EWORKSPACE, "mp_bones_head: workspace too small");
   if (n_tokens == 0) return MP_OK;
   float* values = reinterpret_cast<float*>(workspace);
-  bones_value_kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
+  launch_k(bones_value_kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
                                                                                          values, n_tokens);
   MP_CHECK(check_launch("bones_value_kernel"));
   const int64_t n_out = n_clips * n_segments;
-  bones_mean_kernel<<<(int)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream>>>(values, bone_len, n_clips, (int)n_frames, n_segments);
+  launch_k(bones_mean_kernel, (int)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream, values, bone_len, n_clips, (int)n_frames, n_segments);
   return check_launch("bones_mean_kernel");
 }
 

@@ -30,6 +30,31 @@ int sm_count();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- programmatic dependent launch --------------------------------------------------------------------------------------
+// Every kernel on the hot paths is launched with cudaLaunchAttributeProgrammaticStreamSerialization (off with MANIPOSE_PDL=0) and
+// starts with  pdl_launch_dependents(); <prologue that touches no global data>; pdl_wait();  so that the NEXT kernel's CTAs are
+// resident and past their prologue (barrier init, TMEM allocation, descriptor prefetch) while this one drains: the step is a chain of
+// hundreds of 5-30 us kernels and the launch-to-launch gap is a measurable share of it.  pdl_wait() returns once the preceding kernel
+// has completed and its writes are visible; every kernel calls it before its first global read AND write (a successor may overwrite
+// what its predecessor still reads), which also makes completion transitive along the chain.  Without the attribute both are no-ops.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- skeleton (H36M-17 / MPI-INF-3DHP tree) as compile-time tables --------------
 constexpr int kJ = 17;
 constexpr int kBones = 16;

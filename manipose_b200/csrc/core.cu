@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mp {
@@ -52,9 +54,19 @@ int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
 template <typename D>
 __global__ void cast_f32_16_kernel(const float* __restrict__ src, typename D::T* __restrict__ dst, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) dst[i] = D::from_float(src[i]);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MANIPOSE_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 }  // namespace mp
@@ -92,9 +104,9 @@ int mp_cast_f32_to_16(const float* src, void* dst, int64_t n, int dtype, mp_stre
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == MP_DTYPE_BF16)
-    mp::cast_f32_16_kernel<mp::Bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+    launch_k(mp::cast_f32_16_kernel<mp::Bf16>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   else
-    mp::cast_f32_16_kernel<mp::Fp16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+    launch_k(mp::cast_f32_16_kernel<mp::Fp16>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, src, (__half*)dst, n);
   return mp::check_launch("cast_f32_16_kernel");
 }
 

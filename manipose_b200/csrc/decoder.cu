@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ root,
                    const float* __restrict__ logits, float* __restrict__ poses, float* __restrict__ scores, uint32_t n_poses,
                    uint32_t poses_per_clip, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames, int bulk_in, int bulk_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int kIn = in_floats<RD>();
   constexpr int kTileInBytes = tile_in_bytes<RD>();
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -329,11 +331,15 @@ decoder_fwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
 
 __global__ void softmax_hyp_fwd_kernel(const float* __restrict__ logits, float* __restrict__ scores, uint32_t n_clips, uint32_t n_hyp,
                                        uint32_t n_frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   softmax_hyp_rows(logits, scores, n_clips, n_hyp, n_frames);
 }
 
 __global__ void softmax_hyp_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ grad_scores,
                                        float* __restrict__ grad_logits, uint32_t n_clips, uint32_t n_hyp, uint32_t n_frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t n_items = n_clips * n_frames;
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_items; idx += gridDim.x * blockDim.x) {
     const uint32_t b = idx / n_frames, t = idx - b * n_frames;
@@ -525,6 +531,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1)
 decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bone_len, const float* __restrict__ grad_poses,
                    float* __restrict__ grad_rot6d, float* __restrict__ glen_part, float* __restrict__ grad_root, uint32_t n_poses,
                    uint32_t poses_per_clip, int bulk_ok) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int kIn = in_floats<RD>();
   constexpr int kTileInBytes = tile_in_bytes<RD>();
   constexpr int kBwdWarpBytes = bwd_warp_bytes<RD>();
@@ -619,6 +627,8 @@ decoder_bwd_kernel(const float* __restrict__ rot6d, const float* __restrict__ bo
 // grad_bone_len[clip][bone] = sum of the clip's partial rows, front to back
 __global__ void bone_grad_reduce_kernel(const float* __restrict__ glen_part, float* __restrict__ grad_bone_len, uint32_t n_clips,
                                         uint32_t poses_per_clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_clips * kBones) return;
   const uint32_t c = idx / kBones, i = idx - c * kBones;
@@ -657,7 +667,7 @@ int mp_decoder_fwd(const float* rot6d, const float* bone_len, const float* root,
   if (ctas > max_ctas) ctas = max_ctas;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(
+    launch_k(kernel, (unsigned)ctas, kWarpsPerCta * 32, smem, (cudaStream_t)stream, 
         rot6d, bone_len, root, logits, poses, scores, (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), (uint32_t)n_clips,
         (uint32_t)n_hyp, (uint32_t)n_frames, bulk_in, bulk_out);
   };
@@ -696,13 +706,13 @@ int mp_decoder_bwd(const float* rot6d, const float* bone_len, const float* grad_
   float* part = static_cast<float*>(workspace);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<(unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(rot6d, bone_len, grad_poses, grad_rot6d, part, grad_root,
+    launch_k(kernel, (unsigned)ctas, kBwdWarps * 32, smem, (cudaStream_t)stream, rot6d, bone_len, grad_poses, grad_rot6d, part, grad_root,
                                                                          (uint32_t)n_poses, (uint32_t)(n_hyp * n_frames), bulk_ok);
   };
   if (rot_rep_dim == 6) launch(decoder_bwd_kernel<6>); else launch(decoder_bwd_kernel<4>);
   MP_CHECK(check_launch("decoder_bwd_kernel"));
   const int64_t n_out = n_clips * kBones;
-  bone_grad_reduce_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream>>>(part, grad_bone_len, (uint32_t)n_clips,
+  launch_k(bone_grad_reduce_kernel, (unsigned)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream, part, grad_bone_len, (uint32_t)n_clips,
                                                                                            (uint32_t)(n_hyp * n_frames));
   return check_launch("bone_grad_reduce_kernel");
 }
@@ -715,7 +725,7 @@ int mp_softmax_hyp_fwd(const float* logits, float* scores, int64_t n_clips, int6
   if (n <= 0) return MP_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  softmax_hyp_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, scores, (uint32_t)n_clips, (uint32_t)n_hyp,
+  launch_k(softmax_hyp_fwd_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, logits, scores, (uint32_t)n_clips, (uint32_t)n_hyp,
                                                                             (uint32_t)n_frames);
   return check_launch("softmax_hyp_fwd_kernel");
 }
@@ -729,7 +739,7 @@ int mp_softmax_hyp_bwd(const float* scores, const float* grad_scores, float* gra
   if (n <= 0) return MP_OK;
   int64_t blocks = (n + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  softmax_hyp_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, grad_scores, grad_logits, (uint32_t)n_clips,
+  launch_k(softmax_hyp_bwd_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, scores, grad_scores, grad_logits, (uint32_t)n_clips,
                                                                             (uint32_t)n_hyp, (uint32_t)n_frames);
   return check_launch("softmax_hyp_bwd_kernel");
 }

@@ -63,6 +63,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   constexpr int kBoxes = BN / kBoxCols;
   static_assert(kBoxes % 2 == 0, "boxes alternate between the two epilogue groups");
 
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -114,6 +115,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // the preceding kernel has completed: operands may be read, outputs written
 
   if (warp == 0) {
     if (lane == 0) {
@@ -459,7 +461,7 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMa
   }
   const int items = tiles * splits;
   const int grid = items < sm_count() ? items : sm_count();
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, tr, bias, M, N, K, splits);
+  launch_k(kernel, grid, kGemmThreads, Cfg::kSmemBytes, stream, ta, tw, ty, tr, bias, M, N, K, splits);
   return check_launch("linear_kernel");
 }
 
@@ -496,7 +498,7 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
   const int splits = (k_blocks + k_per - 1) / k_per;
   const int items = tiles * splits;
   const int grid = items < sm_count() ? items : sm_count();
-  kernel<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, ty, ty, nullptr, n_out, k_in, tokens_pad, splits);
+  launch_k(kernel, grid, kGemmThreads, Cfg::kSmemBytes, stream, ta, tw, ty, ty, (const float*)nullptr, n_out, k_in, tokens_pad, splits);
   return check_launch("linear_kernel (wgrad)");
 }
 

@@ -92,6 +92,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   constexpr int BN = 256;
   constexpr int kBoxes = 4;                              // 64-column 16-bit boxes per tile
 
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -123,6 +124,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // the preceding kernel has completed: operands may be read, outputs written
 
   if (warp == 0) {
     if (lane == 0) {
@@ -285,6 +287,7 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   constexpr int BN = 256;
   constexpr int kBoxes = 4;
 
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
@@ -335,6 +338,7 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // the preceding kernel has completed: operands may be read, outputs written
 
   if (warp == 0) {
     if (lane == 0) {
@@ -530,6 +534,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   constexpr int kN = 512;
   constexpr int kGS = kLnSlots / 2;                        // slots per warp group
 
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();             // 128-byte-swizzle tiles need the 1024-byte alignment the declaration asks for
   uint8_t* stage_base = smem;
@@ -564,6 +569,7 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // the preceding kernel has completed: operands may be read, outputs written
 
   if (warp == 0) {
     if (lane == 0) {
@@ -898,6 +904,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_r,
                         const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_p,
                         LnArgs args, int M, int K) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* stage_base = smem;
@@ -953,6 +960,7 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // the preceding kernel has completed: operands may be read, outputs written
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1298,7 +1306,7 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
     const int grid = pair_grid((M + 255) / 256);
     auto launch_as = [&](auto kernel, int smem_bytes) -> int {
       MP_CHECK(set_smem(kernel, smem_bytes));
-      kernel<<<grid, kThreads, smem_bytes, stream>>>(ta, tw, ty, bias, M, N);
+      launch_k(kernel, grid, kThreads, smem_bytes, stream, ta, tw, ty, bias, M, N);
       return check_launch("pair_linear_as_kernel");
     };
     const bool gelu = epilogue == MP_EPI_GELU;
@@ -1314,7 +1322,7 @@ int pair_linear(const void* A, const void* W, const float* bias, void* Y, int M,
   const int grid = pair_grid(tiles);
   auto launch = [&](auto kernel) -> int {
     MP_CHECK(set_smem(kernel, kPairLinearSmem));
-    kernel<<<grid, kThreads, kPairLinearSmem, stream>>>(ta, tw, ty, ty2, bias, M, N, K);
+    launch_k(kernel, grid, kThreads, kPairLinearSmem, stream, ta, tw, ty, ty2, bias, M, N, K);
     return check_launch("pair_linear_kernel");
   };
   if (Y2) return bf ? launch(pair_linear_kernel<kEpiGelu2, Bf16>) : launch(pair_linear_kernel<kEpiGelu2, Fp16>);
@@ -1368,7 +1376,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   static const int cfg = getenv("MANIPOSE_LN_CFG") ? atoi(getenv("MANIPOSE_LN_CFG")) : 0;
   auto launch = [&](auto kernel, int smem_bytes) -> int {
     MP_CHECK(set_smem(kernel, smem_bytes));
-    kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta, tw, tr, tx, th, tp, args, (int)M, (int)K);
+    launch_k(kernel, grid, kThreads, smem_bytes, (cudaStream_t)stream, ta, tw, tr, tx, th, tp, args, (int)M, (int)K);
     return check_launch("pair_linear_ln_kernel");
   };
   const bool bf = dtype == MP_DTYPE_BF16;
@@ -1396,7 +1404,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
     const int grid64 = pair_grid((int)((M + 127) / 128));
     auto launch64 = [&](auto kernel, int smem_bytes) -> int {
       MP_CHECK(set_smem(kernel, smem_bytes));
-      kernel<<<grid64, kThreads, smem_bytes, (cudaStream_t)stream>>>(ta6, tw, tr6, tx6, th6, tp6, args, (int)M, (int)K);
+      launch_k(kernel, grid64, kThreads, smem_bytes, (cudaStream_t)stream, ta6, tw, tr6, tx6, th6, tp6, args, (int)M, (int)K);
       return check_launch("pair_linear_ln64_kernel");
     };
     if (cfg == 5)

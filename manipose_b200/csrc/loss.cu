@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1)
 loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, const float* __restrict__ y,
                 const float* __restrict__ weights, LossDims d, float* __restrict__ wta_val, int64_t* __restrict__ wta_idx,
                 float* __restrict__ per_hyp, double* __restrict__ partials) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpStage<kFwdBufs> st;
@@ -269,6 +271,8 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
 
 __global__ void loss_finalize_kernel(const double* __restrict__ partials, int n_partials, LossDims d, int squared, float beta,
                                      float vel_w, float smooth_w, float* __restrict__ terms) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double a[4] = {0, 0, 0, 0};
@@ -312,6 +316,8 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
                 const float* __restrict__ weights, const int64_t* __restrict__ wta_idx, LossDims d, float beta, float vel_w,
                 float smooth_w, const float* __restrict__ grad_terms, const float* __restrict__ grad_wta_val,
                 float* __restrict__ grad_hyp, float* __restrict__ grad_scores) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpStage<kBwdBufs> st;   // buf[0]: y, buf[1], buf[2]: hypotheses
@@ -448,6 +454,8 @@ __device__ __forceinline__ void aggregate_weighted_body(const float* __restrict_
 }
 __global__ void aggregate_weighted_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out,
                                           uint32_t B, uint32_t K, uint32_t T) {
+  pdl_launch_dependents();
+  pdl_wait();
   if ((uint64_t)B * T * kF < (1ull << 32))
     aggregate_weighted_body<uint32_t>(hyp, scores, out, B, K, T);
   else
@@ -465,6 +473,8 @@ __host__ __device__ constexpr int flip_joint(int j) {
 template <bool kBestScore>
 __global__ void aggregate_tta_kernel(const float* __restrict__ hyp, const float* __restrict__ scores, float* __restrict__ out, uint32_t B,
                                      uint32_t K, uint32_t T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n = (size_t)B * T * kF;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t bt = i / kF;
@@ -520,6 +530,8 @@ __device__ __forceinline__ int argmax_score(const float* __restrict__ sp, uint32
 }
 
 __global__ void argmax_score_kernel(const float* __restrict__ scores, int64_t* __restrict__ idx, uint32_t B, uint32_t K, uint32_t T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t n = B * T;   // check_dims: B T < 2^31
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t b = i / T, t = i - b * T;
@@ -540,6 +552,8 @@ __device__ __forceinline__ void gather_hyp_body(const float* __restrict__ hyp, c
 }
 __global__ void gather_hyp_kernel(const float* __restrict__ hyp, const int64_t* __restrict__ idx, float* __restrict__ out, uint32_t B,
                                   uint32_t K, uint32_t T) {
+  pdl_launch_dependents();
+  pdl_wait();
   if ((uint64_t)B * T * kF < (1ull << 32))
     gather_hyp_body<uint32_t>(hyp, idx, out, B, K, T);
   else
@@ -556,6 +570,8 @@ __device__ __forceinline__ double point_dist(float g0, float g1, float g2, float
 template <bool kVec>
 __global__ void mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ gt, size_t n_points,
                                      double* __restrict__ partials) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[8];
   double acc = 0;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -585,6 +601,8 @@ __global__ void mpjpe_partial_kernel(const float* __restrict__ pred, const float
 }
 // one warp, fixed order: lane l adds partials l, l+32, ..., then a butterfly
 __global__ void mpjpe_finalize_kernel(const double* __restrict__ partials, int n, double n_points, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   double s = 0;
   for (int i = threadIdx.x; i < n; i += 32) s += partials[i];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -631,7 +649,7 @@ int mp_wta_fwd(const float* hyp, const float* y, const float* joint_weights, int
   const int grid = loss_grid(B, T, kTileFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kFwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
+    launch_k(kernel, grid, kFwdWarps * 32, smem, (cudaStream_t)stream, hyp, nullptr, y, joint_weights, d, wta_val, wta_idx, per_hyp, nullptr);
   };
   if (squared)
     launch(loss_fwd_kernel<true, false>);
@@ -658,14 +676,14 @@ int mp_loss_fwd(const float* hyp, const float* scores, const float* y, const flo
   double* partials = reinterpret_cast<double*>(workspace);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kFwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, d, wta_val, wta_idx, nullptr, partials);
+    launch_k(kernel, grid, kFwdWarps * 32, smem, (cudaStream_t)stream, hyp, scores, y, joint_weights, d, wta_val, wta_idx, nullptr, partials);
   };
   if (squared)
     launch(loss_fwd_kernel<true, true>);
   else
     launch(loss_fwd_kernel<false, true>);
   MP_CHECK(check_launch("loss_fwd_kernel"));
-  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid * kFwdWarps, d, squared, beta, vel_w, smooth_w, terms);
+  launch_k(loss_finalize_kernel, 1, 256, 0, (cudaStream_t)stream, partials, grid * kFwdWarps, d, squared, beta, vel_w, smooth_w, terms);
   return check_launch("loss_finalize_kernel");
 }
 
@@ -683,7 +701,7 @@ int mp_loss_bwd(const float* hyp, const float* scores, const float* y, const flo
   const int grid = loss_grid(B, T, kBwdFrames);
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kBwdWarps * 32, smem, (cudaStream_t)stream>>>(hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
+    launch_k(kernel, grid, kBwdWarps * 32, smem, (cudaStream_t)stream, hyp, scores, y, joint_weights, wta_idx, d, beta, vel_w, smooth_w,
                                                                    grad_terms, grad_wta_val, grad_hyp, grad_scores);
   };
   if (squared)
@@ -704,14 +722,14 @@ int mp_aggregate(const float* hyp, const float* scores, const float* y, int mode
   const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 8 ? (n + 255) / 256 : (size_t)sm_count() * 8);
   if (mode == MP_AGG_WEIGHTED_AVE) {
     MP_REQUIRE(scores != nullptr, MP_EINVAL, "Scores required to compute weighted hypothesis average.");
-    aggregate_weighted_kernel<<<blocks, 256, 0, s>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    launch_k(aggregate_weighted_kernel, blocks, 256, 0, s, hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
     return check_launch("aggregate_weighted_kernel");
   }
   MP_REQUIRE(out_idx != nullptr, MP_EINVAL, "mp_aggregate: out_idx required for best_score / oracle");
   if (mode == MP_AGG_BEST_SCORE) {
     MP_REQUIRE(scores != nullptr, MP_EINVAL, "Scores required to compute hypothesis with best confidence.");
     const int b2 = (int)(((size_t)B * T + 255) / 256);
-    argmax_score_kernel<<<b2 < sm_count() * 8 ? b2 : sm_count() * 8, 256, 0, s>>>(scores, out_idx, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    launch_k(argmax_score_kernel, b2 < sm_count() * 8 ? b2 : sm_count() * 8, 256, 0, s, scores, out_idx, (uint32_t)B, (uint32_t)K, (uint32_t)T);
     MP_CHECK(check_launch("argmax_score_kernel"));
   } else if (mode == MP_AGG_ORACLE) {
     MP_REQUIRE(y != nullptr && out_val != nullptr, MP_EINVAL, "Ground-truth required to compute best hypothesis.");
@@ -719,7 +737,7 @@ int mp_aggregate(const float* hyp, const float* scores, const float* y, int mode
   } else {
     return fail(MP_EINVAL, "Only best_score and weighted_ave modes are implemented.Got %d.", mode);
   }
-  gather_hyp_kernel<<<blocks, 256, 0, s>>>(hyp, out_idx, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+  launch_k(gather_hyp_kernel, blocks, 256, 0, s, hyp, out_idx, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
   return check_launch("gather_hyp_kernel");
 }
 
@@ -734,9 +752,9 @@ int mp_aggregate_tta(const float* hyp, const float* scores, int mode, float* out
   const size_t n = (size_t)B * T * kF;
   const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 8 ? (n + 255) / 256 : (size_t)sm_count() * 8);
   if (mode == MP_AGG_WEIGHTED_AVE)
-    aggregate_tta_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    launch_k(aggregate_tta_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
   else
-    aggregate_tta_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
+    launch_k(aggregate_tta_kernel<true>, blocks, 256, 0, (cudaStream_t)stream, hyp, scores, out_pose, (uint32_t)B, (uint32_t)K, (uint32_t)T);
   return check_launch("aggregate_tta_kernel");
 }
 
@@ -754,12 +772,12 @@ int mp_mpjpe(const float* pred, const float* gt, int64_t n_points, float* out, v
   if (aligned16(pred) && aligned16(gt)) {
     blocks = (int)((n_points / 4 + 255) / 256);
     blocks = blocks < 1 ? 1 : (blocks > kMpjpeBlocks ? kMpjpeBlocks : blocks);
-    mpjpe_partial_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+    launch_k(mpjpe_partial_kernel<true>, blocks, 256, 0, (cudaStream_t)stream, pred, gt, (size_t)n_points, partials);
   } else {
-    mpjpe_partial_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, gt, (size_t)n_points, partials);
+    launch_k(mpjpe_partial_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, pred, gt, (size_t)n_points, partials);
   }
   MP_CHECK(check_launch("mpjpe_partial_kernel"));
-  mpjpe_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partials, blocks, (double)n_points, out);
+  launch_k(mpjpe_finalize_kernel, 1, 32, 0, (cudaStream_t)stream, partials, blocks, (double)n_points, out);
   return check_launch("mpjpe_finalize_kernel");
 }
 

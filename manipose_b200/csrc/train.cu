@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(kTokWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* dy,
                      const float* dres, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* dx16,
                      const float* __restrict__ rowscale, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<C>;
   __shared__ float acc[2][C];
   const int lane = threadIdx.x & 31;
@@ -120,6 +122,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 
 template <typename D, bool kBwd>
 __global__ void __launch_bounds__(256) gelu_kernel(const uint4* __restrict__ u, const uint4* __restrict__ da, uint4* __restrict__ out, int64_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 a = u[i];
     uint4 g = make_uint4(0, 0, 0, 0);
@@ -320,6 +324,8 @@ template <int HD, typename D>
 __global__ void __launch_bounds__(kAttnBwdMmaWarps * 32)
 attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
                          uint16_t* __restrict__ dqkv, int L, int Lp, int n_heads, int C, int n_tok, int n_frames, int temporal) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LD = HD * 2 + 16;
   constexpr int CH = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_b[];
@@ -439,6 +445,8 @@ attention_bwd_mma_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __res
 template <typename D>
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, float* __restrict__ colsum,
                                                           int64_t M, int64_t C, int64_t Mpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ uint16_t tile[64][66];
   __shared__ float part[4][64];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -469,6 +477,8 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __rest
 // 64 x 64 tiles.
 template <typename D>
 __global__ void __launch_bounds__(256) refresh_shadows_kernel(const int64_t* __restrict__ table) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ uint16_t tile[64][66];
   const int64_t* e = table + (int64_t)blockIdx.y * 5;
   const float* src = reinterpret_cast<const float*>(e[0]);
@@ -505,6 +515,8 @@ __global__ void __launch_bounds__(256) refresh_shadows_kernel(const int64_t* __r
 template <typename D>
 __global__ void __launch_bounds__(256) colsum16_kernel(const uint4* __restrict__ src, float* __restrict__ colsum, int64_t M, int C8,
                                                        int64_t rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32][65];
   const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
   const int c8 = blockIdx.x * 8 + cx;
@@ -538,6 +550,8 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const uint4* __restrict__
 // -------------------------------------------------------------------------------------------------- grouped row sums (pos-embed gradients)
 // out[(m / div) % mod, c] += x[m, c]: Spatial_pos_embed (div 1, mod tokens), Temporal_pos_embed (div tokens, mod frames)
 __global__ void group_rowsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n_outer, int C, int64_t div, int64_t mod) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = threadIdx.x;
   const int64_t gidx = blockIdx.x;
   float acc = 0.f;
@@ -553,6 +567,8 @@ __global__ void group_rowsum_kernel(const float* __restrict__ x, float* __restri
 template <int KIN>
 __global__ void __launch_bounds__(128) small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ in, float* __restrict__ dW,
                                                           float* __restrict__ db, int64_t R, int O) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int o = blockIdx.x * 128 + threadIdx.x;
   float acc[KIN], ab = 0.f;
 #pragma unroll
@@ -575,6 +591,8 @@ template <int C, typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 residual_rowscale_kernel(const float* __restrict__ x, const uint16_t* __restrict__ y, const float* __restrict__ s, float* __restrict__ out,
                          int64_t n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<C>;
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * kTokWarps;
@@ -591,6 +609,8 @@ residual_rowscale_kernel(const float* __restrict__ x, const uint16_t* __restrict
 template <int C, typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 cast_rowscale_kernel(const float* __restrict__ g, const float* __restrict__ s, uint16_t* __restrict__ out, int64_t n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   using R = Row<C>;
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * kTokWarps;
@@ -611,6 +631,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
                                                    float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev,
                                                    const float* __restrict__ lr_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (lr_dev) lr = *lr_dev;      // the learning rate of a captured step lives on the device too (schedulers change it between replays)
   if (step_dev) {
     const double t = (double)(*step_dev + 1);
@@ -629,7 +651,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-__global__ void adam_bump_kernel(int64_t* step_dev) { *step_dev += 1; }
+__global__ void adam_bump_kernel(int64_t* step_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_dev += 1;
+}
 
 int stream_grid(int64_t n, int per_cta) {
   int64_t ctas = (n + per_cta - 1) / per_cta;
@@ -658,7 +684,7 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   int grid = token_grid(n_tokens);
   if (dgamma && grid > 2 * sm_count()) grid = 2 * sm_count();
   auto launch = [&](auto kernel) {
-    kernel<<<grid, kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, n_tokens);
+    launch_k(kernel, grid, kTokWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
   if (C == 512) {
@@ -682,7 +708,7 @@ static int gelu_launch(const void* u, const void* da, void* out, int64_t n, int 
   if (n == 0) return MP_OK;
   const int64_t n8 = n / 8;
   const int grid = stream_grid(n8, 256);
-  auto launch = [&](auto kernel) { kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)u, (const uint4*)da, (uint4*)out, n8); };
+  auto launch = [&](auto kernel) { launch_k(kernel, grid, 256, 0, (cudaStream_t)stream, (const uint4*)u, (const uint4*)da, (uint4*)out, n8); };
   if (dtype == MP_DTYPE_BF16) {
     if (bwd) launch(gelu_kernel<Bf16, true>); else launch(gelu_kernel<Bf16, false>);
   } else {
@@ -727,7 +753,7 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
     const size_t smem = (size_t)5 * Lp * LD + (size_t)2 * Lp * sizeof(float) + (size_t)n_warps * 16 * LD;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_mma_kernel): %s", cudaGetErrorString(e));
-    kernel<<<(unsigned)n_items, n_warps * 32, smem, (cudaStream_t)stream>>>((const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout,
+    launch_k(kernel, (unsigned)n_items, n_warps * 32, smem, (cudaStream_t)stream, (const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout,
                                                                            (uint16_t*)dqkv, (int)L, Lp, n_heads, C, n_tok, (int)n_frames, temporal);
     return check_launch("attention_bwd_mma_kernel");
   };
@@ -744,9 +770,9 @@ int mp_transpose16(const void* src, void* dst, float* colsum, int64_t M, int64_t
   if (Mpad == 0) return MP_OK;
   const dim3 grid((unsigned)(Mpad / 64), (unsigned)(C / 64));
   if (dtype == MP_DTYPE_BF16)
-    transpose16_kernel<Bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, (uint16_t*)dst, colsum, M, C, Mpad);
+    launch_k(transpose16_kernel<Bf16>, grid, 256, 0, (cudaStream_t)stream, (const uint16_t*)src, (uint16_t*)dst, colsum, M, C, Mpad);
   else
-    transpose16_kernel<Fp16><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, (uint16_t*)dst, colsum, M, C, Mpad);
+    launch_k(transpose16_kernel<Fp16>, grid, 256, 0, (cudaStream_t)stream, (const uint16_t*)src, (uint16_t*)dst, colsum, M, C, Mpad);
   return check_launch("transpose16_kernel");
 }
 
@@ -758,9 +784,9 @@ int mp_refresh_shadows(const int64_t* table, int n_weights, int max_tiles, int d
   if (n_weights == 0) return MP_OK;
   const int gx = max_tiles < 64 ? max_tiles : 64;
   if (dtype == MP_DTYPE_BF16)
-    refresh_shadows_kernel<Bf16><<<dim3(gx, n_weights), 256, 0, (cudaStream_t)stream>>>(table);
+    launch_k(refresh_shadows_kernel<Bf16>, dim3(gx, n_weights), 256, 0, (cudaStream_t)stream, table);
   else
-    refresh_shadows_kernel<Fp16><<<dim3(gx, n_weights), 256, 0, (cudaStream_t)stream>>>(table);
+    launch_k(refresh_shadows_kernel<Fp16>, dim3(gx, n_weights), 256, 0, (cudaStream_t)stream, table);
   return check_launch("refresh_shadows_kernel");
 }
 
@@ -779,9 +805,9 @@ int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype,
   const int64_t rows_per_cta = (M + gy - 1) / gy;
   gy = (M + rows_per_cta - 1) / rows_per_cta;
   if (dtype == MP_DTYPE_BF16)
-    colsum16_kernel<Bf16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, colsum, M, c8, rows_per_cta);
+    launch_k(colsum16_kernel<Bf16>, dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream, (const uint4*)src, colsum, M, c8, rows_per_cta);
   else
-    colsum16_kernel<Fp16><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, colsum, M, c8, rows_per_cta);
+    launch_k(colsum16_kernel<Fp16>, dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream, (const uint4*)src, colsum, M, c8, rows_per_cta);
   return check_launch("colsum16_kernel");
 }
 
@@ -794,7 +820,7 @@ int mp_group_rowsum(const float* x, float* out, int64_t n_rows, int C, int64_t d
   const int64_t n_outer = n_rows / (div * mod);
   int64_t splits = (int64_t)sm_count() * 4 / mod + 1;
   if (splits > n_outer) splits = n_outer;
-  group_rowsum_kernel<<<dim3((unsigned)mod, (unsigned)splits), C, 0, (cudaStream_t)stream>>>(x, out, n_outer, C, div, mod);
+  launch_k(group_rowsum_kernel, dim3((unsigned)mod, (unsigned)splits), C, 0, (cudaStream_t)stream, x, out, n_outer, C, div, mod);
   return check_launch("group_rowsum_kernel");
 }
 
@@ -809,10 +835,10 @@ int mp_small_wgrad(const float* dy, const float* in, float* dW, float* db, int64
   const dim3 grid((unsigned)(n_out / 128), (unsigned)splits);
   cudaStream_t s = (cudaStream_t)stream;
   switch (n_in) {
-    case 2: small_wgrad_kernel<2><<<grid, 128, 0, s>>>(dy, in, dW, db, n_rows, n_out); break;
-    case 3: small_wgrad_kernel<3><<<grid, 128, 0, s>>>(dy, in, dW, db, n_rows, n_out); break;
-    case 34: small_wgrad_kernel<34><<<grid, 128, 0, s>>>(dy, in, dW, db, n_rows, n_out); break;
-    default: small_wgrad_kernel<51><<<grid, 128, 0, s>>>(dy, in, dW, db, n_rows, n_out); break;
+    case 2: launch_k(small_wgrad_kernel<2>, grid, 128, 0, s, dy, in, dW, db, n_rows, n_out); break;
+    case 3: launch_k(small_wgrad_kernel<3>, grid, 128, 0, s, dy, in, dW, db, n_rows, n_out); break;
+    case 34: launch_k(small_wgrad_kernel<34>, grid, 128, 0, s, dy, in, dW, db, n_rows, n_out); break;
+    default: launch_k(small_wgrad_kernel<51>, grid, 128, 0, s, dy, in, dW, db, n_rows, n_out); break;
   }
   return check_launch("small_wgrad_kernel");
 }
@@ -826,7 +852,7 @@ int mp_residual_rowscale(const float* x, const void* y, const float* s, float* o
   MP_REQUIRE(aligned16(x) && aligned16(y) && aligned16(out), MP_EALIGN, "mp_residual_rowscale: rows must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
   auto launch = [&](auto kernel) {
-    kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(x, (const uint16_t*)y, s, out, n_tokens);
+    launch_k(kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, x, (const uint16_t*)y, s, out, n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
   if (C == 512) {
@@ -845,7 +871,7 @@ int mp_cast_rowscale(const float* g, const float* s, void* out, int64_t n_tokens
   MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_cast_rowscale: unknown dtype %d", dtype);
   MP_REQUIRE(aligned16(g) && aligned16(out), MP_EALIGN, "mp_cast_rowscale: rows must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
-  auto launch = [&](auto kernel) { kernel<<<token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream>>>(g, s, (uint16_t*)out, n_tokens); };
+  auto launch = [&](auto kernel) { launch_k(kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, g, s, (uint16_t*)out, n_tokens); };
   const bool bf = dtype == MP_DTYPE_BF16;
   if (C == 512) {
     if (bf) launch(cast_rowscale_kernel<512, Bf16>); else launch(cast_rowscale_kernel<512, Fp16>);
@@ -867,11 +893,11 @@ int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
     bc1 = 1.0f - (float)pow((double)beta1, (double)step);
     bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   }
-  adam_kernel<<<stream_grid(n, 1024), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+  launch_k(adam_kernel, stream_grid(n, 1024), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                                        bc1, bc2_sqrt, grad_scale, step_dev, lr_dev);
   MP_CHECK(check_launch("adam_kernel"));
   if (step_dev) {
-    adam_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    launch_k(adam_bump_kernel, 1, 1, 0, (cudaStream_t)stream, step_dev);
     return check_launch("adam_bump_kernel");
   }
   return MP_OK;
