@@ -287,17 +287,23 @@ int mp_gather_windows(const float* frames2d, const float* frames3d, const int64_
 
 /* LayerNorm backward: dx = LN'(x; gamma, eps)(dy) [+ dres]; dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics; both NULL to skip).
  * dy is fp32 (dy_is_16bit = 0) or `dtype` 16-bit; gamma NULL = no affine; dx may alias dres.  dx16 (may be NULL): also writes
- * 16-bit(rowscale[token] * dx) — the operand of the next backward GEMM (rowscale NULL = 1).  C in {512, 128}. */
+ * 16-bit(rowscale[token] * dx) — the operand of the next backward GEMM (rowscale NULL = 1) — and, with dx16_colsum [C] (may be NULL),
+ * adds its column sums there (the bias gradient of the Linear whose output gradient dx16 is).  C in {512, 128}. */
 int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_is_16bit, const float* dres, float* dx,
-                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, int64_t n_tokens, int C, int dtype, mp_stream_t stream);
+                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, float* dx16_colsum, int64_t n_tokens, int C,
+                     int dtype, mp_stream_t stream);
 /* exact-erf GELU on a 16-bit pre-activation (training keeps the pre-activation): a = gelu(u); du = da * gelu'(u).  n % 8 == 0. */
 int mp_gelu_fwd(const void* u, void* a, int64_t n, int dtype, mp_stream_t stream);
 int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, mp_stream_t stream);
-/* Attention backward (Attention.forward, mix_ste.py:257-275): qkv [tokens,3C], o / dout [tokens,C] -> dqkv [tokens,3C], all 16-bit,
- * same token layout and modes as mp_attention; mma.sync tensor cores, P is recomputed, nothing of size L x L is stored.  head_dim 64 or
- * 16, L <= 256. */
-int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C,
-                     int n_heads, int mode, int dtype, mp_stream_t stream);
+/* the same over an [M, C] matrix, and colsum[C] (fp32) += column sums of du (the fc1 bias gradient) in the same pass.  C % 8 == 0. */
+int mp_gelu_bwd_colsum(const void* u, const void* da, void* du, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream);
+/* Attention backward (Attention.forward, mix_ste.py:257-275): qkv [tokens,3C], dout [tokens,C] -> dqkv [tokens,3C], all 16-bit, same
+ * token layout and modes as mp_attention; P is recomputed, nothing of size L x L is stored.  head_dim 64 with spatial sequences of <= 32
+ * tokens or temporal tracks of <= 128 frames: tcgen05 kernel over block-diagonal 128-row tiles (S and dP in tensor memory; o is not read,
+ * D_i = sum_j P_ij dP_ij).  Otherwise (head_dim 16, L <= 256): mma.sync kernel, one CTA per (sequence, head), reads o.
+ * dqkv_colsum [3C] (may be NULL): += column sums of dqkv (the qkv bias gradient). */
+int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, float* dqkv_colsum, int64_t n_clips, int64_t n_frames,
+                     int n_tok, int C, int n_heads, int mode, int dtype, mp_stream_t stream);
 /* Weight gradient dW[n_out, k_in] (fp32) += dY[tokens, n_out]^T X[tokens, k_in] (16-bit), both operands read in place as MN-major
  * UMMA operands (no transposed copies); the token contraction is split over the SMs, partial tiles added with TMA reduce stores.
  * n_out % 128 == 0, k_in % 128 == 0. */

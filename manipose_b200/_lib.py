@@ -63,10 +63,11 @@ SIGNATURES = {
     "mp_pose_consistency": (I, [P, I64, I64, P, P, P, P, P, P, c_size_t, P]),
     "mp_point_errors_workspace_bytes": (c_size_t, [I64, I]),
     "mp_point_errors": (I, [P, P, I64, I, I, F, P, P, P, c_size_t, P]),
-    "mp_layernorm_bwd": (I, [P, P, F, P, I, P, P, P, P, P, P, I64, I, I, P]),
+    "mp_layernorm_bwd": (I, [P, P, F, P, I, P, P, P, P, P, P, P, I64, I, I, P]),
     "mp_gelu_fwd": (I, [P, P, I64, I, P]),
     "mp_gelu_bwd": (I, [P, P, P, I64, I, P]),
-    "mp_attention_bwd": (I, [P, P, P, P, I64, I64, I, I, I, I, I, P]),
+    "mp_gelu_bwd_colsum": (I, [P, P, P, P, I64, I64, I, P]),
+    "mp_attention_bwd": (I, [P, P, P, P, P, I64, I64, I, I, I, I, I, P]),
     "mp_wgrad": (I, [P, P, P, I64, I64, I64, I, P]),
     "mp_colsum16": (I, [P, P, I64, I64, I, P]),
     "mp_refresh_shadows": (I, [P, I, I, I, P]),

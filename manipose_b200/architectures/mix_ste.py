@@ -537,27 +537,31 @@ class MixSTE(nn.Module):
                 # x3 = post-norm(x2) (+ Temporal_pos_embed after the first block); dx currently is d/dx3
                 if rec["pos"]:
                     T.group_rowsum(dx, g(self.Temporal_pos_embed), n_tok, n_frames)
+                # (the bias gradients are column sums of the 16-bit output gradients: each is taken by the kernel that writes that matrix)
                 T.layernorm_bwd(rec["x2"], post.weight, post.eps, dx, None, dx, g(post.weight), g(post.bias), dt, dx16=dy16,
-                                rowscale=rec["s2"])
+                                rowscale=rec["s2"], dx16_colsum=g(blk.mlp.fc2.bias))
+                fc2_db = None
             else:
                 T.cast_rowscale(dx, rec["s2"], dy16)
+                fc2_db = g(blk.mlp.fc2.bias)
             # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1))))); dy16 = 16-bit(s2 * dx)
-            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), g(blk.mlp.fc2.bias))
+            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), fc2_db)
             da = flat[:n_tokens * hidden].view(n_tokens, hidden)
             T.dgrad(dy16, w_t[wi + 3], da)
-            T.gelu_bwd(rec["u"], da, da)
-            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), g(blk.mlp.fc1.bias))
+            T.gelu_bwd(rec["u"], da, da, colsum=g(blk.mlp.fc1.bias))
+            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), None)
             T.dgrad(da, w_t[wi + 2], dy16)
             # norm2 backward reads dy16 (= d h2) and rewrites it with 16-bit(s1 * dx1), the operand of the attention branch
             T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt, dx16=dy16,
-                            rowscale=rec["s1"])
+                            rowscale=rec["s1"], dx16_colsum=g(blk.attn.proj.bias))
             # ---- attention branch: x1 = x0 + s1 * proj(attention(qkv(norm1(x0))))
-            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), g(blk.attn.proj.bias))
+            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), None)
             do = b16(c)
             T.dgrad(dy16, w_t[wi + 1], do)
             dqkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
-            T.attention_bwd(rec["qkv"], rec["o"], do, dqkv, n_clips, n_frames, n_tok, c, heads, mode)
-            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), g(blk.attn.qkv.bias))
+            qkv_db = g(blk.attn.qkv.bias) if blk.attn.qkv.bias is not None else None
+            T.attention_bwd(rec["qkv"], rec["o"], do, dqkv, n_clips, n_frames, n_tok, c, heads, mode, colsum=qkv_db)
+            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), None)
             T.dgrad(dqkv, w_t[wi + 0], dy16)
             T.layernorm_bwd(rec["x0"], blk.norm1.weight, blk.norm1.eps, dy16, dx, dx, g(blk.norm1.weight), g(blk.norm1.bias), dt)
             rec.clear()

@@ -1244,7 +1244,7 @@ constexpr int kBwdTcSmem = 7 * 16384 + 64;
 template <typename D, bool kTracks>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv,
-                   int n_rows, int n_tok, int C, int n_heads, int G, int tiles_per_clip) {
+                   float* __restrict__ colsum, int n_rows, int n_tok, int C, int n_heads, int G, int tiles_per_clip) {
   pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -1507,8 +1507,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         ptx::tma_store_3d(&tm_dqkv, sdo, 2 * C + head * 64, row0, clip);
       }
       ptx::bulk_commit();
-      ptx::bulk_wait_read<0>();
     }
+    if (colsum != nullptr && threadIdx.x < 96) {
+      // qkv bias gradient: column sums of the three staged tiles (rows that are not stored are exactly zero), one atomic per column
+      const int m = threadIdx.x >> 5, cp = threadIdx.x & 31;                 // tile (dQ | dK | dV), column pair
+      const uint8_t* tb = m == 0 ? sq : (m == 1 ? sk : sdo);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(tb + r * 128 + ((((uint32_t)(cp >> 2)) ^ (uint32_t)(r & 7)) << 4) + (cp & 3) * 4);
+        const float2 f = D::unpack2(v);
+        s0 += f.x;
+        s1 += f.y;
+      }
+      atomicAdd(colsum + m * C + head * 64 + 2 * cp, s0);
+      atomicAdd(colsum + m * C + head * 64 + 2 * cp + 1, s1);
+    }
+    if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1521,8 +1536,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 }  // namespace
 
 // mp_attention_bwd (train.cu) for head_dim 64: spatial sequences of <= 32 tokens, temporal tracks of <= 128 frames.
-int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads, int temporal,
-                     int dtype, cudaStream_t s) {
+int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, float* dqkv_colsum, int64_t n_clips, int64_t n_frames, int n_tok, int C,
+                     int n_heads, int temporal, int dtype, cudaStream_t s) {
   const bool bf = dtype == MP_DTYPE_BF16;
   CUtensorMap tin, tdo, tdq;
   if (temporal) {
@@ -1534,7 +1549,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_cl
     MP_CHECK(get_tmap_track(&tdq, dqkv, n_clips, n_frames, n_tok, 3 * C, (int)n_frames, dtype, P));
     auto launch = [&](auto kernel) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
-      launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, (int)n_frames, n_tok, C, n_heads, P,
+      launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, dqkv_colsum, (int)n_frames, n_tok, C, n_heads, P,
                                                                                           (int)tiles_per_clip);
     };
     if (bf) launch(attn_bwd_tc_kernel<Bf16, true>); else launch(attn_bwd_tc_kernel<Fp16, true>);
@@ -1549,7 +1564,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_cl
   MP_CHECK(get_tmap_clip_rows(&tdq, dqkv, n_clips, rows_per_clip, 3 * C, G, dtype));
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
-    launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, (int)rows_per_clip, n_tok, C, n_heads, G,
+    launch_k(kernel, (unsigned)(n_clips * tiles_per_clip * n_heads), kTcThreads, kBwdTcSmem, s, tin, tdo, tdq, dqkv_colsum, (int)rows_per_clip, n_tok, C, n_heads, G,
                                                                                         (int)tiles_per_clip);
   };
   if (bf) launch(attn_bwd_tc_kernel<Bf16, false>); else launch(attn_bwd_tc_kernel<Fp16, false>);

@@ -17,31 +17,33 @@
 
 namespace mp {
 
-int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C, int n_heads,
-                     int temporal, int dtype, cudaStream_t s);  // attention.cu
+int attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, float* dqkv_colsum, int64_t n_clips, int64_t n_frames, int n_tok, int C,
+                     int n_heads, int temporal, int dtype, cudaStream_t s);  // attention.cu
 namespace {
 
 // -------------------------------------------------------------------------------------------------- LayerNorm backward
 // y = (x - mean) * rstd * gamma + beta.  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ dres], g = dy * gamma;
 // dgamma += sum dy * xhat, dbeta += sum dy (fp32 atomics, one per CTA and channel).  gamma == NULL: no affine.
+// dx16_colsum (may be NULL): += column sums of the dx16 output = the bias gradient of the Linear whose output gradient dx16 is.
 template <int C, bool kDy16, typename D>
 __global__ void __launch_bounds__(kTokWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* dy,
                      const float* dres, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* dx16,
-                     const float* __restrict__ rowscale, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
+                     const float* __restrict__ rowscale, float* __restrict__ dx16_colsum, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
   pdl_launch_dependents();
   pdl_wait();
   using R = Row<C>;
-  __shared__ float acc[2][C];
+  __shared__ float acc[3][C];
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
   const int64_t stride = (int64_t)gridDim.x * kTokWarps;
-  float g[R::kPer], ag[R::kPer], ab[R::kPer];
+  float g[R::kPer], ag[R::kPer], ab[R::kPer], ac[R::kPer];
 #pragma unroll
   for (int i = 0; i < R::kPer; ++i) {
     g[i] = 1.f;
     ag[i] = 0.f;
     ab[i] = 0.f;
+    ac[i] = 0.f;
   }
   if (gamma) R::load_f32(gamma, lane, g);
   for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
@@ -79,25 +81,35 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     if (dx16) {   // the next backward GEMM's operand: 16-bit copy, scaled by the sample's stochastic-depth factor
       const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
 #pragma unroll
-      for (int i = 0; i < R::kPer; ++i) d[i] *= sc;
+      for (int i = 0; i < R::kPer; ++i) {
+        d[i] *= sc;
+        ac[i] += d[i];
+      }
       R::template store_h<D>(dx16 + tok * C, lane, d);
     }
   }
-  if (dgamma) {
+  if (dgamma || dx16_colsum) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       acc[0][c] = 0.f;
       acc[1][c] = 0.f;
+      acc[2][c] = 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < R::kPer; ++i) {
-      atomicAdd(&acc[0][R::chan(lane, i)], ag[i]);
-      atomicAdd(&acc[1][R::chan(lane, i)], ab[i]);
+      if (dgamma) {
+        atomicAdd(&acc[0][R::chan(lane, i)], ag[i]);
+        atomicAdd(&acc[1][R::chan(lane, i)], ab[i]);
+      }
+      if (dx16_colsum) atomicAdd(&acc[2][R::chan(lane, i)], ac[i]);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(dgamma + c, acc[0][c]);
-      atomicAdd(dbeta + c, acc[1][c]);
+      if (dgamma) {
+        atomicAdd(dgamma + c, acc[0][c]);
+        atomicAdd(dbeta + c, acc[1][c]);
+      }
+      if (dx16_colsum) atomicAdd(dx16_colsum + c, acc[2][c]);
     }
   }
 }
@@ -547,6 +559,53 @@ __global__ void __launch_bounds__(256) colsum16_kernel(const uint4* __restrict__
   }
 }
 
+// du = da * gelu'(u) over a [M, C] matrix AND colsum[C] += column sums of du (the fc1 bias gradient): a CTA owns 256 columns x a slab
+// of rows, a warp reads 512 contiguous bytes of a row, 8 rows in flight per CTA; one atomic per column and CTA.
+template <typename D>
+__global__ void __launch_bounds__(256) gelu_bwd_colsum_kernel(const uint4* __restrict__ u, const uint4* __restrict__ da, uint4* __restrict__ out,
+                                                              float* __restrict__ colsum, int64_t M, int C8, int64_t rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8][257];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c8 = blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto one = [&](int64_t m) {
+    const uint4 a = u[m * C8 + c8], g = da[m * C8 + c8];
+    const uint32_t au[4] = {a.x, a.y, a.z, a.w}, gu[4] = {g.x, g.y, g.z, g.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xv = D::unpack2(au[k]), gv = D::unpack2(gu[k]);
+      r[k] = D::pack2(gv.x * gelu_grad(xv.x), gv.y * gelu_grad(xv.y));
+      const float2 rv = D::unpack2(r[k]);     // sum what the weight-gradient GEMM will read
+      acc[2 * k] += rv.x;
+      acc[2 * k + 1] += rv.y;
+    }
+    out[m * C8 + c8] = make_uint4(r[0], r[1], r[2], r[3]);
+  };
+  if (c8 < C8) {
+    int64_t m = r0 + ry;
+    for (; m + 8 < r1; m += 16) {
+      one(m);
+      one(m + 8);
+    }
+    for (; m < r1; m += 8) one(m);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ry][8 * cx + i] = acc[i];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < 8 * C8) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(colsum + col, t);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------- grouped row sums (pos-embed gradients)
 // out[(m / div) % mod, c] += x[m, c]: Spatial_pos_embed (div 1, mod tokens), Temporal_pos_embed (div tokens, mod frames)
 __global__ void group_rowsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n_outer, int C, int64_t div, int64_t mod) {
@@ -669,7 +728,8 @@ int stream_grid(int64_t n, int per_cta) {
 extern "C" {
 
 int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* dy, int dy_is_16bit, const float* dres, float* dx,
-                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, int64_t n_tokens, int C, int dtype, mp_stream_t stream) {
+                     float* dgamma, float* dbeta, void* dx16, const float* rowscale, float* dx16_colsum, int64_t n_tokens, int C, int dtype,
+                     mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(C == 512 || C == 128, MP_EUNSUPPORTED, "mp_layernorm_bwd: C=%d (built for 512 and 128)", C);
@@ -682,9 +742,11 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   if (n_tokens == 0) return MP_OK;
   // every CTA ends with 2 C atomics on the same dgamma / dbeta words: keep the grid at two CTAs per SM when they are wanted
   int grid = token_grid(n_tokens);
-  if (dgamma && grid > 2 * sm_count()) grid = 2 * sm_count();
+  MP_REQUIRE(dx16_colsum == nullptr || dx16 != nullptr, MP_EINVAL, "mp_layernorm_bwd: dx16_colsum needs dx16");
+  if ((dgamma || dx16_colsum) && grid > 2 * sm_count()) grid = 2 * sm_count();
   auto launch = [&](auto kernel) {
-    launch_k(kernel, grid, kTokWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, n_tokens);
+    launch_k(kernel, grid, kTokWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, dx16_colsum,
+             n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
   if (C == 512) {
@@ -723,8 +785,30 @@ int mp_gelu_bwd(const void* u, const void* da, void* du, int64_t n, int dtype, m
   return gelu_launch(u, da, du, n, dtype, true, stream);
 }
 
-int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, int64_t n_clips, int64_t n_frames, int n_tok, int C,
-                     int n_heads, int mode, int dtype, mp_stream_t stream) {
+int mp_gelu_bwd_colsum(const void* u, const void* da, void* du, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream) {
+  using namespace mp;
+  MP_CHECK(require_sm100());
+  MP_REQUIRE(u && da && du && colsum && M >= 0 && C >= 8 && C % 8 == 0, MP_EINVAL, "mp_gelu_bwd_colsum: bad arguments (C %% 8 == 0)");
+  MP_REQUIRE(dtype == MP_DTYPE_BF16 || dtype == MP_DTYPE_FP16, MP_EINVAL, "mp_gelu_bwd_colsum: unknown dtype %d", dtype);
+  MP_REQUIRE(aligned16(u) && aligned16(da) && aligned16(du), MP_EALIGN, "mp_gelu_bwd_colsum: pointers must be 16-byte aligned");
+  if (M == 0) return MP_OK;
+  const int c8 = (int)(C / 8);
+  const int gx = (c8 + 31) / 32;
+  int64_t gy = (int64_t)sm_count() * 4 / gx + 1;
+  if (gy > (M + 31) / 32) gy = (M + 31) / 32;
+  const int64_t rows_per_cta = (M + gy - 1) / gy;
+  gy = (M + rows_per_cta - 1) / rows_per_cta;
+  if (dtype == MP_DTYPE_BF16)
+    launch_k(gelu_bwd_colsum_kernel<Bf16>, dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream, (const uint4*)u, (const uint4*)da, (uint4*)du, colsum,
+             M, c8, rows_per_cta);
+  else
+    launch_k(gelu_bwd_colsum_kernel<Fp16>, dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream, (const uint4*)u, (const uint4*)da, (uint4*)du, colsum,
+             M, c8, rows_per_cta);
+  return check_launch("gelu_bwd_colsum_kernel");
+}
+
+int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqkv, float* dqkv_colsum, int64_t n_clips, int64_t n_frames, int n_tok,
+                     int C, int n_heads, int mode, int dtype, mp_stream_t stream) {
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(qkv && o && dout && dqkv && n_clips >= 0 && n_frames >= 1 && n_tok >= 1 && n_heads >= 1, MP_EINVAL, "mp_attention_bwd: bad arguments");
@@ -743,7 +827,7 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
   // head_dim 64 and short sequences: the tcgen05 block-diagonal kernel (attention.cu); MANIPOSE_ATTN_BWD_MMA keeps the mma.sync one (A/B)
   static const bool legacy = getenv("MANIPOSE_ATTN_BWD_MMA") != nullptr;
   if (hd == 64 && !legacy && (temporal ? n_frames <= 128 : n_tok <= 32))
-    return attention_bwd_tc(qkv, dout, dqkv, n_clips, n_frames, n_tok, C, n_heads, temporal, dtype, (cudaStream_t)stream);
+    return attention_bwd_tc(qkv, dout, dqkv, dqkv_colsum, n_clips, n_frames, n_tok, C, n_heads, temporal, dtype, (cudaStream_t)stream);
   const bool bf = dtype == MP_DTYPE_BF16;
   const int Lp = ((int)L + 31) & ~31;
   int n_warps = Lp / 16;
@@ -755,7 +839,9 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
     MP_REQUIRE(e == cudaSuccess, MP_ELAUNCH, "cudaFuncSetAttribute(attention_bwd_mma_kernel): %s", cudaGetErrorString(e));
     launch_k(kernel, (unsigned)n_items, n_warps * 32, smem, (cudaStream_t)stream, (const uint16_t*)qkv, (const uint16_t*)o, (const uint16_t*)dout,
                                                                            (uint16_t*)dqkv, (int)L, Lp, n_heads, C, n_tok, (int)n_frames, temporal);
-    return check_launch("attention_bwd_mma_kernel");
+    MP_CHECK(check_launch("attention_bwd_mma_kernel"));
+    if (dqkv_colsum) return mp_colsum16(dqkv, dqkv_colsum, n_seq * L, 3 * (int64_t)C, dtype, stream);
+    return MP_OK;
   };
   if (hd == 64) return bf ? launch_mma(attention_bwd_mma_kernel<64, Bf16>, 64) : launch_mma(attention_bwd_mma_kernel<64, Fp16>, 64);
   return bf ? launch_mma(attention_bwd_mma_kernel<16, Bf16>, 16) : launch_mma(attention_bwd_mma_kernel<16, Fp16>, 16);

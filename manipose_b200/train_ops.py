@@ -29,11 +29,13 @@ def pad64(m: int) -> int:
     return (m + 63) // 64 * 64
 
 
-def layernorm_bwd(x, gamma, eps, dy, dres, dx, dgamma, dbeta, dtype, dx16=None, rowscale=None):
-    """dx = LN'(x)(dy) [+ dres]; dgamma / dbeta accumulate (None to skip).  dy fp32 or 16-bit.  dx16: also 16-bit(rowscale * dx)."""
+def layernorm_bwd(x, gamma, eps, dy, dres, dx, dgamma, dbeta, dtype, dx16=None, rowscale=None, dx16_colsum=None):
+    """dx = LN'(x)(dy) [+ dres]; dgamma / dbeta accumulate (None to skip).  dy fp32 or 16-bit.  dx16: also 16-bit(rowscale * dx), whose
+    column sums are added to dx16_colsum (the bias gradient of the Linear that dx16 is the output gradient of)."""
     n_tokens, c = x.shape
     rc = L.load().mp_layernorm_bwd(L.ptr(x), L.ptr(gamma), float(eps), L.ptr(dy), int(dy.dtype != torch.float32), L.ptr(dres), L.ptr(dx),
-                                   L.ptr(dgamma), L.ptr(dbeta), L.ptr(dx16), L.ptr(rowscale), n_tokens, c, dtype, L.stream_ptr())
+                                   L.ptr(dgamma), L.ptr(dbeta), L.ptr(dx16), L.ptr(rowscale), L.ptr(dx16_colsum), n_tokens, c, dtype,
+                                   L.stream_ptr())
     L.check(rc, "mp_layernorm_bwd")
     ops._count()
     return dx
@@ -45,14 +47,21 @@ def gelu_fwd(u, a):
     return a
 
 
-def gelu_bwd(u, da, du):
-    L.check(L.load().mp_gelu_bwd(L.ptr(u), L.ptr(da), L.ptr(du), u.numel(), ops.DTYPE_CODE[u.dtype], L.stream_ptr()), "mp_gelu_bwd")
+def gelu_bwd(u, da, du, colsum=None):
+    """du = da * gelu'(u); colsum [C] += column sums of du (the fc1 bias gradient) in the same pass."""
+    if colsum is None:
+        L.check(L.load().mp_gelu_bwd(L.ptr(u), L.ptr(da), L.ptr(du), u.numel(), ops.DTYPE_CODE[u.dtype], L.stream_ptr()), "mp_gelu_bwd")
+    else:
+        m, c = u.shape
+        L.check(L.load().mp_gelu_bwd_colsum(L.ptr(u), L.ptr(da), L.ptr(du), L.ptr(colsum), m, c, ops.DTYPE_CODE[u.dtype], L.stream_ptr()),
+                "mp_gelu_bwd_colsum")
     ops._count()
     return du
 
 
-def attention_bwd(qkv, o, dout, dqkv, n_clips, n_frames, n_tok, c, n_heads, mode):
-    rc = L.load().mp_attention_bwd(L.ptr(qkv), L.ptr(o), L.ptr(dout), L.ptr(dqkv), n_clips, n_frames, n_tok, c, n_heads, mode,
+def attention_bwd(qkv, o, dout, dqkv, n_clips, n_frames, n_tok, c, n_heads, mode, colsum=None):
+    """dqkv from dout; colsum [3C] += column sums of dqkv (the qkv bias gradient)."""
+    rc = L.load().mp_attention_bwd(L.ptr(qkv), L.ptr(o), L.ptr(dout), L.ptr(dqkv), L.ptr(colsum), n_clips, n_frames, n_tok, c, n_heads, mode,
                                    ops.DTYPE_CODE[qkv.dtype], L.stream_ptr())
     L.check(rc, "mp_attention_bwd")
     ops._count()

@@ -51,6 +51,13 @@ def test_layernorm_bwd_vs_autograd(c, dy16, with_res):
         buf = res.clone()
         T.layernorm_bwd(x.detach(), gamma.detach(), 1e-6, dy, buf, buf, None, None, L.MP_DTYPE_BF16)
         torch.testing.assert_close(buf, want, rtol=1e-4, atol=1e-4)
+    # the 16-bit, row-scaled copy for the next GEMM and its column sums (that Linear's bias gradient), taken in the same pass
+    scale = 0.5 + torch.rand(m, generator=gen, device="cuda")
+    dx16 = torch.empty((m, c), dtype=torch.bfloat16, device="cuda")
+    col = torch.full((c,), 3.0, device="cuda")
+    T.layernorm_bwd(x.detach(), gamma.detach(), 1e-6, dy, res, dx, None, None, L.MP_DTYPE_BF16, dx16=dx16, rowscale=scale, dx16_colsum=col)
+    torch.testing.assert_close(dx16.float(), want * scale[:, None], rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(col - 3.0, (want * scale[:, None]).sum(0), rtol=1e-3, atol=2e-2)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
@@ -68,6 +75,12 @@ def test_gelu_fwd_bwd(dtype):
     T.gelu_bwd(u, da, du)
     torch.testing.assert_close(a.float(), ref.detach(), rtol=RTOL[dtype], atol=RTOL[dtype])
     torch.testing.assert_close(du.float(), uf.grad, rtol=RTOL[dtype], atol=RTOL[dtype])
+    # the same with the column sums of du (the fc1 bias gradient) taken in the same pass; ragged row count, narrow matrix
+    for rows, cols in ((3000, 1024), (777, 256), (5, 8)):
+        du2, col = torch.empty((rows, cols), dtype=td, device="cuda"), torch.full((cols,), -2.0, device="cuda")
+        T.gelu_bwd(u[:rows, :cols].contiguous(), da[:rows, :cols].contiguous(), du2, colsum=col)
+        assert torch.equal(du2, du[:rows, :cols])
+        torch.testing.assert_close(col + 2.0, du2.float().sum(0), rtol=1e-4, atol=2e-2)
 
 
 def _attn(qkv, n_clips, n_frames, n_tok, c, heads, temporal):
@@ -100,9 +113,12 @@ def test_attention_bwd_vs_autograd(n_clips, n_frames, n_tok, c, temporal, dtype)
     qf = qkv.float().requires_grad_()
     _attn(qf, n_clips, n_frames, n_tok, c, 8, temporal).backward(do.float())
     dqkv = torch.full((n, 3 * c), float("nan"), dtype=td, device="cuda")
-    T.attention_bwd(qkv, o, do, dqkv, n_clips, n_frames, n_tok, c, 8, 1 if temporal else 0)
+    col = torch.full((3 * c,), 1.5, device="cuda")
+    T.attention_bwd(qkv, o, do, dqkv, n_clips, n_frames, n_tok, c, 8, 1 if temporal else 0, colsum=col)
     torch.cuda.synchronize()
     assert not torch.isnan(dqkv.float()).any()
+    want_col = dqkv.float().sum(0)                 # the qkv bias gradient, taken by the same kernel
+    torch.testing.assert_close(col - 1.5, want_col, rtol=2e-3, atol=2e-3 * float(want_col.abs().max()) + 1e-3)
     floor = 0.05 * float(qf.grad.norm())     # L = 1: dq = dk = 0 exactly, ours carries the 16-bit rounding of O
     for name, sl in (("dq", slice(0, c)), ("dk", slice(c, 2 * c)), ("dv", slice(2 * c, 3 * c))):
         err = float((dqkv[:, sl].float() - qf.grad[:, sl]).norm())
