@@ -310,6 +310,21 @@ int mp_attention_bwd(const void* qkv, const void* o, const void* dout, void* dqk
 int mp_wgrad(const void* dY, const void* X, float* dW, int64_t n_tokens, int64_t n_out, int64_t k_in, int dtype, mp_stream_t stream);
 /* colsum[C] (fp32) += column sums of a 16-bit [M, C] matrix (bias gradients); C % 8 == 0, src 16-byte aligned. */
 int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype, mp_stream_t stream);
+/* Training path of the K hypothesis heads (MCLHead, rmcl_manifold_mix_ste.py:267-298).  `params` / `grads`: device tables int64 [6][K]
+ * of pointers to the heads' fp32 parameters / gradient buffers, rows = {norm.weight [C], norm.bias [C], prediction_head.weight [D+1, C],
+ * prediction_head.bias [D+1], score_head.weight [17], score_head.bias [1]}.
+ *   mp_heads_fold      the folded Linear of mp_heads_fwd16: wf16 [n_pad, C] (and its transpose wt16 [C, n_pad], may be NULL), bf [n_pad],
+ *                      plus the stacked score weights score_w [K, 17] / score_b [K]
+ *   mp_heads_bwd_pack  dY [tokens, n_pad] 16-bit from d_rot [B,K,T,17,D] and d_logits [B,K,T] (y: the fp32 GEMM output mp_heads_fwd16 left
+ *                      in its workspace); dbf [n_pad] += column sums of dY; score_head gradients are accumulated through `grads`
+ *   mp_heads_unfold    dWf [n_pad, C] (= mp_wgrad(dY, xhat)) and dbf -> the heads' norm / prediction_head gradients, accumulated */
+int mp_heads_fold(const int64_t* params, int n_hyp, int out_dim, int C, int n_pad, void* wf16, void* wt16, float* bf, float* score_w,
+                  float* score_b, int dtype, mp_stream_t stream);
+int mp_heads_bwd_pack(const float* d_rot, const float* d_logits, const float* y, const float* score_w, void* dy16, float* dbf,
+                      const int64_t* grads, int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim, int n_pad, int dtype,
+                      mp_stream_t stream);
+int mp_heads_unfold(const int64_t* params, const int64_t* grads, const float* dwf, const float* dbf, int n_hyp, int out_dim, int C,
+                    mp_stream_t stream);
 /* Refresh the 16-bit shadows of n_weights GEMM weights in ONE launch (after an optimizer step).  table (device, int64[n_weights][5]) =
  * {fp32 source pointer, 16-bit shadow [rows, cols] pointer, transposed shadow [cols, rows] pointer or 0, rows, cols}; rows, cols % 64 == 0;
  * max_tiles = max over weights of rows * cols / 4096. */

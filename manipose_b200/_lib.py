@@ -70,6 +70,9 @@ SIGNATURES = {
     "mp_attention_bwd": (I, [P, P, P, P, P, I64, I64, I, I, I, I, I, P]),
     "mp_wgrad": (I, [P, P, P, I64, I64, I64, I, P]),
     "mp_colsum16": (I, [P, P, I64, I64, I, P]),
+    "mp_heads_fold": (I, [P, I, I, I, I, P, P, P, P, P, I, P]),
+    "mp_heads_bwd_pack": (I, [P, P, P, P, P, P, P, I64, I64, I, I, I, I, P]),
+    "mp_heads_unfold": (I, [P, P, P, P, I, I, I, P]),
     "mp_refresh_shadows": (I, [P, I, I, I, P]),
     "mp_transpose16": (I, [P, P, P, I64, I64, I64, I, P]),
     "mp_group_rowsum": (I, [P, P, I64, I, I64, I64, P]),

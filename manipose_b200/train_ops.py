@@ -235,69 +235,78 @@ def accumulate_stacked(params, stacked: torch.Tensor) -> None:
             grad_of(p).add_(stacked[k].reshape(p.shape))
 
 
+def _head_tables(heads):
+    """Device tables int64 [6][K] of the heads' parameter / gradient pointers (mp_heads_fold / mp_heads_bwd_pack / mp_heads_unfold),
+    rebuilt only when a tensor moved (the optimizer keeps parameters and gradients in flat buffers, so they do not)."""
+    kinds = (lambda h: h.norm.weight, lambda h: h.norm.bias, lambda h: h.prediction_head.weight, lambda h: h.prediction_head.bias,
+             lambda h: h.score_head.weight, lambda h: h.score_head.bias)
+    params = [f(h) for f in kinds for h in heads]
+    key = tuple(p.data_ptr() for p in params) + tuple(grad_of(p).data_ptr() for p in params)
+    cached = getattr(heads[0], "_mp_tables", None)
+    if cached is None or cached[0] != key:
+        dev = params[0].device
+        n = len(params)
+        cached = (key, torch.tensor(key[:n], dtype=torch.int64, device=dev), torch.tensor(key[n:], dtype=torch.int64, device=dev))
+        heads[0]._mp_tables = cached
+    return cached[1], cached[2]
+
+
 class FoldedHeadsFn(torch.autograd.Function):
     """The K hypothesis heads of RMCLRotMixSTE (rmcl_manifold_mix_ste.py:251-298) over a shared normalised input yhat [M, C] (16-bit):
     LN_k(y) = yhat * gamma_k + beta_k, so all heads are ONE Linear with folded parameters W_k * gamma_k, W_k beta_k + b_k (zero-padded to
     128 outputs for the tensor-core kernel, fp32 output), followed by the J-term score dot product.  Parameters are read from the
-    module, not passed through autograd: the backward unfolds the gradients itself and accumulates them straight into ``p.grad`` (one
-    launch per parameter KIND when the heads sit at a constant stride in the flat gradient buffer), like the trunk's reverse sweep —
-    the autograd version cost ~75 tiny launches per step (stack / select backward, zero fills, one AccumulateGrad add per tensor)."""
+    module, not passed through autograd; folding, the packing of the output gradient and the unfolding of the parameter gradients are one
+    kernel each (csrc/heads_train.cu) around the GEMMs, and the gradients are accumulated straight into ``p.grad`` like the trunk's
+    reverse sweep does: 3 launches forward, 5 backward (the torch version of this glue was ~55)."""
 
     @staticmethod
     def forward(ctx, yhat16, heads, b, l, j, out_dim, anchor):   # anchor: a head parameter, only there so that the outputs require grad
         k, d1, c = len(heads), out_dim + 1, yhat16.shape[1]
         code = ops.DTYPE_CODE[yhat16.dtype]
-        gam = torch.stack([h.norm.weight.detach() for h in heads])                       # [K, C]
-        bet = torch.stack([h.norm.bias.detach() for h in heads])
-        w = torch.stack([h.prediction_head.weight.detach() for h in heads])              # [K, D+1, C]
-        bias = torch.stack([h.prediction_head.bias.detach() for h in heads])             # [K, D+1]
-        sw = torch.stack([h.score_head.weight.detach().reshape(-1) for h in heads])      # [K, J]
-        sb = torch.stack([h.score_head.bias.detach().reshape(()) for h in heads])        # [K]
+        dev = yhat16.device
+        params, grads = _head_tables(heads)
         n_pad = (k * d1 + 127) // 128 * 128
-        wf = torch.zeros((n_pad, c), dtype=torch.float32, device=yhat16.device)
-        wf[:k * d1] = (w * gam[:, None, :]).reshape(k * d1, c)
-        bf = torch.zeros(n_pad, dtype=torch.float32, device=yhat16.device)
-        bf[:k * d1] = ((w * bet[:, None, :]).sum(-1) + bias).reshape(k * d1)
-        w16 = ops.cast16(wf, code)
         m = yhat16.shape[0]
-        y = torch.zeros((m, n_pad), dtype=torch.float32, device=yhat16.device)
-        ops.linear(yhat16, w16, bf, y, L.MP_EPI_RESIDUAL, resid=y)
-        out = y[:, :k * d1].reshape(b, l, j, k, d1)
-        rot = out[..., :out_dim].permute(0, 3, 1, 2, 4)
-        score_in = out[..., out_dim]                                                     # [B, L, J, K]
-        logits = (score_in * sw.t()[None, None]).sum(2).permute(0, 2, 1) + sb[None, :, None]
-        ctx.heads, ctx.dims = heads, (b, l, j, k, d1, c, n_pad, out_dim)
-        ctx.save_for_backward(yhat16, w16, score_in, gam, bet, w, sw)
+        wf16 = torch.empty((n_pad, c), dtype=yhat16.dtype, device=dev)
+        wt16 = torch.empty((c, n_pad), dtype=yhat16.dtype, device=dev)
+        bf = torch.empty(n_pad, dtype=torch.float32, device=dev)
+        sw = torch.empty((k, j), dtype=torch.float32, device=dev)
+        sb = torch.empty(k, dtype=torch.float32, device=dev)
+        L.check(L.load().mp_heads_fold(L.ptr(params), k, out_dim, c, n_pad, L.ptr(wf16), L.ptr(wt16), L.ptr(bf), L.ptr(sw), L.ptr(sb), code,
+                                       L.stream_ptr()), "mp_heads_fold")
+        ops._count()
+        y = torch.empty((m, n_pad), dtype=torch.float32, device=dev)     # the GEMM output: the score embeddings are needed again
+        rot = torch.empty((b, k, l, j, out_dim), dtype=torch.float32, device=dev)
+        logits = torch.empty((b, k, l), dtype=torch.float32, device=dev)
+        ops.heads_fwd16(yhat16, wf16, bf, sw, sb, rot, logits, y, b, l, k, out_dim, True)
+        ctx.tables, ctx.dims = (params, grads), (b, l, j, k, d1, c, n_pad, out_dim)
+        ctx.save_for_backward(yhat16, wt16, y, sw)
         return rot, logits
 
     @staticmethod
     def backward(ctx, d_rot, d_logits):
-        yhat16, w16, score_in, gam, bet, w, sw = ctx.saved_tensors
-        heads = ctx.heads
+        yhat16, wt16, y, sw = ctx.saved_tensors
+        params, grads = ctx.tables
         b, l, j, k, d1, c, n_pad, out_dim = ctx.dims
         code = ops.DTYPE_CODE[yhat16.dtype]
+        dev = yhat16.device
         m = yhat16.shape[0]
-        dl = d_logits.permute(0, 2, 1)[:, :, None, :]                                    # [B, L, 1, K]
-        dy = torch.zeros((m, n_pad), dtype=torch.float32, device=yhat16.device)
-        d_out = dy[:, :k * d1].view(b, l, j, k, d1)
-        d_out[..., :out_dim] = d_rot.permute(0, 2, 3, 1, 4)
-        d_out[..., out_dim] = dl * sw.t()[None, None]
-        accumulate_stacked([h.score_head.weight for h in heads], (dl * score_in).sum((0, 1)).t())
-        accumulate_stacked([h.score_head.bias for h in heads], d_logits.sum((0, 2)))
-        dy16 = ops.cast16(dy, code)
-        dwf = torch.zeros((n_pad, c), dtype=torch.float32, device=yhat16.device)
-        dbf = torch.zeros(n_pad, dtype=torch.float32, device=yhat16.device)
-        wgrad(dy16, yhat16, dwf, dbf)
-        w_t = torch.empty((c, n_pad), dtype=yhat16.dtype, device=yhat16.device)
-        transpose16(w16, w_t)
-        da = torch.empty((m, c), dtype=yhat16.dtype, device=yhat16.device)
-        dgrad(dy16, w_t, da)
-        dw3, db2 = dwf[:k * d1].view(k, d1, c), dbf[:k * d1].view(k, d1)
-        # Wf = W * gamma and bf = W beta + b both depend on W: dL/dW[k,d,c] = dWf[k,d,c] gamma[k,c] + dbf[k,d] beta[k,c]
-        accumulate_stacked([h.prediction_head.weight for h in heads], dw3 * gam[:, None, :] + db2[:, :, None] * bet[:, None, :])
-        accumulate_stacked([h.prediction_head.bias for h in heads], db2)
-        accumulate_stacked([h.norm.weight for h in heads], (dw3 * w).sum(1))
-        accumulate_stacked([h.norm.bias for h in heads], (db2[:, :, None] * w).sum(1))
+        if d_rot is None:
+            d_rot = torch.zeros((b, k, l, j, out_dim), dtype=torch.float32, device=dev)
+        if d_logits is None:
+            d_logits = torch.zeros((b, k, l), dtype=torch.float32, device=dev)
+        buf = torch.zeros(n_pad * c + n_pad, dtype=torch.float32, device=dev)
+        dwf, dbf = buf[:n_pad * c].view(n_pad, c), buf[n_pad * c:]
+        dy16 = torch.empty((m, n_pad), dtype=yhat16.dtype, device=dev)
+        rc = L.load().mp_heads_bwd_pack(L.ptr(ops._f32(d_rot)), L.ptr(ops._f32(d_logits)), L.ptr(y), L.ptr(sw), L.ptr(dy16), L.ptr(dbf), L.ptr(grads),
+                                        b, l, k, out_dim, n_pad, code, L.stream_ptr())
+        L.check(rc, "mp_heads_bwd_pack")
+        ops._count()
+        wgrad(dy16, yhat16, dwf, None)
+        da = torch.empty((m, c), dtype=yhat16.dtype, device=dev)
+        dgrad(dy16, wt16, da)
+        L.check(L.load().mp_heads_unfold(L.ptr(params), L.ptr(grads), L.ptr(dwf), L.ptr(dbf), k, out_dim, c, L.stream_ptr()), "mp_heads_unfold")
+        ops._count()
         return da, None, None, None, None, None, None
 
 
