@@ -17,6 +17,8 @@ from functools import partial
 from math import sqrt
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -207,8 +209,8 @@ class MixSTE(nn.Module):
     # fc1 -> GELU -> fc2 + residual + LayerNorms in ONE launch with the hidden activation kept on chip (mp_mlp_ln; C = 512, hidden =
     # 1024 only).  Bit-identical to the two launches it replaces, but SLOWER on B200 (1784 vs 1367 us per 528,768 tokens): the fc2
     # accumulator and two fc1 chunk accumulators fill TMEM, so the LayerNorm epilogue cannot overlap the next tile's fc2 (DESIGN.md
-    # §5, negative results).  Off by default; kept for A/B measurements.
-    fuse_mlp = False
+    # §5, negative results).  Off by default; kept for A/B measurements (MANIPOSE_FUSE_MLP=1 turns it on).
+    fuse_mlp = os.environ.get("MANIPOSE_FUSE_MLP", "0") == "1"
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
