@@ -25,8 +25,12 @@ namespace {
 // y = (x - mean) * rstd * gamma + beta.  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ dres], g = dy * gamma;
 // dgamma += sum dy * xhat, dbeta += sum dy (fp32 atomics, one per CTA and channel).  gamma == NULL: no affine.
 // dx16_colsum (may be NULL): += column sums of the dx16 output = the bias gradient of the Linear whose output gradient dx16 is.
+// One CTA of kLnBwdWarps warps per SM, a warp per row; the NEXT row's x and dy are requested before the current row is reduced and
+// stored (dx may alias dres, so the compiler cannot move those loads above the stores itself): two rows in flight per warp.
+constexpr int kLnBwdWarps = 12;
+
 template <int C, bool kDy16, typename D>
-__global__ void __launch_bounds__(kTokWarps * 32)
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* dy,
                      const float* dres, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* dx16,
                      const float* __restrict__ rowscale, float* __restrict__ dx16_colsum, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
@@ -35,8 +39,8 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   using R = Row<C>;
   __shared__ float acc[3][C];
   const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
-  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
+  const int64_t warp_global = (int64_t)blockIdx.x * kLnBwdWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kLnBwdWarps;
   float g[R::kPer], ag[R::kPer], ab[R::kPer], ac[R::kPer];
 #pragma unroll
   for (int i = 0; i < R::kPer; ++i) {
@@ -46,13 +50,25 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     ac[i] = 0.f;
   }
   if (gamma) R::load_f32(gamma, lane, g);
-  for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
-    float v[R::kPer], d[R::kPer];
-    R::load_x(x + tok * C, lane, v);
+  float vn[R::kPer], dn[R::kPer];
+  auto fetch = [&](int64_t tok) {
+    R::load_x(x + tok * C, lane, vn);
     if (kDy16)
-      R::template load_h<D>(reinterpret_cast<const uint16_t*>(dy) + tok * C, lane, d);
+      R::template load_h<D>(reinterpret_cast<const uint16_t*>(dy) + tok * C, lane, dn);
     else
-      R::load_x(reinterpret_cast<const float*>(dy) + tok * C, lane, d);
+      R::load_x(reinterpret_cast<const float*>(dy) + tok * C, lane, dn);
+  };
+  if (warp_global < n_tokens) fetch(warp_global);
+  for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
+    float v[R::kPer], d[R::kPer], r[R::kPer];
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) {
+      v[i] = vn[i];
+      d[i] = dn[i];
+      r[i] = 0.f;
+    }
+    if (dres) R::load_x(dres + tok * C, lane, r);
+    if (tok + stride < n_tokens) fetch(tok + stride);
     float mean, rstd;
     R::stats(v, eps, mean, rstd);
     float s1 = 0.f, s2 = 0.f;
@@ -70,13 +86,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     s1 = warp_sum(s1) * (1.0f / C);
     s2 = warp_sum(s2) * (1.0f / C);
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2);
-    if (dres) {
-      float r[R::kPer];
-      R::load_x(dres + tok * C, lane, r);
-#pragma unroll
-      for (int i = 0; i < R::kPer; ++i) d[i] += r[i];
-    }
+    for (int i = 0; i < R::kPer; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2) + r[i];
     R::store_x(dx + tok * C, lane, d);
     if (dx16) {   // the next backward GEMM's operand: 16-bit copy, scaled by the sample's stochastic-depth factor
       const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
@@ -740,12 +750,12 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   MP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(dres) && aligned16(dx16), MP_EALIGN,
              "mp_layernorm_bwd: rows must be 16-byte aligned");
   if (n_tokens == 0) return MP_OK;
-  // every CTA ends with 2 C atomics on the same dgamma / dbeta words: keep the grid at two CTAs per SM when they are wanted
-  int grid = token_grid(n_tokens);
   MP_REQUIRE(dx16_colsum == nullptr || dx16 != nullptr, MP_EINVAL, "mp_layernorm_bwd: dx16_colsum needs dx16");
-  if ((dgamma || dx16_colsum) && grid > 2 * sm_count()) grid = 2 * sm_count();
+  // one CTA per SM (every CTA ends with up to 3 C atomics on the same words); few rows: one per warp
+  int64_t ctas = (n_tokens + kLnBwdWarps - 1) / kLnBwdWarps;
+  const int grid = (int)(ctas < sm_count() ? ctas : sm_count());
   auto launch = [&](auto kernel) {
-    launch_k(kernel, grid, kTokWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, dx16_colsum,
+    launch_k(kernel, grid, kLnBwdWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, dx16_colsum,
              n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
