@@ -142,6 +142,40 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-0.5f * ax, e, fmaxf(x, 0.f));
 }
 
+// Two elements at once with the packed fp32 instructions of sm_100 (fma.rn.f32x2 -> FFMA2: two independent IEEE FMAs per issue slot):
+// the degree-6 polynomial and the product t Q(t) take 7 instructions per PAIR instead of per element; results are bit-identical to
+// gelu_erf.  The tensor-core epilogues of fc1 are instruction-issue bound, so this is what they call.
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const float t0 = fminf(a0 * 0.70710678118654752440f, 4.6f), t1 = fminf(a1 * 0.70710678118654752440f, 4.6f);
+  const uint64_t t = pack_f32x2(t0, t1);
+  uint64_t q = pack_f32x2(-9.749186599e-05f, -9.749186599e-05f);
+  q = fma_f32x2(q, t, pack_f32x2(4.431374392e-04f, 4.431374392e-04f));
+  q = fma_f32x2(q, t, pack_f32x2(2.348781295e-03f, 2.348781295e-03f));
+  q = fma_f32x2(q, t, pack_f32x2(-2.950778651e-02f, -2.950778651e-02f));
+  q = fma_f32x2(q, t, pack_f32x2(1.489954364e-01f, 1.489954364e-01f));
+  q = fma_f32x2(q, t, pack_f32x2(9.183205755e-01f, 9.183205755e-01f));
+  q = fma_f32x2(q, t, pack_f32x2(1.627914397e+00f, 1.627914397e+00f));
+  uint64_t tq;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(tq) : "l"(q), "l"(t));
+  float g0, g1, e0, e1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(tq));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-g1));
+  x0 = fmaf(-0.5f * a0, e0, fmaxf(x0, 0.f));
+  x1 = fmaf(-0.5f * a1, e1, fmaxf(x1, 0.f));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

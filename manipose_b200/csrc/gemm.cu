@@ -291,7 +291,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                             __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
               if (EPI == MP_EPI_GELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                for (int e = 0; e < 8; e += 2) gelu_erf2(f[e], f[e + 1]);
               }
               uint4 o;
               o.x = D::pack2(f[0], f[1]);

@@ -224,7 +224,7 @@ pair_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
               if (EPI == MP_EPI_GELU || (EPI == kEpiGelu2 && pass == 1)) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                for (int e = 0; e < 8; e += 2) gelu_erf2(f[e], f[e + 1]);
               }
               uint4 o;
               o.x = D::pack2(f[0], f[1]);
@@ -457,7 +457,7 @@ pair_linear_as_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                             __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w};
               if (EPI == MP_EPI_GELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                for (int e = 0; e < 8; e += 2) gelu_erf2(f[e], f[e + 1]);
               }
               o[half * 4 + c].x = D::pack2(f[0], f[1]);
               o[half * 4 + c].y = D::pack2(f[2], f[3]);

@@ -371,7 +371,7 @@ mlp_ln64_kernel(const __grid_constant__ CUtensorMap tm_hin, const __grid_constan
                           __uint_as_float(r[8 * cc + 4]) + bb.x, __uint_as_float(r[8 * cc + 5]) + bb.y,
                           __uint_as_float(r[8 * cc + 6]) + bb.z, __uint_as_float(r[8 * cc + 7]) + bb.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            for (int e = 0; e < 8; e += 2) gelu_erf2(f[e], f[e + 1]);
             o[half * 4 + cc].x = D::pack2(f[0], f[1]);
             o[half * 4 + cc].y = D::pack2(f[2], f[3]);
             o[half * 4 + cc].z = D::pack2(f[4], f[5]);
