@@ -155,6 +155,37 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_u32x2(uint64_t v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ float sum_f32x2(uint64_t v) {
+  float a, b;
+  unpack_f32x2(v, a, b);
+  return a + b;
+}
+
+// 16-bit pair of ((x - mean) * rstd) * gamma + beta for two adjacent elements (the LayerNorm epilogues): three packed instructions
+template <typename D>
+__device__ __forceinline__ uint32_t pack2_ln(uint64_t x2, uint64_t nmean2, uint64_t rstd2, uint64_t g2, uint64_t b2) {
+  float a, b;
+  unpack_f32x2(fma_f32x2(mul_f32x2(add_f32x2(x2, nmean2), rstd2), g2, b2), a, b);
+  return D::pack2(a, b);
+}
+
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const float a0 = fabsf(x0), a1 = fabsf(x1);
   const float t0 = fminf(a0 * 0.70710678118654752440f, 4.6f), t1 = fminf(a1 * 0.70710678118654752440f, 4.6f);

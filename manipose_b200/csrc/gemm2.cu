@@ -698,7 +698,9 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 
       // ---- pass A: v = resid + scale * (acc + bias); shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      uint64_t s1p = 0, s2p = 0, nshift2 = 0, nmean2 = 0, rstd2 = 0;   // packed accumulators / broadcast operands (common.cuh)
       const float scale = (args.row_scale != nullptr && grow < M) ? __ldg(args.row_scale + grow) : 1.0f;
+      const uint64_t scale2 = pack_f32x2(scale, scale);
 #pragma unroll 1
       for (int j = 0; j < 8; ++j, ++n) {
         const uint32_t ls = n % kGS, slot = (uint32_t)(grp * kGS) + ls;
@@ -719,14 +721,18 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ sw) << 4));
           const float4 bb = __ldg(b4 + c);
           float4 v = *p;
-          v.x = fmaf(scale, __uint_as_float(r[4 * c + 0]) + bb.x, v.x);   // scale == 1: the same two roundings as v += acc + bias
-          v.y = fmaf(scale, __uint_as_float(r[4 * c + 1]) + bb.y, v.y);
-          v.z = fmaf(scale, __uint_as_float(r[4 * c + 2]) + bb.z, v.z);
-          v.w = fmaf(scale, __uint_as_float(r[4 * c + 3]) + bb.w, v.w);
-          if (j == 0 && c == 0) shift = v.x;
-          const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
-          s1 += (d0 + d1) + (d2 + d3);
-          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          // packed fp32 (FFMA2 / FADD2: two elements per issue slot); scale == 1: the same two roundings as v += acc + bias
+          const uint64_t v01 = fma_f32x2(scale2, add_f32x2(pack_u32x2(r[4 * c + 0], r[4 * c + 1]), pack_f32x2(bb.x, bb.y)), pack_f32x2(v.x, v.y));
+          const uint64_t v23 = fma_f32x2(scale2, add_f32x2(pack_u32x2(r[4 * c + 2], r[4 * c + 3]), pack_f32x2(bb.z, bb.w)), pack_f32x2(v.z, v.w));
+          unpack_f32x2(v01, v.x, v.y);
+          unpack_f32x2(v23, v.z, v.w);
+          if (j == 0 && c == 0) {
+            shift = v.x;
+            nshift2 = pack_f32x2(-shift, -shift);
+          }
+          const uint64_t d01 = add_f32x2(v01, nshift2), d23 = add_f32x2(v23, nshift2);
+          s1p = add_f32x2(s1p, add_f32x2(d01, d23));
+          s2p = fma_f32x2(d23, d23, fma_f32x2(d01, d01, s2p));
           r[4 * c + 0] = __float_as_uint(v.x);
           r[4 * c + 1] = __float_as_uint(v.y);
           r[4 * c + 2] = __float_as_uint(v.z);
@@ -755,16 +761,20 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       float mean = 0.f, rstd = 0.f;
       if (has_post || has_ln) {
         ptx::tmem_st_wait();
+        s1 = sum_f32x2(s1p);
+        s2 = sum_f32x2(s2p);
         const float mh = shift + s1 * (1.0f / 256.0f);
         const float m2h = fmaxf(s2 - s1 * s1 * (1.0f / 256.0f), 0.f);
         row_stats_exchange(sx, grp, row, mh, m2h, has_post ? args.post_eps : args.ln_eps, mean, rstd);
+        nmean2 = pack_f32x2(-mean, -mean);
+        rstd2 = pack_f32x2(rstd, rstd);
       }
 
       // ---- pass B (post-norm): y = LN_post(v) (+ pos-embed) -> x_out and back to TMEM, statistics of y
       if (has_post) {
         const float* pos_row = args.pos ? args.pos + (size_t)((grow / args.pos_div) % args.pos_mod) * kN : nullptr;
-        s1 = 0.f;
-        s2 = 0.f;
+        s1p = 0;
+        s2p = 0;
         const bool store_b = args.no_x == 0;        // x_out wanted (false: only the statistics and the TMEM copy for pass C)
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
@@ -780,22 +790,23 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 gg = __ldg(g4 + c), bb = __ldg(be4 + c);
-            float4 y;
-            y.x = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, gg.x, bb.x);
-            y.y = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, gg.y, bb.y);
-            y.z = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, gg.z, bb.z);
-            y.w = fmaf((__uint_as_float(r[4 * c + 3]) - mean) * rstd, gg.w, bb.w);
+            uint64_t y01 = fma_f32x2(mul_f32x2(add_f32x2(pack_u32x2(r[4 * c + 0], r[4 * c + 1]), nmean2), rstd2), pack_f32x2(gg.x, gg.y), pack_f32x2(bb.x, bb.y));
+            uint64_t y23 = fma_f32x2(mul_f32x2(add_f32x2(pack_u32x2(r[4 * c + 2], r[4 * c + 3]), nmean2), rstd2), pack_f32x2(gg.z, gg.w), pack_f32x2(bb.z, bb.w));
             if (pos_row != nullptr && grow < M) {
               const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + col) + c);
-              y.x += pe.x;
-              y.y += pe.y;
-              y.z += pe.z;
-              y.w += pe.w;
+              y01 = add_f32x2(y01, pack_f32x2(pe.x, pe.y));
+              y23 = add_f32x2(y23, pack_f32x2(pe.z, pe.w));
             }
-            if (j == 0 && c == 0) shift = y.x;
-            const float d0 = y.x - shift, d1 = y.y - shift, d2 = y.z - shift, d3 = y.w - shift;
-            s1 += (d0 + d1) + (d2 + d3);
-            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            float4 y;
+            unpack_f32x2(y01, y.x, y.y);
+            unpack_f32x2(y23, y.z, y.w);
+            if (j == 0 && c == 0) {
+              shift = y.x;
+              nshift2 = pack_f32x2(-shift, -shift);
+            }
+            const uint64_t d01 = add_f32x2(y01, nshift2), d23 = add_f32x2(y23, nshift2);
+            s1p = add_f32x2(s1p, add_f32x2(d01, d23));
+            s2p = fma_f32x2(d23, d23, fma_f32x2(d01, d01, s2p));
             r[4 * c + 0] = __float_as_uint(y.x);
             r[4 * c + 1] = __float_as_uint(y.y);
             r[4 * c + 2] = __float_as_uint(y.z);
@@ -816,9 +827,13 @@ pair_linear_ln_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
         if (has_ln) {
           ptx::tmem_st_wait();
+          s1 = sum_f32x2(s1p);
+          s2 = sum_f32x2(s2p);
           const float mh = shift + s1 * (1.0f / 256.0f);
           const float m2h = fmaxf(s2 - s1 * s1 * (1.0f / 256.0f), 0.f);
           row_stats_exchange(sx, grp, row, mh, m2h, args.ln_eps, mean, rstd);
+          nmean2 = pack_f32x2(-mean, -mean);
+          rstd2 = pack_f32x2(rstd, rstd);
         }
       }
 
@@ -1106,7 +1121,9 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 
       // ---- pass A: v = resid + scale * (acc + bias); shifted sums for the row statistics; v goes back to TMEM (and out, if no post-norm)
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      uint64_t s1p = 0, s2p = 0, nshift2 = 0, nmean2 = 0, rstd2 = 0;   // packed accumulators / broadcast operands (common.cuh)
       const float scale = (args.row_scale != nullptr && grow < M) ? __ldg(args.row_scale + grow) : 1.0f;
+      const uint64_t scale2 = pack_f32x2(scale, scale);
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const uint32_t nl = tt * 4u + (uint32_t)j;
@@ -1123,14 +1140,18 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
           float4* p = reinterpret_cast<float4*>(lrow + (((uint32_t)c ^ sw) << 4));
           const float4 bb = __ldg(b4 + c);
           float4 v = *p;
-          v.x = fmaf(scale, __uint_as_float(r[4 * c + 0]) + bb.x, v.x);   // scale == 1: the same two roundings as v += acc + bias
-          v.y = fmaf(scale, __uint_as_float(r[4 * c + 1]) + bb.y, v.y);
-          v.z = fmaf(scale, __uint_as_float(r[4 * c + 2]) + bb.z, v.z);
-          v.w = fmaf(scale, __uint_as_float(r[4 * c + 3]) + bb.w, v.w);
-          if (j == 0 && c == 0) shift = v.x;
-          const float d0 = v.x - shift, d1 = v.y - shift, d2 = v.z - shift, d3 = v.w - shift;
-          s1 += (d0 + d1) + (d2 + d3);
-          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          // packed fp32 (FFMA2 / FADD2: two elements per issue slot); scale == 1: the same two roundings as v += acc + bias
+          const uint64_t v01 = fma_f32x2(scale2, add_f32x2(pack_u32x2(r[4 * c + 0], r[4 * c + 1]), pack_f32x2(bb.x, bb.y)), pack_f32x2(v.x, v.y));
+          const uint64_t v23 = fma_f32x2(scale2, add_f32x2(pack_u32x2(r[4 * c + 2], r[4 * c + 3]), pack_f32x2(bb.z, bb.w)), pack_f32x2(v.z, v.w));
+          unpack_f32x2(v01, v.x, v.y);
+          unpack_f32x2(v23, v.z, v.w);
+          if (j == 0 && c == 0) {
+            shift = v.x;
+            nshift2 = pack_f32x2(-shift, -shift);
+          }
+          const uint64_t d01 = add_f32x2(v01, nshift2), d23 = add_f32x2(v23, nshift2);
+          s1p = add_f32x2(s1p, add_f32x2(d01, d23));
+          s2p = fma_f32x2(d23, d23, fma_f32x2(d01, d01, s2p));
           r[4 * c + 0] = __float_as_uint(v.x);
           r[4 * c + 1] = __float_as_uint(v.y);
           r[4 * c + 2] = __float_as_uint(v.z);
@@ -1153,16 +1174,20 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       float mean = 0.f, rstd = 0.f;
       if (has_post || has_ln) {
         ptx::tmem_st_wait();
+        s1 = sum_f32x2(s1p);
+        s2 = sum_f32x2(s2p);
         const float mq = shift + s1 * (1.0f / 128.0f);
         const float m2q = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
         row_stats(mq, m2q, has_post ? args.post_eps : args.ln_eps, mean, rstd);
+        nmean2 = pack_f32x2(-mean, -mean);
+        rstd2 = pack_f32x2(rstd, rstd);
       }
 
       // ---- pass B (post-norm): y = LN_post(v) (+ pos-embed) -> x_out and back to TMEM, statistics of y
       if (has_post) {
         const float* pos_row = args.pos ? args.pos + (size_t)((grow / args.pos_div) % args.pos_mod) * 512 : nullptr;
-        s1 = 0.f;
-        s2 = 0.f;
+        s1p = 0;
+        s2p = 0;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int col = cbase + 32 * j;
@@ -1174,22 +1199,23 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 gg = __ldg(g4 + c), bb = __ldg(be4 + c);
-            float4 y;
-            y.x = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, gg.x, bb.x);
-            y.y = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, gg.y, bb.y);
-            y.z = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, gg.z, bb.z);
-            y.w = fmaf((__uint_as_float(r[4 * c + 3]) - mean) * rstd, gg.w, bb.w);
+            uint64_t y01 = fma_f32x2(mul_f32x2(add_f32x2(pack_u32x2(r[4 * c + 0], r[4 * c + 1]), nmean2), rstd2), pack_f32x2(gg.x, gg.y), pack_f32x2(bb.x, bb.y));
+            uint64_t y23 = fma_f32x2(mul_f32x2(add_f32x2(pack_u32x2(r[4 * c + 2], r[4 * c + 3]), nmean2), rstd2), pack_f32x2(gg.z, gg.w), pack_f32x2(bb.z, bb.w));
             if (pos_row != nullptr && grow < M) {
               const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + col) + c);
-              y.x += pe.x;
-              y.y += pe.y;
-              y.z += pe.z;
-              y.w += pe.w;
+              y01 = add_f32x2(y01, pack_f32x2(pe.x, pe.y));
+              y23 = add_f32x2(y23, pack_f32x2(pe.z, pe.w));
             }
-            if (j == 0 && c == 0) shift = y.x;
-            const float d0 = y.x - shift, d1 = y.y - shift, d2 = y.z - shift, d3 = y.w - shift;
-            s1 += (d0 + d1) + (d2 + d3);
-            s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+            float4 y;
+            unpack_f32x2(y01, y.x, y.y);
+            unpack_f32x2(y23, y.z, y.w);
+            if (j == 0 && c == 0) {
+              shift = y.x;
+              nshift2 = pack_f32x2(-shift, -shift);
+            }
+            const uint64_t d01 = add_f32x2(y01, nshift2), d23 = add_f32x2(y23, nshift2);
+            s1p = add_f32x2(s1p, add_f32x2(d01, d23));
+            s2p = fma_f32x2(d23, d23, fma_f32x2(d01, d01, s2p));
             r[4 * c + 0] = __float_as_uint(y.x);
             r[4 * c + 1] = __float_as_uint(y.y);
             r[4 * c + 2] = __float_as_uint(y.z);
@@ -1207,9 +1233,13 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         if (last_pass == 1) release_acc();
         if (has_ln) {
           ptx::tmem_st_wait();
+          s1 = sum_f32x2(s1p);
+          s2 = sum_f32x2(s2p);
           const float mq = shift + s1 * (1.0f / 128.0f);
           const float m2q = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
           row_stats(mq, m2q, args.ln_eps, mean, rstd);
+          nmean2 = pack_f32x2(-mean, -mean);
+          rstd2 = pack_f32x2(rstd, rstd);
         }
       }
 
@@ -1232,10 +1262,10 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float4 g0 = __ldg(g4 + 2 * c), g1 = __ldg(g4 + 2 * c + 1), b0 = __ldg(be4 + 2 * c), b1 = __ldg(be4 + 2 * c + 1);
-              o[half * 4 + c].x = D::pack2(fmaf((__uint_as_float(r[8 * c + 0]) - mean) * rstd, g0.x, b0.x), fmaf((__uint_as_float(r[8 * c + 1]) - mean) * rstd, g0.y, b0.y));
-              o[half * 4 + c].y = D::pack2(fmaf((__uint_as_float(r[8 * c + 2]) - mean) * rstd, g0.z, b0.z), fmaf((__uint_as_float(r[8 * c + 3]) - mean) * rstd, g0.w, b0.w));
-              o[half * 4 + c].z = D::pack2(fmaf((__uint_as_float(r[8 * c + 4]) - mean) * rstd, g1.x, b1.x), fmaf((__uint_as_float(r[8 * c + 5]) - mean) * rstd, g1.y, b1.y));
-              o[half * 4 + c].w = D::pack2(fmaf((__uint_as_float(r[8 * c + 6]) - mean) * rstd, g1.z, b1.z), fmaf((__uint_as_float(r[8 * c + 7]) - mean) * rstd, g1.w, b1.w));
+              o[half * 4 + c].x = pack2_ln<D>(pack_u32x2(r[8 * c + 0], r[8 * c + 1]), nmean2, rstd2, pack_f32x2(g0.x, g0.y), pack_f32x2(b0.x, b0.y));
+              o[half * 4 + c].y = pack2_ln<D>(pack_u32x2(r[8 * c + 2], r[8 * c + 3]), nmean2, rstd2, pack_f32x2(g0.z, g0.w), pack_f32x2(b0.z, b0.w));
+              o[half * 4 + c].z = pack2_ln<D>(pack_u32x2(r[8 * c + 4], r[8 * c + 5]), nmean2, rstd2, pack_f32x2(g1.x, g1.y), pack_f32x2(b1.x, b1.y));
+              o[half * 4 + c].w = pack2_ln<D>(pack_u32x2(r[8 * c + 6], r[8 * c + 7]), nmean2, rstd2, pack_f32x2(g1.z, g1.w), pack_f32x2(b1.z, b1.w));
             }
           }
           slot_writable();
