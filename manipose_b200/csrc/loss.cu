@@ -36,6 +36,7 @@ constexpr int kFwdWarps = 12, kFwdBufs = 2;
 constexpr int kBwdWarps = 11, kBwdBufs = 3;
 constexpr int kMaxPartialWarps = 148 * 2 * 16;   // >= SMs x kFwdWarps
 constexpr int kMaxHyp = 32;
+constexpr int kScorePrefetch = 5;          // scores of the first hypotheses (K = 5 by default) are requested ahead of their use
 
 __constant__ float c_ones17[kJ] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
 
@@ -153,6 +154,8 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
 #pragma unroll
   for (int j = 0; j < kJ; ++j) w[j] = weights ? weights[j] : c_ones17[j];
   const float r17 = ieee::rcp_refined(17.0f), r3 = ieee::rcp_refined(3.0f);
+  const uint64_t r3_2 = pack_f32x2(r3, r3), kNeg3x2 = pack_f32x2(-3.0f, -3.0f), kNeg1x2 = pack_f32x2(-1.0f, -1.0f), kHalfx2 = pack_f32x2(0.5f, 0.5f);
+  auto sub_f32x2 = [&](uint64_t a, uint64_t b) { return fma_f32x2(b, kNeg1x2, a); };   // a - b, one rounding per lane
 
   const uint32_t tiles_per_clip = (d.T + kTileFrames - 1) / kTileFrames;
   const uint32_t n_items = d.B * tiles_per_clip;
@@ -171,18 +174,35 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
     const int sy = stage_tile(st.buf[1], st.bar[1], y, ((size_t)b * d.T + t0) * kF, nload * kF, y_total, lane);
     int sh_cur = stage_tile(st.buf[0], st.bar[0], hyp, (((size_t)b * d.K) * d.T + t0) * kF, nload * kF, h_total, lane);
     st.wait(1);
-    float yr[kF], dy[kAllTerms ? kF : 1];
+    // ground truth as PAIRS of joints (2 jp, 2 jp + 1), component by component, for the packed fp32 instructions; joint 16 alone
+    uint64_t Y[8][3], DY[kAllTerms ? 8 : 1][3];
+    float y16[3], dy16[3] = {0.f, 0.f, 0.f};
     {
       const float* yp = st.buf[1] + sy + lane * kF;
 #pragma unroll
-      for (int i = 0; i < kF; ++i) {
-        yr[i] = yp[i];
-        if (kAllTerms) dy[i] = yp[kF + i] - yr[i];
+      for (int jp = 0; jp < 8; ++jp)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float ya = yp[6 * jp + c], yb = yp[6 * jp + 3 + c];
+          Y[jp][c] = pack_f32x2(ya, yb);
+          if (kAllTerms) DY[jp][c] = pack_f32x2(yp[kF + 6 * jp + c] - ya, yp[kF + 6 * jp + 3 + c] - yb);
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        y16[c] = yp[48 + c];
+        if (kAllTerms) dy16[c] = yp[kF + 48 + c] - y16[c];
       }
     }
     __syncwarp();   // buffer 1 is free for hypothesis 1
     float best = INFINITY, vel = 0.f, sm = 0.f;
     int best_k = 0;
+    // the frame's scores are only needed after the last hypothesis: requested now, so that their latency hides under the loop
+    float sc_pre[kScorePrefetch];
+    if (kAllTerms && scores) {
+#pragma unroll
+      for (int k = 0; k < kScorePrefetch; ++k)
+        sc_pre[k] = (valid && (uint32_t)k < d.K) ? scores[((size_t)b * d.K + k) * d.T + t0 + lane] : 0.5f;
+    }
     for (uint32_t k = 0; k < d.K; ++k) {
       const int cur = k & 1;
       int sh_next = 0;
@@ -191,13 +211,53 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
       st.wait(cur);
       const float* hp = st.buf[cur] + sh_cur + lane * kF;
 
-      // ---- frame t of hypothesis k: WTA error (exact) + velocity / smoothness of the pair (t, t+1)
+      // ---- frame t of hypothesis k: WTA error (exact) + velocity / smoothness of the pair (t, t+1).  Two joints per instruction
+      // (fma / mul / add.rn.f32x2: every lane of a packed instruction is the IEEE operation of the scalar form, same order).
       float v[kJ];
       float smin = INFINITY, smax = 0.f, vk = 0.f, sk = 0.f;
+      uint64_t skp = 0;
 #pragma unroll
-      for (int j = 0; j < kJ; ++j) {
+      for (int jp = 0; jp < 8; ++jp) {
+        const int j = 2 * jp;
+        const uint64_t W2 = pack_f32x2(w[j], w[j + 1]);
+        const uint64_t H0 = pack_f32x2(hp[3 * j + 0], hp[3 * j + 3]), H1 = pack_f32x2(hp[3 * j + 1], hp[3 * j + 4]),
+                       H2 = pack_f32x2(hp[3 * j + 2], hp[3 * j + 5]);
+        const uint64_t D0 = sub_f32x2(H0, Y[jp][0]), D1 = sub_f32x2(H1, Y[jp][1]), D2 = sub_f32x2(H2, Y[jp][2]);
+        uint64_t S, V;
+        if (kSquared) {
+          const uint64_t Q0 = mul_f32x2(W2, mul_f32x2(D0, D0)), Q1 = mul_f32x2(W2, mul_f32x2(D1, D1)), Q2 = mul_f32x2(W2, mul_f32x2(D2, D2));
+          S = add_f32x2(add_f32x2(Q0, Q1), Q2);
+          const uint64_t q0 = mul_f32x2(S, r3_2);                                   // ieee::div_rn_core, packed
+          V = fma_f32x2(r3_2, fma_f32x2(kNeg3x2, q0, S), q0);
+        } else {
+          S = fma_f32x2(D2, D2, fma_f32x2(D1, D1, mul_f32x2(D0, D0)));
+          float sa, sb;
+          unpack_f32x2(S, sa, sb);
+          const uint64_t RS = pack_f32x2(ieee::mufu_rsq(sa), ieee::mufu_rsq(sb));   // ieee::sqrt_rn_core, packed
+          const uint64_t G = mul_f32x2(S, RS), Hh = mul_f32x2(RS, kHalfx2);
+          const uint64_t R = fma_f32x2(mul_f32x2(G, kNeg1x2), G, S);
+          V = mul_f32x2(W2, fma_f32x2(R, Hh, G));
+        }
+        float sa, sb;
+        unpack_f32x2(S, sa, sb);
+        smin = fminf(smin, fminf(sa, sb));
+        smax = fmaxf(smax, fmaxf(sa, sb));
+        unpack_f32x2(V, v[j], v[j + 1]);
+        if (kAllTerms) {
+          const uint64_t A0 = sub_f32x2(pack_f32x2(hp[kF + 3 * j + 0], hp[kF + 3 * j + 3]), H0),
+                         A1 = sub_f32x2(pack_f32x2(hp[kF + 3 * j + 1], hp[kF + 3 * j + 4]), H1),
+                         A2 = sub_f32x2(pack_f32x2(hp[kF + 3 * j + 2], hp[kF + 3 * j + 5]), H2);   // hypothesis velocity
+          const uint64_t E0 = sub_f32x2(A0, DY[jp][0]), E1 = sub_f32x2(A1, DY[jp][1]), E2 = sub_f32x2(A2, DY[jp][2]);
+          float qa, qb;
+          unpack_f32x2(fma_f32x2(E2, E2, fma_f32x2(E1, E1, mul_f32x2(E0, E0))), qa, qb);
+          vk += kSquared ? qa + qb : sqrt_approx(qa) + sqrt_approx(qb);
+          skp = fma_f32x2(W2, fma_f32x2(A2, A2, fma_f32x2(A1, A1, mul_f32x2(A0, A0))), skp);
+        }
+      }
+      {   // joint 16
+        constexpr int j = 16;
         const float h0 = hp[j * 3 + 0], h1 = hp[j * 3 + 1], h2 = hp[j * 3 + 2];
-        const float d0 = __fsub_rn(h0, yr[j * 3 + 0]), d1 = __fsub_rn(h1, yr[j * 3 + 1]), d2 = __fsub_rn(h2, yr[j * 3 + 2]);
+        const float d0 = __fsub_rn(h0, y16[0]), d1 = __fsub_rn(h1, y16[1]), d2 = __fsub_rn(h2, y16[2]);
         float s;
         if (kSquared) {
           const float q0 = __fmul_rn(w[j], __fmul_rn(d0, d0));
@@ -212,11 +272,11 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
         smin = fminf(smin, s);
         smax = fmaxf(smax, s);
         if (kAllTerms) {
-          const float a0 = hp[kF + j * 3 + 0] - h0, a1 = hp[kF + j * 3 + 1] - h1, a2 = hp[kF + j * 3 + 2] - h2;   // hypothesis velocity
-          const float e0 = a0 - dy[j * 3 + 0], e1 = a1 - dy[j * 3 + 1], e2 = a2 - dy[j * 3 + 2];
+          const float a0 = hp[kF + j * 3 + 0] - h0, a1 = hp[kF + j * 3 + 1] - h1, a2 = hp[kF + j * 3 + 2] - h2;
+          const float e0 = a0 - dy16[0], e1 = a1 - dy16[1], e2 = a2 - dy16[2];
           const float q = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
           vk += kSquared ? q : sqrt_approx(q);
-          sk = fmaf(w[j], fmaf(a2, a2, fmaf(a1, a1, a0 * a0)), sk);
+          sk = fmaf(w[j], fmaf(a2, a2, fmaf(a1, a1, a0 * a0)), sum_f32x2(skp));
         }
       }
       const float tot = sum17_torch_order(v);
@@ -243,7 +303,10 @@ loss_fwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
       wta_val[(size_t)b * d.T + t0 + lane] = best;
       wta_idx[(size_t)b * d.T + t0 + lane] = best_k;
       if (kAllTerms && scores) {
-        for (uint32_t k = 0; k < d.K; ++k) {
+#pragma unroll
+        for (int k = 0; k < kScorePrefetch; ++k)
+          if ((uint32_t)k < d.K) bce -= (k == best_k) ? fmaxf(logf(sc_pre[k]), -100.f) : fmaxf(logf(1.f - sc_pre[k]), -100.f);
+        for (uint32_t k = kScorePrefetch; k < d.K; ++k) {
           const float s = scores[((size_t)b * d.K + k) * d.T + t0 + lane];
           // F.binary_cross_entropy: log terms clamped at -100
           bce -= ((int)k == best_k) ? fmaxf(logf(s), -100.f) : fmaxf(logf(1.f - s), -100.f);
@@ -366,6 +429,8 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
       int sh_next = 0;
       if (k + 1 < d.K)
         sh_next = stage_tile(st.buf[nxt], st.bar[nxt], hyp, (((size_t)b * d.K + k + 1) * d.T + lo) * kF, (hi - lo) * kF, h_total, lane);
+      const size_t si = ((size_t)b * d.K + k) * d.T + (size_t)(writes ? f : 0);
+      const float sck = (writes && grad_scores) ? scores[si] : 0.5f;     // requested before the wait: its latency hides under the tile
       st.wait(cur);
       const float* hc = st.buf[cur] + sh_cur + row * kF;
       const bool winner = writes && (int64_t)k == kstar;
@@ -406,8 +471,7 @@ loss_bwd_kernel(const float* __restrict__ hyp, const float* __restrict__ scores,
         g[j * 3 + 2] = fmaf(r, d2, p2 - f2);
       }
       if (writes && grad_scores) {
-        const size_t si = ((size_t)b * d.K + k) * d.T + f;
-        const float s = scores[si];
+        const float s = sck;
         const float tgt = winner ? 1.f : 0.f;
         // binary_cross_entropy_backward: (input - target) / max((1 - input) * input, 1e-12)
         grad_scores[si] = c_bce * (s - tgt) / fmaxf((1.f - s) * s, 1e-12f);
