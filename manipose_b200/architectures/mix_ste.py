@@ -194,6 +194,9 @@ class _TrunkFn(torch.autograd.Function):
         return None, None, None, None
 
 
+_WGRAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}   # one second stream per device for the weight-gradient GEMMs (MixSTE._train_backward)
+
+
 class MixSTE(nn.Module):
     """mix_ste.py:12-191.  ``forward(x[B,L,J,in_chans]) -> [B,L,J,out_dim]``."""
 
@@ -211,6 +214,16 @@ class MixSTE(nn.Module):
     # accumulator and two fc1 chunk accumulators fill TMEM, so the LayerNorm epilogue cannot overlap the next tile's fc2 (DESIGN.md
     # §5, negative results).  Off by default; kept for A/B measurements (MANIPOSE_FUSE_MLP=1 turns it on).
     fuse_mlp = os.environ.get("MANIPOSE_FUSE_MLP", "0") == "1"
+    # training: weight-gradient GEMMs on a second stream, under the data-gradient kernels that follow them (MANIPOSE_WGRAD_STREAM=0: in line)
+    overlap_wgrad = os.environ.get("MANIPOSE_WGRAD_STREAM", "1") != "0"
+
+    @staticmethod
+    def _side_stream(dev):
+        key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+        st = _WGRAD_STREAMS.get(key)
+        if st is None:
+            st = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=key)
+        return st
 
     def __init__(self, num_frame=243, num_joints=17, in_chans=2, out_dim=3, embed_dim=512, depth=8, num_heads=8, mlp_ratio=2.0,
                  qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.2, norm_layer=None, mup=False):
@@ -531,6 +544,29 @@ class MixSTE(nn.Module):
         dx = dfeat.contiguous().clone()            # fp32 gradient of the residual stream, updated in place below
         dy16, wide16 = b16(c), b16(max(3 * c, hidden))
         flat = wide16.view(-1)
+        # Weight gradients on a second stream.  dgrad and wgrad of a layer read the same output gradient and are independent, and at a few
+        # thousand rows a GEMM leaves SMs idle (13,770 rows = 108 tiles on 74 CTA pairs: two rounds where 1.46 would do): the weight-
+        # gradient kernel of a layer runs under the data-gradient kernels that follow it and fills those SMs.  `wg(...)` returns the event
+        # the main stream waits for before it overwrites a buffer that weight gradient still reads; a block's last one is joined before
+        # its tape entry is released and the reducer hook runs.  Captured in the step's CUDA graph like any fork / join.
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.overlap_wgrad else None
+
+        def wg(dy, act, gw, gb):
+            if side is None:
+                T.wgrad(dy, act, gw, gb)
+                return None
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                T.wgrad(dy, act, gw, gb)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return ev
+
+        def after(ev):
+            if ev is not None:
+                main.wait_event(ev)
+
         for bi in range(len(blocks) - 1, -1, -1):
             blk, wi, mode, post = blocks[bi]
             rec = tape["blocks"][bi]
@@ -547,25 +583,29 @@ class MixSTE(nn.Module):
                 T.cast_rowscale(dx, rec["s2"], dy16)
                 fc2_db = g(blk.mlp.fc2.bias)
             # ---- MLP branch: x2 = x1 + s2 * (fc2(gelu(fc1(norm2(x1))))); dy16 = 16-bit(s2 * dx)
-            T.wgrad(dy16, rec["a"], g(blk.mlp.fc2.weight), fc2_db)
+            e_fc2 = wg(dy16, rec["a"], g(blk.mlp.fc2.weight), fc2_db)
             da = flat[:n_tokens * hidden].view(n_tokens, hidden)
             T.dgrad(dy16, w_t[wi + 3], da)
             T.gelu_bwd(rec["u"], da, da, colsum=g(blk.mlp.fc1.bias))
-            T.wgrad(da, rec["h2"], g(blk.mlp.fc1.weight), None)
+            e_fc1 = wg(da, rec["h2"], g(blk.mlp.fc1.weight), None)
+            after(e_fc2)                               # dy16 is rewritten next
             T.dgrad(da, w_t[wi + 2], dy16)
             # norm2 backward reads dy16 (= d h2) and rewrites it with 16-bit(s1 * dx1), the operand of the attention branch
             T.layernorm_bwd(rec["x1"], blk.norm2.weight, blk.norm2.eps, dy16, dx, dx, g(blk.norm2.weight), g(blk.norm2.bias), dt, dx16=dy16,
                             rowscale=rec["s1"], dx16_colsum=g(blk.attn.proj.bias))
             # ---- attention branch: x1 = x0 + s1 * proj(attention(qkv(norm1(x0))))
-            T.wgrad(dy16, rec["o"], g(blk.attn.proj.weight), None)
+            e_proj = wg(dy16, rec["o"], g(blk.attn.proj.weight), None)
             do = b16(c)
             T.dgrad(dy16, w_t[wi + 1], do)
             dqkv = flat[:n_tokens * 3 * c].view(n_tokens, 3 * c)
             qkv_db = g(blk.attn.qkv.bias) if blk.attn.qkv.bias is not None else None
+            after(e_fc1)                               # dqkv shares its buffer with da
             T.attention_bwd(rec["qkv"], rec["o"], do, dqkv, n_clips, n_frames, n_tok, c, heads, mode, colsum=qkv_db)
-            T.wgrad(dqkv, rec["h1"], g(blk.attn.qkv.weight), None)
+            e_qkv = wg(dqkv, rec["h1"], g(blk.attn.qkv.weight), None)
+            after(e_proj)                              # dy16 is rewritten next
             T.dgrad(dqkv, w_t[wi + 0], dy16)
             T.layernorm_bwd(rec["x0"], blk.norm1.weight, blk.norm1.eps, dy16, dx, dx, g(blk.norm1.weight), g(blk.norm1.bias), dt)
+            after(e_qkv)                               # the block's gradients are complete; its activations may go
             rec.clear()
             hook = getattr(self, "_on_block_grads", None)
             if hook is not None:
