@@ -4,6 +4,7 @@
 ``forward(x[B,L,17,2]) -> (poses[B,K,L,17,3], scores[B,K,L,1])`` — same names, kwargs and return types as the
 reference so it drops in under hpe/main_h36m_lifting.py, hpe/main_3dhp.py and hpe/eval_utils.py.
 """
+import os
 from typing import Optional
 
 import torch
@@ -158,8 +159,22 @@ class RMCLRotMixSTE(MixSTE):
         return rot, ops.softmax_hyp(logits).unsqueeze(-1)
 
 
+_BRANCH_STREAMS = {}
+
+
+def _branch_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    st = _BRANCH_STREAMS.get(key)
+    if st is None:
+        st = _BRANCH_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
 class RMCLManifoldMixSTE(ManifoldMixSTE):
     """rmcl_manifold_mix_ste.py:15-185."""
+
+    # training: the bone-length backbone runs on a second stream, concurrently with the rotations backbone
+    overlap_branches = os.environ.get("MANIPOSE_BRANCH_STREAM", "1") != "0"
 
     def __init__(self, skeleton, num_frame: int = 243, num_joints: int = 17, num_bones: int = 16, in_chans: int = 2,
                  rot_rep_dim: int = 6, embed_dim_rot: int = 512, depth_rot: int = 8, num_heads_rot: int = 8, embed_dim_seg: int = 128,
@@ -191,8 +206,19 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
         dev = x.device
         if rm._grad_mode() or sm._grad_mode():
             # differentiable path (training): whole batch at once, activations kept for the backward sweep
-            rot, logits = rm.hypotheses_with_grad(x)
-            bones = sm.bone_lengths_with_grad(x)
+            if self.overlap_branches:
+                # the bone-length backbone (C = 128: ~150 short kernels) on its own stream, under the rotations backbone; autograd runs
+                # its backward on that stream too.  MANIPOSE_BRANCH_STREAM=0: one after the other.
+                main, side = torch.cuda.current_stream(dev), _branch_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    bones = sm.bone_lengths_with_grad(x)
+                rot, logits = rm.hypotheses_with_grad(x)
+                main.wait_stream(side)
+                bones.record_stream(main)
+            else:
+                rot, logits = rm.hypotheses_with_grad(x)
+                bones = sm.bone_lengths_with_grad(x)
             poses = ops.decode(rot.reshape(b * k * l, j, d), bones, None, b, k, l, d, self.decoder.exact).view(b, k, l, j, 3)
             return poses, ops.softmax_hyp(logits.contiguous()).unsqueeze(-1)
         poses = torch.empty((b, k, l, j, 3), dtype=torch.float32, device=dev)
