@@ -230,12 +230,23 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
                              torch.empty((mb, sm.num_bones), dtype=torch.float32, device=dev))
         rot, logits, bones = self._scratch
         lib = L.load()
+        main = torch.cuda.current_stream(dev)
+        side = _branch_stream(dev) if self.overlap_branches else None
         for s in range(0, b, mb):
             n = min(mb, b - s)
             xs = x[s:s + n]
-            rm.hypotheses_into(xs, n, rot[:n], logits[:n])
-            with ops.nvtx("manipose.segments"):
-                sm.bone_lengths_into(xs, n, bones[:n])
+            if side is not None:
+                # the bone-length backbone of this micro-batch on the second stream (after the previous micro-batch's decoder, which
+                # reads `bones`), under the rotations backbone; joined before the decoder
+                side.wait_stream(main)
+                with torch.cuda.stream(side), ops.nvtx("manipose.segments"):
+                    sm.bone_lengths_into(xs, n, bones[:n])
+                rm.hypotheses_into(xs, n, rot[:n], logits[:n])
+                main.wait_stream(side)
+            else:
+                rm.hypotheses_into(xs, n, rot[:n], logits[:n])
+                with ops.nvtx("manipose.segments"):
+                    sm.bone_lengths_into(xs, n, bones[:n])
             with ops.nvtx("manipose.decoder"):
                 rc = lib.mp_decoder_fwd(L.ptr(rot), L.ptr(bones), None, L.ptr(logits), L.ptr(poses[s:s + n]), L.ptr(scores[s:s + n]),
                                         n, k, l, d, L.MP_DEC_EXACT if self.decoder.exact else L.MP_DEC_FAST, L.stream_ptr())
