@@ -180,3 +180,30 @@ def test_backward_vs_oracle_autograd(n_clips, k, t):
     torch.testing.assert_close(r.grad.cpu(), r_ref.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(b.grad.cpu(), b_ref.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(tt.grad.cpu(), t_ref.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_clips,k,t", [(37, 5, 243), (9, 1, 7), (3, 2, 50)])
+def test_backward_bone_length_sums_are_deterministic(n_clips, k, t):
+    """grad_bone_len is a per-clip sum over K * T poses: partial rows per warp tile + a fixed-order reduction, so two runs agree bit for
+    bit (round 1 used atomics), also when a 32-pose tile straddles several clips (K * T = 7: up to 5 clips per tile); and it equals the
+    fp64 sum of per-pose gradients taken one clip at a time."""
+    from manipose_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    n = n_clips * k * t
+    rot = torch.randn(n, 17, 6, generator=gen, device="cuda")
+    bones = 0.1 + 0.4 * torch.rand(n_clips, 16, generator=gen, device="cuda")
+    gout = torch.randn(n, 17, 3, generator=gen, device="cuda")
+    grads = []
+    for _ in range(3):
+        r, b = rot.clone().requires_grad_(), bones.clone().requires_grad_()
+        ops.decode(r, b, None, n_clips, k, t).backward(gout)
+        grads.append((r.grad.clone(), b.grad.clone()))
+    for gr, gb in grads[1:]:
+        assert torch.equal(gr, grads[0][0]) and torch.equal(gb, grads[0][1])
+    # one clip at a time (every clip then starts at tile 0: a different tiling of the same sums)
+    for c in (0, n_clips // 2, n_clips - 1):
+        r = rot[c * k * t:(c + 1) * k * t].clone().requires_grad_()
+        b = bones[c:c + 1].clone().requires_grad_()
+        ops.decode(r, b, None, 1, k, t).backward(gout[c * k * t:(c + 1) * k * t])
+        torch.testing.assert_close(grads[0][1][c], b.grad[0], rtol=2e-5, atol=2e-5 * float(b.grad.abs().max()))
+        assert torch.equal(grads[0][0][c * k * t:(c + 1) * k * t], r.grad)

@@ -436,3 +436,83 @@ def test_captured_train_step_matches_eager_steps():
     step(xs[0], ys[0])
     torch.cuda.synchronize()
     assert not torch.equal(o2.flat.flat_param, before)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_heads_training_kernels_vs_torch(dtype):
+    """FoldedHeadsFn (mp_heads_fold -> mp_heads_fwd16; mp_heads_bwd_pack -> wgrad / dgrad -> mp_heads_unfold) against the K separate
+    LayerNorm + Linear + score heads in fp32 torch on the same normalised 16-bit input: outputs, input gradient, every parameter gradient."""
+    import manipose_b200 as mb
+    from manipose_b200 import train_ops as T
+    td = DT[dtype]
+    torch.manual_seed(3)
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=9, n_hyp=5).cuda().set_compute_dtype(dtype)
+    heads = list(model.rotations_module.head)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    with torch.no_grad():
+        for h in heads:
+            for p in h.parameters():
+                p.add_(0.05 * torch.randn(p.shape, generator=gen, device="cuda"))
+    b, l, j, c, d = 3, 9, 17, 512, model.rotations_module.out_dim
+    yhat = torch.randn(b * l * j, c, generator=gen, device="cuda").to(td)
+    g_rot = torch.randn(b, 5, l, j, d, generator=gen, device="cuda")
+    g_log = torch.randn(b, 5, l, generator=gen, device="cuda")
+    # fp32 reference: LN_k(y) = yhat * gamma_k + beta_k (yhat already normalised), prediction Linear, score Linear over the joints
+    yref = yhat.float().requires_grad_()
+    rots, logs = [], []
+    for h in heads:
+        z = yref * h.norm.weight + h.norm.bias
+        out = (z @ h.prediction_head.weight.t() + h.prediction_head.bias).reshape(b, l, j, d + 1)
+        rots.append(out[..., :d])
+        logs.append((out[..., d] * h.score_head.weight.reshape(1, 1, j)).sum(-1) + h.score_head.bias)
+    rot_ref, log_ref = torch.stack(rots, 1), torch.stack(logs, 1)
+    params = [p for h in heads for p in h.parameters()]
+    ref_grads = torch.autograd.grad([rot_ref, log_ref], [yref] + params, [g_rot, g_log])
+    for p in params:
+        p.grad = None
+    yin = yhat.clone().requires_grad_()
+    rot, logits = T.FoldedHeadsFn.apply(yin, heads, b, l, j, d, heads[0].norm.weight)
+    torch.autograd.backward([rot, logits], [g_rot, g_log])
+    tol = RTOL[dtype]
+    torch.testing.assert_close(rot, rot_ref.detach(), rtol=4 * tol, atol=4 * tol)
+    torch.testing.assert_close(logits, log_ref.detach(), rtol=4 * tol, atol=8 * tol)
+    rel = lambda a, r: float((a.float() - r).norm() / r.norm().clamp_min(1e-20))
+    assert rel(yin.grad, ref_grads[0]) <= 3 * tol
+    for p, gr in zip(params, ref_grads[1:]):
+        assert rel(p.grad, gr) <= 3 * tol, (tuple(p.shape), rel(p.grad, gr))
+
+
+def test_backward_streams_do_not_change_the_gradients():
+    """Weight gradients on the second stream / the bone-length backbone on its own stream: same kernels, same inputs, so the same
+    gradients as the in-line order (up to the order of the fp32 atomics of the bias / LayerNorm parameter sums)."""
+    import manipose_b200 as mb
+    from manipose_b200 import metrics
+    from manipose_b200.architectures import mix_ste
+    torch.manual_seed(0)
+    model = mb.RMCLManifoldMixSTE(mb.h36m17_skeleton(), num_frame=27, n_hyp=5, drop_path_rate=0.0).cuda().train().set_compute_dtype("bf16")
+    gen = torch.Generator().manual_seed(1)
+    x = (0.3 * torch.randn(6, 27, 17, 2, generator=gen)).cuda()
+    y = (0.3 * torch.randn(6, 27, 17, 3, generator=gen)).cuda()
+
+    def grads(overlap):
+        mix_ste.MixSTE.overlap_wgrad = overlap
+        type(model).overlap_branches = overlap
+        for p in model.parameters():
+            p.grad = None
+        loss, _ = metrics.losses.training_loss(*model(x), y)
+        loss.backward()
+        torch.cuda.synchronize()
+        return float(loss.detach()), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    was = (mix_ste.MixSTE.overlap_wgrad, type(model).overlap_branches)
+    try:
+        l0, g0 = grads(False)
+        l1, g1 = grads(True)
+        l2, g2 = grads(True)
+    finally:
+        mix_ste.MixSTE.overlap_wgrad, type(model).overlap_branches = was
+    assert l0 == l1 == l2
+    for n in g0:
+        for g in (g1, g2):
+            err = float((g[n] - g0[n]).norm() / g0[n].norm().clamp_min(1e-20))
+            assert err <= 1e-5, (n, err)
