@@ -40,6 +40,10 @@ int mp_abi_version(void);
 const char* mp_last_error(void);
 /* 0 if the current CUDA device is sm_100 (B200), MP_EDEVICE otherwise. */
 int mp_device_check(void);
+/* Persistent kernels size their grids from min(SMs of the device, `sms`); 0 = no limit (the default). Two callers that drive two
+ * streams (two micro-batches in flight) give each the half of the device it can fill, so that a tensor-bound launch of one
+ * runs beside an HBM-bound launch of the other. Process-wide, read at launch time. Returns the previous limit (>= 0). */
+int mp_set_sm_limit(int sms);
 
 /* Skeleton tables (hpe/mh_so3_hpe/data/skeleton.py:7-172, t_pose_operators from
  * hpe/mh_so3_hpe/data/h36m_lifting.py:40-57).  The kernels are specialised at compile time for the

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mp_abi_version": (I, []),
     "mp_last_error": (c_char_p, []),
     "mp_device_check": (I, []),
+    "mp_set_sm_limit": (I, [I]),
     "mp_set_skeleton": (I, [I, ctypes.POINTER(c_int32), ctypes.POINTER(c_float)]),
     "mp_decoder_fwd": (I, [P, P, P, P, P, P, I64, I64, I64, I, I, P]),
     "mp_decoder_bwd_workspace_bytes": (c_size_t, [I64, I64, I64]),

@@ -50,7 +50,12 @@ int require_sm100() {
   return MP_OK;
 }
 
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+static int g_sm_limit = 0;   // mp_set_sm_limit: persistent grids are sized from min(SMs of the device, limit)
+
+int sm_count() {
+  const int sms = g_sm_count > 0 ? g_sm_count : 148;
+  return g_sm_limit > 0 && g_sm_limit < sms ? g_sm_limit : sms;
+}
 
 template <typename D>
 __global__ void cast_f32_16_kernel(const float* __restrict__ src, typename D::T* __restrict__ dst, int64_t n) {
@@ -78,6 +83,13 @@ int mp_abi_version(void) { return MP_ABI_VERSION; }
 const char* mp_last_error(void) { return mp::g_err; }
 
 int mp_device_check(void) { return mp::require_sm100(); }
+
+int mp_set_sm_limit(int sms) {
+  MP_REQUIRE(sms >= 0 && sms % 2 == 0, MP_EINVAL, "mp_set_sm_limit: %d is not 0 or an even number of SMs", sms);
+  const int before = mp::g_sm_limit;
+  mp::g_sm_limit = sms;
+  return before;
+}
 
 int mp_set_skeleton(int num_joints, const int32_t* parents, const float* ops) {
   MP_REQUIRE(parents != nullptr && ops != nullptr, MP_EINVAL, "mp_set_skeleton: null table");
