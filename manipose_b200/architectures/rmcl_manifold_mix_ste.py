@@ -162,11 +162,11 @@ class RMCLRotMixSTE(MixSTE):
 _BRANCH_STREAMS = {}
 
 
-def _branch_stream(dev):
+def _branch_stream(dev, priority: int = 0):
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-    st = _BRANCH_STREAMS.get(key)
+    st = _BRANCH_STREAMS.get((key, priority))
     if st is None:
-        st = _BRANCH_STREAMS[key] = torch.cuda.Stream(device=key)
+        st = _BRANCH_STREAMS[(key, priority)] = torch.cuda.Stream(device=key, priority=priority)
     return st
 
 
@@ -175,6 +175,9 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
 
     # training: the bone-length backbone runs on a second stream, concurrently with the rotations backbone
     overlap_branches = os.environ.get("MANIPOSE_BRANCH_STREAM", "1") != "0"
+    # inference: the rotations backbone on a HIGH-priority stream of its own, so that its persistent kernels (one CTA per SM, statically
+    # assigned tiles: a CTA that starts late delays the whole launch) are placed before the pending CTAs of the bone-length stream
+    trunk_priority = os.environ.get("MANIPOSE_TRUNK_PRIORITY", "0") != "0"
 
     def __init__(self, skeleton, num_frame: int = 243, num_joints: int = 17, num_bones: int = 16, in_chans: int = 2,
                  rot_rep_dim: int = 6, embed_dim_rot: int = 512, depth_rot: int = 8, num_heads_rot: int = 8, embed_dim_seg: int = 128,
@@ -229,9 +232,22 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
                              torch.empty((mb, k, l), dtype=torch.float32, device=dev),
                              torch.empty((mb, sm.num_bones), dtype=torch.float32, device=dev))
         rot, logits, bones = self._scratch
-        lib = L.load()
-        main = torch.cuda.current_stream(dev)
+        caller = torch.cuda.current_stream(dev)
         side = _branch_stream(dev) if self.overlap_branches else None
+        if side is not None and self.trunk_priority:
+            main = _branch_stream(dev, -1)
+            main.wait_stream(caller)
+            with torch.cuda.stream(main):
+                self._lift_micro_batches(x, b, mb, main, side, rot, logits, bones, poses, scores)
+            caller.wait_stream(main)
+        else:
+            self._lift_micro_batches(x, b, mb, caller, side, rot, logits, bones, poses, scores)
+        return poses, scores
+
+    def _lift_micro_batches(self, x, b, mb, main, side, rot, logits, bones, poses, scores) -> None:
+        rm, sm = self.rotations_module, self.segments_module
+        k, l, d = self.n_hyp, rm.num_frame, rm.out_dim
+        lib = L.load()
         for s in range(0, b, mb):
             n = min(mb, b - s)
             xs = x[s:s + n]
@@ -251,7 +267,6 @@ class RMCLManifoldMixSTE(ManifoldMixSTE):
                 rc = lib.mp_decoder_fwd(L.ptr(rot), L.ptr(bones), None, L.ptr(logits), L.ptr(poses[s:s + n]), L.ptr(scores[s:s + n]),
                                         n, k, l, d, L.MP_DEC_EXACT if self.decoder.exact else L.MP_DEC_FAST, L.stream_ptr())
                 L.check(rc, "mp_decoder_fwd")
-        return poses, scores
 
     def concat_hyp_and_scores(self, hypothesis: torch.Tensor, scores: torch.Tensor) -> torch.Tensor:
         """rmcl_manifold_mix_ste.py:108-119 -> [B,K,L,J,4]."""

@@ -61,6 +61,112 @@ layernorm_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, uint
   }
 }
 
+// C = 128 (the bone-length backbone): FOUR tokens per warp.  Lane = 8 * sub + l8 owns the 16-byte chunks i * 8 + l8 (i = 0 .. 3) of
+// token `sub` of the warp's group, so a load instruction covers 4 x 128 contiguous bytes, the row statistics are 3-step butterflies
+// over 8 lanes (5 steps over 32 with one token per warp) and a warp has 2 KB in flight instead of 512 B: the one-token-per-warp
+// kernel ran at half the byte floor (115 us per launch at 497,664 tokens), bound by its dependent shuffle chains.
+struct Row128x4 {
+  __device__ static __forceinline__ float sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+  }
+  __device__ static __forceinline__ void load(const float* __restrict__ row, int l8, float4 (&a)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(row + (i * 8 + l8) * 4);
+  }
+  __device__ static __forceinline__ void stats(const float4 (&a)[4], float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += (a[i].x + a[i].y) + (a[i].z + a[i].w);
+    mean = sum8(s) * (1.0f / 128);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d0 = a[i].x - mean, d1 = a[i].y - mean, d2 = a[i].z - mean, d3 = a[i].w - mean;
+      q = fmaf(d0, d0, q);
+      q = fmaf(d1, d1, q);
+      q = fmaf(d2, d2, q);
+      q = fmaf(d3, d3, q);
+    }
+    rstd = rsqrtf(sum8(q) * (1.0f / 128) + eps);
+  }
+  // g, b: [128] in shared memory
+  __device__ static __forceinline__ void normalize(float4 (&a)[4], float mean, float rstd, const float* g, const float* b, int l8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 gg = *reinterpret_cast<const float4*>(g + (i * 8 + l8) * 4), bb = *reinterpret_cast<const float4*>(b + (i * 8 + l8) * 4);
+      a[i].x = fmaf((a[i].x - mean) * rstd, gg.x, bb.x);
+      a[i].y = fmaf((a[i].y - mean) * rstd, gg.y, bb.y);
+      a[i].z = fmaf((a[i].z - mean) * rstd, gg.z, bb.z);
+      a[i].w = fmaf((a[i].w - mean) * rstd, gg.w, bb.w);
+    }
+  }
+};
+
+template <typename D, bool kPost>
+__global__ void __launch_bounds__(kTokWarps * 32)
+layernorm128_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, uint16_t* __restrict__ h_out,
+                    const float* __restrict__ post_g, const float* __restrict__ post_b, float post_eps, const float* __restrict__ pos,
+                    int64_t pos_div, int64_t pos_mod, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
+                    int64_t n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(16) float prm[4][128];
+  if (threadIdx.x < 128) {
+    prm[0][threadIdx.x] = kPost ? post_g[threadIdx.x] : 1.f;
+    prm[1][threadIdx.x] = kPost ? post_b[threadIdx.x] : 0.f;
+    prm[2][threadIdx.x] = ln_g[threadIdx.x];
+    prm[3][threadIdx.x] = ln_b[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
+  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps * 4;
+  for (int64_t tok = warp_global * 4 + sub; tok - sub < n_tokens; tok += stride) {
+    const bool ok = tok < n_tokens;
+    float4 a[4];
+    if (ok) {
+      Row128x4::load(x_in + tok * 128, l8, a);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mean, rstd;
+    if (kPost) {
+      Row128x4::stats(a, post_eps, mean, rstd);
+      Row128x4::normalize(a, mean, rstd, prm[0], prm[1], l8);
+      if (pos != nullptr && ok) {
+        const float* pe = pos + ((tok / pos_div) % pos_mod) * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(pe + (i * 8 + l8) * 4));
+          a[i].x += p.x;
+          a[i].y += p.y;
+          a[i].z += p.z;
+          a[i].w += p.w;
+        }
+      }
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(x_out + tok * 128 + (i * 8 + l8) * 4) = a[i];
+      }
+    }
+    Row128x4::stats(a, ln_eps, mean, rstd);
+    Row128x4::normalize(a, mean, rstd, prm[2], prm[3], l8);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint2 u;
+        u.x = D::pack2(a[i].x, a[i].y);
+        u.y = D::pack2(a[i].z, a[i].w);
+        *reinterpret_cast<uint2*>(h_out + tok * 128 + (i * 8 + l8) * 4) = u;
+      }
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------- joint embedding
 // x[tok, c] = W[c,0] in0 + W[c,1] in1 + b[c] + spos[tok % J, c]; h = LN(x)          (C = 512)
 template <typename D>
@@ -100,10 +206,15 @@ embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W,
 
 // -------------------------------------------------------------------------------------------------- segment embedding
 // per frame: in[34] -> [16 segments x 128]; a CTA owns ONE segment (its 128 x 34 weight slice lives transposed in
-// shared memory) and streams frames; token = frame * 16 + segment.
+// shared memory) and streams frames; token = frame * 16 + segment.  A warp takes kSegFrames consecutive frames at a time: their
+// inputs (kSegFrames x in_features contiguous floats) are staged transposed in shared memory, so one 16-byte weight read per lane and
+// two broadcast reads of the inputs feed 4 channels x 8 frames = 32 FMAs (one frame per pass re-read the whole weight slice for every
+// frame and was bound by shared-memory bandwidth: 507 us per 128-clip micro-batch, 205 us now).  The
+// accumulation order per output (bias, then features 0 .. in_features-1, then the position embedding) is unchanged.
 constexpr int kSegC = 128;
+constexpr int kSegFrames = 8;
 template <typename D>
-__global__ void __launch_bounds__(kTokWarps * 32)
+__global__ void __launch_bounds__(kTokWarps * 32, 3)
 embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
                       const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                       float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_frames, int in_features,
@@ -111,7 +222,7 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
   pdl_launch_dependents();
   pdl_wait();
   using R = Row<kSegC>;
-  extern __shared__ __align__(16) float wt[];  // [in_features][128]
+  extern __shared__ __align__(16) float wt[];  // [in_features][128], then per warp [in_features][kSegFrames]
   const int seg = blockIdx.y;
   for (int i = threadIdx.x; i < in_features * kSegC; i += blockDim.x) {
     const int c = i % kSegC, f = i / kSegC;
@@ -119,34 +230,88 @@ embed_segments_kernel(const float* __restrict__ in2d, const float* __restrict__ 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  float* xs = wt + in_features * kSegC + (threadIdx.x >> 5) * (in_features * kSegFrames);
   float bb[R::kPer], pe[R::kPer], lg[R::kPer], lb[R::kPer];
   R::load_f32(bias + seg * kSegC, lane, bb);
   R::load_f32(spos + seg * kSegC, lane, pe);
   R::load_f32(ln_g, lane, lg);
   R::load_f32(ln_b, lane, lb);
+  const int64_t n_groups = (n_frames + kSegFrames - 1) / kSegFrames;
   const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
   const int64_t stride = (int64_t)gridDim.x * kTokWarps;
-  for (int64_t fr = warp_global; fr < n_frames; fr += stride) {
-    const float* in = in2d + fr * in_features;
-    float v[R::kPer];
+  const int per_group = kSegFrames * in_features;
+  for (int64_t grp = warp_global; grp < n_groups; grp += stride) {
+    const int64_t fr0 = grp * kSegFrames;
+    const int valid = (int)(n_frames - fr0 < kSegFrames ? n_frames - fr0 : kSegFrames);
+    const float* in = in2d + fr0 * in_features;
+    __syncwarp();                                   // the previous group's reads of xs are done
+    for (int e = lane; e < per_group; e += 32) {
+      const int fr = e / in_features, f = e - fr * in_features;
+      xs[f * kSegFrames + fr] = fr < valid ? __ldg(in + e) : 0.f;
+    }
+    __syncwarp();
+    // (packed fp32 FMAs on inputs stored twice were tried here: 16 instead of 32 FMA instructions per feature, but 12 instead of 8
+    // shared-memory wavefronts - 240 us against 205 us; the loop waits for its shared-memory reads, not for issue slots)
+    float v[kSegFrames][R::kPer];
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) v[i] = bb[i];
+    for (int r = 0; r < kSegFrames; ++r)
+#pragma unroll
+      for (int i = 0; i < R::kPer; ++i) v[r][i] = bb[i];
+#pragma unroll 2
     for (int f = 0; f < in_features; ++f) {
-      const float xin = __ldg(in + f);
       const float4 wv = *reinterpret_cast<const float4*>(wt + f * kSegC + lane * 4);
-      v[0] = fmaf(wv.x, xin, v[0]);
-      v[1] = fmaf(wv.y, xin, v[1]);
-      v[2] = fmaf(wv.z, xin, v[2]);
-      v[3] = fmaf(wv.w, xin, v[3]);
+      const float4 xa = *reinterpret_cast<const float4*>(xs + f * kSegFrames);
+      const float4 xb = *reinterpret_cast<const float4*>(xs + f * kSegFrames + 4);
+      const float xin[kSegFrames] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int r = 0; r < kSegFrames; ++r) {
+        v[r][0] = fmaf(wv.x, xin[r], v[r][0]);
+        v[r][1] = fmaf(wv.y, xin[r], v[r][1]);
+        v[r][2] = fmaf(wv.z, xin[r], v[r][2]);
+        v[r][3] = fmaf(wv.w, xin[r], v[r][3]);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) v[i] += pe[i];
-    const int64_t tok = fr * n_segments + seg;
-    R::store_x(x_out + tok * kSegC, lane, v);
-    float mean, rstd;
-    R::stats(v, ln_eps, mean, rstd);
-    R::normalize(v, mean, rstd, lg, lb);
-    R::template store_h<D>(h_out + tok * kSegC, lane, v);
+    for (int r = 0; r < kSegFrames; ++r) {
+      if (r < valid) {
+#pragma unroll
+        for (int i = 0; i < R::kPer; ++i) v[r][i] += pe[i];
+        const int64_t tok = (fr0 + r) * n_segments + seg;
+        R::store_x(x_out + tok * kSegC, lane, v[r]);
+      }
+    }
+    // the LayerNorm statistics of the kSegFrames rows together: independent shuffle chains
+    float s[kSegFrames], mean[kSegFrames];
+#pragma unroll
+    for (int r = 0; r < kSegFrames; ++r) s[r] = (v[r][0] + v[r][1]) + (v[r][2] + v[r][3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kSegFrames; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < kSegFrames; ++r) {
+      mean[r] = s[r] * (1.0f / kSegC);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < R::kPer; ++i) {
+        const float d = v[r][i] - mean[r];
+        q = fmaf(d, d, q);
+      }
+      s[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kSegFrames; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+#pragma unroll
+    for (int r = 0; r < kSegFrames; ++r) {
+      if (r < valid) {
+        const float rstd = rsqrtf(s[r] * (1.0f / kSegC) + ln_eps);
+        R::normalize(v[r], mean[r], rstd, lg, lb);
+        const int64_t tok = (fr0 + r) * n_segments + seg;
+        R::template store_h<D>(h_out + tok * kSegC, lane, v[r]);
+      }
+    }
   }
 }
 
@@ -304,28 +469,44 @@ bones_value_kernel(const float* __restrict__ x, const float* __restrict__ post_g
                    float* __restrict__ values, int64_t n_tokens) {
   pdl_launch_dependents();
   pdl_wait();
-  using R = Row<kSegC>;
-  const int lane = threadIdx.x & 31;
-  float pg[R::kPer], pb[R::kPer], g[R::kPer], bt[R::kPer], w[R::kPer];
-  R::load_f32(post_g, lane, pg);
-  R::load_f32(post_b, lane, pb);
-  R::load_f32(hg, lane, g);
-  R::load_f32(hb, lane, bt);
-  R::load_f32(hw, lane, w);
+  __shared__ __align__(16) float prm[5][128];
+  if (threadIdx.x < 128) {
+    prm[0][threadIdx.x] = post_g[threadIdx.x];
+    prm[1][threadIdx.x] = post_b[threadIdx.x];
+    prm[2][threadIdx.x] = hg[threadIdx.x];
+    prm[3][threadIdx.x] = hb[threadIdx.x];
+    prm[4][threadIdx.x] = hw[threadIdx.x];
+  }
+  __syncthreads();
+  // four tokens per warp (Row128x4): five 3-step butterflies per token instead of five 5-step ones
+  const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
   const float b0 = hbias[0];
-  for (int64_t tok = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5); tok < n_tokens; tok += (int64_t)gridDim.x * kTokWarps) {
-    float v[R::kPer];
-    R::load_x(x + tok * kSegC, lane, v);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps * 4;
+  for (int64_t tok = ((int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5)) * 4 + sub; tok - sub < n_tokens; tok += stride) {
+    const bool ok = tok < n_tokens;
+    float4 a[4];
+    if (ok) {
+      Row128x4::load(x + tok * 128, l8, a);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float mean, rstd;
-    R::stats(v, post_eps, mean, rstd);
-    R::normalize(v, mean, rstd, pg, pb);
-    R::stats(v, 1e-5f, mean, rstd);
-    R::normalize(v, mean, rstd, g, bt);
+    Row128x4::stats(a, post_eps, mean, rstd);
+    Row128x4::normalize(a, mean, rstd, prm[0], prm[1], l8);
+    Row128x4::stats(a, 1e-5f, mean, rstd);
+    Row128x4::normalize(a, mean, rstd, prm[2], prm[3], l8);
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) acc = fmaf(v[i], w[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) values[tok] = acc + b0;
+    for (int i = 0; i < 4; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(prm[4] + (i * 8 + l8) * 4);
+      acc = fmaf(a[i].x, w.x, acc);
+      acc = fmaf(a[i].y, w.y, acc);
+      acc = fmaf(a[i].z, w.z, acc);
+      acc = fmaf(a[i].w, w.w, acc);
+    }
+    acc = Row128x4::sum8(acc);
+    if (l8 == 0 && ok) values[tok] = acc + b0;
   }
 }
 __global__ void bones_mean_kernel(const float* __restrict__ values, float* __restrict__ bone_len, int64_t n_clips, int n_frames, int n_seg) {
@@ -405,6 +586,19 @@ int mp_layernorm(const float* x_in, float* x_out, void* h_out, const float* post
                                                               pos_div, pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
+  if (C == 128 && ln_gamma != nullptr && h_out != nullptr && (post_gamma == nullptr || x_out != nullptr)) {
+    const int grid4 = token_grid((n_tokens + 3) / 4);
+    auto launch4 = [&](auto kernel) {
+      launch_k(kernel, grid4, kTokWarps * 32, 0, (cudaStream_t)stream, x_in, x_out, (uint16_t*)h_out, post_gamma, post_beta, post_eps, pos_embed,
+                                                                 pos_div, pos_mod, ln_gamma, ln_beta, ln_eps, n_tokens);
+    };
+    if (post_gamma != nullptr) {
+      if (bf) launch4(layernorm128_kernel<Bf16, true>); else launch4(layernorm128_kernel<Fp16, true>);
+    } else {
+      if (bf) launch4(layernorm128_kernel<Bf16, false>); else launch4(layernorm128_kernel<Fp16, false>);
+    }
+    return check_launch("layernorm128_kernel");
+  }
   if (C == 512) {
     if (bf) launch(layernorm_kernel<512, Bf16>); else launch(layernorm_kernel<512, Fp16>);
   } else {
@@ -443,11 +637,14 @@ int mp_embed_segments(const float* in2d, const float* W, const float* b, const f
   MP_REQUIRE(in_features >= 1 && in_features <= 128 && n_segments >= 1 && n_segments <= 64, MP_EINVAL, "mp_embed_segments: bad sizes");
   MP_REQUIRE(aligned16(x_out) && aligned16(h_out), MP_EALIGN, "mp_embed_segments: x_out / h_out must be 16-byte aligned");
   if (n_frames == 0) return MP_OK;
-  const size_t smem = (size_t)in_features * kSegC * sizeof(float);
-  int gx = (int)((n_frames + kTokWarps - 1) / kTokWarps);
-  const int cap = sm_count() * 2 / n_segments + 1;
+  const size_t smem = (size_t)in_features * (kSegC + kTokWarps * kSegFrames) * sizeof(float);
+  const int64_t n_groups = (n_frames + kSegFrames - 1) / kSegFrames;
+  int gx = (int)((n_groups + kTokWarps - 1) / kTokWarps);
+  int cap = sm_count() * 3 / n_segments;   // three resident CTAs per SM (80 registers): one wave
+  if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(kernel, dim3(gx, n_segments), kTokWarps * 32, smem, (cudaStream_t)stream, in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
                                                                                  (uint16_t*)h_out, n_frames, in_features, n_segments);
   };
@@ -517,7 +714,7 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
   MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * sizeof(float), MP_EWORKSPACE, "mp_bones_head: workspace too small");
   if (n_tokens == 0) return MP_OK;
   float* values = reinterpret_cast<float*>(workspace);
-  launch_k(bones_value_kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
+  launch_k(bones_value_kernel, token_grid((n_tokens + 3) / 4), kTokWarps * 32, 0, (cudaStream_t)stream, x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
                                                                                          values, n_tokens);
   MP_CHECK(check_launch("bones_value_kernel"));
   const int64_t n_out = n_clips * n_segments;
