@@ -509,16 +509,28 @@ bones_value_kernel(const float* __restrict__ x, const float* __restrict__ post_g
     if (l8 == 0 && ok) values[tok] = acc + b0;
   }
 }
-__global__ void bones_mean_kernel(const float* __restrict__ values, float* __restrict__ bone_len, int64_t n_clips, int n_frames, int n_seg) {
+// one CTA per clip: thread (tl, s) adds the frames tl, tl + lanes, ... of segment s (coalesced rows of n_seg values), the partial
+// sums are combined in a fixed order (deterministic).  (One thread per (clip, segment) walking all the frames: 28 us of dependent loads.)
+__global__ void __launch_bounds__(256) bones_mean_kernel(const float* __restrict__ values, float* __restrict__ bone_len, int64_t n_clips,
+                                                         int n_frames, int n_seg) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_clips * n_seg) return;
-  const int64_t b = i / n_seg;
-  const int s = (int)(i - b * n_seg);
+  __shared__ float part[256];
+  const int64_t b = blockIdx.x;
+  const int lanes = 256 / n_seg;                 // n_seg <= 64
+  const int s = threadIdx.x % n_seg, tl = threadIdx.x / n_seg;
   float acc = 0.f;
-  for (int t = 0; t < n_frames; ++t) acc += values[(b * n_frames + t) * n_seg + s];
-  bone_len[i] = acc / (float)n_frames;
+  if (tl < lanes) {
+    const float* v = values + b * n_frames * n_seg + s;
+    for (int t = tl; t < n_frames; t += lanes) acc += v[(int64_t)t * n_seg];
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < n_seg) {
+    float tot = 0.f;
+    for (int l = 0; l < lanes; ++l) tot += part[l * n_seg + threadIdx.x];
+    bone_len[b * n_seg + threadIdx.x] = tot / (float)n_frames;
+  }
 }
 
 // K heads, second half of the tensor-core path (mp_heads_fwd16): y [frames * 17, ld] fp32 holds, per token, the K * (D + 1) outputs of the
@@ -710,6 +722,7 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
   MP_REQUIRE(C == kSegC, MP_EUNSUPPORTED, "mp_bones_head: C=%d (built for 128)", C);
   MP_REQUIRE(x && post_gamma && post_beta && hg && hb && hw && hbias && bone_len && workspace, MP_EINVAL, "mp_bones_head: null pointer");
   MP_REQUIRE(aligned16(x), MP_EALIGN, "mp_bones_head: x must be 16-byte aligned");
+  MP_REQUIRE(n_segments >= 1 && n_segments <= 64 && n_clips < ((int64_t)1 << 31), MP_EINVAL, "mp_bones_head: bad sizes (1 <= n_segments <= 64)");
   const int64_t n_tokens = n_clips * n_frames * n_segments;
   MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * sizeof(float), MP_EWORKSPACE, "mp_bones_head: workspace too small");
   if (n_tokens == 0) return MP_OK;
@@ -717,8 +730,7 @@ int mp_bones_head(const float* x, const float* post_gamma, const float* post_bet
   launch_k(bones_value_kernel, token_grid((n_tokens + 3) / 4), kTokWarps * 32, 0, (cudaStream_t)stream, x, post_gamma, post_beta, post_eps, hg, hb, hw, hbias,
                                                                                          values, n_tokens);
   MP_CHECK(check_launch("bones_value_kernel"));
-  const int64_t n_out = n_clips * n_segments;
-  launch_k(bones_mean_kernel, (int)((n_out + 127) / 128), 128, 0, (cudaStream_t)stream, values, bone_len, n_clips, (int)n_frames, n_segments);
+  launch_k(bones_mean_kernel, (int)n_clips, 256, 0, (cudaStream_t)stream, values, bone_len, n_clips, (int)n_frames, n_segments);
   return check_launch("bones_mean_kernel");
 }
 
