@@ -1292,7 +1292,7 @@ pair_linear_ln64_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 }
 
 constexpr int pair_ln64_smem(int stages, int load) { return stages * kStage64 + (4 * load + 4) * kBox64 + 512 + 4 * kRows64 * 8; }
-static_assert(pair_ln64_smem(3, 2) <= 232448 && pair_ln64_smem(2, 3) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+static_assert(pair_ln64_smem(3, 2) <= 232448 && pair_ln64_smem(2, 3) <= 232448 && pair_ln64_smem(4, 1) <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
 constexpr int kPairLinearSmem = 1024 + 5 * (kABytes + kWHalfBytes) + kSlots * kBoxBytes + 512;
 constexpr int pair_ln_smem(int stages, int slots, bool split) { return stages * (kABytes + (split ? 1 : 2) * kWHalfBytes) + slots * kBoxBytes + 256 + 2 * kBM * 8; }
@@ -1415,7 +1415,7 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
   // bandwidth; the 128-row split-accumulation kernel: 580 us), fc2 + post-norm + norm1 750 us (5.05 TB/s = 0.78; the 128-row kernel:
   // 942 us).  MANIPOSE_LN_CFG = 5: 2 stages + 3 residual slots (slower: 602 / 891 us); 1 / 2 / 3: the 128-row kernels (split /
   // single accumulation / 2 stages + 8 slots), kept for A/B measurements.
-  if (cfg == 0 || cfg == 4 || cfg == 5) {
+  if (cfg == 0 || cfg == 4 || cfg == 5 || cfg == 6) {
     CUtensorMap ta6, tr6, tx6, th6, tp6;
     MP_CHECK(get_tmap(&ta6, A, M, K, kRows64, dtype));
     MP_CHECK(get_tmap(&tr6, resid, M, N, kRows64, 2));
@@ -1437,6 +1437,8 @@ extern "C" int mp_linear_ln(const void* A, const void* W, const float* bias, con
       launch_k(kernel, grid64, kThreads, smem_bytes, (cudaStream_t)stream, ta6, tw, tr6, tx6, th6, tp6, args, (int)M, (int)K);
       return check_launch("pair_linear_ln64_kernel");
     };
+    if (cfg == 6)   // 4 operand stages + ONE residual slot per column group: slower (608 / 774 us against 539 / 729 us)
+      return bf ? launch64(pair_linear_ln64_kernel<Bf16, 4, 1>, pair_ln64_smem(4, 1)) : launch64(pair_linear_ln64_kernel<Fp16, 4, 1>, pair_ln64_smem(4, 1));
     if (cfg == 5)
       return bf ? launch64(pair_linear_ln64_kernel<Bf16, 2, 3>, pair_ln64_smem(2, 3)) : launch64(pair_linear_ln64_kernel<Fp16, 2, 3>, pair_ln64_smem(2, 3));
     return bf ? launch64(pair_linear_ln64_kernel<Bf16, 3, 2>, pair_ln64_smem(3, 2)) : launch64(pair_linear_ln64_kernel<Fp16, 3, 2>, pair_ln64_smem(3, 2));

@@ -357,6 +357,46 @@ def test_layernorm_family(c, dtype):
     assert torch.equal(xi, xo)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_bone_backbone_kernels_ragged_sizes(dtype):
+    """The C = 128 kernels work on groups (four tokens per warp, eight frames per warp pass in the segment embedding): token and
+    frame counts that are not multiples of the group sizes, against torch fp32 (manifold_mix_ste.py:139-154, mix_ste.py:123-126)."""
+    from manipose_b200 import ops
+    td, code = DT[dtype], ops.DTYPE_CODE[dtype]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    r = lambda *sh: torch.randn(*sh, generator=gen, device="cuda")
+    c, n_seg = 128, 16
+    for n_clips, n_frames in ((1, 1), (3, 13), (2, 27)):
+        frames = n_clips * n_frames
+        n = frames * n_seg
+        # segment embedding + position embedding + norm1
+        x2d, w, b, spos = 0.3 * r(frames, 34), r(n_seg * c, 34) / 6.0, 0.1 * r(n_seg * c), 0.02 * r(n_seg, c)
+        lg, lb = 1.0 + 0.1 * r(c), 0.1 * r(c)
+        x = torch.full((n + 8, c), 7.0, device="cuda")            # guard rows: nothing may be written past the last token
+        h = torch.full((n + 8, c), 7.0, dtype=td, device="cuda")
+        ops.embed_segments(x2d, w, b, spos.reshape(-1), lg, lb, 1e-6, x, h, frames, 34, n_seg, c, code)
+        want = (F.linear(x2d, w, b).view(frames, n_seg, c) + spos).reshape(n, c)
+        torch.testing.assert_close(x[:n], want, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(h[:n].float(), F.layer_norm(want, (c,), lg, lb, 1e-6), rtol=RTOL[dtype], atol=RTOL[dtype])
+        assert bool((x[n:] == 7.0).all()) and bool((h[n:].float() == 7.0).all())
+        # bone-length head on the same activations
+        pg, pb, hg, hb, hw, hbias = 1.0 + 0.1 * r(c), 0.1 * r(c), 1.0 + 0.1 * r(c), 0.1 * r(c), r(c) / 11.0, 0.1 * r(1)
+        bone = torch.empty(n_clips, n_seg, device="cuda")
+        ws = torch.empty(n, device="cuda")
+        ops.bones_head(x[:n], pg, pb, 1e-6, hg, hb, hw, hbias, bone, n_clips, n_frames, n_seg, c, ws)
+        y = F.layer_norm(F.layer_norm(want, (c,), pg, pb, 1e-6), (c,), hg, hb, 1e-5)
+        wb = (y @ hw + hbias).view(n_clips, n_frames, n_seg).mean(1)
+        torch.testing.assert_close(bone, wb, rtol=1e-4, atol=1e-5)
+    # LayerNorm on token counts 4 k + 1 .. 4 k + 3
+    for n in (1, 6, 431):
+        xin = r(n, c) * 2 + 0.5
+        lg, lb = r(c), r(c)
+        h = torch.full((n + 4, c), 7.0, dtype=td, device="cuda")
+        ops.layernorm(xin, None, h, ln=(lg, lb), ln_eps=1e-6, dtype=code)
+        torch.testing.assert_close(h[:n].float(), F.layer_norm(xin, (c,), lg, lb, 1e-6), rtol=RTOL[dtype], atol=RTOL[dtype])
+        assert bool((h[n:].float() == 7.0).all())
+
+
 def _sd_to(sd, dev):
     return {k: v.to(dev) for k, v in sd.items()}
 
