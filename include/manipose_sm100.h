@@ -225,7 +225,8 @@ int mp_heads_fwd(const float* x, const float* post_gamma, const float* post_beta
 /* The same K heads on the tensor cores (the C = 512 model): xhat [n_frames_total*17, 512] 16-bit is the input ALREADY through
  * Temporal_norm and the affine-free LayerNorm(eps 1e-5) the K heads share (mp_linear_ln writes it as its h output), wf16 [n_pad, 512]
  * 16-bit / bf [n_pad] fp32 the folded parameters (row k*(D+1)+o: gamma_k (.) W_k[o], W_k[o] . beta_k + b_k[o]; rows past K*(D+1) zero):
- * one tcgen05 GEMM with fp32 output into `workspace` ([tokens, n_pad] fp32), then the scatter into rot / the score dot product. */
+ * one tcgen05 GEMM with fp32 output into `workspace` (room for [tokens, n_pad] fp32; only the K*(D+1) useful columns are written, as a dense
+ * [tokens, ld] matrix), then the scatter into rot / the score dot product. */
 int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const float* score_w, const float* score_b, float* rot,
                    float* logits, float* workspace, size_t workspace_bytes, int64_t n_clips, int64_t n_frames, int n_hyp, int out_dim,
                    int with_score, int n_pad, int dtype, mp_stream_t stream);

@@ -13,6 +13,10 @@
 #include "row.cuh"
 
 namespace mp {
+int linear_f32_visible(const void* A, const void* W, const float* bias, float* Y, int64_t M, int64_t N, int64_t K, int64_t visible_cols,
+                       int64_t pitch_cols, int dtype, cudaStream_t s);   // gemm.cu
+}
+namespace mp {
 namespace {
 
 
@@ -544,25 +548,31 @@ heads_finish_kernel(const float* __restrict__ y, int ld, const float* __restrict
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
-  float* tile = sm + (size_t)warp * kJ * KO;          // [17][KO]
+  const int O = out_dim + (with_score ? 1 : 0);
+  const int row_floats = kJ * ld;                     // the frame's 17 rows are one contiguous run of the intermediate (ld % 4 == 0)
+  float* tile = sm + (size_t)warp * row_floats;       // [17][ld]
+  // index math once per launch, not per frame: element i of a head's [17 x out_dim] block comes from tile[(i / out_dim) * ld + i % out_dim]
+  constexpr int kIt = (kJ * 6 + 31) / 32;             // out_dim <= 6
+  int src[kIt];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int i = it * 32 + lane;
+    src[it] = i < kJ * out_dim ? (i / out_dim) * ld + i % out_dim : -1;
+  }
   const int64_t total_frames = n_clips * n_frames;
   for (int64_t fr = (int64_t)blockIdx.x * kTokWarps + warp; fr < total_frames; fr += (int64_t)gridDim.x * kTokWarps) {
     const int64_t b = fr / n_frames;
     const int t = (int)(fr - b * n_frames);
-    for (int i = lane; i < kJ * KO; i += 32) {
-      const int j = i / KO, c = i - j * KO;
-      tile[i] = y[(fr * kJ + j) * ld + c];
-    }
+    const float4* yrow = reinterpret_cast<const float4*>(y + fr * row_floats);
+    for (int i = lane; i < row_floats / 4; i += 32) reinterpret_cast<float4*>(tile)[i] = yrow[i];
     __syncwarp();
     for (int k = 0; k < n_hyp; ++k) {
       float* dst = rot + (((b * n_hyp + k) * n_frames + t) * kJ) * out_dim;
-      for (int i = lane; i < kJ * out_dim; i += 32) {
-        const int j = i / out_dim, o = i - j * out_dim;
-        dst[i] = tile[j * KO + k * O + o];
-      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it)
+        if (src[it] >= 0) dst[it * 32 + lane] = tile[src[it] + k * O];
       if (with_score) {
-        float acc = lane < kJ ? score_w[k * kJ + lane] * tile[lane * KO + k * O + out_dim] : 0.f;
+        float acc = lane < kJ ? score_w[k * kJ + lane] * tile[lane * ld + k * O + out_dim] : 0.f;
         acc = warp_sum(acc);
         if (lane == 0) logits[(b * n_hyp + k) * n_frames + t] = acc + score_b[k];
       }
@@ -694,6 +704,7 @@ int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const 
   using namespace mp;
   MP_CHECK(require_sm100());
   MP_REQUIRE(xhat16 && wf16 && bf && rot && workspace, MP_EINVAL, "mp_heads_fwd16: null pointer");
+  MP_REQUIRE(aligned16(workspace) && aligned16(xhat16) && aligned16(wf16), MP_EALIGN, "mp_heads_fwd16: xhat16 / wf16 / workspace must be 16-byte aligned");
   MP_REQUIRE(!with_score || (score_w && score_b && logits), MP_EINVAL, "mp_heads_fwd16: score head pointers required");
   MP_REQUIRE(n_hyp >= 1 && n_hyp <= 16 && (out_dim == 6 || out_dim == 4 || out_dim == 3), MP_EINVAL, "mp_heads_fwd16: bad n_hyp/out_dim");
   const int O = out_dim + (with_score ? 1 : 0), KO = n_hyp * O;
@@ -702,14 +713,23 @@ int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const 
   const int64_t n_tokens = n_clips * n_frames * kJ;
   MP_REQUIRE(workspace_bytes >= (size_t)n_tokens * n_pad * sizeof(float), MP_EWORKSPACE, "mp_heads_fwd16: workspace too small");
   if (n_clips == 0) return MP_OK;
-  MP_CHECK(mp_linear(xhat16, wf16, bf, nullptr, workspace, n_tokens, n_pad, kHeadC, MP_EPI_BIAS_F32, dtype, stream));
-  const size_t smem = (size_t)kTokWarps * kJ * KO * sizeof(float);
+  // only the KO useful columns of the projection are written, as a dense [tokens, ld] fp32 matrix (ld = KO rounded up to 16 bytes), and read
+  // back by the scatter kernel; MANIPOSE_HEADS_FULL_STORE=1 writes whole n_pad-column rows (A/B)
+  static const bool full_store = getenv("MANIPOSE_HEADS_FULL_STORE") != nullptr;
+  int ld = n_pad;
+  if (n_pad == 128 && !full_store) {
+    ld = (KO + 3) & ~3;
+    MP_CHECK(linear_f32_visible(xhat16, wf16, bf, workspace, n_tokens, n_pad, kHeadC, KO, ld, dtype, (cudaStream_t)stream));
+  } else {
+    MP_CHECK(mp_linear(xhat16, wf16, bf, nullptr, workspace, n_tokens, n_pad, kHeadC, MP_EPI_BIAS_F32, dtype, stream));
+  }
+  const size_t smem = (size_t)kTokWarps * kJ * ld * sizeof(float);
   MP_REQUIRE(smem <= 200 * 1024, MP_EUNSUPPORTED, "mp_heads_fwd16: n_hyp=%d needs %zu bytes of shared memory", n_hyp, smem);
   cudaFuncSetAttribute(heads_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t ctas = (n_clips * n_frames + kTokWarps - 1) / kTokWarps;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (ctas > cap) ctas = cap;
-  launch_k(heads_finish_kernel, (int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream, workspace, n_pad, score_w, score_b, rot, logits, n_clips,
+  launch_k(heads_finish_kernel, (int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream, workspace, ld, score_w, score_b, rot, logits, n_clips,
                                                                                  (int)n_frames, n_hyp, out_dim, with_score);
   return check_launch("heads_finish_kernel");
 }

@@ -356,23 +356,28 @@ static EncodeTiledFn encode_fn() {
 
 struct TmapKey {
   const void* ptr;
-  int64_t rows, cols;
+  int64_t rows, cols, pitch;
   int box_rows, type;
-  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && type == o.type; }
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows && type == o.type;
+  }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.box_rows * 31 + (size_t)k.type;
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (size_t)k.pitch * 0x165667B19E3779F9ull +
+         (size_t)k.box_rows * 31 + (size_t)k.type;
     return h;
   }
 };
 
 // Dense row-major [rows, cols]; box = box_rows x 128 bytes of columns, 128-byte swizzle, OOB reads -> 0, OOB writes dropped.
 // type: 0 = bf16, 1 = fp16, 2 = fp32.  Descriptors are pure functions of the key, so they are memoised per host thread.
-int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type) {
+// pitch_cols > 0: rows are pitch_cols elements apart and only the first `cols` of them are visible (stores past them are dropped).
+int get_tmap_pitch(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type, int64_t pitch_cols) {
   thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  const TmapKey key{ptr, rows, cols, box_rows, type};
+  if (pitch_cols <= 0) pitch_cols = cols;
+  const TmapKey key{ptr, rows, cols, pitch_cols, box_rows, type};
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -382,7 +387,7 @@ int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int 
   MP_REQUIRE(fn != nullptr, MP_EDEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   const int esz = type == 2 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_cols * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = type == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (type == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
@@ -393,6 +398,9 @@ int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int 
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, *out);
   return MP_OK;
+}
+int get_tmap(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int type) {
+  return get_tmap_pitch(out, ptr, rows, cols, box_rows, type, 0);
 }
 
 // 4-D view [clips][frames][tokens][cols] of a 16-bit activation (cols fastest) with a box of `box_frames` frames of ONE token and
@@ -503,6 +511,26 @@ int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap
 }
 
 }  // namespace
+}  // namespace mp
+
+// Y[M, N] fp32 = A W^T + bias of which only the first `visible_cols` columns of every row are written (the K hypothesis heads: 35 useful
+// outputs in a 128-column block; the tensor map of Y drops the rest of each store and packs the rows `pitch_cols` floats apart, so the
+// intermediate is a dense [M, pitch_cols] matrix: 144 instead of 512 bytes per token).
+namespace mp {
+int linear_f32_visible(const void* A, const void* W, const float* bias, float* Y, int64_t M, int64_t N, int64_t K, int64_t visible_cols,
+                       int64_t pitch_cols, int dtype, cudaStream_t s) {
+  MP_REQUIRE(N == 128 && K >= 64 && K % 64 == 0 && visible_cols >= 1 && visible_cols <= pitch_cols && pitch_cols <= N && pitch_cols % 4 == 0 &&
+                 M >= 0 && M < ((int64_t)1 << 31), MP_EINVAL,
+             "linear_f32_visible: unsupported shape M=%lld N=%lld K=%lld visible=%lld pitch=%lld", (long long)M, (long long)N, (long long)K,
+             (long long)visible_cols, (long long)pitch_cols);
+  if (M == 0) return MP_OK;
+  CUtensorMap ta, tw, ty;
+  MP_CHECK(get_tmap(&ta, A, M, K, kBM, dtype));
+  MP_CHECK(get_tmap(&tw, W, N, K, 128, dtype));
+  MP_CHECK(get_tmap_pitch(&ty, Y, M, visible_cols, kBM, 2, pitch_cols));
+  if (dtype == MP_DTYPE_BF16) return launch_linear<128, MP_EPI_BIAS_F32, Bf16>(ta, tw, ty, ty, bias, (int)M, (int)N, (int)K, s);
+  return launch_linear<128, MP_EPI_BIAS_F32, Fp16>(ta, tw, ty, ty, bias, (int)M, (int)N, (int)K, s);
+}
 }  // namespace mp
 
 extern "C" int mp_linear(const void* A, const void* W, const float* bias, const float* resid, void* Y, int64_t M, int64_t N, int64_t K,
