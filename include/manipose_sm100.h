@@ -320,8 +320,8 @@ int mp_colsum16(const void* src, float* colsum, int64_t M, int64_t C, int dtype,
  * prediction_head.bias [D+1], score_head.weight [17], score_head.bias [1]}.
  *   mp_heads_fold      the folded Linear of mp_heads_fwd16: wf16 [n_pad, C] (and its transpose wt16 [C, n_pad], may be NULL), bf [n_pad],
  *                      plus the stacked score weights score_w [K, 17] / score_b [K]
- *   mp_heads_bwd_pack  dY [tokens, n_pad] 16-bit from d_rot [B,K,T,17,D] and d_logits [B,K,T] (y: the fp32 GEMM output mp_heads_fwd16 left
- *                      in its workspace); dbf [n_pad] += column sums of dY; score_head gradients are accumulated through `grads`
+ *   mp_heads_bwd_pack  dY [tokens, n_pad] 16-bit from d_rot [B,K,T,17,D] and d_logits [B,K,T] (y: the workspace of the mp_heads_fwd16 call of the
+ *                      same shape, i.e. its fp32 GEMM output in the layout that call left it in); dbf [n_pad] += column sums of dY; score_head gradients are accumulated through `grads`
  *   mp_heads_unfold    dWf [n_pad, C] (= mp_wgrad(dY, xhat)) and dbf -> the heads' norm / prediction_head gradients, accumulated */
 int mp_heads_fold(const int64_t* params, int n_hyp, int out_dim, int C, int n_pad, void* wf16, void* wt16, float* bf, float* score_w,
                   float* score_b, int dtype, mp_stream_t stream);

@@ -715,10 +715,8 @@ int mp_heads_fwd16(const void* xhat16, const void* wf16, const float* bf, const 
   if (n_clips == 0) return MP_OK;
   // only the KO useful columns of the projection are written, as a dense [tokens, ld] fp32 matrix (ld = KO rounded up to 16 bytes), and read
   // back by the scatter kernel; MANIPOSE_HEADS_FULL_STORE=1 writes whole n_pad-column rows (A/B)
-  static const bool full_store = getenv("MANIPOSE_HEADS_FULL_STORE") != nullptr;
-  int ld = n_pad;
-  if (n_pad == 128 && !full_store) {
-    ld = (KO + 3) & ~3;
+  const int ld = heads_ws_ld(n_hyp, out_dim, with_score, n_pad);
+  if (ld != n_pad) {
     MP_CHECK(linear_f32_visible(xhat16, wf16, bf, workspace, n_tokens, n_pad, kHeadC, KO, ld, dtype, (cudaStream_t)stream));
   } else {
     MP_CHECK(mp_linear(xhat16, wf16, bf, nullptr, workspace, n_tokens, n_pad, kHeadC, MP_EPI_BIAS_F32, dtype, stream));

@@ -1,5 +1,6 @@
 // Shared host/device helpers for libmanipose_sm100.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -51,6 +52,13 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// Pitch (in floats) of the fp32 intermediate that mp_heads_fwd16 leaves in its workspace and mp_heads_bwd_pack reads back: the K * (D + 1)
+// useful columns of the folded projection as a dense matrix (rows padded to 16 bytes); MANIPOSE_HEADS_FULL_STORE=1: whole n_pad-column rows.
+inline int heads_ws_ld(int n_hyp, int out_dim, int with_score, int n_pad) {
+  static const bool full_store = getenv("MANIPOSE_HEADS_FULL_STORE") != nullptr;
+  const int ko = n_hyp * (out_dim + (with_score ? 1 : 0));
+  return (n_pad == 128 && !full_store) ? ((ko + 3) & ~3) : n_pad;
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -67,7 +67,7 @@ template <typename D>
 __global__ void __launch_bounds__(128)
 heads_bwd_pack_kernel(const float* __restrict__ d_rot, const float* __restrict__ d_logits, const float* __restrict__ y, const float* __restrict__ sw,
                       uint16_t* __restrict__ dy16, float* __restrict__ dbf, const int64_t* __restrict__ grads, int64_t n_clips, int n_frames, int n_hyp,
-                      int out_dim, int n_pad, int64_t frames_per_cta) {
+                      int out_dim, int n_pad, int y_ld, int64_t frames_per_cta) {
   pdl_launch_dependents();
   pdl_wait();
   const int d1 = out_dim + 1;
@@ -96,7 +96,7 @@ heads_bwd_pack_kernel(const float* __restrict__ d_rot, const float* __restrict__
         float v = 0.f;
         if (score) {
           v = dl * swk[j];
-          gsw[j] = fmaf(dl, y[m * n_pad + r], gsw[j]);
+          gsw[j] = fmaf(dl, y[m * y_ld + r], gsw[j]);
         } else if (used) {
           v = d_rot[(hk * kJ + j) * out_dim + d];
         }
@@ -173,7 +173,7 @@ int mp_heads_bwd_pack(const float* d_rot, const float* d_logits, const float* y,
   ctas = (frames + per - 1) / per;
   auto launch = [&](auto kernel) {
     launch_k(kernel, (unsigned)ctas, 128, 0, (cudaStream_t)stream, d_rot, d_logits, y, score_w, (uint16_t*)dy16, dbf, grads, n_clips, (int)n_frames, n_hyp,
-             out_dim, n_pad, per);
+             out_dim, n_pad, heads_ws_ld(n_hyp, out_dim, 1, n_pad), per);
   };
   if (dtype == MP_DTYPE_BF16) launch(heads_bwd_pack_kernel<Bf16>); else launch(heads_bwd_pack_kernel<Fp16>);
   return check_launch("heads_bwd_pack_kernel");

@@ -37,7 +37,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   pdl_launch_dependents();
   pdl_wait();
   using R = Row<C>;
-  __shared__ float acc[3][C];
+  extern __shared__ __align__(16) float part[];   // [kLnBwdWarps][3][C] partial column sums (the tail of the kernel)
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kLnBwdWarps + (threadIdx.x >> 5);
   const int64_t stride = (int64_t)gridDim.x * kLnBwdWarps;
@@ -99,27 +99,31 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
   }
   if (dgamma || dx16_colsum) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      acc[0][c] = 0.f;
-      acc[1][c] = 0.f;
-      acc[2][c] = 0.f;
-    }
-    __syncthreads();
+    // every warp's partial column sums as rows of shared memory, added over the warps in a fixed order by the column's thread, then ONE
+    // fp32 reduction per column and CTA.  (atomicAdd on shared floats compiles to compare-and-swap loops: with 12 warps on the same 512
+    // words they were a third of this kernel's time, ncu: ATOMS.CAST.SPIN retried 6.5 times on average.)
+    const int w = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < R::kPer; ++i) {
-      if (dgamma) {
-        atomicAdd(&acc[0][R::chan(lane, i)], ag[i]);
-        atomicAdd(&acc[1][R::chan(lane, i)], ab[i]);
-      }
-      if (dx16_colsum) atomicAdd(&acc[2][R::chan(lane, i)], ac[i]);
+      const int c = R::chan(lane, i);
+      part[(w * 3 + 0) * C + c] = ag[i];
+      part[(w * 3 + 1) * C + c] = ab[i];
+      part[(w * 3 + 2) * C + c] = ac[i];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dgamma) {
-        atomicAdd(dgamma + c, acc[0][c]);
-        atomicAdd(dbeta + c, acc[1][c]);
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kLnBwdWarps; ++ww) {
+        t0 += part[(ww * 3 + 0) * C + c];
+        t1 += part[(ww * 3 + 1) * C + c];
+        t2 += part[(ww * 3 + 2) * C + c];
       }
-      if (dx16_colsum) atomicAdd(dx16_colsum + c, acc[2][c]);
+      if (dgamma) {
+        atomicAdd(dgamma + c, t0);
+        atomicAdd(dbeta + c, t1);
+      }
+      if (dx16_colsum) atomicAdd(dx16_colsum + c, t2);
     }
   }
 }
@@ -754,8 +758,10 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   // one CTA per SM (every CTA ends with up to 3 C atomics on the same words); few rows: one per warp
   int64_t ctas = (n_tokens + kLnBwdWarps - 1) / kLnBwdWarps;
   const int grid = (int)(ctas < sm_count() ? ctas : sm_count());
+  const int smem = kLnBwdWarps * 3 * C * (int)sizeof(float);
   auto launch = [&](auto kernel) {
-    launch_k(kernel, grid, kLnBwdWarps * 32, 0, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, dx16_colsum,
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    launch_k(kernel, grid, kLnBwdWarps * 32, smem, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale, dx16_colsum,
              n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
