@@ -128,6 +128,138 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
+// C = 512 with the rows staged through shared memory by bulk copies.  The kernel above keeps ONE row ahead in registers (two for x / dy would
+// not fit in 168 registers) and still waits for its loads at the top of every row (ncu: 40 % of the loop's stall samples on the first use of
+// dy and dres).  Here every warp owns a ring of kLnRing row slots (x | dy | dres, 5 - 6 KB each); lane 0 requests the row kLnRing - 1
+// iterations ahead with cp.async.bulk (completion on the slot's mbarrier) right after the warp has read a slot into registers, so the loads
+// of the next rows are in flight during the whole of a row's reductions.  The partial column sums of the kernel's tail reuse the ring.
+constexpr int kLnRing = 3;
+template <bool kDy16>
+constexpr int ln_ring_slot_bytes() { return 2048 + (kDy16 ? 1024 : 2048) + 2048; }
+
+template <bool kDy16, typename D>
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
+layernorm_bwd_ring_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float eps, const void* dy, const float* dres, float* dx,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, uint16_t* dx16, const float* __restrict__ rowscale,
+                          float* __restrict__ dx16_colsum, int64_t n_tokens) {   // dx may alias dres, dx16 may alias dy
+  constexpr int C = 512;
+  constexpr int kSlot = ln_ring_slot_bytes<kDy16>();
+  constexpr int kDyBytes = kDy16 ? 1024 : 2048;
+  pdl_launch_dependents();
+  using R = Row<C>;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  float* part = reinterpret_cast<float*>(ring_raw);                              // [kLnBwdWarps][3][C] after the loop
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint8_t* ring = ring_raw + (size_t)w * kLnRing * kSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + (size_t)kLnBwdWarps * kLnRing * kSlot) + w * kLnRing;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLnRing; ++s) ptx::mbar_init(&bars[s], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  pdl_wait();
+  const int64_t warp_global = (int64_t)blockIdx.x * kLnBwdWarps + w;
+  const int64_t stride = (int64_t)gridDim.x * kLnBwdWarps;
+  const uint32_t row_bytes = 2048u + (uint32_t)kDyBytes + (dres ? 2048u : 0u);
+  auto request = [&](int64_t tok, int slot) {        // lane 0
+    uint8_t* sl = ring + slot * kSlot;
+    ptx::mbar_expect_tx(&bars[slot], row_bytes);
+    ptx::bulk_g2s(sl, x + tok * C, 2048, &bars[slot]);
+    ptx::bulk_g2s(sl + 2048, reinterpret_cast<const uint8_t*>(dy) + tok * kDyBytes, kDyBytes, &bars[slot]);
+    if (dres) ptx::bulk_g2s(sl + 2048 + kDyBytes, dres + tok * C, 2048, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLnRing - 1; ++s)
+      if (warp_global + s * stride < n_tokens) request(warp_global + s * stride, s);
+  }
+  float g[R::kPer], ag[R::kPer], ab[R::kPer], ac[R::kPer];
+#pragma unroll
+  for (int i = 0; i < R::kPer; ++i) {
+    g[i] = 1.f;
+    ag[i] = 0.f;
+    ab[i] = 0.f;
+    ac[i] = 0.f;
+  }
+  if (gamma) R::load_f32(gamma, lane, g);
+  uint32_t n = 0;
+  for (int64_t tok = warp_global; tok < n_tokens; tok += stride, ++n) {
+    const int slot = (int)(n % kLnRing);
+    // the row kLnRing - 1 iterations ahead goes into the slot the PREVIOUS iteration has read (all lanes are past their reads: __syncwarp below)
+    if (lane == 0 && tok + (kLnRing - 1) * stride < n_tokens) request(tok + (kLnRing - 1) * stride, (int)((n + kLnRing - 1) % kLnRing));
+    ptx::mbar_wait(&bars[slot], (n / kLnRing) & 1);
+    const uint8_t* sl = ring + slot * kSlot;
+    float v[R::kPer], d[R::kPer], r[R::kPer];
+    R::load_x(reinterpret_cast<const float*>(sl), lane, v);
+    if (kDy16)
+      R::template load_h<D>(reinterpret_cast<const uint16_t*>(sl + 2048), lane, d);
+    else
+      R::load_x(reinterpret_cast<const float*>(sl + 2048), lane, d);
+    if (dres) {
+      R::load_x(reinterpret_cast<const float*>(sl + 2048 + kDyBytes), lane, r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < R::kPer; ++i) r[i] = 0.f;
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();                                   // the slot may be refilled by the next iteration's request
+    float mean, rstd;
+    R::stats(v, eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) {
+      const float xh = (v[i] - mean) * rstd;
+      ag[i] = fmaf(d[i], xh, ag[i]);
+      ab[i] += d[i];
+      const float gi = d[i] * g[i];
+      s1 += gi;
+      s2 = fmaf(gi, xh, s2);
+      v[i] = xh;
+      d[i] = gi;
+    }
+    s1 = warp_sum(s1) * (1.0f / C);
+    s2 = warp_sum(s2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2) + r[i];
+    R::store_x(dx + tok * C, lane, d);
+    if (dx16) {
+      const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
+#pragma unroll
+      for (int i = 0; i < R::kPer; ++i) {
+        d[i] *= sc;
+        ac[i] += d[i];
+      }
+      R::template store_h<D>(dx16 + tok * C, lane, d);
+    }
+  }
+  if (dgamma || dx16_colsum) {
+    __syncthreads();                                // every warp has consumed all the rows it requested: the ring is free
+#pragma unroll
+    for (int i = 0; i < R::kPer; ++i) {
+      const int c = R::chan(lane, i);
+      part[(w * 3 + 0) * C + c] = ag[i];
+      part[(w * 3 + 1) * C + c] = ab[i];
+      part[(w * 3 + 2) * C + c] = ac[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kLnBwdWarps; ++ww) {
+        t0 += part[(ww * 3 + 0) * C + c];
+        t1 += part[(ww * 3 + 1) * C + c];
+        t2 += part[(ww * 3 + 2) * C + c];
+      }
+      if (dgamma) {
+        atomicAdd(dgamma + c, t0);
+        atomicAdd(dbeta + c, t1);
+      }
+      if (dx16_colsum) atomicAdd(dx16_colsum + c, t2);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------- GELU (training forward / backward)
 // Phi(x) from the same erfc fit as gelu_erf; gelu'(x) = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_grad(float x) {
@@ -700,27 +832,57 @@ cast_rowscale_kernel(const float* __restrict__ g, const float* __restrict__ s, u
 // -------------------------------------------------------------------------------------------------- Adam (torch.optim.Adam semantics)
 // step_dev != NULL: the step count lives on the device (value before this step; adam_bump_kernel increments it afterwards), so a
 // captured CUDA graph of the training step advances the bias correction on every replay.
+__device__ __forceinline__ void adam_one(float& pi, float g, float& mi, float& vi, float lr_bc1, float beta1, float beta2, float eps,
+                                         float weight_decay, float bc2_sqrt, float grad_scale) {
+  const float gi = fmaf(weight_decay, pi, g * grad_scale);
+  mi = fmaf(beta1, mi, (1.f - beta1) * gi);
+  vi = fmaf(beta2, vi, (1.f - beta2) * gi * gi);
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi = pi - lr_bc1 * (mi / denom);
+}
+// Four parameters per thread and pass (16-byte loads and stores: 7 memory instructions per 4 parameters instead of 28; the buffers are the
+// flat parameter / gradient / moment buffers, 16-byte aligned), the bias corrections computed by ONE thread per CTA.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
                                                    float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev,
                                                    const float* __restrict__ lr_dev) {
   pdl_launch_dependents();
   pdl_wait();
-  if (lr_dev) lr = *lr_dev;      // the learning rate of a captured step lives on the device too (schedulers change it between replays)
-  if (step_dev) {
-    const double t = (double)(*step_dev + 1);
-    bc1 = (float)(1.0 - pow((double)beta1, t));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    if (lr_dev) lr = *lr_dev;      // the learning rate of a captured step lives on the device too (schedulers change it between replays)
+    if (step_dev) {
+      const double t = (double)(*step_dev + 1);
+      bc1 = (float)(1.0 - pow((double)beta1, t));
+      bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
+    sh[0] = lr / bc1;
+    sh[1] = bc2_sqrt;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float pi = p[i];
-    const float gi = fmaf(weight_decay, pi, g[i] * grad_scale);
-    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
-    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+  __syncthreads();
+  const float lr_bc1 = sh[0];
+  bc2_sqrt = sh[1];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t q = tid; q < n4; q += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[q];
+    const float4 gg = reinterpret_cast<const float4*>(g)[q];
+    float4 mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    adam_one(pp.x, gg.x, mm.x, vv.x, lr_bc1, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+    adam_one(pp.y, gg.y, mm.y, vv.y, lr_bc1, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+    adam_one(pp.z, gg.z, mm.z, vv.z, lr_bc1, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+    adam_one(pp.w, gg.w, mm.w, vv.w, lr_bc1, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+    reinterpret_cast<float4*>(m)[q] = mm;
+    reinterpret_cast<float4*>(v)[q] = vv;
+    reinterpret_cast<float4*>(p)[q] = pp;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_one(pi, g[i], mi, vi, lr_bc1, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+    p[i] = pi;
   }
 }
 
@@ -765,6 +927,24 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
              n_tokens);
   };
   const bool bf = dtype == MP_DTYPE_BF16;
+  // C = 512: rows staged through per-warp shared-memory rings by bulk copies (MANIPOSE_LNBWD_RING=0: the register-prefetch kernel, A/B)
+  static const bool ring = !(getenv("MANIPOSE_LNBWD_RING") && atoi(getenv("MANIPOSE_LNBWD_RING")) == 0);
+  if (C == 512 && ring) {
+    auto launch_ring = [&](auto kernel, int slot_bytes) {
+      const int bytes = kLnBwdWarps * kLnRing * slot_bytes + kLnBwdWarps * kLnRing * 8;
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      launch_k(kernel, grid, kLnBwdWarps * 32, bytes, (cudaStream_t)stream, x, gamma, eps, dy, dres, dx, dgamma, dbeta, (uint16_t*)dx16, rowscale,
+               dx16_colsum, n_tokens);
+    };
+    if (!dy_is_16bit) {
+      if (bf) launch_ring(layernorm_bwd_ring_kernel<false, Bf16>, ln_ring_slot_bytes<false>());
+      else launch_ring(layernorm_bwd_ring_kernel<false, Fp16>, ln_ring_slot_bytes<false>());
+    } else {
+      if (bf) launch_ring(layernorm_bwd_ring_kernel<true, Bf16>, ln_ring_slot_bytes<true>());
+      else launch_ring(layernorm_bwd_ring_kernel<true, Fp16>, ln_ring_slot_bytes<true>());
+    }
+    return check_launch("layernorm_bwd_ring_kernel");
+  }
   if (C == 512) {
     if (!dy_is_16bit) { if (bf) launch(layernorm_bwd_kernel<512, false, Bf16>); else launch(layernorm_bwd_kernel<512, false, Fp16>); }
     else if (bf) launch(layernorm_bwd_kernel<512, true, Bf16>);
@@ -995,7 +1175,7 @@ int mp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
     bc1 = 1.0f - (float)pow((double)beta1, (double)step);
     bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   }
-  launch_k(adam_kernel, stream_grid(n, 1024), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+  launch_k(adam_kernel, stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                                        bc1, bc2_sqrt, grad_scale, step_dev, lr_dev);
   MP_CHECK(check_launch("adam_kernel"));
   if (step_dev) {
