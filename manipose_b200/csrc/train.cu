@@ -928,6 +928,9 @@ int mp_layernorm_bwd(const float* x, const float* gamma, float eps, const void* 
   };
   const bool bf = dtype == MP_DTYPE_BF16;
   // C = 512: rows staged through per-warp shared-memory rings by bulk copies (MANIPOSE_LNBWD_RING=0: the register-prefetch kernel, A/B)
+  // C = 512: rows staged through per-warp shared-memory rings by bulk copies (MANIPOSE_LNBWD_RING=0: the register-prefetch kernel, A/B).
+  // (Two warps per row - half the instruction stream and registers per warp, 20 warps per SM, the row sums combined through shared memory
+  // and a named barrier per pair - was slower: training step 7.32 against 7.20 ms.)
   static const bool ring = !(getenv("MANIPOSE_LNBWD_RING") && atoi(getenv("MANIPOSE_LNBWD_RING")) == 0);
   if (C == 512 && ring) {
     auto launch_ring = [&](auto kernel, int slot_bytes) {
