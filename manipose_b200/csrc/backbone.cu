@@ -173,38 +173,114 @@ layernorm128_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, u
 
 // -------------------------------------------------------------------------------------------------- joint embedding
 // x[tok, c] = W[c,0] in0 + W[c,1] in1 + b[c] + spos[tok % J, c]; h = LN(x)          (C = 512)
+// A pure store stream (3 KB written per token, 8 bytes read).  TWO tokens per warp and pass, every parameter (W columns, bias, LayerNorm
+// affine, the J position-embedding rows) in shared memory: 80 registers instead of 127 (parameters in registers: 16 resident warps per SM,
+// one token in flight each, 470 us per 528,768 tokens = 3.4 TB/s where a fill reaches 7.5), the next pair's inputs requested a pass ahead,
+// the two rows' statistics as independent shuffle chains.  Lane l owns channels [128 c + 4 l, + 4), c = 0..3: conflict-free 16-byte
+// shared-memory reads, 512 contiguous bytes per store instruction.
 template <typename D>
-__global__ void __launch_bounds__(kTokWarps * 32)
+__global__ void __launch_bounds__(kTokWarps * 32, 3)
 embed_joints_kernel(const float* __restrict__ in2d, const float* __restrict__ W, const float* __restrict__ bias,
                     const float* __restrict__ spos, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps,
                     float* __restrict__ x_out, uint16_t* __restrict__ h_out, int64_t n_tokens, int n_joints) {
   pdl_launch_dependents();
   pdl_wait();
-  using R = Row<512>;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
-  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
-  float w0[R::kPer], w1[R::kPer], bb[R::kPer], lg[R::kPer], lb[R::kPer];
-#pragma unroll
-  for (int i = 0; i < R::kPer; ++i) {
-    const int c = R::chan(lane, i);
-    w0[i] = __ldg(W + c * 2 + 0);
-    w1[i] = __ldg(W + c * 2 + 1);
+  constexpr int C = 512;
+  extern __shared__ __align__(16) float prm[];   // w0 | w1 | bias | gamma | beta | spos[n_joints]   ([C] each)
+  float* sw0 = prm;
+  float* sw1 = prm + C;
+  float* sb = prm + 2 * C;
+  float* sg = prm + 3 * C;
+  float* sbt = prm + 4 * C;
+  float* spe = prm + 5 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sw0[c] = W[c * 2 + 0];
+    sw1[c] = W[c * 2 + 1];
+    sb[c] = bias[c];
+    sg[c] = ln_g[c];
+    sbt[c] = ln_b[c];
   }
-  R::load_f32(bias, lane, bb);
-  R::load_f32(ln_g, lane, lg);
-  R::load_f32(ln_b, lane, lb);
-  for (int64_t tok = warp_global; tok < n_tokens; tok += stride) {
-    const float2 p = __ldg(reinterpret_cast<const float2*>(in2d) + tok);
-    float pe[R::kPer], v[R::kPer];
-    R::load_f32(spos + (tok % n_joints) * 512, lane, pe);
+  for (int i = threadIdx.x; i < n_joints * C; i += blockDim.x) spe[i] = spos[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t n_pairs = (n_tokens + 1) / 2;
+  const int64_t pair0 = (int64_t)blockIdx.x * kTokWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kTokWarps;
+  const int jstep = (int)((2 * stride) % n_joints);
+  int j0 = (int)((2 * pair0) % n_joints);
+  const float2* in = reinterpret_cast<const float2*>(in2d);
+  float2 pa = make_float2(0.f, 0.f), pb = pa;
+  if (pair0 < n_pairs) {
+    pa = __ldg(in + 2 * pair0);
+    if (2 * pair0 + 1 < n_tokens) pb = __ldg(in + 2 * pair0 + 1);
+  }
+  for (int64_t pr = pair0; pr < n_pairs; pr += stride) {
+    const int64_t tok = 2 * pr;
+    const bool two = tok + 1 < n_tokens;
+    const float2 p0 = pa, p1 = pb;
+    if (pr + stride < n_pairs) {              // the next pass's inputs
+      pa = __ldg(in + 2 * (pr + stride));
+      if (2 * (pr + stride) + 1 < n_tokens) pb = __ldg(in + 2 * (pr + stride) + 1);
+    }
+    const int j1 = j0 + 1 == n_joints ? 0 : j0 + 1;
+    float v0[16], v1[16];
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) v[i] = fmaf(w1[i], p.y, fmaf(w0[i], p.x, bb[i])) + pe[i];
-    R::store_x(x_out + tok * 512, lane, v);
-    float mean, rstd;
-    R::stats(v, ln_eps, mean, rstd);
-    R::normalize(v, mean, rstd, lg, lb);
-    R::template store_h<D>(h_out + tok * 512, lane, v);
+    for (int c = 0; c < 4; ++c) {
+      const int off = c * 128 + lane * 4;
+      const float4 w0 = *reinterpret_cast<const float4*>(sw0 + off), w1 = *reinterpret_cast<const float4*>(sw1 + off);
+      const float4 bb = *reinterpret_cast<const float4*>(sb + off);
+      const float4 e0 = *reinterpret_cast<const float4*>(spe + j0 * C + off), e1 = *reinterpret_cast<const float4*>(spe + j1 * C + off);
+      v0[4 * c + 0] = fmaf(w1.x, p0.y, fmaf(w0.x, p0.x, bb.x)) + e0.x;
+      v0[4 * c + 1] = fmaf(w1.y, p0.y, fmaf(w0.y, p0.x, bb.y)) + e0.y;
+      v0[4 * c + 2] = fmaf(w1.z, p0.y, fmaf(w0.z, p0.x, bb.z)) + e0.z;
+      v0[4 * c + 3] = fmaf(w1.w, p0.y, fmaf(w0.w, p0.x, bb.w)) + e0.w;
+      v1[4 * c + 0] = fmaf(w1.x, p1.y, fmaf(w0.x, p1.x, bb.x)) + e1.x;
+      v1[4 * c + 1] = fmaf(w1.y, p1.y, fmaf(w0.y, p1.x, bb.y)) + e1.y;
+      v1[4 * c + 2] = fmaf(w1.z, p1.y, fmaf(w0.z, p1.x, bb.z)) + e1.z;
+      v1[4 * c + 3] = fmaf(w1.w, p1.y, fmaf(w0.w, p1.x, bb.w)) + e1.w;
+      *reinterpret_cast<float4*>(x_out + tok * C + off) = make_float4(v0[4 * c + 0], v0[4 * c + 1], v0[4 * c + 2], v0[4 * c + 3]);
+      if (two) *reinterpret_cast<float4*>(x_out + (tok + 1) * C + off) = make_float4(v1[4 * c + 0], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+    }
+    // two-pass statistics of both rows, the shuffle chains interleaved
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s0 += v0[i];
+      s1 += v1[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    const float m0 = s0 * (1.0f / C), m1 = s1 * (1.0f / C);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d0 = v0[i] - m0, d1 = v1[i] - m1;
+      q0 = fmaf(d0, d0, q0);
+      q1 = fmaf(d1, d1, q1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    const float r0 = rsqrtf(q0 * (1.0f / C) + ln_eps), r1 = rsqrtf(q1 * (1.0f / C) + ln_eps);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int off = c * 128 + lane * 4;
+      const float4 gg = *reinterpret_cast<const float4*>(sg + off), bt = *reinterpret_cast<const float4*>(sbt + off);
+      uint2 u0, u1;
+      u0.x = D::pack2(fmaf((v0[4 * c + 0] - m0) * r0, gg.x, bt.x), fmaf((v0[4 * c + 1] - m0) * r0, gg.y, bt.y));
+      u0.y = D::pack2(fmaf((v0[4 * c + 2] - m0) * r0, gg.z, bt.z), fmaf((v0[4 * c + 3] - m0) * r0, gg.w, bt.w));
+      u1.x = D::pack2(fmaf((v1[4 * c + 0] - m1) * r1, gg.x, bt.x), fmaf((v1[4 * c + 1] - m1) * r1, gg.y, bt.y));
+      u1.y = D::pack2(fmaf((v1[4 * c + 2] - m1) * r1, gg.z, bt.z), fmaf((v1[4 * c + 3] - m1) * r1, gg.w, bt.w));
+      *reinterpret_cast<uint2*>(h_out + tok * C + off) = u0;
+      if (two) *reinterpret_cast<uint2*>(h_out + (tok + 1) * C + off) = u1;
+    }
+    j0 += jstep;
+    if (j0 >= n_joints) j0 -= n_joints;
   }
 }
 
@@ -640,9 +716,15 @@ int mp_embed_joints(const float* in2d, const float* W, const float* b, const flo
   MP_REQUIRE(aligned16(x_out) && aligned16(h_out) && (reinterpret_cast<uintptr_t>(in2d) & 7u) == 0, MP_EALIGN,
              "mp_embed_joints: x_out / h_out must be 16-byte aligned, in2d 8-byte aligned");
   if (n_tokens == 0) return MP_OK;
+  MP_REQUIRE(n_joints <= 64, MP_EUNSUPPORTED, "mp_embed_joints: %d joints (the position-embedding rows live in shared memory: at most 64)", n_joints);
+  const int smem = (5 + n_joints) * 512 * (int)sizeof(float);
+  int64_t ctas = ((n_tokens + 1) / 2 + kTokWarps - 1) / kTokWarps;
+  const int64_t cap = (int64_t)sm_count() * 3;   // three resident CTAs per SM (registers)
+  if (ctas > cap) ctas = cap;
   auto launch = [&](auto kernel) {
-    launch_k(kernel, token_grid(n_tokens), kTokWarps * 32, 0, (cudaStream_t)stream, in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
-                                                                              (uint16_t*)h_out, n_tokens, n_joints);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    launch_k(kernel, (int)ctas, kTokWarps * 32, smem, (cudaStream_t)stream, in2d, W, b, spos, ln_gamma, ln_beta, ln_eps, x_out,
+                                                                   (uint16_t*)h_out, n_tokens, n_joints);
   };
   if (dtype == MP_DTYPE_BF16) launch(embed_joints_kernel<Bf16>); else launch(embed_joints_kernel<Fp16>);
   return check_launch("embed_joints_kernel");

@@ -77,6 +77,20 @@ def main():
     y = F.layer_norm(F.layer_norm(xin.double(), (c,), pg.double(), pb.double(), 1e-6), (c,), hg.double(), hb_.double(), 1e-5)
     wb = (y @ hw.double() + hbias.double()).view(clips, t, s).mean(1)
     out["bones_head"] = {"us": us, "gbs": n * c * 4 / us / 1e3, "frac": n * c * 4 / us / 1e3 / hbm, "max_err": float((bone.double() - wb).abs().max())}
+    # ---- joint embedding of the rotations backbone (C = 512): Linear(2 -> 512) + spatial position embedding + norm1
+    del x, h, xin, xo
+    nj = clips * t * 17
+    c5 = 512
+    x2 = 0.3 * r(nj, 2)
+    w5, b5, sp5 = r(c5, 2), 0.1 * r(c5), 0.02 * r(17, c5)
+    g5, bt5 = 1.0 + 0.1 * r(c5), 0.1 * r(c5)
+    x5 = torch.empty(nj, c5, device=dev)
+    h5 = torch.empty(nj, c5, dtype=torch.bfloat16, device=dev)
+    us = timeit(lambda: ops.embed_joints(x2, w5, b5, sp5, g5, bt5, 1e-6, x5, h5, nj, 17, c5, L.MP_DTYPE_BF16))
+    want = (F.linear(x2.double(), w5.double(), b5.double()).view(-1, 17, c5) + sp5.double()).view(nj, c5)
+    err_x = float((x5[:100000].double() - want[:100000]).abs().max())
+    err_h = float((h5[:100000].double() - F.layer_norm(want[:100000], (c5,), g5.double(), bt5.double(), 1e-6)).abs().max())
+    out["embed_joints"] = {"us": us, "gbs": nj * c5 * 6 / us / 1e3, "frac": nj * c5 * 6 / us / 1e3 / hbm, "max_err_x": err_x, "max_err_h": err_h}
     print(json.dumps(out, indent=1))
 
 

@@ -387,6 +387,18 @@ def test_bone_backbone_kernels_ragged_sizes(dtype):
         y = F.layer_norm(F.layer_norm(want, (c,), pg, pb, 1e-6), (c,), hg, hb, 1e-5)
         wb = (y @ hw + hbias).view(n_clips, n_frames, n_seg).mean(1)
         torch.testing.assert_close(bone, wb, rtol=1e-4, atol=1e-5)
+    # joint embedding (C = 512, two tokens per warp pass): odd token counts, joints wrapping inside a pair
+    c5 = 512
+    for n_tok_total, nj in ((1, 17), (17 * 3, 17), (17 * 9 * 2 + 0, 17), (35, 5)):
+        x2 = 0.3 * r(n_tok_total, 2)
+        w5, b5, sp5, g5, bt5 = r(c5, 2), 0.1 * r(c5), 0.02 * r(nj, c5), 1.0 + 0.1 * r(c5), 0.1 * r(c5)
+        x5 = torch.full((n_tok_total + 2, c5), 7.0, device="cuda")
+        h5 = torch.full((n_tok_total + 2, c5), 7.0, dtype=td, device="cuda")
+        ops.embed_joints(x2, w5, b5, sp5, g5, bt5, 1e-6, x5, h5, n_tok_total, nj, c5, code)
+        want5 = F.linear(x2, w5, b5) + sp5[torch.arange(n_tok_total, device="cuda") % nj]
+        torch.testing.assert_close(x5[:n_tok_total], want5, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(h5[:n_tok_total].float(), F.layer_norm(want5, (c5,), g5, bt5, 1e-6), rtol=RTOL[dtype], atol=RTOL[dtype])
+        assert bool((x5[n_tok_total:] == 7.0).all()) and bool((h5[n_tok_total:].float() == 7.0).all())
     # LayerNorm on token counts 4 k + 1 .. 4 k + 3
     for n in (1, 6, 431):
         xin = r(n, c) * 2 + 0.5
