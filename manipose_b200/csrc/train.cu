@@ -174,15 +174,20 @@ layernorm_bwd_ring_kernel(const float* __restrict__ x, const float* __restrict__
     for (int s = 0; s < kLnRing - 1; ++s)
       if (warp_global + s * stride < n_tokens) request(warp_global + s * stride, s);
   }
-  float g[R::kPer], ag[R::kPer], ab[R::kPer], ac[R::kPer];
+  // The per-channel arithmetic of a row runs on the packed fp32 instructions (add / mul / fma .f32x2: two IEEE operations per issue slot, same
+  // results as the scalar forms): the kernel is bound by the length of a row's dependent instruction stream, ~14 packed instead of ~31 scalar
+  // instructions per channel pair.
+  constexpr int kPairs = R::kPer / 2;
+  float g[R::kPer];
 #pragma unroll
-  for (int i = 0; i < R::kPer; ++i) {
-    g[i] = 1.f;
-    ag[i] = 0.f;
-    ab[i] = 0.f;
-    ac[i] = 0.f;
-  }
+  for (int i = 0; i < R::kPer; ++i) g[i] = 1.f;
   if (gamma) R::load_f32(gamma, lane, g);
+  uint64_t G2[kPairs], AG[kPairs], AB[kPairs], AC[kPairs];
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) {
+    G2[k] = pack_f32x2(g[2 * k], g[2 * k + 1]);
+    AG[k] = AB[k] = AC[k] = pack_f32x2(0.f, 0.f);
+  }
   uint32_t n = 0;
   for (int64_t tok = warp_global; tok < n_tokens; tok += stride, ++n) {
     const int slot = (int)(n % kLnRing);
@@ -204,34 +209,66 @@ layernorm_bwd_ring_kernel(const float* __restrict__ x, const float* __restrict__
     }
     ptx::fence_proxy_async_smem();
     __syncwarp();                                   // the slot may be refilled by the next iteration's request
-    float mean, rstd;
-    R::stats(v, eps, mean, rstd);
-    float s1 = 0.f, s2 = 0.f;
+    uint64_t V[kPairs], Dp[kPairs];
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) {
-      const float xh = (v[i] - mean) * rstd;
-      ag[i] = fmaf(d[i], xh, ag[i]);
-      ab[i] += d[i];
-      const float gi = d[i] * g[i];
-      s1 += gi;
-      s2 = fmaf(gi, xh, s2);
-      v[i] = xh;
-      d[i] = gi;
+    for (int k = 0; k < kPairs; ++k) {
+      V[k] = pack_f32x2(v[2 * k], v[2 * k + 1]);
+      Dp[k] = pack_f32x2(d[2 * k], d[2 * k + 1]);
     }
-    s1 = warp_sum(s1) * (1.0f / C);
-    s2 = warp_sum(s2) * (1.0f / C);
+    // mean, then the biased variance around it (two passes, as nn.LayerNorm); V becomes x - mean
+    uint64_t S = V[0];
 #pragma unroll
-    for (int i = 0; i < R::kPer; ++i) d[i] = rstd * (d[i] - s1 - v[i] * s2) + r[i];
+    for (int k = 1; k < kPairs; ++k) S = add_f32x2(S, V[k]);
+    const float mean = warp_sum(sum_f32x2(S)) * (1.0f / C);
+    const uint64_t nm2 = pack_f32x2(-mean, -mean);
+    uint64_t Q = pack_f32x2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kPairs; ++k) {
+      V[k] = add_f32x2(V[k], nm2);
+      Q = fma_f32x2(V[k], V[k], Q);
+    }
+    const float rstd = rsqrtf(warp_sum(sum_f32x2(Q)) * (1.0f / C) + eps);
+    const uint64_t r2 = pack_f32x2(rstd, rstd);
+    uint64_t S1 = pack_f32x2(0.f, 0.f), S2 = S1;
+#pragma unroll
+    for (int k = 0; k < kPairs; ++k) {
+      const uint64_t xh = mul_f32x2(V[k], r2);
+      AG[k] = fma_f32x2(Dp[k], xh, AG[k]);
+      AB[k] = add_f32x2(AB[k], Dp[k]);
+      const uint64_t gi = mul_f32x2(Dp[k], G2[k]);
+      S1 = add_f32x2(S1, gi);
+      S2 = fma_f32x2(gi, xh, S2);
+      V[k] = xh;
+      Dp[k] = gi;
+    }
+    const float s1 = warp_sum(sum_f32x2(S1)) * (1.0f / C);
+    const float s2 = warp_sum(sum_f32x2(S2)) * (1.0f / C);
+    const uint64_t ns1 = pack_f32x2(-s1, -s1), ns2 = pack_f32x2(-s2, -s2);
+#pragma unroll
+    for (int k = 0; k < kPairs; ++k) {
+      const uint64_t t = fma_f32x2(V[k], ns2, add_f32x2(Dp[k], ns1));
+      Dp[k] = fma_f32x2(t, r2, pack_f32x2(r[2 * k], r[2 * k + 1]));
+      unpack_f32x2(Dp[k], d[2 * k], d[2 * k + 1]);
+    }
     R::store_x(dx + tok * C, lane, d);
     if (dx16) {
       const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
+      const uint64_t sc2 = pack_f32x2(sc, sc);
 #pragma unroll
-      for (int i = 0; i < R::kPer; ++i) {
-        d[i] *= sc;
-        ac[i] += d[i];
+      for (int k = 0; k < kPairs; ++k) {
+        Dp[k] = mul_f32x2(Dp[k], sc2);
+        AC[k] = add_f32x2(AC[k], Dp[k]);
+        unpack_f32x2(Dp[k], d[2 * k], d[2 * k + 1]);
       }
       R::template store_h<D>(dx16 + tok * C, lane, d);
     }
+  }
+  float ag[R::kPer], ab[R::kPer], ac[R::kPer];
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) {
+    unpack_f32x2(AG[k], ag[2 * k], ag[2 * k + 1]);
+    unpack_f32x2(AB[k], ab[2 * k], ab[2 * k + 1]);
+    unpack_f32x2(AC[k], ac[2 * k], ac[2 * k + 1]);
   }
   if (dgamma || dx16_colsum) {
     __syncthreads();                                // every warp has consumed all the rows it requested: the ring is free
