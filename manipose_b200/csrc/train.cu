@@ -193,6 +193,7 @@ layernorm_bwd_ring_kernel(const float* __restrict__ x, const float* __restrict__
     const int slot = (int)(n % kLnRing);
     // the row kLnRing - 1 iterations ahead goes into the slot the PREVIOUS iteration has read (all lanes are past their reads: __syncwarp below)
     if (lane == 0 && tok + (kLnRing - 1) * stride < n_tokens) request(tok + (kLnRing - 1) * stride, (int)((n + kLnRing - 1) % kLnRing));
+    const float sc = (dx16 && rowscale) ? __ldg(rowscale + tok) : 1.f;   // requested now, used after the row's reductions
     ptx::mbar_wait(&bars[slot], (n / kLnRing) & 1);
     const uint8_t* sl = ring + slot * kSlot;
     float v[R::kPer], d[R::kPer], r[R::kPer];
@@ -252,7 +253,6 @@ layernorm_bwd_ring_kernel(const float* __restrict__ x, const float* __restrict__
     }
     R::store_x(dx + tok * C, lane, d);
     if (dx16) {
-      const float sc = rowscale ? __ldg(rowscale + tok) : 1.f;
       const uint64_t sc2 = pack_f32x2(sc, sc);
 #pragma unroll
       for (int k = 0; k < kPairs; ++k) {
