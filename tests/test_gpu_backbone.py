@@ -409,6 +409,40 @@ def test_bone_backbone_kernels_ragged_sizes(dtype):
         assert bool((h[n:].float() == 7.0).all())
 
 
+def test_sm_limit_changes_the_grid_not_the_result():
+    """mp_set_sm_limit: persistent kernels size their grids from the limit; tiles are assigned round robin, so the results are the same bits."""
+    from manipose_b200 import ops, _lib as L
+    lib = L.load()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    m, c = 3 * 27 * 17, 512
+    h = torch.randn(m, c, generator=gen, device="cuda").bfloat16()
+    w = (torch.randn(3 * c, c, generator=gen, device="cuda") / math.sqrt(c)).bfloat16()
+    wp = (torch.randn(c, c, generator=gen, device="cuda") / math.sqrt(c)).bfloat16()
+    b, bp = torch.randn(3 * c, generator=gen, device="cuda"), torch.randn(c, generator=gen, device="cuda")
+    g, bt = torch.randn(c, generator=gen, device="cuda"), torch.randn(c, generator=gen, device="cuda")
+    x0 = torch.randn(m, c, generator=gen, device="cuda")
+
+    def run():
+        qkv = torch.empty(m, 3 * c, dtype=torch.bfloat16, device="cuda")
+        o = torch.empty(m, c, dtype=torch.bfloat16, device="cuda")
+        x, hh = x0.clone(), torch.empty(m, c, dtype=torch.bfloat16, device="cuda")
+        ops.linear(h, w, b, qkv, L.MP_EPI_BIAS)
+        ops.attention(qkv, o, 3, 27, 17, c, 8, L.MP_ATTN_TEMPORAL)
+        ops.linear_ln(o, wp, bp, x, x, hh, ln=(g, bt))
+        torch.cuda.synchronize()
+        return qkv, o, x, hh
+
+    want = run()
+    assert lib.mp_set_sm_limit(3) < 0                      # odd: rejected (CTA pairs)
+    assert lib.mp_set_sm_limit(8) == 0                     # returns the previous limit
+    try:
+        got = run()
+    finally:
+        assert lib.mp_set_sm_limit(0) == 8
+    for a, bb in zip(want, got):
+        assert torch.equal(a, bb)
+
+
 def _sd_to(sd, dev):
     return {k: v.to(dev) for k, v in sd.items()}
 
